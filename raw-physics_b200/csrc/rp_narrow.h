@@ -1,0 +1,556 @@
+// rp_narrow.h -- narrowphase for one collider pair: boolean GJK, EPA, contact-manifold clipping.
+//
+// Fixed-capacity scratch instead of the reference's growable arrays (SURVEY.md 7 "hard parts" 3); running out of
+// capacity, or reaching a state where the reference would abort on an assert, raises a status bit and yields
+// "no contact" instead of trapping (failure detection row).
+//
+// Reference: src/physics/gjk.cpp (gjk_collides :350, do_simplex_2/3/4 :36,:57,:122), src/physics/epa.cpp (epa :118,
+// get_face_normal_and_distance_to_origin :32, add_edge :79), src/physics/clipping.cpp (whole file),
+// src/physics/collider.cpp:523-558 (collider_get_contacts).
+#ifndef RP_NARROW_H
+#define RP_NARROW_H
+
+#include "rp_shape.h"
+
+namespace rp {
+
+// status bits (per world on the device, per call on the host)
+enum {
+	ST_GJK_SIMPLEX_OVERFLOW = 1 << 0,   // gjk.cpp:24-26 assert(0): add_to_simplex on a 4-point simplex (quirk q3)
+	ST_EPA_DEGENERATE = 1 << 1,         // epa.cpp:41 / :72 asserts
+	ST_EPA_NO_CONVERGENCE = 1 << 2,     // epa.cpp:233 "EPA did not converge"
+	ST_EPA_CAPACITY = 1 << 3,           // polytope scratch exhausted (reference arrays are unbounded)
+	ST_CLIP_CAPACITY = 1 << 4,          // polygon scratch exhausted
+	ST_EDGE_PARALLEL = 1 << 5,          // clipping.cpp:279 assert (skew-line system singular)
+	ST_CONTACT_CAPACITY = 1 << 6,       // per-world contact buffer exhausted
+	ST_PAIR_CAPACITY = 1 << 7,          // per-world broadphase pair buffer exhausted
+	ST_SOLVER_SINGULAR = 1 << 8,        // pbd_base_constraints.cpp:40,:154 assert(w1 + w2 != 0)
+	ST_NAN = 1 << 9
+};
+
+#define RP_EPA_MAX_VERTS 104   // 4 + 100 iterations (epa.cpp:149)
+#define RP_EPA_MAX_FACES 256
+#define RP_EPA_MAX_EDGES 192
+#define RP_CLIP_MAX_POINTS 160
+#define RP_GJK_MAX_ITERS 100
+#define RP_EPA_MAX_ITERS 100
+
+struct Simplex {
+	V3 a, b, c, d;
+	int num;
+};
+
+// triple_cross (gjk.cpp:32)
+RP_HD V3 cross3(V3 a, V3 b, V3 c) { return cross(cross(a, b), c); }
+
+// Region test shared by do_simplex_3 and the three single-plane cases of do_simplex_4 for the triangle (A, P, Q) with
+// normal n = AP x AQ. `aq_alt` is the vector the "AP region reached through the failed AQ test" branch feeds to
+// triple_cross: it is AP itself everywhere except gjk.cpp:213 (case 0x2), which passes AB (quirk q2).
+// Returns true when the origin projects inside the triangle (caller finishes that region); on the "A region" branches
+// only `a` is (re)written and num is left as it was (quirk q3).
+RP_HD bool gjk_triangle_edges(Simplex* s, V3* dir, V3 a, V3 P, V3 Q, V3 ap, V3 aq, V3 n, V3 ao, V3 ap_alt) {
+	if (dot(cross(n, aq), ao) >= 0.0) {
+		if (dot(aq, ao) >= 0.0) {
+			s->a = a; s->b = Q; s->num = 2;
+			*dir = cross3(aq, ao, aq);
+		} else if (dot(ap, ao) >= 0.0) {
+			s->a = a; s->b = P; s->num = 2;
+			*dir = cross3(ap_alt, ao, ap_alt);
+		} else {
+			s->a = a;
+			*dir = ao;
+		}
+		return false;
+	}
+	if (dot(cross(ap, n), ao) >= 0.0) {
+		if (dot(ap, ao) >= 0.0) {
+			s->a = a; s->b = P; s->num = 2;
+			*dir = cross3(ap, ao, ap);
+		} else {
+			s->a = a;
+			*dir = ao;
+		}
+		return false;
+	}
+	return true;
+}
+
+RP_HD void gjk_line(Simplex* s, V3* dir, V3 a, V3 P, V3 ap, V3 ao) {
+	if (dot(ap, ao) >= 0.0) {
+		s->a = a; s->b = P; s->num = 2;
+		*dir = cross3(ap, ao, ap);
+	} else {
+		s->a = a; s->num = 1;
+		*dir = ao;
+	}
+}
+
+// do_simplex (gjk.cpp:339-348). Returns true on intersection (tetrahedron encloses the origin).
+RP_HD bool gjk_do_simplex(Simplex* s, V3* dir) {
+	V3 a = s->a, b = s->b;
+	V3 ao = zero_minus(a);
+	V3 ab = sub(b, a);
+	if (s->num == 2) {  // gjk.cpp:36-55
+		gjk_line(s, dir, a, b, ab, ao);
+		return false;
+	}
+	V3 c = s->c;
+	V3 ac = sub(c, a);
+	V3 abc = cross(ab, ac);
+	if (s->num == 3) {  // gjk.cpp:57-120
+		if (gjk_triangle_edges(s, dir, a, b, c, ab, ac, abc, ao, ab)) {
+			if (dot(abc, ao) >= 0.0) {
+				s->a = a; s->b = b; s->c = c; s->num = 3;
+				*dir = abc;
+			} else {
+				s->a = a; s->b = c; s->c = b; s->num = 3;
+				*dir = zero_minus(abc);
+			}
+		}
+		return false;
+	}
+	// gjk.cpp:122-337
+	V3 d = s->d;
+	V3 ad = sub(d, a);
+	V3 acd = cross(ac, ad);
+	V3 adb = cross(ad, ab);
+	int planes = 0;
+	if (dot(abc, ao) >= 0.0) planes |= 1;
+	if (dot(acd, ao) >= 0.0) planes |= 2;
+	if (dot(adb, ao) >= 0.0) planes |= 4;
+	switch (planes) {
+		case 0: return true;
+		case 1:
+			if (gjk_triangle_edges(s, dir, a, b, c, ab, ac, abc, ao, ab)) {
+				s->a = a; s->b = b; s->c = c; s->num = 3;
+				*dir = abc;
+			}
+			break;
+		case 2:
+			if (gjk_triangle_edges(s, dir, a, c, d, ac, ad, acd, ao, ab)) {  // ap_alt = ab: quirk q2
+				s->a = a; s->b = c; s->c = d; s->num = 3;
+				*dir = acd;
+			}
+			break;
+		case 3: gjk_line(s, dir, a, c, ac, ao); break;
+		case 4:
+			if (gjk_triangle_edges(s, dir, a, d, b, ad, ab, adb, ao, ad)) {
+				s->a = a; s->b = d; s->c = b; s->num = 3;
+				*dir = adb;
+			}
+			break;
+		case 5: gjk_line(s, dir, a, b, ab, ao); break;
+		case 6: gjk_line(s, dir, a, d, ad, ao); break;
+		default:
+			s->a = a; s->num = 1;
+			*dir = ao;
+			break;
+	}
+	return false;
+}
+
+// gjk_collides (gjk.cpp:350-379). `iters` (optional) receives the number of support iterations, for statistics.
+RP_HD bool gjk(const Shape& A, const Shape& B, Simplex* out, int* status, int* iters) {
+	Simplex s;
+	s.a = support_minkowski(A, B, v3(0.0, 0.0, 1.0));
+	s.b = s.c = s.d = v3(0.0, 0.0, 0.0);
+	s.num = 1;
+	V3 dir = scale(-1.0, s.a);
+	for (int i = 0; i < RP_GJK_MAX_ITERS; ++i) {
+		V3 p = support_minkowski(A, B, dir);
+		if (dot(p, dir) < 0.0) {
+			if (iters) *iters = i + 1;
+			return false;
+		}
+		// add_to_simplex (gjk.cpp:7-30)
+		if (s.num == 1) {
+			s.b = s.a;
+		} else if (s.num == 2) {
+			s.c = s.b; s.b = s.a;
+		} else if (s.num == 3) {
+			s.d = s.c; s.c = s.b; s.b = s.a;
+		} else {
+			*status |= ST_GJK_SIMPLEX_OVERFLOW;  // the reference aborts here
+			if (iters) *iters = i + 1;
+			return false;
+		}
+		s.a = p;
+		++s.num;
+		if (gjk_do_simplex(&s, &dir)) {
+			*out = s;
+			if (iters) *iters = i + 1;
+			return true;
+		}
+	}
+	if (iters) *iters = RP_GJK_MAX_ITERS;
+	return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- EPA
+
+struct EpaScratch {
+	V3 verts[RP_EPA_MAX_VERTS];
+	V3 normals[RP_EPA_MAX_FACES];
+	double dists[RP_EPA_MAX_FACES];
+	uint8_t faces[RP_EPA_MAX_FACES][3];
+	uint8_t edges[RP_EPA_MAX_EDGES][2];
+	int nverts, nfaces, nedges;
+};
+
+// get_face_normal_and_distance_to_origin (epa.cpp:32-77)
+RP_HD bool epa_face_plane(const EpaScratch& e, int ia, int ib, int ic, V3* normal_out, double* dist_out) {
+	V3 a = e.verts[ia];
+	V3 n = normalize(cross(sub(e.verts[ib], a), sub(e.verts[ic], a)));
+	if (!(n.x != 0.0 || n.y != 0.0 || n.z != 0.0)) return false;  // epa.cpp:41
+	double dist = dot(n, a);
+	if (dist < -0.0) {
+		n = zero_minus(n);
+		dist = -dist;
+	} else if (dist >= -0.0 && dist <= 0.0) {
+		bool found = false;
+		for (int i = 0; i < e.nverts; ++i) {
+			double t = dot(n, e.verts[i]);
+			if (t < -0.0 || t > 0.0) {
+				n = t < -0.0 ? n : zero_minus(n);
+				found = true;
+				break;
+			}
+		}
+		if (!found) return false;  // epa.cpp:72
+	}
+	*normal_out = n;
+	*dist_out = dist;
+	return true;
+}
+
+// add_edge (epa.cpp:79-110): an edge seen twice cancels -- by index in either direction or by coordinate-equal
+// endpoints (quirk q8); removal is swap-with-last (light_array.h:146)
+RP_HD bool epa_toggle_edge(EpaScratch& e, int x, int y) {
+	for (int i = 0; i < e.nedges; ++i) {
+		int cx = e.edges[i][0], cy = e.edges[i][1];
+		bool hit = (x == cx && y == cy) || (x == cy && y == cx);
+		if (!hit) {
+			V3 c1 = e.verts[cx], c2 = e.verts[cy], e1 = e.verts[x], e2 = e.verts[y];
+			hit = (equal(c1, e1) && equal(c2, e2)) || (equal(c1, e2) && equal(c2, e1));
+		}
+		if (hit) {
+			--e.nedges;
+			e.edges[i][0] = e.edges[e.nedges][0];
+			e.edges[i][1] = e.edges[e.nedges][1];
+			return true;
+		}
+	}
+	if (e.nedges >= RP_EPA_MAX_EDGES) return false;
+	e.edges[e.nedges][0] = (uint8_t)x;
+	e.edges[e.nedges][1] = (uint8_t)y;
+	++e.nedges;
+	return true;
+}
+
+// epa (epa.cpp:118-238)
+RP_HD bool epa(const Shape& A, const Shape& B, const Simplex& s, EpaScratch& e, V3* normal_out, double* depth_out, int* status,
+	int* iters) {
+	e.verts[0] = s.a; e.verts[1] = s.b; e.verts[2] = s.c; e.verts[3] = s.d;
+	e.nverts = 4;
+	const uint8_t init_faces[4][3] = {{0, 1, 2}, {0, 2, 3}, {0, 3, 1}, {1, 2, 3}};
+	e.nfaces = 0;
+	e.nedges = 0;
+	V3 min_normal = v3(0.0, 0.0, 0.0);
+	double min_dist = 1.7976931348623157e308;
+	for (int i = 0; i < 4; ++i) {
+		V3 n; double d;
+		if (!epa_face_plane(e, init_faces[i][0], init_faces[i][1], init_faces[i][2], &n, &d)) {
+			*status |= ST_EPA_DEGENERATE;
+			return false;
+		}
+		e.faces[i][0] = init_faces[i][0]; e.faces[i][1] = init_faces[i][1]; e.faces[i][2] = init_faces[i][2];
+		e.normals[i] = n;
+		e.dists[i] = d;
+		e.nfaces = i + 1;
+		if (d < min_dist) {
+			min_dist = d;
+			min_normal = n;
+		}
+	}
+	for (int it = 0; it < RP_EPA_MAX_ITERS; ++it) {
+		V3 sp = support_minkowski(A, B, min_normal);
+		double d = dot(min_normal, sp);
+		if (fabs(d - min_dist) < 0.0001) {
+			*normal_out = min_normal;
+			*depth_out = min_dist;
+			if (iters) *iters = it + 1;
+			return true;
+		}
+		int new_index = e.nverts;
+		e.verts[e.nverts++] = sp;  // capacity: 4 + RP_EPA_MAX_ITERS
+
+		// faces that see the new point are removed (swap-with-last while scanning, quirk q7), their edges toggled
+		int i = 0;
+		while (i < e.nfaces) {
+			int fx = e.faces[i][0], fy = e.faces[i][1], fz = e.faces[i][2];
+			V3 centroid = scale(1.0 / 3.0, add(add(e.verts[fy], e.verts[fz]), e.verts[fx]));  // triangle_centroid (epa.cpp:112)
+			if (dot(e.normals[i], sub(sp, centroid)) > 0.0) {
+				if (!epa_toggle_edge(e, fx, fy) || !epa_toggle_edge(e, fy, fz) || !epa_toggle_edge(e, fz, fx)) {
+					*status |= ST_EPA_CAPACITY;
+					return false;
+				}
+				int last = --e.nfaces;
+				e.faces[i][0] = e.faces[last][0]; e.faces[i][1] = e.faces[last][1]; e.faces[i][2] = e.faces[last][2];
+				e.dists[i] = e.dists[last];
+				e.normals[i] = e.normals[last];
+			} else {
+				++i;
+			}
+		}
+		for (int k = 0; k < e.nedges; ++k) {
+			if (e.nfaces >= RP_EPA_MAX_FACES) {
+				*status |= ST_EPA_CAPACITY;
+				return false;
+			}
+			V3 n; double dd;
+			if (!epa_face_plane(e, e.edges[k][0], e.edges[k][1], new_index, &n, &dd)) {
+				*status |= ST_EPA_DEGENERATE;
+				return false;
+			}
+			int f = e.nfaces++;
+			e.faces[f][0] = e.edges[k][0]; e.faces[f][1] = e.edges[k][1]; e.faces[f][2] = (uint8_t)new_index;
+			e.normals[f] = n;
+			e.dists[f] = dd;
+		}
+		min_dist = 1.7976931348623157e308;
+		for (int k = 0; k < e.nfaces; ++k) {
+			if (e.dists[k] < min_dist) {
+				min_dist = e.dists[k];
+				min_normal = e.normals[k];
+			}
+		}
+		e.nedges = 0;
+	}
+	*status |= ST_EPA_NO_CONVERGENCE;
+	if (iters) *iters = RP_EPA_MAX_ITERS;
+	return false;
+}
+
+// ----------------------------------------------------------------------------------------------------------- clipping
+
+struct ClipPlane {
+	V3 normal, point;
+};
+
+#define RP_MAXF(a, b) (((a) > (b)) ? (a) : (b))
+#define RP_MINF(a, b) (((a) < (b)) ? (a) : (b))
+
+// is_point_in_plane (clipping.cpp:12-19): the plane offset is rounded to float (quirk q6)
+RP_HD bool clip_inside(const ClipPlane& pl, V3 p) {
+	float offset = (float)(-dot(pl.normal, pl.point));
+	return !(dot(p, pl.normal) + (double)offset < 0.0);
+}
+
+// plane_edge_intersection (clipping.cpp:21-46): ab_p, the plane offset and the edge factor pass through float
+RP_HD bool clip_edge(const ClipPlane& pl, V3 start, V3 end, V3* out) {
+	V3 ab = sub(end, start);
+	float ab_p = (float)dot(pl.normal, ab);
+	if (fabs((double)ab_p) > 0.000001) {
+		float offset = (float)(-dot(pl.normal, pl.point));
+		V3 p_co = scale((double)(-offset), pl.normal);
+		float fac = (float)(-dot(pl.normal, sub(start, p_co)) / (double)ab_p);
+		fac = (float)RP_MINF(RP_MAXF((double)fac, 0.0), 1.0);
+		*out = add(start, scale((double)fac, ab));
+		return true;
+	}
+	return false;
+}
+
+struct ClipScratch {
+	V3 buf[2][RP_CLIP_MAX_POINTS];
+};
+
+// One Sutherland-Hodgman pass of `in` against one plane (body of the loop at clipping.cpp:63-108).
+RP_HD int clip_pass(const ClipPlane& pl, const V3* in, int n_in, V3* out, bool remove_only, int* status) {
+	int n_out = 0;
+	V3 start = in[n_in - 1];
+	for (int j = 0; j < n_in; ++j) {
+		V3 end = in[j];
+		bool s_in = clip_inside(pl, start);
+		bool e_in = clip_inside(pl, end);
+		V3 tmp;
+		if (n_out + 2 > RP_CLIP_MAX_POINTS) {
+			*status |= ST_CLIP_CAPACITY;
+			return n_out;
+		}
+		if (remove_only) {
+			if (e_in) out[n_out++] = end;
+		} else if (s_in && e_in) {
+			out[n_out++] = end;
+		} else if (s_in && !e_in) {
+			if (clip_edge(pl, start, end, &tmp)) out[n_out++] = tmp;
+		} else if (!s_in && e_in) {
+			if (clip_edge(pl, start, end, &tmp)) out[n_out++] = tmp;
+			out[n_out++] = end;
+		}
+		start = end;
+	}
+	return n_out;
+}
+
+// get_face_with_most_fitting_normal (clipping.cpp:136-152)
+RP_HD int clip_best_face(const Shape& s, int support_idx, V3 normal) {
+	double best = -1.7976931348623157e308;
+	int sel = 0;
+	for (int k = s.v2f_ptr[support_idx]; k < s.v2f_ptr[support_idx + 1]; ++k) {
+		int f = s.v2f_idx[k];
+		double proj = dot(s.tn[f], normal);
+		if (proj > best) {
+			best = proj;
+			sel = f;
+		}
+	}
+	return sel;
+}
+
+// collision_distance_between_skew_lines (clipping.cpp:210-247), quirk q5: the names are swapped but self-consistent
+RP_HD bool clip_skew_lines(V3 p1, V3 d1, V3 p2, V3 d2, V3* l1, V3* l2) {
+	double n1 = d1.x * d2.x + d1.y * d2.y + d1.z * d2.z;
+	double n2 = d2.x * d2.x + d2.y * d2.y + d2.z * d2.z;
+	double m1 = -d1.x * d1.x - d1.y * d1.y - d1.z * d1.z;
+	double m2 = -d2.x * d1.x - d2.y * d1.y - d2.z * d1.z;
+	double r1 = -d1.x * p2.x + d1.x * p1.x - d1.y * p2.y + d1.y * p1.y - d1.z * p2.z + d1.z * p1.z;
+	double r2 = -d2.x * p2.x + d2.x * p1.x - d2.y * p2.y + d2.y * p1.y - d2.z * p2.z + d2.z * p1.z;
+	if ((n1 * m2) - (n2 * m1) == 0) return false;
+	double n = ((r1 * m2) - (r2 * m1)) / ((n1 * m2) - (n2 * m1));
+	double m = ((n1 * r2) - (n2 * r1)) / ((n1 * m2) - (n2 * m1));
+	*l1 = add(p1, scale(m, d1));
+	*l2 = add(p2, scale(n, d2));
+	return true;
+}
+
+// convex_convex_contact_manifold (clipping.cpp:249-341). Sink: void operator()(V3 p1, V3 p2).
+template <class Sink>
+RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipScratch& cs, int* status, Sink& sink) {
+	V3 inv_normal = zero_minus(normal);
+	int sup1 = support_index(h1, normal);
+	int sup2 = support_index(h2, inv_normal);
+	int face1 = clip_best_face(h1, sup1, normal);
+	int face2 = clip_best_face(h2, sup2, inv_normal);
+
+	// get_edge_with_most_fitting_normal (clipping.cpp:154-201)
+	V3 s1 = h1.tv[sup1], s2 = h2.tv[sup2];
+	double best = -1.7976931348623157e308;
+	int e1n = 0, e2n = 0;
+	V3 edge_normal = v3(0.0, 0.0, 0.0);
+	for (int i = h1.v2n_ptr[sup1]; i < h1.v2n_ptr[sup1 + 1]; ++i) {
+		V3 edge1 = sub(s1, h1.tv[h1.v2n_idx[i]]);
+		for (int j = h2.v2n_ptr[sup2]; j < h2.v2n_ptr[sup2 + 1]; ++j) {
+			V3 edge2 = sub(s2, h2.tv[h2.v2n_idx[j]]);
+			V3 cn = normalize(cross(edge1, edge2));
+			V3 cni = zero_minus(cn);
+			double t = dot(cn, normal);
+			if (t > best) {
+				best = t; e1n = h1.v2n_idx[i]; e2n = h2.v2n_idx[j]; edge_normal = cn;
+			}
+			t = dot(cni, normal);
+			if (t > best) {
+				best = t; e1n = h1.v2n_idx[i]; e2n = h2.v2n_idx[j]; edge_normal = cni;
+			}
+		}
+	}
+
+	V3 f1n = h1.tn[face1], f2n = h2.tn[face2];
+	double dot1 = dot(f1n, normal);
+	double dot2 = dot(f2n, inv_normal);
+	double dote = dot(edge_normal, normal);
+	const double EPS = 0.0001;
+	if (dote > dot1 + EPS && dote > dot2 + EPS) {
+		V3 p1 = h1.tv[sup1];
+		V3 d1 = sub(h1.tv[e1n], p1);
+		V3 p2 = h2.tv[sup2];
+		V3 d2 = sub(h2.tv[e2n], p2);
+		V3 l1, l2;
+		if (!clip_skew_lines(p1, d1, p2, d2, &l1, &l2)) {
+			*status |= ST_EDGE_PARALLEL;  // the reference aborts (clipping.cpp:279)
+			return;
+		}
+		sink(l1, l2);
+		return;
+	}
+
+	bool ref1 = dot1 > dot2;
+	const Shape& R = ref1 ? h1 : h2;   // reference hull
+	const Shape& I = ref1 ? h2 : h1;   // incident hull
+	int rface = ref1 ? face1 : face2;
+	int iface = ref1 ? face2 : face1;
+
+	// incident polygon (get_vertices_of_faces, clipping.cpp:241-247)
+	int cur = 0;
+	int n = 0;
+	for (int k = I.face_ptr[iface]; k < I.face_ptr[iface + 1]; ++k) {
+		if (n >= RP_CLIP_MAX_POINTS) {
+			*status |= ST_CLIP_CAPACITY;
+			return;
+		}
+		cs.buf[0][n++] = I.tv[I.face_idx[k]];
+	}
+	// boundary planes of the reference face (build_boundary_planes, clipping.cpp:121-134), clipped one at a time
+	// (sutherland_hodgman, clipping.cpp:52-113)
+	for (int k = R.f2n_ptr[rface]; k < R.f2n_ptr[rface + 1]; ++k) {
+		if (n == 0) break;
+		int nf = R.f2n_idx[k];
+		ClipPlane pl;
+		pl.point = R.tv[R.face_idx[R.face_ptr[nf]]];
+		pl.normal = zero_minus(R.tn[nf]);
+		n = clip_pass(pl, cs.buf[cur], n, cs.buf[cur ^ 1], false, status);
+		cur ^= 1;
+	}
+	ClipPlane rp;
+	rp.normal = zero_minus(ref1 ? f1n : f2n);
+	rp.point = R.tv[R.face_idx[R.face_ptr[rface]]];
+	if (n != 0) {
+		n = clip_pass(rp, cs.buf[cur], n, cs.buf[cur ^ 1], true, status);
+		cur ^= 1;
+	}
+	for (int k = 0; k < n; ++k) {
+		V3 p = cs.buf[cur][k];
+		// get_closest_point_polygon (clipping.cpp:115-119)
+		double dd = dot(scale(-1.0, rp.normal), rp.point);
+		V3 closest = sub(p, scale(dot(rp.normal, p) + dd, rp.normal));
+		V3 diff = sub(p, closest);
+		if (ref1) {
+			double pen = dot(diff, normal);
+			if (pen < 0.0) sink(sub(p, scale(pen, normal)), p);
+		} else {
+			double pen = -dot(diff, normal);
+			if (pen < 0.0) sink(p, add(p, scale(pen, normal)));
+		}
+	}
+}
+
+// collider_get_contacts (collider.cpp:523-558) + clipping_get_contact_manifold (clipping.cpp:343-371) for one collider
+// pair whose GJK verdict is already known to be "colliding" (hull involved) -- see narrow_pair below for the front half.
+template <class Sink>
+RP_HD void manifold(const Shape& A, const Shape& B, V3 normal, double depth, ClipScratch& cs, int* status, Sink& sink) {
+	if (A.type == SHAPE_SPHERE) {
+		V3 p = support(A, normal);
+		sink(p, sub(p, scale(depth, normal)));
+	} else if (B.type == SHAPE_SPHERE) {
+		V3 p = support(B, zero_minus(normal));
+		sink(add(p, scale(depth, normal)), p);
+	} else {
+		manifold_hull_hull(A, B, normal, cs, status, sink);
+	}
+}
+
+// sphere-sphere analytic test (collider.cpp:530-542): squared distance and radius sum are float (quirk q6)
+RP_HD bool sphere_sphere(const Shape& A, const Shape& B, V3* normal, double* depth) {
+	V3 dv = sub(A.center, B.center);
+	float dist2 = (float)dot(dv, dv);
+	float min_dist = A.radius + B.radius;
+	if (dist2 < (min_dist * min_dist)) {
+		*normal = normalize(sub(B.center, A.center));
+		*depth = (double)(min_dist - sqrtf(dist2));
+		return true;
+	}
+	return false;
+}
+
+}  // namespace rp
+#endif

@@ -1,0 +1,142 @@
+// rp_shape.h -- collider instances: CSR hull topology shared by every world, per-pose transform, support mapping.
+//
+// Reference: src/physics/collider.h:6-44 (types), collider.cpp:409-445 (collider_update), util.cpp:60-74
+// (util_get_model_matrix_no_scale), support.cpp:5-39 (support mapping).
+#ifndef RP_SHAPE_H
+#define RP_SHAPE_H
+
+#include "rp_math.h"
+
+namespace rp {
+
+enum { SHAPE_SPHERE = 0, SHAPE_HULL = 1 };  // Collider_Type (collider.h:31-34)
+
+// One convex hull's topology in the reference's own index order (collider_convex_hull_create, collider.cpp:194-364):
+// CSR arrays; v2f keeps the reference's duplicate entries, v2n includes triangulation diagonals, f2n = faces sharing
+// any vertex. Offsets index the pooled arrays of HullPool.
+struct HullTopo {
+	int nv, nf;
+	int vert0;                // first local vertex in HullPool::verts
+	int face0;                // first face in HullPool::normals / face_ptr
+	int fptr0;                // first entry of this hull in HullPool::face_ptr (nf + 1 entries, rebased to the pooled face_idx)
+	int v2f0, v2n0, f2n0;     // first entries of this hull in the other *_ptr arrays (count + 1 entries each, rebased likewise)
+};
+
+struct HullPool {
+	const HullTopo* hulls;
+	const V3* verts;          // local vertices
+	const V3* normals;        // local face normals
+	const int* face_ptr; const int* face_idx;
+	const int* v2f_ptr; const int* v2f_idx;
+	const int* v2n_ptr; const int* v2n_idx;
+	const int* f2n_ptr; const int* f2n_idx;
+};
+
+// A collider of the scene template (shared by all worlds): which hull / sphere radius, and where its transformed
+// vertices and normals live inside one world's transformed-geometry block.
+struct ColliderDesc {
+	int type;
+	int hull;                 // index into HullPool::hulls (SHAPE_HULL)
+	float radius;             // r32, as in Collider_Sphere (collider.h:26-29)
+	int tv0;                  // first transformed vertex (and, for a sphere, the slot holding its centre)
+	int tn0;                  // first transformed normal
+};
+
+// A collider at a pose, as the narrowphase sees it.
+struct Shape {
+	int type;
+	float radius;
+	V3 center;                // sphere centre (collider.cpp:433)
+	const V3* tv;             // transformed vertices
+	const V3* tn;             // transformed (re-normalised) face normals
+	int nv, nf;
+	const int* face_ptr; const int* face_idx;
+	const int* v2f_ptr; const int* v2f_idx;
+	const int* v2n_ptr; const int* v2n_idx;
+	const int* f2n_ptr; const int* f2n_idx;
+};
+
+RP_HD Shape make_shape(const HullPool& pool, const ColliderDesc& c, const V3* world_tv, const V3* world_tn) {
+	Shape s;
+	s.type = c.type;
+	s.radius = c.radius;
+	s.tv = world_tv + c.tv0;
+	s.tn = world_tn + c.tn0;
+	if (c.type == SHAPE_SPHERE) {
+		s.center = s.tv[0];
+		s.nv = 0; s.nf = 0;
+		s.face_ptr = s.face_idx = s.v2f_ptr = s.v2f_idx = s.v2n_ptr = s.v2n_idx = s.f2n_ptr = s.f2n_idx = 0;
+	} else {
+		const HullTopo h = pool.hulls[c.hull];
+		s.center = v3(0.0, 0.0, 0.0);
+		s.nv = h.nv; s.nf = h.nf;
+		s.face_ptr = pool.face_ptr + h.fptr0; s.face_idx = pool.face_idx;
+		s.v2f_ptr = pool.v2f_ptr + h.v2f0; s.v2f_idx = pool.v2f_idx;
+		s.v2n_ptr = pool.v2n_ptr + h.v2n0; s.v2n_idx = pool.v2n_idx;
+		s.f2n_ptr = pool.f2n_ptr + h.f2n0; s.f2n_idx = pool.f2n_idx;
+	}
+	return s;
+}
+
+// Rows 0..2 of the model matrix T * R exactly as gm_mat4_multiply(translation, rotation) forms them
+// (util.cpp:60-74 with quaternion_get_matrix, quaternion.cpp:107): every entry keeps its four-term sum, including the
+// products with the matrices' structural zeros, so signed zeros come out as in the reference.
+struct Pose34 {
+	double m[3][4];
+};
+
+RP_HD Pose34 model_matrix(Q4 q, V3 t) {
+	M3 R = to_mat3(q);
+	double T[3][4] = {{1.0, 0.0, 0.0, t.x}, {0.0, 1.0, 0.0, t.y}, {0.0, 0.0, 1.0, t.z}};
+	Pose34 M;
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+#pragma unroll
+		for (int j = 0; j < 3; ++j) M.m[i][j] = T[i][0] * R.m[0][j] + T[i][1] * R.m[1][j] + T[i][2] * R.m[2][j] + T[i][3] * 0.0;
+		M.m[i][3] = T[i][0] * 0.0 + T[i][1] * 0.0 + T[i][2] * 0.0 + T[i][3] * 1.0;
+	}
+	return M;
+}
+
+// collider_update, vertex half (collider.cpp:414-422): gm_mat4_multiply_vec4(M, (v,1)); the following scale by
+// 1/w is the identity because row 3 of M is (+0,+0,+0,1) and so w == 1 exactly.
+RP_HD V3 transform_point(const Pose34& M, V3 v) {
+	return v3(v.x * M.m[0][0] + v.y * M.m[0][1] + v.z * M.m[0][2] + 1.0 * M.m[0][3],
+	          v.x * M.m[1][0] + v.y * M.m[1][1] + v.z * M.m[1][2] + 1.0 * M.m[1][3],
+	          v.x * M.m[2][0] + v.y * M.m[2][1] + v.z * M.m[2][2] + 1.0 * M.m[2][3]);
+}
+// collider_update, normal half (collider.cpp:425-429): rotate then RE-NORMALISE (not a bitwise no-op)
+RP_HD V3 transform_normal(const Pose34& M, V3 n) {
+	V3 r = v3(M.m[0][0] * n.x + M.m[0][1] * n.y + M.m[0][2] * n.z,
+	          M.m[1][0] * n.x + M.m[1][1] * n.y + M.m[1][2] * n.z,
+	          M.m[2][0] * n.x + M.m[2][1] * n.y + M.m[2][2] * n.z);
+	return normalize(r);
+}
+
+// support_point_get_index (support.cpp:5-17): first maximum wins (strict >), starting from -DBL_MAX
+RP_HD int support_index(const Shape& s, V3 d) {
+	int best = 0;
+	double best_dot = -1.7976931348623157e308;
+	for (int i = 0; i < s.nv; ++i) {
+		double t = dot(s.tv[i], d);
+		if (t > best_dot) {
+			best = i;
+			best_dot = t;
+		}
+	}
+	return best;
+}
+// support_point (support.cpp:19-32)
+RP_HD V3 support(const Shape& s, V3 d) {
+	if (s.type == SHAPE_HULL) return s.tv[support_index(s, d)];
+	return add(s.center, scale((double)s.radius, normalize(d)));
+}
+// support_point_of_minkowski_difference (support.cpp:34-39)
+RP_HD V3 support_minkowski(const Shape& a, const Shape& b, V3 d) {
+	V3 s1 = support(a, d);
+	V3 s2 = support(b, scale(-1.0, d));
+	return sub(s1, s2);
+}
+
+}  // namespace rp
+#endif

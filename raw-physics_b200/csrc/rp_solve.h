@@ -1,0 +1,349 @@
+// rp_solve.h -- per-body integration, XPBD positional / angular primitives, contact, friction and joint solves,
+// velocity derivation and the velocity (dynamic friction + restitution) pass. All routines work on register-resident
+// Body records; the callers (CUDA kernels, or the sequential CPU checker) decide where bodies live and in which order
+// constraints run.
+//
+// Reference: src/physics/pbd.cpp (integrate :537-577, solves :81-406, contact->constraint :408-424, velocity derive
+// :623-643, velocity solve :646-711), src/physics/pbd_base_constraints.cpp (:6-227), src/physics/physics_util.cpp.
+#ifndef RP_SOLVE_H
+#define RP_SOLVE_H
+
+#include "rp_narrow.h"
+
+namespace rp {
+
+#define RP_PI_F 3.14159265358979  // include/gm.h:8
+
+struct Body {
+	V3 x; Q4 q;          // world_position, world_rotation
+	V3 v; V3 w;          // linear_velocity, angular_velocity
+	V3 px; Q4 pq;        // previous_world_position / rotation
+	V3 pv; V3 pw;        // previous_linear_velocity / angular_velocity
+	double inv_mass;
+	M3 inertia, inv_inertia;  // body-frame tensors (entity.h:32-33)
+	double mu_s, mu_d, rest;
+	int fixed, active;
+};
+
+// ------------------------------------------------------------------------------------------------------- integration
+// pbd.cpp:537-577 for one body. `force`/`torque` are the sums of calculate_external_force/torque (physics_util.cpp:5-23).
+RP_HD void integrate(Body& b, double h, V3 force, V3 torque) {
+	b.px = b.x;
+	b.pq = b.q;
+	if (b.fixed || !b.active) return;
+	b.v = add(b.v, scale(h * b.inv_mass, force));
+	b.x = add(b.x, scale(h, b.v));
+	M3 iinv = world_tensor(b.q, b.inv_inertia);
+	M3 iw = world_tensor(b.q, b.inertia);
+	b.w = add(b.w, scale(h, mul(iinv, sub(torque, cross(b.w, mul(iw, b.w))))));
+	Q4 aux = q4(b.w.x, b.w.y, b.w.z, 0.0);
+	Q4 dq = mul(aux, b.q);
+	b.q.x = b.q.x + h * 0.5 * dq.x;
+	b.q.y = b.q.y + h * 0.5 * dq.y;
+	b.q.z = b.q.z + h * 0.5 * dq.z;
+	b.q.w = b.q.w + h * 0.5 * dq.w;
+	b.q = normalize(b.q);
+}
+
+// pbd.cpp:623-643 for one body
+RP_HD void derive_velocity(Body& b, double h) {
+	if (b.fixed || !b.active) return;
+	b.pv = b.v;
+	b.pw = b.w;
+	b.v = scale(1.0 / h, sub(b.x, b.px));
+	Q4 dq = mul(b.q, conj(b.pq));
+	if (dq.w >= 0.0) b.w = scale(2.0 / h, v3(dq.x, dq.y, dq.z));
+	else b.w = scale(-2.0 / h, v3(dq.x, dq.y, dq.z));
+}
+
+// ---------------------------------------------------------------------------------------------- positional primitive
+struct PosPre {  // Position_Constraint_Preprocessed_Data (pbd_base_constraints.h:5-12)
+	V3 r1, r2;
+	M3 ii1, ii2;
+};
+
+// calculate_positional_constraint_preprocessed_data (pbd_base_constraints.cpp:6-15)
+RP_HD PosPre pos_pre(const Body& b1, const Body& b2, V3 r1_lc, V3 r2_lc) {
+	PosPre p;
+	p.r1 = rotate(b1.q, r1_lc);
+	p.r2 = rotate(b2.q, r2_lc);
+	p.ii1 = world_tensor(b1.q, b1.inv_inertia);
+	p.ii2 = world_tensor(b2.q, b2.inv_inertia);
+	return p;
+}
+
+// positional_constraint_get_delta_lambda (pbd_base_constraints.cpp:17-47)
+RP_HD double pos_delta_lambda(const PosPre& p, const Body& b1, const Body& b2, double h, double compliance, double lambda, V3 dx,
+	int* status) {
+	double c = length(dx);
+	if (c <= 1e-50) return 0.0;
+	V3 n = divide(dx, c);
+	double w1 = b1.inv_mass + dot(cross(p.r1, n), mul(p.ii1, cross(p.r1, n)));
+	double w2 = b2.inv_mass + dot(cross(p.r2, n), mul(p.ii2, cross(p.r2, n)));
+	if (!(w1 + w2 != 0.0)) *status |= ST_SOLVER_SINGULAR;  // the reference asserts
+	double til = compliance / (h * h);
+	return (-c - til * lambda) / (w1 + w2 + til);
+}
+
+// quaternion update shared by both apply routines (pbd_base_constraints.cpp:87-103, :189-207): q +/- 0.5 * ((aux,0) (x) q)
+RP_HD void apply_rotation(Body& b, V3 aux, double sign_half) {
+	Q4 d = mul(q4(aux.x, aux.y, aux.z, 0.0), b.q);
+	if (sign_half > 0.0) {
+		b.q.x = b.q.x + 0.5 * d.x; b.q.y = b.q.y + 0.5 * d.y; b.q.z = b.q.z + 0.5 * d.z; b.q.w = b.q.w + 0.5 * d.w;
+	} else {
+		b.q.x = b.q.x - 0.5 * d.x; b.q.y = b.q.y - 0.5 * d.y; b.q.z = b.q.z - 0.5 * d.z; b.q.w = b.q.w - 0.5 * d.w;
+	}
+	b.q = normalize(b.q);
+}
+
+// positional_constraint_apply (pbd_base_constraints.cpp:50-123)
+RP_HD void pos_apply(const PosPre& p, Body& b1, Body& b2, double dl, V3 dx) {
+	double c = length(dx);
+	if (c <= 1e-50) return;
+	V3 n = divide(dx, c);
+	V3 imp = scale(dl, n);
+	if (!b1.fixed) b1.x = add(b1.x, scale(b1.inv_mass, imp));
+	if (!b2.fixed) b2.x = add(b2.x, scale(-b2.inv_mass, imp));
+	V3 aux1 = mul(p.ii1, cross(p.r1, imp));
+	V3 aux2 = mul(p.ii2, cross(p.r2, imp));
+	if (!b1.fixed) apply_rotation(b1, aux1, 1.0);
+	if (!b2.fixed) apply_rotation(b2, aux2, -1.0);
+}
+
+// ------------------------------------------------------------------------------------------------- angular primitive
+struct AngPre {
+	M3 ii1, ii2;
+};
+// calculate_angular_constraint_preprocessed_data (pbd_base_constraints.cpp:125-131)
+RP_HD AngPre ang_pre(const Body& b1, const Body& b2) {
+	AngPre a;
+	a.ii1 = world_tensor(b1.q, b1.inv_inertia);
+	a.ii2 = world_tensor(b2.q, b2.inv_inertia);
+	return a;
+}
+// angular_constraint_get_delta_lambda (pbd_base_constraints.cpp:133-161)
+RP_HD double ang_delta_lambda(const AngPre& a, double h, double compliance, double lambda, V3 dq, int* status) {
+	double theta = length(dq);
+	if (theta <= 1e-50) return 0.0;
+	V3 n = divide(dq, theta);
+	double w1 = dot(n, mul(a.ii1, n));
+	double w2 = dot(n, mul(a.ii2, n));
+	if (!(w1 + w2 != 0.0)) *status |= ST_SOLVER_SINGULAR;
+	double til = compliance / (h * h);
+	return (-theta - til * lambda) / (w1 + w2 + til);
+}
+// angular_constraint_apply (pbd_base_constraints.cpp:164-227)
+RP_HD void ang_apply(const AngPre& a, Body& b1, Body& b2, double dl, V3 dq) {
+	double theta = length(dq);
+	if (theta <= 1e-50) return;
+	V3 n = divide(dq, theta);
+	V3 imp = scale(-dl, n);
+	V3 aux1 = mul(a.ii1, imp);
+	V3 aux2 = mul(a.ii2, imp);
+	if (!b1.fixed) apply_rotation(b1, aux1, 1.0);
+	if (!b2.fixed) apply_rotation(b2, aux2, -1.0);
+}
+
+// ------------------------------------------------------------------------------------------------------ contact solve
+struct Contact {  // Collision_Constraint minus the normal, which is shared by a collider pair's whole manifold
+	V3 r1_lc, r2_lc;
+	double lambda_n, lambda_t;
+};
+
+// clipping_contact_to_collision_constraint (pbd.cpp:408-424)
+RP_HD Contact make_contact(const Body& b1, const Body& b2, V3 p1, V3 p2) {
+	Contact c;
+	c.r1_lc = rotate(conj(b1.q), sub(p1, b1.x));
+	c.r2_lc = rotate(conj(b2.q), sub(p2, b2.x));
+	c.lambda_n = 0.0;
+	c.lambda_t = 0.0;
+	return c;
+}
+
+// collision_constraint_solve (pbd.cpp:107-154), incl. quirk q1 (static friction reuses the normal correction vector)
+RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, int* status) {
+	PosPre p = pos_pre(b1, b2, c.r1_lc, c.r2_lc);
+	V3 p1 = add(b1.x, p.r1);
+	V3 p2 = add(b2.x, p.r2);
+	double d = dot(sub(p1, p2), normal);
+	if (d > 0.0) {
+		V3 dx = scale(d, normal);
+		double dl = pos_delta_lambda(p, b1, b2, h, 0.0, c.lambda_n, dx, status);
+		pos_apply(p, b1, b2, dl, dx);
+		c.lambda_n += dl;
+
+		p = pos_pre(b1, b2, c.r1_lc, c.r2_lc);
+		p1 = add(b1.x, p.r1);
+		p2 = add(b2.x, p.r2);
+		dl = pos_delta_lambda(p, b1, b2, h, 0.0, c.lambda_t, dx, status);
+		double mu = (b1.mu_s + b2.mu_s) / 2.0;
+		double lambda_n = c.lambda_n;
+		double lambda_t = c.lambda_t + dl;
+		if (lambda_t > mu * lambda_n) {
+			V3 p1t = add(b1.px, rotate(b1.pq, c.r1_lc));
+			V3 p2t = add(b2.px, rotate(b2.pq, c.r2_lc));
+			V3 dp = sub(sub(p1, p1t), sub(p2, p2t));
+			V3 dpt = sub(dp, scale(dot(dp, normal), normal));
+			pos_apply(p, b1, b2, dl, dpt);
+			c.lambda_t += dl;
+		}
+	}
+}
+
+// velocity solve for one contact (pbd.cpp:648-711)
+RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, double h) {
+	PosPre p = pos_pre(b1, b2, c.r1_lc, c.r2_lc);
+	V3 v = sub(add(b1.v, cross(b1.w, p.r1)), add(b2.v, cross(b2.w, p.r2)));
+	double vn = dot(n, v);
+	V3 vt = sub(v, scale(vn, n));
+	V3 dv = v3(0.0, 0.0, 0.0);
+	double mu = (b1.mu_d + b2.mu_d) / 2.0;
+	double fn = c.lambda_n / h;
+	double fact = RP_MINF(mu * fabs(fn), length(vt));
+	dv = add(dv, scale(-fact, normalize(vt)));
+	V3 vtil = sub(add(b1.pv, cross(b1.pw, p.r1)), add(b2.pv, cross(b2.pw, p.r2)));
+	double vn_til = dot(n, vtil);
+	double e = b1.rest * b2.rest;
+	fact = -vn + RP_MINF(-e * vn_til, 0.0);
+	dv = add(dv, scale(fact, n));
+	double w1 = b1.inv_mass + dot(cross(p.r1, n), mul(p.ii1, cross(p.r1, n)));
+	double w2 = b2.inv_mass + dot(cross(p.r2, n), mul(p.ii2, cross(p.r2, n)));
+	V3 imp = scale(1.0 / (w1 + w2), dv);
+	if (!b1.fixed) {
+		b1.v = add(b1.v, scale(b1.inv_mass, imp));
+		b1.w = add(b1.w, mul(p.ii1, cross(p.r1, imp)));
+	}
+	if (!b2.fixed) {
+		b2.v = add(b2.v, zero_minus(scale(b2.inv_mass, imp)));
+		b2.w = add(b2.w, zero_minus(mul(p.ii2, cross(p.r2, imp))));
+	}
+}
+
+// -------------------------------------------------------------------------------------------------------------- joints
+enum { JOINT_POSITIONAL = 0, JOINT_MUTUAL_ORIENTATION = 2, JOINT_HINGE = 3, JOINT_SPHERICAL = 4 };  // Constraint_Type (pbd.h:14-20)
+
+struct Joint {  // the external Constraint union (pbd.h:22-91), flattened
+	int type;
+	int e1, e2;
+	int limited;            // hinge
+	int axis[4];            // hinge: e1_aligned, e2_aligned, e1_limit, e2_limit; spherical: e1_swing, e2_swing, e1_twist, e2_twist
+	V3 r1_lc, r2_lc;
+	V3 distance;            // positional
+	double compliance;
+	double lower, upper;    // hinge limits / spherical swing limits
+	double lower2, upper2;  // spherical twist limits
+};
+
+struct JointLambda {  // reset to zero every substep (copy_constraints, pbd.cpp:426-462)
+	double a, b, c;
+};
+
+// limit_angle (pbd.cpp:175-217)
+RP_HD bool limit_angle(V3 n, V3 n1, V3 n2, double alpha, double beta, V3* dq) {
+	double phi = asin(dot(cross(n1, n2), n));
+	if (dot(n1, n2) < 0.0) phi = RP_PI_F - phi;
+	if (phi > RP_PI_F) phi = phi - 2.0 * RP_PI_F;
+	if (phi < -RP_PI_F) phi = phi + 2.0 * RP_PI_F;
+	if (phi < alpha || phi > beta) {
+		phi = ((phi) > (beta)) ? (beta) : (((phi) < (alpha)) ? (alpha) : (phi));  // CLAMP (common.h:22)
+		Q4 rot = quat_axis_angle(n, phi);
+		n1 = rotate(rot, n1);
+		*dq = cross(n1, n2);
+		return true;
+	}
+	return false;
+}
+
+// solve_constraint for the four external types (pbd.cpp:81-97, :156-173, :245-299, :301-379)
+RP_HD void solve_joint(const Joint& j, JointLambda& l, Body& b1, Body& b2, double h, int* status) {
+	if (j.type == JOINT_POSITIONAL) {
+		V3 dx = sub(sub(b1.x, b2.x), j.distance);
+		PosPre p = pos_pre(b1, b2, j.r1_lc, j.r2_lc);
+		double dl = pos_delta_lambda(p, b1, b2, h, j.compliance, l.a, dx, status);
+		pos_apply(p, b1, b2, dl, dx);
+		l.a += dl;
+	} else if (j.type == JOINT_MUTUAL_ORIENTATION) {
+		AngPre a = ang_pre(b1, b2);
+		Q4 aux = mul(b1.q, conj(b2.q));
+		V3 dq = v3(2.0 * aux.x, 2.0 * aux.y, 2.0 * aux.z);
+		double dl = ang_delta_lambda(a, h, j.compliance, l.a, dq, status);
+		ang_apply(a, b1, b2, dl, dq);
+		l.a += dl;
+	} else if (j.type == JOINT_HINGE) {
+		// l.a = lambda_aligned_axes, l.b = lambda_pos, l.c = lambda_limit_axes
+		AngPre a = ang_pre(b1, b2);
+		V3 a1 = axis_world(b1.q, j.axis[0]);
+		V3 a2 = axis_world(b2.q, j.axis[1]);
+		V3 dq = cross(a1, a2);
+		double dl = ang_delta_lambda(a, h, j.compliance, l.a, dq, status);
+		ang_apply(a, b1, b2, dl, dq);
+		l.a += dl;
+
+		PosPre p = pos_pre(b1, b2, j.r1_lc, j.r2_lc);
+		V3 dx = sub(add(b1.x, p.r1), add(b2.x, p.r2));
+		dl = pos_delta_lambda(p, b1, b2, h, 0.0, l.b, dx, status);
+		pos_apply(p, b1, b2, dl, dx);
+		l.b += dl;
+
+		if (j.limited) {
+			V3 n1 = axis_world(b1.q, j.axis[2]);
+			V3 n2 = axis_world(b2.q, j.axis[3]);
+			V3 n = axis_world(b1.q, j.axis[0]);
+			if (limit_angle(n, n1, n2, j.lower, j.upper, &dq)) {
+				AngPre a2p = ang_pre(b1, b2);
+				double dl2 = ang_delta_lambda(a2p, h, 0.0, l.c, dq, status);
+				ang_apply(a2p, b1, b2, dl2, dq);
+				l.c += dl2;
+			}
+		}
+	} else {
+		// spherical: l.a = lambda_pos, l.b = lambda_swing, l.c = lambda_twist
+		const double EPS = 1e-50;
+		PosPre p = pos_pre(b1, b2, j.r1_lc, j.r2_lc);
+		V3 dx = sub(add(b1.x, p.r1), add(b2.x, p.r2));
+		double dl = pos_delta_lambda(p, b1, b2, h, 0.0, l.a, dx, status);
+		pos_apply(p, b1, b2, dl, dx);
+		l.a += dl;
+
+		V3 n1 = axis_world(b1.q, j.axis[0]);
+		V3 n2 = axis_world(b2.q, j.axis[1]);
+		V3 n = cross(n1, n2);
+		double nl = length(n);
+		if (nl > EPS) {
+			n = divide(n, nl);
+			V3 dq;
+			if (limit_angle(n, n1, n2, j.lower, j.upper, &dq)) {
+				AngPre a = ang_pre(b1, b2);
+				double d2 = ang_delta_lambda(a, h, 0.0, l.b, dq, status);
+				ang_apply(a, b1, b2, d2, dq);
+				l.b += d2;
+			}
+		}
+		V3 a1 = axis_world(b1.q, j.axis[0]);
+		V3 t1 = axis_world(b1.q, j.axis[2]);
+		V3 a2 = axis_world(b2.q, j.axis[1]);
+		V3 t2 = axis_world(b2.q, j.axis[3]);
+		n = add(a1, a2);
+		nl = length(n);
+		if (nl > EPS) {
+			n = divide(n, nl);
+			n1 = sub(t1, scale(dot(n, t1), n));
+			n2 = sub(t2, scale(dot(n, t2), n));
+			double l1 = length(n1), l2 = length(n2);
+			if (l1 > EPS && l2 > EPS) {
+				n1 = divide(n1, l1);
+				n2 = divide(n2, l2);
+				V3 dq;
+				if (limit_angle(n, n1, n2, j.lower2, j.upper2, &dq)) {
+					AngPre a = ang_pre(b1, b2);
+					double d3 = ang_delta_lambda(a, h, 0.0, l.c, dq, status);
+					ang_apply(a, b1, b2, d3, dq);
+					l.c += d3;
+				}
+			}
+		}
+	}
+}
+
+}  // namespace rp
+#endif

@@ -24,8 +24,23 @@ def _u(a):
 
 
 def lib_path(flavour="strict"):
+    if flavour == "port":
+        return os.path.join(ROOT, "oracle", "libport_oracle.so")
     name = "libref_oracle.so" if flavour == "strict" else "libref_oracle_fastmath.so"
     return os.path.join(ROOT, "oracle", "_ref", name)
+
+
+class _Prefixed:
+    """Resolves L.ref_xyz to <prefix>_xyz so the reference driver and the CPU restatement (oracle/port, exported as
+    port_*) are driven through the very same code."""
+
+    def __init__(self, lib, prefix):
+        self._lib, self._prefix = lib, prefix
+
+    def __getattr__(self, name):
+        if name.startswith("ref_"):
+            name = self._prefix + name[3:]
+        return getattr(self._lib, name)
 
 
 def available(flavour="strict"):
@@ -36,7 +51,8 @@ class RefWorld:
     """One reference world (the reference keeps its entity table in process globals, so this is a singleton)."""
 
     def __init__(self, flavour="strict"):
-        self.lib = C.CDLL(lib_path(flavour))
+        self.flavour = flavour
+        self.lib = _Prefixed(C.CDLL(lib_path(flavour)), "port" if flavour == "port" else "ref")
         L = self.lib
         L.ref_entity_create.restype = C.c_uint64
         L.ref_entity_create.argtypes = [_dp, _dp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double]
