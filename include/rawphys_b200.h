@@ -1,0 +1,153 @@
+/* rawphys_b200.h -- C ABI of librawphys_b200.so: the XPBD frame step of felipeek/raw-physics on NVIDIA B200 (sm_100a).
+ *
+ * The seam this library replaces is the reference's pair of free functions (src/physics/pbd.h:93-94)
+ *
+ *     void pbd_simulate(r64 dt, Entity** entities, u32 num_substeps, u32 num_pos_iters, boolean enable_collisions);
+ *     void pbd_simulate_with_constraints(r64 dt, Entity** entities, Constraint* external_constraints,
+ *                                        u32 num_substeps, u32 num_pos_iters, boolean enable_collisions);
+ *
+ * and everything they call (broad.cpp, collider.cpp, gjk.cpp, epa.cpp, clipping.cpp, support.cpp,
+ * pbd_base_constraints.cpp, physics_util.cpp). A *scene* is the template the reference builds with
+ * collider_convex_hull_create / collider_sphere_create / entity_create[_fixed] / pbd_*_constraint_init; a *batch* is
+ * n_worlds independent instances of that scene resident in the HBM of one GPU; rp_batch_step is one
+ * pbd_simulate_with_constraints call applied to every world. Plain pointers and sizes only; no global state; every
+ * call returns a status code (0 = RP_OK) instead of aborting. There is NO CPU fallback: without a CUDA device every
+ * batch call fails with RP_ERR_CUDA.
+ *
+ * Body ids are the order of rp_scene_add_body calls and equal the reference's eids when its eid_counter starts at 0.
+ */
+#ifndef RAWPHYS_B200_H
+#define RAWPHYS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rp_scene rp_scene;
+typedef struct rp_batch rp_batch;
+
+enum {
+	RP_OK = 0,
+	RP_ERR_ARG = 1,      /* bad argument */
+	RP_ERR_CUDA = 2,     /* CUDA runtime error or no device; rp_last_error() has the text */
+	RP_ERR_CAPACITY = 3  /* a fixed-capacity device buffer overflowed; see rp_batch_get_status */
+};
+
+/* per-world status bits (rp_batch_get_status); a non-zero word means the reference would have aborted on an assert,
+ * printed a warning, or the device ran out of a fixed capacity in that world */
+enum {
+	RP_ST_GJK_SIMPLEX_OVERFLOW = 1 << 0, /* gjk.cpp:24-26 */
+	RP_ST_EPA_DEGENERATE = 1 << 1,       /* epa.cpp:41,72 */
+	RP_ST_EPA_NO_CONVERGENCE = 1 << 2,   /* epa.cpp:233 */
+	RP_ST_EPA_CAPACITY = 1 << 3,
+	RP_ST_CLIP_CAPACITY = 1 << 4,
+	RP_ST_EDGE_PARALLEL = 1 << 5,        /* clipping.cpp:279 */
+	RP_ST_CONTACT_CAPACITY = 1 << 6,
+	RP_ST_PAIR_CAPACITY = 1 << 7,
+	RP_ST_SOLVER_SINGULAR = 1 << 8,      /* pbd_base_constraints.cpp:40,154 */
+	RP_ST_NAN = 1 << 9
+};
+
+/* PBD_Axis_Type (src/physics/pbd.h:5-12) */
+enum { RP_POSITIVE_X_AXIS = 0, RP_NEGATIVE_X_AXIS, RP_POSITIVE_Y_AXIS, RP_NEGATIVE_Y_AXIS, RP_POSITIVE_Z_AXIS, RP_NEGATIVE_Z_AXIS };
+
+const char* rp_last_error(void);
+/* number of CUDA devices visible, or 0 */
+int rp_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------ scene template */
+rp_scene* rp_scene_create(void);
+void rp_scene_destroy(rp_scene* s);
+
+/* collider_convex_hull_create (collider.cpp:194): triangle soup, vertices already scaled (3 doubles each), indices in
+ * triples. The collider is queued for the NEXT rp_scene_add_body call. Returns its index within that body, or -1. */
+int rp_scene_collider_hull(rp_scene* s, const double* vertices_xyz, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices);
+/* collider_sphere_create (collider.cpp:12) */
+int rp_scene_collider_sphere(rp_scene* s, float radius);
+/* entity_create / entity_create_fixed (entity.cpp:67-77): consumes the queued colliders. Returns the body id or -1. */
+int rp_scene_add_body(rp_scene* s, const double position[3], const double rotation_xyzw[4], double mass, int fixed,
+	double static_friction, double dynamic_friction, double restitution);
+
+/* pbd_positional_constraint_init ... pbd_spherical_joint_constraint_init (pbd.cpp:18-79); return the constraint index */
+int rp_scene_add_positional_constraint(rp_scene* s, int e1, int e2, const double r1_lc[3], const double r2_lc[3], double compliance,
+	const double distance[3]);
+int rp_scene_add_mutual_orientation_constraint(rp_scene* s, int e1, int e2, double compliance);
+int rp_scene_add_hinge_joint_constraint(rp_scene* s, int e1, int e2, const double r1_lc[3], const double r2_lc[3], double compliance,
+	int e1_aligned_axis, int e2_aligned_axis, int limited, int e1_limit_axis, int e2_limit_axis, double lower_limit, double upper_limit);
+int rp_scene_add_spherical_joint_constraint(rp_scene* s, int e1, int e2, const double r1_lc[3], const double r2_lc[3], int e1_swing_axis,
+	int e2_swing_axis, int e1_twist_axis, int e2_twist_axis, double swing_lower, double swing_upper, double twist_lower, double twist_upper);
+
+int rp_scene_num_bodies(const rp_scene* s);
+/* static per-body parameters as entity_create_ex computes them, 25 doubles per body:
+ * inverse_mass, inertia[9], inverse_inertia[9], bounding_sphere_radius, mu_s, mu_d, restitution, fixed, n_colliders */
+#define RP_PARAM_STRIDE 25
+int rp_scene_get_params(const rp_scene* s, double* out);
+/* hull topology in the reference's order (for parity checks): sizes = V, F, sum face elems, sum v2f, sum v2n, sum f2n
+ * (V = -1 for a sphere); the dump fills CSR arrays whose ptr arrays have count + 1 entries */
+int rp_scene_hull_sizes(const rp_scene* s, int body, int collider, int32_t out6[6]);
+int rp_scene_hull_dump(const rp_scene* s, int body, int collider, double* verts, double* normals, uint32_t* face_ptr, uint32_t* face_idx,
+	uint32_t* v2f_ptr, uint32_t* v2f_idx, uint32_t* v2n_ptr, uint32_t* v2n_idx, uint32_t* f2n_ptr, uint32_t* f2n_idx);
+
+/* ------------------------------------------------------------------------------------------------------- batches */
+typedef struct {
+	uint32_t max_pairs_per_world;     /* broadphase (collider-)pair capacity; 0 = derive from the initial poses */
+	uint32_t max_contacts_per_world;  /* contact capacity per substep; 0 = derive */
+	uint32_t solve_threads;           /* threads of the per-world solver CTA (multiple of 32); 0 = derive */
+	double linear_sleeping_threshold;   /* pbd.cpp:13, default 0.10 */
+	double angular_sleeping_threshold;  /* pbd.cpp:14, default 0.10 */
+	double deactivation_time;           /* pbd.cpp:15, default 1.0 */
+} rp_batch_cfg;
+void rp_batch_cfg_default(rp_batch_cfg* cfg);
+
+int rp_batch_create(const rp_scene* scene, uint32_t n_worlds, int cuda_device, const rp_batch_cfg* cfg_or_null, rp_batch** out);
+void rp_batch_destroy(rp_batch* b);
+uint32_t rp_batch_num_worlds(const rp_batch* b);
+uint32_t rp_batch_num_bodies(const rp_batch* b);
+
+/* External forces for the coming step(s), shared by every world: the sums of entity_add_force(e, position, force,
+ * local_coords=false) calls (entity.cpp:176-193) in call order, as calculate_external_force/torque form them. */
+int rp_batch_clear_forces(rp_batch* b);
+int rp_batch_add_force(rp_batch* b, int body, const double position[3], const double force[3]);
+/* the examples' gravity idiom: (0, -g * 1.0 / inverse_mass, 0) at the centre of every body (stack.cpp:93-96) */
+int rp_batch_add_gravity(rp_batch* b, double g);
+
+/* pbd_simulate_with_constraints for every world: enqueued on the batch's CUDA stream, returns without waiting. */
+int rp_batch_step(rp_batch* b, double dt, uint32_t num_substeps, uint32_t num_pos_iters, int enable_collisions);
+int rp_batch_sync(rp_batch* b);
+/* `frames` consecutive steps timed on the device with CUDA events on the batch's stream (milliseconds). */
+int rp_batch_run(rp_batch* b, uint32_t frames, double dt, uint32_t num_substeps, uint32_t num_pos_iters, int enable_collisions,
+	float* gpu_ms_out);
+
+/* Per-body dynamic state record, RP_STATE_STRIDE doubles: world_position[3], world_rotation xyzw[4],
+ * linear_velocity[3], angular_velocity[3], active (0/1), deactivation_time, previous_linear_velocity[3],
+ * previous_angular_velocity[3] (entity.h:21-46). Host arrays are [world][body][RP_STATE_STRIDE]. */
+#define RP_STATE_STRIDE 21
+int rp_batch_upload_state(rp_batch* b, uint32_t first_world, uint32_t n_worlds, const double* host_state);
+int rp_batch_download_state(rp_batch* b, uint32_t first_world, uint32_t n_worlds, double* host_state);
+/* same state for every world (the scene's initial poses are loaded at creation) */
+int rp_batch_broadcast_state(rp_batch* b, const double* host_state_one_world);
+/* Host-buffer form of the step (what a pbd_simulate shim calls): upload `host_state_in` (all worlds), step, download
+ * into `host_state_out`, synchronise. Either pointer may be NULL to skip that copy. */
+int rp_batch_step_host(rp_batch* b, const double* host_state_in, double* host_state_out, double dt, uint32_t num_substeps,
+	uint32_t num_pos_iters, int enable_collisions);
+
+int rp_batch_get_status(rp_batch* b, int32_t* status_per_world);
+/* cumulative work counters since creation: [0] narrowphase collider-pair tests, [1] GJK hits (EPA runs),
+ * [2] contacts, [3] broadphase pairs (per frame, summed), [4] solver levels (per frame, summed), [5] frames */
+int rp_batch_get_counters(rp_batch* b, uint64_t out8[8]);
+
+/* Parity instrumentation: one frame of ONE world stepped substep by substep, logging what the reference's
+ * colliders_get_contacts (collider.cpp:560) returns for every narrowphase pair in pair order: calls_out gets 4 u32 per
+ * call (e1, e2, contact count, index of first contact), contacts_out 9 doubles per contact (point1, point2, normal).
+ * All other worlds are stepped too. Returns counts through n_calls / n_contacts. */
+int rp_batch_step_logged(rp_batch* b, double dt, uint32_t num_substeps, uint32_t num_pos_iters, int enable_collisions, uint32_t world,
+	uint32_t* calls_out, uint32_t max_calls, double* contacts_out, uint32_t max_contacts, uint32_t* n_calls, uint32_t* n_contacts);
+/* broadphase pairs of one world for its current poses (broad_get_collision_pairs, broad.cpp:6): (e1, e2) body ids */
+int rp_batch_broad_pairs(rp_batch* b, uint32_t world, uint32_t* pairs_out, uint32_t max_pairs, uint32_t* n_pairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,691 @@
+// rp_batch.cu -- the C ABI of include/rawphys_b200.h: scene templates on the host, world batches in device memory,
+// frame stepping through a CUDA graph. No CPU fallback: every batch entry point needs a CUDA device.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/rawphys_b200.h"
+#include "rp_kernels.cuh"
+#include "rp_scene.h"
+
+using namespace rp;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+	g_err = msg;
+	return code;
+}
+
+#define RP_CUDA(call)                                                                                                  \
+	do {                                                                                                               \
+		cudaError_t e_ = (call);                                                                                       \
+		if (e_ != cudaSuccess) {                                                                                       \
+			cudaGetLastError();                                                                                        \
+			return fail(RP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                              \
+		}                                                                                                              \
+	} while (0)
+
+struct rp_scene {
+	Scene s;
+};
+
+struct GraphKey {
+	double dt;
+	uint32_t substeps, iters;
+	int collisions;
+	bool operator==(const GraphKey& o) const { return dt == o.dt && substeps == o.substeps && iters == o.iters && collisions == o.collisions; }
+};
+
+struct rp_batch {
+	Scene scene;  // private copy of the template (forces are accumulated here)
+	DevView d;
+	int device = 0;
+	cudaStream_t stream = 0;
+	cudaEvent_t ev0 = 0, ev1 = 0;
+	std::vector<void*> allocs;
+	V3* force_dev = 0;
+	V3* torque_dev = 0;
+	bool forces_dirty = true;
+	double* rec_dev = 0;  // staging for state records, [W][NB][RP_STATE_STRIDE]
+	int solve_threads = 64;
+	int gjk_chunks = 1;
+	int sm_count = 148;
+	bool have_graph = false;
+	GraphKey graph_key;
+	cudaGraph_t graph = 0;
+	cudaGraphExec_t graph_exec = 0;
+};
+
+template <class T>
+static int dev_alloc(rp_batch* b, T** out, size_t n, bool zero = true) {
+	void* p = 0;
+	size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+	RP_CUDA(cudaMalloc(&p, bytes));
+	b->allocs.push_back(p);
+	if (zero) RP_CUDA(cudaMemsetAsync(p, 0, bytes, b->stream));
+	*out = (T*)p;
+	return RP_OK;
+}
+template <class T>
+static int dev_upload(rp_batch* b, const T** out, const std::vector<T>& v) {
+	T* p = 0;
+	int rc = dev_alloc(b, &p, v.size());
+	if (rc) return rc;
+	if (!v.empty()) RP_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, b->stream));
+	*out = p;
+	return RP_OK;
+}
+
+extern "C" {
+
+const char* rp_last_error(void) { return g_err.c_str(); }
+
+int rp_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------- scenes
+rp_scene* rp_scene_create(void) { return new rp_scene(); }
+void rp_scene_destroy(rp_scene* s) { delete s; }
+
+int rp_scene_collider_hull(rp_scene* s, const double* v, uint32_t nv, const uint32_t* idx, uint32_t nidx) {
+	if (!s || !v || !idx || nv == 0 || nidx < 3) return -1;
+	for (uint32_t i = 0; i < nidx; ++i) {
+		if (idx[i] >= nv) return -1;
+	}
+	return s->s.add_hull_collider(v, nv, idx, nidx);
+}
+int rp_scene_collider_sphere(rp_scene* s, float radius) {
+	if (!s) return -1;
+	return s->s.add_sphere_collider(radius);
+}
+int rp_scene_add_body(rp_scene* s, const double pos[3], const double quat[4], double mass, int fixed, double mu_s, double mu_d, double rest) {
+	if (!s || !pos || !quat) return -1;
+	return s->s.add_body(pos, quat, mass, fixed, mu_s, mu_d, rest);
+}
+
+static bool valid_pair(const rp_scene* s, int e1, int e2) {
+	int n = (int)s->s.bodies.size();
+	return s && e1 >= 0 && e2 >= 0 && e1 < n && e2 < n && e1 != e2;
+}
+static V3 vec(const double* p) { return v3(p[0], p[1], p[2]); }
+static Joint blank_joint(int type, int e1, int e2) {
+	Joint j;
+	memset(&j, 0, sizeof(j));
+	j.type = type; j.e1 = e1; j.e2 = e2;
+	return j;
+}
+
+int rp_scene_add_positional_constraint(rp_scene* s, int e1, int e2, const double r1[3], const double r2[3], double compliance, const double dist[3]) {
+	if (!s || !valid_pair(s, e1, e2)) return -1;
+	Joint j = blank_joint(JOINT_POSITIONAL, e1, e2);
+	j.r1_lc = vec(r1); j.r2_lc = vec(r2); j.compliance = compliance; j.distance = vec(dist);
+	s->s.joints.push_back(j);
+	return (int)s->s.joints.size() - 1;
+}
+int rp_scene_add_mutual_orientation_constraint(rp_scene* s, int e1, int e2, double compliance) {
+	if (!s || !valid_pair(s, e1, e2)) return -1;
+	Joint j = blank_joint(JOINT_MUTUAL_ORIENTATION, e1, e2);
+	j.compliance = compliance;
+	s->s.joints.push_back(j);
+	return (int)s->s.joints.size() - 1;
+}
+int rp_scene_add_hinge_joint_constraint(rp_scene* s, int e1, int e2, const double r1[3], const double r2[3], double compliance, int a1, int a2,
+	int limited, int l1, int l2, double lower, double upper) {
+	if (!s || !valid_pair(s, e1, e2)) return -1;
+	Joint j = blank_joint(JOINT_HINGE, e1, e2);
+	j.r1_lc = vec(r1); j.r2_lc = vec(r2); j.compliance = compliance;
+	j.axis[0] = a1; j.axis[1] = a2; j.axis[2] = l1; j.axis[3] = l2;
+	j.limited = limited ? 1 : 0; j.lower = lower; j.upper = upper;
+	s->s.joints.push_back(j);
+	return (int)s->s.joints.size() - 1;
+}
+int rp_scene_add_spherical_joint_constraint(rp_scene* s, int e1, int e2, const double r1[3], const double r2[3], int sw1, int sw2, int tw1,
+	int tw2, double swing_lower, double swing_upper, double twist_lower, double twist_upper) {
+	if (!s || !valid_pair(s, e1, e2)) return -1;
+	Joint j = blank_joint(JOINT_SPHERICAL, e1, e2);
+	j.r1_lc = vec(r1); j.r2_lc = vec(r2);
+	j.axis[0] = sw1; j.axis[1] = sw2; j.axis[2] = tw1; j.axis[3] = tw2;
+	j.lower = swing_lower; j.upper = swing_upper; j.lower2 = twist_lower; j.upper2 = twist_upper;
+	s->s.joints.push_back(j);
+	return (int)s->s.joints.size() - 1;
+}
+
+int rp_scene_num_bodies(const rp_scene* s) { return s ? (int)s->s.bodies.size() : -1; }
+
+int rp_scene_get_params(const rp_scene* s, double* out) {
+	if (!s || !out) return RP_ERR_ARG;
+	for (size_t i = 0; i < s->s.bodies.size(); ++i) {
+		const BodyInit& b = s->s.bodies[i];
+		double* o = out + RP_PARAM_STRIDE * i;
+		o[0] = b.inv_mass;
+		for (int r = 0; r < 3; ++r) {
+			for (int c = 0; c < 3; ++c) {
+				o[1 + 3 * r + c] = b.inertia.m[r][c];
+				o[10 + 3 * r + c] = b.inv_inertia.m[r][c];
+			}
+		}
+		o[19] = b.radius; o[20] = b.mu_s; o[21] = b.mu_d; o[22] = b.rest; o[23] = b.fixed ? 1.0 : 0.0; o[24] = (double)b.ncol;
+	}
+	return RP_OK;
+}
+
+static const HullHost* find_hull(const rp_scene* s, int body, int collider, bool* sphere) {
+	*sphere = false;
+	if (!s || body < 0 || body >= (int)s->s.bodies.size()) return 0;
+	const BodyInit& b = s->s.bodies[body];
+	if (collider < 0 || collider >= b.ncol) return 0;
+	const ColliderDesc& c = s->s.colliders[b.col0 + collider];
+	if (c.type != SHAPE_HULL) {
+		*sphere = true;
+		return 0;
+	}
+	return &s->s.hulls[c.hull];
+}
+
+int rp_scene_hull_sizes(const rp_scene* s, int body, int collider, int32_t out6[6]) {
+	bool sphere;
+	const HullHost* h = find_hull(s, body, collider, &sphere);
+	if (sphere) {
+		out6[0] = -1;
+		return RP_OK;
+	}
+	if (!h) return RP_ERR_ARG;
+	out6[0] = (int32_t)h->verts.size(); out6[1] = (int32_t)h->normals.size(); out6[2] = (int32_t)h->face_idx.size();
+	out6[3] = (int32_t)h->v2f_idx.size(); out6[4] = (int32_t)h->v2n_idx.size(); out6[5] = (int32_t)h->f2n_idx.size();
+	return RP_OK;
+}
+
+static void copy_u32(const std::vector<int>& v, uint32_t* out) {
+	for (size_t i = 0; i < v.size(); ++i) out[i] = (uint32_t)v[i];
+}
+
+int rp_scene_hull_dump(const rp_scene* s, int body, int collider, double* verts, double* normals, uint32_t* face_ptr, uint32_t* face_idx,
+	uint32_t* v2f_ptr, uint32_t* v2f_idx, uint32_t* v2n_ptr, uint32_t* v2n_idx, uint32_t* f2n_ptr, uint32_t* f2n_idx) {
+	bool sphere;
+	const HullHost* h = find_hull(s, body, collider, &sphere);
+	if (!h) return RP_ERR_ARG;
+	memcpy(verts, h->verts.data(), sizeof(V3) * h->verts.size());
+	memcpy(normals, h->normals.data(), sizeof(V3) * h->normals.size());
+	copy_u32(h->face_ptr, face_ptr); copy_u32(h->face_idx, face_idx);
+	copy_u32(h->v2f_ptr, v2f_ptr); copy_u32(h->v2f_idx, v2f_idx);
+	copy_u32(h->v2n_ptr, v2n_ptr); copy_u32(h->v2n_idx, v2n_idx);
+	copy_u32(h->f2n_ptr, f2n_ptr); copy_u32(h->f2n_idx, f2n_idx);
+	return RP_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------- batches
+void rp_batch_cfg_default(rp_batch_cfg* cfg) {
+	if (!cfg) return;
+	memset(cfg, 0, sizeof(*cfg));
+	cfg->linear_sleeping_threshold = 0.10;
+	cfg->angular_sleeping_threshold = 0.10;
+	cfg->deactivation_time = 1.0;
+}
+
+void rp_batch_destroy(rp_batch* b) {
+	if (!b) return;
+	cudaSetDevice(b->device);
+	if (b->stream) cudaStreamSynchronize(b->stream);
+	if (b->graph_exec) cudaGraphExecDestroy(b->graph_exec);
+	if (b->graph) cudaGraphDestroy(b->graph);
+	for (size_t i = 0; i < b->allocs.size(); ++i) cudaFree(b->allocs[i]);
+	if (b->ev0) cudaEventDestroy(b->ev0);
+	if (b->ev1) cudaEventDestroy(b->ev1);
+	if (b->stream) cudaStreamDestroy(b->stream);
+	cudaGetLastError();
+	delete b;
+}
+
+static std::vector<double> initial_records(const Scene& s) {
+	std::vector<double> rec(s.bodies.size() * RP_STATE_STRIDE, 0.0);
+	for (size_t i = 0; i < s.bodies.size(); ++i) {
+		double* r = &rec[i * RP_STATE_STRIDE];
+		const BodyInit& b = s.bodies[i];
+		r[0] = b.x.x; r[1] = b.x.y; r[2] = b.x.z;
+		r[3] = b.q.x; r[4] = b.q.y; r[5] = b.q.z; r[6] = b.q.w;
+		r[13] = 1.0;  // entity->active = true (entity.cpp:50)
+	}
+	return rec;
+}
+
+static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, const rp_batch_cfg* cfg_in, rp_batch* b) {
+	const Scene& s = scene->s;
+	rp_batch_cfg cfg;
+	rp_batch_cfg_default(&cfg);
+	if (cfg_in) cfg = *cfg_in;
+	int ndev = 0;
+	RP_CUDA(cudaGetDeviceCount(&ndev));
+	if (device < 0 || device >= ndev) return fail(RP_ERR_CUDA, "no such CUDA device");
+	RP_CUDA(cudaSetDevice(device));
+	b->device = device;
+	b->scene = s;
+	b->scene.pending.clear();
+	RP_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+	RP_CUDA(cudaEventCreate(&b->ev0));
+	RP_CUDA(cudaEventCreate(&b->ev1));
+	cudaDeviceProp prop;
+	RP_CUDA(cudaGetDeviceProperties(&prop, device));
+	b->sm_count = prop.multiProcessorCount;
+
+	DevView& d = b->d;
+	memset(&d, 0, sizeof(d));
+	d.W = (int)n_worlds;
+	d.NB = (int)s.bodies.size();
+	d.NC = (int)s.colliders.size();
+	d.NJ = (int)s.joints.size();
+	d.TV = s.total_tv;
+	d.TN = s.total_tn;
+	d.lin_sleep = cfg.linear_sleeping_threshold;
+	d.ang_sleep = cfg.angular_sleeping_threshold;
+	d.sleep_time = cfg.deactivation_time;
+	d.dbg_world = -1;
+
+	// capacities: derived from the broadphase of the initial poses unless given
+	size_t init_pairs = 0;
+	for (int i = 0; i < d.NB; ++i) {
+		for (int j = i + 1; j < d.NB; ++j) {
+			double dist = length(sub(s.bodies[i].x, s.bodies[j].x));
+			if (dist <= s.bodies[i].radius + s.bodies[j].radius + 0.1) init_pairs += (size_t)s.bodies[i].ncol * s.bodies[j].ncol;
+		}
+	}
+	size_t mp = cfg.max_pairs_per_world ? cfg.max_pairs_per_world : std::max<size_t>(128, 2 * init_pairs + 64);
+	mp = (mp + 127) / 128 * 128;
+	d.max_pairs = (int)mp;
+	d.max_contacts = (int)(cfg.max_contacts_per_world ? cfg.max_contacts_per_world : std::max<size_t>(256, 8 * (size_t)d.NB));
+	d.max_units = d.NJ + d.max_pairs;
+	b->solve_threads = cfg.solve_threads ? (int)((cfg.solve_threads + 31) / 32 * 32) : 64;
+	if (b->solve_threads > 1024) b->solve_threads = 1024;
+	{
+		int want = (b->sm_count * 8 + d.W - 1) / d.W;
+		int most = (d.max_pairs + 127) / 128;
+		b->gjk_chunks = std::max(1, std::min(want, most));
+	}
+
+	// template
+	std::vector<BodyStatic> bs(d.NB);
+	for (int i = 0; i < d.NB; ++i) {
+		const BodyInit& bi = s.bodies[i];
+		BodyStatic& o = bs[i];
+		memset(&o, 0, sizeof(o));
+		o.inv_mass = bi.inv_mass;
+		o.inertia = bi.inertia; o.inv_inertia = bi.inv_inertia;
+		o.mu_s = bi.mu_s; o.mu_d = bi.mu_d; o.rest = bi.rest; o.radius = bi.radius;
+		o.fixed = bi.fixed; o.col0 = bi.col0; o.ncol = bi.ncol;
+	}
+	HullPoolHost hp = pool_hulls(s);
+	int rc;
+	if ((rc = dev_upload(b, &d.bstat, bs))) return rc;
+	if ((rc = dev_upload(b, &d.cols, s.colliders))) return rc;
+	if ((rc = dev_upload(b, &d.joints, s.joints))) return rc;
+	if ((rc = dev_upload(b, &d.pool.hulls, hp.hulls))) return rc;
+	if ((rc = dev_upload(b, &d.pool.verts, hp.verts))) return rc;
+	if ((rc = dev_upload(b, &d.pool.normals, hp.normals))) return rc;
+	if ((rc = dev_upload(b, &d.pool.face_ptr, hp.face_ptr))) return rc;
+	if ((rc = dev_upload(b, &d.pool.face_idx, hp.face_idx))) return rc;
+	if ((rc = dev_upload(b, &d.pool.v2f_ptr, hp.v2f_ptr))) return rc;
+	if ((rc = dev_upload(b, &d.pool.v2f_idx, hp.v2f_idx))) return rc;
+	if ((rc = dev_upload(b, &d.pool.v2n_ptr, hp.v2n_ptr))) return rc;
+	if ((rc = dev_upload(b, &d.pool.v2n_idx, hp.v2n_idx))) return rc;
+	if ((rc = dev_upload(b, &d.pool.f2n_ptr, hp.f2n_ptr))) return rc;
+	if ((rc = dev_upload(b, &d.pool.f2n_idx, hp.f2n_idx))) return rc;
+	if ((rc = dev_alloc(b, &b->force_dev, (size_t)d.NB))) return rc;
+	if ((rc = dev_alloc(b, &b->torque_dev, (size_t)d.NB))) return rc;
+	d.force = b->force_dev;
+	d.torque = b->torque_dev;
+
+	// per world
+	const size_t W = (size_t)d.W, WB = W * d.NB, WP = W * d.max_pairs, WU = W * d.max_units;
+	if ((rc = dev_alloc(b, &d.dyn, WB))) return rc;
+	if ((rc = dev_alloc(b, &d.active, WB))) return rc;
+	if ((rc = dev_alloc(b, &d.deact, WB))) return rc;
+	if ((rc = dev_alloc(b, &d.tv, W * std::max(d.TV, 1)))) return rc;
+	if ((rc = dev_alloc(b, &d.tn, W * std::max(d.TN, 1)))) return rc;
+	if ((rc = dev_alloc(b, &d.pairs, WP))) return rc;
+	if ((rc = dev_alloc(b, &d.n_pairs, W))) return rc;
+	if ((rc = dev_alloc(b, &d.row_off, WB))) return rc;
+	if ((rc = dev_alloc(b, &d.label, WB))) return rc;
+	if ((rc = dev_alloc(b, &d.isl_flag, WB))) return rc;
+	if ((rc = dev_alloc(b, &d.last_level, WB))) return rc;
+	if ((rc = dev_alloc(b, &d.unit_level, WU))) return rc;
+	if ((rc = dev_alloc(b, &d.sched, WU))) return rc;
+	if ((rc = dev_alloc(b, &d.level_ptr, W * (d.max_units + 2)))) return rc;
+	if ((rc = dev_alloc(b, &d.n_levels, W))) return rc;
+	if ((rc = dev_alloc(b, &d.hits, WP, false))) return rc;
+	if ((rc = dev_alloc(b, &d.hit_count, 1))) return rc;
+	if ((rc = dev_alloc(b, &d.pair_normal, WP, false))) return rc;
+	if ((rc = dev_alloc(b, &d.pair_coff, WP))) return rc;
+	if ((rc = dev_alloc(b, &d.pair_ccnt, WP))) return rc;
+	if ((rc = dev_alloc(b, &d.contacts, W * d.max_contacts, false))) return rc;
+	if ((rc = dev_alloc(b, &d.n_contacts, W))) return rc;
+	if ((rc = dev_alloc(b, &d.lambdas, W * std::max(d.NJ, 1)))) return rc;
+	if ((rc = dev_alloc(b, &d.status, W))) return rc;
+	if ((rc = dev_alloc(b, &d.counters, 8))) return rc;
+	if ((rc = dev_alloc(b, &d.dbg_points, 2 * (size_t)d.max_contacts, false))) return rc;
+	if ((rc = dev_alloc(b, &b->rec_dev, WB * RP_STATE_STRIDE, false))) return rc;
+
+	std::vector<double> rec = initial_records(s);
+	RP_CUDA(cudaMemcpyAsync(b->rec_dev, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+	const unsigned int blocks = (unsigned int)((WB + 127) / 128);
+	k_unpack_state<<<blocks, 128, 0, b->stream>>>(d, b->rec_dev, 0, d.W, 1);
+	RP_CUDA(cudaGetLastError());
+	RP_CUDA(cudaStreamSynchronize(b->stream));
+	return RP_OK;
+}
+
+int rp_batch_create(const rp_scene* scene, uint32_t n_worlds, int device, const rp_batch_cfg* cfg, rp_batch** out) {
+	if (!scene || !out || n_worlds == 0 || n_worlds > 65535 || scene->s.bodies.empty()) return fail(RP_ERR_ARG, "rp_batch_create: bad argument");
+	if (!scene->s.pending.empty()) return fail(RP_ERR_ARG, "rp_batch_create: colliders queued without a body");
+	rp_batch* b = new rp_batch();
+	int rc = create_impl(scene, n_worlds, device, cfg, b);
+	if (rc) {
+		std::string keep = g_err;
+		rp_batch_destroy(b);
+		g_err = keep;
+		return rc;
+	}
+	*out = b;
+	return RP_OK;
+}
+
+uint32_t rp_batch_num_worlds(const rp_batch* b) { return b ? (uint32_t)b->d.W : 0; }
+uint32_t rp_batch_num_bodies(const rp_batch* b) { return b ? (uint32_t)b->d.NB : 0; }
+
+int rp_batch_clear_forces(rp_batch* b) {
+	if (!b) return RP_ERR_ARG;
+	b->scene.clear_forces();
+	b->forces_dirty = true;
+	return RP_OK;
+}
+int rp_batch_add_force(rp_batch* b, int body, const double position[3], const double force[3]) {
+	if (!b || body < 0 || body >= b->d.NB || !position || !force) return RP_ERR_ARG;
+	b->scene.add_force(body, vec(position), vec(force));
+	b->forces_dirty = true;
+	return RP_OK;
+}
+int rp_batch_add_gravity(rp_batch* b, double g) {
+	if (!b) return RP_ERR_ARG;
+	b->scene.add_gravity(g);
+	b->forces_dirty = true;
+	return RP_OK;
+}
+
+static int flush_forces(rp_batch* b) {
+	if (!b->forces_dirty) return RP_OK;
+	// the copies are stream-ordered; the host vectors stay alive in b->scene and pageable copies are staged by the runtime
+	RP_CUDA(cudaMemcpyAsync(b->force_dev, b->scene.force.data(), sizeof(V3) * b->d.NB, cudaMemcpyHostToDevice, b->stream));
+	RP_CUDA(cudaMemcpyAsync(b->torque_dev, b->scene.torque.data(), sizeof(V3) * b->d.NB, cudaMemcpyHostToDevice, b->stream));
+	b->forces_dirty = false;
+	return RP_OK;
+}
+
+// the per-frame prologue: broadphase, islands + sleeping, dependency-level schedule (pbd.cpp:474-533)
+static void enqueue_prologue(rp_batch* b, double dt, int collisions) {
+	const DevView& d = b->d;
+	dim3 rows((d.NB + 127) / 128, d.W);
+	k_broad_rows<false><<<rows, 128, 0, b->stream>>>(d);
+	k_broad_scan<<<d.W, 256, 0, b->stream>>>(d);
+	k_broad_rows<true><<<rows, 128, 0, b->stream>>>(d);
+	k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
+	k_schedule<<<(d.W + 63) / 64, 64, 0, b->stream>>>(d, collisions);
+}
+
+static void enqueue_integrate(rp_batch* b, double h) {
+	const DevView& d = b->d;
+	const size_t WB = (size_t)d.W * d.NB;
+	k_integrate<<<(unsigned int)((WB + 127) / 128), 128, 0, b->stream>>>(d, h);
+}
+static void enqueue_narrow(rp_batch* b) {
+	const DevView& d = b->d;
+	k_gjk<<<dim3(b->gjk_chunks, d.W), 128, 0, b->stream>>>(d);
+	k_manifold<<<b->sm_count * 4, 128, 0, b->stream>>>(d);
+}
+static void enqueue_solve(rp_batch* b, double h, uint32_t iters, int collisions) {
+	k_solve<<<b->d.W, b->solve_threads, 0, b->stream>>>(b->d, h, (int)iters, collisions);
+}
+
+static void enqueue_frame(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int collisions) {
+	const double h = dt / substeps;  // pbd.cpp:472
+	enqueue_prologue(b, dt, collisions);
+	for (uint32_t s = 0; s < substeps; ++s) {
+		enqueue_integrate(b, h);
+		if (collisions) enqueue_narrow(b);
+		enqueue_solve(b, h, iters, collisions);
+	}
+	k_count_frame<<<1, 1, 0, b->stream>>>(b->d);
+}
+
+int rp_batch_step(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int collisions) {
+	if (!b || substeps == 0) return fail(RP_ERR_ARG, "rp_batch_step: bad argument");
+	if (dt <= 0.0) return RP_OK;  // pbd.cpp:471
+	RP_CUDA(cudaSetDevice(b->device));
+	int rc = flush_forces(b);
+	if (rc) return rc;
+	GraphKey key;
+	key.dt = dt; key.substeps = substeps; key.iters = iters; key.collisions = collisions ? 1 : 0;
+	if (!b->have_graph || !(b->graph_key == key)) {
+		if (b->graph_exec) cudaGraphExecDestroy(b->graph_exec);
+		if (b->graph) cudaGraphDestroy(b->graph);
+		b->graph_exec = 0;
+		b->graph = 0;
+		b->have_graph = false;
+		RP_CUDA(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+		enqueue_frame(b, dt, substeps, iters, key.collisions);
+		cudaError_t e = cudaStreamEndCapture(b->stream, &b->graph);
+		if (e != cudaSuccess) return fail(RP_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+		RP_CUDA(cudaGraphInstantiate(&b->graph_exec, b->graph, 0));
+		b->graph_key = key;
+		b->have_graph = true;
+	}
+	RP_CUDA(cudaGraphLaunch(b->graph_exec, b->stream));
+	return RP_OK;
+}
+
+int rp_batch_sync(rp_batch* b) {
+	if (!b) return RP_ERR_ARG;
+	RP_CUDA(cudaSetDevice(b->device));
+	RP_CUDA(cudaStreamSynchronize(b->stream));
+	RP_CUDA(cudaGetLastError());
+	return RP_OK;
+}
+
+int rp_batch_run(rp_batch* b, uint32_t frames, double dt, uint32_t substeps, uint32_t iters, int collisions, float* ms_out) {
+	if (!b) return RP_ERR_ARG;
+	RP_CUDA(cudaSetDevice(b->device));
+	RP_CUDA(cudaEventRecord(b->ev0, b->stream));
+	for (uint32_t f = 0; f < frames; ++f) {
+		int rc = rp_batch_step(b, dt, substeps, iters, collisions);
+		if (rc) return rc;
+	}
+	RP_CUDA(cudaEventRecord(b->ev1, b->stream));
+	RP_CUDA(cudaEventSynchronize(b->ev1));
+	float ms = 0.f;
+	RP_CUDA(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+	if (ms_out) *ms_out = ms;
+	return RP_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------- state
+static int upload_impl(rp_batch* b, uint32_t first, uint32_t n, const double* host, int broadcast) {
+	if (!b || !host || first + n > (uint32_t)b->d.W || n == 0) return fail(RP_ERR_ARG, "state transfer: bad range");
+	RP_CUDA(cudaSetDevice(b->device));
+	const size_t nrec = (size_t)(broadcast ? 1 : n) * b->d.NB;
+	RP_CUDA(cudaMemcpyAsync(b->rec_dev, host, nrec * RP_STATE_STRIDE * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+	const size_t total = (size_t)n * b->d.NB;
+	k_unpack_state<<<(unsigned int)((total + 127) / 128), 128, 0, b->stream>>>(b->d, b->rec_dev, (int)first, (int)n, broadcast);
+	RP_CUDA(cudaGetLastError());
+	return RP_OK;
+}
+
+int rp_batch_upload_state(rp_batch* b, uint32_t first, uint32_t n, const double* host) {
+	int rc = upload_impl(b, first, n, host, 0);
+	if (rc) return rc;
+	RP_CUDA(cudaStreamSynchronize(b->stream));  // the caller may reuse `host` right away
+	return RP_OK;
+}
+int rp_batch_broadcast_state(rp_batch* b, const double* host_one_world) {
+	if (!b) return RP_ERR_ARG;
+	int rc = upload_impl(b, 0, (uint32_t)b->d.W, host_one_world, 1);
+	if (rc) return rc;
+	RP_CUDA(cudaStreamSynchronize(b->stream));
+	return RP_OK;
+}
+static int download_async(rp_batch* b, uint32_t first, uint32_t n, double* host) {
+	if (!b || !host || first + n > (uint32_t)b->d.W || n == 0) return fail(RP_ERR_ARG, "state transfer: bad range");
+	RP_CUDA(cudaSetDevice(b->device));
+	const size_t total = (size_t)n * b->d.NB;
+	k_pack_state<<<(unsigned int)((total + 127) / 128), 128, 0, b->stream>>>(b->d, b->rec_dev, (int)first, (int)n);
+	RP_CUDA(cudaGetLastError());
+	RP_CUDA(cudaMemcpyAsync(host, b->rec_dev, total * RP_STATE_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+	return RP_OK;
+}
+int rp_batch_download_state(rp_batch* b, uint32_t first, uint32_t n, double* host) {
+	int rc = download_async(b, first, n, host);
+	if (rc) return rc;
+	RP_CUDA(cudaStreamSynchronize(b->stream));
+	return RP_OK;
+}
+
+int rp_batch_step_host(rp_batch* b, const double* in, double* out, double dt, uint32_t substeps, uint32_t iters, int collisions) {
+	if (!b) return RP_ERR_ARG;
+	int rc;
+	if (in && (rc = upload_impl(b, 0, (uint32_t)b->d.W, in, 0))) return rc;
+	if ((rc = rp_batch_step(b, dt, substeps, iters, collisions))) return rc;
+	if (out && (rc = download_async(b, 0, (uint32_t)b->d.W, out))) return rc;
+	RP_CUDA(cudaStreamSynchronize(b->stream));
+	return RP_OK;
+}
+
+int rp_batch_get_status(rp_batch* b, int32_t* out) {
+	if (!b || !out) return RP_ERR_ARG;
+	RP_CUDA(cudaSetDevice(b->device));
+	RP_CUDA(cudaMemcpyAsync(out, b->d.status, sizeof(int) * b->d.W, cudaMemcpyDeviceToHost, b->stream));
+	RP_CUDA(cudaStreamSynchronize(b->stream));
+	return RP_OK;
+}
+int rp_batch_get_counters(rp_batch* b, uint64_t out8[8]) {
+	if (!b || !out8) return RP_ERR_ARG;
+	RP_CUDA(cudaSetDevice(b->device));
+	RP_CUDA(cudaMemcpyAsync(out8, b->d.counters, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, b->stream));
+	RP_CUDA(cudaStreamSynchronize(b->stream));
+	return RP_OK;
+}
+
+}  // extern "C"
+
+// --------------------------------------------------------------------------------------------- parity instrumentation
+template <class T>
+static int fetch(rp_batch* b, std::vector<T>& host, const T* dev, size_t n) {
+	host.resize(n);
+	if (n) RP_CUDA(cudaMemcpyAsync(host.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost, b->stream));
+	RP_CUDA(cudaStreamSynchronize(b->stream));
+	return RP_OK;
+}
+
+extern "C" {
+
+int rp_batch_broad_pairs(rp_batch* b, uint32_t world, uint32_t* pairs_out, uint32_t max_pairs, uint32_t* n_out) {
+	if (!b || world >= (uint32_t)b->d.W || !n_out) return RP_ERR_ARG;
+	RP_CUDA(cudaSetDevice(b->device));
+	const DevView& d = b->d;
+	dim3 rows((d.NB + 127) / 128, d.W);
+	k_broad_rows<false><<<rows, 128, 0, b->stream>>>(d);
+	k_broad_scan<<<d.W, 256, 0, b->stream>>>(d);
+	k_broad_rows<true><<<rows, 128, 0, b->stream>>>(d);
+	RP_CUDA(cudaGetLastError());
+	std::vector<int> np;
+	int rc = fetch(b, np, d.n_pairs + world, 1);
+	if (rc) return rc;
+	std::vector<PairRec> pr;
+	if ((rc = fetch(b, pr, d.pairs + (size_t)world * d.max_pairs, (size_t)np[0]))) return rc;
+	uint32_t n = 0;
+	for (int i = 0; i < np[0]; ++i) {
+		if (i > 0 && pr[i].a == pr[i - 1].a && pr[i].b == pr[i - 1].b) continue;  // collider pairs of one body pair
+		if (n < max_pairs && pairs_out) {
+			pairs_out[2 * n] = (uint32_t)pr[i].a;
+			pairs_out[2 * n + 1] = (uint32_t)pr[i].b;
+		}
+		++n;
+	}
+	*n_out = n;
+	return RP_OK;
+}
+
+int rp_batch_step_logged(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int collisions, uint32_t world, uint32_t* calls_out,
+	uint32_t max_calls, double* contacts_out, uint32_t max_contacts, uint32_t* n_calls, uint32_t* n_contacts) {
+	if (!b || substeps == 0 || world >= (uint32_t)b->d.W || !n_calls || !n_contacts) return fail(RP_ERR_ARG, "rp_batch_step_logged: bad argument");
+	*n_calls = 0;
+	*n_contacts = 0;
+	if (dt <= 0.0) return RP_OK;
+	RP_CUDA(cudaSetDevice(b->device));
+	int rc = flush_forces(b);
+	if (rc) return rc;
+	DevView& d = b->d;
+	d.dbg_world = (int)world;
+	const double h = dt / substeps;
+	enqueue_prologue(b, dt, collisions ? 1 : 0);
+	RP_CUDA(cudaGetLastError());
+	std::vector<int> np, active, ccnt, coff;
+	std::vector<PairRec> pr;
+	std::vector<BodyStatic> bs;
+	std::vector<V3> normals, pts;
+	if ((rc = fetch(b, np, d.n_pairs + world, 1))) return rc;
+	if ((rc = fetch(b, pr, d.pairs + (size_t)world * d.max_pairs, (size_t)np[0]))) return rc;
+	if ((rc = fetch(b, active, d.active + (size_t)world * d.NB, (size_t)d.NB))) return rc;
+	if ((rc = fetch(b, bs, d.bstat, (size_t)d.NB))) return rc;
+	uint32_t nc = 0, nk = 0;
+	for (uint32_t s = 0; s < substeps; ++s) {
+		enqueue_integrate(b, h);
+		if (collisions) {
+			enqueue_narrow(b);
+			RP_CUDA(cudaGetLastError());
+			const size_t base = (size_t)world * d.max_pairs;
+			if ((rc = fetch(b, ccnt, d.pair_ccnt + base, (size_t)np[0]))) return rc;
+			if ((rc = fetch(b, coff, d.pair_coff + base, (size_t)np[0]))) return rc;
+			if ((rc = fetch(b, normals, d.pair_normal + base, (size_t)np[0]))) return rc;
+			if ((rc = fetch(b, pts, d.dbg_points, 2 * (size_t)d.max_contacts))) return rc;
+			for (int i = 0; i < np[0]; ++i) {
+				const PairRec& p = pr[i];
+				if ((bs[p.a].fixed || !active[p.a]) && (bs[p.b].fixed || !active[p.b])) continue;
+				bool first = !(i > 0 && pr[i - 1].a == p.a && pr[i - 1].b == p.b);
+				if (first) {
+					if (nc < max_calls && calls_out) {
+						calls_out[4 * nc] = (uint32_t)p.a; calls_out[4 * nc + 1] = (uint32_t)p.b;
+						calls_out[4 * nc + 2] = 0; calls_out[4 * nc + 3] = nk;
+					}
+					++nc;
+				}
+				for (int k = 0; k < ccnt[i]; ++k) {
+					if (nk < max_contacts && contacts_out) {
+						double* o = contacts_out + 9 * (size_t)nk;
+						const V3& p1 = pts[2 * (coff[i] + k)];
+						const V3& p2 = pts[2 * (coff[i] + k) + 1];
+						o[0] = p1.x; o[1] = p1.y; o[2] = p1.z; o[3] = p2.x; o[4] = p2.y; o[5] = p2.z;
+						o[6] = normals[i].x; o[7] = normals[i].y; o[8] = normals[i].z;
+					}
+					++nk;
+				}
+				if (nc - 1 < max_calls && calls_out) calls_out[4 * (nc - 1) + 2] += (uint32_t)ccnt[i];
+			}
+		}
+		enqueue_solve(b, h, iters, collisions ? 1 : 0);
+	}
+	k_count_frame<<<1, 1, 0, b->stream>>>(d);
+	RP_CUDA(cudaGetLastError());
+	RP_CUDA(cudaStreamSynchronize(b->stream));
+	d.dbg_world = -1;
+	*n_calls = nc;
+	*n_contacts = nk;
+	return RP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// rp_device.cuh -- device data model of a batch (n_worlds instances of one scene template in HBM) and the kernels of
+// the XPBD frame step. One launch works on ALL worlds; the per-substep sequence is
+//   k_integrate -> k_gjk -> k_manifold -> k_solve
+// preceded once per frame by k_broad_count / k_broad_scan / k_broad_write / k_islands / k_schedule
+// (pbd_simulate_with_constraints, src/physics/pbd.cpp:468-747). See DESIGN.md for the layout and the roofline of each.
+#ifndef RP_DEVICE_CUH
+#define RP_DEVICE_CUH
+
+#include <cuda_runtime.h>
+
+#include "rp_solve.h"
+
+namespace rp {
+
+// per-world, per-body dynamic state (entity.h:21-46), AoS: the solver gathers whole bodies by index
+struct BodyDyn {
+	double x[3], q[4], v[3], w[3], px[3], pq[4], pv[3], pw[3];
+};
+// per-body static parameters, shared by all worlds (template)
+struct BodyStatic {
+	double inv_mass;
+	M3 inertia, inv_inertia;
+	double mu_s, mu_d, rest, radius;
+	int fixed, col0, ncol, pad;
+};
+struct PairRec {  // one broadphase pair, expanded to collider granularity: bodies a < b, global collider indices ca, cb
+	int a, b, ca, cb;
+};
+struct HitRec {  // GJK verdict "colliding": work item of k_manifold
+	int world, pair;
+	V3 sa, sb, sc, sd;
+};
+
+enum { CNT_PAIR_TESTS = 0, CNT_HITS = 1, CNT_CONTACTS = 2, CNT_BROAD_PAIRS = 3, CNT_LEVELS = 4, CNT_FRAMES = 5 };
+
+struct DevView {
+	int W, NB, NC, NJ, TV, TN;
+	int max_pairs, max_contacts, max_units;
+	double lin_sleep, ang_sleep, sleep_time;
+	// template
+	const BodyStatic* bstat;
+	const ColliderDesc* cols;
+	HullPool pool;
+	const Joint* joints;
+	const V3* force;
+	const V3* torque;
+	// per world
+	BodyDyn* dyn;        // [W][NB]
+	int* active;         // [W][NB]
+	double* deact;       // [W][NB]
+	V3* tv;              // [W][TV] transformed vertices (sphere: centre)
+	V3* tn;              // [W][TN] transformed face normals
+	PairRec* pairs;      // [W][max_pairs]
+	int* n_pairs;        // [W]
+	int* row_off;        // [W][NB] broadphase row counts -> offsets
+	int* label;          // [W][NB] island labels
+	int* isl_flag;       // [W][NB] island "all members may sleep"
+	int* last_level;     // [W][NB] schedule scratch
+	int* unit_level;     // [W][max_units]
+	int* sched;          // [W][max_units] units sorted by dependency level (stable)
+	int* level_ptr;      // [W][max_units + 2]
+	int* n_levels;       // [W]
+	HitRec* hits;        // [W * max_pairs]
+	unsigned int* hit_count;
+	V3* pair_normal;     // [W][max_pairs]
+	int* pair_coff;      // [W][max_pairs]
+	int* pair_ccnt;      // [W][max_pairs]
+	Contact* contacts;   // [W][max_contacts]
+	int* n_contacts;     // [W]
+	JointLambda* lambdas;  // [W][NJ]
+	int* status;         // [W]
+	unsigned long long* counters;
+	// parity instrumentation (rp_batch_step_logged)
+	int dbg_world;
+	V3* dbg_points;      // [max_contacts][2]
+};
+
+}  // namespace rp
+#endif

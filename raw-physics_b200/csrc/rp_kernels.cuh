@@ -1,0 +1,568 @@
+// rp_kernels.cuh -- CUDA kernels of the frame step (sm_100a). Included once, by rp_batch.cu.
+//
+// Arithmetic is FP64 and is the shared core (rp_math.h ... rp_solve.h) compiled with --fmad=false; the kernels only
+// decide WHO computes WHAT and WHEN. Order sensitivity of the reference's sequential Gauss-Seidel is preserved by the
+// dependency-level schedule built in k_schedule: two constraints commute exactly when they share no non-fixed body
+// (fixed bodies are never written, pbd_base_constraints.cpp:73-103), so running each level's units in parallel and the
+// levels in sequence reproduces the sequential result bit for bit.
+#ifndef RP_KERNELS_CUH
+#define RP_KERNELS_CUH
+
+#include "rp_device.cuh"
+
+namespace rp {
+
+// ------------------------------------------------------------------------------------------------------ body access
+__device__ __forceinline__ V3 ld3(const double* p) { return v3(p[0], p[1], p[2]); }
+__device__ __forceinline__ Q4 ld4(const double* p) { return q4(p[0], p[1], p[2], p[3]); }
+__device__ __forceinline__ void st3(double* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+__device__ __forceinline__ void st4(double* p, Q4 q) { p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w; }
+
+__device__ __forceinline__ void load_static(Body& b, const BodyStatic& s) {
+	b.inv_mass = s.inv_mass;
+	b.inertia = s.inertia;
+	b.inv_inertia = s.inv_inertia;
+	b.mu_s = s.mu_s; b.mu_d = s.mu_d; b.rest = s.rest;
+	b.fixed = s.fixed;
+}
+__device__ __forceinline__ void load_dyn(Body& b, const BodyDyn& d) {
+	b.x = ld3(d.x); b.q = ld4(d.q); b.v = ld3(d.v); b.w = ld3(d.w);
+	b.px = ld3(d.px); b.pq = ld4(d.pq); b.pv = ld3(d.pv); b.pw = ld3(d.pw);
+}
+
+// ------------------------------------------------------------------------------------------------------- broadphase
+// broad_get_collision_pairs (broad.cpp:6-29): all i < j with |x_i - x_j| <= r_i + r_j + 0.1, emitted in (i, j) order.
+// Row i is one thread; all threads of a CTA walk j together so the position loads broadcast.
+template <bool WRITE>
+__global__ void __launch_bounds__(128) k_broad_rows(DevView d) {
+	const int w = blockIdx.y;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int row0 = blockIdx.x * blockDim.x;
+	const BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
+	V3 xi = v3(0.0, 0.0, 0.0);
+	double ri = 0.0;
+	int ci0 = 0, nci = 0;
+	if (i < d.NB) {
+		xi = ld3(dyn[i].x);
+		ri = d.bstat[i].radius;
+		ci0 = d.bstat[i].col0;
+		nci = d.bstat[i].ncol;
+	}
+	int count = 0;
+	int out = 0;
+	PairRec* pairs = d.pairs + (size_t)w * d.max_pairs;
+	if (WRITE && i < d.NB) out = d.row_off[(size_t)w * d.NB + i];
+	for (int j = row0 + 1; j < d.NB; ++j) {
+		if (i < d.NB && j > i) {
+			V3 xj = ld3(dyn[j].x);
+			double dist = length(sub(xi, xj));
+			double maxd = ri + d.bstat[j].radius + 0.1;
+			if (dist <= maxd) {
+				int ncj = d.bstat[j].ncol;
+				if (WRITE) {
+					int cj0 = d.bstat[j].col0;
+					for (int a = 0; a < nci; ++a) {
+						for (int b = 0; b < ncj; ++b) {
+							if (out < d.max_pairs) {
+								PairRec pr;
+								pr.a = i; pr.b = j; pr.ca = ci0 + a; pr.cb = cj0 + b;
+								pairs[out] = pr;
+							}
+							++out;
+						}
+					}
+				} else {
+					count += nci * ncj;
+				}
+			}
+		}
+	}
+	if (!WRITE && i < d.NB) d.row_off[(size_t)w * d.NB + i] = count;
+}
+
+// exclusive scan of the row counts of one world (one CTA per world)
+__global__ void __launch_bounds__(256) k_broad_scan(DevView d) {
+	const int w = blockIdx.x;
+	int* row = d.row_off + (size_t)w * d.NB;
+	__shared__ int warp_sums[8];
+	__shared__ int carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	for (int base = 0; base < d.NB; base += blockDim.x) {
+		int i = base + threadIdx.x;
+		int v = i < d.NB ? row[i] : 0;
+		int x = v;
+		for (int o = 1; o < 32; o <<= 1) {
+			int y = __shfl_up_sync(0xffffffffu, x, o);
+			if (lane >= o) x += y;
+		}
+		if (lane == 31) warp_sums[wid] = x;
+		__syncthreads();
+		int prefix = carry;
+		for (int k = 0; k < wid; ++k) prefix += warp_sums[k];
+		if (i < d.NB) row[i] = prefix + x - v;
+		__syncthreads();
+		if (threadIdx.x == blockDim.x - 1) carry = prefix + x;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		int total = carry;
+		if (total > d.max_pairs) {
+			atomicOr(&d.status[w], ST_PAIR_CAPACITY);
+			total = d.max_pairs;
+		}
+		d.n_pairs[w] = total;
+		atomicAdd(&d.counters[CNT_BROAD_PAIRS], (unsigned long long)total);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------- islands + sleeping
+// broad_collect_simulation_islands (broad.cpp:70-116) + the sleep bookkeeping of pbd.cpp:476-506. Islands are the
+// connected components of {pairs, external constraints} restricted to non-fixed bodies; the result does not depend on
+// the order in which unions happen, so min-label propagation replaces the reference's union-find. One CTA per world.
+__global__ void __launch_bounds__(256) k_islands(DevView d, double dt) {
+	const int w = blockIdx.x;
+	int* label = d.label + (size_t)w * d.NB;
+	int* flag = d.isl_flag + (size_t)w * d.NB;
+	BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
+	int* active = d.active + (size_t)w * d.NB;
+	double* deact = d.deact + (size_t)w * d.NB;
+	const PairRec* pairs = d.pairs + (size_t)w * d.max_pairs;
+	const int np = d.n_pairs[w];
+	__shared__ int changed;
+	for (int b = threadIdx.x; b < d.NB; b += blockDim.x) {
+		label[b] = b;
+		flag[b] = 1;
+	}
+	__syncthreads();
+	for (;;) {
+		if (threadIdx.x == 0) changed = 0;
+		__syncthreads();
+		for (int e = threadIdx.x; e < np + d.NJ; e += blockDim.x) {
+			int a, b;
+			if (e < np) {
+				a = pairs[e].a; b = pairs[e].b;
+			} else {
+				a = d.joints[e - np].e1; b = d.joints[e - np].e2;
+			}
+			if (d.bstat[a].fixed || d.bstat[b].fixed) continue;
+			int la = label[a], lb = label[b];
+			if (la != lb) {
+				int m = la < lb ? la : lb;
+				atomicMin(&label[a], m);
+				atomicMin(&label[b], m);
+				changed = 1;
+			}
+		}
+		__syncthreads();
+		int c = changed;
+		__syncthreads();
+		if (!c) break;
+	}
+	for (int b = threadIdx.x; b < d.NB; b += blockDim.x) {
+		if (d.bstat[b].fixed) continue;
+		double lv = length(ld3(dyn[b].v));
+		double av = length(ld3(dyn[b].w));
+		double t = deact[b];
+		if (lv < d.lin_sleep && av < d.ang_sleep) t += dt;
+		else t = 0.0;
+		deact[b] = t;
+		if (t < d.sleep_time) flag[label[b]] = 0;
+	}
+	__syncthreads();
+	for (int b = threadIdx.x; b < d.NB; b += blockDim.x) {
+		if (d.bstat[b].fixed) continue;
+		active[b] = flag[label[b]] ? 0 : 1;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------ level schedule
+// Units of the Gauss-Seidel sweep in the reference's array order: the external constraints first (copy_constraints
+// output is the head of the array, pbd.cpp:580), then the broadphase (collider-)pairs in pair order, each pair standing
+// for its whole manifold (pbd.cpp:584-611). level(u) = 1 + max(level of the previous unit touching either of u's
+// NON-FIXED bodies). One thread per world, once per frame; a stable counting sort by level gives the execution order.
+__global__ void __launch_bounds__(64) k_schedule(DevView d, int collisions) {
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= d.W) return;
+	int* last = d.last_level + (size_t)w * d.NB;
+	int* ulevel = d.unit_level + (size_t)w * d.max_units;
+	int* sched = d.sched + (size_t)w * d.max_units;
+	int* lptr = d.level_ptr + (size_t)w * (d.max_units + 2);
+	const int* active = d.active + (size_t)w * d.NB;
+	const PairRec* pairs = d.pairs + (size_t)w * d.max_pairs;
+	const int np = collisions ? d.n_pairs[w] : 0;
+	const int nu = d.NJ + np;
+	for (int b = 0; b < d.NB; ++b) last[b] = 0;
+	int nl = 0;
+	for (int u = 0; u < nu; ++u) {
+		int a, b;
+		if (u < d.NJ) {
+			a = d.joints[u].e1; b = d.joints[u].e2;
+		} else {
+			a = pairs[u - d.NJ].a; b = pairs[u - d.NJ].b;
+			// pbd.cpp:594: nothing to do when both sides are fixed or asleep
+			if ((d.bstat[a].fixed || !active[a]) && (d.bstat[b].fixed || !active[b])) {
+				ulevel[u] = 0;
+				continue;
+			}
+		}
+		int fa = d.bstat[a].fixed, fb = d.bstat[b].fixed;
+		int la = fa ? 0 : last[a], lb = fb ? 0 : last[b];
+		int lvl = 1 + (la > lb ? la : lb);
+		if (!fa) last[a] = lvl;
+		if (!fb) last[b] = lvl;
+		ulevel[u] = lvl;
+		if (lvl > nl) nl = lvl;
+	}
+	for (int l = 0; l <= nl + 1; ++l) lptr[l] = 0;
+	for (int u = 0; u < nu; ++u) {
+		int l = ulevel[u];
+		if (l > 0) lptr[l + 1] += 1;
+	}
+	// lptr[l] = first slot of level l (levels are 1-based; lptr[1] = 0)
+	for (int l = 2; l <= nl + 1; ++l) lptr[l] += lptr[l - 1];
+	for (int u = 0; u < nu; ++u) {
+		int l = ulevel[u];
+		if (l > 0) sched[lptr[l]++] = u;   // after this loop lptr[l] = END of level l = start of level l + 1
+	}
+	// shift back so that level l spans [lptr[l-1], lptr[l]) with lptr[0] = 0
+	lptr[0] = 0;
+	d.n_levels[w] = nl;
+	atomicAdd(&d.counters[CNT_LEVELS], (unsigned long long)nl);
+}
+
+// ---------------------------------------------------------------------------------------- integrate + collider update
+// pbd.cpp:537-577 (integration) and collider.cpp:409-445 (collider_update) for one body per thread. The reference
+// re-transforms both colliders of every pair every substep (39 % of its time); the same pose gives the same result,
+// so once per body per substep is exactly equivalent.
+__global__ void __launch_bounds__(128) k_integrate(DevView d, double h) {
+	const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid == 0) *d.hit_count = 0u;
+	if (gid >= (size_t)d.W * d.NB) return;
+	const int w = (int)(gid / d.NB), b = (int)(gid % d.NB);
+	if (b == 0) d.n_contacts[w] = 0;
+	if (b < d.NJ) {  // copy_constraints resets every lambda each substep (pbd.cpp:426-462)
+		for (int j = b; j < d.NJ; j += d.NB) {
+			JointLambda z;
+			z.a = z.b = z.c = 0.0;
+			d.lambdas[(size_t)w * d.NJ + j] = z;
+		}
+	}
+	const BodyStatic& s = d.bstat[b];
+	BodyDyn& dd = d.dyn[gid];
+	Body body;
+	load_static(body, s);
+	body.x = ld3(dd.x); body.q = ld4(dd.q); body.v = ld3(dd.v); body.w = ld3(dd.w);
+	body.active = d.active[gid];
+	integrate(body, h, d.force[b], d.torque[b]);
+	st3(dd.px, body.px); st4(dd.pq, body.pq);
+	if (!(body.fixed || !body.active)) {
+		st3(dd.x, body.x); st4(dd.q, body.q); st3(dd.v, body.v); st3(dd.w, body.w);
+	}
+	Pose34 M = model_matrix(body.q, body.x);
+	V3* tv = d.tv + (size_t)w * d.TV;
+	V3* tn = d.tn + (size_t)w * d.TN;
+	for (int c = s.col0; c < s.col0 + s.ncol; ++c) {
+		const ColliderDesc cd = d.cols[c];
+		if (cd.type == SHAPE_SPHERE) {
+			tv[cd.tv0] = body.x;
+		} else {
+			const HullTopo t = d.pool.hulls[cd.hull];
+			for (int k = 0; k < t.nv; ++k) tv[cd.tv0 + k] = transform_point(M, d.pool.verts[t.vert0 + k]);
+			for (int k = 0; k < t.nf; ++k) tn[cd.tn0 + k] = transform_normal(M, d.pool.normals[t.face0 + k]);
+		}
+	}
+}
+
+// ----------------------------------------------------------------------------------------------------- narrowphase 1
+// One thread per (world, collider pair): the pbd.cpp:594 skip rule, then sphere-sphere or boolean GJK
+// (collider.cpp:523-547). Colliding pairs are appended to the global hit list for k_manifold.
+__global__ void __launch_bounds__(128) k_gjk(DevView d) {
+	const int w = blockIdx.y;
+	const int np = d.n_pairs[w];
+	const int* active = d.active + (size_t)w * d.NB;
+	const V3* tv = d.tv + (size_t)w * d.TV;
+	const V3* tn = d.tn + (size_t)w * d.TN;
+	const int lane = threadIdx.x & 31;
+	int tested = 0;
+	// whole warps iterate together (np rounded up per warp) so the ballot below always sees converged lanes
+	for (int p0 = blockIdx.x * blockDim.x; p0 < np; p0 += gridDim.x * blockDim.x) {
+		const int p = p0 + threadIdx.x;
+		bool hit = false;
+		Simplex s;
+		s.a = s.b = s.c = s.d = v3(0.0, 0.0, 0.0);
+		size_t pg = 0;
+		if (p < np) {
+			pg = (size_t)w * d.max_pairs + p;
+			d.pair_ccnt[pg] = 0;
+			const PairRec pr = d.pairs[pg];
+			if (!((d.bstat[pr.a].fixed || !active[pr.a]) && (d.bstat[pr.b].fixed || !active[pr.b]))) {
+				Shape A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
+				Shape B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
+				int st = 0;
+				if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
+					V3 n;
+					double depth;
+					hit = sphere_sphere(A, B, &n, &depth);
+				} else {
+					hit = gjk(A, B, &s, &st, 0);
+				}
+				if (st) atomicOr(&d.status[w], st);
+				++tested;
+			}
+		}
+		// warp-aggregated append to the global hit list
+		const unsigned int mask = __ballot_sync(0xffffffffu, hit);
+		if (mask) {
+			const int leader = __ffs(mask) - 1;
+			unsigned int base = 0;
+			if (lane == leader) base = atomicAdd(d.hit_count, (unsigned int)__popc(mask));
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (hit) {
+				HitRec hr;
+				hr.world = w; hr.pair = p;
+				hr.sa = s.a; hr.sb = s.b; hr.sc = s.c; hr.sd = s.d;
+				d.hits[base + __popc(mask & ((1u << lane) - 1u))] = hr;
+			}
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) tested += __shfl_down_sync(0xffffffffu, tested, o);
+	if (lane == 0 && tested) atomicAdd(&d.counters[CNT_PAIR_TESTS], (unsigned long long)tested);
+}
+
+// ----------------------------------------------------------------------------------------------------- narrowphase 2
+struct StageSink {
+	V3* stage;
+	int n, cap;
+	__device__ __forceinline__ void operator()(V3 p1, V3 p2) {
+		if (n < cap) {
+			stage[2 * n] = p1;
+			stage[2 * n + 1] = p2;
+		}
+		++n;
+	}
+};
+
+struct ManifoldScratch {
+	union {
+		EpaScratch epa;
+		struct {
+			ClipScratch clip;
+			V3 stage[2 * RP_CLIP_MAX_POINTS];
+		} m;
+	};
+};
+
+// One thread per colliding collider pair: EPA (epa.cpp:118), manifold (clipping.cpp:343), contact -> constraint
+// (pbd.cpp:408-424). The pair's contacts get a contiguous run in the world's contact buffer (allocation order between
+// pairs is irrelevant: the solver walks pairs, not the buffer).
+__global__ void __launch_bounds__(128) k_manifold(DevView d) {
+	const unsigned int nh = *d.hit_count;
+	ManifoldScratch sc;
+	int made = 0;
+	for (unsigned int hi = blockIdx.x * blockDim.x + threadIdx.x; hi < nh; hi += gridDim.x * blockDim.x) {
+		const HitRec hr = d.hits[hi];
+		const int w = hr.world;
+		const size_t pg = (size_t)w * d.max_pairs + hr.pair;
+		const PairRec pr = d.pairs[pg];
+		const V3* tv = d.tv + (size_t)w * d.TV;
+		const V3* tn = d.tn + (size_t)w * d.TN;
+		Shape A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
+		Shape B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
+		V3 normal;
+		double depth;
+		int st = 0;
+		bool ok;
+		if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
+			ok = sphere_sphere(A, B, &normal, &depth);
+		} else {
+			Simplex s;
+			s.a = hr.sa; s.b = hr.sb; s.c = hr.sc; s.d = hr.sd;
+			s.num = 4;
+			ok = epa(A, B, s, sc.epa, &normal, &depth, &st, 0);
+		}
+		int n = 0;
+		if (ok) {
+			StageSink sink;
+			sink.stage = sc.m.stage;
+			sink.n = 0;
+			sink.cap = RP_CLIP_MAX_POINTS;
+			manifold(A, B, normal, depth, sc.m.clip, &st, sink);
+			n = sink.n;
+			if (n > sink.cap) {
+				st |= ST_CLIP_CAPACITY;
+				n = sink.cap;
+			}
+		}
+		if (n > 0) {
+			int off = atomicAdd(&d.n_contacts[w], n);
+			if (off + n > d.max_contacts) {
+				st |= ST_CONTACT_CAPACITY;
+				n = d.max_contacts - off;
+				if (n < 0) n = 0;
+			}
+			const BodyDyn& da = d.dyn[(size_t)w * d.NB + pr.a];
+			const BodyDyn& db = d.dyn[(size_t)w * d.NB + pr.b];
+			Body b1, b2;
+			b1.x = ld3(da.x); b1.q = ld4(da.q);
+			b2.x = ld3(db.x); b2.q = ld4(db.q);
+			Contact* out = d.contacts + (size_t)w * d.max_contacts + off;
+			for (int k = 0; k < n; ++k) {
+				out[k] = make_contact(b1, b2, sc.m.stage[2 * k], sc.m.stage[2 * k + 1]);
+				if (w == d.dbg_world) {
+					d.dbg_points[2 * (off + k)] = sc.m.stage[2 * k];
+					d.dbg_points[2 * (off + k) + 1] = sc.m.stage[2 * k + 1];
+				}
+			}
+			d.pair_normal[pg] = normal;
+			d.pair_coff[pg] = off;
+			d.pair_ccnt[pg] = n;
+			made += n;
+		}
+		if (st) atomicOr(&d.status[w], st);
+	}
+	for (int o = 16; o > 0; o >>= 1) made += __shfl_down_sync(0xffffffffu, made, o);
+	if ((threadIdx.x & 31) == 0 && made) atomicAdd(&d.counters[CNT_CONTACTS], (unsigned long long)made);
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&d.counters[CNT_HITS], (unsigned long long)nh);
+}
+
+// -------------------------------------------------------------------------------------------------------------- solve
+// One CTA per world. Positional Gauss-Seidel sweep(s) level by level (pbd.cpp:615-620), velocity derivation
+// (pbd.cpp:623-643), then the velocity pass over the contacts in the same level order (pbd.cpp:646-711).
+__global__ void k_solve(DevView d, double h, int iters, int collisions) {
+	const int w = blockIdx.x;
+	BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
+	const int* active = d.active + (size_t)w * d.NB;
+	const int* sched = d.sched + (size_t)w * d.max_units;
+	const int* lptr = d.level_ptr + (size_t)w * (d.max_units + 2);
+	const PairRec* pairs = d.pairs + (size_t)w * d.max_pairs;
+	const int nl = d.n_levels[w];
+	Contact* contacts = d.contacts + (size_t)w * d.max_contacts;
+	int st = 0;
+
+	for (int it = 0; it < iters; ++it) {
+		for (int l = 1; l <= nl; ++l) {
+			const int u0 = lptr[l - 1], u1 = lptr[l];
+			for (int k = u0 + threadIdx.x; k < u1; k += blockDim.x) {
+				const int u = sched[k];
+				if (u < d.NJ) {
+					const Joint j = d.joints[u];
+					Body b1, b2;
+					load_static(b1, d.bstat[j.e1]);
+					load_static(b2, d.bstat[j.e2]);
+					BodyDyn& d1 = dyn[j.e1];
+					BodyDyn& d2 = dyn[j.e2];
+					b1.x = ld3(d1.x); b1.q = ld4(d1.q);
+					b2.x = ld3(d2.x); b2.q = ld4(d2.q);
+					JointLambda lam = d.lambdas[(size_t)w * d.NJ + u];
+					solve_joint(j, lam, b1, b2, h, &st);
+					d.lambdas[(size_t)w * d.NJ + u] = lam;
+					if (!b1.fixed) { st3(d1.x, b1.x); st4(d1.q, b1.q); }
+					if (!b2.fixed) { st3(d2.x, b2.x); st4(d2.q, b2.q); }
+				} else if (collisions) {
+					const int p = u - d.NJ;
+					const size_t pg = (size_t)w * d.max_pairs + p;
+					const int cnt = d.pair_ccnt[pg];
+					if (cnt == 0) continue;
+					const PairRec pr = pairs[p];
+					const V3 normal = d.pair_normal[pg];
+					Contact* cs = contacts + d.pair_coff[pg];
+					Body b1, b2;
+					load_static(b1, d.bstat[pr.a]);
+					load_static(b2, d.bstat[pr.b]);
+					BodyDyn& d1 = dyn[pr.a];
+					BodyDyn& d2 = dyn[pr.b];
+					b1.x = ld3(d1.x); b1.q = ld4(d1.q); b1.px = ld3(d1.px); b1.pq = ld4(d1.pq);
+					b2.x = ld3(d2.x); b2.q = ld4(d2.q); b2.px = ld3(d2.px); b2.pq = ld4(d2.pq);
+					for (int c = 0; c < cnt; ++c) {
+						Contact ct = cs[c];
+						solve_contact(ct, normal, b1, b2, h, &st);
+						cs[c].lambda_n = ct.lambda_n;
+						cs[c].lambda_t = ct.lambda_t;
+					}
+					if (!b1.fixed) { st3(d1.x, b1.x); st4(d1.q, b1.q); }
+					if (!b2.fixed) { st3(d2.x, b2.x); st4(d2.q, b2.q); }
+				}
+			}
+			__syncthreads();
+		}
+	}
+
+	for (int b = threadIdx.x; b < d.NB; b += blockDim.x) {
+		Body body;
+		body.fixed = d.bstat[b].fixed;
+		body.active = active[b];
+		if (body.fixed || !body.active) continue;
+		BodyDyn& dd = dyn[b];
+		body.x = ld3(dd.x); body.q = ld4(dd.q); body.px = ld3(dd.px); body.pq = ld4(dd.pq);
+		body.v = ld3(dd.v); body.w = ld3(dd.w);
+		derive_velocity(body, h);
+		st3(dd.v, body.v); st3(dd.w, body.w); st3(dd.pv, body.pv); st3(dd.pw, body.pw);
+	}
+	__syncthreads();
+
+	if (collisions) {
+		for (int l = 1; l <= nl; ++l) {
+			const int u0 = lptr[l - 1], u1 = lptr[l];
+			for (int k = u0 + threadIdx.x; k < u1; k += blockDim.x) {
+				const int u = sched[k];
+				if (u < d.NJ) continue;  // the hinge branch of the velocity pass is an empty TODO (pbd.cpp:712-739)
+				const int p = u - d.NJ;
+				const size_t pg = (size_t)w * d.max_pairs + p;
+				const int cnt = d.pair_ccnt[pg];
+				if (cnt == 0) continue;
+				const PairRec pr = pairs[p];
+				const V3 normal = d.pair_normal[pg];
+				const Contact* cs = contacts + d.pair_coff[pg];
+				Body b1, b2;
+				load_static(b1, d.bstat[pr.a]);
+				load_static(b2, d.bstat[pr.b]);
+				BodyDyn& d1 = dyn[pr.a];
+				BodyDyn& d2 = dyn[pr.b];
+				b1.q = ld4(d1.q); b1.v = ld3(d1.v); b1.w = ld3(d1.w); b1.pv = ld3(d1.pv); b1.pw = ld3(d1.pw);
+				b2.q = ld4(d2.q); b2.v = ld3(d2.v); b2.w = ld3(d2.w); b2.pv = ld3(d2.pv); b2.pw = ld3(d2.pw);
+				for (int c = 0; c < cnt; ++c) {
+					const Contact ct = cs[c];
+					solve_contact_velocity(ct, normal, b1, b2, h);
+				}
+				if (!b1.fixed) { st3(d1.v, b1.v); st3(d1.w, b1.w); }
+				if (!b2.fixed) { st3(d2.v, b2.v); st3(d2.w, b2.w); }
+			}
+			__syncthreads();
+		}
+	}
+	if (st) atomicOr(&d.status[w], st);
+}
+
+__global__ void k_count_frame(DevView d) { atomicAdd(&d.counters[CNT_FRAMES], 1ull); }
+
+// -------------------------------------------------------------------------------------------------- state pack/unpack
+// host record (rawphys_b200.h RP_STATE_STRIDE = 21 doubles) <-> BodyDyn + active + deactivation time
+__global__ void __launch_bounds__(128) k_unpack_state(DevView d, const double* rec, int first_world, int n_worlds, int broadcast) {
+	const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= (size_t)n_worlds * d.NB) return;
+	const int wl = (int)(gid / d.NB), b = (int)(gid % d.NB);
+	const double* r = rec + (broadcast ? (size_t)b : gid) * 21;
+	const size_t o = (size_t)(first_world + wl) * d.NB + b;
+	BodyDyn& dd = d.dyn[o];
+	for (int k = 0; k < 3; ++k) { dd.x[k] = r[k]; dd.v[k] = r[7 + k]; dd.w[k] = r[10 + k]; dd.pv[k] = r[15 + k]; dd.pw[k] = r[18 + k]; dd.px[k] = r[k]; }
+	for (int k = 0; k < 4; ++k) { dd.q[k] = r[3 + k]; dd.pq[k] = r[3 + k]; }
+	d.active[o] = r[13] != 0.0 ? 1 : 0;
+	d.deact[o] = r[14];
+}
+__global__ void __launch_bounds__(128) k_pack_state(DevView d, double* rec, int first_world, int n_worlds) {
+	const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= (size_t)n_worlds * d.NB) return;
+	const int wl = (int)(gid / d.NB), b = (int)(gid % d.NB);
+	double* r = rec + gid * 21;
+	const size_t o = (size_t)(first_world + wl) * d.NB + b;
+	const BodyDyn& dd = d.dyn[o];
+	for (int k = 0; k < 3; ++k) { r[k] = dd.x[k]; r[7 + k] = dd.v[k]; r[10 + k] = dd.w[k]; r[15 + k] = dd.pv[k]; r[18 + k] = dd.pw[k]; }
+	for (int k = 0; k < 4; ++k) r[3 + k] = dd.q[k];
+	r[13] = d.active[o] ? 1.0 : 0.0;
+	r[14] = d.deact[o];
+}
+
+}  // namespace rp
+#endif

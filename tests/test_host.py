@@ -1,0 +1,88 @@
+"""CPU tests of the product's host side (-m "not gpu"): the C-ABI library loads, exports every symbol the header
+declares, builds scene templates identical to the reference's, and refuses to compute without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import refdrv
+import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HULLS = np.load(os.path.join(ROOT, "tests", "golden", "hulls.npz"))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    header = open(os.path.join(ROOT, "include", "rawphys_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(rp_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 30
+    L = pkg.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted(pkg.EXPORTS) == declared
+
+
+def test_product_does_not_touch_the_oracle():
+    """The product (package + header) must never import, link or execute anything under oracle/."""
+    for base, _, files in os.walk(os.path.join(ROOT, "raw-physics_b200")):
+        for f in files:
+            if f.endswith((".py", ".h", ".cuh", ".cu", ".cpp")):
+                text = open(os.path.join(base, f)).read()
+                assert "libport_oracle" not in text and "libref_oracle" not in text, f
+                assert "import refdrv" not in text and "oracle/" not in text, f
+
+
+@pytest.mark.parametrize("name", ["stack", "brick_wall", "coin", "pile", "mirror_cube", "spheres", "arm"])
+def test_scene_params_match_reference(pkg, name):
+    """entity_create_ex results (entity.cpp:24-65): inverse mass, inertia (quirk q9), inverse inertia, bounding radius."""
+    kw = dict(n_side=3) if name == "pile" else {}
+    sc = scenes.BUILDERS[name](**kw)
+    got = pkg.Scene(sc).params()
+    assert np.array_equal(got, GOLD[name + "/params"])
+
+
+@pytest.mark.parametrize("mesh", ["cube", "floor", "ico", "ramp", "cylinder", "lever", "seesaw_support"])
+def test_scene_hulls_match_reference(pkg, mesh):
+    sc = scenes.Scene("h")
+    sc.bodies.append(scenes.BodyDesc((0, 0, 0), scenes.IDENT, 1.0, False, [scenes.hull(mesh, (1.0, 1.0, 1.0))]))
+    h = pkg.Scene(sc).hull(0)
+    for k, v in h.items():
+        assert np.array_equal(v, HULLS["%s/%s" % (mesh, k)]), (mesh, k)
+
+
+def test_sphere_collider_has_no_hull(pkg):
+    assert pkg.Scene(scenes.spheres(2)).hull(1) is None
+
+
+def test_bad_arguments_are_refused(pkg):
+    L = pkg.lib()
+    s = pkg.Scene()
+    v = np.zeros((3, 3))
+    idx = np.array([0, 1, 7], dtype=np.uint32)  # index out of range
+    assert L.rp_scene_collider_hull(s.h, v.ctypes.data_as(C.POINTER(C.c_double)), 3, idx.ctypes.data_as(C.POINTER(C.c_uint32)), 3) == -1
+    assert L.rp_scene_collider_hull(s.h, None, 3, None, 3) == -1
+    assert L.rp_scene_add_mutual_orientation_constraint(s.h, 0, 1, 0.0) == -1  # no such bodies
+    out = C.c_void_p()
+    assert L.rp_batch_create(s.h, 1, 0, None, C.byref(out)) == 1  # RP_ERR_ARG: empty scene
+    assert L.rp_batch_create(None, 1, 0, None, C.byref(out)) == 1
+    assert L.rp_batch_step(None, 1.0 / 60, 20, 1, 1) == 1
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device batch creation fails loudly with RP_ERR_CUDA; nothing is computed on the host."""
+    L = pkg.lib()
+    if L.rp_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.RawPhysError) as e:
+        pkg.Batch(pkg.Scene(scenes.stack()), n_worlds=2)
+    assert "code 2" in str(e.value)
+
+
+def test_build_flags_forbid_fma():
+    """Parity depends on --fmad=false (SURVEY.md TL;DR 3) and on sm_100a being the only target."""
+    text = open(os.path.join(ROOT, "raw-physics_b200", "build.py")).read()
+    assert "--fmad=false" in text and "arch=compute_100a,code=sm_100a" in text and "-lineinfo" in text
+    assert "use_fast_math" not in text
