@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- body-substeps/sec of the XPBD frame step on the north-star workload (BASELINE.json):
+4096 independent worlds x (256 cubes + floor) per GPU, dt = 1/60, 20 substeps, 1 positional iteration, collisions on.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--worlds 4096]
+
+One "step" = one 60 Hz frame (= 20 substeps) of every world. The timed window is frames 0..K-1 from the initial poses
+(nothing can fall asleep before 1.0 s of simulated quiet time, pbd.cpp:490-498, so K <= 60 is not deflated by sleeping);
+the W warm-up steps run first and the state is then reset. `value` is timed on the device with CUDA events on the
+stream the kernels are launched on, with state resident in HBM; `e2e` is the same metric through the host-buffer call
+rp_batch_step_host (pinned host state in, pinned host state out, both copies inside the timed region).
+`--impl reference` times the UNMODIFIED reference (oracle/_ref, else the CPU restatement) on all host cores.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DT = 1.0 / 60.0
+SUBSTEPS = 20
+ITERS = 1
+KERNELS_PER_FRAME = 5 + SUBSTEPS * 4 + 1  # broad x3, islands, schedule; per substep integrate, gjk, manifold, solve; frame counter
+
+# Algorithmic work per item, derived in DESIGN.md ("Kernels and rooflines"): bytes that must move and FP64 operations
+# (mul/add/div/sqrt = 1 each, no FMA credit) for one body-substep / pair test / EPA+manifold run / solved contact.
+BYTES = dict(integrate=600.0, gjk=400.0, manifold=776.0, manifold_contact=64.0, solve_body=416.0, solve_contact=208.0)
+FLOPS = dict(integrate=770.0, gjk=620.0, manifold=2000.0, solve_contact=1750.0, solve_body=40.0)
+FLOP_PER_BODY_SUBSTEP = 4.0e3  # algorithmic FP64 flop per body-substep on the W256 world
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU")
+    ap.add_argument("--solve-threads", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / profile / cpu baseline (kernel timing only)")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_single_thread_baseline(flavour, budget_s=12.0):
+    """The reference's own single-threaded step on ONE host core: fresh W256 worlds, first 60 frames each."""
+    import refdrv
+    import scenes
+    desc = scenes.w256()
+    frames, worlds, spent = 60, 0, 0.0
+    while spent < budget_s and worlds < 16:
+        w = refdrv.RefWorld(flavour).load(desc)
+        spent += w.run_timed(frames, DT, SUBSTEPS, ITERS, True)
+        worlds += 1
+    nb = len(desc.bodies)
+    return {"value": nb * SUBSTEPS * frames * worlds / spent, "unit": "body-substeps/s", "cores": 1,
+            "kind": "reference" if flavour == "strict" else "port",
+            "sample": "%d fresh W256 worlds x first %d frames, one thread, %.1f s (%.2f ms/frame/world)" % (worlds, frames, spent, 1e3 * spent / (frames * worlds))}
+
+
+def _ref_worker(flavour, frames_warm, frames, barrier, q):
+    import refdrv
+    import scenes
+    w = refdrv.RefWorld(flavour).load(scenes.w256())
+    barrier.wait()
+    if frames_warm:
+        w.run_timed(frames_warm, DT, SUBSTEPS, ITERS, True)
+        w = refdrv.RefWorld(flavour).load(scenes.w256())  # timed window = frames 0..K-1, as on the GPU arm
+    barrier.wait()
+    t0 = time.perf_counter()
+    w.run_timed(frames, DT, SUBSTEPS, ITERS, True)
+    q.put(time.perf_counter() - t0)
+
+
+def run_reference(args):
+    """Reference arm: the unmodified reference (one world per process, it is single-threaded with global state) on every
+    host core at once; a step = one frame of `cores` worlds."""
+    import multiprocessing as mp
+    import refdrv
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    flavour = "strict" if refdrv.available("strict") else "port"
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ctx = mp.get_context("fork")
+    barrier = ctx.Barrier(cores)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ref_worker, args=(flavour, args.warmup, args.steps, barrier, q)) for _ in range(cores)]
+    for p in procs:
+        p.start()
+    times = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    elapsed = max(times)
+    nb = 257
+    value = nb * cores * SUBSTEPS * args.steps / elapsed
+    line = {"impl": "reference", "metric": "body-substeps/sec", "value": value, "unit": "body-substeps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "w256 (256 cubes + floor), %d worlds (one per host core), frames 0..%d" % (cores, args.steps - 1),
+                       "bodies_per_world": nb, "substeps": SUBSTEPS, "pos_iters": ITERS, "dt": DT},
+            "cpu_baseline": {"value": value, "unit": "body-substeps/s", "cores": cores, "kind": "reference" if flavour == "strict" else "port",
+                             "sample": "%d processes x 1 W256 world x %d frames" % (cores, args.steps)},
+            "e2e": {"value": value, "unit": "body-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import __graft_entry__ as ge
+    import scenes
+    pkg = ge.load_package()
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or pkg.lib().rp_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    desc = scenes.w256()
+    scene = pkg.Scene(desc)
+    W = args.worlds
+    batch = pkg.Batch(scene, n_worlds=W, device=local_rank, solve_threads=args.solve_threads)
+    batch.set_scene_forces(desc)
+    NB = batch.NB
+    init = batch.state(0, 1)[0].copy()
+
+    def barrier():
+        torch.cuda.synchronize()
+        batch.sync()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        batch.step(DT, SUBSTEPS, ITERS, True)
+    batch.broadcast(init)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ms = batch.run(args.steps, DT, SUBSTEPS, ITERS, True)
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(ms)
+    units = NB * W * SUBSTEPS * args.steps * world_size
+    value = units / (ms * 1e-3)
+    status = batch.status()
+
+    line = {"metric": "body-substeps/sec", "value": value, "unit": "body-substeps/s", "n_gpus": world_size, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "w256x%d per GPU (256 cubes + floor per world), frames 0..%d from the initial poses" % (W, args.steps - 1),
+                       "worlds_per_gpu": W, "bodies_per_world": NB, "substeps": SUBSTEPS, "pos_iters": ITERS, "dt": DT, "mode": "batched-worlds, reference Gauss-Seidel order (level schedule)",
+                       "l2": "per-GPU state %.0f MB + transformed hulls %.0f MB > 126 MB L2: inputs larger than L2, no flush" % (
+                           W * NB * 208 / 1e6, W * NB * 336 / 1e6)},
+            "clocks": clocks, "gpu_launches": KERNELS_PER_FRAME * args.steps, "status_bits": int(np.bitwise_or.reduce(status))}
+
+    if not args.no_extras:
+        # ---- end to end through the host-buffer call (pinned host state in and out every step)
+        nrec = W * NB * pkg.STATE_STRIDE
+        h_in = torch.empty(nrec, dtype=torch.float64).pin_memory()
+        h_out = torch.empty(nrec, dtype=torch.float64).pin_memory()
+        h_in.copy_(torch.from_numpy(np.ascontiguousarray(np.broadcast_to(init[None], (W, NB, pkg.STATE_STRIDE))).reshape(-1)))
+        for _ in range(min(args.warmup, 2)):
+            batch.step_host(h_in.data_ptr(), h_out.data_ptr(), DT, SUBSTEPS, ITERS, True)
+        barrier()
+        t0 = time.perf_counter()
+        a, b = h_in, h_out
+        for _ in range(args.steps):
+            batch.step_host(a.data_ptr(), b.data_ptr(), DT, SUBSTEPS, ITERS, True)
+            a, b = b, a
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        line["e2e"] = {"value": units / e2e_s, "unit": "body-substeps/s", "h2d_bytes_per_step": nrec * 8, "d2h_bytes_per_step": nrec * 8,
+                       "ms_per_step": 1e3 * e2e_s / args.steps, "api": "rp_batch_step_host (upload state, step, download state, sync)"}
+
+        # ---- per-kernel device time over the same window + roofline of the dominant kernel
+        batch.broadcast(init)
+        barrier()
+        c0 = batch.counters()
+        fam = batch.profile(args.steps, DT, SUBSTEPS, ITERS, True)
+        c1 = batch.counters()
+        tests = c1["pair_tests"] - c0["pair_tests"]
+        hits = c1["gjk_hits"] - c0["gjk_hits"]
+        contacts = c1["contacts"] - c0["contacts"]
+        bs = NB * W * SUBSTEPS * args.steps
+        alg_bytes = {"integrate": BYTES["integrate"] * bs, "gjk": BYTES["gjk"] * tests,
+                     "manifold": BYTES["manifold"] * hits + BYTES["manifold_contact"] * contacts,
+                     "solve": BYTES["solve_body"] * bs + BYTES["solve_contact"] * contacts}
+        alg_flops = {"integrate": FLOPS["integrate"] * bs, "gjk": FLOPS["gjk"] * tests, "manifold": FLOPS["manifold"] * hits,
+                     "solve": FLOPS["solve_contact"] * contacts + FLOPS["solve_body"] * bs}
+        total_ms = sum(fam.values())
+        top = max(fam, key=fam.get)
+        hbm_peak, hbm_src = measured_peaks()
+        fp64_nofma, fp64_fma = pkg.measure_fp64_peak(local_rank)
+        launches = SUBSTEPS * args.steps if top in alg_bytes else args.steps
+        line["kernels"] = {k: {"ms": round(v, 3), "share": round(v / total_ms, 4)} for k, v in fam.items()}
+        if top in alg_bytes:
+            gbs = alg_bytes[top] / (fam[top] * 1e-3) / 1e9
+            line["roofline"] = {"kernel": "k_" + top, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                "traffic": None, "peak_source": hbm_src, "avg_launch_ms": fam[top] / launches,
+                                "note": "schema bound; the binding resource of this path is the FP64 CUDA-core pipe, see fp64"}
+            tf = alg_flops[top] / (fam[top] * 1e-3) / 1e12
+            line["fp64"] = {"kernel": "k_" + top, "achieved_tflops": tf, "peak_tflops_no_fma": fp64_nofma, "peak_tflops_fma": fp64_fma,
+                            "frac_of_no_fma_peak": tf / fp64_nofma,
+                            "whole_step_tflops": FLOP_PER_BODY_SUBSTEP * (NB * W * SUBSTEPS * args.steps) / (ms * 1e-3) / 1e12,
+                            "whole_step_frac": FLOP_PER_BODY_SUBSTEP * (NB * W * SUBSTEPS * args.steps) / (ms * 1e-3) / 1e12 / fp64_nofma,
+                            "peak_source": "rp_measure_fp64_peak (DMUL+DADD chains, this run)"}
+        line["work_per_world_substep"] = {"pair_tests": tests / (W * SUBSTEPS * args.steps), "epa_runs": hits / (W * SUBSTEPS * args.steps),
+                                          "contacts": contacts / (W * SUBSTEPS * args.steps)}
+        if dist is not None:  # NCCL only gathers aggregate statistics
+            t = torch.tensor([float(tests), float(hits), float(contacts)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            line["aggregate_work"] = {"pair_tests": t[0].item(), "epa_runs": t[1].item(), "contacts": t[2].item()}
+        if rank == 0 and world_size == 1:
+            import refdrv
+            line["cpu_baseline"] = cpu_single_thread_baseline("strict" if refdrv.available("strict") else "port")
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,15 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t num_substeps, uint32_t
 /* broadphase pairs of one world for its current poses (broad_get_collision_pairs, broad.cpp:6): (e1, e2) body ids */
 int rp_batch_broad_pairs(rp_batch* b, uint32_t world, uint32_t* pairs_out, uint32_t max_pairs, uint32_t* n_pairs);
 
+/* Profiling aids (bench.py). Kernel families of one frame, in launch order. */
+enum { RP_K_BROAD = 0, RP_K_ISLANDS, RP_K_SCHEDULE, RP_K_INTEGRATE, RP_K_GJK, RP_K_MANIFOLD, RP_K_SOLVE, RP_NUM_KERNEL_FAMILIES };
+/* device milliseconds per kernel family over `frames` un-graphed frames (CUDA events at every kernel boundary) */
+int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t num_substeps, uint32_t num_pos_iters, int enable_collisions,
+	float ms_out[RP_NUM_KERNEL_FAMILIES]);
+/* measured FP64 CUDA-core rate, TFLOP/s: out2[0] = DMUL+DADD chains (no contraction, as this library is built),
+ * out2[1] = DFMA chains */
+int rp_measure_fp64_peak(int cuda_device, double out2[2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,8 +30,10 @@ EXPORTS = [
     "rp_scene_hull_sizes", "rp_scene_hull_dump", "rp_batch_cfg_default", "rp_batch_create", "rp_batch_destroy", "rp_batch_num_worlds",
     "rp_batch_num_bodies", "rp_batch_clear_forces", "rp_batch_add_force", "rp_batch_add_gravity", "rp_batch_step", "rp_batch_sync",
     "rp_batch_run", "rp_batch_upload_state", "rp_batch_download_state", "rp_batch_broadcast_state", "rp_batch_step_host",
-    "rp_batch_get_status", "rp_batch_get_counters", "rp_batch_step_logged", "rp_batch_broad_pairs",
+    "rp_batch_get_status", "rp_batch_get_counters", "rp_batch_step_logged", "rp_batch_broad_pairs", "rp_batch_profile",
+    "rp_measure_fp64_peak",
 ]
+KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "gjk", "manifold", "solve"]
 
 
 class BatchCfg(C.Structure):
@@ -91,6 +93,8 @@ def lib():
     L.rp_batch_step_logged.argtypes = [C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, _u32p, C.c_uint32, _dp,
                                        C.c_uint32, _u32p, _u32p]
     L.rp_batch_broad_pairs.argtypes = [C.c_void_p, C.c_uint32, _u32p, C.c_uint32, _u32p]
+    L.rp_batch_profile.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_float)]
+    L.rp_measure_fp64_peak.argtypes = [C.c_int, _dp]
     _lib = L
     return L
 
@@ -272,6 +276,12 @@ class Batch:
         return dict(pair_tests=int(out[0]), gjk_hits=int(out[1]), contacts=int(out[2]), broad_pairs=int(out[3]), levels=int(out[4]),
                     frames=int(out[5]))
 
+    def profile(self, frames, dt=1.0 / 60.0, substeps=20, iters=1, collisions=True):
+        """device ms per kernel family over `frames` un-graphed frames"""
+        out = (C.c_float * len(KERNEL_FAMILIES))()
+        _check(self.L.rp_batch_profile(self.h, frames, dt, substeps, iters, int(collisions), out), "rp_batch_profile")
+        return {k: float(out[i]) for i, k in enumerate(KERNEL_FAMILIES)}
+
     def step_logged(self, world=0, dt=1.0 / 60.0, substeps=20, iters=1, collisions=True, max_calls=1 << 16, max_contacts=1 << 18):
         calls = np.zeros((max_calls, 4), dtype=np.uint32)
         contacts = np.zeros((max_contacts, 9))
@@ -287,6 +297,13 @@ class Batch:
         n = C.c_uint32()
         _check(self.L.rp_batch_broad_pairs(self.h, world, _u(buf), max_pairs, C.byref(n)), "rp_batch_broad_pairs")
         return buf[:n.value].astype(np.int64)
+
+
+def measure_fp64_peak(device=0):
+    """(no-FMA TFLOP/s, FMA TFLOP/s) of the FP64 CUDA-core pipe, measured on the device"""
+    out = np.zeros(2)
+    _check(lib().rp_measure_fp64_peak(device, _d(out)), "rp_measure_fp64_peak")
+    return float(out[0]), float(out[1])
 
 
 def state15_to_21(st15):

@@ -688,4 +688,95 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t substeps, uint32_t ite
 	return RP_OK;
 }
 
+// Per-kernel device time of `frames` frames, launched WITHOUT the graph with a CUDA event at every kernel boundary:
+// ms_out[RP_K_BROAD .. RP_K_SOLVE] accumulate the time of each kernel family. Profiling aid for bench.py's roofline
+// block; the headline numbers come from rp_batch_run.
+int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps, uint32_t iters, int collisions, float* ms_out) {
+	if (!b || !ms_out || substeps == 0 || dt <= 0.0) return fail(RP_ERR_ARG, "rp_batch_profile: bad argument");
+	RP_CUDA(cudaSetDevice(b->device));
+	int rc = flush_forces(b);
+	if (rc) return rc;
+	for (int k = 0; k < RP_NUM_KERNEL_FAMILIES; ++k) ms_out[k] = 0.f;
+	const DevView& d = b->d;
+	const double h = dt / substeps;
+	std::vector<cudaEvent_t> ev;
+	std::vector<int> fam;
+	auto mark = [&](int family) -> int {
+		cudaEvent_t e;
+		RP_CUDA(cudaEventCreate(&e));
+		RP_CUDA(cudaEventRecord(e, b->stream));
+		ev.push_back(e);
+		fam.push_back(family);
+		return RP_OK;
+	};
+	if ((rc = mark(-1))) return rc;
+	for (uint32_t f = 0; f < frames; ++f) {
+		dim3 rows((d.NB + 127) / 128, d.W);
+		k_broad_rows<false><<<rows, 128, 0, b->stream>>>(d);
+		k_broad_scan<<<d.W, 256, 0, b->stream>>>(d);
+		k_broad_rows<true><<<rows, 128, 0, b->stream>>>(d);
+		if ((rc = mark(RP_K_BROAD))) return rc;
+		k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
+		if ((rc = mark(RP_K_ISLANDS))) return rc;
+		k_schedule<<<(d.W + 63) / 64, 64, 0, b->stream>>>(d, collisions ? 1 : 0);
+		if ((rc = mark(RP_K_SCHEDULE))) return rc;
+		for (uint32_t s = 0; s < substeps; ++s) {
+			enqueue_integrate(b, h);
+			if ((rc = mark(RP_K_INTEGRATE))) return rc;
+			if (collisions) {
+				k_gjk<<<dim3(b->gjk_chunks, d.W), 128, 0, b->stream>>>(d);
+				if ((rc = mark(RP_K_GJK))) return rc;
+				k_manifold<<<b->sm_count * 4, 128, 0, b->stream>>>(d);
+				if ((rc = mark(RP_K_MANIFOLD))) return rc;
+			}
+			enqueue_solve(b, h, iters, collisions ? 1 : 0);
+			if ((rc = mark(RP_K_SOLVE))) return rc;
+		}
+		k_count_frame<<<1, 1, 0, b->stream>>>(d);
+	}
+	RP_CUDA(cudaGetLastError());
+	RP_CUDA(cudaStreamSynchronize(b->stream));
+	for (size_t i = 1; i < ev.size(); ++i) {
+		float ms = 0.f;
+		RP_CUDA(cudaEventElapsedTime(&ms, ev[i - 1], ev[i]));
+		ms_out[fam[i]] += ms;
+	}
+	for (size_t i = 0; i < ev.size(); ++i) cudaEventDestroy(ev[i]);
+	return RP_OK;
+}
+
+// Measured FP64 rate of the CUDA-core pipe on `device`, TFLOP/s (mul and add counted as one flop each, an FMA as two):
+// out2[0] = independent DMUL+DADD chains (the parity build's instruction mix), out2[1] = DFMA chains.
+int rp_measure_fp64_peak(int device, double out2[2]) {
+	if (!out2) return RP_ERR_ARG;
+	RP_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	RP_CUDA(cudaGetDeviceProperties(&prop, device));
+	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+	double* buf = 0;
+	RP_CUDA(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+	cudaEvent_t e0, e1;
+	RP_CUDA(cudaEventCreate(&e0));
+	RP_CUDA(cudaEventCreate(&e1));
+	for (int mode = 0; mode < 2; ++mode) {
+		float best = 1e30f;
+		for (int rep = 0; rep < 4; ++rep) {
+			RP_CUDA(cudaEventRecord(e0, 0));
+			if (mode == 0) k_fp64_probe<false><<<blocks, threads>>>(buf, iters, 1.0000001, 1e-9);
+			else k_fp64_probe<true><<<blocks, threads>>>(buf, iters, 1.0000001, 1e-9);
+			RP_CUDA(cudaEventRecord(e1, 0));
+			RP_CUDA(cudaEventSynchronize(e1));
+			float ms = 0.f;
+			RP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+			if (rep > 0 && ms < best) best = ms;
+		}
+		const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+		out2[mode] = flops / (best * 1e-3) / 1e12;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(buf);
+	return RP_OK;
+}
+
 }  // extern "C"

@@ -535,6 +535,25 @@ __global__ void k_solve(DevView d, double h, int iters, int collisions) {
 	if (st) atomicOr(&d.status[w], st);
 }
 
+// ------------------------------------------------------------------------------------------------ FP64 pipe probe
+// Roofline denominator for this path: sustained FP64 rate of the CUDA-core pipe with independent DADD/DMUL chains (the
+// form the parity build issues: --fmad=false) or DFMA chains (what the pipe could do if contraction were allowed).
+template <bool FMA>
+__global__ void __launch_bounds__(256) k_fp64_probe(double* out, int iters, double a, double b) {
+	double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+	for (int i = 0; i < iters; ++i) {
+		if (FMA) {
+			x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+			x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+		} else {
+			x0 = __dadd_rn(__dmul_rn(x0, a), b); x1 = __dadd_rn(__dmul_rn(x1, a), b); x2 = __dadd_rn(__dmul_rn(x2, a), b);
+			x3 = __dadd_rn(__dmul_rn(x3, a), b); x4 = __dadd_rn(__dmul_rn(x4, a), b); x5 = __dadd_rn(__dmul_rn(x5, a), b);
+			x6 = __dadd_rn(__dmul_rn(x6, a), b); x7 = __dadd_rn(__dmul_rn(x7, a), b);
+		}
+	}
+	out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
 __global__ void k_count_frame(DevView d) { atomicAdd(&d.counters[CNT_FRAMES], 1ull); }
 
 // -------------------------------------------------------------------------------------------------- state pack/unpack

@@ -83,7 +83,7 @@ def test_contact_sets_bit_exact(pkg, oracle_flavour, name):
     o = refdrv.RefWorld(oracle_flavour).load(sc)
     o.log_enable(True)
     total = 0
-    for f in range(45):
+    for f in range(90 if name == "coin" else 45):
         calls, contacts = b.step_logged(world=1, substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
         o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
         oc, ok = o.log_get()
