@@ -29,12 +29,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 DT = 1.0 / 60.0
 SUBSTEPS = 20
 ITERS = 1
-KERNELS_PER_FRAME = 5 + SUBSTEPS * 4 + 1  # broad x3, islands, schedule; per substep integrate, gjk, manifold, solve; frame counter
 
 # Algorithmic work per item, derived in DESIGN.md ("Kernels and rooflines"): bytes that must move and FP64 operations
 # (mul/add/div/sqrt = 1 each, no FMA credit) for one body-substep / pair test / EPA+manifold run / solved contact.
-BYTES = dict(integrate=600.0, gjk=400.0, manifold=776.0, manifold_contact=64.0, solve_body=416.0, solve_contact=208.0)
-FLOPS = dict(integrate=770.0, gjk=620.0, manifold=2000.0, solve_contact=1750.0, solve_body=40.0)
+BYTES = dict(integrate=600.0, gjk=400.0, manifold=776.0, manifold_contact=64.0, solve_pos_pair=2 * (112.0 + 56.0), solve_contact=80.0,
+             solve_vel_pair=2 * (128.0 + 48.0), solve_contact_vel=64.0)
+FLOPS = dict(integrate=770.0, gjk=620.0, manifold=2000.0, solve_pos_contact=1100.0, solve_vel_contact=650.0)
 FLOP_PER_BODY_SUBSTEP = 4.0e3  # algorithmic FP64 flop per body-substep on the W256 world
 
 
@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU")
-    ap.add_argument("--solve-threads", type=int, default=0)
+    ap.add_argument("--no-cull", action="store_true", help="run GJK on every broadphase pair (disables the exact-safe bounds cull)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / profile / cpu baseline (kernel timing only)")
     return ap.parse_args()
 
@@ -188,7 +188,7 @@ def run_ours(args):
     desc = scenes.w256()
     scene = pkg.Scene(desc)
     W = args.worlds
-    batch = pkg.Batch(scene, n_worlds=W, device=local_rank, solve_threads=args.solve_threads)
+    batch = pkg.Batch(scene, n_worlds=W, device=local_rank, disable_cull=args.no_cull)
     batch.set_scene_forces(desc)
     NB = batch.NB
     init = batch.state(0, 1)[0].copy()
@@ -221,6 +221,11 @@ def run_ours(args):
     units = NB * W * SUBSTEPS * args.steps * world_size
     value = units / (ms * 1e-3)
     status = batch.status()
+    # kernels launched in the timed region: per frame 7 prologue kernels + per substep integrate, cull, gjk, manifold,
+    # derive and one positional + one velocity launch per dependency level, + the frame counter
+    c_levels = batch.counters()
+    depth = int(round(c_levels["levels"] / max(1, c_levels["frames"]) / W)) if c_levels["frames"] else 0
+    launches_total = args.steps * (7 + SUBSTEPS * (5 + depth * (ITERS + 1)) + 1)
 
     line = {"metric": "body-substeps/sec", "value": value, "unit": "body-substeps/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -229,7 +234,7 @@ def run_ours(args):
                        "worlds_per_gpu": W, "bodies_per_world": NB, "substeps": SUBSTEPS, "pos_iters": ITERS, "dt": DT, "mode": "batched-worlds, reference Gauss-Seidel order (level schedule)",
                        "l2": "per-GPU state %.0f MB + transformed hulls %.0f MB > 126 MB L2: inputs larger than L2, no flush" % (
                            W * NB * 208 / 1e6, W * NB * 336 / 1e6)},
-            "clocks": clocks, "gpu_launches": KERNELS_PER_FRAME * args.steps, "status_bits": int(np.bitwise_or.reduce(status))}
+            "clocks": clocks, "gpu_launches": launches_total, "status_bits": int(np.bitwise_or.reduce(status))}
 
     if not args.no_extras:
         # ---- end to end through the host-buffer call (pinned host state in and out every step)
@@ -262,9 +267,10 @@ def run_ours(args):
         bs = NB * W * SUBSTEPS * args.steps
         alg_bytes = {"integrate": BYTES["integrate"] * bs, "gjk": BYTES["gjk"] * tests,
                      "manifold": BYTES["manifold"] * hits + BYTES["manifold_contact"] * contacts,
-                     "solve": BYTES["solve_body"] * bs + BYTES["solve_contact"] * contacts}
+                     "solve_pos": BYTES["solve_pos_pair"] * hits + BYTES["solve_contact"] * contacts,
+                     "solve_vel": BYTES["solve_vel_pair"] * hits + BYTES["solve_contact_vel"] * contacts}
         alg_flops = {"integrate": FLOPS["integrate"] * bs, "gjk": FLOPS["gjk"] * tests, "manifold": FLOPS["manifold"] * hits,
-                     "solve": FLOPS["solve_contact"] * contacts + FLOPS["solve_body"] * bs}
+                     "solve_pos": FLOPS["solve_pos_contact"] * contacts, "solve_vel": FLOPS["solve_vel_contact"] * contacts}
         total_ms = sum(fam.values())
         top = max(fam, key=fam.get)
         hbm_peak, hbm_src = measured_peaks()

@@ -94,7 +94,7 @@ int rp_scene_hull_dump(const rp_scene* s, int body, int collider, double* verts,
 typedef struct {
 	uint32_t max_pairs_per_world;     /* broadphase (collider-)pair capacity; 0 = derive from the initial poses */
 	uint32_t max_contacts_per_world;  /* contact capacity per substep; 0 = derive */
-	uint32_t solve_threads;           /* threads of the per-world solver CTA (multiple of 32); 0 = derive */
+	uint32_t disable_cull;            /* 1 = run GJK on every broadphase pair (the exact-safe bounds cull is on by default) */
 	double linear_sleeping_threshold;   /* pbd.cpp:13, default 0.10 */
 	double angular_sleeping_threshold;  /* pbd.cpp:14, default 0.10 */
 	double deactivation_time;           /* pbd.cpp:15, default 1.0 */
@@ -113,7 +113,9 @@ int rp_batch_add_force(rp_batch* b, int body, const double position[3], const do
 /* the examples' gravity idiom: (0, -g * 1.0 / inverse_mass, 0) at the centre of every body (stack.cpp:93-96) */
 int rp_batch_add_gravity(rp_batch* b, double g);
 
-/* pbd_simulate_with_constraints for every world: enqueued on the batch's CUDA stream, returns without waiting. */
+/* pbd_simulate_with_constraints for every world. The per-frame prologue (broadphase, islands, schedule) is waited for,
+ * because the host needs the frame's dependency depth; the substeps are then enqueued on the batch's CUDA stream as one
+ * graph launch and the call returns without waiting for them. */
 int rp_batch_step(rp_batch* b, double dt, uint32_t num_substeps, uint32_t num_pos_iters, int enable_collisions);
 int rp_batch_sync(rp_batch* b);
 /* `frames` consecutive steps timed on the device with CUDA events on the batch's stream (milliseconds). */
@@ -148,7 +150,10 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t num_substeps, uint32_t
 int rp_batch_broad_pairs(rp_batch* b, uint32_t world, uint32_t* pairs_out, uint32_t max_pairs, uint32_t* n_pairs);
 
 /* Profiling aids (bench.py). Kernel families of one frame, in launch order. */
-enum { RP_K_BROAD = 0, RP_K_ISLANDS, RP_K_SCHEDULE, RP_K_INTEGRATE, RP_K_GJK, RP_K_MANIFOLD, RP_K_SOLVE, RP_NUM_KERNEL_FAMILIES };
+enum {
+	RP_K_BROAD = 0, RP_K_ISLANDS, RP_K_SCHEDULE, RP_K_INTEGRATE, RP_K_CULL, RP_K_GJK, RP_K_MANIFOLD, RP_K_SOLVE_POS, RP_K_DERIVE,
+	RP_K_SOLVE_VEL, RP_NUM_KERNEL_FAMILIES
+};
 /* device milliseconds per kernel family over `frames` un-graphed frames (CUDA events at every kernel boundary) */
 int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t num_substeps, uint32_t num_pos_iters, int enable_collisions,
 	float ms_out[RP_NUM_KERNEL_FAMILIES]);

@@ -8,7 +8,7 @@
 // file:line it follows. What this file adds is only the ORDER of operations, which is the reference's.
 //
 // Pinning: this restatement is checked bit-for-bit against the UNMODIFIED reference compiled into
-// oracle/_ref/libref_oracle.so (tests/test_port_vs_reference.py): hull topology, per-pair GJK/EPA/manifold outputs,
+// oracle/_ref/libref_oracle.so (tests/test_oracle.py): hull topology, per-pair GJK/EPA/manifold outputs,
 // per-substep contact logs and whole trajectories for every scene in tests/scenes.py. The reference has no tests or
 // golden vectors of its own; the committed fixtures under tests/golden/ were generated from that library.
 //
@@ -18,6 +18,7 @@
 // The exported functions mirror oracle/ref_driver.cpp one for one (ref_* -> port_*), so tests drive both through the
 // same Python class.
 #include <chrono>
+#include <random>
 #include <string.h>
 #include <vector>
 
@@ -463,6 +464,64 @@ void port_log_get(uint32_t* calls_out, double* contacts_out) {
 	}
 }
 uint64_t port_total_narrowphase_calls() { return g->calls; }
+
+// Soundness probe for the bounds cull of the CUDA path (k_cull, RP_CULL_MARGIN = 1e-7): random box / octahedron pairs at
+// random, axis-aligned and nearly-touching poses; counts pairs whose world-space bounds are separated by more than the
+// margin and which the reference-order GJK nevertheless reports as colliding. Must return 0.
+uint64_t port_cull_soundness(uint64_t trials, uint64_t seed, uint64_t* separated_out, uint64_t* hits_out) {
+	std::mt19937_64 rng(seed);
+	std::uniform_real_distribution<double> U(-1.0, 1.0);
+	std::vector<V3> la, lb, ta, tb;
+	uint64_t viol = 0, sep = 0, hits = 0;
+	for (uint64_t t = 0; t < trials; ++t) {
+		la.clear(); lb.clear(); ta.clear(); tb.clear();
+		for (int side = 0; side < 2; ++side) {
+			std::vector<V3>& v = side ? lb : la;
+			double big = side ? 25.0 : 2.0;
+			if (t % (side ? 5 : 3) == 0) {
+				double s = 0.5 + fabs(U(rng));
+				v.push_back(v3(s, 0, 0)); v.push_back(v3(-s, 0, 0)); v.push_back(v3(0, s, 0));
+				v.push_back(v3(0, -s, 0)); v.push_back(v3(0, 0, s)); v.push_back(v3(0, 0, -s));
+			} else {
+				double sx = 0.2 + fabs(U(rng)) * big, sy = 0.2 + fabs(U(rng)), sz = 0.2 + fabs(U(rng)) * big;
+				for (int i = 0; i < 8; ++i) v.push_back(v3((i & 1) ? sx : -sx, (i & 2) ? sy : -sy, (i & 4) ? sz : -sz));
+			}
+		}
+		Q4 qa = normalize(q4(U(rng), U(rng), U(rng), U(rng))), qb = normalize(q4(U(rng), U(rng), U(rng), U(rng)));
+		if (t % 4 == 0) { qa = q4(0, 0, 0, 1); qb = q4(0, 0, 0, 1); }
+		V3 xa = v3(3 * U(rng), 3 * U(rng), 3 * U(rng)), xb = v3(3 * U(rng), 3 * U(rng), 3 * U(rng));
+		if (t % 7 == 0) xb = v3(xa.x, xa.y - 1.0 - 2e-6 * U(rng), xa.z);
+		Pose34 Ma = model_matrix(qa, xa), Mb = model_matrix(qb, xb);
+		double lo[2][3], hi[2][3];
+		for (int side = 0; side < 2; ++side) {
+			for (int k = 0; k < 3; ++k) { lo[side][k] = 1e300; hi[side][k] = -1e300; }
+			const std::vector<V3>& src = side ? lb : la;
+			std::vector<V3>& dst = side ? tb : ta;
+			for (size_t i = 0; i < src.size(); ++i) {
+				V3 p = transform_point(side ? Mb : Ma, src[i]);
+				dst.push_back(p);
+				double c[3] = {p.x, p.y, p.z};
+				for (int k = 0; k < 3; ++k) { if (c[k] < lo[side][k]) lo[side][k] = c[k]; if (c[k] > hi[side][k]) hi[side][k] = c[k]; }
+			}
+		}
+		Shape A, B;
+		memset(&A, 0, sizeof(A)); memset(&B, 0, sizeof(B));
+		A.type = B.type = SHAPE_HULL;
+		A.tv = ta.data(); A.nv = (int)ta.size(); B.tv = tb.data(); B.nv = (int)tb.size();
+		bool separated = false;
+		for (int k = 0; k < 3; ++k) {
+			if (lo[0][k] - hi[1][k] > 1e-7 || lo[1][k] - hi[0][k] > 1e-7) separated = true;
+		}
+		Simplex s;
+		int st = 0;
+		bool hit = gjk(A, B, &s, &st, 0);
+		hits += hit;
+		if (separated) { ++sep; if (hit) ++viol; }
+	}
+	if (separated_out) *separated_out = sep;
+	if (hits_out) *hits_out = hits;
+	return viol;
+}
 int port_status() { return g->status; }
 
 }

@@ -33,11 +33,11 @@ EXPORTS = [
     "rp_batch_get_status", "rp_batch_get_counters", "rp_batch_step_logged", "rp_batch_broad_pairs", "rp_batch_profile",
     "rp_measure_fp64_peak",
 ]
-KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "gjk", "manifold", "solve"]
+KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "cull", "gjk", "manifold", "solve_pos", "derive", "solve_vel"]
 
 
 class BatchCfg(C.Structure):
-    _fields_ = [("max_pairs_per_world", C.c_uint32), ("max_contacts_per_world", C.c_uint32), ("solve_threads", C.c_uint32),
+    _fields_ = [("max_pairs_per_world", C.c_uint32), ("max_contacts_per_world", C.c_uint32), ("disable_cull", C.c_uint32),
                 ("linear_sleeping_threshold", C.c_double), ("angular_sleeping_threshold", C.c_double), ("deactivation_time", C.c_double)]
 
 
@@ -196,14 +196,14 @@ class Scene:
 class Batch:
     """n_worlds instances of a scene on one GPU (rp_batch)."""
 
-    def __init__(self, scene, n_worlds=1, device=0, max_pairs=0, max_contacts=0, solve_threads=0):
+    def __init__(self, scene, n_worlds=1, device=0, max_pairs=0, max_contacts=0, disable_cull=False):
         self.L = lib()
         self.scene = scene
         cfg = BatchCfg()
         self.L.rp_batch_cfg_default(C.byref(cfg))
         cfg.max_pairs_per_world = max_pairs
         cfg.max_contacts_per_world = max_contacts
-        cfg.solve_threads = solve_threads
+        cfg.disable_cull = int(disable_cull)
         h = C.c_void_p()
         _check(self.L.rp_batch_create(scene.h, n_worlds, device, C.byref(cfg), C.byref(h)), "rp_batch_create")
         self.h = h

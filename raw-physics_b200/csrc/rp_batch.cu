@@ -36,8 +36,10 @@ struct rp_scene {
 struct GraphKey {
 	double dt;
 	uint32_t substeps, iters;
-	int collisions;
-	bool operator==(const GraphKey& o) const { return dt == o.dt && substeps == o.substeps && iters == o.iters && collisions == o.collisions; }
+	int collisions, levels;
+	bool operator==(const GraphKey& o) const {
+		return dt == o.dt && substeps == o.substeps && iters == o.iters && collisions == o.collisions && levels == o.levels;
+	}
 };
 
 struct rp_batch {
@@ -51,9 +53,11 @@ struct rp_batch {
 	V3* torque_dev = 0;
 	bool forces_dirty = true;
 	double* rec_dev = 0;  // staging for state records, [W][NB][RP_STATE_STRIDE]
-	int solve_threads = 64;
-	int gjk_chunks = 1;
+	int cull_chunks = 1;
 	int sm_count = 148;
+	int cull = 1;            // exact-safe bounds cull before GJK (rp_batch_cfg.disable_cull turns it off)
+	int* levels_host = 0;    // pinned: deepest dependency level of the current frame
+	std::vector<int> joint_level;  // template-constant levels of the external constraints
 	bool have_graph = false;
 	GraphKey graph_key;
 	cudaGraph_t graph = 0;
@@ -241,6 +245,7 @@ void rp_batch_destroy(rp_batch* b) {
 	for (size_t i = 0; i < b->allocs.size(); ++i) cudaFree(b->allocs[i]);
 	if (b->ev0) cudaEventDestroy(b->ev0);
 	if (b->ev1) cudaEventDestroy(b->ev1);
+	if (b->levels_host) cudaFreeHost(b->levels_host);
 	if (b->stream) cudaStreamDestroy(b->stream);
 	cudaGetLastError();
 	delete b;
@@ -303,13 +308,38 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	d.max_pairs = (int)mp;
 	d.max_contacts = (int)(cfg.max_contacts_per_world ? cfg.max_contacts_per_world : std::max<size_t>(256, 8 * (size_t)d.NB));
 	d.max_units = d.NJ + d.max_pairs;
-	b->solve_threads = cfg.solve_threads ? (int)((cfg.solve_threads + 31) / 32 * 32) : 64;
-	if (b->solve_threads > 1024) b->solve_threads = 1024;
+	b->cull = cfg.disable_cull ? 0 : 1;
 	{
 		int want = (b->sm_count * 8 + d.W - 1) / d.W;
-		int most = (d.max_pairs + 127) / 128;
-		b->gjk_chunks = std::max(1, std::min(want, most));
+		int most = (d.max_pairs + 255) / 256;
+		b->cull_chunks = std::max(1, std::min(want, most));
 	}
+	RP_CUDA(cudaHostAlloc((void**)&b->levels_host, sizeof(int), cudaHostAllocDefault));
+
+	// Dependency levels of the external constraints: they head the constraint array (pbd.cpp:580) in every world, so
+	// their part of the schedule is a constant of the template.
+	std::vector<int> jlast(d.NB, 0), jlevel(d.NJ, 0);
+	int jl_max = 0;
+	for (int u = 0; u < d.NJ; ++u) {
+		const Joint& j = s.joints[u];
+		const int fa = s.bodies[j.e1].fixed, fb = s.bodies[j.e2].fixed;
+		const int la = fa ? 0 : jlast[j.e1], lb = fb ? 0 : jlast[j.e2];
+		const int lvl = 1 + std::max(la, lb);
+		if (!fa) jlast[j.e1] = lvl;
+		if (!fb) jlast[j.e2] = lvl;
+		jlevel[u] = lvl;
+		jl_max = std::max(jl_max, lvl);
+	}
+	std::vector<int> jsched, jlptr(jl_max + 1, 0);
+	for (int l = 1; l <= jl_max; ++l) {
+		for (int u = 0; u < d.NJ; ++u) {
+			if (jlevel[u] == l) jsched.push_back(u);
+		}
+		jlptr[l] = (int)jsched.size();
+	}
+	d.joint_levels = jl_max;
+	d.max_levels = jl_max + d.max_pairs;
+	b->joint_level = jlevel;
 
 	// template
 	std::vector<BodyStatic> bs(d.NB);
@@ -327,6 +357,9 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_upload(b, &d.bstat, bs))) return rc;
 	if ((rc = dev_upload(b, &d.cols, s.colliders))) return rc;
 	if ((rc = dev_upload(b, &d.joints, s.joints))) return rc;
+	if ((rc = dev_upload(b, &d.joint_sched, jsched))) return rc;
+	if ((rc = dev_upload(b, &d.joint_lptr, jlptr))) return rc;
+	if ((rc = dev_upload(b, &d.joint_last, jlast))) return rc;
 	if ((rc = dev_upload(b, &d.pool.hulls, hp.hulls))) return rc;
 	if ((rc = dev_upload(b, &d.pool.verts, hp.verts))) return rc;
 	if ((rc = dev_upload(b, &d.pool.normals, hp.normals))) return rc;
@@ -344,7 +377,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	d.torque = b->torque_dev;
 
 	// per world
-	const size_t W = (size_t)d.W, WB = W * d.NB, WP = W * d.max_pairs, WU = W * d.max_units;
+	const size_t W = (size_t)d.W, WB = W * d.NB, WP = W * d.max_pairs;
 	if ((rc = dev_alloc(b, &d.dyn, WB))) return rc;
 	if ((rc = dev_alloc(b, &d.active, WB))) return rc;
 	if ((rc = dev_alloc(b, &d.deact, WB))) return rc;
@@ -356,12 +389,18 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.label, WB))) return rc;
 	if ((rc = dev_alloc(b, &d.isl_flag, WB))) return rc;
 	if ((rc = dev_alloc(b, &d.last_level, WB))) return rc;
-	if ((rc = dev_alloc(b, &d.unit_level, WU))) return rc;
-	if ((rc = dev_alloc(b, &d.sched, WU))) return rc;
-	if ((rc = dev_alloc(b, &d.level_ptr, W * (d.max_units + 2)))) return rc;
-	if ((rc = dev_alloc(b, &d.n_levels, W))) return rc;
+	if ((rc = dev_alloc(b, &d.pair_level, WP))) return rc;
+	if ((rc = dev_alloc(b, &d.lvl_hist, W * (d.max_levels + 2)))) return rc;
+	if ((rc = dev_alloc(b, &d.aabb, W * std::max(d.NC, 1) * 6))) return rc;
+	if ((rc = dev_alloc(b, &d.cands, WP, false))) return rc;
+	if ((rc = dev_alloc(b, &d.cand_count, 1))) return rc;
 	if ((rc = dev_alloc(b, &d.hits, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.hit_count, 1))) return rc;
+	if ((rc = dev_alloc(b, &d.lvl_cap, (size_t)d.max_levels + 2))) return rc;
+	if ((rc = dev_alloc(b, &d.lvl_off, (size_t)d.max_levels + 2))) return rc;
+	if ((rc = dev_alloc(b, &d.lvl_fill, (size_t)d.max_levels + 2))) return rc;
+	if ((rc = dev_alloc(b, &d.lvl_max, 1))) return rc;
+	if ((rc = dev_alloc(b, &d.lvl_items, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.pair_normal, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.pair_coff, WP))) return rc;
 	if ((rc = dev_alloc(b, &d.pair_ccnt, WP))) return rc;
@@ -436,30 +475,53 @@ static void enqueue_prologue(rp_batch* b, double dt, int collisions) {
 	k_broad_scan<<<d.W, 256, 0, b->stream>>>(d);
 	k_broad_rows<true><<<rows, 128, 0, b->stream>>>(d);
 	k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
+	k_level_reset<<<1, 256, 0, b->stream>>>(d);
 	k_schedule<<<(d.W + 63) / 64, 64, 0, b->stream>>>(d, collisions);
+	k_level_offsets<<<1, 1, 0, b->stream>>>(d);
 }
+
+// Runs the prologue and waits for the one number the host needs to shape the rest of the frame: the deepest
+// dependency level over all worlds (= how many level launches each Gauss-Seidel sweep takes).
+static int prologue_levels(rp_batch* b, double dt, int collisions, int* levels) {
+	enqueue_prologue(b, dt, collisions);
+	RP_CUDA(cudaGetLastError());
+	RP_CUDA(cudaMemcpyAsync(b->levels_host, b->d.lvl_max, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+	RP_CUDA(cudaStreamSynchronize(b->stream));
+	*levels = *b->levels_host;
+	return RP_OK;
+}
+
+static unsigned int level_grid(const rp_batch* b) { return (unsigned int)b->sm_count * 8u; }
 
 static void enqueue_integrate(rp_batch* b, double h) {
 	const DevView& d = b->d;
-	const size_t WB = (size_t)d.W * d.NB;
-	k_integrate<<<(unsigned int)((WB + 127) / 128), 128, 0, b->stream>>>(d, h);
+	const size_t n = std::max((size_t)d.W * d.NB, (size_t)d.max_levels + 2);
+	k_integrate<<<(unsigned int)((n + 127) / 128), 128, 0, b->stream>>>(d, h);
 }
 static void enqueue_narrow(rp_batch* b) {
 	const DevView& d = b->d;
-	k_gjk<<<dim3(b->gjk_chunks, d.W), 128, 0, b->stream>>>(d);
+	k_cull<<<dim3(b->cull_chunks, d.W), 256, 0, b->stream>>>(d, b->cull);
+	k_gjk<<<b->sm_count * 8, 128, 0, b->stream>>>(d);
 	k_manifold<<<b->sm_count * 4, 128, 0, b->stream>>>(d);
 }
-static void enqueue_solve(rp_batch* b, double h, uint32_t iters, int collisions) {
-	k_solve<<<b->d.W, b->solve_threads, 0, b->stream>>>(b->d, h, (int)iters, collisions);
+static void enqueue_solve(rp_batch* b, double h, uint32_t iters, int collisions, int levels) {
+	const DevView& d = b->d;
+	for (uint32_t it = 0; it < iters; ++it) {
+		for (int l = 1; l <= levels; ++l) k_pos_level<<<level_grid(b), 128, 0, b->stream>>>(d, h, l, collisions);
+	}
+	const size_t WB = (size_t)d.W * d.NB;
+	k_derive<<<(unsigned int)((WB + 127) / 128), 128, 0, b->stream>>>(d, h);
+	if (collisions) {
+		for (int l = 1; l <= levels; ++l) k_vel_level<<<level_grid(b), 128, 0, b->stream>>>(d, h, l);
+	}
 }
 
-static void enqueue_frame(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int collisions) {
+static void enqueue_substeps(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int collisions, int levels) {
 	const double h = dt / substeps;  // pbd.cpp:472
-	enqueue_prologue(b, dt, collisions);
 	for (uint32_t s = 0; s < substeps; ++s) {
 		enqueue_integrate(b, h);
 		if (collisions) enqueue_narrow(b);
-		enqueue_solve(b, h, iters, collisions);
+		enqueue_solve(b, h, iters, collisions, levels);
 	}
 	k_count_frame<<<1, 1, 0, b->stream>>>(b->d);
 }
@@ -470,8 +532,10 @@ int rp_batch_step(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int
 	RP_CUDA(cudaSetDevice(b->device));
 	int rc = flush_forces(b);
 	if (rc) return rc;
+	int levels = 0;
+	if ((rc = prologue_levels(b, dt, collisions ? 1 : 0, &levels))) return rc;
 	GraphKey key;
-	key.dt = dt; key.substeps = substeps; key.iters = iters; key.collisions = collisions ? 1 : 0;
+	key.dt = dt; key.substeps = substeps; key.iters = iters; key.collisions = collisions ? 1 : 0; key.levels = levels;
 	if (!b->have_graph || !(b->graph_key == key)) {
 		if (b->graph_exec) cudaGraphExecDestroy(b->graph_exec);
 		if (b->graph) cudaGraphDestroy(b->graph);
@@ -479,7 +543,7 @@ int rp_batch_step(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int
 		b->graph = 0;
 		b->have_graph = false;
 		RP_CUDA(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
-		enqueue_frame(b, dt, substeps, iters, key.collisions);
+		enqueue_substeps(b, dt, substeps, iters, key.collisions, levels);
 		cudaError_t e = cudaStreamEndCapture(b->stream, &b->graph);
 		if (e != cudaSuccess) return fail(RP_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
 		RP_CUDA(cudaGraphInstantiate(&b->graph_exec, b->graph, 0));
@@ -632,8 +696,8 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t substeps, uint32_t ite
 	DevView& d = b->d;
 	d.dbg_world = (int)world;
 	const double h = dt / substeps;
-	enqueue_prologue(b, dt, collisions ? 1 : 0);
-	RP_CUDA(cudaGetLastError());
+	int levels = 0;
+	if ((rc = prologue_levels(b, dt, collisions ? 1 : 0, &levels))) return rc;
 	std::vector<int> np, active, ccnt, coff;
 	std::vector<PairRec> pr;
 	std::vector<BodyStatic> bs;
@@ -677,7 +741,7 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t substeps, uint32_t ite
 				if (nc - 1 < max_calls && calls_out) calls_out[4 * (nc - 1) + 2] += (uint32_t)ccnt[i];
 			}
 		}
-		enqueue_solve(b, h, iters, collisions ? 1 : 0);
+		enqueue_solve(b, h, iters, collisions ? 1 : 0, levels);
 	}
 	k_count_frame<<<1, 1, 0, b->stream>>>(d);
 	RP_CUDA(cudaGetLastError());
@@ -709,8 +773,8 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 		fam.push_back(family);
 		return RP_OK;
 	};
-	if ((rc = mark(-1))) return rc;
 	for (uint32_t f = 0; f < frames; ++f) {
+		if ((rc = mark(-1))) return rc;
 		dim3 rows((d.NB + 127) / 128, d.W);
 		k_broad_rows<false><<<rows, 128, 0, b->stream>>>(d);
 		k_broad_scan<<<d.W, 256, 0, b->stream>>>(d);
@@ -718,25 +782,42 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 		if ((rc = mark(RP_K_BROAD))) return rc;
 		k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
 		if ((rc = mark(RP_K_ISLANDS))) return rc;
+		k_level_reset<<<1, 256, 0, b->stream>>>(d);
 		k_schedule<<<(d.W + 63) / 64, 64, 0, b->stream>>>(d, collisions ? 1 : 0);
+		k_level_offsets<<<1, 1, 0, b->stream>>>(d);
 		if ((rc = mark(RP_K_SCHEDULE))) return rc;
+		RP_CUDA(cudaMemcpyAsync(b->levels_host, d.lvl_max, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+		RP_CUDA(cudaStreamSynchronize(b->stream));
+		const int levels = *b->levels_host;
+		if ((rc = mark(-1))) return rc;
 		for (uint32_t s = 0; s < substeps; ++s) {
 			enqueue_integrate(b, h);
 			if ((rc = mark(RP_K_INTEGRATE))) return rc;
 			if (collisions) {
-				k_gjk<<<dim3(b->gjk_chunks, d.W), 128, 0, b->stream>>>(d);
+				k_cull<<<dim3(b->cull_chunks, d.W), 256, 0, b->stream>>>(d, b->cull);
+				if ((rc = mark(RP_K_CULL))) return rc;
+				k_gjk<<<b->sm_count * 8, 128, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_GJK))) return rc;
 				k_manifold<<<b->sm_count * 4, 128, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_MANIFOLD))) return rc;
 			}
-			enqueue_solve(b, h, iters, collisions ? 1 : 0);
-			if ((rc = mark(RP_K_SOLVE))) return rc;
+			for (uint32_t it = 0; it < iters; ++it) {
+				for (int l = 1; l <= levels; ++l) k_pos_level<<<level_grid(b), 128, 0, b->stream>>>(d, h, l, collisions ? 1 : 0);
+			}
+			if ((rc = mark(RP_K_SOLVE_POS))) return rc;
+			k_derive<<<(unsigned int)(((size_t)d.W * d.NB + 127) / 128), 128, 0, b->stream>>>(d, h);
+			if ((rc = mark(RP_K_DERIVE))) return rc;
+			if (collisions) {
+				for (int l = 1; l <= levels; ++l) k_vel_level<<<level_grid(b), 128, 0, b->stream>>>(d, h, l);
+				if ((rc = mark(RP_K_SOLVE_VEL))) return rc;
+			}
 		}
 		k_count_frame<<<1, 1, 0, b->stream>>>(d);
 	}
 	RP_CUDA(cudaGetLastError());
 	RP_CUDA(cudaStreamSynchronize(b->stream));
 	for (size_t i = 1; i < ev.size(); ++i) {
+		if (fam[i] < 0) continue;
 		float ms = 0.f;
 		RP_CUDA(cudaEventElapsedTime(&ms, ev[i - 1], ev[i]));
 		ms_out[fam[i]] += ms;

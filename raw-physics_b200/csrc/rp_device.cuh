@@ -56,12 +56,25 @@ struct DevView {
 	int* label;          // [W][NB] island labels
 	int* isl_flag;       // [W][NB] island "all members may sleep"
 	int* last_level;     // [W][NB] schedule scratch
-	int* unit_level;     // [W][max_units]
-	int* sched;          // [W][max_units] units sorted by dependency level (stable)
-	int* level_ptr;      // [W][max_units + 2]
-	int* n_levels;       // [W]
+	int* pair_level;     // [W][max_pairs] dependency level of each broadphase pair (0 = skipped this frame)
+	int* lvl_hist;       // [W][max_levels + 2] schedule scratch (per-world level histogram)
+	double* aabb;        // [W][NC][6] world-space bounds of every collider (min xyz, max xyz)
+	uint2* cands;        // [W * max_pairs] (world, pair) that survived the skip rule and the bounds cull
+	unsigned int* cand_count;
 	HitRec* hits;        // [W * max_pairs]
 	unsigned int* hit_count;
+	// level-major work lists shared by all worlds: the pairs of dependency level l that have contacts this substep
+	int max_levels;
+	int* lvl_cap;        // [max_levels + 2] pairs scheduled at level l over all worlds (per frame)
+	int* lvl_off;        // [max_levels + 2] exclusive scan of lvl_cap
+	int* lvl_fill;       // [max_levels + 2] pairs of level l with contacts (per substep)
+	int* lvl_max;        // [1] deepest level of the frame over all worlds
+	uint2* lvl_items;    // [W * max_pairs] (world, pair), level l occupies [lvl_off[l], lvl_off[l] + lvl_fill[l])
+	// template-constant schedule of the external constraints (they head the constraint array in every world)
+	const int* joint_sched;   // [NJ] joints sorted by level
+	const int* joint_lptr;    // [joint_levels + 1]
+	const int* joint_last;    // [NB] level of the last joint touching each body (0 = none)
+	int joint_levels;
 	V3* pair_normal;     // [W][max_pairs]
 	int* pair_coff;      // [W][max_pairs]
 	int* pair_ccnt;      // [W][max_pairs]

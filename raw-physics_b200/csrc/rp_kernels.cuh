@@ -181,64 +181,70 @@ __global__ void __launch_bounds__(256) k_islands(DevView d, double dt) {
 // Units of the Gauss-Seidel sweep in the reference's array order: the external constraints first (copy_constraints
 // output is the head of the array, pbd.cpp:580), then the broadphase (collider-)pairs in pair order, each pair standing
 // for its whole manifold (pbd.cpp:584-611). level(u) = 1 + max(level of the previous unit touching either of u's
-// NON-FIXED bodies). One thread per world, once per frame; a stable counting sort by level gives the execution order.
+// NON-FIXED bodies). The joints' levels are the same in every world (host, at batch creation); this kernel continues
+// the recurrence over one world's pairs (one thread per world, once per frame) and adds the world's per-level pair
+// counts to the global capacities of the level-major work lists.
 __global__ void __launch_bounds__(64) k_schedule(DevView d, int collisions) {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= d.W) return;
 	int* last = d.last_level + (size_t)w * d.NB;
-	int* ulevel = d.unit_level + (size_t)w * d.max_units;
-	int* sched = d.sched + (size_t)w * d.max_units;
-	int* lptr = d.level_ptr + (size_t)w * (d.max_units + 2);
+	int* plevel = d.pair_level + (size_t)w * d.max_pairs;
+	int* hist = d.lvl_hist + (size_t)w * (d.max_levels + 2);
 	const int* active = d.active + (size_t)w * d.NB;
 	const PairRec* pairs = d.pairs + (size_t)w * d.max_pairs;
 	const int np = collisions ? d.n_pairs[w] : 0;
-	const int nu = d.NJ + np;
-	for (int b = 0; b < d.NB; ++b) last[b] = 0;
-	int nl = 0;
-	for (int u = 0; u < nu; ++u) {
-		int a, b;
-		if (u < d.NJ) {
-			a = d.joints[u].e1; b = d.joints[u].e2;
-		} else {
-			a = pairs[u - d.NJ].a; b = pairs[u - d.NJ].b;
-			// pbd.cpp:594: nothing to do when both sides are fixed or asleep
-			if ((d.bstat[a].fixed || !active[a]) && (d.bstat[b].fixed || !active[b])) {
-				ulevel[u] = 0;
-				continue;
-			}
+	for (int b = 0; b < d.NB; ++b) last[b] = d.joint_last[b];
+	int nl = d.joint_levels;
+	for (int p = 0; p < np; ++p) {
+		const int a = pairs[p].a, b = pairs[p].b;
+		const int fa = d.bstat[a].fixed, fb = d.bstat[b].fixed;
+		// pbd.cpp:594: nothing to do when both sides are fixed or asleep
+		if ((fa || !active[a]) && (fb || !active[b])) {
+			plevel[p] = 0;
+			continue;
 		}
-		int fa = d.bstat[a].fixed, fb = d.bstat[b].fixed;
-		int la = fa ? 0 : last[a], lb = fb ? 0 : last[b];
-		int lvl = 1 + (la > lb ? la : lb);
+		const int la = fa ? 0 : last[a], lb = fb ? 0 : last[b];
+		const int lvl = 1 + (la > lb ? la : lb);
 		if (!fa) last[a] = lvl;
 		if (!fb) last[b] = lvl;
-		ulevel[u] = lvl;
+		plevel[p] = lvl;
 		if (lvl > nl) nl = lvl;
 	}
-	for (int l = 0; l <= nl + 1; ++l) lptr[l] = 0;
-	for (int u = 0; u < nu; ++u) {
-		int l = ulevel[u];
-		if (l > 0) lptr[l + 1] += 1;
+	for (int l = 0; l <= nl + 1; ++l) hist[l] = 0;
+	for (int p = 0; p < np; ++p) hist[plevel[p]] += 1;
+	for (int l = 1; l <= nl; ++l) {
+		if (hist[l]) atomicAdd(&d.lvl_cap[l], hist[l]);
 	}
-	// lptr[l] = first slot of level l (levels are 1-based; lptr[1] = 0)
-	for (int l = 2; l <= nl + 1; ++l) lptr[l] += lptr[l - 1];
-	for (int u = 0; u < nu; ++u) {
-		int l = ulevel[u];
-		if (l > 0) sched[lptr[l]++] = u;   // after this loop lptr[l] = END of level l = start of level l + 1
-	}
-	// shift back so that level l spans [lptr[l-1], lptr[l]) with lptr[0] = 0
-	lptr[0] = 0;
-	d.n_levels[w] = nl;
+	atomicMax(d.lvl_max, nl);
 	atomicAdd(&d.counters[CNT_LEVELS], (unsigned long long)nl);
+}
+
+// zeroes the per-frame level capacities (before k_schedule) / turns them into list offsets (after it)
+__global__ void __launch_bounds__(256) k_level_reset(DevView d) {
+	for (int l = threadIdx.x; l < d.max_levels + 2; l += blockDim.x) d.lvl_cap[l] = 0;
+	if (threadIdx.x == 0) *d.lvl_max = 0;
+}
+__global__ void k_level_offsets(DevView d) {
+	int run = 0;
+	const int nl = *d.lvl_max;
+	for (int l = 0; l <= nl + 1; ++l) {
+		d.lvl_off[l] = run;
+		run += d.lvl_cap[l];
+	}
 }
 
 // ---------------------------------------------------------------------------------------- integrate + collider update
 // pbd.cpp:537-577 (integration) and collider.cpp:409-445 (collider_update) for one body per thread. The reference
 // re-transforms both colliders of every pair every substep (39 % of its time); the same pose gives the same result,
-// so once per body per substep is exactly equivalent.
+// so once per body per substep is exactly equivalent. Also leaves each collider's world-space bounds
+// for k_cull and resets the per-substep counters.
 __global__ void __launch_bounds__(128) k_integrate(DevView d, double h) {
 	const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (gid == 0) *d.hit_count = 0u;
+	if (gid == 0) {
+		*d.hit_count = 0u;
+		*d.cand_count = 0u;
+	}
+	if (gid < (size_t)d.max_levels + 2) d.lvl_fill[gid] = 0;
 	if (gid >= (size_t)d.W * d.NB) return;
 	const int w = (int)(gid / d.NB), b = (int)(gid % d.NB);
 	if (b == 0) d.n_contacts[w] = 0;
@@ -265,70 +271,117 @@ __global__ void __launch_bounds__(128) k_integrate(DevView d, double h) {
 	V3* tn = d.tn + (size_t)w * d.TN;
 	for (int c = s.col0; c < s.col0 + s.ncol; ++c) {
 		const ColliderDesc cd = d.cols[c];
+		double* bb = d.aabb + ((size_t)w * d.NC + c) * 6;
 		if (cd.type == SHAPE_SPHERE) {
 			tv[cd.tv0] = body.x;
+			const double r = (double)cd.radius;
+			bb[0] = body.x.x - r; bb[1] = body.x.y - r; bb[2] = body.x.z - r;
+			bb[3] = body.x.x + r; bb[4] = body.x.y + r; bb[5] = body.x.z + r;
 		} else {
 			const HullTopo t = d.pool.hulls[cd.hull];
-			for (int k = 0; k < t.nv; ++k) tv[cd.tv0 + k] = transform_point(M, d.pool.verts[t.vert0 + k]);
+			double lo0 = 1.7976931348623157e308, lo1 = lo0, lo2 = lo0, hi0 = -lo0, hi1 = -lo0, hi2 = -lo0;
+			for (int k = 0; k < t.nv; ++k) {
+				const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
+				tv[cd.tv0 + k] = p;
+				lo0 = fmin(lo0, p.x); lo1 = fmin(lo1, p.y); lo2 = fmin(lo2, p.z);
+				hi0 = fmax(hi0, p.x); hi1 = fmax(hi1, p.y); hi2 = fmax(hi2, p.z);
+			}
 			for (int k = 0; k < t.nf; ++k) tn[cd.tn0 + k] = transform_normal(M, d.pool.normals[t.face0 + k]);
+			bb[0] = lo0; bb[1] = lo1; bb[2] = lo2; bb[3] = hi0; bb[4] = hi1; bb[5] = hi2;
 		}
 	}
 }
 
-// ----------------------------------------------------------------------------------------------------- narrowphase 1
-// One thread per (world, collider pair): the pbd.cpp:594 skip rule, then sphere-sphere or boolean GJK
-// (collider.cpp:523-547). Colliding pairs are appended to the global hit list for k_manifold.
-__global__ void __launch_bounds__(128) k_gjk(DevView d) {
+// warp-aggregated append: every lane of the warp calls this; lanes with want == true get consecutive slots
+__device__ __forceinline__ unsigned int warp_append(unsigned int* counter, bool want) {
+	const unsigned int mask = __ballot_sync(0xffffffffu, want);
+	if (!mask) return 0u;
+	const int lane = threadIdx.x & 31;
+	const int leader = __ffs(mask) - 1;
+	unsigned int base = 0;
+	if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(mask));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// ------------------------------------------------------------------------------------------------------------- cull
+// One thread per (world, collider pair): the pbd.cpp:594 skip rule, then an exact-safe bounds test. If the world-space
+// boxes of the two colliders (bounds of the very vertex sets GJK would scan; sphere: centre +/- radius, its support set)
+// are separated by more than RP_CULL_MARGIN along an axis, every Minkowski-difference support point has that coordinate
+// strictly positive (or strictly negative), the origin is outside the difference, and gjk_collides returns false: the
+// pair yields no contacts, exactly as if GJK had run. Survivors go to the dense candidate list of k_gjk.
+#define RP_CULL_MARGIN 1e-7
+__global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 	const int w = blockIdx.y;
 	const int np = d.n_pairs[w];
 	const int* active = d.active + (size_t)w * d.NB;
-	const V3* tv = d.tv + (size_t)w * d.TV;
-	const V3* tn = d.tn + (size_t)w * d.TN;
-	const int lane = threadIdx.x & 31;
 	int tested = 0;
-	// whole warps iterate together (np rounded up per warp) so the ballot below always sees converged lanes
 	for (int p0 = blockIdx.x * blockDim.x; p0 < np; p0 += gridDim.x * blockDim.x) {
 		const int p = p0 + threadIdx.x;
-		bool hit = false;
-		Simplex s;
-		s.a = s.b = s.c = s.d = v3(0.0, 0.0, 0.0);
-		size_t pg = 0;
+		bool keep = false;
 		if (p < np) {
-			pg = (size_t)w * d.max_pairs + p;
+			const size_t pg = (size_t)w * d.max_pairs + p;
 			d.pair_ccnt[pg] = 0;
 			const PairRec pr = d.pairs[pg];
 			if (!((d.bstat[pr.a].fixed || !active[pr.a]) && (d.bstat[pr.b].fixed || !active[pr.b]))) {
-				Shape A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
-				Shape B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
-				int st = 0;
-				if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
-					V3 n;
-					double depth;
-					hit = sphere_sphere(A, B, &n, &depth);
-				} else {
-					hit = gjk(A, B, &s, &st, 0);
-				}
-				if (st) atomicOr(&d.status[w], st);
 				++tested;
+				keep = true;
+				if (cull) {
+					const double* A = d.aabb + ((size_t)w * d.NC + pr.ca) * 6;
+					const double* B = d.aabb + ((size_t)w * d.NC + pr.cb) * 6;
+					const bool both_spheres = d.cols[pr.ca].type == SHAPE_SPHERE && d.cols[pr.cb].type == SHAPE_SPHERE;
+					if (!both_spheres) {  // sphere-sphere pairs never reach GJK (collider.cpp:530)
+						for (int k = 0; k < 3; ++k) {
+							if (A[k] - B[3 + k] > RP_CULL_MARGIN || B[k] - A[3 + k] > RP_CULL_MARGIN) keep = false;
+						}
+					}
+				}
 			}
 		}
-		// warp-aggregated append to the global hit list
-		const unsigned int mask = __ballot_sync(0xffffffffu, hit);
-		if (mask) {
-			const int leader = __ffs(mask) - 1;
-			unsigned int base = 0;
-			if (lane == leader) base = atomicAdd(d.hit_count, (unsigned int)__popc(mask));
-			base = __shfl_sync(0xffffffffu, base, leader);
-			if (hit) {
-				HitRec hr;
-				hr.world = w; hr.pair = p;
-				hr.sa = s.a; hr.sb = s.b; hr.sc = s.c; hr.sd = s.d;
-				d.hits[base + __popc(mask & ((1u << lane) - 1u))] = hr;
-			}
-		}
+		const unsigned int slot = warp_append(d.cand_count, keep);
+		if (keep) d.cands[slot] = make_uint2((unsigned int)w, (unsigned int)p);
 	}
 	for (int o = 16; o > 0; o >>= 1) tested += __shfl_down_sync(0xffffffffu, tested, o);
-	if (lane == 0 && tested) atomicAdd(&d.counters[CNT_PAIR_TESTS], (unsigned long long)tested);
+	if ((threadIdx.x & 31) == 0 && tested) atomicAdd(&d.counters[CNT_PAIR_TESTS], (unsigned long long)tested);
+}
+
+// ----------------------------------------------------------------------------------------------------- narrowphase 1
+// One thread per candidate pair: sphere-sphere test or boolean GJK (collider.cpp:523-547). Colliding pairs are appended
+// to the global hit list for k_manifold.
+__global__ void __launch_bounds__(128) k_gjk(DevView d) {
+	const unsigned int nc = *d.cand_count;
+	for (unsigned int c0 = blockIdx.x * blockDim.x; c0 < nc; c0 += gridDim.x * blockDim.x) {
+		const unsigned int ci = c0 + threadIdx.x;
+		bool hit = false;
+		Simplex s;
+		s.a = s.b = s.c = s.d = v3(0.0, 0.0, 0.0);
+		int w = 0, p = 0;
+		if (ci < nc) {
+			const uint2 cd = d.cands[ci];
+			w = (int)cd.x; p = (int)cd.y;
+			const PairRec pr = d.pairs[(size_t)w * d.max_pairs + p];
+			const V3* tv = d.tv + (size_t)w * d.TV;
+			const V3* tn = d.tn + (size_t)w * d.TN;
+			Shape A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
+			Shape B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
+			int st = 0;
+			if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
+				V3 n;
+				double depth;
+				hit = sphere_sphere(A, B, &n, &depth);
+			} else {
+				hit = gjk(A, B, &s, &st, 0);
+			}
+			if (st) atomicOr(&d.status[w], st);
+		}
+		const unsigned int slot = warp_append(d.hit_count, hit);
+		if (hit) {
+			HitRec hr;
+			hr.world = w; hr.pair = p;
+			hr.sa = s.a; hr.sb = s.b; hr.sc = s.c; hr.sd = s.d;
+			d.hits[slot] = hr;
+		}
+	}
 }
 
 // ----------------------------------------------------------------------------------------------------- narrowphase 2
@@ -356,183 +409,197 @@ struct ManifoldScratch {
 
 // One thread per colliding collider pair: EPA (epa.cpp:118), manifold (clipping.cpp:343), contact -> constraint
 // (pbd.cpp:408-424). The pair's contacts get a contiguous run in the world's contact buffer (allocation order between
-// pairs is irrelevant: the solver walks pairs, not the buffer).
+// pairs is irrelevant: the solver walks pairs, not the buffer), and the pair is appended to the work list of its
+// dependency level.
 __global__ void __launch_bounds__(128) k_manifold(DevView d) {
 	const unsigned int nh = *d.hit_count;
 	ManifoldScratch sc;
 	int made = 0;
-	for (unsigned int hi = blockIdx.x * blockDim.x + threadIdx.x; hi < nh; hi += gridDim.x * blockDim.x) {
-		const HitRec hr = d.hits[hi];
-		const int w = hr.world;
-		const size_t pg = (size_t)w * d.max_pairs + hr.pair;
-		const PairRec pr = d.pairs[pg];
-		const V3* tv = d.tv + (size_t)w * d.TV;
-		const V3* tn = d.tn + (size_t)w * d.TN;
-		Shape A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
-		Shape B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
-		V3 normal;
-		double depth;
-		int st = 0;
-		bool ok;
-		if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
-			ok = sphere_sphere(A, B, &normal, &depth);
-		} else {
-			Simplex s;
-			s.a = hr.sa; s.b = hr.sb; s.c = hr.sc; s.d = hr.sd;
-			s.num = 4;
-			ok = epa(A, B, s, sc.epa, &normal, &depth, &st, 0);
-		}
-		int n = 0;
-		if (ok) {
-			StageSink sink;
-			sink.stage = sc.m.stage;
-			sink.n = 0;
-			sink.cap = RP_CLIP_MAX_POINTS;
-			manifold(A, B, normal, depth, sc.m.clip, &st, sink);
-			n = sink.n;
-			if (n > sink.cap) {
-				st |= ST_CLIP_CAPACITY;
-				n = sink.cap;
+	const int lane = threadIdx.x & 31;
+	for (unsigned int h0 = blockIdx.x * blockDim.x; h0 < nh; h0 += gridDim.x * blockDim.x) {
+		const unsigned int hi = h0 + threadIdx.x;
+		int n = 0, lvl = -1, w = 0, pair = 0;
+		if (hi < nh) {
+			const HitRec hr = d.hits[hi];
+			w = hr.world; pair = hr.pair;
+			const size_t pg = (size_t)w * d.max_pairs + hr.pair;
+			const PairRec pr = d.pairs[pg];
+			const V3* tv = d.tv + (size_t)w * d.TV;
+			const V3* tn = d.tn + (size_t)w * d.TN;
+			Shape A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
+			Shape B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
+			V3 normal;
+			double depth;
+			int st = 0;
+			bool ok;
+			if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
+				ok = sphere_sphere(A, B, &normal, &depth);
+			} else {
+				Simplex s;
+				s.a = hr.sa; s.b = hr.sb; s.c = hr.sc; s.d = hr.sd;
+				s.num = 4;
+				ok = epa(A, B, s, sc.epa, &normal, &depth, &st, 0);
 			}
-		}
-		if (n > 0) {
-			int off = atomicAdd(&d.n_contacts[w], n);
-			if (off + n > d.max_contacts) {
-				st |= ST_CONTACT_CAPACITY;
-				n = d.max_contacts - off;
-				if (n < 0) n = 0;
-			}
-			const BodyDyn& da = d.dyn[(size_t)w * d.NB + pr.a];
-			const BodyDyn& db = d.dyn[(size_t)w * d.NB + pr.b];
-			Body b1, b2;
-			b1.x = ld3(da.x); b1.q = ld4(da.q);
-			b2.x = ld3(db.x); b2.q = ld4(db.q);
-			Contact* out = d.contacts + (size_t)w * d.max_contacts + off;
-			for (int k = 0; k < n; ++k) {
-				out[k] = make_contact(b1, b2, sc.m.stage[2 * k], sc.m.stage[2 * k + 1]);
-				if (w == d.dbg_world) {
-					d.dbg_points[2 * (off + k)] = sc.m.stage[2 * k];
-					d.dbg_points[2 * (off + k) + 1] = sc.m.stage[2 * k + 1];
+			if (ok) {
+				StageSink sink;
+				sink.stage = sc.m.stage;
+				sink.n = 0;
+				sink.cap = RP_CLIP_MAX_POINTS;
+				manifold(A, B, normal, depth, sc.m.clip, &st, sink);
+				n = sink.n;
+				if (n > sink.cap) {
+					st |= ST_CLIP_CAPACITY;
+					n = sink.cap;
 				}
 			}
-			d.pair_normal[pg] = normal;
-			d.pair_coff[pg] = off;
-			d.pair_ccnt[pg] = n;
-			made += n;
+			if (n > 0) {
+				int off = atomicAdd(&d.n_contacts[w], n);
+				if (off + n > d.max_contacts) {
+					st |= ST_CONTACT_CAPACITY;
+					n = d.max_contacts - off;
+					if (n < 0) n = 0;
+				}
+				const BodyDyn& da = d.dyn[(size_t)w * d.NB + pr.a];
+				const BodyDyn& db = d.dyn[(size_t)w * d.NB + pr.b];
+				Body b1, b2;
+				b1.x = ld3(da.x); b1.q = ld4(da.q);
+				b2.x = ld3(db.x); b2.q = ld4(db.q);
+				Contact* out = d.contacts + (size_t)w * d.max_contacts + off;
+				for (int k = 0; k < n; ++k) {
+					out[k] = make_contact(b1, b2, sc.m.stage[2 * k], sc.m.stage[2 * k + 1]);
+					if (w == d.dbg_world) {
+						d.dbg_points[2 * (off + k)] = sc.m.stage[2 * k];
+						d.dbg_points[2 * (off + k) + 1] = sc.m.stage[2 * k + 1];
+					}
+				}
+				d.pair_normal[pg] = normal;
+				d.pair_coff[pg] = off;
+				d.pair_ccnt[pg] = n;
+				made += n;
+				if (n > 0) lvl = d.pair_level[pg];
+			}
+			if (st) atomicOr(&d.status[w], st);
 		}
-		if (st) atomicOr(&d.status[w], st);
+		// append (world, pair) to the list of its level; lanes of one warp that share a level share one atomic
+		const unsigned int peers = __match_any_sync(0xffffffffu, lvl);
+		if (lvl > 0) {
+			const int leader = __ffs(peers) - 1;
+			int base = 0;
+			if (lane == leader) base = atomicAdd(&d.lvl_fill[lvl], __popc(peers));
+			base = __shfl_sync(peers, base, leader);
+			d.lvl_items[d.lvl_off[lvl] + base + __popc(peers & ((1u << lane) - 1u))] = make_uint2((unsigned int)w, (unsigned int)pair);
+		}
 	}
 	for (int o = 16; o > 0; o >>= 1) made += __shfl_down_sync(0xffffffffu, made, o);
-	if ((threadIdx.x & 31) == 0 && made) atomicAdd(&d.counters[CNT_CONTACTS], (unsigned long long)made);
+	if (lane == 0 && made) atomicAdd(&d.counters[CNT_CONTACTS], (unsigned long long)made);
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&d.counters[CNT_HITS], (unsigned long long)nh);
 }
 
 // -------------------------------------------------------------------------------------------------------------- solve
-// One CTA per world. Positional Gauss-Seidel sweep(s) level by level (pbd.cpp:615-620), velocity derivation
-// (pbd.cpp:623-643), then the velocity pass over the contacts in the same level order (pbd.cpp:646-711).
-__global__ void k_solve(DevView d, double h, int iters, int collisions) {
-	const int w = blockIdx.x;
-	BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
-	const int* active = d.active + (size_t)w * d.NB;
-	const int* sched = d.sched + (size_t)w * d.max_units;
-	const int* lptr = d.level_ptr + (size_t)w * (d.max_units + 2);
-	const PairRec* pairs = d.pairs + (size_t)w * d.max_pairs;
-	const int nl = d.n_levels[w];
-	Contact* contacts = d.contacts + (size_t)w * d.max_contacts;
-	int st = 0;
-
-	for (int it = 0; it < iters; ++it) {
-		for (int l = 1; l <= nl; ++l) {
-			const int u0 = lptr[l - 1], u1 = lptr[l];
-			for (int k = u0 + threadIdx.x; k < u1; k += blockDim.x) {
-				const int u = sched[k];
-				if (u < d.NJ) {
-					const Joint j = d.joints[u];
-					Body b1, b2;
-					load_static(b1, d.bstat[j.e1]);
-					load_static(b2, d.bstat[j.e2]);
-					BodyDyn& d1 = dyn[j.e1];
-					BodyDyn& d2 = dyn[j.e2];
-					b1.x = ld3(d1.x); b1.q = ld4(d1.q);
-					b2.x = ld3(d2.x); b2.q = ld4(d2.q);
-					JointLambda lam = d.lambdas[(size_t)w * d.NJ + u];
-					solve_joint(j, lam, b1, b2, h, &st);
-					d.lambdas[(size_t)w * d.NJ + u] = lam;
-					if (!b1.fixed) { st3(d1.x, b1.x); st4(d1.q, b1.q); }
-					if (!b2.fixed) { st3(d2.x, b2.x); st4(d2.q, b2.q); }
-				} else if (collisions) {
-					const int p = u - d.NJ;
-					const size_t pg = (size_t)w * d.max_pairs + p;
-					const int cnt = d.pair_ccnt[pg];
-					if (cnt == 0) continue;
-					const PairRec pr = pairs[p];
-					const V3 normal = d.pair_normal[pg];
-					Contact* cs = contacts + d.pair_coff[pg];
-					Body b1, b2;
-					load_static(b1, d.bstat[pr.a]);
-					load_static(b2, d.bstat[pr.b]);
-					BodyDyn& d1 = dyn[pr.a];
-					BodyDyn& d2 = dyn[pr.b];
-					b1.x = ld3(d1.x); b1.q = ld4(d1.q); b1.px = ld3(d1.px); b1.pq = ld4(d1.pq);
-					b2.x = ld3(d2.x); b2.q = ld4(d2.q); b2.px = ld3(d2.px); b2.pq = ld4(d2.pq);
-					for (int c = 0; c < cnt; ++c) {
-						Contact ct = cs[c];
-						solve_contact(ct, normal, b1, b2, h, &st);
-						cs[c].lambda_n = ct.lambda_n;
-						cs[c].lambda_t = ct.lambda_t;
-					}
-					if (!b1.fixed) { st3(d1.x, b1.x); st4(d1.q, b1.q); }
-					if (!b2.fixed) { st3(d2.x, b2.x); st4(d2.q, b2.q); }
-				}
+// Level-major Gauss-Seidel across ALL worlds: launch l runs every constraint of dependency level l, one thread per
+// unit -- the joints of level l of every world, then the (world, pair) items of level l that have contacts this substep
+// (a pair's manifold is a sequential chain on its two bodies and stays in one thread, bodies in registers). Kernel
+// boundaries are the barriers between levels, so the result equals the reference's sequential sweep (pbd.cpp:615-620).
+__global__ void __launch_bounds__(128) k_pos_level(DevView d, double h, int level, int collisions) {
+	const int nj = level <= d.joint_levels ? d.joint_lptr[level] - d.joint_lptr[level - 1] : 0;
+	const int njw = nj * d.W;
+	const int np = collisions ? d.lvl_fill[level] : 0;
+	int st = 0, stw = 0;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < njw + np; i += gridDim.x * blockDim.x) {
+		if (i < njw) {
+			const int w = i / nj;
+			const int u = d.joint_sched[d.joint_lptr[level - 1] + i % nj];
+			const Joint j = d.joints[u];
+			BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
+			Body b1, b2;
+			load_static(b1, d.bstat[j.e1]);
+			load_static(b2, d.bstat[j.e2]);
+			BodyDyn& d1 = dyn[j.e1];
+			BodyDyn& d2 = dyn[j.e2];
+			b1.x = ld3(d1.x); b1.q = ld4(d1.q);
+			b2.x = ld3(d2.x); b2.q = ld4(d2.q);
+			JointLambda lam = d.lambdas[(size_t)w * d.NJ + u];
+			solve_joint(j, lam, b1, b2, h, &st);
+			d.lambdas[(size_t)w * d.NJ + u] = lam;
+			if (!b1.fixed) { st3(d1.x, b1.x); st4(d1.q, b1.q); }
+			if (!b2.fixed) { st3(d2.x, b2.x); st4(d2.q, b2.q); }
+			stw = w;
+		} else {
+			const uint2 item = d.lvl_items[d.lvl_off[level] + (i - njw)];
+			const int w = (int)item.x;
+			const size_t pg = (size_t)w * d.max_pairs + item.y;
+			const int cnt = d.pair_ccnt[pg];
+			const PairRec pr = d.pairs[pg];
+			const V3 normal = d.pair_normal[pg];
+			Contact* cs = d.contacts + (size_t)w * d.max_contacts + d.pair_coff[pg];
+			BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
+			Body b1, b2;
+			load_static(b1, d.bstat[pr.a]);
+			load_static(b2, d.bstat[pr.b]);
+			BodyDyn& d1 = dyn[pr.a];
+			BodyDyn& d2 = dyn[pr.b];
+			b1.x = ld3(d1.x); b1.q = ld4(d1.q); b1.px = ld3(d1.px); b1.pq = ld4(d1.pq);
+			b2.x = ld3(d2.x); b2.q = ld4(d2.q); b2.px = ld3(d2.px); b2.pq = ld4(d2.pq);
+			for (int c = 0; c < cnt; ++c) {
+				Contact ct = cs[c];
+				solve_contact(ct, normal, b1, b2, h, &st);
+				cs[c].lambda_n = ct.lambda_n;
+				cs[c].lambda_t = ct.lambda_t;
 			}
-			__syncthreads();
+			if (!b1.fixed) { st3(d1.x, b1.x); st4(d1.q, b1.q); }
+			if (!b2.fixed) { st3(d2.x, b2.x); st4(d2.q, b2.q); }
+			stw = w;
+		}
+		if (st) {
+			atomicOr(&d.status[stw], st);
+			st = 0;
 		}
 	}
+}
 
-	for (int b = threadIdx.x; b < d.NB; b += blockDim.x) {
-		Body body;
-		body.fixed = d.bstat[b].fixed;
-		body.active = active[b];
-		if (body.fixed || !body.active) continue;
-		BodyDyn& dd = dyn[b];
-		body.x = ld3(dd.x); body.q = ld4(dd.q); body.px = ld3(dd.px); body.pq = ld4(dd.pq);
-		body.v = ld3(dd.v); body.w = ld3(dd.w);
-		derive_velocity(body, h);
-		st3(dd.v, body.v); st3(dd.w, body.w); st3(dd.pv, body.pv); st3(dd.pw, body.pw);
-	}
-	__syncthreads();
+// velocity derivation (pbd.cpp:623-643), one thread per body
+__global__ void __launch_bounds__(128) k_derive(DevView d, double h) {
+	const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= (size_t)d.W * d.NB) return;
+	const int b = (int)(gid % d.NB);
+	Body body;
+	body.fixed = d.bstat[b].fixed;
+	body.active = d.active[gid];
+	if (body.fixed || !body.active) return;
+	BodyDyn& dd = d.dyn[gid];
+	body.x = ld3(dd.x); body.q = ld4(dd.q); body.px = ld3(dd.px); body.pq = ld4(dd.pq);
+	body.v = ld3(dd.v); body.w = ld3(dd.w);
+	derive_velocity(body, h);
+	st3(dd.v, body.v); st3(dd.w, body.w); st3(dd.pv, body.pv); st3(dd.pw, body.pw);
+}
 
-	if (collisions) {
-		for (int l = 1; l <= nl; ++l) {
-			const int u0 = lptr[l - 1], u1 = lptr[l];
-			for (int k = u0 + threadIdx.x; k < u1; k += blockDim.x) {
-				const int u = sched[k];
-				if (u < d.NJ) continue;  // the hinge branch of the velocity pass is an empty TODO (pbd.cpp:712-739)
-				const int p = u - d.NJ;
-				const size_t pg = (size_t)w * d.max_pairs + p;
-				const int cnt = d.pair_ccnt[pg];
-				if (cnt == 0) continue;
-				const PairRec pr = pairs[p];
-				const V3 normal = d.pair_normal[pg];
-				const Contact* cs = contacts + d.pair_coff[pg];
-				Body b1, b2;
-				load_static(b1, d.bstat[pr.a]);
-				load_static(b2, d.bstat[pr.b]);
-				BodyDyn& d1 = dyn[pr.a];
-				BodyDyn& d2 = dyn[pr.b];
-				b1.q = ld4(d1.q); b1.v = ld3(d1.v); b1.w = ld3(d1.w); b1.pv = ld3(d1.pv); b1.pw = ld3(d1.pw);
-				b2.q = ld4(d2.q); b2.v = ld3(d2.v); b2.w = ld3(d2.w); b2.pv = ld3(d2.pv); b2.pw = ld3(d2.pw);
-				for (int c = 0; c < cnt; ++c) {
-					const Contact ct = cs[c];
-					solve_contact_velocity(ct, normal, b1, b2, h);
-				}
-				if (!b1.fixed) { st3(d1.v, b1.v); st3(d1.w, b1.w); }
-				if (!b2.fixed) { st3(d2.v, b2.v); st3(d2.w, b2.w); }
-			}
-			__syncthreads();
+// velocity pass over the contacts of one level (pbd.cpp:646-711); the hinge branch of the reference's velocity pass is
+// an empty TODO (pbd.cpp:712-739), so joints take no part
+__global__ void __launch_bounds__(128) k_vel_level(DevView d, double h, int level) {
+	const int np = d.lvl_fill[level];
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+		const uint2 item = d.lvl_items[d.lvl_off[level] + i];
+		const int w = (int)item.x;
+		const size_t pg = (size_t)w * d.max_pairs + item.y;
+		const int cnt = d.pair_ccnt[pg];
+		const PairRec pr = d.pairs[pg];
+		const V3 normal = d.pair_normal[pg];
+		const Contact* cs = d.contacts + (size_t)w * d.max_contacts + d.pair_coff[pg];
+		BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
+		Body b1, b2;
+		load_static(b1, d.bstat[pr.a]);
+		load_static(b2, d.bstat[pr.b]);
+		BodyDyn& d1 = dyn[pr.a];
+		BodyDyn& d2 = dyn[pr.b];
+		b1.q = ld4(d1.q); b1.v = ld3(d1.v); b1.w = ld3(d1.w); b1.pv = ld3(d1.pv); b1.pw = ld3(d1.pw);
+		b2.q = ld4(d2.q); b2.v = ld3(d2.v); b2.w = ld3(d2.w); b2.pv = ld3(d2.pv); b2.pw = ld3(d2.pw);
+		for (int c = 0; c < cnt; ++c) {
+			const Contact ct = cs[c];
+			solve_contact_velocity(ct, normal, b1, b2, h);
 		}
+		if (!b1.fixed) { st3(d1.v, b1.v); st3(d1.w, b1.w); }
+		if (!b2.fixed) { st3(d2.v, b2.v); st3(d2.w, b2.w); }
 	}
-	if (st) atomicOr(&d.status[w], st);
 }
 
 // ------------------------------------------------------------------------------------------------ FP64 pipe probe

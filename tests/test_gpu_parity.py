@@ -218,3 +218,32 @@ def test_large_batch_invariants(pkg):
     assert np.array_equal(got[0, :, :15], GOLD["w256/state/5"])
     assert (got == got[0][None]).all()
     assert not b.status().any()
+
+
+@pytest.mark.parametrize("name", ["w256", "pile", "tumble", "coin", "mirror_cube", "cube_storm"])
+def test_bounds_cull_changes_nothing(pkg, name):
+    """k_cull's bounds test must be invisible: with and without it the batch evolves bit-identically (and the number of
+    narrowphase pair visits, which the cull does not change, stays the reference's)."""
+    kw = dict(n_side=3) if name == "pile" else {}
+    sc = scenes.BUILDERS[name](**kw)
+    frames = 25 if name == "w256" else 90
+    a = make(pkg, sc, n_worlds=2)
+    b = make(pkg, sc, n_worlds=2, disable_cull=True)
+    for _ in range(frames):
+        step(a, sc)
+        step(b, sc)
+    assert np.array_equal(a.state(), b.state())
+    ca, cb = a.counters(), b.counters()
+    assert ca["pair_tests"] == cb["pair_tests"] and ca["contacts"] == cb["contacts"] and ca["gjk_hits"] == cb["gjk_hits"]
+
+
+def test_brick_wall_32x32_single_scene(pkg, oracle_flavour):
+    """Config 3: one large scene (1025 bodies), deep dependency chains; level-major solve vs the sequential oracle."""
+    sc = scenes.brick_wall(rows=32, cols=32)
+    b = make(pkg, sc)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    for f in range(3):
+        step(b, sc)
+        o.step()
+        assert np.array_equal(b.state()[0, :, :15], o.state()), f
+    assert not b.status().any()

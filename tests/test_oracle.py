@@ -153,3 +153,16 @@ def test_broadphase_pairs_match_reference():
         p.step()
     assert np.array_equal(r.broad_pairs(), p.broad_pairs())
     assert len(r.broad_pairs()) > 27
+
+
+def test_bounds_cull_is_sound_for_reference_gjk():
+    """The CUDA path skips GJK for collider pairs whose world-space bounds are separated by > 1e-7 (k_cull). That is only
+    exact if the reference-order GJK (with its quirks q2/q3) never reports such a pair as colliding: probed here on 1.5 M
+    random box / octahedron pairs, a quarter axis-aligned, a seventh nearly touching."""
+    import ctypes as C
+    L = C.CDLL(refdrv.lib_path("port"))
+    L.port_cull_soundness.restype = C.c_uint64
+    L.port_cull_soundness.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    sep, hits = C.c_uint64(), C.c_uint64()
+    assert L.port_cull_soundness(1500000, 2024, C.byref(sep), C.byref(hits)) == 0
+    assert sep.value > 300000 and hits.value > 300000
