@@ -398,7 +398,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.hit_count, 1))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_cap, (size_t)d.max_levels + 2))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_off, (size_t)d.max_levels + 2))) return rc;
-	if ((rc = dev_alloc(b, &d.lvl_fill, (size_t)d.max_levels + 2))) return rc;
+	if ((rc = dev_alloc(b, &d.lvl_fill, ((size_t)d.max_levels + 2) * RP_LVL_STRIDE))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_max, 1))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_items, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.pair_normal, WP, false))) return rc;

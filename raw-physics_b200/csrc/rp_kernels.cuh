@@ -10,6 +10,9 @@
 
 #include "rp_device.cuh"
 
+#define RP_LVL_SMEM 64     // levels ranked through shared memory in k_manifold
+#define RP_LVL_STRIDE 32   // ints between consecutive level fill counters (one 128-byte line each)
+
 namespace rp {
 
 // ------------------------------------------------------------------------------------------------------ body access
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(128) k_integrate(DevView d, double h) {
 		*d.hit_count = 0u;
 		*d.cand_count = 0u;
 	}
-	if (gid < (size_t)d.max_levels + 2) d.lvl_fill[gid] = 0;
+	if (gid < (size_t)d.max_levels + 2) d.lvl_fill[gid * RP_LVL_STRIDE] = 0;
 	if (gid >= (size_t)d.W * d.NB) return;
 	const int w = (int)(gid / d.NB), b = (int)(gid % d.NB);
 	if (b == 0) d.n_contacts[w] = 0;
@@ -414,6 +417,7 @@ struct ManifoldScratch {
 __global__ void __launch_bounds__(128) k_manifold(DevView d) {
 	const unsigned int nh = *d.hit_count;
 	ManifoldScratch sc;
+	__shared__ int s_cnt[RP_LVL_SMEM], s_base[RP_LVL_SMEM];
 	int made = 0;
 	const int lane = threadIdx.x & 31;
 	for (unsigned int h0 = blockIdx.x * blockDim.x; h0 < nh; h0 += gridDim.x * blockDim.x) {
@@ -480,14 +484,24 @@ __global__ void __launch_bounds__(128) k_manifold(DevView d) {
 			}
 			if (st) atomicOr(&d.status[w], st);
 		}
-		// append (world, pair) to the list of its level; lanes of one warp that share a level share one atomic
-		const unsigned int peers = __match_any_sync(0xffffffffu, lvl);
+		// append (world, pair) to the list of its level: ranks within the CTA through shared-memory counters, then ONE
+		// global atomic per (CTA, level) on a counter that owns its 128-byte line (RP_LVL_STRIDE)
+		__syncthreads();
+		if (threadIdx.x < RP_LVL_SMEM) s_cnt[threadIdx.x] = 0;
+		__syncthreads();
+		int rank = 0;
 		if (lvl > 0) {
-			const int leader = __ffs(peers) - 1;
-			int base = 0;
-			if (lane == leader) base = atomicAdd(&d.lvl_fill[lvl], __popc(peers));
-			base = __shfl_sync(peers, base, leader);
-			d.lvl_items[d.lvl_off[lvl] + base + __popc(peers & ((1u << lane) - 1u))] = make_uint2((unsigned int)w, (unsigned int)pair);
+			if (lvl < RP_LVL_SMEM) rank = atomicAdd(&s_cnt[lvl], 1);
+			else rank = atomicAdd(&d.lvl_fill[(size_t)lvl * RP_LVL_STRIDE], 1);  // very deep schedules: direct
+		}
+		__syncthreads();
+		if (threadIdx.x < RP_LVL_SMEM && s_cnt[threadIdx.x] > 0) {
+			s_base[threadIdx.x] = atomicAdd(&d.lvl_fill[(size_t)threadIdx.x * RP_LVL_STRIDE], s_cnt[threadIdx.x]);
+		}
+		__syncthreads();
+		if (lvl > 0) {
+			const int slot = (lvl < RP_LVL_SMEM ? s_base[lvl] : 0) + rank;
+			d.lvl_items[d.lvl_off[lvl] + slot] = make_uint2((unsigned int)w, (unsigned int)pair);
 		}
 	}
 	for (int o = 16; o > 0; o >>= 1) made += __shfl_down_sync(0xffffffffu, made, o);
@@ -503,7 +517,7 @@ __global__ void __launch_bounds__(128) k_manifold(DevView d) {
 __global__ void __launch_bounds__(128) k_pos_level(DevView d, double h, int level, int collisions) {
 	const int nj = level <= d.joint_levels ? d.joint_lptr[level] - d.joint_lptr[level - 1] : 0;
 	const int njw = nj * d.W;
-	const int np = collisions ? d.lvl_fill[level] : 0;
+	const int np = collisions ? d.lvl_fill[(size_t)level * RP_LVL_STRIDE] : 0;
 	int st = 0, stw = 0;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < njw + np; i += gridDim.x * blockDim.x) {
 		if (i < njw) {
@@ -576,7 +590,7 @@ __global__ void __launch_bounds__(128) k_derive(DevView d, double h) {
 // velocity pass over the contacts of one level (pbd.cpp:646-711); the hinge branch of the reference's velocity pass is
 // an empty TODO (pbd.cpp:712-739), so joints take no part
 __global__ void __launch_bounds__(128) k_vel_level(DevView d, double h, int level) {
-	const int np = d.lvl_fill[level];
+	const int np = d.lvl_fill[(size_t)level * RP_LVL_STRIDE];
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
 		const uint2 item = d.lvl_items[d.lvl_off[level] + i];
 		const int w = (int)item.x;
