@@ -340,18 +340,16 @@ struct ClipPlane {
 #define RP_MAXF(a, b) (((a) > (b)) ? (a) : (b))
 #define RP_MINF(a, b) (((a) < (b)) ? (a) : (b))
 
-// is_point_in_plane (clipping.cpp:12-19): the plane offset is rounded to float (quirk q6)
-RP_HD bool clip_inside(const ClipPlane& pl, V3 p) {
-	float offset = (float)(-dot(pl.normal, pl.point));
-	return !(dot(p, pl.normal) + (double)offset < 0.0);
-}
+// is_point_in_plane (clipping.cpp:12-19): the plane offset is rounded to float (quirk q6). `offset` is
+// (float)(-dot(normal, point)), hoisted out of the per-vertex calls (same inputs, same value).
+RP_HD float clip_offset(const ClipPlane& pl) { return (float)(-dot(pl.normal, pl.point)); }
+RP_HD bool clip_inside(const ClipPlane& pl, float offset, V3 p) { return !(dot(p, pl.normal) + (double)offset < 0.0); }
 
 // plane_edge_intersection (clipping.cpp:21-46): ab_p, the plane offset and the edge factor pass through float
-RP_HD bool clip_edge(const ClipPlane& pl, V3 start, V3 end, V3* out) {
+RP_HD bool clip_edge(const ClipPlane& pl, float offset, V3 start, V3 end, V3* out) {
 	V3 ab = sub(end, start);
 	float ab_p = (float)dot(pl.normal, ab);
 	if (fabs((double)ab_p) > 0.000001) {
-		float offset = (float)(-dot(pl.normal, pl.point));
 		V3 p_co = scale((double)(-offset), pl.normal);
 		float fac = (float)(-dot(pl.normal, sub(start, p_co)) / (double)ab_p);
 		fac = (float)RP_MINF(RP_MAXF((double)fac, 0.0), 1.0);
@@ -365,14 +363,17 @@ struct ClipScratch {
 	V3 buf[2][RP_CLIP_MAX_POINTS];
 };
 
-// One Sutherland-Hodgman pass of `in` against one plane (body of the loop at clipping.cpp:63-108).
+// One Sutherland-Hodgman pass of `in` against one plane (body of the loop at clipping.cpp:63-108). The reference tests
+// every vertex twice (as the end of one edge and the start of the next); the verdict is a pure function of the vertex,
+// so it is carried over instead.
 RP_HD int clip_pass(const ClipPlane& pl, const V3* in, int n_in, V3* out, bool remove_only, int* status) {
 	int n_out = 0;
+	const float offset = clip_offset(pl);
 	V3 start = in[n_in - 1];
+	bool s_in = clip_inside(pl, offset, start);
 	for (int j = 0; j < n_in; ++j) {
 		V3 end = in[j];
-		bool s_in = clip_inside(pl, start);
-		bool e_in = clip_inside(pl, end);
+		bool e_in = clip_inside(pl, offset, end);
 		V3 tmp;
 		if (n_out + 2 > RP_CLIP_MAX_POINTS) {
 			*status |= ST_CLIP_CAPACITY;
@@ -383,12 +384,13 @@ RP_HD int clip_pass(const ClipPlane& pl, const V3* in, int n_in, V3* out, bool r
 		} else if (s_in && e_in) {
 			out[n_out++] = end;
 		} else if (s_in && !e_in) {
-			if (clip_edge(pl, start, end, &tmp)) out[n_out++] = tmp;
+			if (clip_edge(pl, offset, start, end, &tmp)) out[n_out++] = tmp;
 		} else if (!s_in && e_in) {
-			if (clip_edge(pl, start, end, &tmp)) out[n_out++] = tmp;
+			if (clip_edge(pl, offset, start, end, &tmp)) out[n_out++] = tmp;
 			out[n_out++] = end;
 		}
 		start = end;
+		s_in = e_in;
 	}
 	return n_out;
 }
@@ -433,34 +435,65 @@ RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipS
 	int face1 = clip_best_face(h1, sup1, normal);
 	int face2 = clip_best_face(h2, sup2, inv_normal);
 
-	// get_edge_with_most_fitting_normal (clipping.cpp:154-201)
-	V3 s1 = h1.tv[sup1], s2 = h2.tv[sup2];
-	double best = -1.7976931348623157e308;
-	int e1n = 0, e2n = 0;
-	V3 edge_normal = v3(0.0, 0.0, 0.0);
-	for (int i = h1.v2n_ptr[sup1]; i < h1.v2n_ptr[sup1 + 1]; ++i) {
-		V3 edge1 = sub(s1, h1.tv[h1.v2n_idx[i]]);
-		for (int j = h2.v2n_ptr[sup2]; j < h2.v2n_ptr[sup2 + 1]; ++j) {
-			V3 edge2 = sub(s2, h2.tv[h2.v2n_idx[j]]);
-			V3 cn = normalize(cross(edge1, edge2));
-			V3 cni = zero_minus(cn);
-			double t = dot(cn, normal);
-			if (t > best) {
-				best = t; e1n = h1.v2n_idx[i]; e2n = h2.v2n_idx[j]; edge_normal = cn;
-			}
-			t = dot(cni, normal);
-			if (t > best) {
-				best = t; e1n = h1.v2n_idx[i]; e2n = h2.v2n_idx[j]; edge_normal = cni;
-			}
-		}
-	}
-
 	V3 f1n = h1.tn[face1], f2n = h2.tn[face2];
 	double dot1 = dot(f1n, normal);
 	double dot2 = dot(f2n, inv_normal);
-	double dote = dot(edge_normal, normal);
 	const double EPS = 0.0001;
-	if (dote > dot1 + EPS && dote > dot2 + EPS) {
+
+	// get_edge_with_most_fitting_normal (clipping.cpp:154-201) picks, over all pairs of edges leaving the two support
+	// vertices, the unit cross product best aligned with the collision normal (first maximum wins, both signs tried).
+	// Its result only matters if it beats BOTH face alignments by EPS (clipping.cpp:270). Two exact shortcuts:
+	//  (1) every candidate is a dot of two vectors normalised by gm_vec3_normalize, so it is <= 1 + 12 ulp; if a face
+	//      alignment + EPS already exceeds that bound the edge branch cannot be taken and the search is skipped;
+	//  (2) otherwise a float pre-pass scores every candidate (error << 1e-5) and the FP64 evaluation, in the original
+	//      order with the original strict comparison, runs only on candidates within 1e-3 of the best score -- the
+	//      first exact maximum is always among them, and everything before it is exactly smaller, so the selected
+	//      edge pair, the edge normal and the maximum are the ones the full loop would return.
+	double best = -1.7976931348623157e308;
+	int e1n = 0, e2n = 0;
+	V3 edge_normal = v3(0.0, 0.0, 0.0);
+	const bool edge_possible = !(dot1 + EPS > 1.000000000001 || dot2 + EPS > 1.000000000001);
+	if (edge_possible) {
+		V3 s1 = h1.tv[sup1], s2 = h2.tv[sup2];
+		const float nx = (float)normal.x, ny = (float)normal.y, nz = (float)normal.z;
+		float best_score = -1.0f;
+		for (int pass = 0; pass < 2; ++pass) {
+			for (int i = h1.v2n_ptr[sup1]; i < h1.v2n_ptr[sup1 + 1]; ++i) {
+				V3 edge1 = sub(s1, h1.tv[h1.v2n_idx[i]]);
+				const float ax = (float)edge1.x, ay = (float)edge1.y, az = (float)edge1.z;
+				const float a2 = ax * ax + ay * ay + az * az;
+				for (int j = h2.v2n_ptr[sup2]; j < h2.v2n_ptr[sup2 + 1]; ++j) {
+					V3 edge2 = sub(s2, h2.tv[h2.v2n_idx[j]]);
+					const float bx = (float)edge2.x, by = (float)edge2.y, bz = (float)edge2.z;
+					const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+					const float len2 = cx * cx + cy * cy + cz * cz;
+					const float b2 = bx * bx + by * by + bz * bz;
+					// nearly parallel edges (sin < 1e-2): the float cross product is cancellation noise, so such a
+					// candidate is never scored, always evaluated exactly, and does not set the bar for the others
+					const bool degenerate = !(len2 > 1e-4f * a2 * b2);
+					float score = 0.0f;
+					if (!degenerate) score = fabsf(cx * nx + cy * ny + cz * nz) / sqrtf(len2);
+					if (pass == 0) {
+						if (!degenerate && score > best_score) best_score = score;
+						continue;
+					}
+					if (!degenerate && score < best_score - 1e-3f) continue;
+					V3 cn = normalize(cross(edge1, edge2));
+					V3 cni = zero_minus(cn);
+					double t = dot(cn, normal);
+					if (t > best) {
+						best = t; e1n = h1.v2n_idx[i]; e2n = h2.v2n_idx[j]; edge_normal = cn;
+					}
+					t = dot(cni, normal);
+					if (t > best) {
+						best = t; e1n = h1.v2n_idx[i]; e2n = h2.v2n_idx[j]; edge_normal = cni;
+					}
+				}
+			}
+		}
+	}
+	double dote = dot(edge_normal, normal);
+	if (edge_possible && dote > dot1 + EPS && dote > dot2 + EPS) {
 		V3 p1 = h1.tv[sup1];
 		V3 d1 = sub(h1.tv[e1n], p1);
 		V3 p2 = h2.tv[sup2];
