@@ -507,7 +507,8 @@ uint64_t port_cull_soundness(uint64_t trials, uint64_t seed, uint64_t* separated
 		Shape A, B;
 		memset(&A, 0, sizeof(A)); memset(&B, 0, sizeof(B));
 		A.type = B.type = SHAPE_HULL;
-		A.tv = ta.data(); A.nv = (int)ta.size(); B.tv = tb.data(); B.nv = (int)tb.size();
+		A.vp = (const double*)ta.data(); A.vs = 3; A.vcs = 1; A.nv = (int)ta.size();
+		B.vp = (const double*)tb.data(); B.vs = 3; B.vcs = 1; B.nv = (int)tb.size();
 		bool separated = false;
 		for (int k = 0; k < 3; ++k) {
 			if (lo[0][k] - hi[1][k] > 1e-7 || lo[1][k] - hi[0][k] > 1e-7) separated = true;

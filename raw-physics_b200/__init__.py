@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librawphys_b200.so")
+LIB_PATH = os.environ.get("RAWPHYS_B200_LIB") or os.path.join(HERE, "librawphys_b200.so")  # override: tuning variants
 STATE_STRIDE = 21
 PARAM_STRIDE = 25
 

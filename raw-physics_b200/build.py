@@ -35,10 +35,11 @@ def up_to_date():
     return all(os.path.getmtime(f) <= t for f in SOURCES + HEADERS + [os.path.abspath(__file__)])
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, out=None, defines=()):
+    """`out`/`defines` build an experimental variant next to the product library (tuning runs only)."""
+    if out is None and not force and up_to_date():
         return OUT
-    cmd = [nvcc()] + NVCC_FLAGS + ["-o", OUT] + SOURCES
+    cmd = [nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out or OUT] + SOURCES
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:
@@ -48,7 +49,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed (see raw-physics_b200/build.log)")
     if verbose:
         print(log)
-    return OUT
+    return out or OUT
 
 
 if __name__ == "__main__":

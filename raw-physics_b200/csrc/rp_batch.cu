@@ -351,6 +351,13 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		o.inertia = bi.inertia; o.inv_inertia = bi.inv_inertia;
 		o.mu_s = bi.mu_s; o.mu_d = bi.mu_d; o.rest = bi.rest; o.radius = bi.radius;
 		o.fixed = bi.fixed; o.col0 = bi.col0; o.ncol = bi.ncol;
+		o.tv0 = bi.ncol ? s.colliders[bi.col0].tv0 : 0;
+		o.tn0 = bi.ncol ? s.colliders[bi.col0].tn0 : 0;
+		for (int c = bi.col0; c < bi.col0 + bi.ncol; ++c) {
+			const ColliderDesc& cd = s.colliders[c];
+			o.tvn += cd.type == SHAPE_HULL ? (int)s.hulls[cd.hull].verts.size() : 1;
+			o.tnn += cd.type == SHAPE_HULL ? (int)s.hulls[cd.hull].normals.size() : 0;
+		}
 	}
 	HullPoolHost hp = pool_hulls(s);
 	int rc;
@@ -495,14 +502,14 @@ static unsigned int level_grid(const rp_batch* b) { return (unsigned int)b->sm_c
 
 static void enqueue_integrate(rp_batch* b, double h) {
 	const DevView& d = b->d;
-	const size_t n = std::max((size_t)d.W * d.NB, (size_t)d.max_levels + 2);
-	k_integrate<<<(unsigned int)((n + 127) / 128), 128, 0, b->stream>>>(d, h);
+	k_substep_reset<<<(unsigned int)((std::max(d.W, d.max_levels + 2) + 255) / 256), 256, 0, b->stream>>>(d);
+	k_integrate<<<dim3((d.NB + 127) / 128, d.W), 128, 0, b->stream>>>(d, h);
 }
 static void enqueue_narrow(rp_batch* b) {
 	const DevView& d = b->d;
 	k_cull<<<dim3(b->cull_chunks, d.W), 256, 0, b->stream>>>(d, b->cull);
-	k_gjk<<<b->sm_count * 8, 128, 0, b->stream>>>(d);
-	k_manifold<<<b->sm_count * 4, 128, 0, b->stream>>>(d);
+	k_gjk<<<b->sm_count * 16, RP_GJK_THREADS, 0, b->stream>>>(d);
+	k_manifold<<<b->sm_count * 4, RP_MANIFOLD_THREADS, 0, b->stream>>>(d);
 }
 static void enqueue_solve(rp_batch* b, double h, uint32_t iters, int collisions, int levels) {
 	const DevView& d = b->d;
@@ -796,9 +803,9 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 			if (collisions) {
 				k_cull<<<dim3(b->cull_chunks, d.W), 256, 0, b->stream>>>(d, b->cull);
 				if ((rc = mark(RP_K_CULL))) return rc;
-				k_gjk<<<b->sm_count * 8, 128, 0, b->stream>>>(d);
+				k_gjk<<<b->sm_count * 16, RP_GJK_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_GJK))) return rc;
-				k_manifold<<<b->sm_count * 4, 128, 0, b->stream>>>(d);
+				k_manifold<<<b->sm_count * 4, RP_MANIFOLD_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_MANIFOLD))) return rc;
 			}
 			for (uint32_t it = 0; it < iters; ++it) {

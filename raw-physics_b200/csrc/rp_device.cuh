@@ -21,7 +21,9 @@ struct BodyStatic {
 	double inv_mass;
 	M3 inertia, inv_inertia;
 	double mu_s, mu_d, rest, radius;
-	int fixed, col0, ncol, pad;
+	int fixed, col0, ncol;
+	int tv0, tvn, tn0, tnn;   // extent of the body's colliders in a world's transformed vertex / normal arrays
+	int pad;
 };
 struct PairRec {  // one broadphase pair, expanded to collider granularity: bodies a < b, global collider indices ca, cb
 	int a, b, ca, cb;

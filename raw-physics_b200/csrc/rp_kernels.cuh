@@ -10,6 +10,28 @@
 
 #include "rp_device.cuh"
 
+// occupancy knobs (min resident CTAs per SM handed to __launch_bounds__); tuned on B200, see profiles/
+#ifndef RP_MINB_INTEGRATE
+#define RP_MINB_INTEGRATE 4
+#endif
+#ifndef RP_MINB_GJK
+#define RP_MINB_GJK 8
+#endif
+#ifndef RP_MINB_MANIFOLD
+#define RP_MINB_MANIFOLD 4
+#endif
+#ifndef RP_MINB_POS
+#define RP_MINB_POS 2
+#endif
+#ifndef RP_MINB_VEL
+#define RP_MINB_VEL 2
+#endif
+
+#define RP_GJK_THREADS 64
+#define RP_GJK_STAGE 48          // doubles of shared memory per thread: two hulls of up to 16 vertices in total
+#define RP_MANIFOLD_THREADS 128
+#define RP_MANIFOLD_STAGE 0      // doubles of shared memory per thread for staged hulls in k_manifold (0 = off: measured slower)
+
 #define RP_LVL_SMEM 64     // levels ranked through shared memory in k_manifold
 #define RP_LVL_STRIDE 32   // ints between consecutive level fill counters (one 128-byte line each)
 
@@ -241,58 +263,120 @@ __global__ void k_level_offsets(DevView d) {
 // re-transforms both colliders of every pair every substep (39 % of its time); the same pose gives the same result,
 // so once per body per substep is exactly equivalent. Also leaves each collider's world-space bounds
 // for k_cull and resets the per-substep counters.
-__global__ void __launch_bounds__(128) k_integrate(DevView d, double h) {
-	const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (gid == 0) {
+// per-substep counters
+__global__ void __launch_bounds__(256) k_substep_reset(DevView d) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i == 0) {
 		*d.hit_count = 0u;
 		*d.cand_count = 0u;
 	}
-	if (gid < (size_t)d.max_levels + 2) d.lvl_fill[gid * RP_LVL_STRIDE] = 0;
-	if (gid >= (size_t)d.W * d.NB) return;
-	const int w = (int)(gid / d.NB), b = (int)(gid % d.NB);
-	if (b == 0) d.n_contacts[w] = 0;
-	if (b < d.NJ) {  // copy_constraints resets every lambda each substep (pbd.cpp:426-462)
-		for (int j = b; j < d.NJ; j += d.NB) {
-			JointLambda z;
-			z.a = z.b = z.c = 0.0;
-			d.lambdas[(size_t)w * d.NJ + j] = z;
-		}
+	if (i < d.max_levels + 2) d.lvl_fill[(size_t)i * RP_LVL_STRIDE] = 0;
+	if (i < d.W) d.n_contacts[i] = 0;
+}
+
+#define RP_INT_MAXV 8   // staged write path of k_integrate: bodies of up to 8 transformed vertices and 6 normals (boxes)
+#define RP_INT_MAXF 6
+__global__ void __launch_bounds__(128, RP_MINB_INTEGRATE) k_integrate(DevView d, double h) {
+	// Transformed geometry of the CTA's 128 bodies, staged so that the global writes are coalesced. Rows are padded to an
+	// odd number of doubles: per-thread rows are then free of bank conflicts.
+	__shared__ double s_tv[128 * (RP_INT_MAXV * 3 + 1)];
+	__shared__ double s_tn[128 * (RP_INT_MAXF * 3 + 1)];
+	const int w = blockIdx.y;
+	const int b0 = blockIdx.x * blockDim.x;
+	const int b = b0 + threadIdx.x;
+	const int nb = min(128, d.NB - b0);
+	// staged path only when every body of the CTA has the same small footprint, laid out back to back
+	const BodyStatic& s0 = d.bstat[b0];
+	const int tvn = s0.tvn, tnn = s0.tnn;
+	bool uniform = tvn <= RP_INT_MAXV && tnn <= RP_INT_MAXF;
+	if (b < d.NB) {
+		const BodyStatic& sb = d.bstat[b];
+		uniform = uniform && sb.tvn == tvn && sb.tnn == tnn && sb.tv0 == s0.tv0 + (b - b0) * tvn && sb.tn0 == s0.tn0 + (b - b0) * tnn;
 	}
-	const BodyStatic& s = d.bstat[b];
-	BodyDyn& dd = d.dyn[gid];
-	Body body;
-	load_static(body, s);
-	body.x = ld3(dd.x); body.q = ld4(dd.q); body.v = ld3(dd.v); body.w = ld3(dd.w);
-	body.active = d.active[gid];
-	integrate(body, h, d.force[b], d.torque[b]);
-	st3(dd.px, body.px); st4(dd.pq, body.pq);
-	if (!(body.fixed || !body.active)) {
-		st3(dd.x, body.x); st4(dd.q, body.q); st3(dd.v, body.v); st3(dd.w, body.w);
-	}
-	Pose34 M = model_matrix(body.q, body.x);
-	V3* tv = d.tv + (size_t)w * d.TV;
-	V3* tn = d.tn + (size_t)w * d.TN;
-	for (int c = s.col0; c < s.col0 + s.ncol; ++c) {
-		const ColliderDesc cd = d.cols[c];
-		double* bb = d.aabb + ((size_t)w * d.NC + c) * 6;
-		if (cd.type == SHAPE_SPHERE) {
-			tv[cd.tv0] = body.x;
-			const double r = (double)cd.radius;
-			bb[0] = body.x.x - r; bb[1] = body.x.y - r; bb[2] = body.x.z - r;
-			bb[3] = body.x.x + r; bb[4] = body.x.y + r; bb[5] = body.x.z + r;
-		} else {
-			const HullTopo t = d.pool.hulls[cd.hull];
-			double lo0 = 1.7976931348623157e308, lo1 = lo0, lo2 = lo0, hi0 = -lo0, hi1 = -lo0, hi2 = -lo0;
-			for (int k = 0; k < t.nv; ++k) {
-				const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
-				tv[cd.tv0 + k] = p;
-				lo0 = fmin(lo0, p.x); lo1 = fmin(lo1, p.y); lo2 = fmin(lo2, p.z);
-				hi0 = fmax(hi0, p.x); hi1 = fmax(hi1, p.y); hi2 = fmax(hi2, p.z);
+	const bool staged = __syncthreads_and(uniform) != 0;
+	const int rv = tvn * 3 + 1, rn = tnn * 3 + 1;
+	if (b < d.NB) {
+		const size_t gid = (size_t)w * d.NB + b;
+		if (b < d.NJ) {  // copy_constraints resets every lambda each substep (pbd.cpp:426-462)
+			for (int j = b; j < d.NJ; j += d.NB) {
+				JointLambda z;
+				z.a = z.b = z.c = 0.0;
+				d.lambdas[(size_t)w * d.NJ + j] = z;
 			}
-			for (int k = 0; k < t.nf; ++k) tn[cd.tn0 + k] = transform_normal(M, d.pool.normals[t.face0 + k]);
-			bb[0] = lo0; bb[1] = lo1; bb[2] = lo2; bb[3] = hi0; bb[4] = hi1; bb[5] = hi2;
+		}
+		const BodyStatic& s = d.bstat[b];
+		BodyDyn& dd = d.dyn[gid];
+		Body body;
+		load_static(body, s);
+		body.x = ld3(dd.x); body.q = ld4(dd.q); body.v = ld3(dd.v); body.w = ld3(dd.w);
+		body.active = d.active[gid];
+		integrate(body, h, d.force[b], d.torque[b]);
+		st3(dd.px, body.px); st4(dd.pq, body.pq);
+		if (!(body.fixed || !body.active)) {
+			st3(dd.x, body.x); st4(dd.q, body.q); st3(dd.v, body.v); st3(dd.w, body.w);
+		}
+		Pose34 M = model_matrix(body.q, body.x);
+		V3* tv = d.tv + (size_t)w * d.TV;
+		V3* tn = d.tn + (size_t)w * d.TN;
+		double* row_v = s_tv + (size_t)threadIdx.x * rv;
+		double* row_n = s_tn + (size_t)threadIdx.x * rn;
+		int ov = 0, on = 0;
+		for (int c = s.col0; c < s.col0 + s.ncol; ++c) {
+			const ColliderDesc cd = d.cols[c];
+			double* bb = d.aabb + ((size_t)w * d.NC + c) * 6;
+			if (cd.type == SHAPE_SPHERE) {
+				if (staged) { row_v[ov] = body.x.x; row_v[ov + 1] = body.x.y; row_v[ov + 2] = body.x.z; ov += 3; }
+				else tv[cd.tv0] = body.x;
+				const double r = (double)cd.radius;
+				bb[0] = body.x.x - r; bb[1] = body.x.y - r; bb[2] = body.x.z - r;
+				bb[3] = body.x.x + r; bb[4] = body.x.y + r; bb[5] = body.x.z + r;
+			} else {
+				const HullTopo t = d.pool.hulls[cd.hull];
+				double lo0 = 1.7976931348623157e308, lo1 = lo0, lo2 = lo0, hi0 = -lo0, hi1 = -lo0, hi2 = -lo0;
+				for (int k = 0; k < t.nv; ++k) {
+					const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
+					if (staged) { row_v[ov] = p.x; row_v[ov + 1] = p.y; row_v[ov + 2] = p.z; ov += 3; }
+					else tv[cd.tv0 + k] = p;
+					lo0 = fmin(lo0, p.x); lo1 = fmin(lo1, p.y); lo2 = fmin(lo2, p.z);
+					hi0 = fmax(hi0, p.x); hi1 = fmax(hi1, p.y); hi2 = fmax(hi2, p.z);
+				}
+				for (int k = 0; k < t.nf; ++k) {
+					const V3 n = transform_normal(M, d.pool.normals[t.face0 + k]);
+					if (staged) { row_n[on] = n.x; row_n[on + 1] = n.y; row_n[on + 2] = n.z; on += 3; }
+					else tn[cd.tn0 + k] = n;
+				}
+				bb[0] = lo0; bb[1] = lo1; bb[2] = lo2; bb[3] = hi0; bb[4] = hi1; bb[5] = hi2;
+			}
 		}
 	}
+	if (staged) {
+		__syncthreads();
+		double* gv = (double*)(d.tv + (size_t)w * d.TV + s0.tv0);
+		double* gn = (double*)(d.tn + (size_t)w * d.TN + s0.tn0);
+		const int nv3 = tvn * 3, nn3 = tnn * 3;
+		for (int g = threadIdx.x; g < nb * nv3; g += blockDim.x) gv[g] = s_tv[(g / nv3) * rv + g % nv3];
+		for (int g = threadIdx.x; g < nb * nn3; g += blockDim.x) gn[g] = s_tn[(g / nn3) * rn + g % nn3];
+	}
+}
+
+// Copies a small hull's transformed vertices (and, optionally, face normals) from the world's AoS arrays into the calling
+// thread's column of a thread-interleaved shared-memory block: element e of the thread lives at base[e * nthreads], so
+// the 32 lanes of a warp touch 32 consecutive doubles per access (2 wavefronts) instead of 32 scattered sectors. The
+// narrowphase scans the same vertices many times (support mapping), so this turns an L1-wavefront-bound kernel back
+// into an FP64-bound one. Returns the number of doubles used.
+__device__ __forceinline__ int stage_shape(Shape& s, double* col, int nthreads, bool with_normals) {
+	int e = 0;
+	const double* src = s.vp;
+	for (int k = 0; k < s.nv * 3; ++k) col[(size_t)(e + k) * nthreads] = src[k];
+	s.vp = col + (size_t)e * nthreads; s.vs = 3 * nthreads; s.vcs = nthreads;
+	e += s.nv * 3;
+	if (with_normals) {
+		src = s.np;
+		for (int k = 0; k < s.nf * 3; ++k) col[(size_t)(e + k) * nthreads] = src[k];
+		s.np = col + (size_t)e * nthreads; s.ns = 3 * nthreads; s.ncs = nthreads;
+		e += s.nf * 3;
+	}
+	return e;
 }
 
 // warp-aggregated append: every lane of the warp calls this; lanes with want == true get consecutive slots
@@ -351,8 +435,9 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 // ----------------------------------------------------------------------------------------------------- narrowphase 1
 // One thread per candidate pair: sphere-sphere test or boolean GJK (collider.cpp:523-547). Colliding pairs are appended
 // to the global hit list for k_manifold.
-__global__ void __launch_bounds__(128) k_gjk(DevView d) {
+__global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) {
 	const unsigned int nc = *d.cand_count;
+	__shared__ double s_stage[RP_GJK_STAGE * RP_GJK_THREADS];
 	for (unsigned int c0 = blockIdx.x * blockDim.x; c0 < nc; c0 += gridDim.x * blockDim.x) {
 		const unsigned int ci = c0 + threadIdx.x;
 		bool hit = false;
@@ -373,6 +458,11 @@ __global__ void __launch_bounds__(128) k_gjk(DevView d) {
 				double depth;
 				hit = sphere_sphere(A, B, &n, &depth);
 			} else {
+				if ((A.nv + B.nv) * 3 <= RP_GJK_STAGE) {
+					double* col = s_stage + threadIdx.x;
+					const int used = stage_shape(A, col, RP_GJK_THREADS, false);
+					stage_shape(B, col + (size_t)used * RP_GJK_THREADS, RP_GJK_THREADS, false);
+				}
 				hit = gjk(A, B, &s, &st, 0);
 			}
 			if (st) atomicOr(&d.status[w], st);
@@ -414,7 +504,8 @@ struct ManifoldScratch {
 // (pbd.cpp:408-424). The pair's contacts get a contiguous run in the world's contact buffer (allocation order between
 // pairs is irrelevant: the solver walks pairs, not the buffer), and the pair is appended to the work list of its
 // dependency level.
-__global__ void __launch_bounds__(128) k_manifold(DevView d) {
+__global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manifold(DevView d) {
+	__shared__ double s_stage[RP_MANIFOLD_STAGE * RP_MANIFOLD_THREADS + 1];
 	const unsigned int nh = *d.hit_count;
 	ManifoldScratch sc;
 	__shared__ int s_cnt[RP_LVL_SMEM], s_base[RP_LVL_SMEM];
@@ -432,6 +523,11 @@ __global__ void __launch_bounds__(128) k_manifold(DevView d) {
 			const V3* tn = d.tn + (size_t)w * d.TN;
 			Shape A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
 			Shape B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
+			if (A.type == SHAPE_HULL && B.type == SHAPE_HULL && (A.nv + B.nv + A.nf + B.nf) * 3 <= RP_MANIFOLD_STAGE) {
+				double* col = s_stage + threadIdx.x;
+				const int used = stage_shape(A, col, RP_MANIFOLD_THREADS, true);
+				stage_shape(B, col + (size_t)used * RP_MANIFOLD_THREADS, RP_MANIFOLD_THREADS, true);
+			}
 			V3 normal;
 			double depth;
 			int st = 0;
@@ -487,7 +583,7 @@ __global__ void __launch_bounds__(128) k_manifold(DevView d) {
 		// append (world, pair) to the list of its level: ranks within the CTA through shared-memory counters, then ONE
 		// global atomic per (CTA, level) on a counter that owns its 128-byte line (RP_LVL_STRIDE)
 		__syncthreads();
-		if (threadIdx.x < RP_LVL_SMEM) s_cnt[threadIdx.x] = 0;
+		if (threadIdx.x < RP_LVL_SMEM) s_cnt[threadIdx.x] = 0;  // RP_MANIFOLD_THREADS >= RP_LVL_SMEM
 		__syncthreads();
 		int rank = 0;
 		if (lvl > 0) {
@@ -514,7 +610,7 @@ __global__ void __launch_bounds__(128) k_manifold(DevView d) {
 // unit -- the joints of level l of every world, then the (world, pair) items of level l that have contacts this substep
 // (a pair's manifold is a sequential chain on its two bodies and stays in one thread, bodies in registers). Kernel
 // boundaries are the barriers between levels, so the result equals the reference's sequential sweep (pbd.cpp:615-620).
-__global__ void __launch_bounds__(128) k_pos_level(DevView d, double h, int level, int collisions) {
+__global__ void __launch_bounds__(128, RP_MINB_POS) k_pos_level(DevView d, double h, int level, int collisions) {
 	const int nj = level <= d.joint_levels ? d.joint_lptr[level] - d.joint_lptr[level - 1] : 0;
 	const int njw = nj * d.W;
 	const int np = collisions ? d.lvl_fill[(size_t)level * RP_LVL_STRIDE] : 0;
@@ -589,7 +685,7 @@ __global__ void __launch_bounds__(128) k_derive(DevView d, double h) {
 
 // velocity pass over the contacts of one level (pbd.cpp:646-711); the hinge branch of the reference's velocity pass is
 // an empty TODO (pbd.cpp:712-739), so joints take no part
-__global__ void __launch_bounds__(128) k_vel_level(DevView d, double h, int level) {
+__global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, double h, int level) {
 	const int np = d.lvl_fill[(size_t)level * RP_LVL_STRIDE];
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
 		const uint2 item = d.lvl_items[d.lvl_off[level] + i];

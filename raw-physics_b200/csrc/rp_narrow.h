@@ -401,7 +401,7 @@ RP_HD int clip_best_face(const Shape& s, int support_idx, V3 normal) {
 	int sel = 0;
 	for (int k = s.v2f_ptr[support_idx]; k < s.v2f_ptr[support_idx + 1]; ++k) {
 		int f = s.v2f_idx[k];
-		double proj = dot(s.tn[f], normal);
+		double proj = dot(fnormal(s, f), normal);
 		if (proj > best) {
 			best = proj;
 			sel = f;
@@ -435,7 +435,7 @@ RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipS
 	int face1 = clip_best_face(h1, sup1, normal);
 	int face2 = clip_best_face(h2, sup2, inv_normal);
 
-	V3 f1n = h1.tn[face1], f2n = h2.tn[face2];
+	V3 f1n = fnormal(h1, face1), f2n = fnormal(h2, face2);
 	double dot1 = dot(f1n, normal);
 	double dot2 = dot(f2n, inv_normal);
 	const double EPS = 0.0001;
@@ -454,16 +454,16 @@ RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipS
 	V3 edge_normal = v3(0.0, 0.0, 0.0);
 	const bool edge_possible = !(dot1 + EPS > 1.000000000001 || dot2 + EPS > 1.000000000001);
 	if (edge_possible) {
-		V3 s1 = h1.tv[sup1], s2 = h2.tv[sup2];
+		V3 s1 = vert(h1, sup1), s2 = vert(h2, sup2);
 		const float nx = (float)normal.x, ny = (float)normal.y, nz = (float)normal.z;
 		float best_score = -1.0f;
 		for (int pass = 0; pass < 2; ++pass) {
 			for (int i = h1.v2n_ptr[sup1]; i < h1.v2n_ptr[sup1 + 1]; ++i) {
-				V3 edge1 = sub(s1, h1.tv[h1.v2n_idx[i]]);
+				V3 edge1 = sub(s1, vert(h1, h1.v2n_idx[i]));
 				const float ax = (float)edge1.x, ay = (float)edge1.y, az = (float)edge1.z;
 				const float a2 = ax * ax + ay * ay + az * az;
 				for (int j = h2.v2n_ptr[sup2]; j < h2.v2n_ptr[sup2 + 1]; ++j) {
-					V3 edge2 = sub(s2, h2.tv[h2.v2n_idx[j]]);
+					V3 edge2 = sub(s2, vert(h2, h2.v2n_idx[j]));
 					const float bx = (float)edge2.x, by = (float)edge2.y, bz = (float)edge2.z;
 					const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
 					const float len2 = cx * cx + cy * cy + cz * cz;
@@ -494,10 +494,10 @@ RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipS
 	}
 	double dote = dot(edge_normal, normal);
 	if (edge_possible && dote > dot1 + EPS && dote > dot2 + EPS) {
-		V3 p1 = h1.tv[sup1];
-		V3 d1 = sub(h1.tv[e1n], p1);
-		V3 p2 = h2.tv[sup2];
-		V3 d2 = sub(h2.tv[e2n], p2);
+		V3 p1 = vert(h1, sup1);
+		V3 d1 = sub(vert(h1, e1n), p1);
+		V3 p2 = vert(h2, sup2);
+		V3 d2 = sub(vert(h2, e2n), p2);
 		V3 l1, l2;
 		if (!clip_skew_lines(p1, d1, p2, d2, &l1, &l2)) {
 			*status |= ST_EDGE_PARALLEL;  // the reference aborts (clipping.cpp:279)
@@ -521,7 +521,7 @@ RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipS
 			*status |= ST_CLIP_CAPACITY;
 			return;
 		}
-		cs.buf[0][n++] = I.tv[I.face_idx[k]];
+		cs.buf[0][n++] = vert(I, I.face_idx[k]);
 	}
 	// boundary planes of the reference face (build_boundary_planes, clipping.cpp:121-134), clipped one at a time
 	// (sutherland_hodgman, clipping.cpp:52-113)
@@ -529,14 +529,14 @@ RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipS
 		if (n == 0) break;
 		int nf = R.f2n_idx[k];
 		ClipPlane pl;
-		pl.point = R.tv[R.face_idx[R.face_ptr[nf]]];
-		pl.normal = zero_minus(R.tn[nf]);
+		pl.point = vert(R, R.face_idx[R.face_ptr[nf]]);
+		pl.normal = zero_minus(fnormal(R, nf));
 		n = clip_pass(pl, cs.buf[cur], n, cs.buf[cur ^ 1], false, status);
 		cur ^= 1;
 	}
 	ClipPlane rp;
 	rp.normal = zero_minus(ref1 ? f1n : f2n);
-	rp.point = R.tv[R.face_idx[R.face_ptr[rface]]];
+	rp.point = vert(R, R.face_idx[R.face_ptr[rface]]);
 	if (n != 0) {
 		n = clip_pass(rp, cs.buf[cur], n, cs.buf[cur ^ 1], true, status);
 		cur ^= 1;

@@ -47,8 +47,10 @@ struct Shape {
 	int type;
 	float radius;
 	V3 center;                // sphere centre (collider.cpp:433)
-	const V3* tv;             // transformed vertices
-	const V3* tn;             // transformed (re-normalised) face normals
+	// transformed vertices / (re-normalised) face normals, addressed as base[i * stride + c * cstride] so the same code
+	// reads the AoS arrays in global memory (stride 3, cstride 1) and thread-interleaved copies staged in shared memory
+	const double* vp; int vs, vcs;
+	const double* np; int ns, ncs;
 	int nv, nf;
 	const int* face_ptr; const int* face_idx;
 	const int* v2f_ptr; const int* v2f_idx;
@@ -60,10 +62,10 @@ RP_HD Shape make_shape(const HullPool& pool, const ColliderDesc& c, const V3* wo
 	Shape s;
 	s.type = c.type;
 	s.radius = c.radius;
-	s.tv = world_tv + c.tv0;
-	s.tn = world_tn + c.tn0;
+	s.vp = (const double*)(world_tv + c.tv0); s.vs = 3; s.vcs = 1;
+	s.np = (const double*)(world_tn + c.tn0); s.ns = 3; s.ncs = 1;
 	if (c.type == SHAPE_SPHERE) {
-		s.center = s.tv[0];
+		s.center = world_tv[c.tv0];
 		s.nv = 0; s.nf = 0;
 		s.face_ptr = s.face_idx = s.v2f_ptr = s.v2f_idx = s.v2n_ptr = s.v2n_idx = s.f2n_ptr = s.f2n_idx = 0;
 	} else {
@@ -76,6 +78,15 @@ RP_HD Shape make_shape(const HullPool& pool, const ColliderDesc& c, const V3* wo
 		s.f2n_ptr = pool.f2n_ptr + h.f2n0; s.f2n_idx = pool.f2n_idx;
 	}
 	return s;
+}
+
+RP_HD V3 vert(const Shape& s, int i) {
+	const double* p = s.vp + (size_t)i * s.vs;
+	return v3(p[0], p[s.vcs], p[2 * s.vcs]);
+}
+RP_HD V3 fnormal(const Shape& s, int i) {
+	const double* p = s.np + (size_t)i * s.ns;
+	return v3(p[0], p[s.ncs], p[2 * s.ncs]);
 }
 
 // Rows 0..2 of the model matrix T * R exactly as gm_mat4_multiply(translation, rotation) forms them
@@ -118,7 +129,7 @@ RP_HD int support_index(const Shape& s, V3 d) {
 	int best = 0;
 	double best_dot = -1.7976931348623157e308;
 	for (int i = 0; i < s.nv; ++i) {
-		double t = dot(s.tv[i], d);
+		double t = dot(vert(s, i), d);
 		if (t > best_dot) {
 			best = i;
 			best_dot = t;
@@ -128,7 +139,7 @@ RP_HD int support_index(const Shape& s, V3 d) {
 }
 // support_point (support.cpp:19-32)
 RP_HD V3 support(const Shape& s, V3 d) {
-	if (s.type == SHAPE_HULL) return s.tv[support_index(s, d)];
+	if (s.type == SHAPE_HULL) return vert(s, support_index(s, d));
 	return add(s.center, scale((double)s.radius, normalize(d)));
 }
 // support_point_of_minkowski_difference (support.cpp:34-39)
