@@ -32,9 +32,9 @@ ITERS = 1
 
 # Algorithmic work per item, derived in DESIGN.md ("Kernels and rooflines"): bytes that must move and FP64 operations
 # (mul/add/div/sqrt = 1 each, no FMA credit) for one body-substep / pair test / EPA+manifold run / solved contact.
-BYTES = dict(integrate=600.0, gjk=400.0, manifold=776.0, manifold_contact=64.0, solve_pos_pair=2 * (112.0 + 56.0), solve_contact=80.0,
+BYTES = dict(integrate=600.0, gjk=400.0, epa=16.0 + 96.0 + 384.0 + 40.0, manifold=40.0 + 16.0 + 672.0 + 2 * 56.0, manifold_contact=64.0, solve_pos_pair=2 * (112.0 + 56.0), solve_contact=80.0,
              solve_vel_pair=2 * (128.0 + 48.0), solve_contact_vel=64.0)
-FLOPS = dict(integrate=770.0, gjk=620.0, manifold=2000.0, solve_pos_contact=1100.0, solve_vel_contact=650.0)
+FLOPS = dict(integrate=770.0, gjk=620.0, epa=800.0, manifold=1200.0, solve_pos_contact=1100.0, solve_vel_contact=650.0)
 FLOP_PER_BODY_SUBSTEP = 4.0e3  # algorithmic FP64 flop per body-substep on the W256 world
 
 
@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU")
     ap.add_argument("--no-cull", action="store_true", help="run GJK on every broadphase pair (disables the exact-safe bounds cull)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / profile / cpu baseline (kernel timing only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (tuning runs)")
     return ap.parse_args()
 
 
@@ -221,11 +222,11 @@ def run_ours(args):
     units = NB * W * SUBSTEPS * args.steps * world_size
     value = units / (ms * 1e-3)
     status = batch.status()
-    # kernels launched in the timed region: per frame 7 prologue kernels + per substep integrate, cull, gjk, manifold,
-    # derive and one positional + one velocity launch per dependency level, + the frame counter
+    # kernels launched in the timed region: per frame 7 prologue kernels + per substep reset, integrate, cull, gjk, hits,
+    # epa, manifold, derive and one positional + one velocity launch per dependency level, + the frame counter
     c_levels = batch.counters()
     depth = int(round(c_levels["levels"] / max(1, c_levels["frames"]) / W)) if c_levels["frames"] else 0
-    launches_total = args.steps * (7 + SUBSTEPS * (5 + depth * (ITERS + 1)) + 1)
+    launches_total = args.steps * (7 + SUBSTEPS * (8 + depth * (ITERS + 1)) + 1)
 
     line = {"metric": "body-substeps/sec", "value": value, "unit": "body-substeps/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -266,10 +267,11 @@ def run_ours(args):
         contacts = c1["contacts"] - c0["contacts"]
         bs = NB * W * SUBSTEPS * args.steps
         alg_bytes = {"integrate": BYTES["integrate"] * bs, "gjk": BYTES["gjk"] * tests,
+                     "epa": BYTES["epa"] * hits,
                      "manifold": BYTES["manifold"] * hits + BYTES["manifold_contact"] * contacts,
                      "solve_pos": BYTES["solve_pos_pair"] * hits + BYTES["solve_contact"] * contacts,
                      "solve_vel": BYTES["solve_vel_pair"] * hits + BYTES["solve_contact_vel"] * contacts}
-        alg_flops = {"integrate": FLOPS["integrate"] * bs, "gjk": FLOPS["gjk"] * tests, "manifold": FLOPS["manifold"] * hits,
+        alg_flops = {"integrate": FLOPS["integrate"] * bs, "gjk": FLOPS["gjk"] * tests, "epa": FLOPS["epa"] * hits, "manifold": FLOPS["manifold"] * hits,
                      "solve_pos": FLOPS["solve_pos_contact"] * contacts, "solve_vel": FLOPS["solve_vel_contact"] * contacts}
         total_ms = sum(fam.values())
         top = max(fam, key=fam.get)
@@ -294,7 +296,7 @@ def run_ours(args):
             t = torch.tensor([float(tests), float(hits), float(contacts)], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             line["aggregate_work"] = {"pair_tests": t[0].item(), "epa_runs": t[1].item(), "contacts": t[2].item()}
-        if rank == 0 and world_size == 1:
+        if rank == 0 and world_size == 1 and not args.no_cpu:
             import refdrv
             line["cpu_baseline"] = cpu_single_thread_baseline("strict" if refdrv.available("strict") else "port")
 

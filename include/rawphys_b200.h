@@ -152,7 +152,7 @@ int rp_batch_broad_pairs(rp_batch* b, uint32_t world, uint32_t* pairs_out, uint3
 /* Profiling aids (bench.py). Kernel families of one frame, in launch order. */
 enum {
 	RP_K_BROAD = 0, RP_K_ISLANDS, RP_K_SCHEDULE, RP_K_INTEGRATE, RP_K_CULL, RP_K_GJK, RP_K_MANIFOLD, RP_K_SOLVE_POS, RP_K_DERIVE,
-	RP_K_SOLVE_VEL, RP_NUM_KERNEL_FAMILIES
+	RP_K_SOLVE_VEL, RP_K_EPA, RP_NUM_KERNEL_FAMILIES
 };
 /* device milliseconds per kernel family over `frames` un-graphed frames (CUDA events at every kernel boundary) */
 int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t num_substeps, uint32_t num_pos_iters, int enable_collisions,

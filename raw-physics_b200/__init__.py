@@ -33,7 +33,7 @@ EXPORTS = [
     "rp_batch_get_status", "rp_batch_get_counters", "rp_batch_step_logged", "rp_batch_broad_pairs", "rp_batch_profile",
     "rp_measure_fp64_peak",
 ]
-KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "cull", "gjk", "manifold", "solve_pos", "derive", "solve_vel"]
+KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "cull", "gjk", "manifold", "solve_pos", "derive", "solve_vel", "epa"]
 
 
 class BatchCfg(C.Structure):

@@ -341,15 +341,32 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	d.max_levels = jl_max + d.max_pairs;
 	b->joint_level = jlevel;
 
-	// template
+	// template: per-body records + de-duplicated physical classes
 	std::vector<BodyStatic> bs(d.NB);
+	std::vector<BodyClass> classes;
 	for (int i = 0; i < d.NB; ++i) {
 		const BodyInit& bi = s.bodies[i];
 		BodyStatic& o = bs[i];
 		memset(&o, 0, sizeof(o));
-		o.inv_mass = bi.inv_mass;
-		o.inertia = bi.inertia; o.inv_inertia = bi.inv_inertia;
-		o.mu_s = bi.mu_s; o.mu_d = bi.mu_d; o.rest = bi.rest; o.radius = bi.radius;
+		BodyClass bc;
+		memset(&bc, 0, sizeof(bc));
+		bc.inv_mass = bi.inv_mass;
+		bc.inertia = bi.inertia; bc.inv_inertia = bi.inv_inertia;
+		bc.mu_s = bi.mu_s; bc.mu_d = bi.mu_d; bc.rest = bi.rest;
+		int cls = -1;
+		// bitwise comparison (signed zeros and all); scenes have few classes, and the most recent one usually matches
+		for (int k = (int)classes.size() - 1; k >= 0 && k >= (int)classes.size() - 64; --k) {
+			if (memcmp(&classes[k], &bc, sizeof(bc)) == 0) {
+				cls = k;
+				break;
+			}
+		}
+		if (cls < 0) {
+			cls = (int)classes.size();
+			classes.push_back(bc);
+		}
+		o.cls = cls;
+		o.radius = bi.radius;
 		o.fixed = bi.fixed; o.col0 = bi.col0; o.ncol = bi.ncol;
 		o.tv0 = bi.ncol ? s.colliders[bi.col0].tv0 : 0;
 		o.tn0 = bi.ncol ? s.colliders[bi.col0].tn0 : 0;
@@ -362,6 +379,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	HullPoolHost hp = pool_hulls(s);
 	int rc;
 	if ((rc = dev_upload(b, &d.bstat, bs))) return rc;
+	if ((rc = dev_upload(b, &d.bclass, classes))) return rc;
 	if ((rc = dev_upload(b, &d.cols, s.colliders))) return rc;
 	if ((rc = dev_upload(b, &d.joints, s.joints))) return rc;
 	if ((rc = dev_upload(b, &d.joint_sched, jsched))) return rc;
@@ -401,8 +419,11 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.aabb, W * std::max(d.NC, 1) * 6))) return rc;
 	if ((rc = dev_alloc(b, &d.cands, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.cand_count, 1))) return rc;
+	if ((rc = dev_alloc(b, &d.verdict, WP, false))) return rc;
+	if ((rc = dev_alloc(b, &d.simplex, WP * 4, false))) return rc;
 	if ((rc = dev_alloc(b, &d.hits, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.hit_count, 1))) return rc;
+	if ((rc = dev_alloc(b, &d.epa_out, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_cap, (size_t)d.max_levels + 2))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_off, (size_t)d.max_levels + 2))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_fill, ((size_t)d.max_levels + 2) * RP_LVL_STRIDE))) return rc;
@@ -498,28 +519,42 @@ static int prologue_levels(rp_batch* b, double dt, int collisions, int* levels) 
 	return RP_OK;
 }
 
-static unsigned int level_grid(const rp_batch* b) { return (unsigned int)b->sm_count * 8u; }
+// The level kernels are refill loops over warp-owned chunks (WarpQueue): launch exactly the resident grid so that every
+// lane owns several manifolds.
+static unsigned int pos_grid(const rp_batch* b) { return (unsigned int)b->sm_count * RP_MINB_POS; }
+static unsigned int vel_grid(const rp_batch* b) { return (unsigned int)b->sm_count * RP_MINB_VEL; }
 
 static void enqueue_integrate(rp_batch* b, double h) {
 	const DevView& d = b->d;
 	k_substep_reset<<<(unsigned int)((std::max(d.W, d.max_levels + 2) + 255) / 256), 256, 0, b->stream>>>(d);
-	k_integrate<<<dim3((d.NB + 127) / 128, d.W), 128, 0, b->stream>>>(d, h);
+	k_integrate<<<(unsigned int)(((size_t)d.W * d.NB + RP_INT_THREADS - 1) / RP_INT_THREADS), RP_INT_THREADS, 0, b->stream>>>(d, h);
+}
+// grid of the per-hit kernel: the hit count lives on the device, so the launch covers the candidate capacity in
+// grid-stride trips of at most this many CTAs
+static unsigned int manifold_grid(const rp_batch* b) { return (unsigned int)b->sm_count * 16u; }
+static void launch_cull(rp_batch* b) { k_cull<<<dim3(b->cull_chunks, b->d.W), 256, 0, b->stream>>>(b->d, b->cull); }
+static void launch_gjk(rp_batch* b) {
+	k_gjk<<<b->sm_count * RP_MINB_GJK, RP_GJK_THREADS, 0, b->stream>>>(b->d);
+	k_hits<<<b->sm_count * 8, 256, 0, b->stream>>>(b->d);
+}
+static void launch_manifold(rp_batch* b) {
+	k_epa<<<b->sm_count * RP_MINB_EPA, RP_EPA_THREADS, 0, b->stream>>>(b->d);
+	k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, 0, b->stream>>>(b->d);
 }
 static void enqueue_narrow(rp_batch* b) {
-	const DevView& d = b->d;
-	k_cull<<<dim3(b->cull_chunks, d.W), 256, 0, b->stream>>>(d, b->cull);
-	k_gjk<<<b->sm_count * 16, RP_GJK_THREADS, 0, b->stream>>>(d);
-	k_manifold<<<b->sm_count * 4, RP_MANIFOLD_THREADS, 0, b->stream>>>(d);
+	launch_cull(b);
+	launch_gjk(b);
+	launch_manifold(b);
 }
 static void enqueue_solve(rp_batch* b, double h, uint32_t iters, int collisions, int levels) {
 	const DevView& d = b->d;
 	for (uint32_t it = 0; it < iters; ++it) {
-		for (int l = 1; l <= levels; ++l) k_pos_level<<<level_grid(b), 128, 0, b->stream>>>(d, h, l, collisions);
+		for (int l = 1; l <= levels; ++l) k_pos_level<<<pos_grid(b), 128, 0, b->stream>>>(d, h, l, collisions);
 	}
 	const size_t WB = (size_t)d.W * d.NB;
 	k_derive<<<(unsigned int)((WB + 127) / 128), 128, 0, b->stream>>>(d, h);
 	if (collisions) {
-		for (int l = 1; l <= levels; ++l) k_vel_level<<<level_grid(b), 128, 0, b->stream>>>(d, h, l);
+		for (int l = 1; l <= levels; ++l) k_vel_level<<<vel_grid(b), 128, 0, b->stream>>>(d, h, l);
 	}
 }
 
@@ -801,21 +836,23 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 			enqueue_integrate(b, h);
 			if ((rc = mark(RP_K_INTEGRATE))) return rc;
 			if (collisions) {
-				k_cull<<<dim3(b->cull_chunks, d.W), 256, 0, b->stream>>>(d, b->cull);
+				launch_cull(b);
 				if ((rc = mark(RP_K_CULL))) return rc;
-				k_gjk<<<b->sm_count * 16, RP_GJK_THREADS, 0, b->stream>>>(d);
+				launch_gjk(b);
 				if ((rc = mark(RP_K_GJK))) return rc;
-				k_manifold<<<b->sm_count * 4, RP_MANIFOLD_THREADS, 0, b->stream>>>(d);
+				k_epa<<<b->sm_count * RP_MINB_EPA, RP_EPA_THREADS, 0, b->stream>>>(d);
+				if ((rc = mark(RP_K_EPA))) return rc;
+				k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_MANIFOLD))) return rc;
 			}
 			for (uint32_t it = 0; it < iters; ++it) {
-				for (int l = 1; l <= levels; ++l) k_pos_level<<<level_grid(b), 128, 0, b->stream>>>(d, h, l, collisions ? 1 : 0);
+				for (int l = 1; l <= levels; ++l) k_pos_level<<<pos_grid(b), 128, 0, b->stream>>>(d, h, l, collisions ? 1 : 0);
 			}
 			if ((rc = mark(RP_K_SOLVE_POS))) return rc;
 			k_derive<<<(unsigned int)(((size_t)d.W * d.NB + 127) / 128), 128, 0, b->stream>>>(d, h);
 			if ((rc = mark(RP_K_DERIVE))) return rc;
 			if (collisions) {
-				for (int l = 1; l <= levels; ++l) k_vel_level<<<level_grid(b), 128, 0, b->stream>>>(d, h, l);
+				for (int l = 1; l <= levels; ++l) k_vel_level<<<vel_grid(b), 128, 0, b->stream>>>(d, h, l);
 				if ((rc = mark(RP_K_SOLVE_VEL))) return rc;
 			}
 		}

@@ -16,21 +16,28 @@ namespace rp {
 struct BodyDyn {
 	double x[3], q[4], v[3], w[3], px[3], pq[4], pv[3], pw[3];
 };
-// per-body static parameters, shared by all worlds (template)
-struct BodyStatic {
+// Physical parameters of a body, shared by all worlds (template) and de-duplicated: bodies with bit-identical mass,
+// tensors and coefficients share one record (W256: 2 classes for 257 bodies), so the lanes of a warp that work on
+// different bodies of the same class read the SAME addresses (one broadcast wavefront instead of 32 scattered ones).
+struct BodyClass {
 	double inv_mass;
 	M3 inertia, inv_inertia;
-	double mu_s, mu_d, rest, radius;
+	double mu_s, mu_d, rest;
+};
+// per-body static parameters, shared by all worlds (template)
+struct BodyStatic {
+	double radius;
+	int cls;                  // index into DevView::bclass
 	int fixed, col0, ncol;
 	int tv0, tvn, tn0, tnn;   // extent of the body's colliders in a world's transformed vertex / normal arrays
-	int pad;
 };
 struct PairRec {  // one broadphase pair, expanded to collider granularity: bodies a < b, global collider indices ca, cb
 	int a, b, ca, cb;
 };
-struct HitRec {  // GJK verdict "colliding": work item of k_manifold
-	int world, pair;
-	V3 sa, sb, sc, sd;
+struct EpaOut {  // result of EPA (or the analytic sphere-sphere test) for one hit: work item of k_manifold
+	V3 normal;
+	double depth;
+	int ok, pad;
 };
 
 enum { CNT_PAIR_TESTS = 0, CNT_HITS = 1, CNT_CONTACTS = 2, CNT_BROAD_PAIRS = 3, CNT_LEVELS = 4, CNT_FRAMES = 5 };
@@ -41,6 +48,7 @@ struct DevView {
 	double lin_sleep, ang_sleep, sleep_time;
 	// template
 	const BodyStatic* bstat;
+	const BodyClass* bclass;
 	const ColliderDesc* cols;
 	HullPool pool;
 	const Joint* joints;
@@ -63,8 +71,11 @@ struct DevView {
 	double* aabb;        // [W][NC][6] world-space bounds of every collider (min xyz, max xyz)
 	uint2* cands;        // [W * max_pairs] (world, pair) that survived the skip rule and the bounds cull
 	unsigned int* cand_count;
-	HitRec* hits;        // [W * max_pairs]
+	unsigned char* verdict;  // [W * max_pairs] per candidate: narrowphase says "colliding"
+	V3* simplex;         // [W * max_pairs][4] final GJK tetrahedron of colliding candidates
+	unsigned int* hits;  // [W * max_pairs] indices of the colliding candidates (dense)
 	unsigned int* hit_count;
+	EpaOut* epa_out;     // [W * max_pairs] per hit
 	// level-major work lists shared by all worlds: the pairs of dependency level l that have contacts this substep
 	int max_levels;
 	int* lvl_cap;        // [max_levels + 2] pairs scheduled at level l over all worlds (per frame)

@@ -20,6 +20,9 @@
 #ifndef RP_MINB_MANIFOLD
 #define RP_MINB_MANIFOLD 4
 #endif
+#ifndef RP_MINB_EPA
+#define RP_MINB_EPA 8
+#endif
 #ifndef RP_MINB_POS
 #define RP_MINB_POS 2
 #endif
@@ -30,10 +33,14 @@
 #define RP_GJK_THREADS 64
 #define RP_GJK_STAGE 48          // doubles of shared memory per thread: two hulls of up to 16 vertices in total
 #define RP_MANIFOLD_THREADS 128
-#define RP_MANIFOLD_STAGE 0      // doubles of shared memory per thread for staged hulls in k_manifold (0 = off: measured slower)
+#define RP_EPA_THREADS 64
 
 #define RP_LVL_SMEM 64     // levels ranked through shared memory in k_manifold
-#define RP_LVL_STRIDE 32   // ints between consecutive level fill counters (one 128-byte line each)
+#define RP_LVL_STRIDE 32   // ints between consecutive level fill counters (one 128-byte line each: [0] front, [1] back)
+#ifndef RP_SMALL_MANIFOLD
+#define RP_SMALL_MANIFOLD 1000000  // (off: the refill loops of the solver kernels make manifold length irrelevant)
+// manifolds of up to this many contacts fill a level list from the front, larger ones from the back
+#endif
 
 namespace rp {
 
@@ -43,11 +50,13 @@ __device__ __forceinline__ Q4 ld4(const double* p) { return q4(p[0], p[1], p[2],
 __device__ __forceinline__ void st3(double* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
 __device__ __forceinline__ void st4(double* p, Q4 q) { p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w; }
 
-__device__ __forceinline__ void load_static(Body& b, const BodyStatic& s) {
-	b.inv_mass = s.inv_mass;
-	b.inertia = s.inertia;
-	b.inv_inertia = s.inv_inertia;
-	b.mu_s = s.mu_s; b.mu_d = s.mu_d; b.rest = s.rest;
+__device__ __forceinline__ void load_static(Body& b, const DevView& d, int body) {
+	const BodyStatic& s = d.bstat[body];
+	const BodyClass& c = d.bclass[s.cls];
+	b.inv_mass = c.inv_mass;
+	b.inertia = c.inertia;
+	b.inv_inertia = c.inv_inertia;
+	b.mu_s = c.mu_s; b.mu_d = c.mu_d; b.rest = c.rest;
 	b.fixed = s.fixed;
 }
 __device__ __forceinline__ void load_dyn(Body& b, const BodyDyn& d) {
@@ -270,33 +279,49 @@ __global__ void __launch_bounds__(256) k_substep_reset(DevView d) {
 		*d.hit_count = 0u;
 		*d.cand_count = 0u;
 	}
-	if (i < d.max_levels + 2) d.lvl_fill[(size_t)i * RP_LVL_STRIDE] = 0;
+	if (i < d.max_levels + 2) {
+		d.lvl_fill[(size_t)i * RP_LVL_STRIDE] = 0;
+		d.lvl_fill[(size_t)i * RP_LVL_STRIDE + 1] = 0;
+	}
 	if (i < d.W) d.n_contacts[i] = 0;
 }
 
 #define RP_INT_MAXV 8   // staged write path of k_integrate: bodies of up to 8 transformed vertices and 6 normals (boxes)
 #define RP_INT_MAXF 6
-__global__ void __launch_bounds__(128, RP_MINB_INTEGRATE) k_integrate(DevView d, double h) {
-	// Transformed geometry of the CTA's 128 bodies, staged so that the global writes are coalesced. Rows are padded to an
-	// odd number of doubles: per-thread rows are then free of bank conflicts.
-	__shared__ double s_tv[128 * (RP_INT_MAXV * 3 + 1)];
-	__shared__ double s_tn[128 * (RP_INT_MAXF * 3 + 1)];
-	const int w = blockIdx.y;
-	const int b0 = blockIdx.x * blockDim.x;
-	const int b = b0 + threadIdx.x;
-	const int nb = min(128, d.NB - b0);
-	// staged path only when every body of the CTA has the same small footprint, laid out back to back
-	const BodyStatic& s0 = d.bstat[b0];
-	const int tvn = s0.tvn, tnn = s0.tnn;
-	bool uniform = tvn <= RP_INT_MAXV && tnn <= RP_INT_MAXF;
-	if (b < d.NB) {
-		const BodyStatic& sb = d.bstat[b];
-		uniform = uniform && sb.tvn == tvn && sb.tnn == tnn && sb.tv0 == s0.tv0 + (b - b0) * tvn && sb.tn0 == s0.tn0 + (b - b0) * tnn;
+#define RP_INT_THREADS 128
+#define RP_DYN_DOUBLES 26   // sizeof(BodyDyn) / 8
+#define RP_DYN_LIVE 20      // x q v w px pq: the part of a record k_integrate reads or writes (pv, pw stay untouched)
+#define RP_DYN_ROW 27       // odd row pitch in shared memory: per-thread rows are free of bank conflicts
+// One thread per (world, body), flat over the whole batch: a CTA owns 128 consecutive BodyDyn records, which are
+// contiguous in HBM, so they are moved with coalesced loads/stores through shared memory (per-lane gathers of 208-byte
+// records were the kernel's long-scoreboard stall). The same shared memory is then reused to stage the transformed
+// geometry of the CTA's bodies so that those writes are coalesced too.
+__global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate(DevView d, double h) {
+	__shared__ double s_buf[RP_INT_THREADS * ((RP_INT_MAXV * 3 + 1) + (RP_INT_MAXF * 3 + 1))];
+	static_assert(RP_INT_THREADS * RP_DYN_ROW <= RP_INT_THREADS * ((RP_INT_MAXV * 3 + 1) + (RP_INT_MAXF * 3 + 1)), "staging buffer");
+	const size_t total = (size_t)d.W * d.NB;
+	const size_t g0 = (size_t)blockIdx.x * RP_INT_THREADS;
+	const int nb = (int)(total - g0 < (size_t)RP_INT_THREADS ? total - g0 : (size_t)RP_INT_THREADS);
+	const size_t gid = g0 + threadIdx.x;
+	const bool live = threadIdx.x < nb;
+	const int w = live ? (int)(gid / d.NB) : 0;
+	const int b = live ? (int)(gid % d.NB) : 0;
+	// ---- coalesced load of the CTA's records
+	{
+		const double* g = (const double*)(d.dyn + g0);
+		int r = threadIdx.x / RP_DYN_DOUBLES, c = threadIdx.x - r * RP_DYN_DOUBLES;
+		for (int e = threadIdx.x; e < nb * RP_DYN_DOUBLES; e += RP_INT_THREADS) {
+			if (c < 13) s_buf[r * RP_DYN_ROW + c] = g[e];
+			r += RP_INT_THREADS / RP_DYN_DOUBLES; c += RP_INT_THREADS % RP_DYN_DOUBLES;
+			if (c >= RP_DYN_DOUBLES) { c -= RP_DYN_DOUBLES; ++r; }
+		}
 	}
-	const bool staged = __syncthreads_and(uniform) != 0;
-	const int rv = tvn * 3 + 1, rn = tnn * 3 + 1;
-	if (b < d.NB) {
-		const size_t gid = (size_t)w * d.NB + b;
+	__syncthreads();
+	Body body;
+	BodyStatic s;
+	s.fixed = 1; s.col0 = 0; s.ncol = 0; s.tv0 = 0; s.tvn = 0; s.tn0 = 0; s.tnn = 0; s.cls = 0; s.radius = 0.0;
+	double* row = s_buf + threadIdx.x * RP_DYN_ROW;
+	if (live) {
 		if (b < d.NJ) {  // copy_constraints resets every lambda each substep (pbd.cpp:426-462)
 			for (int j = b; j < d.NJ; j += d.NB) {
 				JointLambda z;
@@ -304,17 +329,44 @@ __global__ void __launch_bounds__(128, RP_MINB_INTEGRATE) k_integrate(DevView d,
 				d.lambdas[(size_t)w * d.NJ + j] = z;
 			}
 		}
-		const BodyStatic& s = d.bstat[b];
-		BodyDyn& dd = d.dyn[gid];
-		Body body;
-		load_static(body, s);
-		body.x = ld3(dd.x); body.q = ld4(dd.q); body.v = ld3(dd.v); body.w = ld3(dd.w);
+		s = d.bstat[b];
+		load_static(body, d, b);
+		body.x = ld3(row); body.q = ld4(row + 3); body.v = ld3(row + 7); body.w = ld3(row + 10);
 		body.active = d.active[gid];
 		integrate(body, h, d.force[b], d.torque[b]);
-		st3(dd.px, body.px); st4(dd.pq, body.pq);
-		if (!(body.fixed || !body.active)) {
-			st3(dd.x, body.x); st4(dd.q, body.q); st3(dd.v, body.v); st3(dd.w, body.w);
+		st3(row, body.x); st4(row + 3, body.q); st3(row + 7, body.v); st3(row + 10, body.w);  // unchanged when fixed or asleep
+		st3(row + 13, body.px); st4(row + 16, body.pq);
+	}
+	__syncthreads();
+	{
+		double* g = (double*)(d.dyn + g0);
+		int r = threadIdx.x / RP_DYN_DOUBLES, c = threadIdx.x - r * RP_DYN_DOUBLES;
+		for (int e = threadIdx.x; e < nb * RP_DYN_DOUBLES; e += RP_INT_THREADS) {
+			if (c < RP_DYN_LIVE) g[e] = s_buf[r * RP_DYN_ROW + c];
+			r += RP_INT_THREADS / RP_DYN_DOUBLES; c += RP_INT_THREADS % RP_DYN_DOUBLES;
+			if (c >= RP_DYN_DOUBLES) { c -= RP_DYN_DOUBLES; ++r; }
 		}
+	}
+	// ---- collider update. Staged path only when every body of the CTA has the same small footprint and the CTA's
+	// blocks of transformed vertices / normals are laid out back to back (they are, across world boundaries too, when
+	// all bodies of the scene have that footprint: TV = NB * tvn).
+	size_t voff = 0, noff = 0;
+	if (live) {
+		voff = (size_t)w * d.TV + s.tv0;
+		noff = (size_t)w * d.TN + s.tn0;
+	}
+	__shared__ size_t s_off[2];
+	__shared__ int s_foot[2];
+	if (threadIdx.x == 0) { s_off[0] = voff; s_off[1] = noff; s_foot[0] = s.tvn; s_foot[1] = s.tnn; }
+	__syncthreads();  // also fences the write-back reads of s_buf against the staging writes below
+	const int tvn = s_foot[0], tnn = s_foot[1];
+	bool uniform = tvn <= RP_INT_MAXV && tnn <= RP_INT_MAXF;
+	if (live) uniform = uniform && s.tvn == tvn && s.tnn == tnn && voff == s_off[0] + (size_t)threadIdx.x * tvn && noff == s_off[1] + (size_t)threadIdx.x * tnn;
+	const bool staged = __syncthreads_and(uniform) != 0;
+	const int rv = tvn * 3 + 1, rn = tnn * 3 + 1;
+	double* s_tv = s_buf;
+	double* s_tn = s_buf + RP_INT_THREADS * (RP_INT_MAXV * 3 + 1);
+	if (live) {
 		Pose34 M = model_matrix(body.q, body.x);
 		V3* tv = d.tv + (size_t)w * d.TV;
 		V3* tn = d.tn + (size_t)w * d.TN;
@@ -351,11 +403,28 @@ __global__ void __launch_bounds__(128, RP_MINB_INTEGRATE) k_integrate(DevView d,
 	}
 	if (staged) {
 		__syncthreads();
-		double* gv = (double*)(d.tv + (size_t)w * d.TV + s0.tv0);
-		double* gn = (double*)(d.tn + (size_t)w * d.TN + s0.tn0);
+		double* gv = (double*)(d.tv + s_off[0]);
+		double* gn = (double*)(d.tn + s_off[1]);
 		const int nv3 = tvn * 3, nn3 = tnn * 3;
-		for (int g = threadIdx.x; g < nb * nv3; g += blockDim.x) gv[g] = s_tv[(g / nv3) * rv + g % nv3];
-		for (int g = threadIdx.x; g < nb * nn3; g += blockDim.x) gn[g] = s_tn[(g / nn3) * rn + g % nn3];
+		// g = r * n3 + c walks in steps of the CTA size; (r, c) are advanced without dividing
+		if (nv3 > 0) {
+			int r = threadIdx.x / nv3, c = threadIdx.x - r * nv3;
+			const int dr = RP_INT_THREADS / nv3, dc = RP_INT_THREADS - dr * nv3;
+			for (int g = threadIdx.x; g < nb * nv3; g += RP_INT_THREADS) {
+				gv[g] = s_tv[r * rv + c];
+				r += dr; c += dc;
+				if (c >= nv3) { c -= nv3; ++r; }
+			}
+		}
+		if (nn3 > 0) {
+			int r = threadIdx.x / nn3, c = threadIdx.x - r * nn3;
+			const int dr = RP_INT_THREADS / nn3, dc = RP_INT_THREADS - dr * nn3;
+			for (int g = threadIdx.x; g < nb * nn3; g += RP_INT_THREADS) {
+				gn[g] = s_tn[r * rn + c];
+				r += dr; c += dc;
+				if (c >= nn3) { c -= nn3; ++r; }
+			}
+		}
 	}
 }
 
@@ -432,52 +501,189 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 	if ((threadIdx.x & 31) == 0 && tested) atomicAdd(&d.counters[CNT_PAIR_TESTS], (unsigned long long)tested);
 }
 
-// ----------------------------------------------------------------------------------------------------- narrowphase 1
-// One thread per candidate pair: sphere-sphere test or boolean GJK (collider.cpp:523-547). Colliding pairs are appended
-// to the global hit list for k_manifold.
+// ----------------------------------------------------------------------------------------------------- narrowphase
+// GJK, EPA and the contact solves are loops whose trip counts differ from pair to pair (GJK 1..15 support iterations,
+// EPA 1..8, manifolds of 1..8 contacts). With one work item per lane a warp runs as long as its slowest lane and the
+// other lanes idle (ncu, round 1: 9..15 of 32 lanes active). The kernels below are therefore written as REFILL loops:
+// a warp owns a contiguous chunk of the work list, every trip of the loop is one iteration of the algorithm for
+// whatever item a lane currently holds, and a lane whose item is finished takes the warp's next item before the next
+// trip. The warp's cursor is warp-uniform (ballot + popc), so taking work needs no atomics.
+struct WarpQueue {
+	unsigned int next, end;
+	__device__ __forceinline__ void init(unsigned int n_items) {
+		const unsigned int warps = gridDim.x * (blockDim.x >> 5);
+		const unsigned int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+		unsigned int chunk = (n_items + warps - 1) / warps;
+		if (chunk < 32u) chunk = 32u;
+		const unsigned long long lo = (unsigned long long)wid * chunk;
+		next = lo < n_items ? (unsigned int)lo : n_items;
+		end = lo + chunk < n_items ? (unsigned int)(lo + chunk) : n_items;
+	}
+	// every lane calls this; lanes with want == true get the next items of the chunk (or 0xffffffff when it is used up)
+	__device__ __forceinline__ unsigned int take(bool want) {
+		const unsigned int mask = __ballot_sync(0xffffffffu, want);
+		const unsigned int mine = next + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u));
+		next += __popc(mask);
+		if (next > end) next = end;
+		return want && mine < end ? mine : 0xffffffffu;
+	}
+	__device__ __forceinline__ bool empty() const { return next >= end; }
+};
+
+// One lane per candidate pair at a time: sphere-sphere test or boolean GJK (collider.cpp:523-547). Writes the verdict of
+// every candidate and, for colliding pairs, the final simplex, both at the candidate's own index (k_hits compacts).
 __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) {
 	const unsigned int nc = *d.cand_count;
 	__shared__ double s_stage[RP_GJK_STAGE * RP_GJK_THREADS];
-	for (unsigned int c0 = blockIdx.x * blockDim.x; c0 < nc; c0 += gridDim.x * blockDim.x) {
-		const unsigned int ci = c0 + threadIdx.x;
-		bool hit = false;
-		Simplex s;
-		s.a = s.b = s.c = s.d = v3(0.0, 0.0, 0.0);
-		int w = 0, p = 0;
-		if (ci < nc) {
+	WarpQueue q;
+	q.init(nc);
+	bool have = false;
+	unsigned int ci = 0;
+	int w = 0, iter = 0, st = 0;
+	Simplex s;
+	s.a = s.b = s.c = s.d = v3(0.0, 0.0, 0.0);
+	s.num = 0;
+	V3 dir = v3(0.0, 0.0, 0.0);
+	Shape A, B;
+	A.type = B.type = SHAPE_SPHERE; A.nv = B.nv = 0;
+	for (;;) {
+		const unsigned int got = q.take(!have);
+		if (got != 0xffffffffu) {
+			ci = got;
 			const uint2 cd = d.cands[ci];
-			w = (int)cd.x; p = (int)cd.y;
-			const PairRec pr = d.pairs[(size_t)w * d.max_pairs + p];
+			w = (int)cd.x;
+			const PairRec pr = d.pairs[(size_t)w * d.max_pairs + cd.y];
 			const V3* tv = d.tv + (size_t)w * d.TV;
 			const V3* tn = d.tn + (size_t)w * d.TN;
-			Shape A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
-			Shape B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
-			int st = 0;
+			A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
+			B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
 			if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
 				V3 n;
 				double depth;
-				hit = sphere_sphere(A, B, &n, &depth);
+				d.verdict[ci] = sphere_sphere(A, B, &n, &depth) ? 1 : 0;  // decided on the spot; the lane refills next trip
 			} else {
 				if ((A.nv + B.nv) * 3 <= RP_GJK_STAGE) {
 					double* col = s_stage + threadIdx.x;
 					const int used = stage_shape(A, col, RP_GJK_THREADS, false);
 					stage_shape(B, col + (size_t)used * RP_GJK_THREADS, RP_GJK_THREADS, false);
 				}
-				hit = gjk(A, B, &s, &st, 0);
+				gjk_begin(A, B, &s, &dir);
+				iter = 0;
+				have = true;
 			}
-			if (st) atomicOr(&d.status[w], st);
 		}
-		const unsigned int slot = warp_append(d.hit_count, hit);
-		if (hit) {
-			HitRec hr;
-			hr.world = w; hr.pair = p;
-			hr.sa = s.a; hr.sb = s.b; hr.sc = s.c; hr.sd = s.d;
-			d.hits[slot] = hr;
+		if (!__any_sync(0xffffffffu, have)) {
+			if (q.empty()) break;
+			continue;
+		}
+		if (have) {
+			int r = gjk_step(A, B, &s, &dir, &st);
+			if (r == GJK_CONTINUE && ++iter >= RP_GJK_MAX_ITERS) r = GJK_MISS;  // gjk.cpp:358
+			if (r != GJK_CONTINUE) {
+				d.verdict[ci] = r == GJK_HIT ? 1 : 0;
+				if (r == GJK_HIT) {
+					V3* o = d.simplex + (size_t)ci * 4;
+					o[0] = s.a; o[1] = s.b; o[2] = s.c; o[3] = s.d;
+				}
+				if (st) {
+					atomicOr(&d.status[w], st);
+					st = 0;
+				}
+				have = false;
+			}
 		}
 	}
 }
 
-// ----------------------------------------------------------------------------------------------------- narrowphase 2
+// candidate verdicts -> dense hit list (order is irrelevant downstream)
+__global__ void __launch_bounds__(256) k_hits(DevView d) {
+	const unsigned int nc = *d.cand_count;
+	for (unsigned int c0 = blockIdx.x * blockDim.x; c0 < nc; c0 += gridDim.x * blockDim.x) {
+		const unsigned int ci = c0 + threadIdx.x;
+		const bool hit = ci < nc && d.verdict[ci] != 0;
+		const unsigned int slot = warp_append(d.hit_count, hit);
+		if (hit) d.hits[slot] = ci;
+	}
+}
+
+// EPA (epa.cpp:118) for every hit, refill loop over its iterations. The polytope lives in the lane's local memory; the
+// two hulls' vertices are staged in shared memory as in k_gjk (EPA only ever asks for support points).
+__global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) {
+	const unsigned int nh = *d.hit_count;
+	__shared__ double s_stage[RP_GJK_STAGE * RP_EPA_THREADS];
+	WarpQueue q;
+	q.init(nh);
+	bool have = false;
+	unsigned int hi = 0;
+	int w = 0, iter = 0, st = 0;
+	EpaScratch e;
+	Shape A, B;
+	A.type = B.type = SHAPE_SPHERE; A.nv = B.nv = 0;
+	for (;;) {
+		const unsigned int got = q.take(!have);
+		if (got != 0xffffffffu) {
+			hi = got;
+			const unsigned int ci = d.hits[hi];
+			const uint2 cd = d.cands[ci];
+			w = (int)cd.x;
+			const PairRec pr = d.pairs[(size_t)w * d.max_pairs + cd.y];
+			const V3* tv = d.tv + (size_t)w * d.TV;
+			const V3* tn = d.tn + (size_t)w * d.TN;
+			A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
+			B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
+			EpaOut out;
+			out.ok = 0; out.pad = 0; out.depth = 0.0; out.normal = v3(0.0, 0.0, 0.0);
+			if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
+				out.ok = sphere_sphere(A, B, &out.normal, &out.depth) ? 1 : 0;
+				d.epa_out[hi] = out;
+			} else {
+				if ((A.nv + B.nv) * 3 <= RP_GJK_STAGE) {
+					double* col = s_stage + threadIdx.x;
+					const int used = stage_shape(A, col, RP_EPA_THREADS, false);
+					stage_shape(B, col + (size_t)used * RP_EPA_THREADS, RP_EPA_THREADS, false);
+				}
+				const V3* sp = d.simplex + (size_t)ci * 4;
+				Simplex s;
+				s.a = sp[0]; s.b = sp[1]; s.c = sp[2]; s.d = sp[3];
+				s.num = 4;
+				if (epa_begin(s, e, &st) == EPA_FAIL) {
+					d.epa_out[hi] = out;
+					atomicOr(&d.status[w], st);
+					st = 0;
+				} else {
+					iter = 0;
+					have = true;
+				}
+			}
+		}
+		if (!__any_sync(0xffffffffu, have)) {
+			if (q.empty()) break;
+			continue;
+		}
+		if (have) {
+			int r = epa_step(A, B, e, &st);
+			if (r == EPA_CONTINUE && ++iter >= RP_EPA_MAX_ITERS) {
+				st |= ST_EPA_NO_CONVERGENCE;  // epa.cpp:233
+				r = EPA_FAIL;
+			}
+			if (r != EPA_CONTINUE) {
+				EpaOut out;
+				out.ok = r == EPA_DONE ? 1 : 0;
+				out.pad = 0;
+				out.normal = e.min_normal;
+				out.depth = e.min_dist;
+				d.epa_out[hi] = out;
+				if (st) {
+					atomicOr(&d.status[w], st);
+					st = 0;
+				}
+				have = false;
+			}
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&d.counters[CNT_HITS], (unsigned long long)nh);
+}
+
 struct StageSink {
 	V3* stage;
 	int n, cap;
@@ -491,61 +697,40 @@ struct StageSink {
 };
 
 struct ManifoldScratch {
-	union {
-		EpaScratch epa;
-		struct {
-			ClipScratch clip;
-			V3 stage[2 * RP_CLIP_MAX_POINTS];
-		} m;
-	};
+	ClipScratch clip;
+	V3 stage[2 * RP_CLIP_MAX_POINTS];
 };
 
-// One thread per colliding collider pair: EPA (epa.cpp:118), manifold (clipping.cpp:343), contact -> constraint
+// One thread per colliding collider pair whose EPA converged: manifold (clipping.cpp:343), contact -> constraint
 // (pbd.cpp:408-424). The pair's contacts get a contiguous run in the world's contact buffer (allocation order between
 // pairs is irrelevant: the solver walks pairs, not the buffer), and the pair is appended to the work list of its
 // dependency level.
 __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manifold(DevView d) {
-	__shared__ double s_stage[RP_MANIFOLD_STAGE * RP_MANIFOLD_THREADS + 1];
 	const unsigned int nh = *d.hit_count;
 	ManifoldScratch sc;
-	__shared__ int s_cnt[RP_LVL_SMEM], s_base[RP_LVL_SMEM];
+	__shared__ int s_cnt[2 * RP_LVL_SMEM], s_base[2 * RP_LVL_SMEM];
 	int made = 0;
 	const int lane = threadIdx.x & 31;
 	for (unsigned int h0 = blockIdx.x * blockDim.x; h0 < nh; h0 += gridDim.x * blockDim.x) {
 		const unsigned int hi = h0 + threadIdx.x;
 		int n = 0, lvl = -1, w = 0, pair = 0;
 		if (hi < nh) {
-			const HitRec hr = d.hits[hi];
-			w = hr.world; pair = hr.pair;
-			const size_t pg = (size_t)w * d.max_pairs + hr.pair;
+			const EpaOut eo = d.epa_out[hi];
+			const uint2 cd = d.cands[d.hits[hi]];
+			w = (int)cd.x; pair = (int)cd.y;
+			const size_t pg = (size_t)w * d.max_pairs + pair;
 			const PairRec pr = d.pairs[pg];
-			const V3* tv = d.tv + (size_t)w * d.TV;
-			const V3* tn = d.tn + (size_t)w * d.TN;
-			Shape A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
-			Shape B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
-			if (A.type == SHAPE_HULL && B.type == SHAPE_HULL && (A.nv + B.nv + A.nf + B.nf) * 3 <= RP_MANIFOLD_STAGE) {
-				double* col = s_stage + threadIdx.x;
-				const int used = stage_shape(A, col, RP_MANIFOLD_THREADS, true);
-				stage_shape(B, col + (size_t)used * RP_MANIFOLD_THREADS, RP_MANIFOLD_THREADS, true);
-			}
-			V3 normal;
-			double depth;
 			int st = 0;
-			bool ok;
-			if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
-				ok = sphere_sphere(A, B, &normal, &depth);
-			} else {
-				Simplex s;
-				s.a = hr.sa; s.b = hr.sb; s.c = hr.sc; s.d = hr.sd;
-				s.num = 4;
-				ok = epa(A, B, s, sc.epa, &normal, &depth, &st, 0);
-			}
-			if (ok) {
+			if (eo.ok) {
+				const V3* tv = d.tv + (size_t)w * d.TV;
+				const V3* tn = d.tn + (size_t)w * d.TN;
+				Shape A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
+				Shape B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
 				StageSink sink;
-				sink.stage = sc.m.stage;
+				sink.stage = sc.stage;
 				sink.n = 0;
 				sink.cap = RP_CLIP_MAX_POINTS;
-				manifold(A, B, normal, depth, sc.m.clip, &st, sink);
+				manifold(A, B, eo.normal, eo.depth, sc.clip, &st, sink);
 				n = sink.n;
 				if (n > sink.cap) {
 					st |= ST_CLIP_CAPACITY;
@@ -566,13 +751,13 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 				b2.x = ld3(db.x); b2.q = ld4(db.q);
 				Contact* out = d.contacts + (size_t)w * d.max_contacts + off;
 				for (int k = 0; k < n; ++k) {
-					out[k] = make_contact(b1, b2, sc.m.stage[2 * k], sc.m.stage[2 * k + 1]);
+					out[k] = make_contact(b1, b2, sc.stage[2 * k], sc.stage[2 * k + 1]);
 					if (w == d.dbg_world) {
-						d.dbg_points[2 * (off + k)] = sc.m.stage[2 * k];
-						d.dbg_points[2 * (off + k) + 1] = sc.m.stage[2 * k + 1];
+						d.dbg_points[2 * (off + k)] = sc.stage[2 * k];
+						d.dbg_points[2 * (off + k) + 1] = sc.stage[2 * k + 1];
 					}
 				}
-				d.pair_normal[pg] = normal;
+				d.pair_normal[pg] = eo.normal;
 				d.pair_coff[pg] = off;
 				d.pair_ccnt[pg] = n;
 				made += n;
@@ -581,28 +766,31 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 			if (st) atomicOr(&d.status[w], st);
 		}
 		// append (world, pair) to the list of its level: ranks within the CTA through shared-memory counters, then ONE
-		// global atomic per (CTA, level) on a counter that owns its 128-byte line (RP_LVL_STRIDE)
+		// global atomic per (CTA, level, end) on a counter line of its own (RP_LVL_STRIDE). A level's list can be filled
+		// from both ends -- small manifolds (<= RP_SMALL_MANIFOLD contacts) from the front, large ones from the back --
+		// which groups manifolds of similar length (order within a level is free: its units commute).
 		__syncthreads();
-		if (threadIdx.x < RP_LVL_SMEM) s_cnt[threadIdx.x] = 0;  // RP_MANIFOLD_THREADS >= RP_LVL_SMEM
+		if (threadIdx.x < 2 * RP_LVL_SMEM) s_cnt[threadIdx.x] = 0;  // RP_MANIFOLD_THREADS >= 2 * RP_LVL_SMEM
 		__syncthreads();
 		int rank = 0;
+		const int big = n > RP_SMALL_MANIFOLD ? 1 : 0;
 		if (lvl > 0) {
-			if (lvl < RP_LVL_SMEM) rank = atomicAdd(&s_cnt[lvl], 1);
-			else rank = atomicAdd(&d.lvl_fill[(size_t)lvl * RP_LVL_STRIDE], 1);  // very deep schedules: direct
+			if (lvl < RP_LVL_SMEM) rank = atomicAdd(&s_cnt[2 * lvl + big], 1);
+			else rank = atomicAdd(&d.lvl_fill[(size_t)lvl * RP_LVL_STRIDE + big], 1);  // very deep schedules: direct
 		}
 		__syncthreads();
-		if (threadIdx.x < RP_LVL_SMEM && s_cnt[threadIdx.x] > 0) {
-			s_base[threadIdx.x] = atomicAdd(&d.lvl_fill[(size_t)threadIdx.x * RP_LVL_STRIDE], s_cnt[threadIdx.x]);
+		if (threadIdx.x < 2 * RP_LVL_SMEM && s_cnt[threadIdx.x] > 0) {
+			s_base[threadIdx.x] = atomicAdd(&d.lvl_fill[(size_t)(threadIdx.x >> 1) * RP_LVL_STRIDE + (threadIdx.x & 1)], s_cnt[threadIdx.x]);
 		}
 		__syncthreads();
 		if (lvl > 0) {
-			const int slot = (lvl < RP_LVL_SMEM ? s_base[lvl] : 0) + rank;
-			d.lvl_items[d.lvl_off[lvl] + slot] = make_uint2((unsigned int)w, (unsigned int)pair);
+			const int slot = (lvl < RP_LVL_SMEM ? s_base[2 * lvl + big] : 0) + rank;
+			const int at = big ? d.lvl_off[lvl + 1] - 1 - slot : d.lvl_off[lvl] + slot;
+			d.lvl_items[at] = make_uint2((unsigned int)w, (unsigned int)pair);
 		}
 	}
 	for (int o = 16; o > 0; o >>= 1) made += __shfl_down_sync(0xffffffffu, made, o);
 	if (lane == 0 && made) atomicAdd(&d.counters[CNT_CONTACTS], (unsigned long long)made);
-	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&d.counters[CNT_HITS], (unsigned long long)nh);
 }
 
 // -------------------------------------------------------------------------------------------------------------- solve
@@ -613,56 +801,82 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 __global__ void __launch_bounds__(128, RP_MINB_POS) k_pos_level(DevView d, double h, int level, int collisions) {
 	const int nj = level <= d.joint_levels ? d.joint_lptr[level] - d.joint_lptr[level - 1] : 0;
 	const int njw = nj * d.W;
-	const int np = collisions ? d.lvl_fill[(size_t)level * RP_LVL_STRIDE] : 0;
-	int st = 0, stw = 0;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < njw + np; i += gridDim.x * blockDim.x) {
-		if (i < njw) {
-			const int w = i / nj;
-			const int u = d.joint_sched[d.joint_lptr[level - 1] + i % nj];
-			const Joint j = d.joints[u];
-			BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
-			Body b1, b2;
-			load_static(b1, d.bstat[j.e1]);
-			load_static(b2, d.bstat[j.e2]);
-			BodyDyn& d1 = dyn[j.e1];
-			BodyDyn& d2 = dyn[j.e2];
-			b1.x = ld3(d1.x); b1.q = ld4(d1.q);
-			b2.x = ld3(d2.x); b2.q = ld4(d2.q);
-			JointLambda lam = d.lambdas[(size_t)w * d.NJ + u];
-			solve_joint(j, lam, b1, b2, h, &st);
-			d.lambdas[(size_t)w * d.NJ + u] = lam;
-			if (!b1.fixed) { st3(d1.x, b1.x); st4(d1.q, b1.q); }
-			if (!b2.fixed) { st3(d2.x, b2.x); st4(d2.q, b2.q); }
-			stw = w;
-		} else {
-			const uint2 item = d.lvl_items[d.lvl_off[level] + (i - njw)];
-			const int w = (int)item.x;
-			const size_t pg = (size_t)w * d.max_pairs + item.y;
-			const int cnt = d.pair_ccnt[pg];
-			const PairRec pr = d.pairs[pg];
-			const V3 normal = d.pair_normal[pg];
-			Contact* cs = d.contacts + (size_t)w * d.max_contacts + d.pair_coff[pg];
-			BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
-			Body b1, b2;
-			load_static(b1, d.bstat[pr.a]);
-			load_static(b2, d.bstat[pr.b]);
-			BodyDyn& d1 = dyn[pr.a];
-			BodyDyn& d2 = dyn[pr.b];
-			b1.x = ld3(d1.x); b1.q = ld4(d1.q); b1.px = ld3(d1.px); b1.pq = ld4(d1.pq);
-			b2.x = ld3(d2.x); b2.q = ld4(d2.q); b2.px = ld3(d2.px); b2.pq = ld4(d2.pq);
-			for (int c = 0; c < cnt; ++c) {
-				Contact ct = cs[c];
-				solve_contact(ct, normal, b1, b2, h, &st);
-				cs[c].lambda_n = ct.lambda_n;
-				cs[c].lambda_t = ct.lambda_t;
-			}
-			if (!b1.fixed) { st3(d1.x, b1.x); st4(d1.q, b1.q); }
-			if (!b2.fixed) { st3(d2.x, b2.x); st4(d2.q, b2.q); }
-			stw = w;
-		}
+	int st = 0;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < njw; i += gridDim.x * blockDim.x) {
+		const int w = i / nj;
+		const int u = d.joint_sched[d.joint_lptr[level - 1] + i % nj];
+		const Joint j = d.joints[u];
+		BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
+		Body b1, b2;
+		load_static(b1, d, j.e1);
+		load_static(b2, d, j.e2);
+		BodyDyn& d1 = dyn[j.e1];
+		BodyDyn& d2 = dyn[j.e2];
+		b1.x = ld3(d1.x); b1.q = ld4(d1.q);
+		b2.x = ld3(d2.x); b2.q = ld4(d2.q);
+		JointLambda lam = d.lambdas[(size_t)w * d.NJ + u];
+		solve_joint(j, lam, b1, b2, h, &st);
+		d.lambdas[(size_t)w * d.NJ + u] = lam;
+		if (!b1.fixed) { st3(d1.x, b1.x); st4(d1.q, b1.q); }
+		if (!b2.fixed) { st3(d2.x, b2.x); st4(d2.q, b2.q); }
 		if (st) {
-			atomicOr(&d.status[stw], st);
+			atomicOr(&d.status[w], st);
 			st = 0;
+		}
+	}
+	if (!collisions) return;
+	// contacts: refill loop, one trip = one contact of whatever manifold a lane holds (see WarpQueue)
+	const int npf = d.lvl_fill[(size_t)level * RP_LVL_STRIDE];
+	const int np = npf + d.lvl_fill[(size_t)level * RP_LVL_STRIDE + 1];
+	const int off0 = d.lvl_off[level], off1 = d.lvl_off[level + 1];
+	WarpQueue q;
+	q.init((unsigned int)np);
+	bool have = false;
+	int w = 0, cnt = 0, c = 0;
+	Contact* cs = 0;
+	BodyDyn* d1 = 0;
+	BodyDyn* d2 = 0;
+	V3 normal = v3(0.0, 0.0, 0.0);
+	Body b1, b2;
+	b1.fixed = b2.fixed = 1;
+	for (;;) {
+		const unsigned int got = q.take(!have);
+		if (got != 0xffffffffu) {
+			const int k = (int)got;
+			const uint2 item = d.lvl_items[k < npf ? off0 + k : off1 - 1 - (k - npf)];
+			w = (int)item.x;
+			const size_t pg = (size_t)w * d.max_pairs + item.y;
+			cnt = d.pair_ccnt[pg];
+			const PairRec pr = d.pairs[pg];
+			normal = d.pair_normal[pg];
+			cs = d.contacts + (size_t)w * d.max_contacts + d.pair_coff[pg];
+			load_static(b1, d, pr.a);
+			load_static(b2, d, pr.b);
+			d1 = d.dyn + (size_t)w * d.NB + pr.a;
+			d2 = d.dyn + (size_t)w * d.NB + pr.b;
+			b1.x = ld3(d1->x); b1.q = ld4(d1->q); b1.px = ld3(d1->px); b1.pq = ld4(d1->pq);
+			b2.x = ld3(d2->x); b2.q = ld4(d2->q); b2.px = ld3(d2->px); b2.pq = ld4(d2->pq);
+			c = 0;
+			have = cnt > 0;
+		}
+		if (!__any_sync(0xffffffffu, have)) {
+			if (q.empty()) break;
+			continue;
+		}
+		if (have) {
+			Contact ct = cs[c];
+			solve_contact(ct, normal, b1, b2, h, &st);
+			cs[c].lambda_n = ct.lambda_n;
+			cs[c].lambda_t = ct.lambda_t;
+			if (++c == cnt) {
+				if (!b1.fixed) { st3(d1->x, b1.x); st4(d1->q, b1.q); }
+				if (!b2.fixed) { st3(d2->x, b2.x); st4(d2->q, b2.q); }
+				if (st) {
+					atomicOr(&d.status[w], st);
+					st = 0;
+				}
+				have = false;
+			}
 		}
 	}
 }
@@ -686,29 +900,52 @@ __global__ void __launch_bounds__(128) k_derive(DevView d, double h) {
 // velocity pass over the contacts of one level (pbd.cpp:646-711); the hinge branch of the reference's velocity pass is
 // an empty TODO (pbd.cpp:712-739), so joints take no part
 __global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, double h, int level) {
-	const int np = d.lvl_fill[(size_t)level * RP_LVL_STRIDE];
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
-		const uint2 item = d.lvl_items[d.lvl_off[level] + i];
-		const int w = (int)item.x;
-		const size_t pg = (size_t)w * d.max_pairs + item.y;
-		const int cnt = d.pair_ccnt[pg];
-		const PairRec pr = d.pairs[pg];
-		const V3 normal = d.pair_normal[pg];
-		const Contact* cs = d.contacts + (size_t)w * d.max_contacts + d.pair_coff[pg];
-		BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
-		Body b1, b2;
-		load_static(b1, d.bstat[pr.a]);
-		load_static(b2, d.bstat[pr.b]);
-		BodyDyn& d1 = dyn[pr.a];
-		BodyDyn& d2 = dyn[pr.b];
-		b1.q = ld4(d1.q); b1.v = ld3(d1.v); b1.w = ld3(d1.w); b1.pv = ld3(d1.pv); b1.pw = ld3(d1.pw);
-		b2.q = ld4(d2.q); b2.v = ld3(d2.v); b2.w = ld3(d2.w); b2.pv = ld3(d2.pv); b2.pw = ld3(d2.pw);
-		for (int c = 0; c < cnt; ++c) {
+	const int npf = d.lvl_fill[(size_t)level * RP_LVL_STRIDE];
+	const int np = npf + d.lvl_fill[(size_t)level * RP_LVL_STRIDE + 1];
+	const int off0 = d.lvl_off[level], off1 = d.lvl_off[level + 1];
+	WarpQueue q;
+	q.init((unsigned int)np);
+	bool have = false;
+	int cnt = 0, c = 0;
+	const Contact* cs = 0;
+	BodyDyn* d1 = 0;
+	BodyDyn* d2 = 0;
+	V3 normal = v3(0.0, 0.0, 0.0);
+	Body b1, b2;
+	b1.fixed = b2.fixed = 1;
+	for (;;) {
+		const unsigned int got = q.take(!have);
+		if (got != 0xffffffffu) {
+			const int k = (int)got;
+			const uint2 item = d.lvl_items[k < npf ? off0 + k : off1 - 1 - (k - npf)];
+			const int w = (int)item.x;
+			const size_t pg = (size_t)w * d.max_pairs + item.y;
+			cnt = d.pair_ccnt[pg];
+			const PairRec pr = d.pairs[pg];
+			normal = d.pair_normal[pg];
+			cs = d.contacts + (size_t)w * d.max_contacts + d.pair_coff[pg];
+			load_static(b1, d, pr.a);
+			load_static(b2, d, pr.b);
+			d1 = d.dyn + (size_t)w * d.NB + pr.a;
+			d2 = d.dyn + (size_t)w * d.NB + pr.b;
+			b1.q = ld4(d1->q); b1.v = ld3(d1->v); b1.w = ld3(d1->w); b1.pv = ld3(d1->pv); b1.pw = ld3(d1->pw);
+			b2.q = ld4(d2->q); b2.v = ld3(d2->v); b2.w = ld3(d2->w); b2.pv = ld3(d2->pv); b2.pw = ld3(d2->pw);
+			c = 0;
+			have = cnt > 0;
+		}
+		if (!__any_sync(0xffffffffu, have)) {
+			if (q.empty()) break;
+			continue;
+		}
+		if (have) {
 			const Contact ct = cs[c];
 			solve_contact_velocity(ct, normal, b1, b2, h);
+			if (++c == cnt) {
+				if (!b1.fixed) { st3(d1->v, b1.v); st3(d1->w, b1.w); }
+				if (!b2.fixed) { st3(d2->v, b2.v); st3(d2->w, b2.w); }
+				have = false;
+			}
 		}
-		if (!b1.fixed) { st3(d1.v, b1.v); st3(d1.w, b1.w); }
-		if (!b2.fixed) { st3(d2.v, b2.v); st3(d2.w, b2.w); }
 	}
 }
 

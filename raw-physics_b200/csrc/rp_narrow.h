@@ -149,37 +149,48 @@ RP_HD bool gjk_do_simplex(Simplex* s, V3* dir) {
 	return false;
 }
 
-// gjk_collides (gjk.cpp:350-379). `iters` (optional) receives the number of support iterations, for statistics.
+// gjk_collides (gjk.cpp:350-379), cut into its loop-carried pieces so that a GPU lane can interleave the iterations of
+// successive pairs (k_gjk refills a lane the moment its pair is decided): gjk_begin is the code before the loop,
+// gjk_step one trip of it.
+enum { GJK_CONTINUE = 0, GJK_HIT = 1, GJK_MISS = 2 };
+
+RP_HD void gjk_begin(const Shape& A, const Shape& B, Simplex* s, V3* dir) {
+	s->a = support_minkowski(A, B, v3(0.0, 0.0, 1.0));
+	s->b = s->c = s->d = v3(0.0, 0.0, 0.0);
+	s->num = 1;
+	*dir = scale(-1.0, s->a);
+}
+
+RP_HD int gjk_step(const Shape& A, const Shape& B, Simplex* s, V3* dir, int* status) {
+	V3 p = support_minkowski(A, B, *dir);
+	if (dot(p, *dir) < 0.0) return GJK_MISS;
+	// add_to_simplex (gjk.cpp:7-30)
+	if (s->num == 1) {
+		s->b = s->a;
+	} else if (s->num == 2) {
+		s->c = s->b; s->b = s->a;
+	} else if (s->num == 3) {
+		s->d = s->c; s->c = s->b; s->b = s->a;
+	} else {
+		*status |= ST_GJK_SIMPLEX_OVERFLOW;  // the reference aborts here
+		return GJK_MISS;
+	}
+	s->a = p;
+	++s->num;
+	return gjk_do_simplex(s, dir) ? GJK_HIT : GJK_CONTINUE;
+}
+
+// `iters` (optional) receives the number of support iterations, for statistics.
 RP_HD bool gjk(const Shape& A, const Shape& B, Simplex* out, int* status, int* iters) {
 	Simplex s;
-	s.a = support_minkowski(A, B, v3(0.0, 0.0, 1.0));
-	s.b = s.c = s.d = v3(0.0, 0.0, 0.0);
-	s.num = 1;
-	V3 dir = scale(-1.0, s.a);
+	V3 dir;
+	gjk_begin(A, B, &s, &dir);
 	for (int i = 0; i < RP_GJK_MAX_ITERS; ++i) {
-		V3 p = support_minkowski(A, B, dir);
-		if (dot(p, dir) < 0.0) {
+		const int r = gjk_step(A, B, &s, &dir, status);
+		if (r != GJK_CONTINUE) {
 			if (iters) *iters = i + 1;
-			return false;
-		}
-		// add_to_simplex (gjk.cpp:7-30)
-		if (s.num == 1) {
-			s.b = s.a;
-		} else if (s.num == 2) {
-			s.c = s.b; s.b = s.a;
-		} else if (s.num == 3) {
-			s.d = s.c; s.c = s.b; s.b = s.a;
-		} else {
-			*status |= ST_GJK_SIMPLEX_OVERFLOW;  // the reference aborts here
-			if (iters) *iters = i + 1;
-			return false;
-		}
-		s.a = p;
-		++s.num;
-		if (gjk_do_simplex(&s, &dir)) {
-			*out = s;
-			if (iters) *iters = i + 1;
-			return true;
+			if (r == GJK_HIT) *out = s;
+			return r == GJK_HIT;
 		}
 	}
 	if (iters) *iters = RP_GJK_MAX_ITERS;
@@ -195,6 +206,8 @@ struct EpaScratch {
 	uint8_t faces[RP_EPA_MAX_FACES][3];
 	uint8_t edges[RP_EPA_MAX_EDGES][2];
 	int nverts, nfaces, nedges;
+	V3 min_normal;   // closest face so far (first strictly smaller distance wins, epa.cpp:141-144,:222-228)
+	double min_dist;
 };
 
 // get_face_normal_and_distance_to_origin (epa.cpp:32-77)
@@ -247,84 +260,101 @@ RP_HD bool epa_toggle_edge(EpaScratch& e, int x, int y) {
 	return true;
 }
 
-// epa (epa.cpp:118-238)
-RP_HD bool epa(const Shape& A, const Shape& B, const Simplex& s, EpaScratch& e, V3* normal_out, double* depth_out, int* status,
-	int* iters) {
+// epa (epa.cpp:118-238), cut into its loop-carried pieces like gjk above: epa_begin is the code before the loop
+// (polytope from the GJK tetrahedron, epa.cpp:8-30,:122-146), epa_step one trip of it. The running minimum lives in
+// the scratch record.
+enum { EPA_CONTINUE = 0, EPA_DONE = 1, EPA_FAIL = 2 };
+
+RP_HD int epa_begin(const Simplex& s, EpaScratch& e, int* status) {
 	e.verts[0] = s.a; e.verts[1] = s.b; e.verts[2] = s.c; e.verts[3] = s.d;
 	e.nverts = 4;
 	const uint8_t init_faces[4][3] = {{0, 1, 2}, {0, 2, 3}, {0, 3, 1}, {1, 2, 3}};
 	e.nfaces = 0;
 	e.nedges = 0;
-	V3 min_normal = v3(0.0, 0.0, 0.0);
-	double min_dist = 1.7976931348623157e308;
+	e.min_normal = v3(0.0, 0.0, 0.0);
+	e.min_dist = 1.7976931348623157e308;
 	for (int i = 0; i < 4; ++i) {
 		V3 n; double d;
 		if (!epa_face_plane(e, init_faces[i][0], init_faces[i][1], init_faces[i][2], &n, &d)) {
 			*status |= ST_EPA_DEGENERATE;
-			return false;
+			return EPA_FAIL;
 		}
 		e.faces[i][0] = init_faces[i][0]; e.faces[i][1] = init_faces[i][1]; e.faces[i][2] = init_faces[i][2];
 		e.normals[i] = n;
 		e.dists[i] = d;
 		e.nfaces = i + 1;
-		if (d < min_dist) {
-			min_dist = d;
-			min_normal = n;
+		if (d < e.min_dist) {
+			e.min_dist = d;
+			e.min_normal = n;
 		}
 	}
+	return EPA_CONTINUE;
+}
+
+RP_HD int epa_step(const Shape& A, const Shape& B, EpaScratch& e, int* status) {
+	const V3 min_normal = e.min_normal;
+	V3 sp = support_minkowski(A, B, min_normal);
+	double d = dot(min_normal, sp);
+	if (fabs(d - e.min_dist) < 0.0001) return EPA_DONE;  // result: e.min_normal, e.min_dist
+	int new_index = e.nverts;
+	e.verts[e.nverts++] = sp;  // capacity: 4 + RP_EPA_MAX_ITERS
+
+	// faces that see the new point are removed (swap-with-last while scanning, quirk q7), their edges toggled
+	int i = 0;
+	while (i < e.nfaces) {
+		int fx = e.faces[i][0], fy = e.faces[i][1], fz = e.faces[i][2];
+		V3 centroid = scale(1.0 / 3.0, add(add(e.verts[fy], e.verts[fz]), e.verts[fx]));  // triangle_centroid (epa.cpp:112)
+		if (dot(e.normals[i], sub(sp, centroid)) > 0.0) {
+			if (!epa_toggle_edge(e, fx, fy) || !epa_toggle_edge(e, fy, fz) || !epa_toggle_edge(e, fz, fx)) {
+				*status |= ST_EPA_CAPACITY;
+				return EPA_FAIL;
+			}
+			int last = --e.nfaces;
+			e.faces[i][0] = e.faces[last][0]; e.faces[i][1] = e.faces[last][1]; e.faces[i][2] = e.faces[last][2];
+			e.dists[i] = e.dists[last];
+			e.normals[i] = e.normals[last];
+		} else {
+			++i;
+		}
+	}
+	for (int k = 0; k < e.nedges; ++k) {
+		if (e.nfaces >= RP_EPA_MAX_FACES) {
+			*status |= ST_EPA_CAPACITY;
+			return EPA_FAIL;
+		}
+		V3 n; double dd;
+		if (!epa_face_plane(e, e.edges[k][0], e.edges[k][1], new_index, &n, &dd)) {
+			*status |= ST_EPA_DEGENERATE;
+			return EPA_FAIL;
+		}
+		int f = e.nfaces++;
+		e.faces[f][0] = e.edges[k][0]; e.faces[f][1] = e.edges[k][1]; e.faces[f][2] = (uint8_t)new_index;
+		e.normals[f] = n;
+		e.dists[f] = dd;
+	}
+	e.min_dist = 1.7976931348623157e308;
+	for (int k = 0; k < e.nfaces; ++k) {
+		if (e.dists[k] < e.min_dist) {
+			e.min_dist = e.dists[k];
+			e.min_normal = e.normals[k];
+		}
+	}
+	e.nedges = 0;
+	return EPA_CONTINUE;
+}
+
+RP_HD bool epa(const Shape& A, const Shape& B, const Simplex& s, EpaScratch& e, V3* normal_out, double* depth_out, int* status,
+	int* iters) {
+	if (epa_begin(s, e, status) == EPA_FAIL) return false;
 	for (int it = 0; it < RP_EPA_MAX_ITERS; ++it) {
-		V3 sp = support_minkowski(A, B, min_normal);
-		double d = dot(min_normal, sp);
-		if (fabs(d - min_dist) < 0.0001) {
-			*normal_out = min_normal;
-			*depth_out = min_dist;
+		const int r = epa_step(A, B, e, status);
+		if (r == EPA_DONE) {
+			*normal_out = e.min_normal;
+			*depth_out = e.min_dist;
 			if (iters) *iters = it + 1;
 			return true;
 		}
-		int new_index = e.nverts;
-		e.verts[e.nverts++] = sp;  // capacity: 4 + RP_EPA_MAX_ITERS
-
-		// faces that see the new point are removed (swap-with-last while scanning, quirk q7), their edges toggled
-		int i = 0;
-		while (i < e.nfaces) {
-			int fx = e.faces[i][0], fy = e.faces[i][1], fz = e.faces[i][2];
-			V3 centroid = scale(1.0 / 3.0, add(add(e.verts[fy], e.verts[fz]), e.verts[fx]));  // triangle_centroid (epa.cpp:112)
-			if (dot(e.normals[i], sub(sp, centroid)) > 0.0) {
-				if (!epa_toggle_edge(e, fx, fy) || !epa_toggle_edge(e, fy, fz) || !epa_toggle_edge(e, fz, fx)) {
-					*status |= ST_EPA_CAPACITY;
-					return false;
-				}
-				int last = --e.nfaces;
-				e.faces[i][0] = e.faces[last][0]; e.faces[i][1] = e.faces[last][1]; e.faces[i][2] = e.faces[last][2];
-				e.dists[i] = e.dists[last];
-				e.normals[i] = e.normals[last];
-			} else {
-				++i;
-			}
-		}
-		for (int k = 0; k < e.nedges; ++k) {
-			if (e.nfaces >= RP_EPA_MAX_FACES) {
-				*status |= ST_EPA_CAPACITY;
-				return false;
-			}
-			V3 n; double dd;
-			if (!epa_face_plane(e, e.edges[k][0], e.edges[k][1], new_index, &n, &dd)) {
-				*status |= ST_EPA_DEGENERATE;
-				return false;
-			}
-			int f = e.nfaces++;
-			e.faces[f][0] = e.edges[k][0]; e.faces[f][1] = e.edges[k][1]; e.faces[f][2] = (uint8_t)new_index;
-			e.normals[f] = n;
-			e.dists[f] = dd;
-		}
-		min_dist = 1.7976931348623157e308;
-		for (int k = 0; k < e.nfaces; ++k) {
-			if (e.dists[k] < min_dist) {
-				min_dist = e.dists[k];
-				min_normal = e.normals[k];
-			}
-		}
-		e.nedges = 0;
+		if (r == EPA_FAIL) return false;
 	}
 	*status |= ST_EPA_NO_CONVERGENCE;
 	if (iters) *iters = RP_EPA_MAX_ITERS;

@@ -62,14 +62,33 @@ struct PosPre {  // Position_Constraint_Preprocessed_Data (pbd_base_constraints.
 	M3 ii1, ii2;
 };
 
+// A fixed body (entity_create_fixed, entity.cpp:24-65 with mass -> inverse_mass 0 and zero tensors; Scene::add_body)
+// has inverse mass +0 and an all +0 inverse inertia tensor. For such a body R * 0 * R^T is a matrix of signed zeros,
+// every product with it is a signed zero, and its generalised inverse mass 0 + (+-0) is +0 exactly -- so the tensor
+// and the w term are not evaluated at all; a fixed body is never written (pbd_base_constraints.cpp:73-103), so its
+// tensor has no other use. The CPU restatement runs this same code against the compiled reference.
+RP_HD M3 zero_m3() {
+	M3 z;
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+#pragma unroll
+		for (int j = 0; j < 3; ++j) z.m[i][j] = 0.0;
+	}
+	return z;
+}
 // calculate_positional_constraint_preprocessed_data (pbd_base_constraints.cpp:6-15)
 RP_HD PosPre pos_pre(const Body& b1, const Body& b2, V3 r1_lc, V3 r2_lc) {
 	PosPre p;
 	p.r1 = rotate(b1.q, r1_lc);
 	p.r2 = rotate(b2.q, r2_lc);
-	p.ii1 = world_tensor(b1.q, b1.inv_inertia);
-	p.ii2 = world_tensor(b2.q, b2.inv_inertia);
+	p.ii1 = b1.fixed ? zero_m3() : world_tensor(b1.q, b1.inv_inertia);
+	p.ii2 = b2.fixed ? zero_m3() : world_tensor(b2.q, b2.inv_inertia);
 	return p;
+}
+// generalised inverse mass of one body along n at arm r (pbd_base_constraints.cpp:38-39, pbd.cpp:697-698)
+RP_HD double inv_mass_along(const Body& b, V3 r, const M3& ii, V3 n) {
+	if (b.fixed) return 0.0;
+	return b.inv_mass + dot(cross(r, n), mul(ii, cross(r, n)));
 }
 
 // positional_constraint_get_delta_lambda (pbd_base_constraints.cpp:17-47)
@@ -78,8 +97,8 @@ RP_HD double pos_delta_lambda(const PosPre& p, const Body& b1, const Body& b2, d
 	double c = length(dx);
 	if (c <= 1e-50) return 0.0;
 	V3 n = divide(dx, c);
-	double w1 = b1.inv_mass + dot(cross(p.r1, n), mul(p.ii1, cross(p.r1, n)));
-	double w2 = b2.inv_mass + dot(cross(p.r2, n), mul(p.ii2, cross(p.r2, n)));
+	double w1 = inv_mass_along(b1, p.r1, p.ii1, n);
+	double w2 = inv_mass_along(b2, p.r2, p.ii2, n);
 	if (!(w1 + w2 != 0.0)) *status |= ST_SOLVER_SINGULAR;  // the reference asserts
 	double til = compliance / (h * h);
 	return (-c - til * lambda) / (w1 + w2 + til);
@@ -104,10 +123,8 @@ RP_HD void pos_apply(const PosPre& p, Body& b1, Body& b2, double dl, V3 dx) {
 	V3 imp = scale(dl, n);
 	if (!b1.fixed) b1.x = add(b1.x, scale(b1.inv_mass, imp));
 	if (!b2.fixed) b2.x = add(b2.x, scale(-b2.inv_mass, imp));
-	V3 aux1 = mul(p.ii1, cross(p.r1, imp));
-	V3 aux2 = mul(p.ii2, cross(p.r2, imp));
-	if (!b1.fixed) apply_rotation(b1, aux1, 1.0);
-	if (!b2.fixed) apply_rotation(b2, aux2, -1.0);
+	if (!b1.fixed) apply_rotation(b1, mul(p.ii1, cross(p.r1, imp)), 1.0);
+	if (!b2.fixed) apply_rotation(b2, mul(p.ii2, cross(p.r2, imp)), -1.0);
 }
 
 // ------------------------------------------------------------------------------------------------- angular primitive
@@ -117,8 +134,8 @@ struct AngPre {
 // calculate_angular_constraint_preprocessed_data (pbd_base_constraints.cpp:125-131)
 RP_HD AngPre ang_pre(const Body& b1, const Body& b2) {
 	AngPre a;
-	a.ii1 = world_tensor(b1.q, b1.inv_inertia);
-	a.ii2 = world_tensor(b2.q, b2.inv_inertia);
+	a.ii1 = b1.fixed ? zero_m3() : world_tensor(b1.q, b1.inv_inertia);
+	a.ii2 = b2.fixed ? zero_m3() : world_tensor(b2.q, b2.inv_inertia);
 	return a;
 }
 // angular_constraint_get_delta_lambda (pbd_base_constraints.cpp:133-161)
@@ -126,6 +143,7 @@ RP_HD double ang_delta_lambda(const AngPre& a, double h, double compliance, doub
 	double theta = length(dq);
 	if (theta <= 1e-50) return 0.0;
 	V3 n = divide(dq, theta);
+	// a fixed body's term n . (0 n) is a signed zero; w1 + w2 is then the other body's term (or +-0, flagged below)
 	double w1 = dot(n, mul(a.ii1, n));
 	double w2 = dot(n, mul(a.ii2, n));
 	if (!(w1 + w2 != 0.0)) *status |= ST_SOLVER_SINGULAR;
@@ -138,10 +156,8 @@ RP_HD void ang_apply(const AngPre& a, Body& b1, Body& b2, double dl, V3 dq) {
 	if (theta <= 1e-50) return;
 	V3 n = divide(dq, theta);
 	V3 imp = scale(-dl, n);
-	V3 aux1 = mul(a.ii1, imp);
-	V3 aux2 = mul(a.ii2, imp);
-	if (!b1.fixed) apply_rotation(b1, aux1, 1.0);
-	if (!b2.fixed) apply_rotation(b2, aux2, -1.0);
+	if (!b1.fixed) apply_rotation(b1, mul(a.ii1, imp), 1.0);
+	if (!b2.fixed) apply_rotation(b2, mul(a.ii2, imp), -1.0);
 }
 
 // ------------------------------------------------------------------------------------------------------ contact solve
@@ -206,8 +222,8 @@ RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, do
 	double e = b1.rest * b2.rest;
 	fact = -vn + RP_MINF(-e * vn_til, 0.0);
 	dv = add(dv, scale(fact, n));
-	double w1 = b1.inv_mass + dot(cross(p.r1, n), mul(p.ii1, cross(p.r1, n)));
-	double w2 = b2.inv_mass + dot(cross(p.r2, n), mul(p.ii2, cross(p.r2, n)));
+	double w1 = inv_mass_along(b1, p.r1, p.ii1, n);
+	double w2 = inv_mass_along(b2, p.r2, p.ii2, n);
 	V3 imp = scale(1.0 / (w1 + w2), dv);
 	if (!b1.fixed) {
 		b1.v = add(b1.v, scale(b1.inv_mass, imp));
