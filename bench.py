@@ -48,6 +48,12 @@ def parse():
     ap.add_argument("--no-cull", action="store_true", help="run GJK on every broadphase pair (disables the exact-safe bounds cull)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / profile / cpu baseline (kernel timing only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (tuning runs)")
+    ap.add_argument("--hetero", action="store_true",
+                    help="also time the same window with every world started from a DIFFERENT pose set (random yaw and lateral "
+                         "offset per cube): reported next to the headline as `heterogeneous`")
+    ap.add_argument("--ncu-frame", type=int, default=-1,
+                    help="profiling aid: run this many frames, then bracket ONE more frame with cudaProfilerStart/Stop and exit "
+                         "(use with ncu --profile-from-start off); prints nothing")
     return ap.parse_args()
 
 
@@ -208,6 +214,16 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if args.ncu_frame >= 0:
+        batch.run(max(args.ncu_frame, 1), DT, SUBSTEPS, ITERS, True)
+        barrier()
+        torch.cuda.profiler.start()
+        batch.run(1, DT, SUBSTEPS, ITERS, True)
+        barrier()
+        torch.cuda.profiler.stop()
+        batch.close()
+        return
+
     # ---- device-resident throughput
     for _ in range(args.warmup):
         batch.step(DT, SUBSTEPS, ITERS, True)
@@ -222,11 +238,11 @@ def run_ours(args):
     units = NB * W * SUBSTEPS * args.steps * world_size
     value = units / (ms * 1e-3)
     status = batch.status()
-    # kernels launched in the timed region: per frame 7 prologue kernels + per substep reset, integrate, cull, gjk, hits,
-    # epa, manifold, derive and one positional + one velocity launch per dependency level, + the frame counter
+    # kernels launched in the timed region: per frame 7 prologue kernels + per substep reset, integrate, cull, gjk,
+    # epa, manifold and one positional + one velocity launch per dependency level, + the end-of-frame derive and frame counter
     c_levels = batch.counters()
     depth = int(round(c_levels["levels"] / max(1, c_levels["frames"]) / W)) if c_levels["frames"] else 0
-    launches_total = args.steps * (7 + SUBSTEPS * (8 + depth * (ITERS + 1)) + 1)
+    launches_total = args.steps * (7 + SUBSTEPS * (6 + depth * (ITERS + 1)) + 2)
 
     line = {"metric": "body-substeps/sec", "value": value, "unit": "body-substeps/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -296,6 +312,30 @@ def run_ours(args):
             t = torch.tensor([float(tests), float(hits), float(contacts)], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             line["aggregate_work"] = {"pair_tests": t[0].item(), "epa_runs": t[1].item(), "contacts": t[2].item()}
+        if args.hetero:
+            # The headline workload is BASELINE.json's: 4096 COPIES of one scene, so the lanes of a warp (same pair index,
+            # neighbouring worlds) follow the same control flow. This leg breaks that: each cube of each world gets its own
+            # yaw in +-0.3 rad and a lateral offset in +-0.2, so contacts form at different times and with different
+            # manifolds in every world. Same kernels, same window.
+            rng = np.random.default_rng(1234 + rank)
+            st = np.ascontiguousarray(np.broadcast_to(init[None], (W, NB, pkg.STATE_STRIDE))).copy()
+            yaw = rng.uniform(-0.3, 0.3, size=(W, NB - 1))
+            st[:, 1:, 0] += rng.uniform(-0.2, 0.2, size=(W, NB - 1))
+            st[:, 1:, 2] += rng.uniform(-0.2, 0.2, size=(W, NB - 1))
+            st[:, 1:, 3] = 0.0
+            st[:, 1:, 4] = np.sin(0.5 * yaw)
+            st[:, 1:, 5] = 0.0
+            st[:, 1:, 6] = np.cos(0.5 * yaw)
+            batch.upload(st)
+            barrier()
+            c0 = batch.counters()
+            hms = max_over_ranks(batch.run(args.steps, DT, SUBSTEPS, ITERS, True))
+            barrier()
+            c1 = batch.counters()
+            line["heterogeneous"] = {"value": units / (hms * 1e-3), "unit": "body-substeps/s", "ms_per_step": hms / args.steps,
+                                     "status_bits": int(np.bitwise_or.reduce(batch.status())),
+                                     "contacts_per_world_substep": (c1["contacts"] - c0["contacts"]) / (W * SUBSTEPS * args.steps),
+                                     "note": "every world started from its own poses (per-cube yaw +-0.3 rad, offset +-0.2): no cross-world coherence"}
         if rank == 0 and world_size == 1 and not args.no_cpu:
             import refdrv
             line["cpu_baseline"] = cpu_single_thread_baseline("strict" if refdrv.available("strict") else "port")

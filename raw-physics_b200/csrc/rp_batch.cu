@@ -285,6 +285,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	DevView& d = b->d;
 	memset(&d, 0, sizeof(d));
 	d.W = (int)n_worlds;
+	d.WS = (d.W + 31) / 32 * 32;
 	d.NB = (int)s.bodies.size();
 	d.NC = (int)s.colliders.size();
 	d.NJ = (int)s.joints.size();
@@ -310,8 +311,10 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	d.max_units = d.NJ + d.max_pairs;
 	b->cull = cfg.disable_cull ? 0 : 1;
 	{
-		int want = (b->sm_count * 8 + d.W - 1) / d.W;
-		int most = (d.max_pairs + 255) / 256;
+		// k_cull: grid.y = groups of 32 worlds (lane = world), a CTA's 8 warps take 8 pair indices per trip
+		const int groups = (d.W + 31) / 32;
+		int want = (b->sm_count * 16 + groups - 1) / groups;
+		int most = (d.max_pairs + 7) / 8;
 		b->cull_chunks = std::max(1, std::min(want, most));
 	}
 	RP_CUDA(cudaHostAlloc((void**)&b->levels_host, sizeof(int), cudaHostAllocDefault));
@@ -401,25 +404,26 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	d.force = b->force_dev;
 	d.torque = b->torque_dev;
 
-	// per world
-	const size_t W = (size_t)d.W, WB = W * d.NB, WP = W * d.max_pairs;
-	if ((rc = dev_alloc(b, &d.dyn, WB))) return rc;
-	if ((rc = dev_alloc(b, &d.active, WB))) return rc;
-	if ((rc = dev_alloc(b, &d.deact, WB))) return rc;
-	if ((rc = dev_alloc(b, &d.tv, W * std::max(d.TV, 1)))) return rc;
-	if ((rc = dev_alloc(b, &d.tn, W * std::max(d.TN, 1)))) return rc;
-	if ((rc = dev_alloc(b, &d.pairs, WP))) return rc;
+	// per world (world-minor arrays are padded to WS worlds)
+	const size_t W = (size_t)d.W, WS = (size_t)d.WS, WB = W * d.NB, SB = WS * d.NB, WP = W * d.max_pairs, SP = WS * d.max_pairs;
+	if ((rc = dev_alloc(b, &d.dyn, SB * RP_DYN_DOUBLES))) return rc;
+	if ((rc = dev_alloc(b, &d.active, SB))) return rc;
+	if ((rc = dev_alloc(b, &d.vstamp, SB))) return rc;
+	if ((rc = dev_alloc(b, &d.epoch, 1))) return rc;
+	if ((rc = dev_alloc(b, &d.deact, SB))) return rc;
+	if ((rc = dev_alloc(b, &d.tv, WS * std::max(d.TV, 1) * 3))) return rc;
+	if ((rc = dev_alloc(b, &d.tn, WS * std::max(d.TN, 1) * 3))) return rc;
+	if ((rc = dev_alloc(b, &d.pairs, SP))) return rc;
 	if ((rc = dev_alloc(b, &d.n_pairs, W))) return rc;
 	if ((rc = dev_alloc(b, &d.row_off, WB))) return rc;
 	if ((rc = dev_alloc(b, &d.label, WB))) return rc;
 	if ((rc = dev_alloc(b, &d.isl_flag, WB))) return rc;
-	if ((rc = dev_alloc(b, &d.last_level, WB))) return rc;
-	if ((rc = dev_alloc(b, &d.pair_level, WP))) return rc;
-	if ((rc = dev_alloc(b, &d.lvl_hist, W * (d.max_levels + 2)))) return rc;
-	if ((rc = dev_alloc(b, &d.aabb, W * std::max(d.NC, 1) * 6))) return rc;
+	if ((rc = dev_alloc(b, &d.last_level, SB))) return rc;
+	if ((rc = dev_alloc(b, &d.pair_level, SP))) return rc;
+	if ((rc = dev_alloc(b, &d.lvl_hist, WS * (d.max_levels + 2)))) return rc;
+	if ((rc = dev_alloc(b, &d.aabb, WS * std::max(d.NC, 1) * 6))) return rc;
 	if ((rc = dev_alloc(b, &d.cands, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.cand_count, 1))) return rc;
-	if ((rc = dev_alloc(b, &d.verdict, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.simplex, WP * 4, false))) return rc;
 	if ((rc = dev_alloc(b, &d.hits, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.hit_count, 1))) return rc;
@@ -429,12 +433,12 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.lvl_fill, ((size_t)d.max_levels + 2) * RP_LVL_STRIDE))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_max, 1))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_items, WP, false))) return rc;
-	if ((rc = dev_alloc(b, &d.pair_normal, WP, false))) return rc;
-	if ((rc = dev_alloc(b, &d.pair_coff, WP))) return rc;
-	if ((rc = dev_alloc(b, &d.pair_ccnt, WP))) return rc;
+	if ((rc = dev_alloc(b, &d.pair_normal, SP, false))) return rc;
+	if ((rc = dev_alloc(b, &d.pair_coff, SP))) return rc;
+	if ((rc = dev_alloc(b, &d.pair_ccnt, SP))) return rc;
 	if ((rc = dev_alloc(b, &d.contacts, W * d.max_contacts, false))) return rc;
 	if ((rc = dev_alloc(b, &d.n_contacts, W))) return rc;
-	if ((rc = dev_alloc(b, &d.lambdas, W * std::max(d.NJ, 1)))) return rc;
+	if ((rc = dev_alloc(b, &d.lambdas, WS * std::max(d.NJ, 1)))) return rc;
 	if ((rc = dev_alloc(b, &d.status, W))) return rc;
 	if ((rc = dev_alloc(b, &d.counters, 8))) return rc;
 	if ((rc = dev_alloc(b, &d.dbg_points, 2 * (size_t)d.max_contacts, false))) return rc;
@@ -442,8 +446,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 
 	std::vector<double> rec = initial_records(s);
 	RP_CUDA(cudaMemcpyAsync(b->rec_dev, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
-	const unsigned int blocks = (unsigned int)((WB + 127) / 128);
-	k_unpack_state<<<blocks, 128, 0, b->stream>>>(d, b->rec_dev, 0, d.W, 1);
+	k_unpack_state<<<dim3(d.NB, (d.W + 127) / 128), 128, 0, b->stream>>>(d, b->rec_dev, 0, d.W, 1);
 	RP_CUDA(cudaGetLastError());
 	RP_CUDA(cudaStreamSynchronize(b->stream));
 	return RP_OK;
@@ -495,13 +498,18 @@ static int flush_forces(rp_batch* b) {
 	return RP_OK;
 }
 
+static void launch_broad(rp_batch* b) {
+	const DevView& d = b->d;
+	const dim3 rows((d.NB + 7) / 8, d.WS / 32), blk(32, 8);
+	k_broad_rows<false><<<rows, blk, 0, b->stream>>>(d);
+	k_broad_scan<<<d.W, 256, 0, b->stream>>>(d);
+	k_broad_rows<true><<<rows, blk, 0, b->stream>>>(d);
+}
+
 // the per-frame prologue: broadphase, islands + sleeping, dependency-level schedule (pbd.cpp:474-533)
 static void enqueue_prologue(rp_batch* b, double dt, int collisions) {
 	const DevView& d = b->d;
-	dim3 rows((d.NB + 127) / 128, d.W);
-	k_broad_rows<false><<<rows, 128, 0, b->stream>>>(d);
-	k_broad_scan<<<d.W, 256, 0, b->stream>>>(d);
-	k_broad_rows<true><<<rows, 128, 0, b->stream>>>(d);
+	launch_broad(b);
 	k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
 	k_level_reset<<<1, 256, 0, b->stream>>>(d);
 	k_schedule<<<(d.W + 63) / 64, 64, 0, b->stream>>>(d, collisions);
@@ -527,18 +535,15 @@ static unsigned int vel_grid(const rp_batch* b) { return (unsigned int)b->sm_cou
 static void enqueue_integrate(rp_batch* b, double h) {
 	const DevView& d = b->d;
 	k_substep_reset<<<(unsigned int)((std::max(d.W, d.max_levels + 2) + 255) / 256), 256, 0, b->stream>>>(d);
-	k_integrate<<<(unsigned int)(((size_t)d.W * d.NB + RP_INT_THREADS - 1) / RP_INT_THREADS), RP_INT_THREADS, 0, b->stream>>>(d, h);
+	k_integrate<<<dim3(d.NB, (d.W + RP_INT_THREADS - 1) / RP_INT_THREADS), RP_INT_THREADS, 0, b->stream>>>(d, h);
 }
 // grid of the per-hit kernel: the hit count lives on the device, so the launch covers the candidate capacity in
 // grid-stride trips of at most this many CTAs
 static unsigned int manifold_grid(const rp_batch* b) { return (unsigned int)b->sm_count * 16u; }
-static void launch_cull(rp_batch* b) { k_cull<<<dim3(b->cull_chunks, b->d.W), 256, 0, b->stream>>>(b->d, b->cull); }
-static void launch_gjk(rp_batch* b) {
-	k_gjk<<<b->sm_count * RP_MINB_GJK, RP_GJK_THREADS, 0, b->stream>>>(b->d);
-	k_hits<<<b->sm_count * 8, 256, 0, b->stream>>>(b->d);
-}
+static void launch_cull(rp_batch* b) { k_cull<<<dim3(b->cull_chunks, (b->d.W + 31) / 32), 256, 0, b->stream>>>(b->d, b->cull); }
+static void launch_gjk(rp_batch* b) { k_gjk<<<b->sm_count * 16, RP_GJK_THREADS, 0, b->stream>>>(b->d); }
 static void launch_manifold(rp_batch* b) {
-	k_epa<<<b->sm_count * RP_MINB_EPA, RP_EPA_THREADS, 0, b->stream>>>(b->d);
+	k_epa<<<b->sm_count * 16, RP_EPA_THREADS, 0, b->stream>>>(b->d);
 	k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, 0, b->stream>>>(b->d);
 }
 static void enqueue_narrow(rp_batch* b) {
@@ -551,11 +556,16 @@ static void enqueue_solve(rp_batch* b, double h, uint32_t iters, int collisions,
 	for (uint32_t it = 0; it < iters; ++it) {
 		for (int l = 1; l <= levels; ++l) k_pos_level<<<pos_grid(b), 128, 0, b->stream>>>(d, h, l, collisions);
 	}
-	const size_t WB = (size_t)d.W * d.NB;
-	k_derive<<<(unsigned int)((WB + 127) / 128), 128, 0, b->stream>>>(d, h);
+	// velocity derivation (pbd.cpp:623-643) is lazy: a body's velocities are derived by the first velocity-level unit
+	// that touches it, else by the next substep's k_integrate, else by k_derive at the end of the frame
 	if (collisions) {
 		for (int l = 1; l <= levels; ++l) k_vel_level<<<vel_grid(b), 128, 0, b->stream>>>(d, h, l);
 	}
+}
+static void enqueue_frame_end(rp_batch* b, double h) {
+	const DevView& d = b->d;
+	k_derive<<<dim3(d.NB, (d.W + 127) / 128), 128, 0, b->stream>>>(d, h);
+	k_count_frame<<<1, 1, 0, b->stream>>>(d);
 }
 
 static void enqueue_substeps(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int collisions, int levels) {
@@ -565,7 +575,7 @@ static void enqueue_substeps(rp_batch* b, double dt, uint32_t substeps, uint32_t
 		if (collisions) enqueue_narrow(b);
 		enqueue_solve(b, h, iters, collisions, levels);
 	}
-	k_count_frame<<<1, 1, 0, b->stream>>>(b->d);
+	enqueue_frame_end(b, h);
 }
 
 int rp_batch_step(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int collisions) {
@@ -626,8 +636,7 @@ static int upload_impl(rp_batch* b, uint32_t first, uint32_t n, const double* ho
 	RP_CUDA(cudaSetDevice(b->device));
 	const size_t nrec = (size_t)(broadcast ? 1 : n) * b->d.NB;
 	RP_CUDA(cudaMemcpyAsync(b->rec_dev, host, nrec * RP_STATE_STRIDE * sizeof(double), cudaMemcpyHostToDevice, b->stream));
-	const size_t total = (size_t)n * b->d.NB;
-	k_unpack_state<<<(unsigned int)((total + 127) / 128), 128, 0, b->stream>>>(b->d, b->rec_dev, (int)first, (int)n, broadcast);
+	k_unpack_state<<<dim3(b->d.NB, (n + 127) / 128), 128, 0, b->stream>>>(b->d, b->rec_dev, (int)first, (int)n, broadcast);
 	RP_CUDA(cudaGetLastError());
 	return RP_OK;
 }
@@ -649,7 +658,7 @@ static int download_async(rp_batch* b, uint32_t first, uint32_t n, double* host)
 	if (!b || !host || first + n > (uint32_t)b->d.W || n == 0) return fail(RP_ERR_ARG, "state transfer: bad range");
 	RP_CUDA(cudaSetDevice(b->device));
 	const size_t total = (size_t)n * b->d.NB;
-	k_pack_state<<<(unsigned int)((total + 127) / 128), 128, 0, b->stream>>>(b->d, b->rec_dev, (int)first, (int)n);
+	k_pack_state<<<dim3(b->d.NB, (n + 127) / 128), 128, 0, b->stream>>>(b->d, b->rec_dev, (int)first, (int)n);
 	RP_CUDA(cudaGetLastError());
 	RP_CUDA(cudaMemcpyAsync(host, b->rec_dev, total * RP_STATE_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
 	return RP_OK;
@@ -697,22 +706,31 @@ static int fetch(rp_batch* b, std::vector<T>& host, const T* dev, size_t n) {
 	return RP_OK;
 }
 
+// one world's column of a world-minor array: element e at dev[e * stride + w]
+template <class T>
+static int fetch_world(rp_batch* b, std::vector<T>& host, const T* dev, size_t n, int w) {
+	host.resize(n);
+	if (n) {
+		RP_CUDA(cudaMemcpy2DAsync(host.data(), sizeof(T), dev + w, (size_t)b->d.WS * sizeof(T), sizeof(T), n, cudaMemcpyDeviceToHost,
+			b->stream));
+	}
+	RP_CUDA(cudaStreamSynchronize(b->stream));
+	return RP_OK;
+}
+
 extern "C" {
 
 int rp_batch_broad_pairs(rp_batch* b, uint32_t world, uint32_t* pairs_out, uint32_t max_pairs, uint32_t* n_out) {
 	if (!b || world >= (uint32_t)b->d.W || !n_out) return RP_ERR_ARG;
 	RP_CUDA(cudaSetDevice(b->device));
 	const DevView& d = b->d;
-	dim3 rows((d.NB + 127) / 128, d.W);
-	k_broad_rows<false><<<rows, 128, 0, b->stream>>>(d);
-	k_broad_scan<<<d.W, 256, 0, b->stream>>>(d);
-	k_broad_rows<true><<<rows, 128, 0, b->stream>>>(d);
+	launch_broad(b);
 	RP_CUDA(cudaGetLastError());
 	std::vector<int> np;
 	int rc = fetch(b, np, d.n_pairs + world, 1);
 	if (rc) return rc;
 	std::vector<PairRec> pr;
-	if ((rc = fetch(b, pr, d.pairs + (size_t)world * d.max_pairs, (size_t)np[0]))) return rc;
+	if ((rc = fetch_world(b, pr, d.pairs, (size_t)np[0], (int)world))) return rc;
 	uint32_t n = 0;
 	for (int i = 0; i < np[0]; ++i) {
 		if (i > 0 && pr[i].a == pr[i - 1].a && pr[i].b == pr[i - 1].b) continue;  // collider pairs of one body pair
@@ -745,8 +763,8 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t substeps, uint32_t ite
 	std::vector<BodyStatic> bs;
 	std::vector<V3> normals, pts;
 	if ((rc = fetch(b, np, d.n_pairs + world, 1))) return rc;
-	if ((rc = fetch(b, pr, d.pairs + (size_t)world * d.max_pairs, (size_t)np[0]))) return rc;
-	if ((rc = fetch(b, active, d.active + (size_t)world * d.NB, (size_t)d.NB))) return rc;
+	if ((rc = fetch_world(b, pr, d.pairs, (size_t)np[0], (int)world))) return rc;
+	if ((rc = fetch_world(b, active, d.active, (size_t)d.NB, (int)world))) return rc;
 	if ((rc = fetch(b, bs, d.bstat, (size_t)d.NB))) return rc;
 	uint32_t nc = 0, nk = 0;
 	for (uint32_t s = 0; s < substeps; ++s) {
@@ -754,10 +772,9 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t substeps, uint32_t ite
 		if (collisions) {
 			enqueue_narrow(b);
 			RP_CUDA(cudaGetLastError());
-			const size_t base = (size_t)world * d.max_pairs;
-			if ((rc = fetch(b, ccnt, d.pair_ccnt + base, (size_t)np[0]))) return rc;
-			if ((rc = fetch(b, coff, d.pair_coff + base, (size_t)np[0]))) return rc;
-			if ((rc = fetch(b, normals, d.pair_normal + base, (size_t)np[0]))) return rc;
+			if ((rc = fetch_world(b, ccnt, d.pair_ccnt, (size_t)np[0], (int)world))) return rc;
+			if ((rc = fetch_world(b, coff, d.pair_coff, (size_t)np[0], (int)world))) return rc;
+			if ((rc = fetch_world(b, normals, d.pair_normal, (size_t)np[0], (int)world))) return rc;
 			if ((rc = fetch(b, pts, d.dbg_points, 2 * (size_t)d.max_contacts))) return rc;
 			for (int i = 0; i < np[0]; ++i) {
 				const PairRec& p = pr[i];
@@ -785,7 +802,7 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t substeps, uint32_t ite
 		}
 		enqueue_solve(b, h, iters, collisions ? 1 : 0, levels);
 	}
-	k_count_frame<<<1, 1, 0, b->stream>>>(d);
+	enqueue_frame_end(b, h);
 	RP_CUDA(cudaGetLastError());
 	RP_CUDA(cudaStreamSynchronize(b->stream));
 	d.dbg_world = -1;
@@ -817,10 +834,7 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 	};
 	for (uint32_t f = 0; f < frames; ++f) {
 		if ((rc = mark(-1))) return rc;
-		dim3 rows((d.NB + 127) / 128, d.W);
-		k_broad_rows<false><<<rows, 128, 0, b->stream>>>(d);
-		k_broad_scan<<<d.W, 256, 0, b->stream>>>(d);
-		k_broad_rows<true><<<rows, 128, 0, b->stream>>>(d);
+		launch_broad(b);
 		if ((rc = mark(RP_K_BROAD))) return rc;
 		k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
 		if ((rc = mark(RP_K_ISLANDS))) return rc;
@@ -840,7 +854,7 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 				if ((rc = mark(RP_K_CULL))) return rc;
 				launch_gjk(b);
 				if ((rc = mark(RP_K_GJK))) return rc;
-				k_epa<<<b->sm_count * RP_MINB_EPA, RP_EPA_THREADS, 0, b->stream>>>(d);
+				k_epa<<<b->sm_count * 16, RP_EPA_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_EPA))) return rc;
 				k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_MANIFOLD))) return rc;
@@ -849,14 +863,13 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 				for (int l = 1; l <= levels; ++l) k_pos_level<<<pos_grid(b), 128, 0, b->stream>>>(d, h, l, collisions ? 1 : 0);
 			}
 			if ((rc = mark(RP_K_SOLVE_POS))) return rc;
-			k_derive<<<(unsigned int)(((size_t)d.W * d.NB + 127) / 128), 128, 0, b->stream>>>(d, h);
-			if ((rc = mark(RP_K_DERIVE))) return rc;
 			if (collisions) {
 				for (int l = 1; l <= levels; ++l) k_vel_level<<<vel_grid(b), 128, 0, b->stream>>>(d, h, l);
 				if ((rc = mark(RP_K_SOLVE_VEL))) return rc;
 			}
 		}
-		k_count_frame<<<1, 1, 0, b->stream>>>(d);
+		enqueue_frame_end(b, h);
+		if ((rc = mark(RP_K_DERIVE))) return rc;
 	}
 	RP_CUDA(cudaGetLastError());
 	RP_CUDA(cudaStreamSynchronize(b->stream));

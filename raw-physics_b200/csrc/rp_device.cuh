@@ -12,10 +12,9 @@
 
 namespace rp {
 
-// per-world, per-body dynamic state (entity.h:21-46), AoS: the solver gathers whole bodies by index
-struct BodyDyn {
-	double x[3], q[4], v[3], w[3], px[3], pq[4], pv[3], pw[3];
-};
+// per-world, per-body dynamic state (entity.h:21-46): x[3] q[4] v[3] w[3] prev_x[3] prev_q[4] prev_v[3] prev_w[3], stored
+// world-minor: component f of body b in world w at dyn[(b * RP_DYN_DOUBLES + f) * WS + w] (see rp_kernels.cuh "layout")
+#define RP_DYN_DOUBLES 26
 // Physical parameters of a body, shared by all worlds (template) and de-duplicated: bodies with bit-identical mass,
 // tensors and coefficients share one record (W256: 2 classes for 257 bodies), so the lanes of a warp that work on
 // different bodies of the same class read the SAME addresses (one broadcast wavefront instead of 32 scattered ones).
@@ -44,6 +43,7 @@ enum { CNT_PAIR_TESTS = 0, CNT_HITS = 1, CNT_CONTACTS = 2, CNT_BROAD_PAIRS = 3, 
 
 struct DevView {
 	int W, NB, NC, NJ, TV, TN;
+	int WS;              // world stride of every world-minor array: W rounded up to a multiple of 32
 	int max_pairs, max_contacts, max_units;
 	double lin_sleep, ang_sleep, sleep_time;
 	// template
@@ -54,26 +54,27 @@ struct DevView {
 	const Joint* joints;
 	const V3* force;
 	const V3* torque;
-	// per world
-	BodyDyn* dyn;        // [W][NB]
-	int* active;         // [W][NB]
-	double* deact;       // [W][NB]
-	V3* tv;              // [W][TV] transformed vertices (sphere: centre)
-	V3* tn;              // [W][TN] transformed face normals
-	PairRec* pairs;      // [W][max_pairs]
+	// per world, world-minor ([...][WS]) unless noted
+	double* dyn;         // [NB][RP_DYN_DOUBLES][WS]
+	int* active;         // [NB][WS]
+	int* vstamp;         // [NB][WS] substep counter value at which the body's velocities were last derived (lazy k_derive)
+	int* epoch;          // [1] substep counter, +1 per substep (k_substep_reset)
+	double* deact;       // [NB][WS]
+	double* tv;          // [TV][3][WS] transformed vertices (sphere: centre)
+	double* tn;          // [TN][3][WS] transformed face normals
+	PairRec* pairs;      // [max_pairs][WS]
 	int* n_pairs;        // [W]
-	int* row_off;        // [W][NB] broadphase row counts -> offsets
-	int* label;          // [W][NB] island labels
+	int* row_off;        // [W][NB] broadphase row counts -> offsets (world-major: scanned by one CTA per world)
+	int* label;          // [W][NB] island labels (world-major scratch of k_islands)
 	int* isl_flag;       // [W][NB] island "all members may sleep"
-	int* last_level;     // [W][NB] schedule scratch
-	int* pair_level;     // [W][max_pairs] dependency level of each broadphase pair (0 = skipped this frame)
-	int* lvl_hist;       // [W][max_levels + 2] schedule scratch (per-world level histogram)
-	double* aabb;        // [W][NC][6] world-space bounds of every collider (min xyz, max xyz)
+	int* last_level;     // [NB][WS] schedule scratch
+	int* pair_level;     // [max_pairs][WS] dependency level of each broadphase pair (0 = skipped this frame)
+	int* lvl_hist;       // [max_levels + 2][WS] schedule scratch (per-world level histogram)
+	double* aabb;        // [NC][6][WS] world-space bounds of every collider (min xyz, max xyz)
 	uint2* cands;        // [W * max_pairs] (world, pair) that survived the skip rule and the bounds cull
 	unsigned int* cand_count;
-	unsigned char* verdict;  // [W * max_pairs] per candidate: narrowphase says "colliding"
-	V3* simplex;         // [W * max_pairs][4] final GJK tetrahedron of colliding candidates
-	unsigned int* hits;  // [W * max_pairs] indices of the colliding candidates (dense)
+	unsigned int* hits;  // [W * max_pairs] indices (into cands) of the colliding candidates, dense
+	V3* simplex;         // [W * max_pairs][4] final GJK tetrahedron of each hit
 	unsigned int* hit_count;
 	EpaOut* epa_out;     // [W * max_pairs] per hit
 	// level-major work lists shared by all worlds: the pairs of dependency level l that have contacts this substep
@@ -88,12 +89,12 @@ struct DevView {
 	const int* joint_lptr;    // [joint_levels + 1]
 	const int* joint_last;    // [NB] level of the last joint touching each body (0 = none)
 	int joint_levels;
-	V3* pair_normal;     // [W][max_pairs]
-	int* pair_coff;      // [W][max_pairs]
-	int* pair_ccnt;      // [W][max_pairs]
-	Contact* contacts;   // [W][max_contacts]
+	V3* pair_normal;     // [max_pairs][WS]
+	int* pair_coff;      // [max_pairs][WS]
+	int* pair_ccnt;      // [max_pairs][WS]
+	Contact* contacts;   // [W][max_contacts] (world-major records: a manifold's contacts are walked by one thread)
 	int* n_contacts;     // [W]
-	JointLambda* lambdas;  // [W][NJ]
+	JointLambda* lambdas;  // [NJ][WS]
 	int* status;         // [W]
 	unsigned long long* counters;
 	// parity instrumentation (rp_batch_step_logged)

@@ -44,11 +44,32 @@
 
 namespace rp {
 
-// ------------------------------------------------------------------------------------------------------ body access
-__device__ __forceinline__ V3 ld3(const double* p) { return v3(p[0], p[1], p[2]); }
-__device__ __forceinline__ Q4 ld4(const double* p) { return q4(p[0], p[1], p[2], p[3]); }
-__device__ __forceinline__ void st3(double* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
-__device__ __forceinline__ void st4(double* p, Q4 q) { p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w; }
+// ---------------------------------------------------------------------------------------------------------- layout
+// Everything that is per world is stored WORLD-MINOR: element e of world w lives at base[e * WS + w] (WS = number of
+// worlds rounded up to a multiple of 32). The kernels map lane -> world, so the 32 lanes of a warp -- the same body, the
+// same pair index or the same contact slot in 32 neighbouring worlds -- read 32 consecutive doubles: every per-lane
+// gather of the world-major layout (32 wavefronts per load instruction; ncu, round 1: k_manifold at 68 % of the LSU
+// wavefront peak with 24 stall cycles on the long scoreboard per issued instruction) becomes one coalesced request.
+enum { DF_X = 0, DF_Q = 3, DF_V = 7, DF_W = 10, DF_PX = 13, DF_PQ = 16, DF_PV = 20, DF_PW = 23 };  // fields of a body's dynamic record
+
+struct DynRef {  // one body's dynamic record: field component f at p[f * s]
+	double* p;
+	size_t s;
+};
+__device__ __forceinline__ DynRef dyn_ref(const DevView& d, int w, int b) {
+	DynRef r;
+	r.p = d.dyn + (size_t)b * RP_DYN_DOUBLES * d.WS + w;
+	r.s = d.WS;
+	return r;
+}
+__device__ __forceinline__ V3 ld3(const DynRef& r, int f) { return v3(r.p[f * r.s], r.p[(f + 1) * r.s], r.p[(f + 2) * r.s]); }
+__device__ __forceinline__ Q4 ld4(const DynRef& r, int f) { return q4(r.p[f * r.s], r.p[(f + 1) * r.s], r.p[(f + 2) * r.s], r.p[(f + 3) * r.s]); }
+__device__ __forceinline__ void st3(const DynRef& r, int f, V3 v) { r.p[f * r.s] = v.x; r.p[(f + 1) * r.s] = v.y; r.p[(f + 2) * r.s] = v.z; }
+__device__ __forceinline__ void st4(const DynRef& r, int f, Q4 q) {
+	r.p[f * r.s] = q.x; r.p[(f + 1) * r.s] = q.y; r.p[(f + 2) * r.s] = q.z; r.p[(f + 3) * r.s] = q.w;
+}
+__device__ __forceinline__ size_t bidx(const DevView& d, int b, int w) { return (size_t)b * d.WS + w; }  // per-body arrays
+__device__ __forceinline__ size_t pidx(const DevView& d, int p, int w) { return (size_t)p * d.WS + w; }  // per-pair arrays
 
 __device__ __forceinline__ void load_static(Body& b, const DevView& d, int body) {
 	const BodyStatic& s = d.bstat[body];
@@ -59,62 +80,73 @@ __device__ __forceinline__ void load_static(Body& b, const DevView& d, int body)
 	b.mu_s = c.mu_s; b.mu_d = c.mu_d; b.rest = c.rest;
 	b.fixed = s.fixed;
 }
-__device__ __forceinline__ void load_dyn(Body& b, const BodyDyn& d) {
-	b.x = ld3(d.x); b.q = ld4(d.q); b.v = ld3(d.v); b.w = ld3(d.w);
-	b.px = ld3(d.px); b.pq = ld4(d.pq); b.pv = ld3(d.pv); b.pw = ld3(d.pw);
+
+// A collider of world w at its current pose: transformed vertices / normals addressed in the world-minor arrays
+// (vertex stride 3 * WS, component stride WS).
+__device__ __forceinline__ Shape dev_shape(const DevView& d, const ColliderDesc& c, int w) {
+	Shape s;
+	s.type = c.type;
+	s.radius = c.radius;
+	s.vp = d.tv + (size_t)c.tv0 * 3 * d.WS + w; s.vs = 3 * d.WS; s.vcs = d.WS;
+	s.np = d.tn + (size_t)c.tn0 * 3 * d.WS + w; s.ns = 3 * d.WS; s.ncs = d.WS;
+	if (c.type == SHAPE_SPHERE) {
+		s.center = v3(s.vp[0], s.vp[d.WS], s.vp[2 * (size_t)d.WS]);
+		s.nv = 0; s.nf = 0;
+		s.face_ptr = s.face_idx = s.v2f_ptr = s.v2f_idx = s.v2n_ptr = s.v2n_idx = s.f2n_ptr = s.f2n_idx = 0;
+	} else {
+		const HullTopo h = d.pool.hulls[c.hull];
+		s.center = v3(0.0, 0.0, 0.0);
+		s.nv = h.nv; s.nf = h.nf;
+		s.face_ptr = d.pool.face_ptr + h.fptr0; s.face_idx = d.pool.face_idx;
+		s.v2f_ptr = d.pool.v2f_ptr + h.v2f0; s.v2f_idx = d.pool.v2f_idx;
+		s.v2n_ptr = d.pool.v2n_ptr + h.v2n0; s.v2n_idx = d.pool.v2n_idx;
+		s.f2n_ptr = d.pool.f2n_ptr + h.f2n0; s.f2n_idx = d.pool.f2n_idx;
+	}
+	return s;
 }
 
 // ------------------------------------------------------------------------------------------------------- broadphase
 // broad_get_collision_pairs (broad.cpp:6-29): all i < j with |x_i - x_j| <= r_i + r_j + 0.1, emitted in (i, j) order.
-// Row i is one thread; all threads of a CTA walk j together so the position loads broadcast.
+// Thread = (world, row i): blockDim = (32 worlds, 8 rows); the lanes of a warp walk j together for 32 worlds.
 template <bool WRITE>
-__global__ void __launch_bounds__(128) k_broad_rows(DevView d) {
-	const int w = blockIdx.y;
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	const int row0 = blockIdx.x * blockDim.x;
-	const BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
-	V3 xi = v3(0.0, 0.0, 0.0);
-	double ri = 0.0;
-	int ci0 = 0, nci = 0;
-	if (i < d.NB) {
-		xi = ld3(dyn[i].x);
-		ri = d.bstat[i].radius;
-		ci0 = d.bstat[i].col0;
-		nci = d.bstat[i].ncol;
-	}
+__global__ void __launch_bounds__(256) k_broad_rows(DevView d) {
+	const int w = blockIdx.y * 32 + threadIdx.x;
+	const int i = blockIdx.x * blockDim.y + threadIdx.y;
+	if (w >= d.W || i >= d.NB) return;
+	const double* X = d.dyn + w;  // x of body j: X[(j * RP_DYN_DOUBLES + c) * WS]
+	const size_t S = d.WS;
+	const V3 xi = v3(X[((size_t)i * RP_DYN_DOUBLES + 0) * S], X[((size_t)i * RP_DYN_DOUBLES + 1) * S], X[((size_t)i * RP_DYN_DOUBLES + 2) * S]);
+	const double ri = d.bstat[i].radius;
+	const int ci0 = d.bstat[i].col0, nci = d.bstat[i].ncol;
 	int count = 0;
-	int out = 0;
-	PairRec* pairs = d.pairs + (size_t)w * d.max_pairs;
-	if (WRITE && i < d.NB) out = d.row_off[(size_t)w * d.NB + i];
-	for (int j = row0 + 1; j < d.NB; ++j) {
-		if (i < d.NB && j > i) {
-			V3 xj = ld3(dyn[j].x);
-			double dist = length(sub(xi, xj));
-			double maxd = ri + d.bstat[j].radius + 0.1;
-			if (dist <= maxd) {
-				int ncj = d.bstat[j].ncol;
-				if (WRITE) {
-					int cj0 = d.bstat[j].col0;
-					for (int a = 0; a < nci; ++a) {
-						for (int b = 0; b < ncj; ++b) {
-							if (out < d.max_pairs) {
-								PairRec pr;
-								pr.a = i; pr.b = j; pr.ca = ci0 + a; pr.cb = cj0 + b;
-								pairs[out] = pr;
-							}
-							++out;
+	int out = WRITE ? d.row_off[(size_t)w * d.NB + i] : 0;
+	for (int j = i + 1; j < d.NB; ++j) {
+		const V3 xj = v3(X[((size_t)j * RP_DYN_DOUBLES + 0) * S], X[((size_t)j * RP_DYN_DOUBLES + 1) * S], X[((size_t)j * RP_DYN_DOUBLES + 2) * S]);
+		const double dist = length(sub(xi, xj));
+		const double maxd = ri + d.bstat[j].radius + 0.1;
+		if (dist <= maxd) {
+			const int ncj = d.bstat[j].ncol;
+			if (WRITE) {
+				const int cj0 = d.bstat[j].col0;
+				for (int a = 0; a < nci; ++a) {
+					for (int b = 0; b < ncj; ++b) {
+						if (out < d.max_pairs) {
+							PairRec pr;
+							pr.a = i; pr.b = j; pr.ca = ci0 + a; pr.cb = cj0 + b;
+							d.pairs[pidx(d, out, w)] = pr;
 						}
+						++out;
 					}
-				} else {
-					count += nci * ncj;
 				}
+			} else {
+				count += nci * ncj;
 			}
 		}
 	}
-	if (!WRITE && i < d.NB) d.row_off[(size_t)w * d.NB + i] = count;
+	if (!WRITE) d.row_off[(size_t)w * d.NB + i] = count;
 }
 
-// exclusive scan of the row counts of one world (one CTA per world)
+// exclusive scan of the row counts of one world (one CTA per world; row_off is [W][NB])
 __global__ void __launch_bounds__(256) k_broad_scan(DevView d) {
 	const int w = blockIdx.x;
 	int* row = d.row_off + (size_t)w * d.NB;
@@ -154,15 +186,12 @@ __global__ void __launch_bounds__(256) k_broad_scan(DevView d) {
 // ------------------------------------------------------------------------------------------------- islands + sleeping
 // broad_collect_simulation_islands (broad.cpp:70-116) + the sleep bookkeeping of pbd.cpp:476-506. Islands are the
 // connected components of {pairs, external constraints} restricted to non-fixed bodies; the result does not depend on
-// the order in which unions happen, so min-label propagation replaces the reference's union-find. One CTA per world.
+// the order in which unions happen, so min-label propagation replaces the reference's union-find. One CTA per world
+// (labels and flags are [W][NB] scratch; the strided reads of the world-minor arrays are once per frame).
 __global__ void __launch_bounds__(256) k_islands(DevView d, double dt) {
 	const int w = blockIdx.x;
 	int* label = d.label + (size_t)w * d.NB;
 	int* flag = d.isl_flag + (size_t)w * d.NB;
-	BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
-	int* active = d.active + (size_t)w * d.NB;
-	double* deact = d.deact + (size_t)w * d.NB;
-	const PairRec* pairs = d.pairs + (size_t)w * d.max_pairs;
 	const int np = d.n_pairs[w];
 	__shared__ int changed;
 	for (int b = threadIdx.x; b < d.NB; b += blockDim.x) {
@@ -176,7 +205,8 @@ __global__ void __launch_bounds__(256) k_islands(DevView d, double dt) {
 		for (int e = threadIdx.x; e < np + d.NJ; e += blockDim.x) {
 			int a, b;
 			if (e < np) {
-				a = pairs[e].a; b = pairs[e].b;
+				const PairRec pr = d.pairs[pidx(d, e, w)];
+				a = pr.a; b = pr.b;
 			} else {
 				a = d.joints[e - np].e1; b = d.joints[e - np].e2;
 			}
@@ -196,18 +226,19 @@ __global__ void __launch_bounds__(256) k_islands(DevView d, double dt) {
 	}
 	for (int b = threadIdx.x; b < d.NB; b += blockDim.x) {
 		if (d.bstat[b].fixed) continue;
-		double lv = length(ld3(dyn[b].v));
-		double av = length(ld3(dyn[b].w));
-		double t = deact[b];
+		const DynRef r = dyn_ref(d, w, b);
+		double lv = length(ld3(r, DF_V));
+		double av = length(ld3(r, DF_W));
+		double t = d.deact[bidx(d, b, w)];
 		if (lv < d.lin_sleep && av < d.ang_sleep) t += dt;
 		else t = 0.0;
-		deact[b] = t;
+		d.deact[bidx(d, b, w)] = t;
 		if (t < d.sleep_time) flag[label[b]] = 0;
 	}
 	__syncthreads();
 	for (int b = threadIdx.x; b < d.NB; b += blockDim.x) {
 		if (d.bstat[b].fixed) continue;
-		active[b] = flag[label[b]] ? 0 : 1;
+		d.active[bidx(d, b, w)] = flag[label[b]] ? 0 : 1;
 	}
 }
 
@@ -216,38 +247,41 @@ __global__ void __launch_bounds__(256) k_islands(DevView d, double dt) {
 // output is the head of the array, pbd.cpp:580), then the broadphase (collider-)pairs in pair order, each pair standing
 // for its whole manifold (pbd.cpp:584-611). level(u) = 1 + max(level of the previous unit touching either of u's
 // NON-FIXED bodies). The joints' levels are the same in every world (host, at batch creation); this kernel continues
-// the recurrence over one world's pairs (one thread per world, once per frame) and adds the world's per-level pair
-// counts to the global capacities of the level-major work lists.
+// the recurrence over one world's pairs (one thread per world, once per frame; all its arrays are world-minor, so the
+// 32 worlds of a warp read consecutive words) and adds the world's per-level pair counts to the global capacities of
+// the level-major work lists.
 __global__ void __launch_bounds__(64) k_schedule(DevView d, int collisions) {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= d.W) return;
-	int* last = d.last_level + (size_t)w * d.NB;
-	int* plevel = d.pair_level + (size_t)w * d.max_pairs;
-	int* hist = d.lvl_hist + (size_t)w * (d.max_levels + 2);
-	const int* active = d.active + (size_t)w * d.NB;
-	const PairRec* pairs = d.pairs + (size_t)w * d.max_pairs;
+	int* last = d.last_level + w;      // [NB][WS]
+	int* plevel = d.pair_level + w;    // [max_pairs][WS]
+	int* hist = d.lvl_hist + w;        // [max_levels + 2][WS]
+	const int* active = d.active + w;  // [NB][WS]
+	const size_t S = d.WS;
 	const int np = collisions ? d.n_pairs[w] : 0;
-	for (int b = 0; b < d.NB; ++b) last[b] = d.joint_last[b];
+	for (int b = 0; b < d.NB; ++b) last[b * S] = d.joint_last[b];
 	int nl = d.joint_levels;
 	for (int p = 0; p < np; ++p) {
-		const int a = pairs[p].a, b = pairs[p].b;
+		const PairRec pr = d.pairs[pidx(d, p, w)];
+		const int a = pr.a, b = pr.b;
 		const int fa = d.bstat[a].fixed, fb = d.bstat[b].fixed;
 		// pbd.cpp:594: nothing to do when both sides are fixed or asleep
-		if ((fa || !active[a]) && (fb || !active[b])) {
-			plevel[p] = 0;
+		if ((fa || !active[a * S]) && (fb || !active[b * S])) {
+			plevel[p * S] = 0;
 			continue;
 		}
-		const int la = fa ? 0 : last[a], lb = fb ? 0 : last[b];
+		const int la = fa ? 0 : last[a * S], lb = fb ? 0 : last[b * S];
 		const int lvl = 1 + (la > lb ? la : lb);
-		if (!fa) last[a] = lvl;
-		if (!fb) last[b] = lvl;
-		plevel[p] = lvl;
+		if (!fa) last[a * S] = lvl;
+		if (!fb) last[b * S] = lvl;
+		plevel[p * S] = lvl;
 		if (lvl > nl) nl = lvl;
 	}
-	for (int l = 0; l <= nl + 1; ++l) hist[l] = 0;
-	for (int p = 0; p < np; ++p) hist[plevel[p]] += 1;
+	for (int l = 0; l <= nl + 1; ++l) hist[l * S] = 0;
+	for (int p = 0; p < np; ++p) hist[plevel[p * S] * S] += 1;
 	for (int l = 1; l <= nl; ++l) {
-		if (hist[l]) atomicAdd(&d.lvl_cap[l], hist[l]);
+		const int c = hist[l * S];
+		if (c) atomicAdd(&d.lvl_cap[l], c);
 	}
 	atomicMax(d.lvl_max, nl);
 	atomicAdd(&d.counters[CNT_LEVELS], (unsigned long long)nl);
@@ -268,16 +302,13 @@ __global__ void k_level_offsets(DevView d) {
 }
 
 // ---------------------------------------------------------------------------------------- integrate + collider update
-// pbd.cpp:537-577 (integration) and collider.cpp:409-445 (collider_update) for one body per thread. The reference
-// re-transforms both colliders of every pair every substep (39 % of its time); the same pose gives the same result,
-// so once per body per substep is exactly equivalent (SURVEY.md 8 a5). Also leaves each collider's world-space bounds
-// for k_cull and resets the per-substep counters.
 // per-substep counters
 __global__ void __launch_bounds__(256) k_substep_reset(DevView d) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i == 0) {
 		*d.hit_count = 0u;
 		*d.cand_count = 0u;
+		*d.epoch += 1;
 	}
 	if (i < d.max_levels + 2) {
 		d.lvl_fill[(size_t)i * RP_LVL_STRIDE] = 0;
@@ -286,162 +317,89 @@ __global__ void __launch_bounds__(256) k_substep_reset(DevView d) {
 	if (i < d.W) d.n_contacts[i] = 0;
 }
 
-#define RP_INT_MAXV 8   // staged write path of k_integrate: bodies of up to 8 transformed vertices and 6 normals (boxes)
-#define RP_INT_MAXF 6
 #define RP_INT_THREADS 128
-#define RP_DYN_DOUBLES 26   // sizeof(BodyDyn) / 8
-#define RP_DYN_LIVE 20      // x q v w px pq: the part of a record k_integrate reads or writes (pv, pw stay untouched)
-#define RP_DYN_ROW 27       // odd row pitch in shared memory: per-thread rows are free of bank conflicts
-// One thread per (world, body), flat over the whole batch: a CTA owns 128 consecutive BodyDyn records, which are
-// contiguous in HBM, so they are moved with coalesced loads/stores through shared memory (per-lane gathers of 208-byte
-// records were the kernel's long-scoreboard stall). The same shared memory is then reused to stage the transformed
-// geometry of the CTA's bodies so that those writes are coalesced too.
+// pbd.cpp:537-577 (integration) and collider.cpp:409-445 (collider_update) for one body per thread. The reference
+// re-transforms both colliders of every pair every substep (39 % of its time); the same pose gives the same result,
+// so once per body per substep is exactly equivalent (SURVEY.md 8 a5). Also leaves each collider's world-space bounds
+// for k_cull. Grid = (bodies, world blocks): a CTA is ONE body in 128 consecutive worlds, so the statics and the hull
+// are the same for every lane and every load/store of the world-minor arrays is coalesced.
 __global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate(DevView d, double h) {
-	__shared__ double s_buf[RP_INT_THREADS * ((RP_INT_MAXV * 3 + 1) + (RP_INT_MAXF * 3 + 1))];
-	static_assert(RP_INT_THREADS * RP_DYN_ROW <= RP_INT_THREADS * ((RP_INT_MAXV * 3 + 1) + (RP_INT_MAXF * 3 + 1)), "staging buffer");
-	const size_t total = (size_t)d.W * d.NB;
-	const size_t g0 = (size_t)blockIdx.x * RP_INT_THREADS;
-	const int nb = (int)(total - g0 < (size_t)RP_INT_THREADS ? total - g0 : (size_t)RP_INT_THREADS);
-	const size_t gid = g0 + threadIdx.x;
-	const bool live = threadIdx.x < nb;
-	const int w = live ? (int)(gid / d.NB) : 0;
-	const int b = live ? (int)(gid % d.NB) : 0;
-	// ---- coalesced load of the CTA's records
-	{
-		const double* g = (const double*)(d.dyn + g0);
-		int r = threadIdx.x / RP_DYN_DOUBLES, c = threadIdx.x - r * RP_DYN_DOUBLES;
-		for (int e = threadIdx.x; e < nb * RP_DYN_DOUBLES; e += RP_INT_THREADS) {
-			if (c < 13) s_buf[r * RP_DYN_ROW + c] = g[e];
-			r += RP_INT_THREADS / RP_DYN_DOUBLES; c += RP_INT_THREADS % RP_DYN_DOUBLES;
-			if (c >= RP_DYN_DOUBLES) { c -= RP_DYN_DOUBLES; ++r; }
+	const int w = blockIdx.y * RP_INT_THREADS + threadIdx.x;
+	const int b = blockIdx.x;
+	if (w >= d.W) return;
+	const int epoch = *d.epoch;
+	const size_t S = d.WS;
+	if (b < d.NJ) {  // copy_constraints resets every lambda each substep (pbd.cpp:426-462)
+		for (int j = b; j < d.NJ; j += d.NB) {
+			JointLambda z;
+			z.a = z.b = z.c = 0.0;
+			d.lambdas[(size_t)j * S + w] = z;
 		}
 	}
-	__syncthreads();
+	const BodyStatic s = d.bstat[b];
 	Body body;
-	BodyStatic s;
-	s.fixed = 1; s.col0 = 0; s.ncol = 0; s.tv0 = 0; s.tvn = 0; s.tn0 = 0; s.tnn = 0; s.cls = 0; s.radius = 0.0;
-	double* row = s_buf + threadIdx.x * RP_DYN_ROW;
-	if (live) {
-		if (b < d.NJ) {  // copy_constraints resets every lambda each substep (pbd.cpp:426-462)
-			for (int j = b; j < d.NJ; j += d.NB) {
-				JointLambda z;
-				z.a = z.b = z.c = 0.0;
-				d.lambdas[(size_t)w * d.NJ + j] = z;
-			}
-		}
-		s = d.bstat[b];
-		load_static(body, d, b);
-		body.x = ld3(row); body.q = ld4(row + 3); body.v = ld3(row + 7); body.w = ld3(row + 10);
-		body.active = d.active[gid];
-		integrate(body, h, d.force[b], d.torque[b]);
-		st3(row, body.x); st4(row + 3, body.q); st3(row + 7, body.v); st3(row + 10, body.w);  // unchanged when fixed or asleep
-		st3(row + 13, body.px); st4(row + 16, body.pq);
+	load_static(body, d, b);
+	const DynRef r = dyn_ref(d, w, b);
+	body.x = ld3(r, DF_X); body.q = ld4(r, DF_Q); body.v = ld3(r, DF_V); body.w = ld3(r, DF_W);
+	body.active = d.active[bidx(d, b, w)];
+	const bool moving = !(body.fixed || !body.active);
+	// lazy velocity derivation of the PREVIOUS substep (pbd.cpp:623-643) for a body no velocity-level unit touched
+	// there: (x, q, prev x, prev q, v, w) are still exactly what the reference's derivation pass would have seen. Its
+	// prev-velocity outputs are not stored: nothing reads them before this substep's derivation rewrites them.
+	if (moving && d.vstamp[bidx(d, b, w)] != epoch - 1) {
+		body.px = ld3(r, DF_PX); body.pq = ld4(r, DF_PQ);
+		derive_velocity(body, h);
 	}
-	__syncthreads();
-	{
-		double* g = (double*)(d.dyn + g0);
-		int r = threadIdx.x / RP_DYN_DOUBLES, c = threadIdx.x - r * RP_DYN_DOUBLES;
-		for (int e = threadIdx.x; e < nb * RP_DYN_DOUBLES; e += RP_INT_THREADS) {
-			if (c < RP_DYN_LIVE) g[e] = s_buf[r * RP_DYN_ROW + c];
-			r += RP_INT_THREADS / RP_DYN_DOUBLES; c += RP_INT_THREADS % RP_DYN_DOUBLES;
-			if (c >= RP_DYN_DOUBLES) { c -= RP_DYN_DOUBLES; ++r; }
-		}
+	integrate(body, h, d.force[b], d.torque[b]);
+	st3(r, DF_PX, body.px); st4(r, DF_PQ, body.pq);
+	if (moving) {
+		st3(r, DF_X, body.x); st4(r, DF_Q, body.q); st3(r, DF_V, body.v); st3(r, DF_W, body.w);
 	}
-	// ---- collider update. Staged path only when every body of the CTA has the same small footprint and the CTA's
-	// blocks of transformed vertices / normals are laid out back to back (they are, across world boundaries too, when
-	// all bodies of the scene have that footprint: TV = NB * tvn).
-	size_t voff = 0, noff = 0;
-	if (live) {
-		voff = (size_t)w * d.TV + s.tv0;
-		noff = (size_t)w * d.TN + s.tn0;
-	}
-	__shared__ size_t s_off[2];
-	__shared__ int s_foot[2];
-	if (threadIdx.x == 0) { s_off[0] = voff; s_off[1] = noff; s_foot[0] = s.tvn; s_foot[1] = s.tnn; }
-	__syncthreads();  // also fences the write-back reads of s_buf against the staging writes below
-	const int tvn = s_foot[0], tnn = s_foot[1];
-	bool uniform = tvn <= RP_INT_MAXV && tnn <= RP_INT_MAXF;
-	if (live) uniform = uniform && s.tvn == tvn && s.tnn == tnn && voff == s_off[0] + (size_t)threadIdx.x * tvn && noff == s_off[1] + (size_t)threadIdx.x * tnn;
-	const bool staged = __syncthreads_and(uniform) != 0;
-	const int rv = tvn * 3 + 1, rn = tnn * 3 + 1;
-	double* s_tv = s_buf;
-	double* s_tn = s_buf + RP_INT_THREADS * (RP_INT_MAXV * 3 + 1);
-	if (live) {
-		Pose34 M = model_matrix(body.q, body.x);
-		V3* tv = d.tv + (size_t)w * d.TV;
-		V3* tn = d.tn + (size_t)w * d.TN;
-		double* row_v = s_tv + (size_t)threadIdx.x * rv;
-		double* row_n = s_tn + (size_t)threadIdx.x * rn;
-		int ov = 0, on = 0;
-		for (int c = s.col0; c < s.col0 + s.ncol; ++c) {
-			const ColliderDesc cd = d.cols[c];
-			double* bb = d.aabb + ((size_t)w * d.NC + c) * 6;
-			if (cd.type == SHAPE_SPHERE) {
-				if (staged) { row_v[ov] = body.x.x; row_v[ov + 1] = body.x.y; row_v[ov + 2] = body.x.z; ov += 3; }
-				else tv[cd.tv0] = body.x;
-				const double r = (double)cd.radius;
-				bb[0] = body.x.x - r; bb[1] = body.x.y - r; bb[2] = body.x.z - r;
-				bb[3] = body.x.x + r; bb[4] = body.x.y + r; bb[5] = body.x.z + r;
-			} else {
-				const HullTopo t = d.pool.hulls[cd.hull];
-				double lo0 = 1.7976931348623157e308, lo1 = lo0, lo2 = lo0, hi0 = -lo0, hi1 = -lo0, hi2 = -lo0;
-				for (int k = 0; k < t.nv; ++k) {
-					const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
-					if (staged) { row_v[ov] = p.x; row_v[ov + 1] = p.y; row_v[ov + 2] = p.z; ov += 3; }
-					else tv[cd.tv0 + k] = p;
-					lo0 = fmin(lo0, p.x); lo1 = fmin(lo1, p.y); lo2 = fmin(lo2, p.z);
-					hi0 = fmax(hi0, p.x); hi1 = fmax(hi1, p.y); hi2 = fmax(hi2, p.z);
-				}
-				for (int k = 0; k < t.nf; ++k) {
-					const V3 n = transform_normal(M, d.pool.normals[t.face0 + k]);
-					if (staged) { row_n[on] = n.x; row_n[on + 1] = n.y; row_n[on + 2] = n.z; on += 3; }
-					else tn[cd.tn0 + k] = n;
-				}
-				bb[0] = lo0; bb[1] = lo1; bb[2] = lo2; bb[3] = hi0; bb[4] = hi1; bb[5] = hi2;
+	const Pose34 M = model_matrix(body.q, body.x);
+	for (int c = s.col0; c < s.col0 + s.ncol; ++c) {
+		const ColliderDesc cd = d.cols[c];
+		double* bb = d.aabb + (size_t)c * 6 * S + w;
+		double* tv = d.tv + (size_t)cd.tv0 * 3 * S + w;
+		if (cd.type == SHAPE_SPHERE) {
+			tv[0] = body.x.x; tv[S] = body.x.y; tv[2 * S] = body.x.z;
+			const double rad = (double)cd.radius;
+			bb[0] = body.x.x - rad; bb[S] = body.x.y - rad; bb[2 * S] = body.x.z - rad;
+			bb[3 * S] = body.x.x + rad; bb[4 * S] = body.x.y + rad; bb[5 * S] = body.x.z + rad;
+		} else {
+			const HullTopo t = d.pool.hulls[cd.hull];
+			double* tn = d.tn + (size_t)cd.tn0 * 3 * S + w;
+			double lo0 = 1.7976931348623157e308, lo1 = lo0, lo2 = lo0, hi0 = -lo0, hi1 = -lo0, hi2 = -lo0;
+			for (int k = 0; k < t.nv; ++k) {
+				const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
+				tv[(size_t)(3 * k) * S] = p.x; tv[(size_t)(3 * k + 1) * S] = p.y; tv[(size_t)(3 * k + 2) * S] = p.z;
+				lo0 = fmin(lo0, p.x); lo1 = fmin(lo1, p.y); lo2 = fmin(lo2, p.z);
+				hi0 = fmax(hi0, p.x); hi1 = fmax(hi1, p.y); hi2 = fmax(hi2, p.z);
 			}
-		}
-	}
-	if (staged) {
-		__syncthreads();
-		double* gv = (double*)(d.tv + s_off[0]);
-		double* gn = (double*)(d.tn + s_off[1]);
-		const int nv3 = tvn * 3, nn3 = tnn * 3;
-		// g = r * n3 + c walks in steps of the CTA size; (r, c) are advanced without dividing
-		if (nv3 > 0) {
-			int r = threadIdx.x / nv3, c = threadIdx.x - r * nv3;
-			const int dr = RP_INT_THREADS / nv3, dc = RP_INT_THREADS - dr * nv3;
-			for (int g = threadIdx.x; g < nb * nv3; g += RP_INT_THREADS) {
-				gv[g] = s_tv[r * rv + c];
-				r += dr; c += dc;
-				if (c >= nv3) { c -= nv3; ++r; }
+			for (int k = 0; k < t.nf; ++k) {
+				const V3 n = transform_normal(M, d.pool.normals[t.face0 + k]);
+				tn[(size_t)(3 * k) * S] = n.x; tn[(size_t)(3 * k + 1) * S] = n.y; tn[(size_t)(3 * k + 2) * S] = n.z;
 			}
-		}
-		if (nn3 > 0) {
-			int r = threadIdx.x / nn3, c = threadIdx.x - r * nn3;
-			const int dr = RP_INT_THREADS / nn3, dc = RP_INT_THREADS - dr * nn3;
-			for (int g = threadIdx.x; g < nb * nn3; g += RP_INT_THREADS) {
-				gn[g] = s_tn[r * rn + c];
-				r += dr; c += dc;
-				if (c >= nn3) { c -= nn3; ++r; }
-			}
+			bb[0] = lo0; bb[S] = lo1; bb[2 * S] = lo2; bb[3 * S] = hi0; bb[4 * S] = hi1; bb[5 * S] = hi2;
 		}
 	}
 }
 
-// Copies a small hull's transformed vertices (and, optionally, face normals) from the world's AoS arrays into the calling
-// thread's column of a thread-interleaved shared-memory block: element e of the thread lives at base[e * nthreads], so
-// the 32 lanes of a warp touch 32 consecutive doubles per access (2 wavefronts) instead of 32 scattered sectors. The
-// narrowphase scans the same vertices many times (support mapping), so this turns an L1-wavefront-bound kernel back
-// into an FP64-bound one. Returns the number of doubles used.
+// Copies a small hull's transformed vertices (and, optionally, face normals) from the world-minor arrays into the
+// calling thread's column of a thread-interleaved shared-memory block: element e of the thread lives at
+// base[e * nthreads], so the 32 lanes of a warp touch 32 consecutive doubles per access whatever (world, body) each lane
+// holds. The narrowphase scans the same vertices many times (support mapping), and 16 vertices x 3 x 32 lanes of a warp
+// are 12 kB -- more than a warp's share of L1. Returns the number of doubles used.
 __device__ __forceinline__ int stage_shape(Shape& s, double* col, int nthreads, bool with_normals) {
 	int e = 0;
 	const double* src = s.vp;
-	for (int k = 0; k < s.nv * 3; ++k) col[(size_t)(e + k) * nthreads] = src[k];
+	const size_t cs = (size_t)s.vcs;  // global layout: vertex stride = 3 * component stride, so element k sits at k * cs
+	for (int k = 0; k < s.nv * 3; ++k) col[(size_t)(e + k) * nthreads] = src[k * cs];
 	s.vp = col + (size_t)e * nthreads; s.vs = 3 * nthreads; s.vcs = nthreads;
 	e += s.nv * 3;
 	if (with_normals) {
 		src = s.np;
-		for (int k = 0; k < s.nf * 3; ++k) col[(size_t)(e + k) * nthreads] = src[k];
+		const size_t ncs = (size_t)s.ncs;
+		for (int k = 0; k < s.nf * 3; ++k) col[(size_t)(e + k) * nthreads] = src[k * ncs];
 		s.np = col + (size_t)e * nthreads; s.ns = 3 * nthreads; s.ncs = nthreads;
 		e += s.nf * 3;
 	}
@@ -467,28 +425,39 @@ __device__ __forceinline__ unsigned int warp_append(unsigned int* counter, bool 
 // strictly positive (or strictly negative), the origin is outside the difference, and gjk_collides returns false: the
 // pair yields no contacts, exactly as if GJK had run. Survivors go to the dense candidate list of k_gjk.
 #define RP_CULL_MARGIN 1e-7
+// Work order. The lanes of a warp take the SAME pair index of 32 CONSECUTIVE worlds (lane = world, warp = pair index),
+// and every list built downstream (candidates -> hits -> level lists) keeps that order. The worlds of a batch are
+// instances of one template, so their pair lists line up and the same pair in neighbouring worlds is in a similar
+// configuration: GJK/EPA iteration counts, clipping cases and manifold sizes are correlated across the lanes of a warp
+// (identical for identical worlds), which keeps the warps of the branchy narrowphase and of the solver converged and
+// their world-minor loads coalesced. With unrelated worlds the order is merely as good as any other.
 __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
-	const int w = blockIdx.y;
-	const int np = d.n_pairs[w];
-	const int* active = d.active + (size_t)w * d.NB;
+	const int lane = threadIdx.x & 31;
+	const int w = blockIdx.y * 32 + lane;
+	const bool wlive = w < d.W;
+	const int np = wlive ? d.n_pairs[w] : 0;
+	int np_max = np;
+	for (int o = 16; o > 0; o >>= 1) np_max = max(np_max, __shfl_xor_sync(0xffffffffu, np_max, o));
+	const int* active = d.active + (wlive ? w : 0);
+	const size_t S = d.WS;
 	int tested = 0;
-	for (int p0 = blockIdx.x * blockDim.x; p0 < np; p0 += gridDim.x * blockDim.x) {
-		const int p = p0 + threadIdx.x;
+	const int warps_per_cta = blockDim.x >> 5;
+	for (int p = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); p < np_max; p += gridDim.x * warps_per_cta) {
 		bool keep = false;
 		if (p < np) {
-			const size_t pg = (size_t)w * d.max_pairs + p;
+			const size_t pg = pidx(d, p, w);
 			d.pair_ccnt[pg] = 0;
 			const PairRec pr = d.pairs[pg];
-			if (!((d.bstat[pr.a].fixed || !active[pr.a]) && (d.bstat[pr.b].fixed || !active[pr.b]))) {
+			if (!((d.bstat[pr.a].fixed || !active[pr.a * S]) && (d.bstat[pr.b].fixed || !active[pr.b * S]))) {
 				++tested;
 				keep = true;
 				if (cull) {
-					const double* A = d.aabb + ((size_t)w * d.NC + pr.ca) * 6;
-					const double* B = d.aabb + ((size_t)w * d.NC + pr.cb) * 6;
+					const double* A = d.aabb + (size_t)pr.ca * 6 * S + w;
+					const double* B = d.aabb + (size_t)pr.cb * 6 * S + w;
 					const bool both_spheres = d.cols[pr.ca].type == SHAPE_SPHERE && d.cols[pr.cb].type == SHAPE_SPHERE;
 					if (!both_spheres) {  // sphere-sphere pairs never reach GJK (collider.cpp:530)
 						for (int k = 0; k < 3; ++k) {
-							if (A[k] - B[3 + k] > RP_CULL_MARGIN || B[k] - A[3 + k] > RP_CULL_MARGIN) keep = false;
+							if (A[k * S] - B[(3 + k) * S] > RP_CULL_MARGIN || B[k * S] - A[(3 + k) * S] > RP_CULL_MARGIN) keep = false;
 						}
 					}
 				}
@@ -498,16 +467,13 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 		if (keep) d.cands[slot] = make_uint2((unsigned int)w, (unsigned int)p);
 	}
 	for (int o = 16; o > 0; o >>= 1) tested += __shfl_down_sync(0xffffffffu, tested, o);
-	if ((threadIdx.x & 31) == 0 && tested) atomicAdd(&d.counters[CNT_PAIR_TESTS], (unsigned long long)tested);
+	if (lane == 0 && tested) atomicAdd(&d.counters[CNT_PAIR_TESTS], (unsigned long long)tested);
 }
 
 // ----------------------------------------------------------------------------------------------------- narrowphase
-// GJK, EPA and the contact solves are loops whose trip counts differ from pair to pair (GJK 1..15 support iterations,
-// EPA 1..8, manifolds of 1..8 contacts). With one work item per lane a warp runs as long as its slowest lane and the
-// other lanes idle (ncu, round 1: 9..15 of 32 lanes active). The kernels below are therefore written as REFILL loops:
-// a warp owns a contiguous chunk of the work list, every trip of the loop is one iteration of the algorithm for
-// whatever item a lane currently holds, and a lane whose item is finished takes the warp's next item before the next
-// trip. The warp's cursor is warp-uniform (ballot + popc), so taking work needs no atomics.
+// A warp's cursor over a contiguous chunk of a work list (used by the solver's refill loops): every trip of the loop is
+// one step for whatever item a lane currently holds, and a lane whose item is finished takes the warp's next item
+// before the next trip. The cursor is warp-uniform (ballot + popc), so taking work needs no atomics.
 struct WarpQueue {
 	unsigned int next, end;
 	__device__ __forceinline__ void init(unsigned int n_items) {
@@ -530,156 +496,79 @@ struct WarpQueue {
 	__device__ __forceinline__ bool empty() const { return next >= end; }
 };
 
-// One lane per candidate pair at a time: sphere-sphere test or boolean GJK (collider.cpp:523-547). Writes the verdict of
-// every candidate and, for colliding pairs, the final simplex, both at the candidate's own index (k_hits compacts).
+// One thread per candidate pair: sphere-sphere test or boolean GJK (collider.cpp:523-547). Colliding pairs are appended
+// (warp-aggregated, order-preserving within the warp) to the hit list together with their final simplex.
 __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) {
 	const unsigned int nc = *d.cand_count;
 	__shared__ double s_stage[RP_GJK_STAGE * RP_GJK_THREADS];
-	WarpQueue q;
-	q.init(nc);
-	bool have = false;
-	unsigned int ci = 0;
-	int w = 0, iter = 0, st = 0;
-	Simplex s;
-	s.a = s.b = s.c = s.d = v3(0.0, 0.0, 0.0);
-	s.num = 0;
-	V3 dir = v3(0.0, 0.0, 0.0);
-	Shape A, B;
-	A.type = B.type = SHAPE_SPHERE; A.nv = B.nv = 0;
-	for (;;) {
-		const unsigned int got = q.take(!have);
-		if (got != 0xffffffffu) {
-			ci = got;
+	for (unsigned int c0 = blockIdx.x * blockDim.x; c0 < nc; c0 += gridDim.x * blockDim.x) {
+		const unsigned int ci = c0 + threadIdx.x;
+		bool hit = false;
+		Simplex s;
+		s.a = s.b = s.c = s.d = v3(0.0, 0.0, 0.0);
+		if (ci < nc) {
 			const uint2 cd = d.cands[ci];
-			w = (int)cd.x;
-			const PairRec pr = d.pairs[(size_t)w * d.max_pairs + cd.y];
-			const V3* tv = d.tv + (size_t)w * d.TV;
-			const V3* tn = d.tn + (size_t)w * d.TN;
-			A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
-			B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
+			const int w = (int)cd.x;
+			const PairRec pr = d.pairs[pidx(d, (int)cd.y, w)];
+			Shape A = dev_shape(d, d.cols[pr.ca], w);
+			Shape B = dev_shape(d, d.cols[pr.cb], w);
+			int st = 0;
 			if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
 				V3 n;
 				double depth;
-				d.verdict[ci] = sphere_sphere(A, B, &n, &depth) ? 1 : 0;  // decided on the spot; the lane refills next trip
+				hit = sphere_sphere(A, B, &n, &depth);
 			} else {
 				if ((A.nv + B.nv) * 3 <= RP_GJK_STAGE) {
 					double* col = s_stage + threadIdx.x;
 					const int used = stage_shape(A, col, RP_GJK_THREADS, false);
 					stage_shape(B, col + (size_t)used * RP_GJK_THREADS, RP_GJK_THREADS, false);
 				}
-				gjk_begin(A, B, &s, &dir);
-				iter = 0;
-				have = true;
+				hit = gjk(A, B, &s, &st, 0);
 			}
+			if (st) atomicOr(&d.status[w], st);
 		}
-		if (!__any_sync(0xffffffffu, have)) {
-			if (q.empty()) break;
-			continue;
-		}
-		if (have) {
-			int r = gjk_step(A, B, &s, &dir, &st);
-			if (r == GJK_CONTINUE && ++iter >= RP_GJK_MAX_ITERS) r = GJK_MISS;  // gjk.cpp:358
-			if (r != GJK_CONTINUE) {
-				d.verdict[ci] = r == GJK_HIT ? 1 : 0;
-				if (r == GJK_HIT) {
-					V3* o = d.simplex + (size_t)ci * 4;
-					o[0] = s.a; o[1] = s.b; o[2] = s.c; o[3] = s.d;
-				}
-				if (st) {
-					atomicOr(&d.status[w], st);
-					st = 0;
-				}
-				have = false;
-			}
-		}
-	}
-}
-
-// candidate verdicts -> dense hit list (order is irrelevant downstream)
-__global__ void __launch_bounds__(256) k_hits(DevView d) {
-	const unsigned int nc = *d.cand_count;
-	for (unsigned int c0 = blockIdx.x * blockDim.x; c0 < nc; c0 += gridDim.x * blockDim.x) {
-		const unsigned int ci = c0 + threadIdx.x;
-		const bool hit = ci < nc && d.verdict[ci] != 0;
 		const unsigned int slot = warp_append(d.hit_count, hit);
-		if (hit) d.hits[slot] = ci;
+		if (hit) {
+			d.hits[slot] = ci;
+			V3* o = d.simplex + (size_t)slot * 4;
+			o[0] = s.a; o[1] = s.b; o[2] = s.c; o[3] = s.d;
+		}
 	}
 }
 
-// EPA (epa.cpp:118) for every hit, refill loop over its iterations. The polytope lives in the lane's local memory; the
-// two hulls' vertices are staged in shared memory as in k_gjk (EPA only ever asks for support points).
+// EPA (epa.cpp:118) for every hit, one thread per hit. The polytope lives in the thread's local memory; the two hulls'
+// vertices are staged in shared memory as in k_gjk (EPA only ever asks for support points). Kept apart from
+// k_manifold: lanes leave EPA after different numbers of iterations, and the kernel boundary is what brings a warp
+// back together before the clipping code.
 __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) {
 	const unsigned int nh = *d.hit_count;
 	__shared__ double s_stage[RP_GJK_STAGE * RP_EPA_THREADS];
-	WarpQueue q;
-	q.init(nh);
-	bool have = false;
-	unsigned int hi = 0;
-	int w = 0, iter = 0, st = 0;
 	EpaScratch e;
-	Shape A, B;
-	A.type = B.type = SHAPE_SPHERE; A.nv = B.nv = 0;
-	for (;;) {
-		const unsigned int got = q.take(!have);
-		if (got != 0xffffffffu) {
-			hi = got;
-			const unsigned int ci = d.hits[hi];
-			const uint2 cd = d.cands[ci];
-			w = (int)cd.x;
-			const PairRec pr = d.pairs[(size_t)w * d.max_pairs + cd.y];
-			const V3* tv = d.tv + (size_t)w * d.TV;
-			const V3* tn = d.tn + (size_t)w * d.TN;
-			A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
-			B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
-			EpaOut out;
-			out.ok = 0; out.pad = 0; out.depth = 0.0; out.normal = v3(0.0, 0.0, 0.0);
-			if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
-				out.ok = sphere_sphere(A, B, &out.normal, &out.depth) ? 1 : 0;
-				d.epa_out[hi] = out;
-			} else {
-				if ((A.nv + B.nv) * 3 <= RP_GJK_STAGE) {
-					double* col = s_stage + threadIdx.x;
-					const int used = stage_shape(A, col, RP_EPA_THREADS, false);
-					stage_shape(B, col + (size_t)used * RP_EPA_THREADS, RP_EPA_THREADS, false);
-				}
-				const V3* sp = d.simplex + (size_t)ci * 4;
-				Simplex s;
-				s.a = sp[0]; s.b = sp[1]; s.c = sp[2]; s.d = sp[3];
-				s.num = 4;
-				if (epa_begin(s, e, &st) == EPA_FAIL) {
-					d.epa_out[hi] = out;
-					atomicOr(&d.status[w], st);
-					st = 0;
-				} else {
-					iter = 0;
-					have = true;
-				}
+	for (unsigned int hi = blockIdx.x * blockDim.x + threadIdx.x; hi < nh; hi += gridDim.x * blockDim.x) {
+		const uint2 cd = d.cands[d.hits[hi]];
+		const int w = (int)cd.x;
+		const PairRec pr = d.pairs[pidx(d, (int)cd.y, w)];
+		Shape A = dev_shape(d, d.cols[pr.ca], w);
+		Shape B = dev_shape(d, d.cols[pr.cb], w);
+		EpaOut out;
+		out.ok = 0; out.pad = 0; out.depth = 0.0; out.normal = v3(0.0, 0.0, 0.0);
+		int st = 0;
+		if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
+			out.ok = sphere_sphere(A, B, &out.normal, &out.depth) ? 1 : 0;
+		} else {
+			if ((A.nv + B.nv) * 3 <= RP_GJK_STAGE) {
+				double* col = s_stage + threadIdx.x;
+				const int used = stage_shape(A, col, RP_EPA_THREADS, false);
+				stage_shape(B, col + (size_t)used * RP_EPA_THREADS, RP_EPA_THREADS, false);
 			}
+			const V3* sp = d.simplex + (size_t)hi * 4;
+			Simplex s;
+			s.a = sp[0]; s.b = sp[1]; s.c = sp[2]; s.d = sp[3];
+			s.num = 4;
+			out.ok = epa(A, B, s, e, &out.normal, &out.depth, &st, 0) ? 1 : 0;
 		}
-		if (!__any_sync(0xffffffffu, have)) {
-			if (q.empty()) break;
-			continue;
-		}
-		if (have) {
-			int r = epa_step(A, B, e, &st);
-			if (r == EPA_CONTINUE && ++iter >= RP_EPA_MAX_ITERS) {
-				st |= ST_EPA_NO_CONVERGENCE;  // epa.cpp:233
-				r = EPA_FAIL;
-			}
-			if (r != EPA_CONTINUE) {
-				EpaOut out;
-				out.ok = r == EPA_DONE ? 1 : 0;
-				out.pad = 0;
-				out.normal = e.min_normal;
-				out.depth = e.min_dist;
-				d.epa_out[hi] = out;
-				if (st) {
-					atomicOr(&d.status[w], st);
-					st = 0;
-				}
-				have = false;
-			}
-		}
+		d.epa_out[hi] = out;
+		if (st) atomicOr(&d.status[w], st);
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&d.counters[CNT_HITS], (unsigned long long)nh);
 }
@@ -718,14 +607,12 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 			const EpaOut eo = d.epa_out[hi];
 			const uint2 cd = d.cands[d.hits[hi]];
 			w = (int)cd.x; pair = (int)cd.y;
-			const size_t pg = (size_t)w * d.max_pairs + pair;
+			const size_t pg = pidx(d, pair, w);
 			const PairRec pr = d.pairs[pg];
 			int st = 0;
 			if (eo.ok) {
-				const V3* tv = d.tv + (size_t)w * d.TV;
-				const V3* tn = d.tn + (size_t)w * d.TN;
-				Shape A = make_shape(d.pool, d.cols[pr.ca], tv, tn);
-				Shape B = make_shape(d.pool, d.cols[pr.cb], tv, tn);
+				Shape A = dev_shape(d, d.cols[pr.ca], w);
+				Shape B = dev_shape(d, d.cols[pr.cb], w);
 				StageSink sink;
 				sink.stage = sc.stage;
 				sink.n = 0;
@@ -744,11 +631,11 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 					n = d.max_contacts - off;
 					if (n < 0) n = 0;
 				}
-				const BodyDyn& da = d.dyn[(size_t)w * d.NB + pr.a];
-				const BodyDyn& db = d.dyn[(size_t)w * d.NB + pr.b];
+				const DynRef ra = dyn_ref(d, w, pr.a);
+				const DynRef rb = dyn_ref(d, w, pr.b);
 				Body b1, b2;
-				b1.x = ld3(da.x); b1.q = ld4(da.q);
-				b2.x = ld3(db.x); b2.q = ld4(db.q);
+				b1.x = ld3(ra, DF_X); b1.q = ld4(ra, DF_Q);
+				b2.x = ld3(rb, DF_X); b2.q = ld4(rb, DF_Q);
 				Contact* out = d.contacts + (size_t)w * d.max_contacts + off;
 				for (int k = 0; k < n; ++k) {
 					out[k] = make_contact(b1, b2, sc.stage[2 * k], sc.stage[2 * k + 1]);
@@ -794,38 +681,38 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 }
 
 // -------------------------------------------------------------------------------------------------------------- solve
-// Level-major Gauss-Seidel across ALL worlds: launch l runs every constraint of dependency level l, one thread per
-// unit -- the joints of level l of every world, then the (world, pair) items of level l that have contacts this substep
-// (a pair's manifold is a sequential chain on its two bodies and stays in one thread, bodies in registers). Kernel
-// boundaries are the barriers between levels, so the result equals the reference's sequential sweep (pbd.cpp:615-620).
+// Level-major Gauss-Seidel across ALL worlds: launch l runs every constraint of dependency level l -- the joints of
+// level l of every world, then the (world, pair) items of level l that have contacts this substep (a pair's manifold is
+// a sequential chain on its two bodies and stays in one thread, bodies in registers). Kernel boundaries are the barriers
+// between levels, so the result equals the reference's sequential sweep (pbd.cpp:615-620). The contact part is a refill
+// loop (WarpQueue): one trip = one contact of whatever manifold a lane holds, so lanes with short manifolds do not wait
+// for lanes with long ones.
 __global__ void __launch_bounds__(128, RP_MINB_POS) k_pos_level(DevView d, double h, int level, int collisions) {
 	const int nj = level <= d.joint_levels ? d.joint_lptr[level] - d.joint_lptr[level - 1] : 0;
 	const int njw = nj * d.W;
 	int st = 0;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < njw; i += gridDim.x * blockDim.x) {
-		const int w = i / nj;
-		const int u = d.joint_sched[d.joint_lptr[level - 1] + i % nj];
+		const int w = i % d.W;  // lane = world
+		const int u = d.joint_sched[d.joint_lptr[level - 1] + i / d.W];
 		const Joint j = d.joints[u];
-		BodyDyn* dyn = d.dyn + (size_t)w * d.NB;
 		Body b1, b2;
 		load_static(b1, d, j.e1);
 		load_static(b2, d, j.e2);
-		BodyDyn& d1 = dyn[j.e1];
-		BodyDyn& d2 = dyn[j.e2];
-		b1.x = ld3(d1.x); b1.q = ld4(d1.q);
-		b2.x = ld3(d2.x); b2.q = ld4(d2.q);
-		JointLambda lam = d.lambdas[(size_t)w * d.NJ + u];
+		const DynRef r1 = dyn_ref(d, w, j.e1);
+		const DynRef r2 = dyn_ref(d, w, j.e2);
+		b1.x = ld3(r1, DF_X); b1.q = ld4(r1, DF_Q);
+		b2.x = ld3(r2, DF_X); b2.q = ld4(r2, DF_Q);
+		JointLambda lam = d.lambdas[(size_t)u * d.WS + w];
 		solve_joint(j, lam, b1, b2, h, &st);
-		d.lambdas[(size_t)w * d.NJ + u] = lam;
-		if (!b1.fixed) { st3(d1.x, b1.x); st4(d1.q, b1.q); }
-		if (!b2.fixed) { st3(d2.x, b2.x); st4(d2.q, b2.q); }
+		d.lambdas[(size_t)u * d.WS + w] = lam;
+		if (!b1.fixed) { st3(r1, DF_X, b1.x); st4(r1, DF_Q, b1.q); }
+		if (!b2.fixed) { st3(r2, DF_X, b2.x); st4(r2, DF_Q, b2.q); }
 		if (st) {
 			atomicOr(&d.status[w], st);
 			st = 0;
 		}
 	}
 	if (!collisions) return;
-	// contacts: refill loop, one trip = one contact of whatever manifold a lane holds (see WarpQueue)
 	const int npf = d.lvl_fill[(size_t)level * RP_LVL_STRIDE];
 	const int np = npf + d.lvl_fill[(size_t)level * RP_LVL_STRIDE + 1];
 	const int off0 = d.lvl_off[level], off1 = d.lvl_off[level + 1];
@@ -834,8 +721,8 @@ __global__ void __launch_bounds__(128, RP_MINB_POS) k_pos_level(DevView d, doubl
 	bool have = false;
 	int w = 0, cnt = 0, c = 0;
 	Contact* cs = 0;
-	BodyDyn* d1 = 0;
-	BodyDyn* d2 = 0;
+	DynRef r1, r2;
+	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
 	V3 normal = v3(0.0, 0.0, 0.0);
 	Body b1, b2;
 	b1.fixed = b2.fixed = 1;
@@ -845,17 +732,17 @@ __global__ void __launch_bounds__(128, RP_MINB_POS) k_pos_level(DevView d, doubl
 			const int k = (int)got;
 			const uint2 item = d.lvl_items[k < npf ? off0 + k : off1 - 1 - (k - npf)];
 			w = (int)item.x;
-			const size_t pg = (size_t)w * d.max_pairs + item.y;
+			const size_t pg = pidx(d, (int)item.y, w);
 			cnt = d.pair_ccnt[pg];
 			const PairRec pr = d.pairs[pg];
 			normal = d.pair_normal[pg];
 			cs = d.contacts + (size_t)w * d.max_contacts + d.pair_coff[pg];
 			load_static(b1, d, pr.a);
 			load_static(b2, d, pr.b);
-			d1 = d.dyn + (size_t)w * d.NB + pr.a;
-			d2 = d.dyn + (size_t)w * d.NB + pr.b;
-			b1.x = ld3(d1->x); b1.q = ld4(d1->q); b1.px = ld3(d1->px); b1.pq = ld4(d1->pq);
-			b2.x = ld3(d2->x); b2.q = ld4(d2->q); b2.px = ld3(d2->px); b2.pq = ld4(d2->pq);
+			r1 = dyn_ref(d, w, pr.a);
+			r2 = dyn_ref(d, w, pr.b);
+			b1.x = ld3(r1, DF_X); b1.q = ld4(r1, DF_Q); b1.px = ld3(r1, DF_PX); b1.pq = ld4(r1, DF_PQ);
+			b2.x = ld3(r2, DF_X); b2.q = ld4(r2, DF_Q); b2.px = ld3(r2, DF_PX); b2.pq = ld4(r2, DF_PQ);
 			c = 0;
 			have = cnt > 0;
 		}
@@ -869,8 +756,8 @@ __global__ void __launch_bounds__(128, RP_MINB_POS) k_pos_level(DevView d, doubl
 			cs[c].lambda_n = ct.lambda_n;
 			cs[c].lambda_t = ct.lambda_t;
 			if (++c == cnt) {
-				if (!b1.fixed) { st3(d1->x, b1.x); st4(d1->q, b1.q); }
-				if (!b2.fixed) { st3(d2->x, b2.x); st4(d2->q, b2.q); }
+				if (!b1.fixed) { st3(r1, DF_X, b1.x); st4(r1, DF_Q, b1.q); }
+				if (!b2.fixed) { st3(r2, DF_X, b2.x); st4(r2, DF_Q, b2.q); }
 				if (st) {
 					atomicOr(&d.status[w], st);
 					st = 0;
@@ -881,20 +768,42 @@ __global__ void __launch_bounds__(128, RP_MINB_POS) k_pos_level(DevView d, doubl
 	}
 }
 
-// velocity derivation (pbd.cpp:623-643), one thread per body
+// velocity derivation (pbd.cpp:623-643), one thread per body, for the bodies whose velocities are still pending at the
+// end of the frame (not touched by a velocity-level unit of the last substep). Derivation is a pure function of the
+// body's own (x, q, prev x, prev q, v, w), none of which the velocity pass writes before deriving, so WHEN it happens
+// between the positional sweep and the first read of v/w does not change a bit.
 __global__ void __launch_bounds__(128) k_derive(DevView d, double h) {
-	const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (gid >= (size_t)d.W * d.NB) return;
-	const int b = (int)(gid % d.NB);
+	const int w = blockIdx.y * blockDim.x + threadIdx.x;
+	const int b = blockIdx.x;
+	if (w >= d.W) return;
+	const int epoch = *d.epoch;
+	// every body leaves the frame stamped "current" (a body that wakes up next frame must not look pending)
+	if (d.vstamp[bidx(d, b, w)] == epoch) return;
+	d.vstamp[bidx(d, b, w)] = epoch;
 	Body body;
 	body.fixed = d.bstat[b].fixed;
-	body.active = d.active[gid];
+	body.active = d.active[bidx(d, b, w)];
 	if (body.fixed || !body.active) return;
-	BodyDyn& dd = d.dyn[gid];
-	body.x = ld3(dd.x); body.q = ld4(dd.q); body.px = ld3(dd.px); body.pq = ld4(dd.pq);
-	body.v = ld3(dd.v); body.w = ld3(dd.w);
+	const DynRef r = dyn_ref(d, w, b);
+	body.x = ld3(r, DF_X); body.q = ld4(r, DF_Q); body.px = ld3(r, DF_PX); body.pq = ld4(r, DF_PQ);
+	body.v = ld3(r, DF_V); body.w = ld3(r, DF_W);
 	derive_velocity(body, h);
-	st3(dd.v, body.v); st3(dd.w, body.w); st3(dd.pv, body.pv); st3(dd.pw, body.pw);
+	st3(r, DF_V, body.v); st3(r, DF_W, body.w); st3(r, DF_PV, body.pv); st3(r, DF_PW, body.pw);
+}
+
+// Loads what the velocity pass needs of one body. If the body's velocities have not been derived in this substep yet
+// (first velocity-level unit that touches it), derives them here (pbd.cpp:623-643) and returns true: the caller then
+// also stores the prev-velocities and stamps the body.
+__device__ __forceinline__ bool load_for_velocity(Body& b, const DynRef& r, int active, int stamp, int epoch, double h) {
+	b.q = ld4(r, DF_Q); b.v = ld3(r, DF_V); b.w = ld3(r, DF_W);
+	b.active = active;
+	if (!(b.fixed || !b.active) && stamp != epoch) {
+		b.x = ld3(r, DF_X); b.px = ld3(r, DF_PX); b.pq = ld4(r, DF_PQ);
+		derive_velocity(b, h);
+		return true;
+	}
+	b.pv = ld3(r, DF_PV); b.pw = ld3(r, DF_PW);
+	return false;
 }
 
 // velocity pass over the contacts of one level (pbd.cpp:646-711); the hinge branch of the reference's velocity pass is
@@ -908,8 +817,12 @@ __global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, doubl
 	bool have = false;
 	int cnt = 0, c = 0;
 	const Contact* cs = 0;
-	BodyDyn* d1 = 0;
-	BodyDyn* d2 = 0;
+	DynRef r1, r2;
+	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
+	int* stamp1 = 0;
+	int* stamp2 = 0;
+	bool fresh1 = false, fresh2 = false;
+	const int epoch = *d.epoch;
 	V3 normal = v3(0.0, 0.0, 0.0);
 	Body b1, b2;
 	b1.fixed = b2.fixed = 1;
@@ -919,17 +832,19 @@ __global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, doubl
 			const int k = (int)got;
 			const uint2 item = d.lvl_items[k < npf ? off0 + k : off1 - 1 - (k - npf)];
 			const int w = (int)item.x;
-			const size_t pg = (size_t)w * d.max_pairs + item.y;
+			const size_t pg = pidx(d, (int)item.y, w);
 			cnt = d.pair_ccnt[pg];
 			const PairRec pr = d.pairs[pg];
 			normal = d.pair_normal[pg];
 			cs = d.contacts + (size_t)w * d.max_contacts + d.pair_coff[pg];
 			load_static(b1, d, pr.a);
 			load_static(b2, d, pr.b);
-			d1 = d.dyn + (size_t)w * d.NB + pr.a;
-			d2 = d.dyn + (size_t)w * d.NB + pr.b;
-			b1.q = ld4(d1->q); b1.v = ld3(d1->v); b1.w = ld3(d1->w); b1.pv = ld3(d1->pv); b1.pw = ld3(d1->pw);
-			b2.q = ld4(d2->q); b2.v = ld3(d2->v); b2.w = ld3(d2->w); b2.pv = ld3(d2->pv); b2.pw = ld3(d2->pw);
+			r1 = dyn_ref(d, w, pr.a);
+			r2 = dyn_ref(d, w, pr.b);
+			stamp1 = d.vstamp + bidx(d, pr.a, w);
+			stamp2 = d.vstamp + bidx(d, pr.b, w);
+			fresh1 = load_for_velocity(b1, r1, d.active[bidx(d, pr.a, w)], *stamp1, epoch, h);
+			fresh2 = load_for_velocity(b2, r2, d.active[bidx(d, pr.b, w)], *stamp2, epoch, h);
 			c = 0;
 			have = cnt > 0;
 		}
@@ -941,8 +856,10 @@ __global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, doubl
 			const Contact ct = cs[c];
 			solve_contact_velocity(ct, normal, b1, b2, h);
 			if (++c == cnt) {
-				if (!b1.fixed) { st3(d1->v, b1.v); st3(d1->w, b1.w); }
-				if (!b2.fixed) { st3(d2->v, b2.v); st3(d2->w, b2.w); }
+				if (!b1.fixed) { st3(r1, DF_V, b1.v); st3(r1, DF_W, b1.w); }
+				if (!b2.fixed) { st3(r2, DF_V, b2.v); st3(r2, DF_W, b2.w); }
+				if (fresh1) { st3(r1, DF_PV, b1.pv); st3(r1, DF_PW, b1.pw); *stamp1 = epoch; }
+				if (fresh2) { st3(r2, DF_PV, b2.pv); st3(r2, DF_PW, b2.pw); *stamp2 = epoch; }
 				have = false;
 			}
 		}
@@ -971,30 +888,37 @@ __global__ void __launch_bounds__(256) k_fp64_probe(double* out, int iters, doub
 __global__ void k_count_frame(DevView d) { atomicAdd(&d.counters[CNT_FRAMES], 1ull); }
 
 // -------------------------------------------------------------------------------------------------- state pack/unpack
-// host record (rawphys_b200.h RP_STATE_STRIDE = 21 doubles) <-> BodyDyn + active + deactivation time
+// host record (rawphys_b200.h RP_STATE_STRIDE = 21 doubles, [world][body]) <-> world-minor dynamic state + active +
+// deactivation time. Thread = (world, body) with lane = world: the device side is coalesced, the record side strided.
 __global__ void __launch_bounds__(128) k_unpack_state(DevView d, const double* rec, int first_world, int n_worlds, int broadcast) {
-	const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (gid >= (size_t)n_worlds * d.NB) return;
-	const int wl = (int)(gid / d.NB), b = (int)(gid % d.NB);
-	const double* r = rec + (broadcast ? (size_t)b : gid) * 21;
-	const size_t o = (size_t)(first_world + wl) * d.NB + b;
-	BodyDyn& dd = d.dyn[o];
-	for (int k = 0; k < 3; ++k) { dd.x[k] = r[k]; dd.v[k] = r[7 + k]; dd.w[k] = r[10 + k]; dd.pv[k] = r[15 + k]; dd.pw[k] = r[18 + k]; dd.px[k] = r[k]; }
-	for (int k = 0; k < 4; ++k) { dd.q[k] = r[3 + k]; dd.pq[k] = r[3 + k]; }
-	d.active[o] = r[13] != 0.0 ? 1 : 0;
-	d.deact[o] = r[14];
+	const int wl = blockIdx.y * blockDim.x + threadIdx.x;
+	const int b = blockIdx.x;
+	if (wl >= n_worlds) return;
+	const double* r = rec + (broadcast ? (size_t)b : (size_t)wl * d.NB + b) * 21;
+	const int w = first_world + wl;
+	const DynRef o = dyn_ref(d, w, b);
+	st3(o, DF_X, v3(r[0], r[1], r[2])); st4(o, DF_Q, q4(r[3], r[4], r[5], r[6]));
+	st3(o, DF_V, v3(r[7], r[8], r[9])); st3(o, DF_W, v3(r[10], r[11], r[12]));
+	st3(o, DF_PX, v3(r[0], r[1], r[2])); st4(o, DF_PQ, q4(r[3], r[4], r[5], r[6]));
+	st3(o, DF_PV, v3(r[15], r[16], r[17])); st3(o, DF_PW, v3(r[18], r[19], r[20]));
+	d.active[bidx(d, b, w)] = r[13] != 0.0 ? 1 : 0;
+	d.deact[bidx(d, b, w)] = r[14];
+	d.vstamp[bidx(d, b, w)] = *d.epoch;  // uploaded velocities are current
 }
 __global__ void __launch_bounds__(128) k_pack_state(DevView d, double* rec, int first_world, int n_worlds) {
-	const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (gid >= (size_t)n_worlds * d.NB) return;
-	const int wl = (int)(gid / d.NB), b = (int)(gid % d.NB);
-	double* r = rec + gid * 21;
-	const size_t o = (size_t)(first_world + wl) * d.NB + b;
-	const BodyDyn& dd = d.dyn[o];
-	for (int k = 0; k < 3; ++k) { r[k] = dd.x[k]; r[7 + k] = dd.v[k]; r[10 + k] = dd.w[k]; r[15 + k] = dd.pv[k]; r[18 + k] = dd.pw[k]; }
-	for (int k = 0; k < 4; ++k) r[3 + k] = dd.q[k];
-	r[13] = d.active[o] ? 1.0 : 0.0;
-	r[14] = d.deact[o];
+	const int wl = blockIdx.y * blockDim.x + threadIdx.x;
+	const int b = blockIdx.x;
+	if (wl >= n_worlds) return;
+	double* r = rec + ((size_t)wl * d.NB + b) * 21;
+	const int w = first_world + wl;
+	const DynRef o = dyn_ref(d, w, b);
+	const V3 x = ld3(o, DF_X), v = ld3(o, DF_V), om = ld3(o, DF_W), pv = ld3(o, DF_PV), pw = ld3(o, DF_PW);
+	const Q4 q = ld4(o, DF_Q);
+	r[0] = x.x; r[1] = x.y; r[2] = x.z; r[3] = q.x; r[4] = q.y; r[5] = q.z; r[6] = q.w;
+	r[7] = v.x; r[8] = v.y; r[9] = v.z; r[10] = om.x; r[11] = om.y; r[12] = om.z;
+	r[13] = d.active[bidx(d, b, w)] ? 1.0 : 0.0;
+	r[14] = d.deact[bidx(d, b, w)];
+	r[15] = pv.x; r[16] = pv.y; r[17] = pv.z; r[18] = pw.x; r[19] = pw.y; r[20] = pw.z;
 }
 
 }  // namespace rp

@@ -381,7 +381,7 @@ RP_HD bool clip_edge(const ClipPlane& pl, float offset, V3 start, V3 end, V3* ou
 	float ab_p = (float)dot(pl.normal, ab);
 	if (fabs((double)ab_p) > 0.000001) {
 		V3 p_co = scale((double)(-offset), pl.normal);
-		float fac = (float)(-dot(pl.normal, sub(start, p_co)) / (double)ab_p);
+		float fac = (float)fdiv(-dot(pl.normal, sub(start, p_co)), (double)ab_p);
 		fac = (float)RP_MINF(RP_MAXF((double)fac, 0.0), 1.0);
 		*out = add(start, scale((double)fac, ab));
 		return true;
@@ -449,8 +449,8 @@ RP_HD bool clip_skew_lines(V3 p1, V3 d1, V3 p2, V3 d2, V3* l1, V3* l2) {
 	double r1 = -d1.x * p2.x + d1.x * p1.x - d1.y * p2.y + d1.y * p1.y - d1.z * p2.z + d1.z * p1.z;
 	double r2 = -d2.x * p2.x + d2.x * p1.x - d2.y * p2.y + d2.y * p1.y - d2.z * p2.z + d2.z * p1.z;
 	if ((n1 * m2) - (n2 * m1) == 0) return false;
-	double n = ((r1 * m2) - (r2 * m1)) / ((n1 * m2) - (n2 * m1));
-	double m = ((n1 * r2) - (n2 * r1)) / ((n1 * m2) - (n2 * m1));
+	double n = fdiv((r1 * m2) - (r2 * m1), (n1 * m2) - (n2 * m1));
+	double m = fdiv((n1 * r2) - (n2 * r1), (n1 * m2) - (n2 * m1));
 	*l1 = add(p1, scale(m, d1));
 	*l2 = add(p2, scale(n, d2));
 	return true;

@@ -100,7 +100,7 @@ RP_HD double pos_delta_lambda(const PosPre& p, const Body& b1, const Body& b2, d
 	double w1 = inv_mass_along(b1, p.r1, p.ii1, n);
 	double w2 = inv_mass_along(b2, p.r2, p.ii2, n);
 	if (!(w1 + w2 != 0.0)) *status |= ST_SOLVER_SINGULAR;  // the reference asserts
-	double til = compliance / (h * h);
+	double til = fdiv(compliance, h * h);
 	return (-c - til * lambda) / (w1 + w2 + til);
 }
 
@@ -147,7 +147,7 @@ RP_HD double ang_delta_lambda(const AngPre& a, double h, double compliance, doub
 	double w1 = dot(n, mul(a.ii1, n));
 	double w2 = dot(n, mul(a.ii2, n));
 	if (!(w1 + w2 != 0.0)) *status |= ST_SOLVER_SINGULAR;
-	double til = compliance / (h * h);
+	double til = fdiv(compliance, h * h);
 	return (-theta - til * lambda) / (w1 + w2 + til);
 }
 // angular_constraint_apply (pbd_base_constraints.cpp:164-227)
@@ -214,7 +214,7 @@ RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, do
 	V3 vt = sub(v, scale(vn, n));
 	V3 dv = v3(0.0, 0.0, 0.0);
 	double mu = (b1.mu_d + b2.mu_d) / 2.0;
-	double fn = c.lambda_n / h;
+	double fn = fdiv(c.lambda_n, h);
 	double fact = RP_MINF(mu * fabs(fn), length(vt));
 	dv = add(dv, scale(-fact, normalize(vt)));
 	V3 vtil = sub(add(b1.pv, cross(b1.pw, p.r1)), add(b2.pv, cross(b2.pw, p.r2)));
