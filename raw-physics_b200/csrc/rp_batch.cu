@@ -436,7 +436,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.pair_normal, SP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.pair_coff, SP))) return rc;
 	if ((rc = dev_alloc(b, &d.pair_ccnt, SP))) return rc;
-	if ((rc = dev_alloc(b, &d.contacts, W * d.max_contacts, false))) return rc;
+	if ((rc = dev_alloc(b, &d.contacts, WS * d.max_contacts * 8, false))) return rc;
 	if ((rc = dev_alloc(b, &d.n_contacts, W))) return rc;
 	if ((rc = dev_alloc(b, &d.lambdas, WS * std::max(d.NJ, 1)))) return rc;
 	if ((rc = dev_alloc(b, &d.status, W))) return rc;
@@ -498,6 +498,12 @@ static int flush_forces(rp_batch* b) {
 	return RP_OK;
 }
 
+static void launch_schedule(rp_batch* b, int collisions) {
+	const DevView& d = b->d;
+	const size_t smem = (size_t)d.NB * 32 * sizeof(int);
+	if (smem <= 48 * 1024) k_schedule<true><<<(d.W + 31) / 32, 32, smem, b->stream>>>(d, collisions);
+	else k_schedule<false><<<(d.W + 31) / 32, 32, 0, b->stream>>>(d, collisions);
+}
 static void launch_broad(rp_batch* b) {
 	const DevView& d = b->d;
 	const dim3 rows((d.NB + 7) / 8, d.WS / 32), blk(32, 8);
@@ -512,7 +518,7 @@ static void enqueue_prologue(rp_batch* b, double dt, int collisions) {
 	launch_broad(b);
 	k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
 	k_level_reset<<<1, 256, 0, b->stream>>>(d);
-	k_schedule<<<(d.W + 63) / 64, 64, 0, b->stream>>>(d, collisions);
+	launch_schedule(b, collisions);
 	k_level_offsets<<<1, 1, 0, b->stream>>>(d);
 }
 
@@ -839,7 +845,7 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 		k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
 		if ((rc = mark(RP_K_ISLANDS))) return rc;
 		k_level_reset<<<1, 256, 0, b->stream>>>(d);
-		k_schedule<<<(d.W + 63) / 64, 64, 0, b->stream>>>(d, collisions ? 1 : 0);
+		launch_schedule(b, collisions ? 1 : 0);
 		k_level_offsets<<<1, 1, 0, b->stream>>>(d);
 		if ((rc = mark(RP_K_SCHEDULE))) return rc;
 		RP_CUDA(cudaMemcpyAsync(b->levels_host, d.lvl_max, sizeof(int), cudaMemcpyDeviceToHost, b->stream));

@@ -92,7 +92,7 @@ struct DevView {
 	V3* pair_normal;     // [max_pairs][WS]
 	int* pair_coff;      // [max_pairs][WS]
 	int* pair_ccnt;      // [max_pairs][WS]
-	Contact* contacts;   // [W][max_contacts] (world-major records: a manifold's contacts are walked by one thread)
+	double* contacts;    // [max_contacts][8][WS] contact records (r1_lc, r2_lc, lambda_n, lambda_t), see contact_ptr
 	int* n_contacts;     // [W]
 	JointLambda* lambdas;  // [NJ][WS]
 	int* status;         // [W]

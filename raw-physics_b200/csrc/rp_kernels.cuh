@@ -68,6 +68,21 @@ __device__ __forceinline__ void st3(const DynRef& r, int f, V3 v) { r.p[f * r.s]
 __device__ __forceinline__ void st4(const DynRef& r, int f, Q4 q) {
 	r.p[f * r.s] = q.x; r.p[(f + 1) * r.s] = q.y; r.p[(f + 2) * r.s] = q.z; r.p[(f + 3) * r.s] = q.w;
 }
+// contact record (r1_lc, r2_lc, lambda_n, lambda_t) of slot k of a world: component f at p[(k * 8 + f) * WS]
+__device__ __forceinline__ double* contact_ptr(const DevView& d, int w, int slot) { return d.contacts + (size_t)slot * 8 * d.WS + w; }
+__device__ __forceinline__ Contact ld_contact(const double* p, size_t S) {
+	Contact c;
+	c.r1_lc = v3(p[0], p[S], p[2 * S]);
+	c.r2_lc = v3(p[3 * S], p[4 * S], p[5 * S]);
+	c.lambda_n = p[6 * S];
+	c.lambda_t = p[7 * S];
+	return c;
+}
+__device__ __forceinline__ void st_contact(double* p, size_t S, const Contact& c) {
+	p[0] = c.r1_lc.x; p[S] = c.r1_lc.y; p[2 * S] = c.r1_lc.z;
+	p[3 * S] = c.r2_lc.x; p[4 * S] = c.r2_lc.y; p[5 * S] = c.r2_lc.z;
+	p[6 * S] = c.lambda_n; p[7 * S] = c.lambda_t;
+}
 __device__ __forceinline__ size_t bidx(const DevView& d, int b, int w) { return (size_t)b * d.WS + w; }  // per-body arrays
 __device__ __forceinline__ size_t pidx(const DevView& d, int p, int w) { return (size_t)p * d.WS + w; }  // per-pair arrays
 
@@ -250,16 +265,21 @@ __global__ void __launch_bounds__(256) k_islands(DevView d, double dt) {
 // the recurrence over one world's pairs (one thread per world, once per frame; all its arrays are world-minor, so the
 // 32 worlds of a warp read consecutive words) and adds the world's per-level pair counts to the global capacities of
 // the level-major work lists.
-__global__ void __launch_bounds__(64) k_schedule(DevView d, int collisions) {
+// SMEM: the per-body "level of the last unit that touched me" table of the CTA's 32 worlds lives in shared memory
+// ([NB][32] ints; the recurrence is a chain of dependent reads of it), else in the world-minor global scratch.
+template <bool SMEM>
+__global__ void __launch_bounds__(32) k_schedule(DevView d, int collisions) {
+	extern __shared__ int s_last[];
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= d.W) return;
-	int* last = d.last_level + w;      // [NB][WS]
+	int* last = SMEM ? s_last + threadIdx.x : d.last_level + w;  // [NB][32] or [NB][WS]
+	const size_t LS = SMEM ? 32 : (size_t)d.WS;
 	int* plevel = d.pair_level + w;    // [max_pairs][WS]
 	int* hist = d.lvl_hist + w;        // [max_levels + 2][WS]
 	const int* active = d.active + w;  // [NB][WS]
 	const size_t S = d.WS;
 	const int np = collisions ? d.n_pairs[w] : 0;
-	for (int b = 0; b < d.NB; ++b) last[b * S] = d.joint_last[b];
+	for (int b = 0; b < d.NB; ++b) last[b * LS] = d.joint_last[b];
 	int nl = d.joint_levels;
 	for (int p = 0; p < np; ++p) {
 		const PairRec pr = d.pairs[pidx(d, p, w)];
@@ -270,10 +290,10 @@ __global__ void __launch_bounds__(64) k_schedule(DevView d, int collisions) {
 			plevel[p * S] = 0;
 			continue;
 		}
-		const int la = fa ? 0 : last[a * S], lb = fb ? 0 : last[b * S];
+		const int la = fa ? 0 : last[a * LS], lb = fb ? 0 : last[b * LS];
 		const int lvl = 1 + (la > lb ? la : lb);
-		if (!fa) last[a * S] = lvl;
-		if (!fb) last[b * S] = lvl;
+		if (!fa) last[a * LS] = lvl;
+		if (!fb) last[b * LS] = lvl;
 		plevel[p * S] = lvl;
 		if (lvl > nl) nl = lvl;
 	}
@@ -636,9 +656,8 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 				Body b1, b2;
 				b1.x = ld3(ra, DF_X); b1.q = ld4(ra, DF_Q);
 				b2.x = ld3(rb, DF_X); b2.q = ld4(rb, DF_Q);
-				Contact* out = d.contacts + (size_t)w * d.max_contacts + off;
 				for (int k = 0; k < n; ++k) {
-					out[k] = make_contact(b1, b2, sc.stage[2 * k], sc.stage[2 * k + 1]);
+					st_contact(contact_ptr(d, w, off + k), d.WS, make_contact(b1, b2, sc.stage[2 * k], sc.stage[2 * k + 1]));
 					if (w == d.dbg_world) {
 						d.dbg_points[2 * (off + k)] = sc.stage[2 * k];
 						d.dbg_points[2 * (off + k) + 1] = sc.stage[2 * k + 1];
@@ -720,7 +739,7 @@ __global__ void __launch_bounds__(128, RP_MINB_POS) k_pos_level(DevView d, doubl
 	q.init((unsigned int)np);
 	bool have = false;
 	int w = 0, cnt = 0, c = 0;
-	Contact* cs = 0;
+	double* cs = 0;
 	DynRef r1, r2;
 	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
 	V3 normal = v3(0.0, 0.0, 0.0);
@@ -736,7 +755,7 @@ __global__ void __launch_bounds__(128, RP_MINB_POS) k_pos_level(DevView d, doubl
 			cnt = d.pair_ccnt[pg];
 			const PairRec pr = d.pairs[pg];
 			normal = d.pair_normal[pg];
-			cs = d.contacts + (size_t)w * d.max_contacts + d.pair_coff[pg];
+			cs = contact_ptr(d, w, d.pair_coff[pg]);
 			load_static(b1, d, pr.a);
 			load_static(b2, d, pr.b);
 			r1 = dyn_ref(d, w, pr.a);
@@ -751,10 +770,11 @@ __global__ void __launch_bounds__(128, RP_MINB_POS) k_pos_level(DevView d, doubl
 			continue;
 		}
 		if (have) {
-			Contact ct = cs[c];
+			double* cp = cs + (size_t)c * 8 * d.WS;
+			Contact ct = ld_contact(cp, d.WS);
 			solve_contact(ct, normal, b1, b2, h, &st);
-			cs[c].lambda_n = ct.lambda_n;
-			cs[c].lambda_t = ct.lambda_t;
+			cp[6 * (size_t)d.WS] = ct.lambda_n;
+			cp[7 * (size_t)d.WS] = ct.lambda_t;
 			if (++c == cnt) {
 				if (!b1.fixed) { st3(r1, DF_X, b1.x); st4(r1, DF_Q, b1.q); }
 				if (!b2.fixed) { st3(r2, DF_X, b2.x); st4(r2, DF_Q, b2.q); }
@@ -816,7 +836,7 @@ __global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, doubl
 	q.init((unsigned int)np);
 	bool have = false;
 	int cnt = 0, c = 0;
-	const Contact* cs = 0;
+	const double* cs = 0;
 	DynRef r1, r2;
 	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
 	int* stamp1 = 0;
@@ -836,7 +856,7 @@ __global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, doubl
 			cnt = d.pair_ccnt[pg];
 			const PairRec pr = d.pairs[pg];
 			normal = d.pair_normal[pg];
-			cs = d.contacts + (size_t)w * d.max_contacts + d.pair_coff[pg];
+			cs = contact_ptr(d, w, d.pair_coff[pg]);
 			load_static(b1, d, pr.a);
 			load_static(b2, d, pr.b);
 			r1 = dyn_ref(d, w, pr.a);
@@ -853,7 +873,7 @@ __global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, doubl
 			continue;
 		}
 		if (have) {
-			const Contact ct = cs[c];
+			const Contact ct = ld_contact(cs + (size_t)c * 8 * d.WS, d.WS);
 			solve_contact_velocity(ct, normal, b1, b2, h);
 			if (++c == cnt) {
 				if (!b1.fixed) { st3(r1, DF_V, b1.v); st3(r1, DF_W, b1.w); }
