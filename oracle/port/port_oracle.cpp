@@ -73,6 +73,7 @@ void sync_bodies(World& w) {  // instantiate per-world state for bodies added si
 		b.inv_mass = bi.inv_mass;
 		b.inertia = bi.inertia; b.inv_inertia = bi.inv_inertia;
 		b.mu_s = bi.mu_s; b.mu_d = bi.mu_d; b.rest = bi.rest;
+		b.ii_bound = tensor_bound(bi.inv_inertia);
 		b.fixed = bi.fixed;
 		b.active = 1;
 		w.bodies.push_back(b);
@@ -526,3 +527,11 @@ uint64_t port_cull_soundness(uint64_t trials, uint64_t seed, uint64_t* separated
 int port_status() { return g->status; }
 
 }
+
+#if defined(RP_COUNT_FRICTION)
+// diagnostics build only (make -C oracle port CXXFLAGS+=-DRP_COUNT_FRICTION): how often the static-friction bound of
+// solve_contact settles the branch, how often the exact evaluation runs, and how often the branch is taken
+extern "C" void port_friction_counts(long out3[3]) {
+	out3[0] = rp::g_friction_skipped; out3[1] = rp::g_friction_evaluated; out3[2] = rp::g_friction_taken;
+}
+#endif

@@ -29,6 +29,8 @@ static int fail(int code, const std::string& msg) {
 		}                                                                                                              \
 	} while (0)
 
+#define RP_SCHED_SMEM_MAX (160 * 1024)  // dynamic shared memory k_schedule<true> may ask for (opted in at batch creation)
+
 struct rp_scene {
 	Scene s;
 };
@@ -318,6 +320,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		b->cull_chunks = std::max(1, std::min(want, most));
 	}
 	RP_CUDA(cudaHostAlloc((void**)&b->levels_host, sizeof(int), cudaHostAllocDefault));
+	RP_CUDA(cudaFuncSetAttribute(k_schedule<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_SCHED_SMEM_MAX));
 
 	// Dependency levels of the external constraints: they head the constraint array (pbd.cpp:580) in every world, so
 	// their part of the schedule is a constant of the template.
@@ -356,6 +359,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		bc.inv_mass = bi.inv_mass;
 		bc.inertia = bi.inertia; bc.inv_inertia = bi.inv_inertia;
 		bc.mu_s = bi.mu_s; bc.mu_d = bi.mu_d; bc.rest = bi.rest;
+		bc.ii_bound = tensor_bound(bi.inv_inertia);
 		int cls = -1;
 		// bitwise comparison (signed zeros and all); scenes have few classes, and the most recent one usually matches
 		for (int k = (int)classes.size() - 1; k >= 0 && k >= (int)classes.size() - 64; --k) {
@@ -500,8 +504,8 @@ static int flush_forces(rp_batch* b) {
 
 static void launch_schedule(rp_batch* b, int collisions) {
 	const DevView& d = b->d;
-	const size_t smem = (size_t)d.NB * 32 * sizeof(int);
-	if (smem <= 48 * 1024) k_schedule<true><<<(d.W + 31) / 32, 32, smem, b->stream>>>(d, collisions);
+	const size_t smem = (size_t)d.NB * 32 * sizeof(int) + RP_SCHED_HIST * 32 * sizeof(int) + (size_t)d.NB * 32;
+	if (smem <= RP_SCHED_SMEM_MAX) k_schedule<true><<<(d.W + 31) / 32, 32, smem, b->stream>>>(d, collisions);
 	else k_schedule<false><<<(d.W + 31) / 32, 32, 0, b->stream>>>(d, collisions);
 }
 static void launch_broad(rp_batch* b) {

@@ -22,6 +22,7 @@ struct BodyClass {
 	double inv_mass;
 	M3 inertia, inv_inertia;
 	double mu_s, mu_d, rest;
+	double ii_bound;   // tensor_bound(inv_inertia), see solve_contact
 };
 // per-body static parameters, shared by all worlds (template)
 struct BodyStatic {

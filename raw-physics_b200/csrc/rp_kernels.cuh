@@ -12,7 +12,7 @@
 
 // occupancy knobs (min resident CTAs per SM handed to __launch_bounds__); tuned on B200, see profiles/
 #ifndef RP_MINB_INTEGRATE
-#define RP_MINB_INTEGRATE 4
+#define RP_MINB_INTEGRATE 6
 #endif
 #ifndef RP_MINB_GJK
 #define RP_MINB_GJK 8
@@ -21,7 +21,7 @@
 #define RP_MINB_MANIFOLD 4
 #endif
 #ifndef RP_MINB_EPA
-#define RP_MINB_EPA 8
+#define RP_MINB_EPA 6
 #endif
 #ifndef RP_MINB_POS
 #define RP_MINB_POS 2
@@ -93,6 +93,7 @@ __device__ __forceinline__ void load_static(Body& b, const DevView& d, int body)
 	b.inertia = c.inertia;
 	b.inv_inertia = c.inv_inertia;
 	b.mu_s = c.mu_s; b.mu_d = c.mu_d; b.rest = c.rest;
+	b.ii_bound = c.ii_bound;
 	b.fixed = s.fixed;
 }
 
@@ -137,9 +138,16 @@ __global__ void __launch_bounds__(256) k_broad_rows(DevView d) {
 	int out = WRITE ? d.row_off[(size_t)w * d.NB + i] : 0;
 	for (int j = i + 1; j < d.NB; ++j) {
 		const V3 xj = v3(X[((size_t)j * RP_DYN_DOUBLES + 0) * S], X[((size_t)j * RP_DYN_DOUBLES + 1) * S], X[((size_t)j * RP_DYN_DOUBLES + 2) * S]);
-		const double dist = length(sub(xi, xj));
+		// broad.cpp:19-20 compares sqrt(|xi - xj|^2) with ri + rj + 0.1. Squared distances outside a 4e-12 relative band
+		// around maxd^2 decide the comparison without the square root (sqrt is monotonic and both roundings are 1e-16
+		// effects); inside the band the reference's expression is evaluated as written.
+		const V3 dv = sub(xi, xj);
+		const double d2 = dv.x * dv.x + dv.y * dv.y + dv.z * dv.z;
 		const double maxd = ri + d.bstat[j].radius + 0.1;
-		if (dist <= maxd) {
+		const double m2 = maxd * maxd;
+		bool near = d2 < m2 * (1.0 - 4e-12);
+		if (!near && !(d2 > m2 * (1.0 + 4e-12))) near = sqrt(d2) <= maxd;
+		if (near) {
 			const int ncj = d.bstat[j].ncol;
 			if (WRITE) {
 				const int cj0 = d.bstat[j].col0;
@@ -265,28 +273,52 @@ __global__ void __launch_bounds__(256) k_islands(DevView d, double dt) {
 // the recurrence over one world's pairs (one thread per world, once per frame; all its arrays are world-minor, so the
 // 32 worlds of a warp read consecutive words) and adds the world's per-level pair counts to the global capacities of
 // the level-major work lists.
-// SMEM: the per-body "level of the last unit that touched me" table of the CTA's 32 worlds lives in shared memory
-// ([NB][32] ints; the recurrence is a chain of dependent reads of it), else in the world-minor global scratch.
+// SMEM: the tables the recurrence reads in a dependent chain live in shared memory for the CTA's 32 worlds -- per body
+// the level of the last unit that touched it ([NB][32] ints) and its "takes part" flags (fixed / active, [NB][32]
+// bytes), and the per-world level histogram ([RP_SCHED_HIST][32] ints) -- so an iteration's only global access is the
+// (coalesced, prefetchable) pair record. Scenes too large for that use the world-minor global scratch.
+#define RP_SCHED_HIST 64
 template <bool SMEM>
 __global__ void __launch_bounds__(32) k_schedule(DevView d, int collisions) {
-	extern __shared__ int s_last[];
+	extern __shared__ int s_sched[];
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
-	if (w >= d.W) return;
-	int* last = SMEM ? s_last + threadIdx.x : d.last_level + w;  // [NB][32] or [NB][WS]
-	const size_t LS = SMEM ? 32 : (size_t)d.WS;
-	int* plevel = d.pair_level + w;    // [max_pairs][WS]
-	int* hist = d.lvl_hist + w;        // [max_levels + 2][WS]
-	const int* active = d.active + w;  // [NB][WS]
+	const bool live = w < d.W;
 	const size_t S = d.WS;
-	const int np = collisions ? d.n_pairs[w] : 0;
-	for (int b = 0; b < d.NB; ++b) last[b * LS] = d.joint_last[b];
+	int* last = SMEM ? s_sched + threadIdx.x : d.last_level + (live ? w : 0);  // [NB][32] or [NB][WS]
+	const size_t LS = SMEM ? 32 : S;
+	int* s_hist = s_sched + (size_t)d.NB * 32 + threadIdx.x;                     // [RP_SCHED_HIST][32] (SMEM only)
+	unsigned char* s_flag = (unsigned char*)(s_sched + (size_t)d.NB * 32 + RP_SCHED_HIST * 32) + threadIdx.x;  // [NB][32] (SMEM only)
+	int* plevel = d.pair_level + (live ? w : 0);    // [max_pairs][WS]
+	int* hist = d.lvl_hist + (live ? w : 0);        // [max_levels + 2][WS]
+	const int* active = d.active + (live ? w : 0);  // [NB][WS]
+	const int np = (collisions && live) ? d.n_pairs[w] : 0;
+	// flag bit 0: fixed, bit 1: fixed or asleep (pbd.cpp:594)
+	for (int b = 0; b < d.NB; ++b) {
+		if (SMEM || live) last[b * LS] = d.joint_last[b];
+		if (SMEM) {
+			const int f = d.bstat[b].fixed;
+			s_flag[b * 32] = (unsigned char)((f ? 1 : 0) | ((f || !(live && active[b * S])) ? 2 : 0));
+		}
+	}
+	if (SMEM) {
+		for (int l = 0; l < RP_SCHED_HIST; ++l) s_hist[l * 32] = 0;
+	}
 	int nl = d.joint_levels;
+	int deep = 0;  // pairs scheduled at levels >= RP_SCHED_HIST (counted through the global histogram)
+#pragma unroll 4
 	for (int p = 0; p < np; ++p) {
 		const PairRec pr = d.pairs[pidx(d, p, w)];
 		const int a = pr.a, b = pr.b;
-		const int fa = d.bstat[a].fixed, fb = d.bstat[b].fixed;
+		int fa, fb, sa, sb;
+		if (SMEM) {
+			const int ga = s_flag[a * 32], gb = s_flag[b * 32];
+			fa = ga & 1; fb = gb & 1; sa = ga & 2; sb = gb & 2;
+		} else {
+			fa = d.bstat[a].fixed; fb = d.bstat[b].fixed;
+			sa = fa || !active[a * S]; sb = fb || !active[b * S];
+		}
 		// pbd.cpp:594: nothing to do when both sides are fixed or asleep
-		if ((fa || !active[a * S]) && (fb || !active[b * S])) {
+		if (sa && sb) {
 			plevel[p * S] = 0;
 			continue;
 		}
@@ -296,15 +328,32 @@ __global__ void __launch_bounds__(32) k_schedule(DevView d, int collisions) {
 		if (!fb) last[b * LS] = lvl;
 		plevel[p * S] = lvl;
 		if (lvl > nl) nl = lvl;
+		if (SMEM) {
+			if (lvl < RP_SCHED_HIST) s_hist[lvl * 32] += 1;
+			else ++deep;
+		}
 	}
-	for (int l = 0; l <= nl + 1; ++l) hist[l * S] = 0;
-	for (int p = 0; p < np; ++p) hist[plevel[p * S] * S] += 1;
-	for (int l = 1; l <= nl; ++l) {
-		const int c = hist[l * S];
-		if (c) atomicAdd(&d.lvl_cap[l], c);
+	// per-level pair counts of the warp's 32 worlds -> one atomic per (warp, level): per-thread atomics on the handful of
+	// lvl_cap words serialise (4096 worlds x 14 levels on 14 addresses cost 0.6 ms per frame)
+	int nl_warp = live ? nl : 0;
+	for (int o = 16; o > 0; o >>= 1) nl_warp = max(nl_warp, __shfl_xor_sync(0xffffffffu, nl_warp, o));
+	const int deep_any = __any_sync(0xffffffffu, deep != 0);
+	const bool use_smem_hist = SMEM && !deep_any;
+	if (!use_smem_hist && live) {
+		for (int l = 0; l <= nl + 1; ++l) hist[l * S] = 0;
+		for (int p = 0; p < np; ++p) hist[plevel[p * S] * S] += 1;
 	}
-	atomicMax(d.lvl_max, nl);
-	atomicAdd(&d.counters[CNT_LEVELS], (unsigned long long)nl);
+	for (int l = 1; l <= nl_warp; ++l) {
+		int c = 0;
+		if (live && l <= nl) c = use_smem_hist ? s_hist[l * 32] : hist[l * S];
+		c = __reduce_add_sync(0xffffffffu, c);
+		if (threadIdx.x == 0 && c) atomicAdd(&d.lvl_cap[l], c);
+	}
+	const int nl_sum = __reduce_add_sync(0xffffffffu, live ? nl : 0);
+	if (threadIdx.x == 0) {
+		atomicMax(d.lvl_max, nl_warp);
+		atomicAdd(&d.counters[CNT_LEVELS], (unsigned long long)nl_sum);
+	}
 }
 
 // zeroes the per-frame level capacities (before k_schedule) / turns them into list offsets (after it)
@@ -542,8 +591,10 @@ __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) 
 					double* col = s_stage + threadIdx.x;
 					const int used = stage_shape(A, col, RP_GJK_THREADS, false);
 					stage_shape(B, col + (size_t)used * RP_GJK_THREADS, RP_GJK_THREADS, false);
+					hit = gjk(StagedShape<RP_GJK_THREADS>(A), StagedShape<RP_GJK_THREADS>(B), &s, &st, 0);
+				} else {
+					hit = gjk(A, B, &s, &st, 0);
 				}
-				hit = gjk(A, B, &s, &st, 0);
 			}
 			if (st) atomicOr(&d.status[w], st);
 		}
@@ -576,16 +627,18 @@ __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) 
 		if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
 			out.ok = sphere_sphere(A, B, &out.normal, &out.depth) ? 1 : 0;
 		} else {
-			if ((A.nv + B.nv) * 3 <= RP_GJK_STAGE) {
-				double* col = s_stage + threadIdx.x;
-				const int used = stage_shape(A, col, RP_EPA_THREADS, false);
-				stage_shape(B, col + (size_t)used * RP_EPA_THREADS, RP_EPA_THREADS, false);
-			}
 			const V3* sp = d.simplex + (size_t)hi * 4;
 			Simplex s;
 			s.a = sp[0]; s.b = sp[1]; s.c = sp[2]; s.d = sp[3];
 			s.num = 4;
-			out.ok = epa(A, B, s, e, &out.normal, &out.depth, &st, 0) ? 1 : 0;
+			if ((A.nv + B.nv) * 3 <= RP_GJK_STAGE) {
+				double* col = s_stage + threadIdx.x;
+				const int used = stage_shape(A, col, RP_EPA_THREADS, false);
+				stage_shape(B, col + (size_t)used * RP_EPA_THREADS, RP_EPA_THREADS, false);
+				out.ok = epa(StagedShape<RP_EPA_THREADS>(A), StagedShape<RP_EPA_THREADS>(B), s, e, &out.normal, &out.depth, &st, 0) ? 1 : 0;
+			} else {
+				out.ok = epa(A, B, s, e, &out.normal, &out.depth, &st, 0) ? 1 : 0;
+			}
 		}
 		d.epa_out[hi] = out;
 		if (st) atomicOr(&d.status[w], st);
@@ -842,6 +895,8 @@ __global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, doubl
 	int* stamp1 = 0;
 	int* stamp2 = 0;
 	bool fresh1 = false, fresh2 = false;
+	AngPre tens;
+	tens.ii1 = tens.ii2 = zero_m3();
 	const int epoch = *d.epoch;
 	V3 normal = v3(0.0, 0.0, 0.0);
 	Body b1, b2;
@@ -865,6 +920,7 @@ __global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, doubl
 			stamp2 = d.vstamp + bidx(d, pr.b, w);
 			fresh1 = load_for_velocity(b1, r1, d.active[bidx(d, pr.a, w)], *stamp1, epoch, h);
 			fresh2 = load_for_velocity(b2, r2, d.active[bidx(d, pr.b, w)], *stamp2, epoch, h);
+			tens = vel_tensors(b1, b2);
 			c = 0;
 			have = cnt > 0;
 		}
@@ -874,7 +930,7 @@ __global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, doubl
 		}
 		if (have) {
 			const Contact ct = ld_contact(cs + (size_t)c * 8 * d.WS, d.WS);
-			solve_contact_velocity(ct, normal, b1, b2, h);
+			solve_contact_velocity(ct, normal, b1, b2, h, tens);
 			if (++c == cnt) {
 				if (!b1.fixed) { st3(r1, DF_V, b1.v); st3(r1, DF_W, b1.w); }
 				if (!b2.fixed) { st3(r2, DF_V, b2.v); st3(r2, DF_W, b2.w); }

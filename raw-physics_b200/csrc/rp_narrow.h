@@ -154,14 +154,16 @@ RP_HD bool gjk_do_simplex(Simplex* s, V3* dir) {
 // gjk_step one trip of it.
 enum { GJK_CONTINUE = 0, GJK_HIT = 1, GJK_MISS = 2 };
 
-RP_HD void gjk_begin(const Shape& A, const Shape& B, Simplex* s, V3* dir) {
+template <class SA, class SB>
+RP_HD void gjk_begin(const SA& A, const SB& B, Simplex* s, V3* dir) {
 	s->a = support_minkowski(A, B, v3(0.0, 0.0, 1.0));
 	s->b = s->c = s->d = v3(0.0, 0.0, 0.0);
 	s->num = 1;
 	*dir = scale(-1.0, s->a);
 }
 
-RP_HD int gjk_step(const Shape& A, const Shape& B, Simplex* s, V3* dir, int* status) {
+template <class SA, class SB>
+RP_HD int gjk_step(const SA& A, const SB& B, Simplex* s, V3* dir, int* status) {
 	V3 p = support_minkowski(A, B, *dir);
 	if (dot(p, *dir) < 0.0) return GJK_MISS;
 	// add_to_simplex (gjk.cpp:7-30)
@@ -181,7 +183,8 @@ RP_HD int gjk_step(const Shape& A, const Shape& B, Simplex* s, V3* dir, int* sta
 }
 
 // `iters` (optional) receives the number of support iterations, for statistics.
-RP_HD bool gjk(const Shape& A, const Shape& B, Simplex* out, int* status, int* iters) {
+template <class SA, class SB>
+RP_HD bool gjk(const SA& A, const SB& B, Simplex* out, int* status, int* iters) {
 	Simplex s;
 	V3 dir;
 	gjk_begin(A, B, &s, &dir);
@@ -291,7 +294,8 @@ RP_HD int epa_begin(const Simplex& s, EpaScratch& e, int* status) {
 	return EPA_CONTINUE;
 }
 
-RP_HD int epa_step(const Shape& A, const Shape& B, EpaScratch& e, int* status) {
+template <class SA, class SB>
+RP_HD int epa_step(const SA& A, const SB& B, EpaScratch& e, int* status) {
 	const V3 min_normal = e.min_normal;
 	V3 sp = support_minkowski(A, B, min_normal);
 	double d = dot(min_normal, sp);
@@ -343,7 +347,8 @@ RP_HD int epa_step(const Shape& A, const Shape& B, EpaScratch& e, int* status) {
 	return EPA_CONTINUE;
 }
 
-RP_HD bool epa(const Shape& A, const Shape& B, const Simplex& s, EpaScratch& e, V3* normal_out, double* depth_out, int* status,
+template <class SA, class SB>
+RP_HD bool epa(const SA& A, const SB& B, const Simplex& s, EpaScratch& e, V3* normal_out, double* depth_out, int* status,
 	int* iters) {
 	if (epa_begin(s, e, status) == EPA_FAIL) return false;
 	for (int it = 0; it < RP_EPA_MAX_ITERS; ++it) {

@@ -84,6 +84,20 @@ RP_HD V3 vert(const Shape& s, int i) {
 	const double* p = s.vp + (size_t)i * s.vs;
 	return v3(p[0], p[s.vcs], p[2 * s.vcs]);
 }
+// A shape whose vertices were staged into a thread-interleaved block of NT columns (k_gjk / k_epa): the strides are
+// compile-time constants, so an unrolled support scan addresses the vertices with immediate offsets instead of
+// recomputing 64-bit addresses per vertex (ncu, round 1: address arithmetic and loads were half of k_gjk's
+// instructions). The routines that only need vertices are templates over the shape type for this.
+template <int NT>
+struct StagedShape : Shape {
+	RP_HD StagedShape() {}
+	RP_HD explicit StagedShape(const Shape& s) : Shape(s) {}
+};
+template <int NT>
+RP_HD V3 vert(const StagedShape<NT>& s, int i) {
+	const double* p = s.vp + i * (3 * NT);
+	return v3(p[0], p[NT], p[2 * NT]);
+}
 RP_HD V3 fnormal(const Shape& s, int i) {
 	const double* p = s.np + (size_t)i * s.ns;
 	return v3(p[0], p[s.ncs], p[2 * s.ncs]);
@@ -125,9 +139,11 @@ RP_HD V3 transform_normal(const Pose34& M, V3 n) {
 }
 
 // support_point_get_index (support.cpp:5-17): first maximum wins (strict >), starting from -DBL_MAX
-RP_HD int support_index(const Shape& s, V3 d) {
+template <class S>
+RP_HD int support_index(const S& s, V3 d) {
 	int best = 0;
 	double best_dot = -1.7976931348623157e308;
+#pragma unroll 4
 	for (int i = 0; i < s.nv; ++i) {
 		double t = dot(vert(s, i), d);
 		if (t > best_dot) {
@@ -138,12 +154,14 @@ RP_HD int support_index(const Shape& s, V3 d) {
 	return best;
 }
 // support_point (support.cpp:19-32)
-RP_HD V3 support(const Shape& s, V3 d) {
+template <class S>
+RP_HD V3 support(const S& s, V3 d) {
 	if (s.type == SHAPE_HULL) return vert(s, support_index(s, d));
 	return add(s.center, scale((double)s.radius, normalize(d)));
 }
 // support_point_of_minkowski_difference (support.cpp:34-39)
-RP_HD V3 support_minkowski(const Shape& a, const Shape& b, V3 d) {
+template <class SA, class SB>
+RP_HD V3 support_minkowski(const SA& a, const SB& b, V3 d) {
 	V3 s1 = support(a, d);
 	V3 s2 = support(b, scale(-1.0, d));
 	return sub(s1, s2);

@@ -22,8 +22,19 @@ struct Body {
 	double inv_mass;
 	M3 inertia, inv_inertia;  // body-frame tensors (entity.h:32-33)
 	double mu_s, mu_d, rest;
+	double ii_bound;     // an upper bound of the largest eigenvalue of inv_inertia (its infinity norm; tensor_bound)
 	int fixed, active;
 };
+
+// infinity norm of a symmetric (or any) 3x3 tensor: >= its spectral radius
+RP_HD double tensor_bound(const M3& a) {
+	double best = 0.0;
+	for (int i = 0; i < 3; ++i) {
+		double row = fabs(a.m[i][0]) + fabs(a.m[i][1]) + fabs(a.m[i][2]);
+		if (row > best) best = row;
+	}
+	return best;
+}
 
 // ------------------------------------------------------------------------------------------------------- integration
 // pbd.cpp:537-577 for one body. `force`/`torque` are the sums of calculate_external_force/torque (physics_util.cpp:5-23).
@@ -176,6 +187,9 @@ RP_HD Contact make_contact(const Body& b1, const Body& b2, V3 p1, V3 p2) {
 	return c;
 }
 
+#if defined(RP_COUNT_FRICTION) && !defined(__CUDA_ARCH__)
+static long g_friction_skipped = 0, g_friction_taken = 0, g_friction_evaluated = 0;  // diagnostics build of the port only
+#endif
 // collision_constraint_solve (pbd.cpp:107-154), incl. quirk q1 (static friction reuses the normal correction vector)
 RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, int* status) {
 	PosPre p = pos_pre(b1, b2, c.r1_lc, c.r2_lc);
@@ -188,6 +202,34 @@ RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, in
 		pos_apply(p, b1, b2, dl, dx);
 		c.lambda_n += dl;
 
+		// The rest of the routine only acts if lambda_t + dl_t > mu * lambda_n (pbd.cpp:138), with
+		// dl_t = -|dx| / (w1' + w2') evaluated at the corrected poses (contacts have zero compliance). By quirk q1 dl_t
+		// is of the size of the normal step, so for mu < 1 the test practically always fails -- after a second round of
+		// world-space tensors. It is decided without them whenever a bound already settles it: w_i' = 1/m_i +
+		// (r_i' x n)^T I_i'^-1 (r_i' x n) <= 1/m_i + |r_i|^2 lmax(I_i^-1) =: W_i (rotations keep |r_i| and the
+		// eigenvalues, |n| = 1), hence lambda_t + dl_t <= lambda_t - |dx| / (W_1 + W_2); if that is below mu * lambda_n by
+		// more than `margin` -- a millionth of the magnitudes involved, nine orders of magnitude above the rounding
+		// error of either side -- the floating-point test cannot come out true, and nothing else in the skipped code
+		// has an effect (lambda_t and the bodies are only written inside the branch).
+		{
+			const double wub = (b1.fixed ? 0.0 : b1.inv_mass + dot(c.r1_lc, c.r1_lc) * b1.ii_bound) +
+			                   (b2.fixed ? 0.0 : b2.inv_mass + dot(c.r2_lc, c.r2_lc) * b2.ii_bound);
+			const double mu_ln = ((b1.mu_s + b2.mu_s) / 2.0) * c.lambda_n;
+			if (wub > 0.0) {
+				const double step = length(dx) / wub;
+				const double margin = 1e-6 * (fabs(c.lambda_t) + step + fabs(mu_ln));
+				if (c.lambda_t - step + margin < mu_ln) {
+#if defined(RP_COUNT_FRICTION) && !defined(__CUDA_ARCH__)
+					++g_friction_skipped;
+#endif
+					return;
+				}
+			}
+		}
+
+#if defined(RP_COUNT_FRICTION) && !defined(__CUDA_ARCH__)
+		++g_friction_evaluated;
+#endif
 		p = pos_pre(b1, b2, c.r1_lc, c.r2_lc);
 		p1 = add(b1.x, p.r1);
 		p2 = add(b2.x, p.r2);
@@ -202,13 +244,25 @@ RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, in
 			V3 dpt = sub(dp, scale(dot(dp, normal), normal));
 			pos_apply(p, b1, b2, dl, dpt);
 			c.lambda_t += dl;
+#if defined(RP_COUNT_FRICTION) && !defined(__CUDA_ARCH__)
+			++g_friction_taken;
+#endif
 		}
 	}
 }
 
-// velocity solve for one contact (pbd.cpp:648-711)
-RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, double h) {
-	PosPre p = pos_pre(b1, b2, c.r1_lc, c.r2_lc);
+// velocity solve for one contact (pbd.cpp:648-711). The world-space inverse inertia tensors of the preprocessed data
+// depend on the orientations only, and the velocity pass never writes an orientation: a caller that walks several
+// contacts of one body pair computes them once (vel_tensors) and passes them in; the reference recomputes the same
+// values per contact (pbd.cpp:651).
+RP_HD AngPre vel_tensors(const Body& b1, const Body& b2) { return ang_pre(b1, b2); }
+
+RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, double h, const AngPre& t) {
+	PosPre p;
+	p.r1 = rotate(b1.q, c.r1_lc);
+	p.r2 = rotate(b2.q, c.r2_lc);
+	p.ii1 = t.ii1;
+	p.ii2 = t.ii2;
 	V3 v = sub(add(b1.v, cross(b1.w, p.r1)), add(b2.v, cross(b2.w, p.r2)));
 	double vn = dot(n, v);
 	V3 vt = sub(v, scale(vn, n));
@@ -233,6 +287,9 @@ RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, do
 		b2.v = add(b2.v, zero_minus(scale(b2.inv_mass, imp)));
 		b2.w = add(b2.w, zero_minus(mul(p.ii2, cross(p.r2, imp))));
 	}
+}
+RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, double h) {
+	solve_contact_velocity(c, n, b1, b2, h, vel_tensors(b1, b2));
 }
 
 // -------------------------------------------------------------------------------------------------------------- joints
