@@ -70,6 +70,19 @@ int rp_scene_collider_sphere(rp_scene* s, float radius);
 int rp_scene_add_body(rp_scene* s, const double position[3], const double rotation_xyzw[4], double mass, int fixed,
 	double static_friction, double dynamic_friction, double restitution);
 
+/* Adoption of objects the reference has ALREADY built (what the pbd_simulate shim does, raw-physics_b200/shim/pbd_b200.cpp):
+ * a Collider_Convex_Hull as it lies in memory (src/physics/collider.h:19-29: vertices, faces[].elements / .normal,
+ * vertex_to_faces, vertex_to_neighbors, face_to_neighbors) as CSR arrays (ptr arrays have count + 1 entries), queued for
+ * the next body like rp_scene_collider_hull; and an Entity's derived parameters (src/entity.h:27-40: inverse_mass,
+ * inertia_tensor, inverse_inertia_tensor row-major, bounding_sphere_radius, fixed, coefficients) taken as they are
+ * instead of being recomputed by entity_create_ex. Return the collider index / body id, or -1. */
+int rp_scene_collider_hull_topology(rp_scene* s, const double* vertices_xyz, uint32_t n_vertices, const double* face_normals_xyz,
+	uint32_t n_faces, const uint32_t* face_ptr, const uint32_t* face_idx, const uint32_t* v2f_ptr, const uint32_t* v2f_idx,
+	const uint32_t* v2n_ptr, const uint32_t* v2n_idx, const uint32_t* f2n_ptr, const uint32_t* f2n_idx);
+int rp_scene_add_body_params(rp_scene* s, const double position[3], const double rotation_xyzw[4], double inverse_mass,
+	const double inertia[9], const double inverse_inertia[9], double bounding_sphere_radius, int fixed, double static_friction,
+	double dynamic_friction, double restitution);
+
 /* pbd_positional_constraint_init ... pbd_spherical_joint_constraint_init (pbd.cpp:18-79); return the constraint index */
 int rp_scene_add_positional_constraint(rp_scene* s, int e1, int e2, const double r1_lc[3], const double r2_lc[3], double compliance,
 	const double distance[3]);
@@ -135,7 +148,9 @@ int rp_batch_broadcast_state(rp_batch* b, const double* host_state_one_world);
 int rp_batch_step_host(rp_batch* b, const double* host_state_in, double* host_state_out, double dt, uint32_t num_substeps,
 	uint32_t num_pos_iters, int enable_collisions);
 
+/* status words accumulate (bitwise or) from batch creation or the last rp_batch_clear_status */
 int rp_batch_get_status(rp_batch* b, int32_t* status_per_world);
+int rp_batch_clear_status(rp_batch* b);
 /* cumulative work counters since creation: [0] narrowphase collider-pair tests, [1] GJK hits (EPA runs),
  * [2] contacts, [3] broadphase pairs (per frame, summed), [4] solver levels (per frame, summed), [5] frames */
 int rp_batch_get_counters(rp_batch* b, uint64_t out8[8]);

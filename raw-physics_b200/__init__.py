@@ -25,12 +25,12 @@ _u64p = C.POINTER(C.c_uint64)
 # every symbol include/rawphys_b200.h declares (tests check the library exports each one)
 EXPORTS = [
     "rp_last_error", "rp_device_count", "rp_scene_create", "rp_scene_destroy", "rp_scene_collider_hull", "rp_scene_collider_sphere",
-    "rp_scene_add_body", "rp_scene_add_positional_constraint", "rp_scene_add_mutual_orientation_constraint",
+    "rp_scene_add_body", "rp_scene_collider_hull_topology", "rp_scene_add_body_params", "rp_scene_add_positional_constraint", "rp_scene_add_mutual_orientation_constraint",
     "rp_scene_add_hinge_joint_constraint", "rp_scene_add_spherical_joint_constraint", "rp_scene_num_bodies", "rp_scene_get_params",
     "rp_scene_hull_sizes", "rp_scene_hull_dump", "rp_batch_cfg_default", "rp_batch_create", "rp_batch_destroy", "rp_batch_num_worlds",
     "rp_batch_num_bodies", "rp_batch_clear_forces", "rp_batch_add_force", "rp_batch_add_gravity", "rp_batch_step", "rp_batch_sync",
     "rp_batch_run", "rp_batch_upload_state", "rp_batch_download_state", "rp_batch_broadcast_state", "rp_batch_step_host",
-    "rp_batch_get_status", "rp_batch_get_counters", "rp_batch_step_logged", "rp_batch_broad_pairs", "rp_batch_profile",
+    "rp_batch_get_status", "rp_batch_clear_status", "rp_batch_get_counters", "rp_batch_step_logged", "rp_batch_broad_pairs", "rp_batch_profile",
     "rp_measure_fp64_peak",
 ]
 KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "cull", "gjk", "manifold", "solve_pos", "derive", "solve_vel", "epa"]
@@ -61,6 +61,8 @@ def lib():
     L.rp_scene_collider_hull.argtypes = [C.c_void_p, _dp, C.c_uint32, _u32p, C.c_uint32]
     L.rp_scene_collider_sphere.argtypes = [C.c_void_p, C.c_float]
     L.rp_scene_add_body.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double]
+    L.rp_scene_collider_hull_topology.argtypes = [C.c_void_p, _dp, C.c_uint32, _dp, C.c_uint32] + [_u32p] * 8
+    L.rp_scene_add_body_params.argtypes = [C.c_void_p, _dp, _dp, C.c_double, _dp, _dp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double]
     L.rp_scene_add_positional_constraint.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_double, _dp]
     L.rp_scene_add_mutual_orientation_constraint.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
     L.rp_scene_add_hinge_joint_constraint.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_int,
@@ -89,6 +91,7 @@ def lib():
     L.rp_batch_broadcast_state.argtypes = [C.c_void_p, C.c_void_p]
     L.rp_batch_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_int]
     L.rp_batch_get_status.argtypes = [C.c_void_p, _i32p]
+    L.rp_batch_clear_status.argtypes = [C.c_void_p]
     L.rp_batch_get_counters.argtypes = [C.c_void_p, _u64p]
     L.rp_batch_step_logged.argtypes = [C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, _u32p, C.c_uint32, _dp,
                                        C.c_uint32, _u32p, _u32p]

@@ -57,6 +57,7 @@ struct rp_batch {
 	double* rec_dev = 0;  // staging for state records, [W][NB][RP_STATE_STRIDE]
 	int cull_chunks = 1;
 	int sm_count = 148;
+	unsigned int pos_grid = 148, vel_grid = 148;  // resident CTAs of the cooperative sweep kernels
 	int cull = 1;            // exact-safe bounds cull before GJK (rp_batch_cfg.disable_cull turns it off)
 	int* levels_host = 0;    // pinned: deepest dependency level of the current frame
 	std::vector<int> joint_level;  // template-constant levels of the external constraints
@@ -84,6 +85,23 @@ static int dev_upload(rp_batch* b, const T** out, const std::vector<T>& v) {
 	if (!v.empty()) RP_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, b->stream));
 	*out = p;
 	return RP_OK;
+}
+
+// launches `kernel` as a cooperative grid (cg::this_grid().sync() inside); capturable into the frame graph
+template <class... Args>
+static cudaError_t launch_cooperative(void (*kernel)(Args...), unsigned int grid, unsigned int block, cudaStream_t stream, Args... args) {
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.gridDim = dim3(grid);
+	cfg.blockDim = dim3(block);
+	cfg.dynamicSmemBytes = 0;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr;
+	attr.id = cudaLaunchAttributeCooperative;
+	attr.val.cooperative = 1;
+	cfg.attrs = &attr;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 extern "C" {
@@ -117,6 +135,44 @@ int rp_scene_collider_sphere(rp_scene* s, float radius) {
 int rp_scene_add_body(rp_scene* s, const double pos[3], const double quat[4], double mass, int fixed, double mu_s, double mu_d, double rest) {
 	if (!s || !pos || !quat) return -1;
 	return s->s.add_body(pos, quat, mass, fixed, mu_s, mu_d, rest);
+}
+
+static bool csr_ok(const uint32_t* ptr, const uint32_t* idx, uint32_t rows, uint32_t limit) {
+	if (!ptr || ptr[0] != 0) return false;
+	for (uint32_t r = 0; r < rows; ++r) {
+		if (ptr[r + 1] < ptr[r]) return false;
+	}
+	if (ptr[rows] && !idx) return false;
+	for (uint32_t k = 0; k < ptr[rows]; ++k) {
+		if (idx[k] >= limit) return false;
+	}
+	return true;
+}
+static void csr_copy(const uint32_t* ptr, const uint32_t* idx, uint32_t rows, std::vector<int>& optr, std::vector<int>& oidx) {
+	optr.assign(ptr, ptr + rows + 1);
+	oidx.assign(idx, idx + ptr[rows]);
+}
+int rp_scene_collider_hull_topology(rp_scene* s, const double* verts, uint32_t nv, const double* normals, uint32_t nf, const uint32_t* face_ptr,
+	const uint32_t* face_idx, const uint32_t* v2f_ptr, const uint32_t* v2f_idx, const uint32_t* v2n_ptr, const uint32_t* v2n_idx,
+	const uint32_t* f2n_ptr, const uint32_t* f2n_idx) {
+	if (!s || !verts || !normals || nv == 0 || nf == 0) return -1;
+	if (!csr_ok(face_ptr, face_idx, nf, nv) || !csr_ok(v2f_ptr, v2f_idx, nv, nf) || !csr_ok(v2n_ptr, v2n_idx, nv, nv) ||
+		!csr_ok(f2n_ptr, f2n_idx, nf, nf)) return -1;
+	HullHost h;
+	h.verts.resize(nv);
+	h.normals.resize(nf);
+	memcpy(h.verts.data(), verts, sizeof(V3) * nv);
+	memcpy(h.normals.data(), normals, sizeof(V3) * nf);
+	csr_copy(face_ptr, face_idx, nf, h.face_ptr, h.face_idx);
+	csr_copy(v2f_ptr, v2f_idx, nv, h.v2f_ptr, h.v2f_idx);
+	csr_copy(v2n_ptr, v2n_idx, nv, h.v2n_ptr, h.v2n_idx);
+	csr_copy(f2n_ptr, f2n_idx, nf, h.f2n_ptr, h.f2n_idx);
+	return s->s.add_hull_topology(h);
+}
+int rp_scene_add_body_params(rp_scene* s, const double pos[3], const double quat[4], double inverse_mass, const double inertia[9],
+	const double inverse_inertia[9], double radius, int fixed, double mu_s, double mu_d, double rest) {
+	if (!s || !pos || !quat || !inertia || !inverse_inertia) return -1;
+	return s->s.add_body_params(pos, quat, inverse_mass, inertia, inverse_inertia, radius, fixed, mu_s, mu_d, rest);
 }
 
 static bool valid_pair(const rp_scene* s, int e1, int e2) {
@@ -318,6 +374,17 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		int want = (b->sm_count * 16 + groups - 1) / groups;
 		int most = (d.max_pairs + 7) / 8;
 		b->cull_chunks = std::max(1, std::min(want, most));
+	}
+	{
+		int coop = 0, per_sm = 0;
+		RP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+		if (!coop) return fail(RP_ERR_CUDA, "device does not support cooperative launches");
+		RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_pos, 128, 0));
+		if (per_sm < 1) return fail(RP_ERR_CUDA, "k_solve_pos does not fit an SM");
+		b->pos_grid = (unsigned int)(b->sm_count * per_sm);
+		RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_vel, 128, 0));
+		if (per_sm < 1) return fail(RP_ERR_CUDA, "k_solve_vel does not fit an SM");
+		b->vel_grid = (unsigned int)(b->sm_count * per_sm);
 	}
 	RP_CUDA(cudaHostAlloc((void**)&b->levels_host, sizeof(int), cudaHostAllocDefault));
 	RP_CUDA(cudaFuncSetAttribute(k_schedule<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_SCHED_SMEM_MAX));
@@ -537,10 +604,14 @@ static int prologue_levels(rp_batch* b, double dt, int collisions, int* levels) 
 	return RP_OK;
 }
 
-// The level kernels are refill loops over warp-owned chunks (WarpQueue): launch exactly the resident grid so that every
-// lane owns several manifolds.
-static unsigned int pos_grid(const rp_batch* b) { return (unsigned int)b->sm_count * RP_MINB_POS; }
-static unsigned int vel_grid(const rp_batch* b) { return (unsigned int)b->sm_count * RP_MINB_VEL; }
+// The Gauss-Seidel sweeps are cooperative grids (grid-wide barrier between levels) of refill loops over warp-owned chunks
+// (WarpQueue): launch exactly the CTAs that are resident at once (occupancy measured at batch creation).
+static void launch_solve_pos(rp_batch* b, double h, int levels, uint32_t iters, int collisions) {
+	if (levels > 0 && iters > 0) launch_cooperative(k_solve_pos, b->pos_grid, 128u, b->stream, b->d, h, levels, (int)iters, collisions);
+}
+static void launch_solve_vel(rp_batch* b, double h, int levels) {
+	if (levels > 0) launch_cooperative(k_solve_vel, b->vel_grid, 128u, b->stream, b->d, h, levels);
+}
 
 static void enqueue_integrate(rp_batch* b, double h) {
 	const DevView& d = b->d;
@@ -562,15 +633,10 @@ static void enqueue_narrow(rp_batch* b) {
 	launch_manifold(b);
 }
 static void enqueue_solve(rp_batch* b, double h, uint32_t iters, int collisions, int levels) {
-	const DevView& d = b->d;
-	for (uint32_t it = 0; it < iters; ++it) {
-		for (int l = 1; l <= levels; ++l) k_pos_level<<<pos_grid(b), 128, 0, b->stream>>>(d, h, l, collisions);
-	}
+	launch_solve_pos(b, h, levels, iters, collisions);
 	// velocity derivation (pbd.cpp:623-643) is lazy: a body's velocities are derived by the first velocity-level unit
 	// that touches it, else by the next substep's k_integrate, else by k_derive at the end of the frame
-	if (collisions) {
-		for (int l = 1; l <= levels; ++l) k_vel_level<<<vel_grid(b), 128, 0, b->stream>>>(d, h, l);
-	}
+	if (collisions) launch_solve_vel(b, h, levels);
 }
 static void enqueue_frame_end(rp_batch* b, double h) {
 	const DevView& d = b->d;
@@ -695,6 +761,12 @@ int rp_batch_get_status(rp_batch* b, int32_t* out) {
 	RP_CUDA(cudaSetDevice(b->device));
 	RP_CUDA(cudaMemcpyAsync(out, b->d.status, sizeof(int) * b->d.W, cudaMemcpyDeviceToHost, b->stream));
 	RP_CUDA(cudaStreamSynchronize(b->stream));
+	return RP_OK;
+}
+int rp_batch_clear_status(rp_batch* b) {
+	if (!b) return RP_ERR_ARG;
+	RP_CUDA(cudaSetDevice(b->device));
+	RP_CUDA(cudaMemsetAsync(b->d.status, 0, sizeof(int) * b->d.W, b->stream));
 	return RP_OK;
 }
 int rp_batch_get_counters(rp_batch* b, uint64_t out8[8]) {
@@ -869,12 +941,10 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 				k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_MANIFOLD))) return rc;
 			}
-			for (uint32_t it = 0; it < iters; ++it) {
-				for (int l = 1; l <= levels; ++l) k_pos_level<<<pos_grid(b), 128, 0, b->stream>>>(d, h, l, collisions ? 1 : 0);
-			}
+			launch_solve_pos(b, h, levels, iters, collisions ? 1 : 0);
 			if ((rc = mark(RP_K_SOLVE_POS))) return rc;
 			if (collisions) {
-				for (int l = 1; l <= levels; ++l) k_vel_level<<<vel_grid(b), 128, 0, b->stream>>>(d, h, l);
+				launch_solve_vel(b, h, levels);
 				if ((rc = mark(RP_K_SOLVE_VEL))) return rc;
 			}
 		}

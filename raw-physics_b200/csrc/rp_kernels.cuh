@@ -8,6 +8,8 @@
 #ifndef RP_KERNELS_CUH
 #define RP_KERNELS_CUH
 
+#include <cooperative_groups.h>
+
 #include "rp_device.cuh"
 
 // occupancy knobs (min resident CTAs per SM handed to __launch_bounds__); tuned on B200, see profiles/
@@ -41,6 +43,8 @@
 #define RP_SMALL_MANIFOLD 1000000  // (off: the refill loops of the solver kernels make manifold length irrelevant)
 // manifolds of up to this many contacts fill a level list from the front, larger ones from the back
 #endif
+
+namespace cg = cooperative_groups;
 
 namespace rp {
 
@@ -759,8 +763,14 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 // between levels, so the result equals the reference's sequential sweep (pbd.cpp:615-620). The contact part is a refill
 // loop (WarpQueue): one trip = one contact of whatever manifold a lane holds, so lanes with short manifolds do not wait
 // for lanes with long ones.
-__global__ void __launch_bounds__(128, RP_MINB_POS) k_pos_level(DevView d, double h, int level, int collisions) {
-	const int nj = level <= d.joint_levels ? d.joint_lptr[level] - d.joint_lptr[level - 1] : 0;
+//
+// ONE launch runs the whole sweep (k_solve_pos: every level of every positional iteration; k_solve_vel: every level of
+// the velocity pass): a cooperative grid of exactly the resident CTAs walks the levels with a grid-wide barrier between
+// two levels that both have work. Whether a level has work (joints of that level, or lvl_fill > 0 after this substep's
+// k_manifold) is the same for every CTA, so EMPTY levels cost nothing -- no launch, no barrier. In the first second of
+// the north-star window more than half of the scheduled levels hold no contact yet (ncu, frame 40: 6 of 11 level
+// launches ran empty at ~5 us each).
+__device__ __forceinline__ void pos_level(const DevView& d, double h, int level, int nj, int collisions) {
 	const int njw = nj * d.W;
 	int st = 0;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < njw; i += gridDim.x * blockDim.x) {
@@ -841,6 +851,21 @@ __global__ void __launch_bounds__(128, RP_MINB_POS) k_pos_level(DevView d, doubl
 	}
 }
 
+__global__ void __launch_bounds__(128, RP_MINB_POS) k_solve_pos(DevView d, double h, int levels, int iters, int collisions) {
+	cg::grid_group grid = cg::this_grid();
+	bool dirty = false;
+	for (int it = 0; it < iters; ++it) {
+		for (int level = 1; level <= levels; ++level) {
+			const int nj = level <= d.joint_levels ? d.joint_lptr[level] - d.joint_lptr[level - 1] : 0;
+			const int np = collisions ? d.lvl_fill[(size_t)level * RP_LVL_STRIDE] + d.lvl_fill[(size_t)level * RP_LVL_STRIDE + 1] : 0;
+			if (nj == 0 && np == 0) continue;
+			if (dirty) grid.sync();
+			pos_level(d, h, level, nj, collisions);
+			dirty = true;
+		}
+	}
+}
+
 // velocity derivation (pbd.cpp:623-643), one thread per body, for the bodies whose velocities are still pending at the
 // end of the frame (not touched by a velocity-level unit of the last substep). Derivation is a pure function of the
 // body's own (x, q, prev x, prev q, v, w), none of which the velocity pass writes before deriving, so WHEN it happens
@@ -881,7 +906,7 @@ __device__ __forceinline__ bool load_for_velocity(Body& b, const DynRef& r, int 
 
 // velocity pass over the contacts of one level (pbd.cpp:646-711); the hinge branch of the reference's velocity pass is
 // an empty TODO (pbd.cpp:712-739), so joints take no part
-__global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, double h, int level) {
+__device__ __forceinline__ void vel_level(const DevView& d, double h, int level) {
 	const int npf = d.lvl_fill[(size_t)level * RP_LVL_STRIDE];
 	const int np = npf + d.lvl_fill[(size_t)level * RP_LVL_STRIDE + 1];
 	const int off0 = d.lvl_off[level], off1 = d.lvl_off[level + 1];
@@ -939,6 +964,17 @@ __global__ void __launch_bounds__(128, RP_MINB_VEL) k_vel_level(DevView d, doubl
 				have = false;
 			}
 		}
+	}
+}
+
+__global__ void __launch_bounds__(128, RP_MINB_VEL) k_solve_vel(DevView d, double h, int levels) {
+	cg::grid_group grid = cg::this_grid();
+	bool dirty = false;
+	for (int level = 1; level <= levels; ++level) {
+		if (d.lvl_fill[(size_t)level * RP_LVL_STRIDE] + d.lvl_fill[(size_t)level * RP_LVL_STRIDE + 1] == 0) continue;
+		if (dirty) grid.sync();
+		vel_level(d, h, level);
+		dirty = true;
 	}
 }
 

@@ -193,6 +193,32 @@ int Scene::add_hull_collider(const double* vx, uint32_t nverts, const uint32_t* 
 	return (int)pending.size() - 1;
 }
 
+int Scene::add_hull_topology(const HullHost& h) {
+	int id = -1;
+	for (size_t k = 0; k < hulls.size(); ++k) {  // identical topologies share one pool entry
+		const HullHost& o = hulls[k];
+		if (o.verts.size() == h.verts.size() && o.normals.size() == h.normals.size() &&
+			memcmp(o.verts.data(), h.verts.data(), sizeof(V3) * h.verts.size()) == 0 &&
+			memcmp(o.normals.data(), h.normals.data(), sizeof(V3) * h.normals.size()) == 0 && o.face_ptr == h.face_ptr &&
+			o.face_idx == h.face_idx && o.v2f_ptr == h.v2f_ptr && o.v2f_idx == h.v2f_idx && o.v2n_ptr == h.v2n_ptr && o.v2n_idx == h.v2n_idx &&
+			o.f2n_ptr == h.f2n_ptr && o.f2n_idx == h.f2n_idx) {
+			id = (int)k;
+			break;
+		}
+	}
+	if (id < 0) {
+		id = (int)hulls.size();
+		hulls.push_back(h);
+	}
+	ColliderDesc c;
+	c.type = SHAPE_HULL;
+	c.hull = id;
+	c.radius = 0.0f;
+	c.tv0 = c.tn0 = 0;
+	pending.push_back(c);
+	return (int)pending.size() - 1;
+}
+
 int Scene::add_sphere_collider(float radius) {  // collider_sphere_create (collider.cpp:12-18)
 	ColliderDesc c;
 	c.type = SHAPE_SPHERE;
@@ -202,6 +228,8 @@ int Scene::add_sphere_collider(float radius) {  // collider_sphere_create (colli
 	pending.push_back(c);
 	return (int)pending.size() - 1;
 }
+
+static int commit_body(Scene& sc, BodyInit& b);
 
 // entity_create_ex (entity.cpp:24-65)
 int Scene::add_body(const double* pos, const double* quat, double mass, int fixed, double mu_s, double mu_d, double rest) {
@@ -267,6 +295,39 @@ int Scene::add_body(const double* pos, const double* quat, double mass, int fixe
 		}
 		inverse(b.inertia, &b.inv_inertia);
 	}
+	return commit_body(*this, b);
+}
+
+int Scene::add_body_params(const double* pos, const double* quat, double inv_mass, const double* inertia9, const double* inv_inertia9,
+	double radius, int fixed, double mu_s, double mu_d, double rest) {
+	BodyInit b;
+	b.x = v3(pos[0], pos[1], pos[2]);
+	b.q = q4(quat[0], quat[1], quat[2], quat[3]);
+	b.col0 = (int)colliders.size();
+	b.ncol = (int)pending.size();
+	b.fixed = fixed ? 1 : 0;
+	b.mu_s = mu_s; b.mu_d = mu_d; b.rest = rest;
+	b.radius = radius;
+	b.inv_mass = inv_mass;
+	for (int r = 0; r < 3; ++r) {
+		for (int c = 0; c < 3; ++c) {
+			b.inertia.m[r][c] = inertia9[3 * r + c];
+			b.inv_inertia.m[r][c] = inv_inertia9[3 * r + c];
+		}
+	}
+	return commit_body(*this, b);
+}
+
+// moves the queued colliders under the new body and appends it
+static int commit_body(Scene& sc, BodyInit& b) {
+	std::vector<ColliderDesc>& pending = sc.pending;
+	std::vector<ColliderDesc>& colliders = sc.colliders;
+	std::vector<HullHost>& hulls = sc.hulls;
+	int& total_tv = sc.total_tv;
+	int& total_tn = sc.total_tn;
+	std::vector<BodyInit>& bodies = sc.bodies;
+	std::vector<V3>& force = sc.force;
+	std::vector<V3>& torque = sc.torque;
 	for (size_t i = 0; i < pending.size(); ++i) {
 		ColliderDesc c = pending[i];
 		c.tv0 = total_tv;

@@ -43,6 +43,11 @@ struct Scene {
 
 	int add_hull_collider(const double* verts_xyz, uint32_t nverts, const uint32_t* indices, uint32_t nidx);
 	int add_sphere_collider(float radius);
+	// a hull whose topology already exists (Collider_Convex_Hull as the reference holds it, collider.h:19-29): adopted as is
+	int add_hull_topology(const HullHost& h);
+	// an entity whose derived parameters already exist (Entity fields, entity.h:27-40): adopted as they are
+	int add_body_params(const double* pos, const double* quat_xyzw, double inv_mass, const double* inertia9, const double* inv_inertia9,
+		double radius, int fixed, double mu_s, double mu_d, double rest);
 	int add_body(const double* pos, const double* quat_xyzw, double mass, int fixed, double mu_s, double mu_d, double rest);
 	void clear_forces();
 	void add_force(int body, V3 position, V3 f);   // entity_add_force with local_coords = false (entity.cpp:176-193)

@@ -26,7 +26,9 @@ def _u(a):
 def lib_path(flavour="strict"):
     if flavour == "port":
         return os.path.join(ROOT, "oracle", "libport_oracle.so")
-    name = "libref_oracle.so" if flavour == "strict" else "libref_oracle_fastmath.so"
+    # "shim": the reference's own object code for everything except the frame step, whose two entry points are
+    # redirected to raw-physics_b200/shim/pbd_b200.cpp -> librawphys_b200.so (oracle/Makefile `shim`); needs a GPU to step
+    name = {"strict": "libref_oracle.so", "shim": "libref_shim.so"}.get(flavour, "libref_oracle_fastmath.so")
     return os.path.join(ROOT, "oracle", "_ref", name)
 
 

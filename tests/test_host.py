@@ -86,3 +86,45 @@ def test_build_flags_forbid_fma():
     text = open(os.path.join(ROOT, "raw-physics_b200", "build.py")).read()
     assert "--fmad=false" in text and "arch=compute_100a,code=sm_100a" in text and "-lineinfo" in text
     assert "use_fast_math" not in text
+
+
+def test_adopted_topology_and_params_round_trip(pkg):
+    """rp_scene_collider_hull_topology / rp_scene_add_body_params (what the pbd_simulate shim feeds from the reference's
+    own Collider_Convex_Hull / Entity structs) reproduce the template built from the triangle soups, array for array."""
+    import ctypes as C
+    sc = scenes.BUILDERS["coin"]()
+    built = pkg.Scene(sc)
+    params = built.params()
+    L = pkg.lib()
+    dp, up = C.POINTER(C.c_double), C.POINTER(C.c_uint32)
+    adopted = pkg.Scene()
+    for i, b in enumerate(sc.bodies):
+        for c in range(len(b.colliders)):
+            h = built.hull(i, c)
+            if h is None:
+                assert L.rp_scene_collider_sphere(adopted.h, C.c_float(b.colliders[c].radius)) >= 0
+                continue
+            args = [h[k].ctypes.data_as(up) for k in ("face_ptr", "face_idx", "v2f_ptr", "v2f_idx", "v2n_ptr", "v2n_idx", "f2n_ptr", "f2n_idx")]
+            assert L.rp_scene_collider_hull_topology(adopted.h, h["verts"].ctypes.data_as(dp), h["verts"].shape[0],
+                                                     h["normals"].ctypes.data_as(dp), h["normals"].shape[0], *args) >= 0
+        p = params[i]
+        pos = np.asarray(b.position, dtype=np.float64)
+        rot = np.asarray(b.rotation, dtype=np.float64)
+        inertia, inv = np.ascontiguousarray(p[1:10]), np.ascontiguousarray(p[10:19])
+        assert L.rp_scene_add_body_params(adopted.h, pos.ctypes.data_as(dp), rot.ctypes.data_as(dp), p[0], inertia.ctypes.data_as(dp),
+                                          inv.ctypes.data_as(dp), p[19], int(p[23]), p[20], p[21], p[22]) == i
+    assert np.array_equal(adopted.params(), params)
+    for i, b in enumerate(sc.bodies):
+        for c in range(len(b.colliders)):
+            h0, h1 = built.hull(i, c), adopted.hull(i, c)
+            assert (h0 is None) == (h1 is None)
+            if h0 is not None:
+                assert all(np.array_equal(h0[k], h1[k]) for k in h0)
+    # malformed CSR input is refused, not adopted
+    h = built.hull(1, 0)
+    bad = h["face_idx"].copy()
+    bad[0] = 10 ** 6
+    args = [h[k].ctypes.data_as(up) for k in ("face_ptr",)] + [bad.ctypes.data_as(up)] + [
+        h[k].ctypes.data_as(up) for k in ("v2f_ptr", "v2f_idx", "v2n_ptr", "v2n_idx", "f2n_ptr", "f2n_idx")]
+    assert L.rp_scene_collider_hull_topology(adopted.h, h["verts"].ctypes.data_as(dp), h["verts"].shape[0],
+                                             h["normals"].ctypes.data_as(dp), h["normals"].shape[0], *args) == -1
