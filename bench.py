@@ -57,6 +57,16 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu --set full capture
+    (profiles/ncu_traffic.json, written by profiles/summarise_ncu.py from the capture named inside it), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get("kernels", {}).get(kernel)
+    return None if d is None else d["dram_read"] + d["dram_write"]
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -191,6 +201,8 @@ def run_ours(args):
     if world_size > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from rawphys_b200 import multi
+    job = multi.Job(dist, "cuda")  # worlds are sharded over ranks with no data-path collective; NCCL only aggregates
 
     desc = scenes.w256()
     scene = pkg.Scene(desc)
@@ -207,12 +219,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = job.max_over_ranks
 
     if args.ncu_frame >= 0:
         batch.run(max(args.ncu_frame, 1), DT, SUBSTEPS, ITERS, True)
@@ -297,7 +304,7 @@ def run_ours(args):
         if top in alg_bytes:
             gbs = alg_bytes[top] / (fam[top] * 1e-3) / 1e9
             line["roofline"] = {"kernel": "k_" + top, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                                "traffic": None, "peak_source": hbm_src, "avg_launch_ms": fam[top] / launches,
+                                "traffic": ncu_traffic("k_" + top), "peak_source": hbm_src, "avg_launch_ms": fam[top] / launches,
                                 "note": "schema bound; the binding resource of this path is the FP64 CUDA-core pipe, see fp64"}
             tf = alg_flops[top] / (fam[top] * 1e-3) / 1e12
             line["fp64"] = {"kernel": "k_" + top, "achieved_tflops": tf, "peak_tflops_no_fma": fp64_nofma, "peak_tflops_fma": fp64_fma,
@@ -308,9 +315,8 @@ def run_ours(args):
         line["work_per_world_substep"] = {"pair_tests": tests / (W * SUBSTEPS * args.steps), "epa_runs": hits / (W * SUBSTEPS * args.steps),
                                           "contacts": contacts / (W * SUBSTEPS * args.steps)}
         if dist is not None:  # NCCL only gathers aggregate statistics
-            t = torch.tensor([float(tests), float(hits), float(contacts)], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            line["aggregate_work"] = {"pair_tests": t[0].item(), "epa_runs": t[1].item(), "contacts": t[2].item()}
+            t = job.sum_over_ranks([tests, hits, contacts])
+            line["aggregate_work"] = {"pair_tests": float(t[0]), "epa_runs": float(t[1]), "contacts": float(t[2])}
         if args.hetero:
             # The headline workload is BASELINE.json's: 4096 COPIES of one scene, so the lanes of a warp (same pair index,
             # neighbouring worlds) follow the same control flow. This leg breaks that: each cube of each world gets its own
@@ -331,8 +337,11 @@ def run_ours(args):
             hms = max_over_ranks(batch.run(args.steps, DT, SUBSTEPS, ITERS, True))
             barrier()
             c1 = batch.counters()
+            batch.upload(st)
+            hfam = batch.profile(args.steps, DT, SUBSTEPS, ITERS, True)
             line["heterogeneous"] = {"value": units / (hms * 1e-3), "unit": "body-substeps/s", "ms_per_step": hms / args.steps,
                                      "status_bits": int(np.bitwise_or.reduce(batch.status())),
+                                     "kernels_ms": {k: round(v, 1) for k, v in hfam.items()},
                                      "contacts_per_world_substep": (c1["contacts"] - c0["contacts"]) / (W * SUBSTEPS * args.steps),
                                      "note": "every world started from its own poses (per-cube yaw +-0.3 rad, offset +-0.2): no cross-world coherence"}
         if rank == 0 and world_size == 1 and not args.no_cpu:

@@ -52,5 +52,24 @@ def build(force=False, verbose=False, out=None, defines=()):
     return out or OUT
 
 
+HOST_SRC = os.path.join(HERE, "host", "rp_headless.cpp")
+HOST_OUT = os.path.join(HERE, "rp_headless")
+
+
+def build_host(force=False):
+    """The headless driver (host C++ over the C ABI): raw-physics_b200/rp_headless, linked against the library next to it."""
+    deps = [HOST_SRC, OUT, os.path.join(CSRC, "rp_math.h"), os.path.join(os.path.dirname(HERE), "include", "rawphys_b200.h")]
+    if not force and os.path.exists(HOST_OUT) and all(os.path.getmtime(f) <= os.path.getmtime(HOST_OUT) for f in deps):
+        return HOST_OUT
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-o", HOST_OUT, HOST_SRC, "-L" + HERE, "-lrawphys_b200",
+           "-Wl,-rpath,$ORIGIN", "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("building rp_headless failed")
+    return HOST_OUT
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
+    build_host(force="--force" in sys.argv)

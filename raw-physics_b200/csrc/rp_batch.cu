@@ -441,6 +441,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		}
 		o.cls = cls;
 		o.radius = bi.radius;
+		o.rfar = (bi.radius + 0.1) * (1.0 + 1e-9);
 		o.fixed = bi.fixed; o.col0 = bi.col0; o.ncol = bi.ncol;
 		o.tv0 = bi.ncol ? s.colliders[bi.col0].tv0 : 0;
 		o.tn0 = bi.ncol ? s.colliders[bi.col0].tn0 : 0;
@@ -486,7 +487,16 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.tn, WS * std::max(d.TN, 1) * 3))) return rc;
 	if ((rc = dev_alloc(b, &d.pairs, SP))) return rc;
 	if ((rc = dev_alloc(b, &d.n_pairs, W))) return rc;
-	if ((rc = dev_alloc(b, &d.row_off, WB))) return rc;
+	{
+		std::vector<int2> cells;
+		for (int i = 0; i + 1 < d.NB; ++i) {
+			for (int j0 = i + 1; j0 < d.NB; j0 += 32) cells.push_back(make_int2(i, j0));
+		}
+		d.n_cells = (int)cells.size();
+		if ((rc = dev_upload(b, &d.cells, cells))) return rc;
+		if ((rc = dev_alloc(b, &d.cell_mask, WS * std::max(d.n_cells, 1)))) return rc;
+		if ((rc = dev_alloc(b, &d.cell_off, WS * std::max(d.n_cells, 1)))) return rc;
+	}
 	if ((rc = dev_alloc(b, &d.label, WB))) return rc;
 	if ((rc = dev_alloc(b, &d.isl_flag, WB))) return rc;
 	if ((rc = dev_alloc(b, &d.last_level, SB))) return rc;
@@ -577,10 +587,12 @@ static void launch_schedule(rp_batch* b, int collisions) {
 }
 static void launch_broad(rp_batch* b) {
 	const DevView& d = b->d;
-	const dim3 rows((d.NB + 7) / 8, d.WS / 32), blk(32, 8);
-	k_broad_rows<false><<<rows, blk, 0, b->stream>>>(d);
-	k_broad_scan<<<d.W, 256, 0, b->stream>>>(d);
-	k_broad_rows<true><<<rows, blk, 0, b->stream>>>(d);
+	if (d.n_cells > 0) {
+		const dim3 grid((d.n_cells + 7) / 8, d.WS / 32), blk(32, 8);
+		k_broad_cells<<<grid, blk, 0, b->stream>>>(d);
+		k_broad_scan<<<d.WS / 32, dim3(32, RP_BROAD_SEGS), 0, b->stream>>>(d);
+		k_broad_write<<<grid, blk, 0, b->stream>>>(d);
+	}
 }
 
 // the per-frame prologue: broadphase, islands + sleeping, dependency-level schedule (pbd.cpp:474-533)

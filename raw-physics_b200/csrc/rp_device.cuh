@@ -1,7 +1,7 @@
 // rp_device.cuh -- device data model of a batch (n_worlds instances of one scene template in HBM) and the kernels of
 // the XPBD frame step. One launch works on ALL worlds; the per-substep sequence is
 //   k_integrate -> k_gjk -> k_manifold -> k_solve
-// preceded once per frame by k_broad_count / k_broad_scan / k_broad_write / k_islands / k_schedule
+// preceded once per frame by k_broad_cells / k_broad_scan / k_broad_write / k_islands / k_schedule
 // (pbd_simulate_with_constraints, src/physics/pbd.cpp:468-747). See DESIGN.md for the layout and the roofline of each.
 #ifndef RP_DEVICE_CUH
 #define RP_DEVICE_CUH
@@ -27,11 +27,12 @@ struct BodyClass {
 // per-body static parameters, shared by all worlds (template)
 struct BodyStatic {
 	double radius;
+	double rfar;              // (radius + 0.1) * (1 + 1e-9): this body's share of the broadphase's axis-reject threshold
 	int cls;                  // index into DevView::bclass
 	int fixed, col0, ncol;
 	int tv0, tvn, tn0, tnn;   // extent of the body's colliders in a world's transformed vertex / normal arrays
 };
-struct PairRec {  // one broadphase pair, expanded to collider granularity: bodies a < b, global collider indices ca, cb
+struct __align__(16) PairRec {  // one broadphase pair, expanded to collider granularity: bodies a < b, global collider indices ca, cb
 	int a, b, ca, cb;
 };
 struct EpaOut {  // result of EPA (or the analytic sphere-sphere test) for one hit: work item of k_manifold
@@ -65,7 +66,10 @@ struct DevView {
 	double* tn;          // [TN][3][WS] transformed face normals
 	PairRec* pairs;      // [max_pairs][WS]
 	int* n_pairs;        // [W]
-	int* row_off;        // [W][NB] broadphase row counts -> offsets (world-major: scanned by one CTA per world)
+	int n_cells;         // broadphase cells: (row i, 32 consecutive j) pieces of the i < j triangle, in (i, j) order
+	const int2* cells;   // [n_cells] (i, first j), template constant
+	unsigned int* cell_mask;  // [n_cells][WS] bit k = body pair (i, j0 + k) is near
+	int* cell_off;       // [n_cells][WS] collider pairs of the cell -> offset of its first pair in the world's list
 	int* label;          // [W][NB] island labels (world-major scratch of k_islands)
 	int* isl_flag;       // [W][NB] island "all members may sleep"
 	int* last_level;     // [NB][WS] schedule scratch

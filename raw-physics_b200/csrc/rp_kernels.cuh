@@ -127,86 +127,151 @@ __device__ __forceinline__ Shape dev_shape(const DevView& d, const ColliderDesc&
 
 // ------------------------------------------------------------------------------------------------------- broadphase
 // broad_get_collision_pairs (broad.cpp:6-29): all i < j with |x_i - x_j| <= r_i + r_j + 0.1, emitted in (i, j) order.
-// Thread = (world, row i): blockDim = (32 worlds, 8 rows); the lanes of a warp walk j together for 32 worlds.
-template <bool WRITE>
-__global__ void __launch_bounds__(256) k_broad_rows(DevView d) {
+#ifndef RP_BROAD_BATCH
+#define RP_BROAD_BATCH 8
+#endif
+#define RP_BROAD_SEGS 8
+// The (i, j) triangle is cut into CELLS of one row i and up to 32 consecutive j (DevView::cells, in (i, j) order; a
+// constant of the template): one thread per (world, cell), lane = world. A row per thread leaves the rows of big bodies
+// -- the floor pairs with everything -- as 256-step dependent chains that the whole launch waits for; cells are at most 32
+// steps each. Pass 1 leaves a bit mask of the near j of every cell and the number of collider pairs they expand to;
+// k_broad_scan turns the counts into offsets (cell order = pair order); pass 2 expands the masks. Nothing is tested twice.
+__global__ void __launch_bounds__(256) k_broad_cells(DevView d) {
 	const int w = blockIdx.y * 32 + threadIdx.x;
-	const int i = blockIdx.x * blockDim.y + threadIdx.y;
-	if (w >= d.W || i >= d.NB) return;
+	const int c = blockIdx.x * blockDim.y + threadIdx.y;
+	if (w >= d.W || c >= d.n_cells) return;
+	const int2 cell = d.cells[c];
+	const int i = cell.x, j0 = cell.y;
+	const int j1 = j0 + 32 < d.NB ? j0 + 32 : d.NB;
 	const double* X = d.dyn + w;  // x of body j: X[(j * RP_DYN_DOUBLES + c) * WS]
 	const size_t S = d.WS;
-	const V3 xi = v3(X[((size_t)i * RP_DYN_DOUBLES + 0) * S], X[((size_t)i * RP_DYN_DOUBLES + 1) * S], X[((size_t)i * RP_DYN_DOUBLES + 2) * S]);
+	const size_t body_stride = (size_t)RP_DYN_DOUBLES * S;
+	const V3 xi = v3(X[(size_t)i * body_stride], X[(size_t)i * body_stride + S], X[(size_t)i * body_stride + 2 * S]);
 	const double ri = d.bstat[i].radius;
-	const int ci0 = d.bstat[i].col0, nci = d.bstat[i].ncol;
+	const int nci = d.bstat[i].ncol;
+	// Axis rejects first: |x_i - x_j| along one axis already above (r_i + r_j + 0.1)(1 + 1e-9) puts the distance the
+	// reference computes (sqrt of a sum of rounded squares, each term within 3 ulp) above r_i + r_j + 0.1 as well, so the
+	// pair is not emitted -- decided after one load and three FP64 instructions instead of fifteen. The threshold is the
+	// sum of two per-body terms prepared once (BodyStatic::rfar), both rounded up by 1e-9 >> the 1e-16 roundings involved.
+	// Survivors get the reference's own expression below.
+	const double ri_far = ri * (1.0 + 1e-9);
+	unsigned int mask = 0u;
 	int count = 0;
-	int out = WRITE ? d.row_off[(size_t)w * d.NB + i] : 0;
-	for (int j = i + 1; j < d.NB; ++j) {
-		const V3 xj = v3(X[((size_t)j * RP_DYN_DOUBLES + 0) * S], X[((size_t)j * RP_DYN_DOUBLES + 1) * S], X[((size_t)j * RP_DYN_DOUBLES + 2) * S]);
-		// broad.cpp:19-20 compares sqrt(|xi - xj|^2) with ri + rj + 0.1. Squared distances outside a 4e-12 relative band
-		// around maxd^2 decide the comparison without the square root (sqrt is monotonic and both roundings are 1e-16
-		// effects); inside the band the reference's expression is evaluated as written.
-		const V3 dv = sub(xi, xj);
-		const double d2 = dv.x * dv.x + dv.y * dv.y + dv.z * dv.z;
-		const double maxd = ri + d.bstat[j].radius + 0.1;
-		const double m2 = maxd * maxd;
-		bool near = d2 < m2 * (1.0 - 4e-12);
-		if (!near && !(d2 > m2 * (1.0 + 4e-12))) near = sqrt(d2) <= maxd;
-		if (near) {
-			const int ncj = d.bstat[j].ncol;
-			if (WRITE) {
-				const int cj0 = d.bstat[j].col0;
-				for (int a = 0; a < nci; ++a) {
-					for (int b = 0; b < ncj; ++b) {
-						if (out < d.max_pairs) {
-							PairRec pr;
-							pr.a = i; pr.b = j; pr.ca = ci0 + a; pr.cb = cj0 + b;
-							d.pairs[pidx(d, out, w)] = pr;
-						}
-						++out;
-					}
-				}
-			} else {
-				count += nci * ncj;
+	// the x coordinates of RP_BROAD_BATCH bodies are fetched together (independent loads in flight), then looked at in order
+	for (int jb = j0; jb < j1; jb += RP_BROAD_BATCH) {
+		double xs[RP_BROAD_BATCH], thrs[RP_BROAD_BATCH];
+#pragma unroll
+		for (int k = 0; k < RP_BROAD_BATCH; ++k) {
+			const int jj = jb + k < j1 ? jb + k : j1 - 1;
+			xs[k] = X[(size_t)jj * body_stride];
+			thrs[k] = ri_far + d.bstat[jj].rfar;
+		}
+#pragma unroll
+		for (int k = 0; k < RP_BROAD_BATCH; ++k) {
+			const int j = jb + k;
+			if (j >= j1) break;
+			const double thr = thrs[k];
+			const double* xj = X + (size_t)j * body_stride;
+			V3 dv;
+			dv.x = xi.x - xs[k];
+			if (fabs(dv.x) > thr) continue;
+			dv.z = xi.z - xj[2 * S];
+			if (fabs(dv.z) > thr) continue;
+			dv.y = xi.y - xj[S];
+			if (fabs(dv.y) > thr) continue;
+			// broad.cpp:19-20 compares sqrt(|xi - xj|^2) with ri + rj + 0.1. Squared distances outside a 4e-12 relative
+			// band around maxd^2 decide the comparison without the square root (sqrt is monotonic and both roundings are
+			// 1e-16 effects); inside the band the reference's expression is evaluated as written.
+			const double d2 = dv.x * dv.x + dv.y * dv.y + dv.z * dv.z;
+			const double maxd = ri + d.bstat[j].radius + 0.1;
+			const double m2 = maxd * maxd;
+			bool near = d2 < m2 * (1.0 - 4e-12);
+			if (!near && !(d2 > m2 * (1.0 + 4e-12))) near = sqrt(d2) <= maxd;
+			if (near) {
+				mask |= 1u << (j - j0);
+				count += nci * d.bstat[j].ncol;
 			}
 		}
 	}
-	if (!WRITE) d.row_off[(size_t)w * d.NB + i] = count;
+	d.cell_mask[(size_t)c * S + w] = mask;
+	d.cell_off[(size_t)c * S + w] = count;
 }
 
-// exclusive scan of the row counts of one world (one CTA per world; row_off is [W][NB])
-__global__ void __launch_bounds__(256) k_broad_scan(DevView d) {
-	const int w = blockIdx.x;
-	int* row = d.row_off + (size_t)w * d.NB;
-	__shared__ int warp_sums[8];
-	__shared__ int carry;
-	if (threadIdx.x == 0) carry = 0;
-	__syncthreads();
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	for (int base = 0; base < d.NB; base += blockDim.x) {
-		int i = base + threadIdx.x;
-		int v = i < d.NB ? row[i] : 0;
-		int x = v;
-		for (int o = 1; o < 32; o <<= 1) {
-			int y = __shfl_up_sync(0xffffffffu, x, o);
-			if (lane >= o) x += y;
-		}
-		if (lane == 31) warp_sums[wid] = x;
-		__syncthreads();
-		int prefix = carry;
-		for (int k = 0; k < wid; ++k) prefix += warp_sums[k];
-		if (i < d.NB) row[i] = prefix + x - v;
-		__syncthreads();
-		if (threadIdx.x == blockDim.x - 1) carry = prefix + x;
-		__syncthreads();
+// exclusive scan of the cell counts of every world: thread = (world, segment of the cell list); blockDim = (32, RP_BROAD_SEGS)
+__global__ void __launch_bounds__(32 * RP_BROAD_SEGS) k_broad_scan(DevView d) {
+	const int w = blockIdx.x * 32 + threadIdx.x;
+	const int seg = threadIdx.y;
+	const bool live = w < d.W;
+	const size_t S = d.WS;
+	int* off = d.cell_off + (live ? w : 0);
+	const int per = (d.n_cells + RP_BROAD_SEGS - 1) / RP_BROAD_SEGS;
+	const int c0 = seg * per < d.n_cells ? seg * per : d.n_cells;
+	const int c1 = c0 + per < d.n_cells ? c0 + per : d.n_cells;
+	__shared__ int s_sum[RP_BROAD_SEGS][32];
+	int sum = 0;
+	if (live) {
+#pragma unroll 8
+		for (int c = c0; c < c1; ++c) sum += off[(size_t)c * S];
 	}
-	if (threadIdx.x == 0) {
-		int total = carry;
-		if (total > d.max_pairs) {
-			atomicOr(&d.status[w], ST_PAIR_CAPACITY);
-			total = d.max_pairs;
+	s_sum[seg][threadIdx.x] = sum;
+	__syncthreads();
+	int run = 0, total = 0;
+	for (int k = 0; k < RP_BROAD_SEGS; ++k) {
+		if (k < seg) run += s_sum[k][threadIdx.x];
+		total += s_sum[k][threadIdx.x];
+	}
+	if (live) {
+		for (int cb = c0; cb < c1; cb += 8) {
+			int v[8];
+#pragma unroll
+			for (int k = 0; k < 8; ++k) v[k] = cb + k < c1 ? off[(size_t)(cb + k) * S] : 0;
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				if (cb + k < c1) off[(size_t)(cb + k) * S] = run;
+				run += v[k];
+			}
 		}
-		d.n_pairs[w] = total;
-		atomicAdd(&d.counters[CNT_BROAD_PAIRS], (unsigned long long)total);
+		if (seg == 0) {
+			if (total > d.max_pairs) {
+				atomicOr(&d.status[w], ST_PAIR_CAPACITY);
+				total = d.max_pairs;
+			}
+			d.n_pairs[w] = total;
+		}
+	}
+	if (seg == 0) {
+		unsigned long long t = live ? (unsigned long long)total : 0ull;
+		for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+		if (threadIdx.x == 0 && t) atomicAdd(&d.counters[CNT_BROAD_PAIRS], t);
+	}
+}
+
+// pass 2: every cell writes the pairs of its mask at its offset (collider pairs of one body pair stay adjacent, sub-collider
+// i outer, j inner: collider.cpp:563-571)
+__global__ void __launch_bounds__(256) k_broad_write(DevView d) {
+	const int w = blockIdx.y * 32 + threadIdx.x;
+	const int c = blockIdx.x * blockDim.y + threadIdx.y;
+	if (w >= d.W || c >= d.n_cells) return;
+	unsigned int mask = d.cell_mask[(size_t)c * d.WS + w];
+	if (!mask) return;
+	int out = d.cell_off[(size_t)c * d.WS + w];
+	const int2 cell = d.cells[c];
+	const int i = cell.x;
+	const int ci0 = d.bstat[i].col0, nci = d.bstat[i].ncol;
+	while (mask) {
+		const int j = cell.y + __ffs(mask) - 1;
+		mask &= mask - 1u;
+		const int cj0 = d.bstat[j].col0, ncj = d.bstat[j].ncol;
+		for (int a = 0; a < nci; ++a) {
+			for (int b = 0; b < ncj; ++b) {
+				if (out < d.max_pairs) {
+					PairRec pr;
+					pr.a = i; pr.b = j; pr.ca = ci0 + a; pr.cb = cj0 + b;
+					d.pairs[pidx(d, out, w)] = pr;
+				}
+				++out;
+			}
+		}
 	}
 }
 
@@ -309,32 +374,42 @@ __global__ void __launch_bounds__(32) k_schedule(DevView d, int collisions) {
 	}
 	int nl = d.joint_levels;
 	int deep = 0;  // pairs scheduled at levels >= RP_SCHED_HIST (counted through the global histogram)
-#pragma unroll 4
-	for (int p = 0; p < np; ++p) {
-		const PairRec pr = d.pairs[pidx(d, p, w)];
-		const int a = pr.a, b = pr.b;
-		int fa, fb, sa, sb;
-		if (SMEM) {
-			const int ga = s_flag[a * 32], gb = s_flag[b * 32];
-			fa = ga & 1; fb = gb & 1; sa = ga & 2; sb = gb & 2;
-		} else {
-			fa = d.bstat[a].fixed; fb = d.bstat[b].fixed;
-			sa = fa || !active[a * S]; sb = fb || !active[b * S];
+	// the recurrence is a dependent chain through shared memory; its only global reads, the pair records, are fetched
+	// eight at a time ahead of it (one thread per world has no other way to keep several loads in flight)
+	for (int p0 = 0; p0 < np; p0 += 8) {
+		int2 ab[8];
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			if (p0 + k < np) ab[k] = *reinterpret_cast<const int2*>(&d.pairs[pidx(d, p0 + k, w)]);
 		}
-		// pbd.cpp:594: nothing to do when both sides are fixed or asleep
-		if (sa && sb) {
-			plevel[p * S] = 0;
-			continue;
-		}
-		const int la = fa ? 0 : last[a * LS], lb = fb ? 0 : last[b * LS];
-		const int lvl = 1 + (la > lb ? la : lb);
-		if (!fa) last[a * LS] = lvl;
-		if (!fb) last[b * LS] = lvl;
-		plevel[p * S] = lvl;
-		if (lvl > nl) nl = lvl;
-		if (SMEM) {
-			if (lvl < RP_SCHED_HIST) s_hist[lvl * 32] += 1;
-			else ++deep;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const int p = p0 + k;
+			if (p >= np) break;
+			const int a = ab[k].x, b = ab[k].y;
+			int fa, fb, sa, sb;
+			if (SMEM) {
+				const int ga = s_flag[a * 32], gb = s_flag[b * 32];
+				fa = ga & 1; fb = gb & 1; sa = ga & 2; sb = gb & 2;
+			} else {
+				fa = d.bstat[a].fixed; fb = d.bstat[b].fixed;
+				sa = fa || !active[a * S]; sb = fb || !active[b * S];
+			}
+			// pbd.cpp:594: nothing to do when both sides are fixed or asleep
+			if (sa && sb) {
+				plevel[p * S] = 0;
+				continue;
+			}
+			const int la = fa ? 0 : last[a * LS], lb = fb ? 0 : last[b * LS];
+			const int lvl = 1 + (la > lb ? la : lb);
+			if (!fa) last[a * LS] = lvl;
+			if (!fb) last[b * LS] = lvl;
+			plevel[p * S] = lvl;
+			if (lvl > nl) nl = lvl;
+			if (SMEM) {
+				if (lvl < RP_SCHED_HIST) s_hist[lvl * 32] += 1;
+				else ++deep;
+			}
 		}
 	}
 	// per-level pair counts of the warp's 32 worlds -> one atomic per (warp, level): per-thread atomics on the handful of
@@ -498,6 +573,9 @@ __device__ __forceinline__ unsigned int warp_append(unsigned int* counter, bool 
 // strictly positive (or strictly negative), the origin is outside the difference, and gjk_collides returns false: the
 // pair yields no contacts, exactly as if GJK had run. Survivors go to the dense candidate list of k_gjk.
 #define RP_CULL_MARGIN 1e-7
+#ifndef RP_CULL_ILP
+#define RP_CULL_ILP 2
+#endif
 // Work order. The lanes of a warp take the SAME pair index of 32 CONSECUTIVE worlds (lane = world, warp = pair index),
 // and every list built downstream (candidates -> hits -> level lists) keeps that order. The worlds of a batch are
 // instances of one template, so their pair lists line up and the same pair in neighbouring worlds is in a similar
@@ -511,33 +589,63 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 	const int np = wlive ? d.n_pairs[w] : 0;
 	int np_max = np;
 	for (int o = 16; o > 0; o >>= 1) np_max = max(np_max, __shfl_xor_sync(0xffffffffu, np_max, o));
-	const int* active = d.active + (wlive ? w : 0);
+	const int w0 = wlive ? w : 0;
+	const int* active = d.active + w0;
 	const size_t S = d.WS;
 	int tested = 0;
 	const int warps_per_cta = blockDim.x >> 5;
-	for (int p = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); p < np_max; p += gridDim.x * warps_per_cta) {
-		bool keep = false;
-		if (p < np) {
-			const size_t pg = pidx(d, p, w);
-			d.pair_ccnt[pg] = 0;
-			const PairRec pr = d.pairs[pg];
-			if (!((d.bstat[pr.a].fixed || !active[pr.a * S]) && (d.bstat[pr.b].fixed || !active[pr.b * S]))) {
-				++tested;
-				keep = true;
-				if (cull) {
-					const double* A = d.aabb + (size_t)pr.ca * 6 * S + w;
-					const double* B = d.aabb + (size_t)pr.cb * 6 * S + w;
-					const bool both_spheres = d.cols[pr.ca].type == SHAPE_SPHERE && d.cols[pr.cb].type == SHAPE_SPHERE;
-					if (!both_spheres) {  // sphere-sphere pairs never reach GJK (collider.cpp:530)
-						for (int k = 0; k < 3; ++k) {
-							if (A[k * S] - B[(3 + k) * S] > RP_CULL_MARGIN || B[k * S] - A[(3 + k) * S] > RP_CULL_MARGIN) keep = false;
-						}
-					}
-				}
+	const int stride = gridDim.x * warps_per_cta;
+	// The test is three dependent round trips to memory and nothing else (pair record -> sleep flags + bounds), and the
+	// bounds are what it moves: 12 doubles per pair, 260 MB per substep through L2 for the north-star batch. So: (1) the
+	// bounds are fetched one axis at a time, vertical axis first -- resting and stacked bodies, the floor pairs above all,
+	// separate along y -- and the other two axes only if some lane of the warp still needs them; (2) RP_CULL_ILP pair
+	// indices per trip, every load of a stage issued for all of them before its first use.
+	for (int p0 = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); p0 < np_max; p0 += RP_CULL_ILP * stride) {
+		PairRec pr[RP_CULL_ILP];
+		bool in[RP_CULL_ILP], keep[RP_CULL_ILP], bounds[RP_CULL_ILP];
+#pragma unroll
+		for (int u = 0; u < RP_CULL_ILP; ++u) {
+			const int p = p0 + u * stride;
+			in[u] = p < np;
+			pr[u] = d.pairs[pidx(d, in[u] ? p : 0, w0)];
+		}
+		int fa[RP_CULL_ILP], fb[RP_CULL_ILP], aa[RP_CULL_ILP], ab[RP_CULL_ILP], ta[RP_CULL_ILP], tb[RP_CULL_ILP];
+		double lo_a[RP_CULL_ILP], hi_a[RP_CULL_ILP], lo_b[RP_CULL_ILP], hi_b[RP_CULL_ILP];
+#pragma unroll
+		for (int u = 0; u < RP_CULL_ILP; ++u) {
+			fa[u] = d.bstat[pr[u].a].fixed; fb[u] = d.bstat[pr[u].b].fixed;
+			aa[u] = active[pr[u].a * S]; ab[u] = active[pr[u].b * S];
+			ta[u] = d.cols[pr[u].ca].type; tb[u] = d.cols[pr[u].cb].type;
+			const double* pa = d.aabb + (size_t)pr[u].ca * 6 * S + w0;
+			const double* pb = d.aabb + (size_t)pr[u].cb * 6 * S + w0;
+			lo_a[u] = pa[S]; hi_a[u] = pa[4 * S]; lo_b[u] = pb[S]; hi_b[u] = pb[4 * S];
+		}
+#pragma unroll
+		for (int u = 0; u < RP_CULL_ILP; ++u) {
+			// pbd.cpp:594 skip rule; sphere-sphere pairs never reach GJK (collider.cpp:530) and are never culled
+			keep[u] = in[u] && !((fa[u] || !aa[u]) && (fb[u] || !ab[u]));
+			if (keep[u]) ++tested;
+			bounds[u] = keep[u] && cull && !(ta[u] == SHAPE_SPHERE && tb[u] == SHAPE_SPHERE);
+			if (bounds[u] && (lo_a[u] - hi_b[u] > RP_CULL_MARGIN || lo_b[u] - hi_a[u] > RP_CULL_MARGIN)) keep[u] = bounds[u] = false;
+		}
+#pragma unroll
+		for (int u = 0; u < RP_CULL_ILP; ++u) {
+			if (__any_sync(0xffffffffu, bounds[u])) {
+				const double* pa = d.aabb + (size_t)pr[u].ca * 6 * S + w0;
+				const double* pb = d.aabb + (size_t)pr[u].cb * 6 * S + w0;
+				const double ax0 = pa[0], ax1 = pa[3 * S], az0 = pa[2 * S], az1 = pa[5 * S];
+				const double bx0 = pb[0], bx1 = pb[3 * S], bz0 = pb[2 * S], bz1 = pb[5 * S];
+				if (bounds[u] && (ax0 - bx1 > RP_CULL_MARGIN || bx0 - ax1 > RP_CULL_MARGIN || az0 - bz1 > RP_CULL_MARGIN ||
+					bz0 - az1 > RP_CULL_MARGIN)) keep[u] = false;
 			}
 		}
-		const unsigned int slot = warp_append(d.cand_count, keep);
-		if (keep) d.cands[slot] = make_uint2((unsigned int)w, (unsigned int)p);
+#pragma unroll
+		for (int u = 0; u < RP_CULL_ILP; ++u) {
+			const int p = p0 + u * stride;
+			if (in[u]) d.pair_ccnt[pidx(d, p, w)] = 0;
+			const unsigned int slot = warp_append(d.cand_count, keep[u]);
+			if (keep[u]) d.cands[slot] = make_uint2((unsigned int)w, (unsigned int)p);
+		}
 	}
 	for (int o = 16; o > 0; o >>= 1) tested += __shfl_down_sync(0xffffffffu, tested, o);
 	if (lane == 0 && tested) atomicAdd(&d.counters[CNT_PAIR_TESTS], (unsigned long long)tested);

@@ -1,0 +1,81 @@
+"""The C++ headless driver (raw-physics_b200/host/rp_headless.cpp -> raw-physics_b200/rp_headless): scenes built and
+stepped by host C++ through the C ABI only, its state dumps compared with the oracle stepping the same example
+(tests/scenes.py restates the same init() halves independently, in Python)."""
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import refdrv
+import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "raw-physics_b200", "rp_headless")
+
+
+def read_dump(path):
+    """-> {frame: [bodies][21] array} (format: header of rp_headless.cpp)."""
+    raw = open(path, "rb").read()
+    magic, version, nb, records, stride, every, _ = struct.unpack_from("<IIIIIIQ", raw, 0)
+    assert magic == 0x44485052 and version == 1 and stride == 21
+    out, off = {}, 32
+    for _ in range(records):
+        frame, _pad = struct.unpack_from("<II", raw, off)
+        off += 8
+        out[frame] = np.frombuffer(raw, dtype="<f8", count=nb * stride, offset=off).reshape(nb, stride).copy()
+        off += nb * stride * 8
+    assert off == len(raw)
+    return out
+
+
+def run(tmp_path, *args):
+    dump = str(tmp_path / "dump.bin")
+    r = subprocess.run([EXE, "--dump", dump] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return json.loads(r.stdout.strip().splitlines()[-1]), read_dump(dump)
+
+
+def test_headless_driver_needs_a_gpu(pkg):
+    """No CUDA device -> a clear failure, never a CPU path (runs on the CPU-only build container too)."""
+    assert os.path.exists(EXE)
+    r = subprocess.run([EXE, "--scene", "stack", "--frames", "1"], capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,args,builder,kw,frames", [
+    ("stack", [], "stack", {}, 90),
+    ("brick_wall", ["--rows", 6, "--cols", 4], "brick_wall", dict(rows=6, cols=4), 60),
+    ("w256", [], "w256", {}, 12),
+])
+def test_headless_dump_bit_exact(pkg, oracle_flavour, tmp_path, scene, args, builder, kw, frames):
+    info, dump = run(tmp_path, "--scene", scene, "--frames", frames, "--worlds", 5, "--dump-every", 3, *args)
+    assert info["status_bits"] == 0 and info["diverged_worlds"] == 0 and info["worlds"] == 5
+    sc = scenes.BUILDERS[builder](**kw)
+    assert info["bodies"] == len(sc.bodies)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    seen = 0
+    for f in range(1, frames + 1):
+        o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+        if f in dump:
+            assert np.array_equal(dump[f][:, :15], o.state()), (scene, f)
+            seen += 1
+    assert seen == len(dump) == frames // 3
+
+
+@pytest.mark.gpu
+def test_headless_levers_within_tolerance(pkg, oracle_flavour, tmp_path):
+    """hinge_joints.cpp's levers, spun about their hinges: libm (asin/sin/cos) scene, 1e-9 as in test_gpu_parity.py."""
+    info, dump = run(tmp_path, "--scene", "levers", "--frames", 60, "--worlds", 2)
+    assert info["status_bits"] == 0 and info["diverged_worlds"] == 0
+    sc = scenes.BUILDERS["hinge_joints"]()
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    worst = 0.0
+    for f in range(1, 61):
+        o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+        worst = max(worst, float(np.abs(dump[f][:, :7] - o.state()[:, :7]).max()))
+    print("levers: worst |pose diff| = %g" % worst)
+    assert worst <= 1e-9
