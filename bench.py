@@ -186,6 +186,21 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def hetero_state(init, W, NB, stride, rank):
+    """Every cube of every world gets its own yaw in +-0.3 rad and a lateral offset in +-0.2: contacts form at different
+    times and with different manifolds in every world (no cross-world coherence for the lane = world work order)."""
+    rng = np.random.default_rng(1234 + rank)
+    st = np.ascontiguousarray(np.broadcast_to(init[None], (W, NB, stride))).copy()
+    yaw = rng.uniform(-0.3, 0.3, size=(W, NB - 1))
+    st[:, 1:, 0] += rng.uniform(-0.2, 0.2, size=(W, NB - 1))
+    st[:, 1:, 2] += rng.uniform(-0.2, 0.2, size=(W, NB - 1))
+    st[:, 1:, 3] = 0.0
+    st[:, 1:, 4] = np.sin(0.5 * yaw)
+    st[:, 1:, 5] = 0.0
+    st[:, 1:, 6] = np.cos(0.5 * yaw)
+    return st
+
+
 def run_ours(args):
     import torch
     import __graft_entry__ as ge
@@ -222,6 +237,8 @@ def run_ours(args):
     max_over_ranks = job.max_over_ranks
 
     if args.ncu_frame >= 0:
+        if args.hetero:
+            batch.upload(hetero_state(init, W, NB, pkg.STATE_STRIDE, rank))
         batch.run(max(args.ncu_frame, 1), DT, SUBSTEPS, ITERS, True)
         barrier()
         torch.cuda.profiler.start()
@@ -319,18 +336,8 @@ def run_ours(args):
             line["aggregate_work"] = {"pair_tests": float(t[0]), "epa_runs": float(t[1]), "contacts": float(t[2])}
         if args.hetero:
             # The headline workload is BASELINE.json's: 4096 COPIES of one scene, so the lanes of a warp (same pair index,
-            # neighbouring worlds) follow the same control flow. This leg breaks that: each cube of each world gets its own
-            # yaw in +-0.3 rad and a lateral offset in +-0.2, so contacts form at different times and with different
-            # manifolds in every world. Same kernels, same window.
-            rng = np.random.default_rng(1234 + rank)
-            st = np.ascontiguousarray(np.broadcast_to(init[None], (W, NB, pkg.STATE_STRIDE))).copy()
-            yaw = rng.uniform(-0.3, 0.3, size=(W, NB - 1))
-            st[:, 1:, 0] += rng.uniform(-0.2, 0.2, size=(W, NB - 1))
-            st[:, 1:, 2] += rng.uniform(-0.2, 0.2, size=(W, NB - 1))
-            st[:, 1:, 3] = 0.0
-            st[:, 1:, 4] = np.sin(0.5 * yaw)
-            st[:, 1:, 5] = 0.0
-            st[:, 1:, 6] = np.cos(0.5 * yaw)
+            # neighbouring worlds) follow the same control flow. This leg breaks that (hetero_state). Same kernels, same window.
+            st = hetero_state(init, W, NB, pkg.STATE_STRIDE, rank)
             batch.upload(st)
             barrier()
             c0 = batch.counters()

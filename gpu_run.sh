@@ -1,12 +1,9 @@
 mkdir -p gpurun_out
-( time python -m pytest tests -m gpu -q -x ) 2>&1 | tail -15 > gpurun_out/r18_tests.txt
-cat gpurun_out/r18_tests.txt
-python bench.py --steps 60 --warmup 3 --no-cpu --hetero > gpurun_out/r18_bench.json 2> gpurun_out/r18_bench.err
-tail -3 gpurun_out/r18_bench.err
+python bench.py --steps 60 --warmup 3 --no-cpu > gpurun_out/r20_bench.json 2> gpurun_out/r20_bench.err
 python -c "
-import json,sys; d=json.load(open('gpurun_out/r18_bench.json')); print('base', round(d['value']/1e6,1), round(d['ms_per_step'],2), round(d['e2e']['value']/1e6,1), d['status_bits'], {k:round(v['ms'],0) for k,v in d['kernels'].items()}); print(d.get('heterogeneous'))"
-for v in epa8 epa9 man5 man6 int8 gjk10 gjk12; do
-  RAWPHYS_B200_LIB=$PWD/raw-physics_b200/variants/lib_$v.so python bench.py --steps 60 --warmup 3 --no-cpu > gpurun_out/var_$v.json 2>gpurun_out/var_$v.err
-  python -c "
-import json,sys; d=json.load(open('gpurun_out/var_$v.json')); print('$v', round(d['value']/1e6,1), round(d['ms_per_step'],2), {k:round(v['ms'],0) for k,v in d['kernels'].items() if v['ms']>60})"
-done
+import json,sys; d=json.load(open('gpurun_out/r20_bench.json')); print('base', round(d['value']/1e6,1), round(d['ms_per_step'],2), round(d['e2e']['value']/1e6,1), d['status_bits'], {k:round(v['ms'],0) for k,v in d['kernels'].items()})"
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'k_(gjk|epa|manifold)' -c 3 -o gpurun_out/r20_hetero -f python bench.py --ncu-frame 40 --hetero > gpurun_out/r20_ncu.log 2>&1
+tail -3 gpurun_out/r20_ncu.log
+ncu -i gpurun_out/r20_hetero.ncu-rep --page raw --csv > gpurun_out/r20_hetero.raw.csv 2>/dev/null
+ncu -i gpurun_out/r20_hetero.ncu-rep --page source --csv -k regex:k_epa > gpurun_out/r20_hetero_epa.source.csv 2>/dev/null
+ls -la gpurun_out | tail -5

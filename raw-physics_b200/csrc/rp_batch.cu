@@ -379,7 +379,8 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		int coop = 0, per_sm = 0;
 		RP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
 		if (!coop) return fail(RP_ERR_CUDA, "device does not support cooperative launches");
-		RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_pos, 128, 0));
+		if (d.NJ > 0) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_pos<true>, 128, 0));
+		else RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_pos<false>, 128, 0));
 		if (per_sm < 1) return fail(RP_ERR_CUDA, "k_solve_pos does not fit an SM");
 		b->pos_grid = (unsigned int)(b->sm_count * per_sm);
 		RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_vel, 128, 0));
@@ -619,7 +620,9 @@ static int prologue_levels(rp_batch* b, double dt, int collisions, int* levels) 
 // The Gauss-Seidel sweeps are cooperative grids (grid-wide barrier between levels) of refill loops over warp-owned chunks
 // (WarpQueue): launch exactly the CTAs that are resident at once (occupancy measured at batch creation).
 static void launch_solve_pos(rp_batch* b, double h, int levels, uint32_t iters, int collisions) {
-	if (levels > 0 && iters > 0) launch_cooperative(k_solve_pos, b->pos_grid, 128u, b->stream, b->d, h, levels, (int)iters, collisions);
+	if (levels <= 0 || iters == 0) return;
+	if (b->d.NJ > 0) launch_cooperative(k_solve_pos<true>, b->pos_grid, 128u, b->stream, b->d, h, levels, (int)iters, collisions);
+	else launch_cooperative(k_solve_pos<false>, b->pos_grid, 128u, b->stream, b->d, h, levels, (int)iters, collisions);
 }
 static void launch_solve_vel(rp_batch* b, double h, int levels) {
 	if (levels > 0) launch_cooperative(k_solve_vel, b->vel_grid, 128u, b->stream, b->d, h, levels);

@@ -26,10 +26,10 @@
 #define RP_MINB_EPA 6
 #endif
 #ifndef RP_MINB_POS
-#define RP_MINB_POS 2
+#define RP_MINB_POS 3
 #endif
 #ifndef RP_MINB_VEL
-#define RP_MINB_VEL 2
+#define RP_MINB_VEL 3
 #endif
 
 #define RP_GJK_THREADS 64
@@ -96,6 +96,7 @@ __device__ __forceinline__ void load_static(Body& b, const DevView& d, int body)
 	b.inv_mass = c.inv_mass;
 	b.inertia = c.inertia;
 	b.inv_inertia = c.inv_inertia;
+	b.inv_inertia_p = &c.inv_inertia;
 	b.mu_s = c.mu_s; b.mu_d = c.mu_d; b.rest = c.rest;
 	b.ii_bound = c.ii_bound;
 	b.fixed = s.fixed;
@@ -878,8 +879,17 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 // k_manifold) is the same for every CTA, so EMPTY levels cost nothing -- no launch, no barrier. In the first second of
 // the north-star window more than half of the scheduled levels hold no contact yet (ncu, frame 40: 6 of 11 level
 // launches ran empty at ~5 us each).
+// previous poses for the static-friction branch of solve_contact, fetched only if it is taken
+struct PrevFromDyn {
+	DynRef r1, r2;
+	__device__ __forceinline__ void operator()(Body& b1, Body& b2) const {
+		b1.px = ld3(r1, DF_PX); b1.pq = ld4(r1, DF_PQ);
+		b2.px = ld3(r2, DF_PX); b2.pq = ld4(r2, DF_PQ);
+	}
+};
+template <bool JOINTS>
 __device__ __forceinline__ void pos_level(const DevView& d, double h, int level, int nj, int collisions) {
-	const int njw = nj * d.W;
+	const int njw = JOINTS ? nj * d.W : 0;
 	int st = 0;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < njw; i += gridDim.x * blockDim.x) {
 		const int w = i % d.W;  // lane = world
@@ -931,8 +941,8 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 			load_static(b2, d, pr.b);
 			r1 = dyn_ref(d, w, pr.a);
 			r2 = dyn_ref(d, w, pr.b);
-			b1.x = ld3(r1, DF_X); b1.q = ld4(r1, DF_Q); b1.px = ld3(r1, DF_PX); b1.pq = ld4(r1, DF_PQ);
-			b2.x = ld3(r2, DF_X); b2.q = ld4(r2, DF_Q); b2.px = ld3(r2, DF_PX); b2.pq = ld4(r2, DF_PQ);
+			b1.x = ld3(r1, DF_X); b1.q = ld4(r1, DF_Q);
+			b2.x = ld3(r2, DF_X); b2.q = ld4(r2, DF_Q);
 			c = 0;
 			have = cnt > 0;
 		}
@@ -943,7 +953,7 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 		if (have) {
 			double* cp = cs + (size_t)c * 8 * d.WS;
 			Contact ct = ld_contact(cp, d.WS);
-			solve_contact(ct, normal, b1, b2, h, &st);
+			solve_contact(ct, normal, b1, b2, h, &st, PrevFromDyn{r1, r2});
 			cp[6 * (size_t)d.WS] = ct.lambda_n;
 			cp[7 * (size_t)d.WS] = ct.lambda_t;
 			if (++c == cnt) {
@@ -959,16 +969,20 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 	}
 }
 
+// JOINTS = false is the build for scenes without external constraints: the joint solves (hinge, spherical, their libm
+// calls) are three quarters of this kernel's 14 k instructions, and the contact loop already runs short of instruction
+// cache at two warps per scheduler (ncu, round 1: no_instruction is its second largest stall).
+template <bool JOINTS>
 __global__ void __launch_bounds__(128, RP_MINB_POS) k_solve_pos(DevView d, double h, int levels, int iters, int collisions) {
 	cg::grid_group grid = cg::this_grid();
 	bool dirty = false;
 	for (int it = 0; it < iters; ++it) {
 		for (int level = 1; level <= levels; ++level) {
-			const int nj = level <= d.joint_levels ? d.joint_lptr[level] - d.joint_lptr[level - 1] : 0;
+			const int nj = JOINTS && level <= d.joint_levels ? d.joint_lptr[level] - d.joint_lptr[level - 1] : 0;
 			const int np = collisions ? d.lvl_fill[(size_t)level * RP_LVL_STRIDE] + d.lvl_fill[(size_t)level * RP_LVL_STRIDE + 1] : 0;
 			if (nj == 0 && np == 0) continue;
 			if (dirty) grid.sync();
-			pos_level(d, h, level, nj, collisions);
+			pos_level<JOINTS>(d, h, level, nj, collisions);
 			dirty = true;
 		}
 	}

@@ -21,10 +21,30 @@ struct Body {
 	V3 pv; V3 pw;        // previous_linear_velocity / angular_velocity
 	double inv_mass;
 	M3 inertia, inv_inertia;  // body-frame tensors (entity.h:32-33)
+	const M3* inv_inertia_p;  // device code: where inv_inertia lives in the template (read when needed, see inv_inertia_of)
 	double mu_s, mu_d, rest;
 	double ii_bound;     // an upper bound of the largest eigenvalue of inv_inertia (its infinity norm; tensor_bound)
 	int fixed, active;
 };
+
+// The body-frame inverse inertia tensor as the constraint solves read it. On the device the nine doubles are fetched from
+// the template (read-only path, L1-resident, the same address for every lane working on bodies of one class) each time a
+// world-space tensor is formed, instead of occupying 18 registers per body for the whole life of a manifold: the
+// positional sweep needs two bodies, their tensors in both frames and a contact at once and does not fit 255 registers
+// otherwise. The host checker reads the copy inside the Body.
+#ifdef __CUDA_ARCH__
+RP_HD M3 inv_inertia_of(const Body& b) {
+	M3 r;
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+#pragma unroll
+		for (int j = 0; j < 3; ++j) r.m[i][j] = __ldg(&b.inv_inertia_p->m[i][j]);
+	}
+	return r;
+}
+#else
+RP_HD const M3& inv_inertia_of(const Body& b) { return b.inv_inertia; }
+#endif
 
 // infinity norm of a symmetric (or any) 3x3 tensor: >= its spectral radius
 RP_HD double tensor_bound(const M3& a) {
@@ -92,8 +112,8 @@ RP_HD PosPre pos_pre(const Body& b1, const Body& b2, V3 r1_lc, V3 r2_lc) {
 	PosPre p;
 	p.r1 = rotate(b1.q, r1_lc);
 	p.r2 = rotate(b2.q, r2_lc);
-	p.ii1 = b1.fixed ? zero_m3() : world_tensor(b1.q, b1.inv_inertia);
-	p.ii2 = b2.fixed ? zero_m3() : world_tensor(b2.q, b2.inv_inertia);
+	p.ii1 = b1.fixed ? zero_m3() : world_tensor(b1.q, inv_inertia_of(b1));
+	p.ii2 = b2.fixed ? zero_m3() : world_tensor(b2.q, inv_inertia_of(b2));
 	return p;
 }
 // generalised inverse mass of one body along n at arm r (pbd_base_constraints.cpp:38-39, pbd.cpp:697-698)
@@ -145,8 +165,8 @@ struct AngPre {
 // calculate_angular_constraint_preprocessed_data (pbd_base_constraints.cpp:125-131)
 RP_HD AngPre ang_pre(const Body& b1, const Body& b2) {
 	AngPre a;
-	a.ii1 = b1.fixed ? zero_m3() : world_tensor(b1.q, b1.inv_inertia);
-	a.ii2 = b2.fixed ? zero_m3() : world_tensor(b2.q, b2.inv_inertia);
+	a.ii1 = b1.fixed ? zero_m3() : world_tensor(b1.q, inv_inertia_of(b1));
+	a.ii2 = b2.fixed ? zero_m3() : world_tensor(b2.q, inv_inertia_of(b2));
 	return a;
 }
 // angular_constraint_get_delta_lambda (pbd_base_constraints.cpp:133-161)
@@ -190,8 +210,14 @@ RP_HD Contact make_contact(const Body& b1, const Body& b2, V3 p1, V3 p2) {
 #if defined(RP_COUNT_FRICTION) && !defined(__CUDA_ARCH__)
 static long g_friction_skipped = 0, g_friction_taken = 0, g_friction_evaluated = 0;  // diagnostics build of the port only
 #endif
-// collision_constraint_solve (pbd.cpp:107-154), incl. quirk q1 (static friction reuses the normal correction vector)
-RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, int* status) {
+// collision_constraint_solve (pbd.cpp:107-154), incl. quirk q1 (static friction reuses the normal correction vector).
+// `prev(b1, b2)` is called right before the previous poses (px, pq) are read -- only inside the static-friction branch,
+// which is rarely taken -- so a caller may leave them unloaded until then (PrevInBody: they are already in the bodies).
+struct PrevInBody {
+	RP_HD void operator()(Body&, Body&) const {}
+};
+template <class PrevPose>
+RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, int* status, const PrevPose& prev) {
 	PosPre p = pos_pre(b1, b2, c.r1_lc, c.r2_lc);
 	V3 p1 = add(b1.x, p.r1);
 	V3 p2 = add(b2.x, p.r2);
@@ -238,6 +264,7 @@ RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, in
 		double lambda_n = c.lambda_n;
 		double lambda_t = c.lambda_t + dl;
 		if (lambda_t > mu * lambda_n) {
+			prev(b1, b2);
 			V3 p1t = add(b1.px, rotate(b1.pq, c.r1_lc));
 			V3 p2t = add(b2.px, rotate(b2.pq, c.r2_lc));
 			V3 dp = sub(sub(p1, p1t), sub(p2, p2t));
@@ -249,6 +276,10 @@ RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, in
 #endif
 		}
 	}
+}
+
+RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, int* status) {
+	solve_contact(c, normal, b1, b2, h, status, PrevInBody());
 }
 
 // velocity solve for one contact (pbd.cpp:648-711). The world-space inverse inertia tensors of the preprocessed data
