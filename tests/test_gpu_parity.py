@@ -247,3 +247,41 @@ def test_brick_wall_32x32_single_scene(pkg, oracle_flavour):
         o.step()
         assert np.array_equal(b.state()[0, :, :15], o.state()), f
     assert not b.status().any()
+
+
+def test_config2_4096_copies_of_the_stack_scene(pkg, oracle_flavour):
+    """BASELINE config 2: 4096 copies of the reference's stack scene on one GPU for 600 frames; every
+    world bitwise equal to world 0, and world 0 equal to the oracle at frames 1, 60 and 600 (all asleep by then)."""
+    sc = scenes.stack()
+    b = make(pkg, sc, n_worlds=4096)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    for f in range(1, 601):
+        step(b, sc)
+        o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+        if f in (1, 60, 600):
+            got = b.state()
+            assert np.array_equal(got[0, :, :15], o.state()), f
+            assert (got == got[0]).all(), f
+    assert not got[0, 1:, 13].any()  # every cube asleep
+    assert not b.status().any()
+
+
+def test_config5_joint_worlds_sharded(pkg, oracle_flavour):
+    """BASELINE config 5 in small: hinge-lever worlds split over two batches the way multi.partition splits them over
+    ranks; each shard's worlds equal the oracle's single world within the joint tolerance."""
+    import __graft_entry__ as ge
+    ge.load_package()
+    from rawphys_b200 import multi
+    sc = scenes.hinge_joints()
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    shards = [make(pkg, sc, n_worlds=n) for (_, n) in multi.partition(257, 2)]
+    assert [s.W for s in shards] == [129, 128]
+    for f in range(40):
+        for s in shards:
+            step(s, sc)
+        o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+    want = o.state()
+    for s in shards:
+        got = s.state()
+        assert (got == got[0]).all()
+        assert np.abs(got[0, :, :7] - want[:, :7]).max() <= 1e-9
