@@ -104,10 +104,19 @@ int rp_scene_hull_dump(const rp_scene* s, int body, int collider, double* verts,
 	uint32_t* v2f_ptr, uint32_t* v2f_idx, uint32_t* v2n_ptr, uint32_t* v2n_idx, uint32_t* f2n_ptr, uint32_t* f2n_idx);
 
 /* ------------------------------------------------------------------------------------------------------- batches */
+/* Order of the Gauss-Seidel sweeps over a world's constraints (rp_batch_cfg.solve_order).
+ * RP_ORDER_REFERENCE: the reference's array order (external constraints, then contacts in broadphase-pair order,
+ *   pbd.cpp:580-620), run as dependency levels -- results identical to the reference's. The default.
+ * RP_ORDER_COLOURED: a greedy colouring of the constraint graph rebuilt every frame; colours run in ascending order. Far
+ *   fewer sequential stages for one large scene (a 32 x 32 brick wall: ~10 instead of ~150), trajectories equal to the
+ *   reference's only within solver accuracy. */
+enum { RP_ORDER_REFERENCE = 0, RP_ORDER_COLOURED = 1 };
+
 typedef struct {
 	uint32_t max_pairs_per_world;     /* broadphase (collider-)pair capacity; 0 = derive from the initial poses */
 	uint32_t max_contacts_per_world;  /* contact capacity per substep; 0 = derive */
 	uint32_t disable_cull;            /* 1 = run GJK on every broadphase pair (the exact-safe bounds cull is on by default) */
+	uint32_t solve_order;             /* RP_ORDER_REFERENCE (default) or RP_ORDER_COLOURED */
 	double linear_sleeping_threshold;   /* pbd.cpp:13, default 0.10 */
 	double angular_sleeping_threshold;  /* pbd.cpp:14, default 0.10 */
 	double deactivation_time;           /* pbd.cpp:15, default 1.0 */

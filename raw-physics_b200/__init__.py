@@ -38,6 +38,7 @@ KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "cull", "gj
 
 class BatchCfg(C.Structure):
     _fields_ = [("max_pairs_per_world", C.c_uint32), ("max_contacts_per_world", C.c_uint32), ("disable_cull", C.c_uint32),
+                ("solve_order", C.c_uint32),
                 ("linear_sleeping_threshold", C.c_double), ("angular_sleeping_threshold", C.c_double), ("deactivation_time", C.c_double)]
 
 
@@ -199,7 +200,7 @@ class Scene:
 class Batch:
     """n_worlds instances of a scene on one GPU (rp_batch)."""
 
-    def __init__(self, scene, n_worlds=1, device=0, max_pairs=0, max_contacts=0, disable_cull=False):
+    def __init__(self, scene, n_worlds=1, device=0, max_pairs=0, max_contacts=0, disable_cull=False, coloured=False):
         self.L = lib()
         self.scene = scene
         cfg = BatchCfg()
@@ -207,6 +208,7 @@ class Batch:
         cfg.max_pairs_per_world = max_pairs
         cfg.max_contacts_per_world = max_contacts
         cfg.disable_cull = int(disable_cull)
+        cfg.solve_order = 1 if coloured else 0  # RP_ORDER_COLOURED / RP_ORDER_REFERENCE
         h = C.c_void_p()
         _check(self.L.rp_batch_create(scene.h, n_worlds, device, C.byref(cfg), C.byref(h)), "rp_batch_create")
         self.h = h

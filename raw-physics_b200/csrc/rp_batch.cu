@@ -59,6 +59,7 @@ struct rp_batch {
 	int sm_count = 148;
 	unsigned int pos_grid = 148, vel_grid = 148;  // resident CTAs of the cooperative sweep kernels
 	int cull = 1;            // exact-safe bounds cull before GJK (rp_batch_cfg.disable_cull turns it off)
+	int coloured = 0;        // rp_batch_cfg.solve_order == RP_ORDER_COLOURED
 	int* levels_host = 0;    // pinned: deepest dependency level of the current frame
 	std::vector<int> joint_level;  // template-constant levels of the external constraints
 	bool have_graph = false;
@@ -340,6 +341,8 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	RP_CUDA(cudaGetDeviceProperties(&prop, device));
 	b->sm_count = prop.multiProcessorCount;
 
+	if (cfg.solve_order > RP_ORDER_COLOURED) return fail(RP_ERR_ARG, "rp_batch_create: unknown solve_order");
+	b->coloured = cfg.solve_order == RP_ORDER_COLOURED ? 1 : 0;
 	DevView& d = b->d;
 	memset(&d, 0, sizeof(d));
 	d.W = (int)n_worlds;
@@ -388,19 +391,29 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		b->vel_grid = (unsigned int)(b->sm_count * per_sm);
 	}
 	RP_CUDA(cudaHostAlloc((void**)&b->levels_host, sizeof(int), cudaHostAllocDefault));
-	RP_CUDA(cudaFuncSetAttribute(k_schedule<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_SCHED_SMEM_MAX));
+	RP_CUDA(cudaFuncSetAttribute(k_schedule<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_SCHED_SMEM_MAX));
+	RP_CUDA(cudaFuncSetAttribute(k_schedule<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_SCHED_SMEM_MAX));
 
 	// Dependency levels of the external constraints: they head the constraint array (pbd.cpp:580) in every world, so
 	// their part of the schedule is a constant of the template.
 	std::vector<int> jlast(d.NB, 0), jlevel(d.NJ, 0);
+	std::vector<unsigned long long> jcolours(d.NB, 0ull);
 	int jl_max = 0;
 	for (int u = 0; u < d.NJ; ++u) {
 		const Joint& j = s.joints[u];
 		const int fa = s.bodies[j.e1].fixed, fb = s.bodies[j.e2].fixed;
-		const int la = fa ? 0 : jlast[j.e1], lb = fb ? 0 : jlast[j.e2];
-		const int lvl = 1 + std::max(la, lb);
-		if (!fa) jlast[j.e1] = lvl;
-		if (!fb) jlast[j.e2] = lvl;
+		int lvl;
+		if (b->coloured) {
+			unsigned long long na, nb;
+			lvl = SchedEntry<true>::place(fa ? 0ull : jcolours[j.e1], fb ? 0ull : jcolours[j.e2], &na, &nb);
+			if (!fa) jcolours[j.e1] = na;
+			if (!fb) jcolours[j.e2] = nb;
+		} else {
+			int na, nb;
+			lvl = SchedEntry<false>::place(fa ? 0 : jlast[j.e1], fb ? 0 : jlast[j.e2], &na, &nb);
+			if (!fa) jlast[j.e1] = na;
+			if (!fb) jlast[j.e2] = nb;
+		}
 		jlevel[u] = lvl;
 		jl_max = std::max(jl_max, lvl);
 	}
@@ -461,6 +474,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_upload(b, &d.joint_sched, jsched))) return rc;
 	if ((rc = dev_upload(b, &d.joint_lptr, jlptr))) return rc;
 	if ((rc = dev_upload(b, &d.joint_last, jlast))) return rc;
+	if ((rc = dev_upload(b, &d.joint_colours, jcolours))) return rc;
 	if ((rc = dev_upload(b, &d.pool.hulls, hp.hulls))) return rc;
 	if ((rc = dev_upload(b, &d.pool.verts, hp.verts))) return rc;
 	if ((rc = dev_upload(b, &d.pool.normals, hp.normals))) return rc;
@@ -501,6 +515,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.label, WB))) return rc;
 	if ((rc = dev_alloc(b, &d.isl_flag, WB))) return rc;
 	if ((rc = dev_alloc(b, &d.last_level, SB))) return rc;
+	if ((rc = dev_alloc(b, &d.colour_tab, b->coloured ? SB : 1))) return rc;
 	if ((rc = dev_alloc(b, &d.pair_level, SP))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_hist, WS * (d.max_levels + 2)))) return rc;
 	if ((rc = dev_alloc(b, &d.aabb, WS * std::max(d.NC, 1) * 6))) return rc;
@@ -582,9 +597,16 @@ static int flush_forces(rp_batch* b) {
 
 static void launch_schedule(rp_batch* b, int collisions) {
 	const DevView& d = b->d;
-	const size_t smem = (size_t)d.NB * 32 * sizeof(int) + RP_SCHED_HIST * 32 * sizeof(int) + (size_t)d.NB * 32;
-	if (smem <= RP_SCHED_SMEM_MAX) k_schedule<true><<<(d.W + 31) / 32, 32, smem, b->stream>>>(d, collisions);
-	else k_schedule<false><<<(d.W + 31) / 32, 32, 0, b->stream>>>(d, collisions);
+	const size_t entry = b->coloured ? sizeof(unsigned long long) : sizeof(int);
+	const size_t smem = (size_t)d.NB * 32 * entry + RP_SCHED_HIST * 32 * sizeof(int) + (size_t)d.NB * 32;
+	const unsigned int grid = (unsigned int)((d.W + 31) / 32);
+	if (b->coloured) {
+		if (smem <= RP_SCHED_SMEM_MAX) k_schedule<true, true><<<grid, 32, smem, b->stream>>>(d, collisions);
+		else k_schedule<false, true><<<grid, 32, 0, b->stream>>>(d, collisions);
+	} else {
+		if (smem <= RP_SCHED_SMEM_MAX) k_schedule<true, false><<<grid, 32, smem, b->stream>>>(d, collisions);
+		else k_schedule<false, false><<<grid, 32, 0, b->stream>>>(d, collisions);
+	}
 }
 static void launch_broad(rp_batch* b) {
 	const DevView& d = b->d;

@@ -73,6 +73,7 @@ struct DevView {
 	int* label;          // [W][NB] island labels (world-major scratch of k_islands)
 	int* isl_flag;       // [W][NB] island "all members may sleep"
 	int* last_level;     // [NB][WS] schedule scratch
+	unsigned long long* colour_tab;  // [NB][WS] schedule scratch of the coloured order (when the table does not fit shared memory)
 	int* pair_level;     // [max_pairs][WS] dependency level of each broadphase pair (0 = skipped this frame)
 	int* lvl_hist;       // [max_levels + 2][WS] schedule scratch (per-world level histogram)
 	double* aabb;        // [NC][6][WS] world-space bounds of every collider (min xyz, max xyz)
@@ -93,6 +94,7 @@ struct DevView {
 	const int* joint_sched;   // [NJ] joints sorted by level
 	const int* joint_lptr;    // [joint_levels + 1]
 	const int* joint_last;    // [NB] level of the last joint touching each body (0 = none)
+	const unsigned long long* joint_colours;  // [NB] coloured order: colours the joints of each body have taken (SchedEntry<true>)
 	int joint_levels;
 	V3* pair_normal;     // [max_pairs][WS]
 	int* pair_coff;      // [max_pairs][WS]

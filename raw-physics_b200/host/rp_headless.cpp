@@ -5,6 +5,7 @@
 //
 //   rp_headless --scene stack|w256|brick_wall|levers [--rows R] [--cols C] [--worlds W] [--frames F] [--dt DT]
 //               [--substeps S] [--iters I] [--device D] [--meshes DIR] [--dump FILE] [--dump-every K] [--no-collisions]
+//               [--coloured]   (RP_ORDER_COLOURED: graph-coloured sweeps for one large scene, not bit-comparable)
 //
 // Scenes restate the init() halves of the reference's examples (cited per builder); their update() halves are all the
 // same sequence -- gravity force on every entity, pbd_simulate, clear forces (stack.cpp:86-104) -- which is what run()
@@ -32,7 +33,7 @@ struct Options {
 	std::string scene = "stack", meshes, dump;
 	int rows = 32, cols = 32, worlds = 1, frames = 60, substeps = 20, iters = 1, device = 0, dump_every = 1;
 	double dt = 1.0 / 60.0;
-	bool collisions = true;
+	bool collisions = true, coloured = false;
 };
 
 [[noreturn]] void die(const std::string& what) {
@@ -184,6 +185,7 @@ void parse(int argc, char** argv, Options& o) {
 		else if (a == "--dump") o.dump = next();
 		else if (a == "--dump-every") o.dump_every = atoi(next());
 		else if (a == "--no-collisions") o.collisions = false;
+		else if (a == "--coloured") o.coloured = true;
 		else die("unknown argument " + a);
 	}
 	if (o.worlds < 1 || o.frames < 0 || o.substeps < 1 || o.iters < 0 || o.dump_every < 1 || o.rows < 1 || o.cols < 1) die("bad argument value");
@@ -213,7 +215,10 @@ int main(int argc, char** argv) {
 	else die("unknown scene " + o.scene);
 
 	rp_batch* batch = 0;
-	if (rp_batch_create(scene, (uint32_t)o.worlds, o.device, 0, &batch) != RP_OK) die("rp_batch_create");
+	rp_batch_cfg cfg;
+	rp_batch_cfg_default(&cfg);
+	cfg.solve_order = o.coloured ? RP_ORDER_COLOURED : RP_ORDER_REFERENCE;
+	if (rp_batch_create(scene, (uint32_t)o.worlds, o.device, &cfg, &batch) != RP_OK) die("rp_batch_create");
 	const uint32_t nb = rp_batch_num_bodies(batch);
 	std::vector<double> state((size_t)nb * RP_STATE_STRIDE);
 	if (!spin.empty()) {  // initial angular velocities: edit world 0's records and hand them to every world
@@ -275,10 +280,11 @@ int main(int argc, char** argv) {
 	uint64_t counters[8];
 	if (rp_batch_get_counters(batch, counters) != RP_OK) die("rp_batch_get_counters");
 	const double units = (double)nb * o.worlds * o.substeps * o.frames;
-	printf("{\"scene\": \"%s\", \"worlds\": %d, \"bodies\": %u, \"frames\": %d, \"substeps\": %d, \"seconds\": %.6f, \"ms_per_frame\": %.4f, "
+	printf("{\"scene\": \"%s\", \"order\": \"%s\", \"sweep_depth\": %.1f, \"worlds\": %d, \"bodies\": %u, \"frames\": %d, \"substeps\": %d, \"seconds\": %.6f, \"ms_per_frame\": %.4f, "
 	       "\"body_substeps_per_s\": %.6g, \"status_bits\": %d, \"diverged_worlds\": %d, \"pair_tests\": %llu, \"epa_runs\": %llu, "
 	       "\"contacts\": %llu}\n",
-		o.scene.c_str(), o.worlds, nb, o.frames, o.substeps, seconds, o.frames ? 1e3 * seconds / o.frames : 0.0,
+		o.scene.c_str(), o.coloured ? "coloured" : "reference", counters[5] ? (double)counters[4] / (double)counters[5] / o.worlds : 0.0, o.worlds, nb,
+		o.frames, o.substeps, seconds, o.frames ? 1e3 * seconds / o.frames : 0.0,
 		seconds > 0.0 ? units / seconds : 0.0, (int)bits, diverged, (unsigned long long)counters[0], (unsigned long long)counters[1],
 		(unsigned long long)counters[2]);
 	rp_batch_destroy(batch);
