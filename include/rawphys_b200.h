@@ -135,9 +135,9 @@ int rp_batch_add_force(rp_batch* b, int body, const double position[3], const do
 /* the examples' gravity idiom: (0, -g * 1.0 / inverse_mass, 0) at the centre of every body (stack.cpp:93-96) */
 int rp_batch_add_gravity(rp_batch* b, double g);
 
-/* pbd_simulate_with_constraints for every world. The per-frame prologue (broadphase, islands, schedule) is waited for,
- * because the host needs the frame's dependency depth; the substeps are then enqueued on the batch's CUDA stream as one
- * graph launch and the call returns without waiting for them. */
+/* pbd_simulate_with_constraints for every world. The whole frame -- broadphase, islands + sleeping, schedule, then the
+ * substeps -- is enqueued on the batch's CUDA stream as ONE graph launch (captured once per (dt, substeps, iters,
+ * collisions)) and the call returns without waiting for it; nothing about the frame is read back by the host. */
 int rp_batch_step(rp_batch* b, double dt, uint32_t num_substeps, uint32_t num_pos_iters, int enable_collisions);
 int rp_batch_sync(rp_batch* b);
 /* `frames` consecutive steps timed on the device with CUDA events on the batch's stream (milliseconds). */

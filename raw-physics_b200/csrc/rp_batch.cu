@@ -38,9 +38,9 @@ struct rp_scene {
 struct GraphKey {
 	double dt;
 	uint32_t substeps, iters;
-	int collisions, levels;
+	int collisions;
 	bool operator==(const GraphKey& o) const {
-		return dt == o.dt && substeps == o.substeps && iters == o.iters && collisions == o.collisions && levels == o.levels;
+		return dt == o.dt && substeps == o.substeps && iters == o.iters && collisions == o.collisions;
 	}
 };
 
@@ -60,7 +60,6 @@ struct rp_batch {
 	unsigned int pos_grid = 148, vel_grid = 148;  // resident CTAs of the cooperative sweep kernels
 	int cull = 1;            // exact-safe bounds cull before GJK (rp_batch_cfg.disable_cull turns it off)
 	int coloured = 0;        // rp_batch_cfg.solve_order == RP_ORDER_COLOURED
-	int* levels_host = 0;    // pinned: deepest dependency level of the current frame
 	std::vector<int> joint_level;  // template-constant levels of the external constraints
 	bool have_graph = false;
 	GraphKey graph_key;
@@ -304,7 +303,6 @@ void rp_batch_destroy(rp_batch* b) {
 	for (size_t i = 0; i < b->allocs.size(); ++i) cudaFree(b->allocs[i]);
 	if (b->ev0) cudaEventDestroy(b->ev0);
 	if (b->ev1) cudaEventDestroy(b->ev1);
-	if (b->levels_host) cudaFreeHost(b->levels_host);
 	if (b->stream) cudaStreamDestroy(b->stream);
 	cudaGetLastError();
 	delete b;
@@ -390,7 +388,6 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		if (per_sm < 1) return fail(RP_ERR_CUDA, "k_solve_vel does not fit an SM");
 		b->vel_grid = (unsigned int)(b->sm_count * per_sm);
 	}
-	RP_CUDA(cudaHostAlloc((void**)&b->levels_host, sizeof(int), cudaHostAllocDefault));
 	RP_CUDA(cudaFuncSetAttribute(k_schedule<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_SCHED_SMEM_MAX));
 	RP_CUDA(cudaFuncSetAttribute(k_schedule<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_SCHED_SMEM_MAX));
 
@@ -628,26 +625,15 @@ static void enqueue_prologue(rp_batch* b, double dt, int collisions) {
 	k_level_offsets<<<1, 1, 0, b->stream>>>(d);
 }
 
-// Runs the prologue and waits for the one number the host needs to shape the rest of the frame: the deepest
-// dependency level over all worlds (= how many level launches each Gauss-Seidel sweep takes).
-static int prologue_levels(rp_batch* b, double dt, int collisions, int* levels) {
-	enqueue_prologue(b, dt, collisions);
-	RP_CUDA(cudaGetLastError());
-	RP_CUDA(cudaMemcpyAsync(b->levels_host, b->d.lvl_max, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-	RP_CUDA(cudaStreamSynchronize(b->stream));
-	*levels = *b->levels_host;
-	return RP_OK;
-}
-
 // The Gauss-Seidel sweeps are cooperative grids (grid-wide barrier between levels) of refill loops over warp-owned chunks
 // (WarpQueue): launch exactly the CTAs that are resident at once (occupancy measured at batch creation).
-static void launch_solve_pos(rp_batch* b, double h, int levels, uint32_t iters, int collisions) {
-	if (levels <= 0 || iters == 0) return;
-	if (b->d.NJ > 0) launch_cooperative(k_solve_pos<true>, b->pos_grid, 128u, b->stream, b->d, h, levels, (int)iters, collisions);
-	else launch_cooperative(k_solve_pos<false>, b->pos_grid, 128u, b->stream, b->d, h, levels, (int)iters, collisions);
+static void launch_solve_pos(rp_batch* b, double h, uint32_t iters, int collisions) {
+	if (iters == 0) return;
+	if (b->d.NJ > 0) launch_cooperative(k_solve_pos<true>, b->pos_grid, 128u, b->stream, b->d, h, (int)iters, collisions);
+	else launch_cooperative(k_solve_pos<false>, b->pos_grid, 128u, b->stream, b->d, h, (int)iters, collisions);
 }
-static void launch_solve_vel(rp_batch* b, double h, int levels) {
-	if (levels > 0) launch_cooperative(k_solve_vel, b->vel_grid, 128u, b->stream, b->d, h, levels);
+static void launch_solve_vel(rp_batch* b, double h) {
+	launch_cooperative(k_solve_vel, b->vel_grid, 128u, b->stream, b->d, h);
 }
 
 static void enqueue_integrate(rp_batch* b, double h) {
@@ -669,11 +655,11 @@ static void enqueue_narrow(rp_batch* b) {
 	launch_gjk(b);
 	launch_manifold(b);
 }
-static void enqueue_solve(rp_batch* b, double h, uint32_t iters, int collisions, int levels) {
-	launch_solve_pos(b, h, levels, iters, collisions);
+static void enqueue_solve(rp_batch* b, double h, uint32_t iters, int collisions) {
+	launch_solve_pos(b, h, iters, collisions);
 	// velocity derivation (pbd.cpp:623-643) is lazy: a body's velocities are derived by the first velocity-level unit
 	// that touches it, else by the next substep's k_integrate, else by k_derive at the end of the frame
-	if (collisions) launch_solve_vel(b, h, levels);
+	if (collisions) launch_solve_vel(b, h);
 }
 static void enqueue_frame_end(rp_batch* b, double h) {
 	const DevView& d = b->d;
@@ -681,12 +667,15 @@ static void enqueue_frame_end(rp_batch* b, double h) {
 	k_count_frame<<<1, 1, 0, b->stream>>>(d);
 }
 
-static void enqueue_substeps(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int collisions, int levels) {
+// one whole frame: prologue + substeps + end of frame. The sweep depth of the frame stays on the device (the sweep kernels
+// read it), so nothing here depends on the state and the sequence is captured once per (dt, substeps, iters, collisions).
+static void enqueue_frame(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int collisions) {
 	const double h = dt / substeps;  // pbd.cpp:472
+	enqueue_prologue(b, dt, collisions);
 	for (uint32_t s = 0; s < substeps; ++s) {
 		enqueue_integrate(b, h);
 		if (collisions) enqueue_narrow(b);
-		enqueue_solve(b, h, iters, collisions, levels);
+		enqueue_solve(b, h, iters, collisions);
 	}
 	enqueue_frame_end(b, h);
 }
@@ -697,10 +686,8 @@ int rp_batch_step(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int
 	RP_CUDA(cudaSetDevice(b->device));
 	int rc = flush_forces(b);
 	if (rc) return rc;
-	int levels = 0;
-	if ((rc = prologue_levels(b, dt, collisions ? 1 : 0, &levels))) return rc;
 	GraphKey key;
-	key.dt = dt; key.substeps = substeps; key.iters = iters; key.collisions = collisions ? 1 : 0; key.levels = levels;
+	key.dt = dt; key.substeps = substeps; key.iters = iters; key.collisions = collisions ? 1 : 0;
 	if (!b->have_graph || !(b->graph_key == key)) {
 		if (b->graph_exec) cudaGraphExecDestroy(b->graph_exec);
 		if (b->graph) cudaGraphDestroy(b->graph);
@@ -708,7 +695,7 @@ int rp_batch_step(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int
 		b->graph = 0;
 		b->have_graph = false;
 		RP_CUDA(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
-		enqueue_substeps(b, dt, substeps, iters, key.collisions, levels);
+		enqueue_frame(b, dt, substeps, iters, key.collisions);
 		cudaError_t e = cudaStreamEndCapture(b->stream, &b->graph);
 		if (e != cudaSuccess) return fail(RP_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
 		RP_CUDA(cudaGraphInstantiate(&b->graph_exec, b->graph, 0));
@@ -875,8 +862,8 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t substeps, uint32_t ite
 	DevView& d = b->d;
 	d.dbg_world = (int)world;
 	const double h = dt / substeps;
-	int levels = 0;
-	if ((rc = prologue_levels(b, dt, collisions ? 1 : 0, &levels))) return rc;
+	enqueue_prologue(b, dt, collisions ? 1 : 0);
+	RP_CUDA(cudaGetLastError());
 	std::vector<int> np, active, ccnt, coff;
 	std::vector<PairRec> pr;
 	std::vector<BodyStatic> bs;
@@ -919,7 +906,7 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t substeps, uint32_t ite
 				if (nc - 1 < max_calls && calls_out) calls_out[4 * (nc - 1) + 2] += (uint32_t)ccnt[i];
 			}
 		}
-		enqueue_solve(b, h, iters, collisions ? 1 : 0, levels);
+		enqueue_solve(b, h, iters, collisions ? 1 : 0);
 	}
 	enqueue_frame_end(b, h);
 	RP_CUDA(cudaGetLastError());
@@ -961,9 +948,7 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 		launch_schedule(b, collisions ? 1 : 0);
 		k_level_offsets<<<1, 1, 0, b->stream>>>(d);
 		if ((rc = mark(RP_K_SCHEDULE))) return rc;
-		RP_CUDA(cudaMemcpyAsync(b->levels_host, d.lvl_max, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
 		RP_CUDA(cudaStreamSynchronize(b->stream));
-		const int levels = *b->levels_host;
 		if ((rc = mark(-1))) return rc;
 		for (uint32_t s = 0; s < substeps; ++s) {
 			enqueue_integrate(b, h);
@@ -978,10 +963,10 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 				k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_MANIFOLD))) return rc;
 			}
-			launch_solve_pos(b, h, levels, iters, collisions ? 1 : 0);
+			launch_solve_pos(b, h, iters, collisions ? 1 : 0);
 			if ((rc = mark(RP_K_SOLVE_POS))) return rc;
 			if (collisions) {
-				launch_solve_vel(b, h, levels);
+				launch_solve_vel(b, h);
 				if ((rc = mark(RP_K_SOLVE_VEL))) return rc;
 			}
 		}

@@ -1023,8 +1023,9 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 // calls) are three quarters of this kernel's 14 k instructions, and the contact loop already runs short of instruction
 // cache at two warps per scheduler (ncu, round 1: no_instruction is its second largest stall).
 template <bool JOINTS>
-__global__ void __launch_bounds__(128, RP_MINB_POS) k_solve_pos(DevView d, double h, int levels, int iters, int collisions) {
+__global__ void __launch_bounds__(128, RP_MINB_POS) k_solve_pos(DevView d, double h, int iters, int collisions) {
 	cg::grid_group grid = cg::this_grid();
+	const int levels = *d.lvl_max;  // this frame's sweep depth over all worlds (k_schedule): read here, the host never needs it
 	bool dirty = false;
 	for (int it = 0; it < iters; ++it) {
 		for (int level = 1; level <= levels; ++level) {
@@ -1139,8 +1140,9 @@ __device__ __forceinline__ void vel_level(const DevView& d, double h, int level)
 	}
 }
 
-__global__ void __launch_bounds__(128, RP_MINB_VEL) k_solve_vel(DevView d, double h, int levels) {
+__global__ void __launch_bounds__(128, RP_MINB_VEL) k_solve_vel(DevView d, double h) {
 	cg::grid_group grid = cg::this_grid();
+	const int levels = *d.lvl_max;
 	bool dirty = false;
 	for (int level = 1; level <= levels; ++level) {
 		if (d.lvl_fill[(size_t)level * RP_LVL_STRIDE] + d.lvl_fill[(size_t)level * RP_LVL_STRIDE + 1] == 0) continue;
