@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--hetero", action="store_true",
                     help="also time the same window with every world started from a DIFFERENT pose set (random yaw and lateral "
                          "offset per cube): reported next to the headline as `heterogeneous`")
+    ap.add_argument("--e2e-parts", type=int, default=2, help="sub-batches (host threads) of the pipelined end-to-end leg")
     ap.add_argument("--ncu-frame", type=int, default=-1,
                     help="profiling aid: run this many frames, then bracket ONE more frame with cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints nothing")
@@ -319,22 +320,23 @@ def run_ours(args):
         line["e2e"] = {"value": units / e2e_s, "unit": "body-substeps/s", "h2d_bytes_per_step": nrec * 8, "d2h_bytes_per_step": nrec * 8,
                        "ms_per_step": 1e3 * e2e_s / args.steps, "api": "rp_batch_step_host (upload state, step, download state, sync)"}
 
-        # ---- the same end-to-end loop with the worlds split over two half-size batches, each driven by its own host
-        # thread on its own stream: one half's PCIe copies overlap the other half's kernels. Same public call
+        # ---- the same end-to-end loop with the worlds split over P sub-batches, each driven by its own host thread on its
+        # own stream: one sub-batch's PCIe copies overlap the others' kernels. Same public call
         # (rp_batch_step_host), same bytes per step, same worlds; reported as `e2e` when it is the faster of the two.
-        if W % 2 == 0 and W >= 64:
+        P = args.e2e_parts
+        if P > 1 and W % P == 0 and W // P >= 32:
             rewind()
             start_state = torch.from_numpy(batch.state().reshape(-1))
-            halves = [pkg.Batch(scene, n_worlds=W // 2, device=local_rank, disable_cull=args.no_cull) for _ in range(2)]
+            halves = [pkg.Batch(scene, n_worlds=W // P, device=local_rank, disable_cull=args.no_cull) for _ in range(P)]
             for hb in halves:
                 hb.set_scene_forces(desc)
-            half = nrec // 2
+            part = nrec // P
             h_in.copy_(start_state)
-            bufs = [(h_in[:half], h_out[:half]), (h_in[half:], h_out[half:])]
+            bufs = [(h_in[i * part:(i + 1) * part], h_out[i * part:(i + 1) * part]) for i in range(P)]
             for hb, (a, b) in zip(halves, bufs):
                 hb.step_host(a.data_ptr(), b.data_ptr(), DT, SUBSTEPS, ITERS, True)  # warm-up (graph capture)
             h_in.copy_(start_state)
-            gate = threading.Barrier(3)
+            gate = threading.Barrier(P + 1)
 
             def drive(hb, a, b):
                 gate.wait()
@@ -358,7 +360,7 @@ def run_ours(args):
             single = dict(line["e2e"])
             piped = {"value": units / piped_s, "unit": "body-substeps/s", "h2d_bytes_per_step": nrec * 8, "d2h_bytes_per_step": nrec * 8,
                      "ms_per_step": 1e3 * piped_s / args.steps, "status_bits": bits,
-                     "api": "rp_batch_step_host on two half-size batches from two host threads (copies of one half overlap kernels of the other)"}
+                     "api": "rp_batch_step_host on %d sub-batches of %d worlds from %d host threads (the copies of one overlap the kernels of the others)" % (P, W // P, P)}
             if piped["value"] > single["value"] and bits == 0:
                 line["e2e"] = piped
                 line["e2e_single_batch"] = single

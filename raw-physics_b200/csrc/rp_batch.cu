@@ -29,6 +29,9 @@ static int fail(int code, const std::string& msg) {
 		}                                                                                                              \
 	} while (0)
 
+#ifndef RP_CULL_CTAS_PER_SM
+#define RP_CULL_CTAS_PER_SM 16  // k_cull grid: CTAs of 8 warps per SM's worth of pair indices (a warp walks the rest in trips)
+#endif
 #define RP_SCHED_SMEM_MAX (160 * 1024)  // dynamic shared memory k_schedule<true> may ask for (opted in at batch creation)
 
 struct rp_scene {
@@ -372,7 +375,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	{
 		// k_cull: grid.y = groups of 32 worlds (lane = world), a CTA's 8 warps take 8 pair indices per trip
 		const int groups = (d.W + 31) / 32;
-		int want = (b->sm_count * 16 + groups - 1) / groups;
+		int want = (b->sm_count * RP_CULL_CTAS_PER_SM + groups - 1) / groups;
 		int most = (d.max_pairs + 7) / 8;
 		b->cull_chunks = std::max(1, std::min(want, most));
 	}

@@ -625,7 +625,7 @@ __device__ __forceinline__ unsigned int warp_append(unsigned int* counter, bool 
 // pair yields no contacts, exactly as if GJK had run. Survivors go to the dense candidate list of k_gjk.
 #define RP_CULL_MARGIN 1e-7
 #ifndef RP_CULL_ILP
-#define RP_CULL_ILP 2
+#define RP_CULL_ILP 1
 #endif
 // Work order. The lanes of a warp take the SAME pair index of 32 CONSECUTIVE worlds (lane = world, warp = pair index),
 // and every list built downstream (candidates -> hits -> level lists) keeps that order. The worlds of a batch are
