@@ -29,7 +29,7 @@
 #define RP_MINB_POS 3
 #endif
 #ifndef RP_MINB_VEL
-#define RP_MINB_VEL 3
+#define RP_MINB_VEL 4
 #endif
 
 #define RP_GJK_THREADS 64
@@ -1063,17 +1063,22 @@ __global__ void __launch_bounds__(128) k_derive(DevView d, double h) {
 }
 
 // Loads what the velocity pass needs of one body. If the body's velocities have not been derived in this substep yet
-// (first velocity-level unit that touches it), derives them here (pbd.cpp:623-643) and returns true: the caller then
-// also stores the prev-velocities and stamps the body.
-__device__ __forceinline__ bool load_for_velocity(Body& b, const DynRef& r, int active, int stamp, int epoch, double h) {
+// (first velocity-level unit that touches it), derives them here (pbd.cpp:623-643), stores the previous velocities the
+// derivation leaves (they are part of the body's state) and stamps the body; returns true if it did. The previous
+// velocities are kept in registers only if the restitution term will read them (`need_prev`).
+__device__ __forceinline__ bool load_for_velocity(Body& b, const DynRef& r, int active, int* stamp, int epoch, double h, bool need_prev) {
 	b.q = ld4(r, DF_Q); b.v = ld3(r, DF_V); b.w = ld3(r, DF_W);
 	b.active = active;
-	if (!(b.fixed || !b.active) && stamp != epoch) {
+	if (!(b.fixed || !b.active) && *stamp != epoch) {
 		b.x = ld3(r, DF_X); b.px = ld3(r, DF_PX); b.pq = ld4(r, DF_PQ);
 		derive_velocity(b, h);
+		st3(r, DF_PV, b.pv); st3(r, DF_PW, b.pw);
+		*stamp = epoch;
 		return true;
 	}
-	b.pv = ld3(r, DF_PV); b.pw = ld3(r, DF_PW);
+	if (need_prev) {
+		b.pv = ld3(r, DF_PV); b.pw = ld3(r, DF_PW);
+	}
 	return false;
 }
 
@@ -1090,9 +1095,6 @@ __device__ __forceinline__ void vel_level(const DevView& d, double h, int level)
 	const double* cs = 0;
 	DynRef r1, r2;
 	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
-	int* stamp1 = 0;
-	int* stamp2 = 0;
-	bool fresh1 = false, fresh2 = false;
 	AngPre tens;
 	tens.ii1 = tens.ii2 = zero_m3();
 	const int epoch = *d.epoch;
@@ -1107,20 +1109,22 @@ __device__ __forceinline__ void vel_level(const DevView& d, double h, int level)
 			const int w = (int)item.x;
 			const size_t pg = pidx(d, (int)item.y, w);
 			cnt = d.pair_ccnt[pg];
-			const PairRec pr = d.pairs[pg];
-			normal = d.pair_normal[pg];
-			cs = contact_ptr(d, w, d.pair_coff[pg]);
-			load_static(b1, d, pr.a);
-			load_static(b2, d, pr.b);
-			r1 = dyn_ref(d, w, pr.a);
-			r2 = dyn_ref(d, w, pr.b);
-			stamp1 = d.vstamp + bidx(d, pr.a, w);
-			stamp2 = d.vstamp + bidx(d, pr.b, w);
-			fresh1 = load_for_velocity(b1, r1, d.active[bidx(d, pr.a, w)], *stamp1, epoch, h);
-			fresh2 = load_for_velocity(b2, r2, d.active[bidx(d, pr.b, w)], *stamp2, epoch, h);
-			tens = vel_tensors(b1, b2);
-			c = 0;
-			have = cnt > 0;
+			if (cnt > 0) {  // (k_manifold only lists pairs with contacts)
+				const PairRec pr = d.pairs[pg];
+				normal = d.pair_normal[pg];
+				cs = contact_ptr(d, w, d.pair_coff[pg]);
+				load_static(b1, d, pr.a);
+				load_static(b2, d, pr.b);
+				r1 = dyn_ref(d, w, pr.a);
+				r2 = dyn_ref(d, w, pr.b);
+				// restitution 0 on either side: the velocity solve never reads the previous velocities (solve_contact_velocity)
+				const bool need_prev = b1.rest * b2.rest != 0.0;
+				load_for_velocity(b1, r1, d.active[bidx(d, pr.a, w)], d.vstamp + bidx(d, pr.a, w), epoch, h, need_prev);
+				load_for_velocity(b2, r2, d.active[bidx(d, pr.b, w)], d.vstamp + bidx(d, pr.b, w), epoch, h, need_prev);
+				tens = vel_tensors(b1, b2);
+				c = 0;
+				have = true;
+			}
 		}
 		if (!__any_sync(0xffffffffu, have)) {
 			if (q.empty()) break;
@@ -1132,8 +1136,6 @@ __device__ __forceinline__ void vel_level(const DevView& d, double h, int level)
 			if (++c == cnt) {
 				if (!b1.fixed) { st3(r1, DF_V, b1.v); st3(r1, DF_W, b1.w); }
 				if (!b2.fixed) { st3(r2, DF_V, b2.v); st3(r2, DF_W, b2.w); }
-				if (fresh1) { st3(r1, DF_PV, b1.pv); st3(r1, DF_PW, b1.pw); *stamp1 = epoch; }
-				if (fresh2) { st3(r2, DF_PV, b2.pv); st3(r2, DF_PW, b2.pw); *stamp2 = epoch; }
 				have = false;
 			}
 		}

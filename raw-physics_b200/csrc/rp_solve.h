@@ -302,10 +302,16 @@ RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, do
 	double fn = fdiv(c.lambda_n, h);
 	double fact = RP_MINF(mu * fabs(fn), length(vt));
 	dv = add(dv, scale(-fact, normalize(vt)));
-	V3 vtil = sub(add(b1.pv, cross(b1.pw, p.r1)), add(b2.pv, cross(b2.pw, p.r2)));
-	double vn_til = dot(n, vtil);
 	double e = b1.rest * b2.rest;
-	fact = -vn + RP_MINF(-e * vn_til, 0.0);
+	if (e == 0.0) {
+		// -e * vn_til is a signed zero (or NaN), which the reference's MIN(x, 0) turns into +0.0 either way: the previous
+		// velocities are not needed at all (callers may leave pv / pw unloaded when either restitution is zero)
+		fact = -vn + 0.0;
+	} else {
+		V3 vtil = sub(add(b1.pv, cross(b1.pw, p.r1)), add(b2.pv, cross(b2.pw, p.r2)));
+		double vn_til = dot(n, vtil);
+		fact = -vn + RP_MINF(-e * vn_til, 0.0);
+	}
 	dv = add(dv, scale(fact, n));
 	double w1 = inv_mass_along(b1, p.r1, p.ii1, n);
 	double w2 = inv_mass_along(b2, p.r2, p.ii2, n);
