@@ -77,8 +77,10 @@ def ncu_traffic(kernel):
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
         return None
-    d = json.load(open(p)).get("kernels", {}).get(kernel)
-    return None if d is None else d["dram_read"] + d["dram_write"]
+    for name, d in json.load(open(p)).get("kernels", {}).items():
+        if name.split("<")[0] == kernel:  # template instances are listed as k_solve_pos<0>
+            return d["dram_read"] + d["dram_write"]
+    return None
 
 
 def measured_peaks():
