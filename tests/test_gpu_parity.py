@@ -285,3 +285,66 @@ def test_config5_joint_worlds_sharded(pkg, oracle_flavour):
         got = s.state()
         assert (got == got[0]).all()
         assert np.abs(got[0, :, :7] - want[:, :7]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("name,substeps,iters,dt", [("stack", 5, 3, 1.0 / 60.0), ("tumble", 8, 2, 1.0 / 90.0), ("hinge_joints", 10, 4, 1.0 / 60.0)])
+def test_other_step_settings(pkg, oracle_flavour, name, substeps, iters, dt):
+    """pbd_simulate's remaining arguments (pbd.cpp:464-472): dt, num_substeps and num_pos_iters other than the examples'
+    1/60, 20, 1 -- several positional sweeps per substep go through the same level schedule."""
+    sc = scenes.BUILDERS[name]()
+    b = make(pkg, sc, n_worlds=2)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    for f in range(40):
+        b.step(dt=dt, substeps=substeps, iters=iters, collisions=sc.collisions)
+        o.step(dt=dt, substeps=substeps, iters=iters, collisions=sc.collisions)
+    got, want = b.state()[0, :, :15], o.state()
+    if sc.constraints:
+        assert np.abs(got[:, :7] - want[:, :7]).max() <= 1e-9
+    else:
+        assert np.array_equal(got, want)
+    assert not b.status().any()
+
+
+def test_collisions_disabled_and_zero_dt(pkg, oracle_flavour):
+    """enable_collisions = false skips broadphase-to-contact work entirely (pbd.cpp:584); dt <= 0 is a no-op (:471)."""
+    sc = scenes.stack()
+    b = make(pkg, sc, n_worlds=2)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    before = b.state()
+    b.step(dt=0.0)
+    b.step(dt=-1.0)
+    assert np.array_equal(b.state(), before)
+    for f in range(20):
+        b.step(collisions=False)
+        o.step(collisions=False)
+    assert np.array_equal(b.state()[0, :, :15], o.state())
+    assert b.counters()["pair_tests"] == 0
+
+
+@pytest.mark.parametrize("n_worlds", [1, 31, 33])
+def test_ragged_world_counts(pkg, oracle_flavour, n_worlds):
+    """world counts that do not fill a warp's 32 lanes: the padded lanes must neither disturb the live ones nor be visible"""
+    sc = scenes.stack()
+    b = make(pkg, sc, n_worlds=n_worlds)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    for f in range(30):
+        step(b, sc)
+        o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+    got = b.state()
+    assert got.shape[0] == n_worlds and (got == got[0]).all()
+    assert np.array_equal(got[0, :, :15], o.state())
+    assert b.status().shape == (n_worlds,) and not b.status().any()
+
+
+def test_world_without_pairs(pkg, oracle_flavour):
+    """a single free body: empty broadphase, empty schedule, nothing to solve -- ballistic motion only"""
+    sc = scenes.Scene("lonely")
+    sc.bodies.append(scenes.BodyDesc((0.0, 5.0, 0.0), scenes.IDENT, 2.0, False, [scenes.hull("cube", (1.0, 1.0, 1.0))]))
+    b = make(pkg, sc, n_worlds=3)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    for f in range(10):
+        step(b, sc)
+        o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+    assert np.array_equal(b.state()[0, :, :15], o.state())
+    c = b.counters()
+    assert c["broad_pairs"] == 0 and c["contacts"] == 0 and not b.status().any()
