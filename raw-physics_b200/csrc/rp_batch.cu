@@ -347,7 +347,10 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	DevView& d = b->d;
 	memset(&d, 0, sizeof(d));
 	d.W = (int)n_worlds;
-	d.WS = (d.W + 31) / 32 * 32;
+	// world stride: a multiple of 32 so that a warp's 32 worlds start on an aligned line -- except for batches smaller than
+	// a warp (one large scene), where padding would only put 31 unused slots between consecutive bodies, pairs and
+	// contacts of the one world and leave the item-per-lane kernels (GJK, EPA, clipping, the sweeps) with strided accesses
+	d.WS = d.W >= 32 ? (d.W + 31) / 32 * 32 : d.W;
 	d.NB = (int)s.bodies.size();
 	d.NC = (int)s.colliders.size();
 	d.NJ = (int)s.joints.size();
@@ -611,9 +614,9 @@ static void launch_schedule(rp_batch* b, int collisions) {
 static void launch_broad(rp_batch* b) {
 	const DevView& d = b->d;
 	if (d.n_cells > 0) {
-		const dim3 grid((d.n_cells + 7) / 8, d.WS / 32), blk(32, 8);
+		const dim3 grid((d.n_cells + 7) / 8, (d.W + 31) / 32), blk(32, 8);
 		k_broad_cells<<<grid, blk, 0, b->stream>>>(d);
-		k_broad_scan<<<d.WS / 32, dim3(32, RP_BROAD_SEGS), 0, b->stream>>>(d);
+		k_broad_scan<<<(d.W + 31) / 32, dim3(32, RP_BROAD_SEGS), 0, b->stream>>>(d);
 		k_broad_write<<<grid, blk, 0, b->stream>>>(d);
 	}
 }

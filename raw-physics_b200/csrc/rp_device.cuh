@@ -45,7 +45,7 @@ enum { CNT_PAIR_TESTS = 0, CNT_HITS = 1, CNT_CONTACTS = 2, CNT_BROAD_PAIRS = 3, 
 
 struct DevView {
 	int W, NB, NC, NJ, TV, TN;
-	int WS;              // world stride of every world-minor array: W rounded up to a multiple of 32
+	int WS;              // world stride of every world-minor array: W rounded up to a multiple of 32 (W itself when W < 32)
 	int max_pairs, max_contacts, max_units;
 	double lin_sleep, ang_sleep, sleep_time;
 	// template
