@@ -77,9 +77,9 @@ struct DevView {
 	int* pair_level;     // [max_pairs][WS] dependency level of each broadphase pair (0 = skipped this frame)
 	int* lvl_hist;       // [max_levels + 2][WS] schedule scratch (per-world level histogram)
 	double* aabb;        // [NC][6][WS] world-space bounds of every collider (min xyz, max xyz)
-	uint2* cands;        // [W * max_pairs] (world, pair) that survived the skip rule and the bounds cull
+	uint4* cands;        // [W * max_pairs] (world, pair, collider a, collider b) that survived the skip rule and the bounds cull
 	unsigned int* cand_count;
-	unsigned int* hits;  // [W * max_pairs] indices (into cands) of the colliding candidates, dense
+	uint4* hits;         // [W * max_pairs] the colliding candidates' records, dense (one load tells EPA / clipping where their inputs are)
 	V3* simplex;         // [W * max_pairs][4] final GJK tetrahedron of each hit
 	unsigned int* hit_count;
 	EpaOut* epa_out;     // [W * max_pairs] per hit

@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 			const int p = p0 + u * stride;
 			if (in[u]) d.pair_ccnt[pidx(d, p, w)] = 0;
 			const unsigned int slot = warp_append(d.cand_count, keep[u]);
-			if (keep[u]) d.cands[slot] = make_uint2((unsigned int)w, (unsigned int)p);
+			if (keep[u]) d.cands[slot] = make_uint4((unsigned int)w, (unsigned int)p, (unsigned int)pr[u].ca, (unsigned int)pr[u].cb);
 		}
 	}
 	for (int o = 16; o > 0; o >>= 1) tested += __shfl_down_sync(0xffffffffu, tested, o);
@@ -738,12 +738,12 @@ __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) 
 		bool hit = false;
 		Simplex s;
 		s.a = s.b = s.c = s.d = v3(0.0, 0.0, 0.0);
+		uint4 cd = make_uint4(0u, 0u, 0u, 0u);
 		if (ci < nc) {
-			const uint2 cd = d.cands[ci];
+			cd = d.cands[ci];  // (world, pair, collider a, collider b): everything the narrowphase needs to find its inputs
 			const int w = (int)cd.x;
-			const PairRec pr = d.pairs[pidx(d, (int)cd.y, w)];
-			Shape A = dev_shape(d, d.cols[pr.ca], w);
-			Shape B = dev_shape(d, d.cols[pr.cb], w);
+			Shape A = dev_shape(d, d.cols[cd.z], w);
+			Shape B = dev_shape(d, d.cols[cd.w], w);
 			int st = 0;
 			if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
 				V3 n;
@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) 
 		}
 		const unsigned int slot = warp_append(d.hit_count, hit);
 		if (hit) {
-			d.hits[slot] = ci;
+			d.hits[slot] = cd;
 			V3* o = d.simplex + (size_t)slot * 4;
 			o[0] = s.a; o[1] = s.b; o[2] = s.c; o[3] = s.d;
 		}
@@ -779,11 +779,10 @@ __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) 
 	__shared__ double s_stage[RP_GJK_STAGE * RP_EPA_THREADS];
 	EpaScratch e;
 	for (unsigned int hi = blockIdx.x * blockDim.x + threadIdx.x; hi < nh; hi += gridDim.x * blockDim.x) {
-		const uint2 cd = d.cands[d.hits[hi]];
+		const uint4 cd = d.hits[hi];
 		const int w = (int)cd.x;
-		const PairRec pr = d.pairs[pidx(d, (int)cd.y, w)];
-		Shape A = dev_shape(d, d.cols[pr.ca], w);
-		Shape B = dev_shape(d, d.cols[pr.cb], w);
+		Shape A = dev_shape(d, d.cols[cd.z], w);
+		Shape B = dev_shape(d, d.cols[cd.w], w);
 		EpaOut out;
 		out.ok = 0; out.pad = 0; out.depth = 0.0; out.normal = v3(0.0, 0.0, 0.0);
 		int st = 0;
@@ -841,14 +840,13 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 		int n = 0, lvl = -1, w = 0, pair = 0;
 		if (hi < nh) {
 			const EpaOut eo = d.epa_out[hi];
-			const uint2 cd = d.cands[d.hits[hi]];
+			const uint4 cd = d.hits[hi];
 			w = (int)cd.x; pair = (int)cd.y;
 			const size_t pg = pidx(d, pair, w);
-			const PairRec pr = d.pairs[pg];
 			int st = 0;
 			if (eo.ok) {
-				Shape A = dev_shape(d, d.cols[pr.ca], w);
-				Shape B = dev_shape(d, d.cols[pr.cb], w);
+				Shape A = dev_shape(d, d.cols[cd.z], w);
+				Shape B = dev_shape(d, d.cols[cd.w], w);
 				StageSink sink;
 				sink.stage = sc.stage;
 				sink.n = 0;
@@ -867,6 +865,7 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 					n = d.max_contacts - off;
 					if (n < 0) n = 0;
 				}
+				const PairRec pr = d.pairs[pg];
 				const DynRef ra = dyn_ref(d, w, pr.a);
 				const DynRef rb = dyn_ref(d, w, pr.b);
 				Body b1, b2;
