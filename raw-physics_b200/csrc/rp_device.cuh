@@ -35,6 +35,12 @@ struct BodyStatic {
 struct __align__(16) PairRec {  // one broadphase pair, expanded to collider granularity: bodies a < b, global collider indices ca, cb
 	int a, b, ca, cb;
 };
+struct __align__(16) SolveItem {  // one unit of a sweep: a collider pair's manifold, with what the solver needs to start on it
+	int w, a, b;      // world, bodies (a < b)
+	int coff, cnt;    // the manifold's run in the world's contact buffer
+	int pad;
+	V3 normal;        // shared by the whole manifold
+};
 struct EpaOut {  // result of EPA (or the analytic sphere-sphere test) for one hit: work item of k_manifold
 	V3 normal;
 	double depth;
@@ -89,7 +95,7 @@ struct DevView {
 	int* lvl_off;        // [max_levels + 2] exclusive scan of lvl_cap
 	int* lvl_fill;       // [max_levels + 2] pairs of level l with contacts (per substep)
 	int* lvl_max;        // [1] deepest level of the frame over all worlds
-	uint2* lvl_items;    // [W * max_pairs] (world, pair), level l occupies [lvl_off[l], lvl_off[l] + lvl_fill[l])
+	SolveItem* lvl_items;  // [W * max_pairs] level l occupies [lvl_off[l], lvl_off[l] + lvl_fill[l])
 	// template-constant schedule of the external constraints (they head the constraint array in every world)
 	const int* joint_sched;   // [NJ] joints sorted by level
 	const int* joint_lptr;    // [joint_levels + 1]

@@ -838,6 +838,9 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 	for (unsigned int h0 = blockIdx.x * blockDim.x; h0 < nh; h0 += gridDim.x * blockDim.x) {
 		const unsigned int hi = h0 + threadIdx.x;
 		int n = 0, lvl = -1, w = 0, pair = 0;
+		SolveItem item;
+		item.w = item.a = item.b = item.coff = item.cnt = item.pad = 0;
+		item.normal = v3(0.0, 0.0, 0.0);
 		if (hi < nh) {
 			const EpaOut eo = d.epa_out[hi];
 			const uint4 cd = d.hits[hi];
@@ -883,10 +886,11 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 				d.pair_ccnt[pg] = n;
 				made += n;
 				if (n > 0) lvl = d.pair_level[pg];
+				item.w = w; item.a = pr.a; item.b = pr.b; item.coff = off; item.cnt = n; item.normal = eo.normal;
 			}
 			if (st) atomicOr(&d.status[w], st);
 		}
-		// append (world, pair) to the list of its level: ranks within the CTA through shared-memory counters, then ONE
+		// append the unit (a self-contained SolveItem: the sweeps start on it after one load) to the list of its level: ranks within the CTA through shared-memory counters, then ONE
 		// global atomic per (CTA, level, end) on a counter line of its own (RP_LVL_STRIDE). A level's list can be filled
 		// from both ends -- small manifolds (<= RP_SMALL_MANIFOLD contacts) from the front, large ones from the back --
 		// which groups manifolds of similar length (order within a level is free: its units commute).
@@ -907,7 +911,7 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 		if (lvl > 0) {
 			const int slot = (lvl < RP_LVL_SMEM ? s_base[2 * lvl + big] : 0) + rank;
 			const int at = big ? d.lvl_off[lvl + 1] - 1 - slot : d.lvl_off[lvl] + slot;
-			d.lvl_items[at] = make_uint2((unsigned int)w, (unsigned int)pair);
+			d.lvl_items[at] = item;
 		}
 	}
 	for (int o = 16; o > 0; o >>= 1) made += __shfl_down_sync(0xffffffffu, made, o);
@@ -979,17 +983,15 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 		const unsigned int got = q.take(!have);
 		if (got != 0xffffffffu) {
 			const int k = (int)got;
-			const uint2 item = d.lvl_items[k < npf ? off0 + k : off1 - 1 - (k - npf)];
-			w = (int)item.x;
-			const size_t pg = pidx(d, (int)item.y, w);
-			cnt = d.pair_ccnt[pg];
-			const PairRec pr = d.pairs[pg];
-			normal = d.pair_normal[pg];
-			cs = contact_ptr(d, w, d.pair_coff[pg]);
-			load_static(b1, d, pr.a);
-			load_static(b2, d, pr.b);
-			r1 = dyn_ref(d, w, pr.a);
-			r2 = dyn_ref(d, w, pr.b);
+			const SolveItem item = d.lvl_items[k < npf ? off0 + k : off1 - 1 - (k - npf)];
+			w = item.w;
+			cnt = item.cnt;
+			normal = item.normal;
+			cs = contact_ptr(d, w, item.coff);
+			load_static(b1, d, item.a);
+			load_static(b2, d, item.b);
+			r1 = dyn_ref(d, w, item.a);
+			r2 = dyn_ref(d, w, item.b);
 			b1.x = ld3(r1, DF_X); b1.q = ld4(r1, DF_Q);
 			b2.x = ld3(r2, DF_X); b2.q = ld4(r2, DF_Q);
 			c = 0;
@@ -1104,14 +1106,13 @@ __device__ __forceinline__ void vel_level(const DevView& d, double h, int level)
 		const unsigned int got = q.take(!have);
 		if (got != 0xffffffffu) {
 			const int k = (int)got;
-			const uint2 item = d.lvl_items[k < npf ? off0 + k : off1 - 1 - (k - npf)];
-			const int w = (int)item.x;
-			const size_t pg = pidx(d, (int)item.y, w);
-			cnt = d.pair_ccnt[pg];
+			const SolveItem item = d.lvl_items[k < npf ? off0 + k : off1 - 1 - (k - npf)];
+			const int w = item.w;
+			cnt = item.cnt;
 			if (cnt > 0) {  // (k_manifold only lists pairs with contacts)
-				const PairRec pr = d.pairs[pg];
-				normal = d.pair_normal[pg];
-				cs = contact_ptr(d, w, d.pair_coff[pg]);
+				const PairRec pr = {item.a, item.b, 0, 0};
+				normal = item.normal;
+				cs = contact_ptr(d, w, item.coff);
 				load_static(b1, d, pr.a);
 				load_static(b2, d, pr.b);
 				r1 = dyn_ref(d, w, pr.a);
