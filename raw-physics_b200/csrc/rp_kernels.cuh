@@ -37,7 +37,6 @@
 #define RP_MANIFOLD_THREADS 128
 #define RP_EPA_THREADS 64
 
-#define RP_LVL_SMEM 64     // levels ranked through shared memory in k_manifold
 #define RP_LVL_STRIDE 32   // ints between consecutive level fill counters (one 128-byte line each: [0] front, [1] back)
 #ifndef RP_SMALL_MANIFOLD
 #define RP_SMALL_MANIFOLD 1000000  // (off: the refill loops of the solver kernels make manifold length irrelevant)
@@ -832,7 +831,6 @@ struct ManifoldScratch {
 __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manifold(DevView d) {
 	const unsigned int nh = *d.hit_count;
 	ManifoldScratch sc;
-	__shared__ int s_cnt[2 * RP_LVL_SMEM], s_base[2 * RP_LVL_SMEM];
 	int made = 0;
 	const int lane = threadIdx.x & 31;
 	for (unsigned int h0 = blockIdx.x * blockDim.x; h0 < nh; h0 += gridDim.x * blockDim.x) {
@@ -890,28 +888,25 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 			}
 			if (st) atomicOr(&d.status[w], st);
 		}
-		// append the unit (a self-contained SolveItem: the sweeps start on it after one load) to the list of its level: ranks within the CTA through shared-memory counters, then ONE
-		// global atomic per (CTA, level, end) on a counter line of its own (RP_LVL_STRIDE). A level's list can be filled
-		// from both ends -- small manifolds (<= RP_SMALL_MANIFOLD contacts) from the front, large ones from the back --
-		// which groups manifolds of similar length (order within a level is free: its units commute).
-		__syncthreads();
-		if (threadIdx.x < 2 * RP_LVL_SMEM) s_cnt[threadIdx.x] = 0;  // RP_MANIFOLD_THREADS >= 2 * RP_LVL_SMEM
-		__syncthreads();
-		int rank = 0;
-		const int big = n > RP_SMALL_MANIFOLD ? 1 : 0;
-		if (lvl > 0) {
-			if (lvl < RP_LVL_SMEM) rank = atomicAdd(&s_cnt[2 * lvl + big], 1);
-			else rank = atomicAdd(&d.lvl_fill[(size_t)lvl * RP_LVL_STRIDE + big], 1);  // very deep schedules: direct
-		}
-		__syncthreads();
-		if (threadIdx.x < 2 * RP_LVL_SMEM && s_cnt[threadIdx.x] > 0) {
-			s_base[threadIdx.x] = atomicAdd(&d.lvl_fill[(size_t)(threadIdx.x >> 1) * RP_LVL_STRIDE + (threadIdx.x & 1)], s_cnt[threadIdx.x]);
-		}
-		__syncthreads();
-		if (lvl > 0) {
-			const int slot = (lvl < RP_LVL_SMEM ? s_base[2 * lvl + big] : 0) + rank;
-			const int at = big ? d.lvl_off[lvl + 1] - 1 - slot : d.lvl_off[lvl] + slot;
-			d.lvl_items[at] = item;
+		// append the unit (a self-contained SolveItem: the sweeps start on it after one load) to the list of its level.
+		// Ranks come from the WARP: lanes with the same (level, end) elect a leader that takes their slots with one
+		// atomic on that level's fill counter (each counter on a line of its own, RP_LVL_STRIDE). With lane = world the
+		// lanes of a warp hold the same pair of neighbouring worlds and so, as a rule, the same level: one atomic per warp
+		// and no CTA-wide barrier (four __syncthreads per trip made every warp wait for the CTA's slowest clipping case).
+		// A level's list can be filled from both ends -- small manifolds (<= RP_SMALL_MANIFOLD contacts) from the front,
+		// large ones from the back -- which groups manifolds of similar length (order within a level is free).
+		{
+			const int big = n > RP_SMALL_MANIFOLD ? 1 : 0;
+			const int key = lvl > 0 ? 2 * lvl + big : -1;
+			const unsigned int peers = __match_any_sync(0xffffffffu, key);
+			int slot = 0;
+			if (lvl > 0) {
+				const int leader = __ffs(peers) - 1;
+				if (lane == leader) slot = atomicAdd(&d.lvl_fill[(size_t)lvl * RP_LVL_STRIDE + big], __popc(peers));
+				slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1u));
+				const int at = big ? d.lvl_off[lvl + 1] - 1 - slot : d.lvl_off[lvl] + slot;
+				d.lvl_items[at] = item;
+			}
 		}
 	}
 	for (int o = 16; o > 0; o >>= 1) made += __shfl_down_sync(0xffffffffu, made, o);
