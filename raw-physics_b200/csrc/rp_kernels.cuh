@@ -556,13 +556,15 @@ __global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate
 	const Pose34 M = model_matrix(body.q, body.x);
 	for (int c = s.col0; c < s.col0 + s.ncol; ++c) {
 		const ColliderDesc cd = d.cols[c];
-		double* bb = d.aabb + (size_t)c * 6 * S + w;
+		// bounds are kept in float, lower ends rounded down and upper ends up: still boxes AROUND the vertex sets, so the
+		// cull stays exact-safe (it can only keep a pair it might have dropped), at half the bytes written here and read there
+		float* bb = d.aabb + (size_t)c * 6 * S + w;
 		double* tv = d.tv + (size_t)cd.tv0 * 3 * S + w;
 		if (cd.type == SHAPE_SPHERE) {
 			tv[0] = body.x.x; tv[S] = body.x.y; tv[2 * S] = body.x.z;
 			const double rad = (double)cd.radius;
-			bb[0] = body.x.x - rad; bb[S] = body.x.y - rad; bb[2 * S] = body.x.z - rad;
-			bb[3 * S] = body.x.x + rad; bb[4 * S] = body.x.y + rad; bb[5 * S] = body.x.z + rad;
+			bb[0] = __double2float_rd(body.x.x - rad); bb[S] = __double2float_rd(body.x.y - rad); bb[2 * S] = __double2float_rd(body.x.z - rad);
+			bb[3 * S] = __double2float_ru(body.x.x + rad); bb[4 * S] = __double2float_ru(body.x.y + rad); bb[5 * S] = __double2float_ru(body.x.z + rad);
 		} else {
 			const HullTopo t = d.pool.hulls[cd.hull];
 			double* tn = d.tn + (size_t)cd.tn0 * 3 * S + w;
@@ -577,7 +579,8 @@ __global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate
 				const V3 n = transform_normal(M, d.pool.normals[t.face0 + k]);
 				tn[(size_t)(3 * k) * S] = n.x; tn[(size_t)(3 * k + 1) * S] = n.y; tn[(size_t)(3 * k + 2) * S] = n.z;
 			}
-			bb[0] = lo0; bb[S] = lo1; bb[2 * S] = lo2; bb[3 * S] = hi0; bb[4 * S] = hi1; bb[5 * S] = hi2;
+			bb[0] = __double2float_rd(lo0); bb[S] = __double2float_rd(lo1); bb[2 * S] = __double2float_rd(lo2);
+			bb[3 * S] = __double2float_ru(hi0); bb[4 * S] = __double2float_ru(hi1); bb[5 * S] = __double2float_ru(hi2);
 		}
 	}
 }
@@ -666,8 +669,8 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 			fa[u] = d.bstat[pr[u].a].fixed; fb[u] = d.bstat[pr[u].b].fixed;
 			aa[u] = active[pr[u].a * S]; ab[u] = active[pr[u].b * S];
 			ta[u] = d.cols[pr[u].ca].type; tb[u] = d.cols[pr[u].cb].type;
-			const double* pa = d.aabb + (size_t)pr[u].ca * 6 * S + w0;
-			const double* pb = d.aabb + (size_t)pr[u].cb * 6 * S + w0;
+			const float* pa = d.aabb + (size_t)pr[u].ca * 6 * S + w0;
+			const float* pb = d.aabb + (size_t)pr[u].cb * 6 * S + w0;
 			lo_a[u] = pa[S]; hi_a[u] = pa[4 * S]; lo_b[u] = pb[S]; hi_b[u] = pb[4 * S];
 		}
 #pragma unroll
@@ -681,8 +684,8 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 #pragma unroll
 		for (int u = 0; u < RP_CULL_ILP; ++u) {
 			if (__any_sync(0xffffffffu, bounds[u])) {
-				const double* pa = d.aabb + (size_t)pr[u].ca * 6 * S + w0;
-				const double* pb = d.aabb + (size_t)pr[u].cb * 6 * S + w0;
+				const float* pa = d.aabb + (size_t)pr[u].ca * 6 * S + w0;
+				const float* pb = d.aabb + (size_t)pr[u].cb * 6 * S + w0;
 				const double ax0 = pa[0], ax1 = pa[3 * S], az0 = pa[2 * S], az1 = pa[5 * S];
 				const double bx0 = pb[0], bx1 = pb[3 * S], bz0 = pb[2 * S], bz1 = pb[5 * S];
 				if (bounds[u] && (ax0 - bx1 > RP_CULL_MARGIN || bx0 - ax1 > RP_CULL_MARGIN || az0 - bz1 > RP_CULL_MARGIN ||
