@@ -522,6 +522,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.pair_level, SP))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_hist, WS * (d.max_levels + 2)))) return rc;
 	if ((rc = dev_alloc(b, &d.aabb, WS * std::max(d.NC, 1) * 6))) return rc;
+	if ((rc = dev_alloc(b, &d.geom_stamp, WS * std::max(d.NC, 1)))) return rc;
 	if ((rc = dev_alloc(b, &d.cands, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.cand_count, 1))) return rc;
 	if ((rc = dev_alloc(b, &d.simplex, WP * 4, false))) return rc;
@@ -650,7 +651,10 @@ static void enqueue_integrate(rp_batch* b, double h) {
 // grid of the per-hit kernel: the hit count lives on the device, so the launch covers the candidate capacity in
 // grid-stride trips of at most this many CTAs
 static unsigned int manifold_grid(const rp_batch* b) { return (unsigned int)b->sm_count * 16u; }
-static void launch_cull(rp_batch* b) { k_cull<<<dim3(b->cull_chunks, (b->d.W + 31) / 32), 256, 0, b->stream>>>(b->d, b->cull); }
+static void launch_cull(rp_batch* b) {
+	k_cull<<<dim3(b->cull_chunks, (b->d.W + 31) / 32), 256, 0, b->stream>>>(b->d, b->cull);
+	k_transform<<<dim3(b->d.NB, (b->d.W + RP_INT_THREADS - 1) / RP_INT_THREADS), RP_INT_THREADS, 0, b->stream>>>(b->d);
+}
 static void launch_gjk(rp_batch* b) { k_gjk<<<b->sm_count * 16, RP_GJK_THREADS, 0, b->stream>>>(b->d); }
 static void launch_manifold(rp_batch* b) {
 	k_epa<<<b->sm_count * 16, RP_EPA_THREADS, 0, b->stream>>>(b->d);

@@ -82,6 +82,7 @@ struct DevView {
 	unsigned long long* colour_tab;  // [NB][WS] schedule scratch of the coloured order (when the table does not fit shared memory)
 	int* pair_level;     // [max_pairs][WS] dependency level of each broadphase pair (0 = skipped this frame)
 	int* lvl_hist;       // [max_levels + 2][WS] schedule scratch (per-world level histogram)
+	int* geom_stamp;     // [NC][WS] substep counter value at which k_cull last asked for the collider's transformed geometry
 	float* aabb;         // [NC][6][WS] world-space bounds of every collider (min xyz rounded down, max xyz rounded up)
 	uint4* cands;        // [W * max_pairs] (world, pair, collider a, collider b) that survived the skip rule and the bounds cull
 	unsigned int* cand_count;

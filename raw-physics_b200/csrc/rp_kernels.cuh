@@ -553,34 +553,69 @@ __global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate
 	if (moving) {
 		st3(r, DF_X, body.x); st4(r, DF_Q, body.q); st3(r, DF_V, body.v); st3(r, DF_W, body.w);
 	}
+	// collider_update (collider.cpp:409-445) is split in two. Here: the world-space bounds of every collider of the body
+	// (from the transformed vertices, which stay in registers) for k_cull. The transformed vertices and face normals
+	// themselves are written by k_transform, after the cull, and only for colliders that are part of a surviving
+	// candidate pair: geometry nothing will look at is not written (it is the larger half of what this kernel, which runs
+	// at the HBM roof, used to store).
 	const Pose34 M = model_matrix(body.q, body.x);
 	for (int c = s.col0; c < s.col0 + s.ncol; ++c) {
 		const ColliderDesc cd = d.cols[c];
 		// bounds are kept in float, lower ends rounded down and upper ends up: still boxes AROUND the vertex sets, so the
 		// cull stays exact-safe (it can only keep a pair it might have dropped), at half the bytes written here and read there
 		float* bb = d.aabb + (size_t)c * 6 * S + w;
-		double* tv = d.tv + (size_t)cd.tv0 * 3 * S + w;
 		if (cd.type == SHAPE_SPHERE) {
-			tv[0] = body.x.x; tv[S] = body.x.y; tv[2 * S] = body.x.z;
 			const double rad = (double)cd.radius;
 			bb[0] = __double2float_rd(body.x.x - rad); bb[S] = __double2float_rd(body.x.y - rad); bb[2 * S] = __double2float_rd(body.x.z - rad);
 			bb[3 * S] = __double2float_ru(body.x.x + rad); bb[4 * S] = __double2float_ru(body.x.y + rad); bb[5 * S] = __double2float_ru(body.x.z + rad);
 		} else {
 			const HullTopo t = d.pool.hulls[cd.hull];
-			double* tn = d.tn + (size_t)cd.tn0 * 3 * S + w;
 			double lo0 = 1.7976931348623157e308, lo1 = lo0, lo2 = lo0, hi0 = -lo0, hi1 = -lo0, hi2 = -lo0;
 			for (int k = 0; k < t.nv; ++k) {
 				const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
-				tv[(size_t)(3 * k) * S] = p.x; tv[(size_t)(3 * k + 1) * S] = p.y; tv[(size_t)(3 * k + 2) * S] = p.z;
 				lo0 = fmin(lo0, p.x); lo1 = fmin(lo1, p.y); lo2 = fmin(lo2, p.z);
 				hi0 = fmax(hi0, p.x); hi1 = fmax(hi1, p.y); hi2 = fmax(hi2, p.z);
+			}
+			bb[0] = __double2float_rd(lo0); bb[S] = __double2float_rd(lo1); bb[2 * S] = __double2float_rd(lo2);
+			bb[3 * S] = __double2float_ru(hi0); bb[4 * S] = __double2float_ru(hi1); bb[5 * S] = __double2float_ru(hi2);
+		}
+	}
+}
+
+// collider_update's other half (collider.cpp:409-445), after k_cull: transformed vertices and re-normalised face normals
+// of the colliders k_cull marked (geom_stamp == this substep) -- the ones GJK, EPA or clipping will read. Same pose, same
+// operations as the reference's per-pair calls (pbd.cpp:598-599), so the same bits. Thread = (body, world), lane = world.
+__global__ void __launch_bounds__(RP_INT_THREADS) k_transform(DevView d) {
+	const int w = blockIdx.y * RP_INT_THREADS + threadIdx.x;
+	const int b = blockIdx.x;
+	if (w >= d.W) return;
+	const int epoch = *d.epoch;
+	const size_t S = d.WS;
+	const BodyStatic s = d.bstat[b];
+	bool any = false;
+	for (int c = s.col0; c < s.col0 + s.ncol; ++c) any = any || d.geom_stamp[(size_t)c * S + w] == epoch;
+	if (!any) return;
+	const DynRef r = dyn_ref(d, w, b);
+	const V3 x = ld3(r, DF_X);
+	const Q4 q = ld4(r, DF_Q);
+	const Pose34 M = model_matrix(q, x);
+	for (int c = s.col0; c < s.col0 + s.ncol; ++c) {
+		if (d.geom_stamp[(size_t)c * S + w] != epoch) continue;
+		const ColliderDesc cd = d.cols[c];
+		double* tv = d.tv + (size_t)cd.tv0 * 3 * S + w;
+		if (cd.type == SHAPE_SPHERE) {
+			tv[0] = x.x; tv[S] = x.y; tv[2 * S] = x.z;
+		} else {
+			const HullTopo t = d.pool.hulls[cd.hull];
+			double* tn = d.tn + (size_t)cd.tn0 * 3 * S + w;
+			for (int k = 0; k < t.nv; ++k) {
+				const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
+				tv[(size_t)(3 * k) * S] = p.x; tv[(size_t)(3 * k + 1) * S] = p.y; tv[(size_t)(3 * k + 2) * S] = p.z;
 			}
 			for (int k = 0; k < t.nf; ++k) {
 				const V3 n = transform_normal(M, d.pool.normals[t.face0 + k]);
 				tn[(size_t)(3 * k) * S] = n.x; tn[(size_t)(3 * k + 1) * S] = n.y; tn[(size_t)(3 * k + 2) * S] = n.z;
 			}
-			bb[0] = __double2float_rd(lo0); bb[S] = __double2float_rd(lo1); bb[2 * S] = __double2float_rd(lo2);
-			bb[3 * S] = __double2float_ru(hi0); bb[4 * S] = __double2float_ru(hi1); bb[5 * S] = __double2float_ru(hi2);
 		}
 	}
 }
@@ -645,6 +680,7 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 	const int w0 = wlive ? w : 0;
 	const int* active = d.active + w0;
 	const size_t S = d.WS;
+	const int epoch = *d.epoch;
 	int tested = 0;
 	const int warps_per_cta = blockDim.x >> 5;
 	const int stride = gridDim.x * warps_per_cta;
@@ -697,7 +733,12 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 			const int p = p0 + u * stride;
 			if (in[u]) d.pair_ccnt[pidx(d, p, w)] = 0;
 			const unsigned int slot = warp_append(d.cand_count, keep[u]);
-			if (keep[u]) d.cands[slot] = make_uint4((unsigned int)w, (unsigned int)p, (unsigned int)pr[u].ca, (unsigned int)pr[u].cb);
+			if (keep[u]) {
+				d.cands[slot] = make_uint4((unsigned int)w, (unsigned int)p, (unsigned int)pr[u].ca, (unsigned int)pr[u].cb);
+				// k_transform writes the geometry of these two colliders (every writer of a stamp writes the same value)
+				d.geom_stamp[(size_t)pr[u].ca * S + w] = epoch;
+				d.geom_stamp[(size_t)pr[u].cb * S + w] = epoch;
+			}
 		}
 	}
 	for (int o = 16; o > 0; o >>= 1) tested += __shfl_down_sync(0xffffffffu, tested, o);
