@@ -45,9 +45,9 @@ def window_text(steps):
 
 # Algorithmic work per item, derived in DESIGN.md ("Kernels and rooflines"): bytes that must move and FP64 operations
 # (mul/add/div/sqrt = 1 each, no FMA credit) for one body-substep / pair test / EPA+manifold run / solved contact.
-BYTES = dict(integrate=600.0, gjk=400.0, epa=16.0 + 96.0 + 384.0 + 40.0, manifold=40.0 + 16.0 + 672.0 + 2 * 56.0, manifold_contact=64.0, solve_pos_pair=2 * (112.0 + 56.0), solve_contact=80.0,
+BYTES = dict(integrate=288.0, gjk=400.0, epa=16.0 + 96.0 + 384.0 + 40.0, manifold=40.0 + 16.0 + 672.0 + 2 * 56.0, manifold_contact=64.0, solve_pos_pair=2 * (112.0 + 56.0), solve_contact=80.0,
              solve_vel_pair=2 * (128.0 + 48.0), solve_contact_vel=64.0)
-FLOPS = dict(integrate=770.0, gjk=620.0, epa=800.0, manifold=1200.0, solve_pos_contact=1100.0, solve_vel_contact=650.0)
+FLOPS = dict(integrate=590.0, gjk=620.0, epa=800.0, manifold=1200.0, solve_pos_contact=1100.0, solve_vel_contact=650.0)
 FLOP_PER_BODY_SUBSTEP = 4.0e3  # algorithmic FP64 flop per body-substep on the W256 world
 
 
