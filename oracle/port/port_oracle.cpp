@@ -343,6 +343,14 @@ void port_get_state(double* out) {
 		o[14] = g->deact[i];
 	}
 }
+// previous_linear_velocity / previous_angular_velocity of every body (entity.h:45-46), 6 doubles each
+void port_get_prev_velocities(double* out) {
+	for (size_t i = 0; i < g->bodies.size(); ++i) {
+		const Body& b = g->bodies[i];
+		double* o = out + 6 * i;
+		o[0] = b.pv.x; o[1] = b.pv.y; o[2] = b.pv.z; o[3] = b.pw.x; o[4] = b.pw.y; o[5] = b.pw.z;
+	}
+}
 void port_set_state(const double* in) {
 	sync_bodies(*g);
 	for (size_t i = 0; i < g->bodies.size(); ++i) {

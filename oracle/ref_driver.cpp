@@ -257,6 +257,16 @@ void ref_get_state(double* out) {
 	}
 }
 
+// previous_linear_velocity / previous_angular_velocity of every entity (entity.h:45-46), 6 doubles each
+void ref_get_prev_velocities(double* out) {
+	for (u32 i = 0; i < array_length(entities); ++i) {
+		Entity* e = entities[i];
+		double* o = out + 6 * i;
+		o[0] = e->previous_linear_velocity.x; o[1] = e->previous_linear_velocity.y; o[2] = e->previous_linear_velocity.z;
+		o[3] = e->previous_angular_velocity.x; o[4] = e->previous_angular_velocity.y; o[5] = e->previous_angular_velocity.z;
+	}
+}
+
 void ref_set_state(const double* in) {
 	for (u32 i = 0; i < array_length(entities); ++i) {
 		Entity* e = entities[i];

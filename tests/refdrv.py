@@ -143,6 +143,13 @@ class RefWorld:
         self.lib.ref_get_state(_d(out))
         return out
 
+    def prev_velocities(self):
+        """previous_linear_velocity, previous_angular_velocity per entity (what RP_STATE_STRIDE records hold at [15:21])"""
+        n = int(self.lib.ref_num_entities())
+        out = np.zeros((n, 6))
+        self.lib.ref_get_prev_velocities(_d(out))
+        return out
+
     def set_state(self, st):
         st = np.ascontiguousarray(st, dtype=np.float64)
         self.lib.ref_set_state(_d(st))

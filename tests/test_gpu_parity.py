@@ -348,3 +348,19 @@ def test_world_without_pairs(pkg, oracle_flavour):
     assert np.array_equal(b.state()[0, :, :15], o.state())
     c = b.counters()
     assert c["broad_pairs"] == 0 and c["contacts"] == 0 and not b.status().any()
+
+
+@pytest.mark.parametrize("name", ["stack", "tumble", "coin"])
+def test_previous_velocities_match(pkg, oracle_flavour, name):
+    """columns 15..20 of the state record: Entity::previous_linear_velocity / previous_angular_velocity as pbd_simulate
+    leaves them (pbd.cpp:629-630: the velocities each body had before the LAST substep's derivation)."""
+    sc = scenes.BUILDERS[name]()
+    b = make(pkg, sc, n_worlds=2)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    for f in range(45):
+        step(b, sc)
+        o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+        if f % 11 == 0 or f == 44:
+            got = b.state()[0]
+            assert np.array_equal(got[:, :15], o.state()), f
+            assert np.array_equal(got[:, 15:21], o.prev_velocities()), f

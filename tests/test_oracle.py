@@ -166,3 +166,16 @@ def test_bounds_cull_is_sound_for_reference_gjk():
     sep, hits = C.c_uint64(), C.c_uint64()
     assert L.port_cull_soundness(1500000, 2024, C.byref(sep), C.byref(hits)) == 0
     assert sep.value > 300000 and hits.value > 300000
+
+
+@pytest.mark.skipif(not refdrv.available("strict"), reason="needs oracle/_ref (built where /root/reference is present)")
+@pytest.mark.parametrize("name", ["stack", "tumble", "coin"])
+def test_port_previous_velocities_match_reference(name):
+    """Entity::previous_linear_velocity / previous_angular_velocity (entity.h:45-46) after pbd_simulate"""
+    sc = scenes.BUILDERS[name]()
+    a, b = refdrv.RefWorld("strict").load(sc), refdrv.RefWorld("port").load(sc)
+    for f in range(40):
+        a.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+        b.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+    assert np.array_equal(a.state(), b.state()) and np.array_equal(a.prev_velocities(), b.prev_velocities())
+    assert np.abs(a.prev_velocities()).max() > 0
