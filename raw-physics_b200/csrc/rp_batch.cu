@@ -63,6 +63,7 @@ struct rp_batch {
 	unsigned int pos_grid = 148, vel_grid = 148;  // resident CTAs of the cooperative sweep kernels
 	int cull = 1;            // exact-safe bounds cull before GJK (rp_batch_cfg.disable_cull turns it off)
 	int coloured = 0;        // rp_batch_cfg.solve_order == RP_ORDER_COLOURED
+	bool no_restitution = false;  // every body's restitution coefficient is zero (k_integrate's store_velocities)
 	std::vector<int> joint_level;  // template-constant levels of the external constraints
 	bool have_graph = false;
 	GraphKey graph_key;
@@ -434,6 +435,8 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	// template: per-body records + de-duplicated physical classes
 	std::vector<BodyStatic> bs(d.NB);
 	std::vector<BodyClass> classes;
+	b->no_restitution = true;
+	for (int i = 0; i < d.NB; ++i) b->no_restitution = b->no_restitution && s.bodies[i].rest == 0.0;
 	for (int i = 0; i < d.NB; ++i) {
 		const BodyInit& bi = s.bodies[i];
 		BodyStatic& o = bs[i];
@@ -643,10 +646,11 @@ static void launch_solve_vel(rp_batch* b, double h) {
 	launch_cooperative(k_solve_vel, b->vel_grid, 128u, b->stream, b->d, h);
 }
 
-static void enqueue_integrate(rp_batch* b, double h) {
+static void enqueue_integrate(rp_batch* b, double h, bool last_substep) {
 	const DevView& d = b->d;
 	k_substep_reset<<<(unsigned int)((std::max(d.W, d.max_levels + 2) + 255) / 256), 256, 0, b->stream>>>(d);
-	k_integrate<<<dim3(d.NB, (d.W + RP_INT_THREADS - 1) / RP_INT_THREADS), RP_INT_THREADS, 0, b->stream>>>(d, h);
+	const int store_velocities = last_substep || !b->no_restitution ? 1 : 0;
+	k_integrate<<<dim3(d.NB, (d.W + RP_INT_THREADS - 1) / RP_INT_THREADS), RP_INT_THREADS, 0, b->stream>>>(d, h, store_velocities);
 }
 // grid of the per-hit kernel: the hit count lives on the device, so the launch covers the candidate capacity in
 // grid-stride trips of at most this many CTAs
@@ -683,7 +687,7 @@ static void enqueue_frame(rp_batch* b, double dt, uint32_t substeps, uint32_t it
 	const double h = dt / substeps;  // pbd.cpp:472
 	enqueue_prologue(b, dt, collisions);
 	for (uint32_t s = 0; s < substeps; ++s) {
-		enqueue_integrate(b, h);
+		enqueue_integrate(b, h, s + 1 == substeps);
 		if (collisions) enqueue_narrow(b);
 		enqueue_solve(b, h, iters, collisions);
 	}
@@ -884,7 +888,7 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t substeps, uint32_t ite
 	if ((rc = fetch(b, bs, d.bstat, (size_t)d.NB))) return rc;
 	uint32_t nc = 0, nk = 0;
 	for (uint32_t s = 0; s < substeps; ++s) {
-		enqueue_integrate(b, h);
+		enqueue_integrate(b, h, s + 1 == substeps);
 		if (collisions) {
 			enqueue_narrow(b);
 			RP_CUDA(cudaGetLastError());
@@ -961,7 +965,7 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 		RP_CUDA(cudaStreamSynchronize(b->stream));
 		if ((rc = mark(-1))) return rc;
 		for (uint32_t s = 0; s < substeps; ++s) {
-			enqueue_integrate(b, h);
+			enqueue_integrate(b, h, s + 1 == substeps);
 			if ((rc = mark(RP_K_INTEGRATE))) return rc;
 			if (collisions) {
 				launch_cull(b);

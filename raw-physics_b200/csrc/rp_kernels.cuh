@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(256) k_substep_reset(DevView d) {
 // so once per body per substep is exactly equivalent. Also leaves each collider's world-space bounds
 // for k_cull. Grid = (bodies, world blocks): a CTA is ONE body in 128 consecutive worlds, so the statics and the hull
 // are the same for every lane and every load/store of the world-minor arrays is coalesced.
-__global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate(DevView d, double h) {
+__global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate(DevView d, double h, int store_velocities) {
 	const int w = blockIdx.y * RP_INT_THREADS + threadIdx.x;
 	const int b = blockIdx.x;
 	if (w >= d.W) return;
@@ -538,20 +538,30 @@ __global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate
 	Body body;
 	load_static(body, d, b);
 	const DynRef r = dyn_ref(d, w, b);
-	body.x = ld3(r, DF_X); body.q = ld4(r, DF_Q); body.v = ld3(r, DF_V); body.w = ld3(r, DF_W);
+	body.x = ld3(r, DF_X); body.q = ld4(r, DF_Q);
 	body.active = d.active[bidx(d, b, w)];
 	const bool moving = !(body.fixed || !body.active);
 	// lazy velocity derivation of the PREVIOUS substep (pbd.cpp:623-643) for a body no velocity-level unit touched
-	// there: (x, q, prev x, prev q, v, w) are still exactly what the reference's derivation pass would have seen. Its
-	// prev-velocity outputs are not stored: nothing reads them before this substep's derivation rewrites them.
+	// there: (x, q, prev x, prev q) are still exactly what the reference's derivation pass would have seen, and the
+	// derived velocities depend on nothing else -- the stored velocities of such a body are not even read. (What the
+	// derivation would have left as previous velocities is not stored either: nothing reads it before this substep's
+	// derivation rewrites it.)
 	if (moving && d.vstamp[bidx(d, b, w)] != epoch - 1) {
+		body.v = body.w = v3(0.0, 0.0, 0.0);
 		body.px = ld3(r, DF_PX); body.pq = ld4(r, DF_PQ);
 		derive_velocity(body, h);
+	} else {
+		body.v = ld3(r, DF_V); body.w = ld3(r, DF_W);
 	}
 	integrate(body, h, d.force[b], d.torque[b]);
 	st3(r, DF_PX, body.px); st4(r, DF_PQ, body.pq);
 	if (moving) {
-		st3(r, DF_X, body.x); st4(r, DF_Q, body.q); st3(r, DF_V, body.v); st3(r, DF_W, body.w);
+		st3(r, DF_X, body.x); st4(r, DF_Q, body.q);
+		// The velocities as integrated are read by one thing only: this substep's derivation turns them into the body's
+		// PREVIOUS velocities (pbd.cpp:629-630), which the velocity pass reads for restitution and the caller sees after
+		// the frame. In a scene without restitution (every coefficient zero: solve_contact_velocity never looks at them)
+		// they are dead until the last substep, and the host asks for them to be stored only there.
+		if (store_velocities) { st3(r, DF_V, body.v); st3(r, DF_W, body.w); }
 	}
 	// collider_update (collider.cpp:409-445) is split in two. Here: the world-space bounds of every collider of the body
 	// (from the transformed vertices, which stay in registers) for k_cull. The transformed vertices and face normals
