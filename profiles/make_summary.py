@@ -29,9 +29,10 @@ def table(dd):
 
 
 ki = d["kernels"]["k_integrate"]
+kt = d["kernels"]["k_transform"]
 lines = ["# ncu summary, round 1, final state (commit %s)\n" % d["commit"],
-         "`ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_(integrate|cull|gjk|epa|manifold|solve_pos|solve_vel) -c 7 python bench.py --ncu-frame 40`",
-         "on one B200 (gpurun, `scripts/gpu_evidence.sh`): the seven kernels of substep 0 of frame 40 of the north-star workload (4096 worlds x 257 bodies). A second pass",
+         "`ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_(integrate|cull|transform|gjk|epa|manifold|solve_pos|solve_vel) -c 8 python bench.py --ncu-frame 40`",
+         "on one B200 (gpurun, `scripts/gpu_evidence.sh`): the eight kernels of substep 0 of frame 40 of the north-star workload (4096 worlds x 257 bodies). A second pass",
          "captured the per-frame prologue. Per-launch numbers under ncu are cold-cache and serialised: they are for shares and diagnosis; bench values come from",
          "`bench.py` without a profiler (`bench_r1_final.json`: %.2f ms/frame, %.4g body-substeps/s, e2e %.4g). Raw tables: `ncu_r1_final_*.json`; launch list of a" % (
              b["ms_per_step"], b["value"], b["e2e"]["value"]),
@@ -39,17 +40,19 @@ lines = ["# ncu summary, round 1, final state (commit %s)\n" % d["commit"],
          "## One substep (frame 40)\n"] + table(d) + ["\n## Per-frame prologue (frame 40)\n"] + table(pr) + ["""
 ## Reading
 
-* `k_integrate` moves %.0f MB per launch in %.0f us = %.1f TB/s = %.0f %% of the measured HBM copy peak (6459 GB/s, MEASURED_PEAKS.json): HBM-bound; 82 %% of the
-  bytes are writes (previous pose, new state, transformed vertices and normals, bounds). It is the top kernel of the frame in `bench.py`'s device-timed
-  breakdown (%.0f of %.0f ms over the 60-frame window), hence the `roofline` block of the bench line: algorithmic 600 B/body-substep -> %.2f of the peak.
-* Everything else is latency-bound at 12-25 %% achieved occupancy: `k_epa` and `k_manifold` on local memory (polytope / clip buffers do not fit L1 at their
-  occupancy: L1 hit ~50 %%) and on the loads that feed their dot products, `k_gjk` on dependent FP64 chains (FP64 pipe 26 %%), the two sweeps on dependent FP64
-  chains and on `grid.sync()` between levels (a full level of the W256 batch is 4096 warp-items for 1776-2368 resident warps).
+* `k_integrate` + `k_transform` are the streaming kernels: %.0f + %.0f MB of DRAM traffic in %.0f + %.0f us (%.1f and %.1f TB/s; measured HBM copy peak 6.46 TB/s,
+  MEASURED_PEAKS.json). Until the collider update was split, `k_integrate` alone moved 653 MB per launch at 84 %% of that peak; now the transformed geometry
+  is written after the cull and only for colliders of surviving candidate pairs (47 %% of the bodies over the W256 window).
+* Everything else is latency-bound at 12-25 %% achieved occupancy: `k_epa` and `k_manifold` (the top kernel of the frame in `bench.py`'s device-timed
+  breakdown: %.0f of %.0f ms over the 60-frame window) on local memory (polytope / clip buffers do not fit L1 at their occupancy: L1 hit ~50 %%) and on the
+  loads that feed their dot products, `k_gjk` on dependent FP64 chains (FP64 pipe 26 %%), the two sweeps on dependent FP64 chains and on `grid.sync()`
+  between levels (a full level of the W256 batch is 4096 warp-items for 1776-2368 resident warps).
 * The sweeps over this round, same frame: 22 level launches, 390 us -> 2 cooperative launches, %.0f us.
-* `k_cull`: DRAM-latency bound (the bounds it reads were evicted by `k_integrate`'s writes: L2 hit 19 %%).
+* `k_cull`: DRAM-latency bound (what it reads was evicted by the kernels before it: L2 hit < 20 %%).
 * Prologue: 0.64 ms per frame (4 %% of the frame): `k_broad_cells` 245 us (was 2 x 330 us as row kernels), `k_schedule` 181 us (was 328), `k_islands` 165 us.
-""" % ((ki["dram_read"] + ki["dram_write"]) / 1e6, ki["us"], (ki["dram_read"] + ki["dram_write"]) / ki["us"] / 1e6,
-       100 * (ki["dram_read"] + ki["dram_write"]) / ki["us"] / 1e6 / 6.459, b["kernels"]["integrate"]["ms"], sum(v["ms"] for v in b["kernels"].values()),
-       b["roofline"]["frac"], d["kernels"]["k_solve_pos<0>"]["us"] + d["kernels"]["k_solve_vel"]["us"])]
+""" % ((ki["dram_read"] + ki["dram_write"]) / 1e6, (kt["dram_read"] + kt["dram_write"]) / 1e6, ki["us"], kt["us"],
+       (ki["dram_read"] + ki["dram_write"]) / ki["us"] / 1e6, (kt["dram_read"] + kt["dram_write"]) / kt["us"] / 1e6,
+       b["kernels"]["manifold"]["ms"], sum(v["ms"] for v in b["kernels"].values()),
+       d["kernels"]["k_solve_pos<0>"]["us"] + d["kernels"]["k_solve_vel"]["us"])]
 open(os.path.join(HERE, "ncu_r1_final_summary.md"), "w").write("\n".join(lines))
 print("wrote ncu_r1_final_summary.md")
