@@ -123,6 +123,8 @@ typedef struct {
 } rp_batch_cfg;
 void rp_batch_cfg_default(rp_batch_cfg* cfg);
 
+/* 1 <= n_worlds <= 65535 per batch (several batches may live on one device, each with its own stream); RP_ERR_ARG otherwise.
+ * Device memory is allocated here and nowhere else: about 1.1 MB per world of 257 bodies. */
 int rp_batch_create(const rp_scene* scene, uint32_t n_worlds, int cuda_device, const rp_batch_cfg* cfg_or_null, rp_batch** out);
 void rp_batch_destroy(rp_batch* b);
 uint32_t rp_batch_num_worlds(const rp_batch* b);
