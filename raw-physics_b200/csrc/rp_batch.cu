@@ -63,6 +63,7 @@ struct rp_batch {
 	unsigned int pos_grid = 148, vel_grid = 148;  // resident CTAs of the cooperative sweep kernels
 	int cull = 1;            // exact-safe bounds cull before GJK (rp_batch_cfg.disable_cull turns it off)
 	int coloured = 0;        // rp_batch_cfg.solve_order == RP_ORDER_COLOURED
+	bool has_big_pairs = false;   // some collider pair is too large for k_gjk's per-thread staging: k_gjk_warp is launched too
 	bool no_restitution = false;  // every body's restitution coefficient is zero (k_integrate's store_velocities)
 	std::vector<int> joint_level;  // template-constant levels of the external constraints
 	bool have_graph = false;
@@ -528,6 +529,17 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.geom_stamp, WS * std::max(d.NC, 1)))) return rc;
 	if ((rc = dev_alloc(b, &d.cands, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.cand_count, 1))) return rc;
+	if ((rc = dev_alloc(b, &d.big_count, 1))) return rc;
+	d.cand_cap = (unsigned int)WP;
+	{
+		// does any pair of colliders exceed the per-thread staging block of k_gjk? (two largest vertex counts)
+		int n1 = 0, n2 = 0;
+		for (size_t c = 0; c < s.colliders.size(); ++c) {
+			const int nv = s.colliders[c].nv;
+			if (nv > n1) { n2 = n1; n1 = nv; } else if (nv > n2) n2 = nv;
+		}
+		b->has_big_pairs = (n1 + n2) * 3 > RP_GJK_STAGE;
+	}
 	if ((rc = dev_alloc(b, &d.simplex, WP * 4, false))) return rc;
 	if ((rc = dev_alloc(b, &d.hits, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.hit_count, 1))) return rc;
@@ -659,7 +671,10 @@ static void launch_cull(rp_batch* b) {
 	k_cull<<<dim3(b->cull_chunks, (b->d.W + 31) / 32), 256, 0, b->stream>>>(b->d, b->cull);
 	k_transform<<<dim3(b->d.NB, (b->d.W + RP_INT_THREADS - 1) / RP_INT_THREADS), RP_INT_THREADS, 0, b->stream>>>(b->d);
 }
-static void launch_gjk(rp_batch* b) { k_gjk<<<b->sm_count * 16, RP_GJK_THREADS, 0, b->stream>>>(b->d); }
+static void launch_gjk(rp_batch* b) {
+	k_gjk<<<b->sm_count * 16, RP_GJK_THREADS, 0, b->stream>>>(b->d);
+	if (b->has_big_pairs) k_gjk_warp<<<b->sm_count * 8, RP_GJK_WARP_THREADS, 0, b->stream>>>(b->d);
+}
 static void launch_manifold(rp_batch* b) {
 	k_epa<<<b->sm_count * 16, RP_EPA_THREADS, 0, b->stream>>>(b->d);
 	k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, 0, b->stream>>>(b->d);

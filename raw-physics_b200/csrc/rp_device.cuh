@@ -86,6 +86,8 @@ struct DevView {
 	float* aabb;         // [NC][6][WS] world-space bounds of every collider (min xyz rounded down, max xyz rounded up)
 	uint4* cands;        // [W * max_pairs] (world, pair, collider a, collider b) that survived the skip rule and the bounds cull
 	unsigned int* cand_count;
+	unsigned int* big_count;   // candidates with hulls too large to stage per thread: kept at the END of cands, taken by k_gjk_warp
+	unsigned int cand_cap;     // W * max_pairs
 	uint4* hits;         // [W * max_pairs] the colliding candidates' records, dense (one load tells EPA / clipping where their inputs are)
 	V3* simplex;         // [W * max_pairs][4] final GJK tetrahedron of each hit
 	unsigned int* hit_count;

@@ -506,6 +506,7 @@ __global__ void __launch_bounds__(256) k_substep_reset(DevView d) {
 	if (i == 0) {
 		*d.hit_count = 0u;
 		*d.cand_count = 0u;
+		*d.big_count = 0u;
 		*d.epoch += 1;
 	}
 	if (i < d.max_levels + 2) {
@@ -742,7 +743,11 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 		for (int u = 0; u < RP_CULL_ILP; ++u) {
 			const int p = p0 + u * stride;
 			if (in[u]) d.pair_ccnt[pidx(d, p, w)] = 0;
-			const unsigned int slot = warp_append(d.cand_count, keep[u]);
+			// pairs whose hulls do not fit k_gjk's per-thread staging block go to the back of the list, for k_gjk_warp
+			const bool big = keep[u] && (d.cols[pr[u].ca].nv + d.cols[pr[u].cb].nv) * 3 > RP_GJK_STAGE;
+			const unsigned int front = warp_append(d.cand_count, keep[u] && !big);
+			const unsigned int back = warp_append(d.big_count, big);
+			const unsigned int slot = big ? d.cand_cap - 1u - back : front;
 			if (keep[u]) {
 				d.cands[slot] = make_uint4((unsigned int)w, (unsigned int)p, (unsigned int)pr[u].ca, (unsigned int)pr[u].cb);
 				// k_transform writes the geometry of these two colliders (every writer of a stamp writes the same value)
@@ -819,6 +824,79 @@ __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) 
 			d.hits[slot] = cd;
 			V3* o = d.simplex + (size_t)slot * 4;
 			o[0] = s.a; o[1] = s.b; o[2] = s.c; o[3] = s.d;
+		}
+	}
+}
+
+// ---- one WARP per candidate pair, for hulls too large to stage per thread (a cylinder has 128 vertices, a tessellated
+// sphere over a thousand): the 32 lanes run the same GJK instance in lockstep, and the support scans -- everything such a
+// pair spends its time in -- are split across them: every lane keeps the first maximum of its share of the vertices
+// (ascending, strict >, as support_point_get_index does, support.cpp:5-17), then a butterfly of shuffles picks the largest
+// value and, among equal values, the lowest index: exactly the vertex the sequential scan returns. Hulls of up to
+// RP_WARP_HULL_MAX vertices are staged in shared memory first (component planes, so the lanes' reads are consecutive).
+#define RP_GJK_WARP_THREADS 128
+#define RP_WARP_HULL_MAX 128
+struct WarpShape : Shape {
+	__device__ WarpShape() {}
+	__device__ explicit WarpShape(const Shape& s) : Shape(s) {}
+};
+__device__ __forceinline__ int support_index(const WarpShape& s, V3 d) {
+	const int lane = threadIdx.x & 31;
+	int best = 0x7fffffff;
+	double best_dot = -1.7976931348623157e308;
+	for (int i = lane; i < s.nv; i += 32) {
+		const double t = dot(vert(static_cast<const Shape&>(s), i), d);
+		if (t > best_dot) {
+			best = i;
+			best_dot = t;
+		}
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		const double od = __shfl_xor_sync(0xffffffffu, best_dot, o);
+		const int oi = __shfl_xor_sync(0xffffffffu, best, o);
+		if (od > best_dot || (od == best_dot && oi < best)) {
+			best_dot = od;
+			best = oi;
+		}
+	}
+	return best == 0x7fffffff ? 0 : best;
+}
+// copies a hull's transformed vertices into the warp's block of shared memory as component planes
+__device__ __forceinline__ void warp_stage(Shape& s, double* block) {
+	if (s.type != SHAPE_HULL || s.nv > RP_WARP_HULL_MAX) return;  // spheres have no vertices; larger hulls are scanned in place
+	const int lane = threadIdx.x & 31;
+	for (int k = lane; k < s.nv; k += 32) {
+		const V3 p = vert(s, k);
+		block[k] = p.x; block[RP_WARP_HULL_MAX + k] = p.y; block[2 * RP_WARP_HULL_MAX + k] = p.z;
+	}
+	s.vp = block; s.vs = 1; s.vcs = RP_WARP_HULL_MAX;
+}
+__global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_gjk_warp(DevView d) {
+	const unsigned int nb = *d.big_count;
+	__shared__ double s_hull[RP_GJK_WARP_THREADS / 32][2][3 * RP_WARP_HULL_MAX];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const unsigned int warps = gridDim.x * (RP_GJK_WARP_THREADS / 32);
+	for (unsigned int k = blockIdx.x * (RP_GJK_WARP_THREADS / 32) + wib; k < nb; k += warps) {
+		const uint4 cd = d.cands[d.cand_cap - 1u - k];
+		const int w = (int)cd.x;
+		Shape A = dev_shape(d, d.cols[cd.z], w);
+		Shape B = dev_shape(d, d.cols[cd.w], w);
+		__syncwarp();  // the previous pair's scans are done with the block
+		warp_stage(A, s_hull[wib][0]);
+		warp_stage(B, s_hull[wib][1]);
+		__syncwarp();
+		Simplex s;
+		int st = 0;
+		const bool hit = gjk(WarpShape(A), WarpShape(B), &s, &st, 0);  // the same instance on all 32 lanes
+		if (lane == 0) {
+			if (st) atomicOr(&d.status[w], st);
+			if (hit) {
+				const unsigned int slot = atomicAdd(d.hit_count, 1u);
+				d.hits[slot] = cd;
+				V3* o = d.simplex + (size_t)slot * 4;
+				o[0] = s.a; o[1] = s.b; o[2] = s.c; o[3] = s.d;
+			}
 		}
 	}
 }

@@ -189,6 +189,7 @@ int Scene::add_hull_collider(const double* vx, uint32_t nverts, const uint32_t* 
 	c.hull = id;
 	c.radius = 0.0f;
 	c.tv0 = c.tn0 = 0;
+	c.nv = (int)hulls[id].verts.size();
 	pending.push_back(c);
 	return (int)pending.size() - 1;
 }
@@ -215,6 +216,7 @@ int Scene::add_hull_topology(const HullHost& h) {
 	c.hull = id;
 	c.radius = 0.0f;
 	c.tv0 = c.tn0 = 0;
+	c.nv = (int)hulls[id].verts.size();
 	pending.push_back(c);
 	return (int)pending.size() - 1;
 }
@@ -225,6 +227,7 @@ int Scene::add_sphere_collider(float radius) {  // collider_sphere_create (colli
 	c.hull = -1;
 	c.radius = radius;
 	c.tv0 = c.tn0 = 0;
+	c.nv = 0;
 	pending.push_back(c);
 	return (int)pending.size() - 1;
 }

@@ -40,6 +40,7 @@ struct ColliderDesc {
 	float radius;             // r32, as in Collider_Sphere (collider.h:26-29)
 	int tv0;                  // first transformed vertex (and, for a sphere, the slot holding its centre)
 	int tn0;                  // first transformed normal
+	int nv;                   // vertices of the hull (0 for a sphere): decides which narrowphase kernel takes a pair
 };
 
 // A collider at a pose, as the narrowphase sees it.
