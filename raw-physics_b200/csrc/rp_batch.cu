@@ -539,6 +539,8 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 			if (nv > n1) { n2 = n1; n1 = nv; } else if (nv > n2) n2 = nv;
 		}
 		b->has_big_pairs = (n1 + n2) * 3 > RP_GJK_STAGE;
+		d.split_big = b->has_big_pairs ? 1 : 0;
+		if ((rc = dev_alloc(b, &d.big_sup, b->has_big_pairs ? WP : 1, false))) return rc;
 	}
 	if ((rc = dev_alloc(b, &d.simplex, WP * 4, false))) return rc;
 	if ((rc = dev_alloc(b, &d.hits, WP, false))) return rc;
@@ -677,6 +679,7 @@ static void launch_gjk(rp_batch* b) {
 }
 static void launch_manifold(rp_batch* b) {
 	k_epa<<<b->sm_count * 16, RP_EPA_THREADS, 0, b->stream>>>(b->d);
+	if (b->has_big_pairs) k_epa_warp<<<b->sm_count * 8, RP_GJK_WARP_THREADS, 0, b->stream>>>(b->d);
 	k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, 0, b->stream>>>(b->d);
 }
 static void enqueue_narrow(rp_batch* b) {
@@ -988,6 +991,7 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 				launch_gjk(b);
 				if ((rc = mark(RP_K_GJK))) return rc;
 				k_epa<<<b->sm_count * 16, RP_EPA_THREADS, 0, b->stream>>>(d);
+				if (b->has_big_pairs) k_epa_warp<<<b->sm_count * 8, RP_GJK_WARP_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_EPA))) return rc;
 				k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_MANIFOLD))) return rc;

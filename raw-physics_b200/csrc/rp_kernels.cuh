@@ -912,6 +912,7 @@ __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) 
 	for (unsigned int hi = blockIdx.x * blockDim.x + threadIdx.x; hi < nh; hi += gridDim.x * blockDim.x) {
 		const uint4 cd = d.hits[hi];
 		const int w = (int)cd.x;
+		if (d.split_big && (d.cols[cd.z].nv + d.cols[cd.w].nv) * 3 > RP_GJK_STAGE) continue;  // k_epa_warp's
 		Shape A = dev_shape(d, d.cols[cd.z], w);
 		Shape B = dev_shape(d, d.cols[cd.w], w);
 		EpaOut out;
@@ -937,6 +938,46 @@ __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) 
 		if (st) atomicOr(&d.status[w], st);
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&d.counters[CNT_HITS], (unsigned long long)nh);
+}
+
+// EPA for the hits of large pairs, one warp per hit like k_gjk_warp (the polytope is small; the support scans over the
+// big hulls are what is shared out). While the hulls are still staged, the warp also finds the two support vertices along
+// +-normal that clipping starts from (convex_convex_contact_manifold, clipping.cpp:255-256) and leaves them for k_manifold.
+__global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_epa_warp(DevView d) {
+	const unsigned int nh = *d.hit_count;
+	__shared__ double s_hull[RP_GJK_WARP_THREADS / 32][2][3 * RP_WARP_HULL_MAX];
+	EpaScratch e;
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const unsigned int warps = gridDim.x * (RP_GJK_WARP_THREADS / 32);
+	for (unsigned int hi = blockIdx.x * (RP_GJK_WARP_THREADS / 32) + wib; hi < nh; hi += warps) {
+		const uint4 cd = d.hits[hi];
+		if (!((d.cols[cd.z].nv + d.cols[cd.w].nv) * 3 > RP_GJK_STAGE)) continue;  // k_epa's
+		const int w = (int)cd.x;
+		Shape A = dev_shape(d, d.cols[cd.z], w);
+		Shape B = dev_shape(d, d.cols[cd.w], w);
+		__syncwarp();
+		warp_stage(A, s_hull[wib][0]);
+		warp_stage(B, s_hull[wib][1]);
+		__syncwarp();
+		const V3* sp = d.simplex + (size_t)hi * 4;
+		Simplex s;
+		s.a = sp[0]; s.b = sp[1]; s.c = sp[2]; s.d = sp[3];
+		s.num = 4;
+		EpaOut out;
+		out.ok = 0; out.pad = 0; out.depth = 0.0; out.normal = v3(0.0, 0.0, 0.0);
+		int st = 0;
+		out.ok = epa(WarpShape(A), WarpShape(B), s, e, &out.normal, &out.depth, &st, 0) ? 1 : 0;  // the same instance on all lanes
+		int2 sup = make_int2(-1, -1);
+		if (out.ok && A.type == SHAPE_HULL && B.type == SHAPE_HULL) {
+			sup.x = support_index(WarpShape(A), out.normal);
+			sup.y = support_index(WarpShape(B), zero_minus(out.normal));
+		}
+		if (lane == 0) {
+			d.epa_out[hi] = out;
+			d.big_sup[hi] = sup;
+			if (st) atomicOr(&d.status[w], st);
+		}
+	}
 }
 
 struct StageSink {
@@ -984,7 +1025,12 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 				sink.stage = sc.stage;
 				sink.n = 0;
 				sink.cap = RP_CLIP_MAX_POINTS;
-				manifold(A, B, eo.normal, eo.depth, sc.clip, &st, sink);
+				int sup1 = -1, sup2 = -1;
+				if (d.split_big && (d.cols[cd.z].nv + d.cols[cd.w].nv) * 3 > RP_GJK_STAGE) {
+					const int2 sup = d.big_sup[hi];
+					sup1 = sup.x; sup2 = sup.y;
+				}
+				manifold(A, B, eo.normal, eo.depth, sc.clip, &st, sink, sup1, sup2);
 				n = sink.n;
 				if (n > sink.cap) {
 					st |= ST_CLIP_CAPACITY;

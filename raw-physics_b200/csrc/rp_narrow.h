@@ -462,11 +462,14 @@ RP_HD bool clip_skew_lines(V3 p1, V3 d1, V3 p2, V3 d2, V3* l1, V3* l2) {
 }
 
 // convex_convex_contact_manifold (clipping.cpp:249-341). Sink: void operator()(V3 p1, V3 p2).
+// `sup1_known` / `sup2_known` (>= 0): the support vertices along +-normal when a caller has already found them (the GPU
+// finds them with a whole warp for large hulls, k_epa_warp); the scan here would return the same indices.
 template <class Sink>
-RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipScratch& cs, int* status, Sink& sink) {
+RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipScratch& cs, int* status, Sink& sink, int sup1_known = -1,
+	int sup2_known = -1) {
 	V3 inv_normal = zero_minus(normal);
-	int sup1 = support_index(h1, normal);
-	int sup2 = support_index(h2, inv_normal);
+	int sup1 = sup1_known >= 0 ? sup1_known : support_index(h1, normal);
+	int sup2 = sup2_known >= 0 ? sup2_known : support_index(h2, inv_normal);
 	int face1 = clip_best_face(h1, sup1, normal);
 	int face2 = clip_best_face(h2, sup2, inv_normal);
 
@@ -595,7 +598,8 @@ RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipS
 // collider_get_contacts (collider.cpp:523-558) + clipping_get_contact_manifold (clipping.cpp:343-371) for one collider
 // pair whose GJK verdict is already known to be "colliding" (hull involved) -- see narrow_pair below for the front half.
 template <class Sink>
-RP_HD void manifold(const Shape& A, const Shape& B, V3 normal, double depth, ClipScratch& cs, int* status, Sink& sink) {
+RP_HD void manifold(const Shape& A, const Shape& B, V3 normal, double depth, ClipScratch& cs, int* status, Sink& sink, int sup1_known = -1,
+	int sup2_known = -1) {
 	if (A.type == SHAPE_SPHERE) {
 		V3 p = support(A, normal);
 		sink(p, sub(p, scale(depth, normal)));
@@ -603,7 +607,7 @@ RP_HD void manifold(const Shape& A, const Shape& B, V3 normal, double depth, Cli
 		V3 p = support(B, zero_minus(normal));
 		sink(add(p, scale(depth, normal)), p);
 	} else {
-		manifold_hull_hull(A, B, normal, cs, status, sink);
+		manifold_hull_hull(A, B, normal, cs, status, sink, sup1_known, sup2_known);
 	}
 }
 
