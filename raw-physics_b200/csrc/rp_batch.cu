@@ -619,7 +619,8 @@ static int flush_forces(rp_batch* b) {
 static void launch_schedule(rp_batch* b, int collisions) {
 	const DevView& d = b->d;
 	const size_t entry = b->coloured ? sizeof(unsigned long long) : sizeof(int);
-	const size_t smem = (size_t)d.NB * 32 * entry + RP_SCHED_HIST * 32 * sizeof(int) + (size_t)d.NB * 32;
+	const size_t lanes = d.W < 32 ? d.W : 32;  // columns of the shared tables (k_schedule's SL)
+	const size_t smem = ((size_t)d.NB * lanes * entry + RP_SCHED_HIST * lanes * sizeof(int) + (size_t)d.NB * lanes + 15) / 16 * 16;
 	const unsigned int grid = (unsigned int)((d.W + 31) / 32);
 	if (b->coloured) {
 		if (smem <= RP_SCHED_SMEM_MAX) k_schedule<true, true><<<grid, 32, smem, b->stream>>>(d, collisions);

@@ -400,26 +400,31 @@ __global__ void __launch_bounds__(32) k_schedule(DevView d, int collisions) {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool live = w < d.W;
 	const size_t S = d.WS;
+	// shared tables are [..][SL] with SL = the lanes that hold a world: 32, or the whole batch when it is smaller than a warp
+	// (one large scene must not pay 32 columns for its one world -- its tables would not fit)
+	const int SL = d.W < 32 ? d.W : 32;
 	Entry* s_tab = reinterpret_cast<Entry*>(s_sched_raw);
-	Entry* last = SMEM ? s_tab + threadIdx.x : SchedEntry<COLOUR>::scratch(d) + (live ? w : 0);  // [NB][32] or [NB][WS]
-	const size_t LS = SMEM ? 32 : S;
-	int* s_sched = reinterpret_cast<int*>(s_tab + (size_t)d.NB * 32);
-	int* s_hist = s_sched + threadIdx.x;                                          // [RP_SCHED_HIST][32] (SMEM only)
-	unsigned char* s_flag = (unsigned char*)(s_sched + RP_SCHED_HIST * 32) + threadIdx.x;  // [NB][32] (SMEM only)
+	Entry* last = SMEM ? s_tab + (live ? threadIdx.x : 0) : SchedEntry<COLOUR>::scratch(d) + (live ? w : 0);  // [NB][SL] or [NB][WS]
+	const size_t LS = SMEM ? SL : S;
+	int* s_sched = reinterpret_cast<int*>(s_tab + (size_t)d.NB * SL);
+	int* s_hist = s_sched + (live ? threadIdx.x : 0);                                          // [RP_SCHED_HIST][SL] (SMEM only)
+	unsigned char* s_flag = (unsigned char*)(s_sched + RP_SCHED_HIST * SL) + (live ? threadIdx.x : 0);  // [NB][SL] (SMEM only)
 	int* plevel = d.pair_level + (live ? w : 0);    // [max_pairs][WS]
 	int* hist = d.lvl_hist + (live ? w : 0);        // [max_levels + 2][WS]
 	const int* active = d.active + (live ? w : 0);  // [NB][WS]
 	const int np = (collisions && live) ? d.n_pairs[w] : 0;
 	// flag bit 0: fixed, bit 1: fixed or asleep (pbd.cpp:594)
-	for (int b = 0; b < d.NB; ++b) {
-		if (SMEM || live) last[b * LS] = SchedEntry<COLOUR>::initial(d, b);
-		if (SMEM) {
-			const int f = d.bstat[b].fixed;
-			s_flag[b * 32] = (unsigned char)((f ? 1 : 0) | ((f || !(live && active[b * S])) ? 2 : 0));
+	if (live) {
+		for (int b = 0; b < d.NB; ++b) {
+			last[b * LS] = SchedEntry<COLOUR>::initial(d, b);
+			if (SMEM) {
+				const int f = d.bstat[b].fixed;
+				s_flag[b * SL] = (unsigned char)((f ? 1 : 0) | ((f || !active[b * S]) ? 2 : 0));
+			}
 		}
-	}
-	if (SMEM) {
-		for (int l = 0; l < RP_SCHED_HIST; ++l) s_hist[l * 32] = 0;
+		if (SMEM) {
+			for (int l = 0; l < RP_SCHED_HIST; ++l) s_hist[l * SL] = 0;
+		}
 	}
 	int nl = d.joint_levels;
 	int deep = 0;  // pairs scheduled at levels >= RP_SCHED_HIST (counted through the global histogram)
@@ -438,7 +443,7 @@ __global__ void __launch_bounds__(32) k_schedule(DevView d, int collisions) {
 			const int a = ab[k].x, b = ab[k].y;
 			int fa, fb, sa, sb;
 			if (SMEM) {
-				const int ga = s_flag[a * 32], gb = s_flag[b * 32];
+				const int ga = s_flag[a * SL], gb = s_flag[b * SL];
 				fa = ga & 1; fb = gb & 1; sa = ga & 2; sb = gb & 2;
 			} else {
 				fa = d.bstat[a].fixed; fb = d.bstat[b].fixed;
@@ -457,7 +462,7 @@ __global__ void __launch_bounds__(32) k_schedule(DevView d, int collisions) {
 			plevel[p * S] = lvl;
 			if (lvl > nl) nl = lvl;
 			if (SMEM) {
-				if (lvl < RP_SCHED_HIST) s_hist[lvl * 32] += 1;
+				if (lvl < RP_SCHED_HIST) s_hist[lvl * SL] += 1;
 				else ++deep;
 			}
 		}
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(32) k_schedule(DevView d, int collisions) {
 	}
 	for (int l = 1; l <= nl_warp; ++l) {
 		int c = 0;
-		if (live && l <= nl) c = use_smem_hist ? s_hist[l * 32] : hist[l * S];
+		if (live && l <= nl) c = use_smem_hist ? s_hist[l * SL] : hist[l * S];
 		c = __reduce_add_sync(0xffffffffu, c);
 		if (threadIdx.x == 0 && c) atomicAdd(&d.lvl_cap[l], c);
 	}
