@@ -364,3 +364,30 @@ def test_previous_velocities_match(pkg, oracle_flavour, name):
             got = b.state()[0]
             assert np.array_equal(got[:, :15], o.state()), f
             assert np.array_equal(got[:, 15:21], o.prev_velocities()), f
+
+
+def test_spot_storm_compound_large_hulls(pkg, oracle_flavour):
+    """spot_storm.cpp: 8 compound bodies x 11 hulls of up to 529 vertices. Collider pairs of one body
+    pair stay in the reference's (i outer, j inner) order, hulls too large for the per-thread staging block go through the
+    warp-per-pair kernels (k_gjk_warp / k_epa_warp; hulls above 128 vertices are scanned in place): bit-exact trajectories
+    and per-substep contact sets."""
+    sc = scenes.spot_storm(n=2)
+    b = make(pkg, sc, n_worlds=2, max_pairs=8192, max_contacts=8192)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    for f in range(30):
+        step(b, sc)
+        o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+        if f % 5 == 4:
+            got = b.state()
+            assert np.array_equal(got[0, :, :15], o.state()), (f, np.abs(got[0, :, :15] - o.state()).max())
+            assert np.array_equal(got[0], got[1])
+    assert not b.status().any()
+    # one more frame with the contact log of every substep
+    o.log_enable(True)
+    o.log_clear()
+    o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+    want_calls, want_contacts = o.log_get()
+    o.log_enable(False)
+    calls, contacts = b.step_logged(world=1, substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+    assert np.array_equal(calls, want_calls) and np.array_equal(contacts, want_contacts)
+    assert want_contacts.shape[0] > 0

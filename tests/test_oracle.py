@@ -179,3 +179,20 @@ def test_port_previous_velocities_match_reference(name):
         b.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
     assert np.array_equal(a.state(), b.state()) and np.array_equal(a.prev_velocities(), b.prev_velocities())
     assert np.abs(a.prev_velocities()).max() > 0
+
+
+@pytest.mark.skipif(not refdrv.available("strict"), reason="needs oracle/_ref (built where /root/reference is present)")
+def test_port_spot_storm_matches_reference():
+    """spot_storm.cpp: compound bodies of 11 hulls (up to 529 vertices / 1000 faces): hull construction, the default inertia
+    over several hulls, collider-pair expansion order and the narrowphase on large hulls, against the compiled reference"""
+    sc = scenes.spot_storm(n=2)
+    a, b = refdrv.RefWorld("strict").load(sc), refdrv.RefWorld("port").load(sc)
+    assert np.array_equal(a.params(), b.params())
+    for c in (0, 1, 10):
+        ha, hb = a.hull(1, c), b.hull(1, c)
+        assert all(np.array_equal(ha[k], hb[k]) for k in ha)
+    for f in range(24):
+        a.step()
+        b.step()
+    assert np.array_equal(a.state(), b.state())
+    assert a.state()[1:, 1].min() < 3.0  # they have landed: contacts were solved
