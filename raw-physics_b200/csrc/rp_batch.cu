@@ -63,6 +63,9 @@ struct rp_batch {
 	unsigned int pos_grid = 148, vel_grid = 148;  // resident CTAs of the cooperative sweep kernels
 	int cull = 1;            // exact-safe bounds cull before GJK (rp_batch_cfg.disable_cull turns it off)
 	int coloured = 0;        // rp_batch_cfg.solve_order == RP_ORDER_COLOURED
+	int live_lists = 0;        // the scene can have deep, mostly empty schedules (compound bodies): the sweeps list the levels with work
+	size_t live_smem = 0;      // dynamic shared memory of the sweep kernels for that list
+	unsigned int transform_slices = 1;  // gridDim.z of k_transform: threads that share one collider's vertices and normals
 	bool has_big_pairs = false;   // some collider pair is too large for k_gjk's per-thread staging: k_gjk_warp is launched too
 	bool no_restitution = false;  // every body's restitution coefficient is zero (k_integrate's store_velocities)
 	std::vector<int> joint_level;  // template-constant levels of the external constraints
@@ -94,12 +97,13 @@ static int dev_upload(rp_batch* b, const T** out, const std::vector<T>& v) {
 
 // launches `kernel` as a cooperative grid (cg::this_grid().sync() inside); capturable into the frame graph
 template <class... Args>
-static cudaError_t launch_cooperative(void (*kernel)(Args...), unsigned int grid, unsigned int block, cudaStream_t stream, Args... args) {
+static cudaError_t launch_cooperative(void (*kernel)(Args...), unsigned int grid, unsigned int block, size_t smem, cudaStream_t stream,
+	Args... args) {
 	cudaLaunchConfig_t cfg;
 	memset(&cfg, 0, sizeof(cfg));
 	cfg.gridDim = dim3(grid);
 	cfg.blockDim = dim3(block);
-	cfg.dynamicSmemBytes = 0;
+	cfg.dynamicSmemBytes = smem;
 	cfg.stream = stream;
 	cudaLaunchAttribute attr;
 	attr.id = cudaLaunchAttributeCooperative;
@@ -388,11 +392,16 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		int coop = 0, per_sm = 0;
 		RP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
 		if (!coop) return fail(RP_ERR_CUDA, "device does not support cooperative launches");
-		if (d.NJ > 0) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_pos<true>, 128, 0));
-		else RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_pos<false>, 128, 0));
+		// deep, mostly empty schedules come from compound bodies (a pair of bodies with m and n colliders chains m * n units)
+		int most_colliders = 0;
+		for (size_t i = 0; i < s.bodies.size(); ++i) most_colliders = std::max(most_colliders, s.bodies[i].ncol);
+		b->live_lists = most_colliders > 2 ? 1 : 0;
+		b->live_smem = b->live_lists ? sizeof(LiveLevels) : 0;
+		if (d.NJ > 0) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_pos<true>, 128, b->live_smem));
+		else RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_pos<false>, 128, b->live_smem));
 		if (per_sm < 1) return fail(RP_ERR_CUDA, "k_solve_pos does not fit an SM");
 		b->pos_grid = (unsigned int)(b->sm_count * per_sm);
-		RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_vel, 128, 0));
+		RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_vel, 128, b->live_smem));
 		if (per_sm < 1) return fail(RP_ERR_CUDA, "k_solve_vel does not fit an SM");
 		b->vel_grid = (unsigned int)(b->sm_count * per_sm);
 	}
@@ -539,6 +548,19 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 			if (nv > n1) { n2 = n1; n1 = nv; } else if (nv > n2) n2 = nv;
 		}
 		b->has_big_pairs = (n1 + n2) * 3 > RP_GJK_STAGE;
+		// heavy geometry: bounds per collider instead of per body, and several threads per collider in k_transform
+		int body_most = 0, collider_most = 0;
+		for (size_t i = 0; i < s.bodies.size(); ++i) {
+			int nv = 0;
+			for (int c = s.bodies[i].col0; c < s.bodies[i].col0 + s.bodies[i].ncol; ++c) {
+				const ColliderDesc& cd = s.colliders[c];
+				nv += cd.nv;
+				if (cd.type == SHAPE_HULL) collider_most = std::max(collider_most, cd.nv + (int)s.hulls[cd.hull].normals.size());
+			}
+			body_most = std::max(body_most, nv);
+		}
+		d.split_bounds = body_most > 64 ? 1 : 0;
+		b->transform_slices = (unsigned int)std::min(16, std::max(1, collider_most / 64));
 		d.split_big = b->has_big_pairs ? 1 : 0;
 		if ((rc = dev_alloc(b, &d.big_sup, b->has_big_pairs ? WP : 1, false))) return rc;
 	}
@@ -654,11 +676,11 @@ static void enqueue_prologue(rp_batch* b, double dt, int collisions) {
 // (WarpQueue): launch exactly the CTAs that are resident at once (occupancy measured at batch creation).
 static void launch_solve_pos(rp_batch* b, double h, uint32_t iters, int collisions) {
 	if (iters == 0) return;
-	if (b->d.NJ > 0) launch_cooperative(k_solve_pos<true>, b->pos_grid, 128u, b->stream, b->d, h, (int)iters, collisions);
-	else launch_cooperative(k_solve_pos<false>, b->pos_grid, 128u, b->stream, b->d, h, (int)iters, collisions);
+	if (b->d.NJ > 0) launch_cooperative(k_solve_pos<true>, b->pos_grid, 128u, b->live_smem, b->stream, b->d, h, (int)iters, collisions, b->live_lists);
+	else launch_cooperative(k_solve_pos<false>, b->pos_grid, 128u, b->live_smem, b->stream, b->d, h, (int)iters, collisions, b->live_lists);
 }
 static void launch_solve_vel(rp_batch* b, double h) {
-	launch_cooperative(k_solve_vel, b->vel_grid, 128u, b->stream, b->d, h);
+	launch_cooperative(k_solve_vel, b->vel_grid, 128u, b->live_smem, b->stream, b->d, h, b->live_lists);
 }
 
 static void enqueue_integrate(rp_batch* b, double h, bool last_substep) {
@@ -671,8 +693,11 @@ static void enqueue_integrate(rp_batch* b, double h, bool last_substep) {
 // grid-stride trips of at most this many CTAs
 static unsigned int manifold_grid(const rp_batch* b) { return (unsigned int)b->sm_count * 16u; }
 static void launch_cull(rp_batch* b) {
-	k_cull<<<dim3(b->cull_chunks, (b->d.W + 31) / 32), 256, 0, b->stream>>>(b->d, b->cull);
-	k_transform<<<dim3(b->d.NB, (b->d.W + RP_INT_THREADS - 1) / RP_INT_THREADS), RP_INT_THREADS, 0, b->stream>>>(b->d);
+	const DevView& d = b->d;
+	const unsigned int wblocks = (unsigned int)((d.W + RP_INT_THREADS - 1) / RP_INT_THREADS);
+	if (d.split_bounds) k_bounds<<<dim3(d.NC, wblocks), RP_INT_THREADS, 0, b->stream>>>(d);
+	k_cull<<<dim3(b->cull_chunks, (d.W + 31) / 32), 256, 0, b->stream>>>(d, b->cull);
+	k_transform<<<dim3(d.NC, wblocks, b->transform_slices), RP_INT_THREADS, 0, b->stream>>>(d);
 }
 static void launch_gjk(rp_batch* b) {
 	k_gjk<<<b->sm_count * 16, RP_GJK_THREADS, 0, b->stream>>>(b->d);

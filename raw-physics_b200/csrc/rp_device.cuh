@@ -88,6 +88,7 @@ struct DevView {
 	unsigned int* cand_count;
 	unsigned int* big_count;   // candidates with hulls too large to stage per thread: kept at the END of cands, taken by k_gjk_warp
 	unsigned int cand_cap;     // W * max_pairs
+	int split_bounds;          // bodies carry so much geometry that the bounds are computed per collider (k_bounds), not per body in k_integrate
 	int split_big;             // the scene has such pairs: k_epa leaves them to k_epa_warp, k_manifold takes their supports from big_sup
 	int2* big_sup;             // [W * max_pairs] per hit of a large pair: support vertices of the two hulls along +-normal (k_epa_warp)
 	uint4* hits;         // [W * max_pairs] the colliding candidates' records, dense (one load tells EPA / clipping where their inputs are)

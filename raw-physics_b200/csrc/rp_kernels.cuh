@@ -522,6 +522,24 @@ __global__ void __launch_bounds__(256) k_substep_reset(DevView d) {
 }
 
 #define RP_INT_THREADS 128
+// world-space bounds of one collider from its body's pose (collider_update's bounds, see k_integrate / k_bounds)
+__device__ __forceinline__ void collider_bounds(const DevView& d, const ColliderDesc& cd, const Pose34& M, V3 x, float* bb, size_t S) {
+	if (cd.type == SHAPE_SPHERE) {
+		const double rad = (double)cd.radius;
+		bb[0] = __double2float_rd(x.x - rad); bb[S] = __double2float_rd(x.y - rad); bb[2 * S] = __double2float_rd(x.z - rad);
+		bb[3 * S] = __double2float_ru(x.x + rad); bb[4 * S] = __double2float_ru(x.y + rad); bb[5 * S] = __double2float_ru(x.z + rad);
+	} else {
+		const HullTopo t = d.pool.hulls[cd.hull];
+		double lo0 = 1.7976931348623157e308, lo1 = lo0, lo2 = lo0, hi0 = -lo0, hi1 = -lo0, hi2 = -lo0;
+		for (int k = 0; k < t.nv; ++k) {
+			const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
+			lo0 = fmin(lo0, p.x); lo1 = fmin(lo1, p.y); lo2 = fmin(lo2, p.z);
+			hi0 = fmax(hi0, p.x); hi1 = fmax(hi1, p.y); hi2 = fmax(hi2, p.z);
+		}
+		bb[0] = __double2float_rd(lo0); bb[S] = __double2float_rd(lo1); bb[2 * S] = __double2float_rd(lo2);
+		bb[3 * S] = __double2float_ru(hi0); bb[4 * S] = __double2float_ru(hi1); bb[5 * S] = __double2float_ru(hi2);
+	}
+}
 // pbd.cpp:537-577 (integration) and collider.cpp:409-445 (collider_update) for one body per thread. The reference
 // re-transforms both colliders of every pair every substep (39 % of its time); the same pose gives the same result,
 // so once per body per substep is exactly equivalent. Also leaves each collider's world-space bounds
@@ -574,65 +592,56 @@ __global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate
 	// themselves are written by k_transform, after the cull, and only for colliders that are part of a surviving
 	// candidate pair: geometry nothing will look at is not written (it is the larger half of what this kernel, which runs
 	// at the HBM roof, used to store).
+	if (d.split_bounds) return;  // k_bounds does it per collider
+	// bounds are kept in float, lower ends rounded down and upper ends up: still boxes AROUND the vertex sets, so the cull
+	// stays exact-safe (it can only keep a pair it might have dropped), at half the bytes written here and read there
 	const Pose34 M = model_matrix(body.q, body.x);
-	for (int c = s.col0; c < s.col0 + s.ncol; ++c) {
-		const ColliderDesc cd = d.cols[c];
-		// bounds are kept in float, lower ends rounded down and upper ends up: still boxes AROUND the vertex sets, so the
-		// cull stays exact-safe (it can only keep a pair it might have dropped), at half the bytes written here and read there
-		float* bb = d.aabb + (size_t)c * 6 * S + w;
-		if (cd.type == SHAPE_SPHERE) {
-			const double rad = (double)cd.radius;
-			bb[0] = __double2float_rd(body.x.x - rad); bb[S] = __double2float_rd(body.x.y - rad); bb[2 * S] = __double2float_rd(body.x.z - rad);
-			bb[3 * S] = __double2float_ru(body.x.x + rad); bb[4 * S] = __double2float_ru(body.x.y + rad); bb[5 * S] = __double2float_ru(body.x.z + rad);
-		} else {
-			const HullTopo t = d.pool.hulls[cd.hull];
-			double lo0 = 1.7976931348623157e308, lo1 = lo0, lo2 = lo0, hi0 = -lo0, hi1 = -lo0, hi2 = -lo0;
-			for (int k = 0; k < t.nv; ++k) {
-				const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
-				lo0 = fmin(lo0, p.x); lo1 = fmin(lo1, p.y); lo2 = fmin(lo2, p.z);
-				hi0 = fmax(hi0, p.x); hi1 = fmax(hi1, p.y); hi2 = fmax(hi2, p.z);
-			}
-			bb[0] = __double2float_rd(lo0); bb[S] = __double2float_rd(lo1); bb[2 * S] = __double2float_rd(lo2);
-			bb[3 * S] = __double2float_ru(hi0); bb[4 * S] = __double2float_ru(hi1); bb[5 * S] = __double2float_ru(hi2);
-		}
-	}
+	for (int c = s.col0; c < s.col0 + s.ncol; ++c) collider_bounds(d, d.cols[c], M, body.x, d.aabb + (size_t)c * 6 * S + w, S);
+}
+
+// the bounds of every collider, one thread per (collider, world): for scenes whose bodies carry so many vertices (compound
+// bodies of large hulls) that k_integrate's one thread per body would walk thousands of them
+__global__ void __launch_bounds__(RP_INT_THREADS) k_bounds(DevView d) {
+	const int w = blockIdx.y * RP_INT_THREADS + threadIdx.x;
+	const int c = blockIdx.x;
+	if (w >= d.W) return;
+	const ColliderDesc cd = d.cols[c];
+	const DynRef r = dyn_ref(d, w, cd.body);
+	const V3 x = ld3(r, DF_X);
+	const Pose34 M = model_matrix(ld4(r, DF_Q), x);
+	collider_bounds(d, cd, M, x, d.aabb + (size_t)c * 6 * d.WS + w, d.WS);
 }
 
 // collider_update's other half (collider.cpp:409-445), after k_cull: transformed vertices and re-normalised face normals
 // of the colliders k_cull marked (geom_stamp == this substep) -- the ones GJK, EPA or clipping will read. Same pose, same
-// operations as the reference's per-pair calls (pbd.cpp:598-599), so the same bits. Thread = (body, world), lane = world.
+// operations as the reference's per-pair calls (pbd.cpp:598-599), so the same bits. Thread = (collider, world, slice):
+// lane = world; gridDim.z slices share out the vertices and normals of large hulls (one slice for the small hulls of the
+// headline scenes).
 __global__ void __launch_bounds__(RP_INT_THREADS) k_transform(DevView d) {
 	const int w = blockIdx.y * RP_INT_THREADS + threadIdx.x;
-	const int b = blockIdx.x;
+	const int c = blockIdx.x;
 	if (w >= d.W) return;
-	const int epoch = *d.epoch;
 	const size_t S = d.WS;
-	const BodyStatic s = d.bstat[b];
-	bool any = false;
-	for (int c = s.col0; c < s.col0 + s.ncol; ++c) any = any || d.geom_stamp[(size_t)c * S + w] == epoch;
-	if (!any) return;
-	const DynRef r = dyn_ref(d, w, b);
+	if (d.geom_stamp[(size_t)c * S + w] != *d.epoch) return;
+	const ColliderDesc cd = d.cols[c];
+	const DynRef r = dyn_ref(d, w, cd.body);
 	const V3 x = ld3(r, DF_X);
-	const Q4 q = ld4(r, DF_Q);
-	const Pose34 M = model_matrix(q, x);
-	for (int c = s.col0; c < s.col0 + s.ncol; ++c) {
-		if (d.geom_stamp[(size_t)c * S + w] != epoch) continue;
-		const ColliderDesc cd = d.cols[c];
-		double* tv = d.tv + (size_t)cd.tv0 * 3 * S + w;
-		if (cd.type == SHAPE_SPHERE) {
-			tv[0] = x.x; tv[S] = x.y; tv[2 * S] = x.z;
-		} else {
-			const HullTopo t = d.pool.hulls[cd.hull];
-			double* tn = d.tn + (size_t)cd.tn0 * 3 * S + w;
-			for (int k = 0; k < t.nv; ++k) {
-				const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
-				tv[(size_t)(3 * k) * S] = p.x; tv[(size_t)(3 * k + 1) * S] = p.y; tv[(size_t)(3 * k + 2) * S] = p.z;
-			}
-			for (int k = 0; k < t.nf; ++k) {
-				const V3 n = transform_normal(M, d.pool.normals[t.face0 + k]);
-				tn[(size_t)(3 * k) * S] = n.x; tn[(size_t)(3 * k + 1) * S] = n.y; tn[(size_t)(3 * k + 2) * S] = n.z;
-			}
-		}
+	const Pose34 M = model_matrix(ld4(r, DF_Q), x);
+	double* tv = d.tv + (size_t)cd.tv0 * 3 * S + w;
+	const int first = blockIdx.z, step = gridDim.z;
+	if (cd.type == SHAPE_SPHERE) {
+		if (first == 0) { tv[0] = x.x; tv[S] = x.y; tv[2 * S] = x.z; }
+		return;
+	}
+	const HullTopo t = d.pool.hulls[cd.hull];
+	double* tn = d.tn + (size_t)cd.tn0 * 3 * S + w;
+	for (int k = first; k < t.nv; k += step) {
+		const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
+		tv[(size_t)(3 * k) * S] = p.x; tv[(size_t)(3 * k + 1) * S] = p.y; tv[(size_t)(3 * k + 2) * S] = p.z;
+	}
+	for (int k = first; k < t.nf; k += step) {
+		const V3 n = transform_normal(M, d.pool.normals[t.face0 + k]);
+		tn[(size_t)(3 * k) * S] = n.x; tn[(size_t)(3 * k + 1) * S] = n.y; tn[(size_t)(3 * k + 2) * S] = n.z;
 	}
 }
 
@@ -1201,13 +1210,67 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 // JOINTS = false is the build for scenes without external constraints: the joint solves (hinge, spherical, their libm
 // calls) are three quarters of this kernel's 14 k instructions, and the contact loop already runs short of instruction
 // cache at two warps per scheduler (ncu, round 1: no_instruction is its second largest stall).
+// Deep schedules are mostly empty: a pair of compound bodies expands to (colliders x colliders) units that all share the
+// two bodies and therefore chain (spot_storm: 11 x 11 = 121 units per body pair, sweeps 1300+ levels deep), of which a
+// handful have contacts in any one substep. Walking every level just to find it empty costs two dependent loads each, so
+// for schedules deeper than RP_LIVE_MIN every CTA first builds the ascending list of levels that have work (same inputs,
+// same list in every CTA, so the grid barriers stay matched) and the sweep walks that.
+#define RP_LIVE_MIN 64
+#define RP_LIVE_MAX 4096
+struct LiveLevels {
+	int list[RP_LIVE_MAX];
+	unsigned int mask[RP_LIVE_MAX / 32];
+	int off[RP_LIVE_MAX / 32];
+	int n;
+};
+// returns the number of listed levels, or -1 when the plain walk over 1..levels is to be used. The list lives in DYNAMIC
+// shared memory that the host only asks for when the scene can have deep schedules (`enabled`): the sweeps of the headline
+// scenes keep those 17 kB as L1.
 template <bool JOINTS>
-__global__ void __launch_bounds__(128, RP_MINB_POS) k_solve_pos(DevView d, double h, int iters, int collisions) {
+__device__ __forceinline__ int list_live_levels(const DevView& d, LiveLevels& s, int levels, int collisions, int enabled) {
+	if (!enabled || levels <= RP_LIVE_MIN || levels > RP_LIVE_MAX) return -1;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	const int nchunks = (levels + 31) >> 5;
+	for (int c = warp; c < nchunks; c += nwarps) {
+		const int l = 1 + (c << 5) + lane;
+		bool live = false;
+		if (l <= levels) {
+			if (collisions) live = d.lvl_fill[(size_t)l * RP_LVL_STRIDE] + d.lvl_fill[(size_t)l * RP_LVL_STRIDE + 1] > 0;
+			if (JOINTS && l <= d.joint_levels) live = live || d.joint_lptr[l] > d.joint_lptr[l - 1];
+		}
+		const unsigned int m = __ballot_sync(0xffffffffu, live);
+		if (lane == 0) s.mask[c] = m;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int run = 0;
+		for (int c = 0; c < nchunks; ++c) {
+			s.off[c] = run;
+			run += __popc(s.mask[c]);
+		}
+		s.n = run;
+	}
+	__syncthreads();
+	for (int c = warp; c < nchunks; c += nwarps) {
+		const unsigned int m = s.mask[c];
+		if ((m >> lane) & 1u) s.list[s.off[c] + __popc(m & ((1u << lane) - 1u))] = 1 + (c << 5) + lane;
+	}
+	__syncthreads();
+	return s.n;
+}
+
+template <bool JOINTS>
+__global__ void __launch_bounds__(128, RP_MINB_POS) k_solve_pos(DevView d, double h, int iters, int collisions, int live_lists) {
 	cg::grid_group grid = cg::this_grid();
+	extern __shared__ __align__(16) unsigned char s_live_raw[];
+	LiveLevels& s_live = *reinterpret_cast<LiveLevels*>(s_live_raw);
 	const int levels = *d.lvl_max;  // this frame's sweep depth over all worlds (k_schedule): read here, the host never needs it
+	const int n_live = list_live_levels<JOINTS>(d, s_live, levels, collisions, live_lists);
+	const int trips = n_live >= 0 ? n_live : levels;
 	bool dirty = false;
 	for (int it = 0; it < iters; ++it) {
-		for (int level = 1; level <= levels; ++level) {
+		for (int i = 0; i < trips; ++i) {
+			const int level = n_live >= 0 ? s_live.list[i] : i + 1;
 			const int nj = JOINTS && level <= d.joint_levels ? d.joint_lptr[level] - d.joint_lptr[level - 1] : 0;
 			const int np = collisions ? d.lvl_fill[(size_t)level * RP_LVL_STRIDE] + d.lvl_fill[(size_t)level * RP_LVL_STRIDE + 1] : 0;
 			if (nj == 0 && np == 0) continue;
@@ -1320,11 +1383,16 @@ __device__ __forceinline__ void vel_level(const DevView& d, double h, int level)
 	}
 }
 
-__global__ void __launch_bounds__(128, RP_MINB_VEL) k_solve_vel(DevView d, double h) {
+__global__ void __launch_bounds__(128, RP_MINB_VEL) k_solve_vel(DevView d, double h, int live_lists) {
 	cg::grid_group grid = cg::this_grid();
+	extern __shared__ __align__(16) unsigned char s_live_raw[];
+	LiveLevels& s_live = *reinterpret_cast<LiveLevels*>(s_live_raw);
 	const int levels = *d.lvl_max;
+	const int n_live = list_live_levels<false>(d, s_live, levels, 1, live_lists);
+	const int trips = n_live >= 0 ? n_live : levels;
 	bool dirty = false;
-	for (int level = 1; level <= levels; ++level) {
+	for (int i = 0; i < trips; ++i) {
+		const int level = n_live >= 0 ? s_live.list[i] : i + 1;
 		if (d.lvl_fill[(size_t)level * RP_LVL_STRIDE] + d.lvl_fill[(size_t)level * RP_LVL_STRIDE + 1] == 0) continue;
 		if (dirty) grid.sync();
 		vel_level(d, h, level);

@@ -190,6 +190,7 @@ int Scene::add_hull_collider(const double* vx, uint32_t nverts, const uint32_t* 
 	c.radius = 0.0f;
 	c.tv0 = c.tn0 = 0;
 	c.nv = (int)hulls[id].verts.size();
+	c.body = -1;
 	pending.push_back(c);
 	return (int)pending.size() - 1;
 }
@@ -217,6 +218,7 @@ int Scene::add_hull_topology(const HullHost& h) {
 	c.radius = 0.0f;
 	c.tv0 = c.tn0 = 0;
 	c.nv = (int)hulls[id].verts.size();
+	c.body = -1;
 	pending.push_back(c);
 	return (int)pending.size() - 1;
 }
@@ -228,6 +230,7 @@ int Scene::add_sphere_collider(float radius) {  // collider_sphere_create (colli
 	c.radius = radius;
 	c.tv0 = c.tn0 = 0;
 	c.nv = 0;
+	c.body = -1;
 	pending.push_back(c);
 	return (int)pending.size() - 1;
 }
@@ -333,6 +336,7 @@ static int commit_body(Scene& sc, BodyInit& b) {
 	std::vector<V3>& torque = sc.torque;
 	for (size_t i = 0; i < pending.size(); ++i) {
 		ColliderDesc c = pending[i];
+		c.body = (int)bodies.size();
 		c.tv0 = total_tv;
 		c.tn0 = total_tn;
 		if (c.type == SHAPE_HULL) {

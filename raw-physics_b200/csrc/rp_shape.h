@@ -41,6 +41,7 @@ struct ColliderDesc {
 	int tv0;                  // first transformed vertex (and, for a sphere, the slot holding its centre)
 	int tn0;                  // first transformed normal
 	int nv;                   // vertices of the hull (0 for a sphere): decides which narrowphase kernel takes a pair
+	int body;                 // the body that carries this collider
 };
 
 // A collider at a pose, as the narrowphase sees it.
