@@ -695,6 +695,7 @@ static unsigned int manifold_grid(const rp_batch* b) { return (unsigned int)b->s
 static void launch_cull(rp_batch* b) {
 	const DevView& d = b->d;
 	const unsigned int wblocks = (unsigned int)((d.W + RP_INT_THREADS - 1) / RP_INT_THREADS);
+	if (d.NC == 0) return;  // bodies without colliders (joint-only scenes): no pairs, no candidates, nothing to transform
 	if (d.split_bounds) k_bounds<<<dim3(d.NC, wblocks), RP_INT_THREADS, 0, b->stream>>>(d);
 	k_cull<<<dim3(b->cull_chunks, (d.W + 31) / 32), 256, 0, b->stream>>>(d, b->cull);
 	k_transform<<<dim3(d.NC, wblocks, b->transform_slices), RP_INT_THREADS, 0, b->stream>>>(d);
