@@ -1,7 +1,8 @@
 // rp_device.cuh -- device data model of a batch (n_worlds instances of one scene template in HBM) and the kernels of
 // the XPBD frame step. One launch works on ALL worlds; the per-substep sequence is
-//   k_integrate -> k_gjk -> k_manifold -> k_solve
-// preceded once per frame by k_broad_cells / k_broad_scan / k_broad_write / k_islands / k_schedule
+//   k_integrate -> [k_bounds] -> k_cull -> k_transform -> k_gjk [k_gjk_warp] -> k_epa [k_epa_warp] -> k_manifold
+//   -> k_solve_pos -> k_solve_vel
+// preceded once per frame by k_broad_cells / k_broad_scan / k_broad_write / k_islands / k_schedule and followed by k_derive
 // (pbd_simulate_with_constraints, src/physics/pbd.cpp:468-747). See DESIGN.md for the layout and the roofline of each.
 #ifndef RP_DEVICE_CUH
 #define RP_DEVICE_CUH
