@@ -128,3 +128,19 @@ def test_adopted_topology_and_params_round_trip(pkg):
         h[k].ctypes.data_as(up) for k in ("v2f_ptr", "v2f_idx", "v2n_ptr", "v2n_idx", "f2n_ptr", "f2n_idx")]
     assert L.rp_scene_collider_hull_topology(adopted.h, h["verts"].ctypes.data_as(dp), h["verts"].shape[0],
                                              h["normals"].ctypes.data_as(dp), h["normals"].shape[0], *args) == -1
+
+
+def test_shim_build_links_against_the_library(pkg):
+    """oracle/_ref/libref_shim.so (the unmodified reference + raw-physics_b200/shim/pbd_b200.cpp, `make -C oracle shim`)
+    loads, resolves librawphys_b200.so through its rpath and builds scenes with the reference's own code; stepping it
+    needs a GPU (tests/test_gpu_shim.py)."""
+    import refdrv
+    if not (refdrv.available("shim") and refdrv.available("strict")):
+        pytest.skip("built only where /root/reference is present")
+    sc = scenes.BUILDERS["mirror_cube"]()
+    a, b = refdrv.RefWorld("strict").load(sc), refdrv.RefWorld("shim").load(sc)
+    assert np.array_equal(a.params(), b.params()) and np.array_equal(a.state(), b.state())
+    src = open(os.path.join(ROOT, "raw-physics_b200", "shim", "pbd_b200.cpp")).read()
+    for needle in ("rp_scene_collider_hull_topology", "rp_scene_add_body_params", "rp_batch_step_host", "_Z12pbd_simulatedPP6Entityjji",
+                   "_Z29pbd_simulate_with_constraintsdPP6EntityP10Constraintjji"):
+        assert needle in src
