@@ -32,6 +32,7 @@ TRAJ = {
     "pile": (dict(n_side=3), [1, 40]),
     "tumble": ({}, [1, 90]),
     "w256": ({}, [1, 5]),
+    "spot_storm": (dict(n=2), [1, 24]),
 }
 HULLS = ["cube", "floor", "ico", "ramp", "cylinder", "lever", "seesaw_support"]
 
@@ -48,6 +49,7 @@ def main():
                 w.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
                 done += 1
             out["%s/state/%d" % (name, f)] = w.state()
+            out["%s/prev_vel/%d" % (name, f)] = w.prev_velocities()
             if f == 1:
                 calls, contacts = w.log_get()
                 out["%s/calls" % name] = calls

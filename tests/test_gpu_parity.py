@@ -107,6 +107,7 @@ def test_golden_fixtures(pkg):
                 step(b, sc)
                 done += 1
             assert np.array_equal(b.state()[0, :, :15], GOLD["%s/state/%d" % (name, f)]), (name, f)
+            assert np.array_equal(b.state()[0, :, 15:21], GOLD["%s/prev_vel/%d" % (name, f)]), (name, f)
 
 
 def test_known_answer_vector(pkg):

@@ -20,7 +20,7 @@ HULLS = np.load(os.path.join(HERE, "golden", "hulls.npz"))
 need_ref = pytest.mark.skipif(not refdrv.available("strict"), reason="oracle/_ref/libref_oracle.so not present")
 
 TRAJ = {"stack": {}, "brick_wall": {}, "cube_storm": {}, "seesaw": {}, "cube_and_ramp": {}, "coin": {}, "spring": {}, "hinge_joints": {},
-        "arm": {}, "triple_pendula": {}, "mirror_cube": {}, "spheres": {}, "pile": dict(n_side=3), "tumble": {}, "w256": {}}
+        "arm": {}, "triple_pendula": {}, "mirror_cube": {}, "spheres": {}, "pile": dict(n_side=3), "tumble": {}, "w256": {}, "spot_storm": dict(n=2)}
 
 
 def golden_frames(name):
@@ -70,6 +70,7 @@ def test_port_matches_golden_trajectories(name):
             w.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
             done += 1
         assert np.array_equal(w.state(), GOLD["%s/state/%d" % (name, f)]), (name, f)
+        assert np.array_equal(w.prev_velocities(), GOLD["%s/prev_vel/%d" % (name, f)]), (name, f)
         if f == 1:
             calls, contacts = w.log_get()
             assert np.array_equal(calls, GOLD[name + "/calls"])
