@@ -18,11 +18,16 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))
+WINDOWS = np.load(os.path.join(ROOT, "tests", "golden", "windows.npz"))
 
 CONTACT_SCENES = {"stack": ({}, 90), "brick_wall": ({}, 60), "cube_storm": ({}, 90), "seesaw": ({}, 120), "cube_and_ramp": ({}, 120),
                   "coin": ({}, 90), "mirror_cube": ({}, 120), "spheres": ({}, 150), "pile": (dict(n_side=3), 60), "tumble": ({}, 120),
-                  "spring": ({}, 60)}
-JOINT_SCENES = {"hinge_joints": ({}, 120), "arm": ({}, 120), "triple_pendula": ({}, 40)}
+                  "spring": ({}, 60),
+                  # positional + mutual-orientation joints + contacts: no libm call on the path (pbd.cpp:156-173), so bit-exact
+                  "mutual_orientation": ({}, 90)}
+JOINT_SCENES = {"hinge_joints": ({}, 120), "arm": ({}, 120), "triple_pendula": ({}, 40),
+                # a hinge limited to [0, 0] at 50 substeps x 50 iterations (rott_pendulum.cpp:154); NEGATIVE_* axis selectors (q4)
+                "rott_pendulum": ({}, 30), "negative_axes": ({}, 60)}
 
 
 def make(pkg, sc, n_worlds=1, **kw):
@@ -108,6 +113,49 @@ def test_golden_fixtures(pkg):
                 done += 1
             assert np.array_equal(b.state()[0, :, :15], GOLD["%s/state/%d" % (name, f)]), (name, f)
             assert np.array_equal(b.state()[0, :, 15:21], GOLD["%s/prev_vel/%d" % (name, f)]), (name, f)
+
+
+def window_digest(calls, contacts):
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(calls, dtype=np.uint32).tobytes())
+    h.update(np.ascontiguousarray(contacts, dtype=np.float64).tobytes())
+    return np.frombuffer(h.digest(), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("name,kw,frames", [("w256", {}, 60), ("brick_wall_32x32", dict(rows=32, cols=32), 30)])
+def test_timed_window_bit_exact(pkg, oracle_flavour, name, kw, frames):
+    """What bench.py TIMES is what is checked: the whole W256 window (frames 0..59; the driver's K = 20 run times frames
+    40..59, where a world holds ~310 contacts per substep) and 30 frames of the 32x32 brick wall as one scene, frame by
+    frame against the oracle stepped alongside AND the compiled reference's committed outputs (tests/golden/windows.npz):
+    state every frame, narrowphase call / contact counts every frame (pbd.cpp:584-611), and every call row and contact point
+    of the last frame."""
+    sc = scenes.BUILDERS[name.split("_32")[0]](**kw)
+    b = make(pkg, sc, n_worlds=2)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    want = WINDOWS[name + "/counts"]
+    c0 = b.counters()
+    for f in range(frames):
+        last = f + 1 == frames
+        if last:
+            calls, contacts = b.step_logged(world=1, substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions, max_calls=1 << 18)
+        else:
+            step(b, sc)
+        o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+        got = b.state()
+        assert np.array_equal(got[1, :, :15], o.state()), (name, f, np.abs(got[1, :, :15] - o.state()).max())
+        assert np.array_equal(got[0], got[1])
+        c1 = b.counters()
+        assert ((c1["pair_tests"] - c0["pair_tests"]) // 2, (c1["contacts"] - c0["contacts"]) // 2) == tuple(want[f]), (name, f)
+        c0 = c1
+        key = "%s/state/%d" % (name, f + 1)
+        if key in WINDOWS.files:
+            assert np.array_equal(got[0, :, :15], WINDOWS[key]), key
+    assert np.array_equal(window_digest(calls, contacts), WINDOWS[name + "/last_log_digest"])
+    sub = refdrv.split_substeps(calls)
+    assert np.array_equal(np.asarray(sub[-1], dtype=np.uint32), WINDOWS[name + "/last_substep_calls"])
+    assert np.array_equal(contacts[int(sub[-1][0][3]):], WINDOWS[name + "/last_substep_contacts"])
+    assert not b.status().any()
 
 
 def test_known_answer_vector(pkg):

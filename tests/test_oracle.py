@@ -16,11 +16,12 @@ import scenes
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = np.load(os.path.join(HERE, "golden", "trajectories.npz"))
 HULLS = np.load(os.path.join(HERE, "golden", "hulls.npz"))
+WINDOWS = np.load(os.path.join(HERE, "golden", "windows.npz"))
 
 need_ref = pytest.mark.skipif(not refdrv.available("strict"), reason="oracle/_ref/libref_oracle.so not present")
 
 TRAJ = {"stack": {}, "brick_wall": {}, "cube_storm": {}, "seesaw": {}, "cube_and_ramp": {}, "coin": {}, "spring": {}, "hinge_joints": {},
-        "arm": {}, "triple_pendula": {}, "mirror_cube": {}, "spheres": {}, "pile": dict(n_side=3), "tumble": {}, "w256": {}, "spot_storm": dict(n=2)}
+        "arm": {}, "triple_pendula": {}, "rott_pendulum": {}, "mutual_orientation": {}, "negative_axes": {}, "mirror_cube": {}, "spheres": {}, "pile": dict(n_side=3), "tumble": {}, "w256": {}, "spot_storm": dict(n=2)}
 
 
 def golden_frames(name):
@@ -197,3 +198,34 @@ def test_port_spot_storm_matches_reference():
         b.step()
     assert np.array_equal(a.state(), b.state())
     assert a.state()[1:, 1].min() < 3.0  # they have landed: contacts were solved
+
+
+def window_digest(calls, contacts):
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(calls, dtype=np.uint32).tobytes())
+    h.update(np.ascontiguousarray(contacts, dtype=np.float64).tobytes())
+    return np.frombuffer(h.digest(), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("name,kw,frames", [("w256", {}, 60), ("brick_wall_32x32", dict(rows=32, cols=32), 30)])
+def test_port_matches_timed_windows(name, kw, frames):
+    """The windows bench.py TIMES (W256 frames 0..59, brick wall 32x32 frames 0..29): per-frame narrowphase call and contact
+    counts, states at three frames and the digest of the last frame's whole contact log, against the compiled reference's
+    (tests/golden/windows.npz)."""
+    sc = scenes.BUILDERS[name.split("_32")[0]](**kw)
+    w = refdrv.RefWorld("port").load(sc)
+    w.log_enable(True)
+    want = WINDOWS[name + "/counts"]
+    for f in range(frames):
+        w.log_clear()
+        w.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+        calls, contacts = w.log_get()
+        assert (len(calls), len(contacts)) == tuple(want[f]), (name, f)
+        key = "%s/state/%d" % (name, f + 1)
+        if key in WINDOWS.files:
+            assert np.array_equal(w.state(), WINDOWS[key]), key
+    assert np.array_equal(window_digest(calls, contacts), WINDOWS[name + "/last_log_digest"])
+    sub = refdrv.split_substeps(calls)
+    assert np.array_equal(np.asarray(sub[-1], dtype=np.uint32), WINDOWS[name + "/last_substep_calls"])
+    assert np.array_equal(contacts[int(sub[-1][0][3]):], WINDOWS[name + "/last_substep_contacts"])
