@@ -117,6 +117,8 @@ typedef struct {
 	uint32_t max_contacts_per_world;  /* contact capacity per substep; 0 = derive */
 	uint32_t disable_cull;            /* 1 = run GJK on every broadphase pair (the exact-safe bounds cull is on by default) */
 	uint32_t solve_order;             /* RP_ORDER_REFERENCE (default) or RP_ORDER_COLOURED */
+	uint32_t sweep_block_worlds;      /* worlds per CTA of the world-block Gauss-Seidel sweeps; 0 = choose (level-major sweeps for small batches) */
+	uint32_t reserved0;
 	double linear_sleeping_threshold;   /* pbd.cpp:13, default 0.10 */
 	double angular_sleeping_threshold;  /* pbd.cpp:14, default 0.10 */
 	double deactivation_time;           /* pbd.cpp:15, default 1.0 */
@@ -163,7 +165,8 @@ int rp_batch_step_host(rp_batch* b, const double* host_state_in, double* host_st
 int rp_batch_get_status(rp_batch* b, int32_t* status_per_world);
 int rp_batch_clear_status(rp_batch* b);
 /* cumulative work counters since creation: [0] narrowphase collider-pair tests, [1] GJK hits (EPA runs),
- * [2] contacts, [3] broadphase pairs (per frame, summed), [4] solver levels (per frame, summed), [5] frames */
+ * [2] contacts, [3] broadphase pairs (per frame, summed), [4] solver levels (per frame, summed), [5] frames,
+ * [6] GJK runs (pair tests that survived the bounds cull) */
 int rp_batch_get_counters(rp_batch* b, uint64_t out8[8]);
 
 /* Parity instrumentation: one frame of ONE world stepped substep by substep, logging what the reference's

@@ -105,6 +105,8 @@ void update_colliders(World& w, int bi) {
 	}
 }
 
+static int g_epa_reruns = 0, g_clip_reruns = 0;  // pairs that overflowed the small stores (port_tier_reruns)
+
 struct VecSink {
 	std::vector<LoggedContact>* out;
 	V3 n;
@@ -124,17 +126,20 @@ void narrow_pair(World& w, int ca, int cb, std::vector<LoggedContact>& out) {
 	double depth;
 	static EpaScratch es;
 	static ClipScratch cs;
+	// the small stores the CUDA kernels keep in shared memory, with the full ones as second tier (rp_narrow.h)
+	static EpaSmallArrays es_small;
+	static ClipSmallArrays cs_small;
 	if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
 		if (!sphere_sphere(A, B, &normal, &depth)) return;
 	} else {
 		Simplex s;
 		if (!gjk(A, B, &s, &w.status, 0)) return;
-		if (!epa(A, B, s, es, &normal, &depth, &w.status, 0)) return;
+		if (!epa_tiered(A, B, s, es_small, es, &normal, &depth, &w.status, &g_epa_reruns)) return;
 	}
 	VecSink sink;
 	sink.out = &out;
 	sink.n = normal;
-	manifold(A, B, normal, depth, cs, &w.status, sink);
+	manifold_tiered(A, B, normal, depth, cs_small, cs, &w.status, sink, &g_clip_reruns);
 }
 
 int uf_find(std::vector<int>& p, int x) {
@@ -533,6 +538,8 @@ uint64_t port_cull_soundness(uint64_t trials, uint64_t seed, uint64_t* separated
 	return viol;
 }
 int port_status() { return g->status; }
+// pairs whose polytope / clip polygon outgrew the small (shared-memory sized) stores and were rerun on the full ones
+void port_tier_reruns(int out2[2]) { out2[0] = g_epa_reruns; out2[1] = g_clip_reruns; }
 
 }
 

@@ -38,7 +38,7 @@ KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "cull", "gj
 
 class BatchCfg(C.Structure):
     _fields_ = [("max_pairs_per_world", C.c_uint32), ("max_contacts_per_world", C.c_uint32), ("disable_cull", C.c_uint32),
-                ("solve_order", C.c_uint32),
+                ("solve_order", C.c_uint32), ("sweep_block_worlds", C.c_uint32), ("reserved0", C.c_uint32),
                 ("linear_sleeping_threshold", C.c_double), ("angular_sleeping_threshold", C.c_double), ("deactivation_time", C.c_double)]
 
 
@@ -200,7 +200,7 @@ class Scene:
 class Batch:
     """n_worlds instances of a scene on one GPU (rp_batch)."""
 
-    def __init__(self, scene, n_worlds=1, device=0, max_pairs=0, max_contacts=0, disable_cull=False, coloured=False):
+    def __init__(self, scene, n_worlds=1, device=0, max_pairs=0, max_contacts=0, disable_cull=False, coloured=False, sweep_block_worlds=0):
         self.L = lib()
         self.scene = scene
         cfg = BatchCfg()
@@ -209,6 +209,7 @@ class Batch:
         cfg.max_contacts_per_world = max_contacts
         cfg.disable_cull = int(disable_cull)
         cfg.solve_order = 1 if coloured else 0  # RP_ORDER_COLOURED / RP_ORDER_REFERENCE
+        cfg.sweep_block_worlds = sweep_block_worlds  # 0: the library chooses (world-block sweeps for large batches)
         h = C.c_void_p()
         _check(self.L.rp_batch_create(scene.h, n_worlds, device, C.byref(cfg), C.byref(h)), "rp_batch_create")
         self.h = h
@@ -279,7 +280,7 @@ class Batch:
         out = np.zeros(8, dtype=np.uint64)
         _check(self.L.rp_batch_get_counters(self.h, out.ctypes.data_as(_u64p)), "rp_batch_get_counters")
         return dict(pair_tests=int(out[0]), gjk_hits=int(out[1]), contacts=int(out[2]), broad_pairs=int(out[3]), levels=int(out[4]),
-                    frames=int(out[5]))
+                    frames=int(out[5]), gjk_runs=int(out[6]))
 
     def profile(self, frames, dt=1.0 / 60.0, substeps=20, iters=1, collisions=True):
         """device ms per kernel family over `frames` un-graphed frames"""

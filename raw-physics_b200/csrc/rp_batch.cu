@@ -1,6 +1,7 @@
 // rp_batch.cu -- the C ABI of include/rawphys_b200.h: scene templates on the host, world batches in device memory,
 // frame stepping through a CUDA graph. No CPU fallback: every batch entry point needs a CUDA device.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -68,6 +69,8 @@ struct rp_batch {
 	unsigned int transform_slices = 1;  // gridDim.z of k_transform: threads that share one collider's vertices and normals
 	bool has_big_pairs = false;   // some collider pair is too large for k_gjk's per-thread staging: k_gjk_warp is launched too
 	bool no_restitution = false;  // every body's restitution coefficient is zero (k_integrate's store_velocities)
+	int sweep_wpb = 0;            // worlds per CTA of the world-block sweeps (k_solve_block); 0 = level-major cooperative sweeps
+	size_t sweep_smem = 0;        // dynamic shared memory of k_solve_block (its per-level cursors)
 	std::vector<int> joint_level;  // template-constant levels of the external constraints
 	bool have_graph = false;
 	GraphKey graph_key;
@@ -397,14 +400,17 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		for (size_t i = 0; i < s.bodies.size(); ++i) most_colliders = std::max(most_colliders, s.bodies[i].ncol);
 		b->live_lists = most_colliders > 2 ? 1 : 0;
 		b->live_smem = b->live_lists ? sizeof(LiveLevels) : 0;
-		if (d.NJ > 0) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_pos<true>, 128, b->live_smem));
-		else RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_pos<false>, 128, b->live_smem));
+		if (d.NJ > 0) RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_pos<true>, RP_POS_THREADS, b->live_smem));
+		else RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_pos<false>, RP_POS_THREADS, b->live_smem));
 		if (per_sm < 1) return fail(RP_ERR_CUDA, "k_solve_pos does not fit an SM");
 		b->pos_grid = (unsigned int)(b->sm_count * per_sm);
-		RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_vel, 128, b->live_smem));
+		RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_vel, RP_VEL_THREADS, b->live_smem));
 		if (per_sm < 1) return fail(RP_ERR_CUDA, "k_solve_vel does not fit an SM");
 		b->vel_grid = (unsigned int)(b->sm_count * per_sm);
 	}
+	// the polytope / clip-polygon stores of the narrowphase live in (dynamic) shared memory
+	RP_CUDA(cudaFuncSetAttribute(k_epa, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_EPA_SMEM_BYTES));
+	RP_CUDA(cudaFuncSetAttribute(k_manifold, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_MANIFOLD_SMEM_BYTES));
 	RP_CUDA(cudaFuncSetAttribute(k_schedule<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_SCHED_SMEM_MAX));
 	RP_CUDA(cudaFuncSetAttribute(k_schedule<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_SCHED_SMEM_MAX));
 
@@ -514,8 +520,13 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.vstamp, SB))) return rc;
 	if ((rc = dev_alloc(b, &d.epoch, 1))) return rc;
 	if ((rc = dev_alloc(b, &d.deact, SB))) return rc;
-	if ((rc = dev_alloc(b, &d.tv, WS * std::max(d.TV, 1) * 3))) return rc;
+	// transformed geometry is not stored: the narrowphase evaluates vertices and face normals from the poses (PoseShape)
+	if ((rc = dev_alloc(b, &d.tv, 1))) return rc;
+#if defined(RP_STORED_NORMALS)
 	if ((rc = dev_alloc(b, &d.tn, WS * std::max(d.TN, 1) * 3))) return rc;
+#else
+	if ((rc = dev_alloc(b, &d.tn, 1))) return rc;
+#endif
 	if ((rc = dev_alloc(b, &d.pairs, SP))) return rc;
 	if ((rc = dev_alloc(b, &d.n_pairs, W))) return rc;
 	{
@@ -564,7 +575,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		d.split_big = b->has_big_pairs ? 1 : 0;
 		if ((rc = dev_alloc(b, &d.big_sup, b->has_big_pairs ? WP : 1, false))) return rc;
 	}
-	if ((rc = dev_alloc(b, &d.simplex, WP * 4, false))) return rc;
+	if ((rc = dev_alloc(b, &d.simplex, WP * 12, false))) return rc;
 	if ((rc = dev_alloc(b, &d.hits, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.hit_count, 1))) return rc;
 	if ((rc = dev_alloc(b, &d.epa_out, WP, false))) return rc;
@@ -576,6 +587,27 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.pair_normal, SP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.pair_coff, SP))) return rc;
 	if ((rc = dev_alloc(b, &d.pair_ccnt, SP))) return rc;
+	{
+		// World-block sweeps (k_solve_block) on request (rp_batch_cfg.sweep_block_worlds), if the per-level cursors fit shared
+		// memory. Measured on the north-star batch (4096 x W256, frames 40..59, ms per 400 substeps): level-major cooperative
+		// sweeps 180; world blocks of 2 / 4 / 8 / 16 worlds 355 / 227 / 219 / 193 -- a block only has its own worlds' units of
+		// a level to fill its lanes with, where the level-major lists pack every world's, so the default stays level-major.
+		int wpb = 0;
+		if (cfg.sweep_block_worlds) wpb = (int)cfg.sweep_block_worlds;
+		if (const char* e = getenv("RP_SWEEP_WPB")) wpb = atoi(e);  // tuning aid
+		const size_t smem = ((size_t)d.max_levels + 2) * sizeof(int);
+		if (wpb > RP_SB_MAX_WPB) wpb = RP_SB_MAX_WPB;
+		if (wpb > 0 && smem <= 96 * 1024) {
+			b->sweep_wpb = wpb;
+			b->sweep_smem = smem;
+			d.block_mode = 1;
+			RP_CUDA(cudaFuncSetAttribute(k_solve_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			RP_CUDA(cudaFuncSetAttribute(k_solve_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		}
+		if ((rc = dev_alloc(b, &d.live, d.block_mode ? SP : 1, false))) return rc;
+		if ((rc = dev_alloc(b, &d.n_live, W))) return rc;
+		if ((rc = dev_alloc(b, &d.blk_items, d.block_mode ? WP : 1, false))) return rc;
+	}
 	if ((rc = dev_alloc(b, &d.contacts, WS * d.max_contacts * 8, false))) return rc;
 	if ((rc = dev_alloc(b, &d.n_contacts, W))) return rc;
 	if ((rc = dev_alloc(b, &d.lambdas, WS * std::max(d.NJ, 1)))) return rc;
@@ -676,11 +708,11 @@ static void enqueue_prologue(rp_batch* b, double dt, int collisions) {
 // (WarpQueue): launch exactly the CTAs that are resident at once (occupancy measured at batch creation).
 static void launch_solve_pos(rp_batch* b, double h, uint32_t iters, int collisions) {
 	if (iters == 0) return;
-	if (b->d.NJ > 0) launch_cooperative(k_solve_pos<true>, b->pos_grid, 128u, b->live_smem, b->stream, b->d, h, (int)iters, collisions, b->live_lists);
-	else launch_cooperative(k_solve_pos<false>, b->pos_grid, 128u, b->live_smem, b->stream, b->d, h, (int)iters, collisions, b->live_lists);
+	if (b->d.NJ > 0) launch_cooperative(k_solve_pos<true>, b->pos_grid, (unsigned int)RP_POS_THREADS, b->live_smem, b->stream, b->d, h, (int)iters, collisions, b->live_lists);
+	else launch_cooperative(k_solve_pos<false>, b->pos_grid, (unsigned int)RP_POS_THREADS, b->live_smem, b->stream, b->d, h, (int)iters, collisions, b->live_lists);
 }
 static void launch_solve_vel(rp_batch* b, double h) {
-	launch_cooperative(k_solve_vel, b->vel_grid, 128u, b->live_smem, b->stream, b->d, h, b->live_lists);
+	launch_cooperative(k_solve_vel, b->vel_grid, (unsigned int)RP_VEL_THREADS, b->live_smem, b->stream, b->d, h, b->live_lists);
 }
 
 static void enqueue_integrate(rp_batch* b, double h, bool last_substep) {
@@ -698,16 +730,18 @@ static void launch_cull(rp_batch* b) {
 	if (d.NC == 0) return;  // bodies without colliders (joint-only scenes): no pairs, no candidates, nothing to transform
 	if (d.split_bounds) k_bounds<<<dim3(d.NC, wblocks), RP_INT_THREADS, 0, b->stream>>>(d);
 	k_cull<<<dim3(b->cull_chunks, (d.W + 31) / 32), 256, 0, b->stream>>>(d, b->cull);
+#if defined(RP_STORED_NORMALS)
 	k_transform<<<dim3(d.NC, wblocks, b->transform_slices), RP_INT_THREADS, 0, b->stream>>>(d);
+#endif
 }
 static void launch_gjk(rp_batch* b) {
 	k_gjk<<<b->sm_count * 16, RP_GJK_THREADS, 0, b->stream>>>(b->d);
 	if (b->has_big_pairs) k_gjk_warp<<<b->sm_count * 8, RP_GJK_WARP_THREADS, 0, b->stream>>>(b->d);
 }
 static void launch_manifold(rp_batch* b) {
-	k_epa<<<b->sm_count * 16, RP_EPA_THREADS, 0, b->stream>>>(b->d);
+	k_epa<<<b->sm_count * 16, RP_EPA_THREADS, RP_EPA_SMEM_BYTES, b->stream>>>(b->d);
 	if (b->has_big_pairs) k_epa_warp<<<b->sm_count * 8, RP_GJK_WARP_THREADS, 0, b->stream>>>(b->d);
-	k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, 0, b->stream>>>(b->d);
+	k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, RP_MANIFOLD_SMEM_BYTES, b->stream>>>(b->d);
 }
 static void enqueue_narrow(rp_batch* b) {
 	launch_cull(b);
@@ -715,6 +749,13 @@ static void enqueue_narrow(rp_batch* b) {
 	launch_manifold(b);
 }
 static void enqueue_solve(rp_batch* b, double h, uint32_t iters, int collisions) {
+	if (b->sweep_wpb > 0) {
+		// both sweeps of the substep in one launch, CTA = a block of worlds (k_solve_block)
+		const unsigned int grid = (unsigned int)((b->d.W + b->sweep_wpb - 1) / b->sweep_wpb);
+		if (b->d.NJ > 0) k_solve_block<true><<<grid, RP_SB_THREADS, b->sweep_smem, b->stream>>>(b->d, h, (int)iters, collisions, b->sweep_wpb);
+		else k_solve_block<false><<<grid, RP_SB_THREADS, b->sweep_smem, b->stream>>>(b->d, h, (int)iters, collisions, b->sweep_wpb);
+		return;
+	}
 	launch_solve_pos(b, h, iters, collisions);
 	// velocity derivation (pbd.cpp:623-643) is lazy: a body's velocities are derived by the first velocity-level unit
 	// that touches it, else by the next substep's k_integrate, else by k_derive at the end of the frame
@@ -1017,17 +1058,22 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 				if ((rc = mark(RP_K_CULL))) return rc;
 				launch_gjk(b);
 				if ((rc = mark(RP_K_GJK))) return rc;
-				k_epa<<<b->sm_count * 16, RP_EPA_THREADS, 0, b->stream>>>(d);
+				k_epa<<<b->sm_count * 16, RP_EPA_THREADS, RP_EPA_SMEM_BYTES, b->stream>>>(d);
 				if (b->has_big_pairs) k_epa_warp<<<b->sm_count * 8, RP_GJK_WARP_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_EPA))) return rc;
-				k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, 0, b->stream>>>(d);
+				k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, RP_MANIFOLD_SMEM_BYTES, b->stream>>>(d);
 				if ((rc = mark(RP_K_MANIFOLD))) return rc;
 			}
-			launch_solve_pos(b, h, iters, collisions ? 1 : 0);
-			if ((rc = mark(RP_K_SOLVE_POS))) return rc;
-			if (collisions) {
-				launch_solve_vel(b, h);
-				if ((rc = mark(RP_K_SOLVE_VEL))) return rc;
+			if (b->sweep_wpb > 0) {
+				enqueue_solve(b, h, iters, collisions ? 1 : 0);  // both sweeps in one launch: reported as solve_pos
+				if ((rc = mark(RP_K_SOLVE_POS))) return rc;
+			} else {
+				launch_solve_pos(b, h, iters, collisions ? 1 : 0);
+				if ((rc = mark(RP_K_SOLVE_POS))) return rc;
+				if (collisions) {
+					launch_solve_vel(b, h);
+					if ((rc = mark(RP_K_SOLVE_VEL))) return rc;
+				}
 			}
 		}
 		enqueue_frame_end(b, h);

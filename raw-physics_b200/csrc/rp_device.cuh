@@ -48,7 +48,7 @@ struct EpaOut {  // result of EPA (or the analytic sphere-sphere test) for one h
 	int ok, pad;
 };
 
-enum { CNT_PAIR_TESTS = 0, CNT_HITS = 1, CNT_CONTACTS = 2, CNT_BROAD_PAIRS = 3, CNT_LEVELS = 4, CNT_FRAMES = 5 };
+enum { CNT_PAIR_TESTS = 0, CNT_HITS = 1, CNT_CONTACTS = 2, CNT_BROAD_PAIRS = 3, CNT_LEVELS = 4, CNT_FRAMES = 5, CNT_CANDS = 6 };
 
 struct DevView {
 	int W, NB, NC, NJ, TV, TN;
@@ -93,7 +93,7 @@ struct DevView {
 	int split_big;             // the scene has such pairs: k_epa leaves them to k_epa_warp, k_manifold takes their supports from big_sup
 	int2* big_sup;             // [W * max_pairs] per hit of a large pair: support vertices of the two hulls along +-normal (k_epa_warp)
 	uint4* hits;         // [W * max_pairs] the colliding candidates' records, dense (one load tells EPA / clipping where their inputs are)
-	V3* simplex;         // [W * max_pairs][4] final GJK tetrahedron of each hit
+	double* simplex;     // [12][W * max_pairs] final GJK tetrahedron of each hit, as component planes (st_simplex)
 	unsigned int* hit_count;
 	EpaOut* epa_out;     // [W * max_pairs] per hit
 	// level-major work lists shared by all worlds: the pairs of dependency level l that have contacts this substep
@@ -103,6 +103,12 @@ struct DevView {
 	int* lvl_fill;       // [max_levels + 2] pairs of level l with contacts (per substep)
 	int* lvl_max;        // [1] deepest level of the frame over all worlds
 	SolveItem* lvl_items;  // [W * max_pairs] level l occupies [lvl_off[l], lvl_off[l] + lvl_fill[l])
+	// world-block sweeps (k_solve_block): the units of each WORLD that have contacts this substep, and each world block's
+	// units sorted by level
+	int block_mode;      // 1: the sweeps run per block of `worlds per block` consecutive worlds, CTA-scoped barriers between levels
+	uint2* live;         // [max_pairs][WS] per world: (pair, level) of its units with contacts, in arrival order (k_manifold)
+	int* n_live;         // [W]
+	unsigned int* blk_items;  // [W * max_pairs] block b's region starts at (first world of b) * max_pairs: (pair << 6 | world in block)
 	// template-constant schedule of the external constraints (they head the constraint array in every world)
 	const int* joint_sched;   // [NJ] joints sorted by level
 	const int* joint_lptr;    // [joint_levels + 1]

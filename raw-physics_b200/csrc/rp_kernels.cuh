@@ -23,13 +23,24 @@
 #define RP_MINB_MANIFOLD 4
 #endif
 #ifndef RP_MINB_EPA
-#define RP_MINB_EPA 6
+#define RP_MINB_EPA 5
 #endif
 #ifndef RP_MINB_POS
 #define RP_MINB_POS 3
 #endif
 #ifndef RP_MINB_VEL
 #define RP_MINB_VEL 4
+#endif
+#ifndef RP_POS_THREADS
+#define RP_POS_THREADS 128  // CTA sizes of the cooperative sweeps (with RP_MINB_*: resident warps, hence trips per level)
+#endif
+#ifndef RP_VEL_THREADS
+#define RP_VEL_THREADS 128
+#endif
+#ifdef RP_POS_MAXNREG  // tuning: an explicit register cap instead of a minimum CTA count
+#define RP_POS_BOUNDS __maxnreg__(RP_POS_MAXNREG)
+#else
+#define RP_POS_BOUNDS __launch_bounds__(RP_POS_THREADS, RP_MINB_POS)
 #endif
 
 #define RP_GJK_THREADS 64
@@ -117,6 +128,38 @@ __device__ __forceinline__ Shape dev_shape(const DevView& d, const ColliderDesc&
 		const HullTopo h = d.pool.hulls[c.hull];
 		s.center = v3(0.0, 0.0, 0.0);
 		s.nv = h.nv; s.nf = h.nf;
+		s.face_ptr = d.pool.face_ptr + h.fptr0; s.face_idx = d.pool.face_idx;
+		s.v2f_ptr = d.pool.v2f_ptr + h.v2f0; s.v2f_idx = d.pool.v2f_idx;
+		s.v2n_ptr = d.pool.v2n_ptr + h.v2n0; s.v2n_idx = d.pool.v2n_idx;
+		s.f2n_ptr = d.pool.f2n_ptr + h.f2n0; s.f2n_idx = d.pool.f2n_idx;
+	}
+	return s;
+}
+
+// The same collider as a PoseShape (rp_shape.h): nothing of its transformed geometry is read from memory -- the body's pose
+// (7 doubles, world-minor, coalesced) gives the model matrix, and vertices / face normals are evaluated from the hull's local
+// data (template arrays: the same addresses for every lane that works on the same hull, L1-resident) when they are needed.
+__device__ __forceinline__ PoseShape dev_pose_shape(const DevView& d, const ColliderDesc& c, int w) {
+	PoseShape s;
+	s.type = c.type;
+	s.radius = c.radius;
+	const DynRef r = dyn_ref(d, w, c.body);
+	const V3 x = ld3(r, DF_X);
+	s.vp = 0; s.vs = 0; s.vcs = 0;
+	s.np = d.tn + (size_t)c.tn0 * 3 * d.WS + w; s.ns = 3 * d.WS; s.ncs = d.WS;  // (read only in the RP_STORED_NORMALS build)
+	if (c.type == SHAPE_SPHERE) {
+		s.center = x;  // collider.cpp:433
+		s.nv = 0; s.nf = 0;
+		s.face_ptr = s.face_idx = s.v2f_ptr = s.v2f_idx = s.v2n_ptr = s.v2n_idx = s.f2n_ptr = s.f2n_idx = 0;
+		s.lv = s.ln = 0;
+		s.M = model_matrix(q4(0.0, 0.0, 0.0, 1.0), x);
+	} else {
+		const HullTopo h = d.pool.hulls[c.hull];
+		s.M = model_matrix(ld4(r, DF_Q), x);
+		s.center = v3(0.0, 0.0, 0.0);
+		s.nv = h.nv; s.nf = h.nf;
+		s.lv = d.pool.verts + h.vert0;
+		s.ln = d.pool.normals + h.face0;
 		s.face_ptr = d.pool.face_ptr + h.fptr0; s.face_idx = d.pool.face_idx;
 		s.v2f_ptr = d.pool.v2f_ptr + h.v2f0; s.v2f_idx = d.pool.v2f_idx;
 		s.v2n_ptr = d.pool.v2n_ptr + h.v2n0; s.v2n_idx = d.pool.v2n_idx;
@@ -518,7 +561,10 @@ __global__ void __launch_bounds__(256) k_substep_reset(DevView d) {
 		d.lvl_fill[(size_t)i * RP_LVL_STRIDE] = 0;
 		d.lvl_fill[(size_t)i * RP_LVL_STRIDE + 1] = 0;
 	}
-	if (i < d.W) d.n_contacts[i] = 0;
+	if (i < d.W) {
+		d.n_contacts[i] = 0;
+		d.n_live[i] = 0;
+	}
 }
 
 #define RP_INT_THREADS 128
@@ -612,11 +658,10 @@ __global__ void __launch_bounds__(RP_INT_THREADS) k_bounds(DevView d) {
 	collider_bounds(d, cd, M, x, d.aabb + (size_t)c * 6 * d.WS + w, d.WS);
 }
 
-// collider_update's other half (collider.cpp:409-445), after k_cull: transformed vertices and re-normalised face normals
-// of the colliders k_cull marked (geom_stamp == this substep) -- the ones GJK, EPA or clipping will read. Same pose, same
-// operations as the reference's per-pair calls (pbd.cpp:598-599), so the same bits. Thread = (collider, world, slice):
-// lane = world; gridDim.z slices share out the vertices and normals of large hulls (one slice for the small hulls of the
-// headline scenes).
+// Only in the RP_STORED_NORMALS build (a tuning variant; by default the narrowphase evaluates face normals from the pose as it
+// does vertices, see PoseShape): re-normalised face normals (collider.cpp:425-429) of the colliders k_cull marked
+// (geom_stamp == this substep), after k_cull. Thread = (collider, world, slice): lane = world; gridDim.z slices share out the
+// normals of large hulls.
 __global__ void __launch_bounds__(RP_INT_THREADS) k_transform(DevView d) {
 	const int w = blockIdx.y * RP_INT_THREADS + threadIdx.x;
 	const int c = blockIdx.x;
@@ -624,21 +669,12 @@ __global__ void __launch_bounds__(RP_INT_THREADS) k_transform(DevView d) {
 	const size_t S = d.WS;
 	if (d.geom_stamp[(size_t)c * S + w] != *d.epoch) return;
 	const ColliderDesc cd = d.cols[c];
+	if (cd.type == SHAPE_SPHERE) return;
 	const DynRef r = dyn_ref(d, w, cd.body);
-	const V3 x = ld3(r, DF_X);
-	const Pose34 M = model_matrix(ld4(r, DF_Q), x);
-	double* tv = d.tv + (size_t)cd.tv0 * 3 * S + w;
+	const Pose34 M = model_matrix(ld4(r, DF_Q), ld3(r, DF_X));
 	const int first = blockIdx.z, step = gridDim.z;
-	if (cd.type == SHAPE_SPHERE) {
-		if (first == 0) { tv[0] = x.x; tv[S] = x.y; tv[2 * S] = x.z; }
-		return;
-	}
 	const HullTopo t = d.pool.hulls[cd.hull];
 	double* tn = d.tn + (size_t)cd.tn0 * 3 * S + w;
-	for (int k = first; k < t.nv; k += step) {
-		const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
-		tv[(size_t)(3 * k) * S] = p.x; tv[(size_t)(3 * k + 1) * S] = p.y; tv[(size_t)(3 * k + 2) * S] = p.z;
-	}
 	for (int k = first; k < t.nf; k += step) {
 		const V3 n = transform_normal(M, d.pool.normals[t.face0 + k]);
 		tn[(size_t)(3 * k) * S] = n.x; tn[(size_t)(3 * k + 1) * S] = n.y; tn[(size_t)(3 * k + 2) * S] = n.z;
@@ -650,21 +686,33 @@ __global__ void __launch_bounds__(RP_INT_THREADS) k_transform(DevView d) {
 // base[e * nthreads], so the 32 lanes of a warp touch 32 consecutive doubles per access whatever (world, body) each lane
 // holds. The narrowphase scans the same vertices many times (support mapping), and 16 vertices x 3 x 32 lanes of a warp
 // are 12 kB -- more than a warp's share of L1. Returns the number of doubles used.
-__device__ __forceinline__ int stage_shape(Shape& s, double* col, int nthreads, bool with_normals) {
-	int e = 0;
-	const double* src = s.vp;
-	const size_t cs = (size_t)s.vcs;  // global layout: vertex stride = 3 * component stride, so element k sits at k * cs
-	for (int k = 0; k < s.nv * 3; ++k) col[(size_t)(e + k) * nthreads] = src[k * cs];
-	s.vp = col + (size_t)e * nthreads; s.vs = 3 * nthreads; s.vcs = nthreads;
-	e += s.nv * 3;
-	if (with_normals) {
-		src = s.np;
-		const size_t ncs = (size_t)s.ncs;
-		for (int k = 0; k < s.nf * 3; ++k) col[(size_t)(e + k) * nthreads] = src[k * ncs];
-		s.np = col + (size_t)e * nthreads; s.ns = 3 * nthreads; s.ncs = nthreads;
-		e += s.nf * 3;
+__device__ __forceinline__ int stage_shape(PoseShape& s, double* col, int nthreads) {
+	// the vertices are evaluated from the pose (collider_update's expression, collider.cpp:414-422), not loaded
+	for (int k = 0; k < s.nv; ++k) {
+		const V3 p = vert(s, k);
+		col[(size_t)(3 * k) * nthreads] = p.x; col[(size_t)(3 * k + 1) * nthreads] = p.y; col[(size_t)(3 * k + 2) * nthreads] = p.z;
 	}
-	return e;
+	s.vp = col; s.vs = 3 * nthreads; s.vcs = nthreads;
+	return s.nv * 3;
+}
+
+// final GJK tetrahedron of hit `slot`, stored as 12 component planes of `cand_cap` doubles: the lanes of a warp hold
+// consecutive hits, so every access is one coalesced request (as 4 x V3 records per hit the twelve loads of k_epa each touched
+// 32 different sectors: 9 % of its stall samples, ncu round 2)
+__device__ __forceinline__ void st_simplex(const DevView& d, unsigned int slot, const Simplex& s) {
+	double* o = d.simplex + slot;
+	const size_t S = d.cand_cap;
+	o[0] = s.a.x; o[S] = s.a.y; o[2 * S] = s.a.z; o[3 * S] = s.b.x; o[4 * S] = s.b.y; o[5 * S] = s.b.z;
+	o[6 * S] = s.c.x; o[7 * S] = s.c.y; o[8 * S] = s.c.z; o[9 * S] = s.d.x; o[10 * S] = s.d.y; o[11 * S] = s.d.z;
+}
+__device__ __forceinline__ Simplex ld_simplex(const DevView& d, unsigned int slot) {
+	const double* o = d.simplex + slot;
+	const size_t S = d.cand_cap;
+	Simplex s;
+	s.a = v3(o[0], o[S], o[2 * S]); s.b = v3(o[3 * S], o[4 * S], o[5 * S]);
+	s.c = v3(o[6 * S], o[7 * S], o[8 * S]); s.d = v3(o[9 * S], o[10 * S], o[11 * S]);
+	s.num = 4;
+	return s;
 }
 
 // warp-aggregated append: every lane of the warp calls this; lanes with want == true get consecutive slots
@@ -764,9 +812,11 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 			const unsigned int slot = big ? d.cand_cap - 1u - back : front;
 			if (keep[u]) {
 				d.cands[slot] = make_uint4((unsigned int)w, (unsigned int)p, (unsigned int)pr[u].ca, (unsigned int)pr[u].cb);
-				// k_transform writes the geometry of these two colliders (every writer of a stamp writes the same value)
+#if defined(RP_STORED_NORMALS)
+				// k_transform writes the face normals of these two colliders (every writer of a stamp writes the same value)
 				d.geom_stamp[(size_t)pr[u].ca * S + w] = epoch;
 				d.geom_stamp[(size_t)pr[u].cb * S + w] = epoch;
+#endif
 			}
 		}
 	}
@@ -804,6 +854,7 @@ struct WarpQueue {
 // (warp-aggregated, order-preserving within the warp) to the hit list together with their final simplex.
 __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) {
 	const unsigned int nc = *d.cand_count;
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&d.counters[CNT_CANDS], (unsigned long long)nc + *d.big_count);
 	__shared__ double s_stage[RP_GJK_STAGE * RP_GJK_THREADS];
 	for (unsigned int c0 = blockIdx.x * blockDim.x; c0 < nc; c0 += gridDim.x * blockDim.x) {
 		const unsigned int ci = c0 + threadIdx.x;
@@ -814,8 +865,8 @@ __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) 
 		if (ci < nc) {
 			cd = d.cands[ci];  // (world, pair, collider a, collider b): everything the narrowphase needs to find its inputs
 			const int w = (int)cd.x;
-			Shape A = dev_shape(d, d.cols[cd.z], w);
-			Shape B = dev_shape(d, d.cols[cd.w], w);
+			PoseShape A = dev_pose_shape(d, d.cols[cd.z], w);
+			PoseShape B = dev_pose_shape(d, d.cols[cd.w], w);
 			int st = 0;
 			if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
 				V3 n;
@@ -824,8 +875,8 @@ __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) 
 			} else {
 				if ((A.nv + B.nv) * 3 <= RP_GJK_STAGE) {
 					double* col = s_stage + threadIdx.x;
-					const int used = stage_shape(A, col, RP_GJK_THREADS, false);
-					stage_shape(B, col + (size_t)used * RP_GJK_THREADS, RP_GJK_THREADS, false);
+					const int used = stage_shape(A, col, RP_GJK_THREADS);
+					stage_shape(B, col + (size_t)used * RP_GJK_THREADS, RP_GJK_THREADS);
 					hit = gjk(StagedShape<RP_GJK_THREADS>(A), StagedShape<RP_GJK_THREADS>(B), &s, &st, 0);
 				} else {
 					hit = gjk(A, B, &s, &st, 0);
@@ -836,8 +887,7 @@ __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) 
 		const unsigned int slot = warp_append(d.hit_count, hit);
 		if (hit) {
 			d.hits[slot] = cd;
-			V3* o = d.simplex + (size_t)slot * 4;
-			o[0] = s.a; o[1] = s.b; o[2] = s.c; o[3] = s.d;
+			st_simplex(d, slot, s);
 		}
 	}
 }
@@ -850,16 +900,20 @@ __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) 
 // RP_WARP_HULL_MAX vertices are staged in shared memory first (component planes, so the lanes' reads are consecutive).
 #define RP_GJK_WARP_THREADS 128
 #define RP_WARP_HULL_MAX 128
-struct WarpShape : Shape {
+struct WarpShape : PoseShape {
 	__device__ WarpShape() {}
-	__device__ explicit WarpShape(const Shape& s) : Shape(s) {}
+	__device__ explicit WarpShape(const PoseShape& s) : PoseShape(s) {}
 };
+// staged in the warp's block (vp set by warp_stage) or, for hulls too large for it, evaluated from the pose in place
+__device__ __forceinline__ V3 vert(const WarpShape& s, int i) {
+	return s.vp ? vert(static_cast<const Shape&>(s), i) : vert(static_cast<const PoseShape&>(s), i);
+}
 __device__ __forceinline__ int support_index(const WarpShape& s, V3 d) {
 	const int lane = threadIdx.x & 31;
 	int best = 0x7fffffff;
 	double best_dot = -1.7976931348623157e308;
 	for (int i = lane; i < s.nv; i += 32) {
-		const double t = dot(vert(static_cast<const Shape&>(s), i), d);
+		const double t = dot(vert(s, i), d);
 		if (t > best_dot) {
 			best = i;
 			best_dot = t;
@@ -876,9 +930,9 @@ __device__ __forceinline__ int support_index(const WarpShape& s, V3 d) {
 	}
 	return best == 0x7fffffff ? 0 : best;
 }
-// copies a hull's transformed vertices into the warp's block of shared memory as component planes
-__device__ __forceinline__ void warp_stage(Shape& s, double* block) {
-	if (s.type != SHAPE_HULL || s.nv > RP_WARP_HULL_MAX) return;  // spheres have no vertices; larger hulls are scanned in place
+// evaluates a hull's transformed vertices into the warp's block of shared memory as component planes
+__device__ __forceinline__ void warp_stage(PoseShape& s, double* block) {
+	if (s.type != SHAPE_HULL || s.nv > RP_WARP_HULL_MAX) return;  // spheres have no vertices; larger hulls are evaluated in place
 	const int lane = threadIdx.x & 31;
 	for (int k = lane; k < s.nv; k += 32) {
 		const V3 p = vert(s, k);
@@ -894,8 +948,8 @@ __global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_gjk_warp(DevView d) {
 	for (unsigned int k = blockIdx.x * (RP_GJK_WARP_THREADS / 32) + wib; k < nb; k += warps) {
 		const uint4 cd = d.cands[d.cand_cap - 1u - k];
 		const int w = (int)cd.x;
-		Shape A = dev_shape(d, d.cols[cd.z], w);
-		Shape B = dev_shape(d, d.cols[cd.w], w);
+		PoseShape A = dev_pose_shape(d, d.cols[cd.z], w);
+		PoseShape B = dev_pose_shape(d, d.cols[cd.w], w);
 		__syncwarp();  // the previous pair's scans are done with the block
 		warp_stage(A, s_hull[wib][0]);
 		warp_stage(B, s_hull[wib][1]);
@@ -908,45 +962,106 @@ __global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_gjk_warp(DevView d) {
 			if (hit) {
 				const unsigned int slot = atomicAdd(d.hit_count, 1u);
 				d.hits[slot] = cd;
-				V3* o = d.simplex + (size_t)slot * 4;
-				o[0] = s.a; o[1] = s.b; o[2] = s.c; o[3] = s.d;
+				st_simplex(d, slot, s);
 			}
 		}
 	}
 }
 
-// EPA (epa.cpp:118) for every hit, one thread per hit. The polytope lives in the thread's local memory; the two hulls'
-// vertices are staged in shared memory as in k_gjk (EPA only ever asks for support points). Kept apart from
-// k_manifold: lanes leave EPA after different numbers of iterations, and the kernel boundary is what brings a warp
-// back together before the clipping code.
+// The EPA polytope of one thread in a thread-interleaved block of shared memory (element e of thread t at base[e * NT + t]:
+// the 32 lanes of a warp touch 32 consecutive words whatever each lane indexes). Store concept of rp_narrow.h, small
+// capacities, SOFT: a pair whose polytope outgrows it is rerun on the full-capacity store in local memory (epa_full).
+// Round 1 kept the full store (11.8 kB) in every thread's local memory; at 12 warps per SM it missed L1 on every step
+// (ncu: L1 hit 53 %, 6 long-scoreboard stall cycles per issued instruction, FP64 pipe 9.7 %).
+#define RP_EPA_POLY_DOUBLES (3 * RP_EPA_SMALL_VERTS + 4 * RP_EPA_SMALL_FACES)  // vertices, face normals, face distances
+#define RP_EPA_POLY_INTS (RP_EPA_SMALL_FACES + RP_EPA_SMALL_EDGES)             // packed face triples, packed edges
+template <int NT>
+struct EpaShared {
+	enum { MAXV = RP_EPA_SMALL_VERTS, MAXF = RP_EPA_SMALL_FACES, MAXE = RP_EPA_SMALL_EDGES, SOFT = 1 };
+	double* col;  // this thread's column of doubles: vertices [0, 3V), normals [3V, 3V + 3F), distances [3V + 3F, 3V + 4F)
+	int* icol;    // this thread's column of ints: faces [0, F), edges [F, F + E)
+	int nverts, nfaces, nedges;
+	V3 min_normal;
+	double min_dist;
+	__device__ __forceinline__ V3 vert(int i) const { const double* p = col + (3 * i) * NT; return v3(p[0], p[NT], p[2 * NT]); }
+	__device__ __forceinline__ void set_vert(int i, V3 v) { double* p = col + (3 * i) * NT; p[0] = v.x; p[NT] = v.y; p[2 * NT] = v.z; }
+	__device__ __forceinline__ V3 normal(int i) const { const double* p = col + (3 * MAXV + 3 * i) * NT; return v3(p[0], p[NT], p[2 * NT]); }
+	__device__ __forceinline__ double dist(int i) const { return col[(3 * MAXV + 3 * MAXF + i) * NT]; }
+	__device__ __forceinline__ void set_plane(int i, V3 n, double d) {
+		double* p = col + (3 * MAXV + 3 * i) * NT;
+		p[0] = n.x; p[NT] = n.y; p[2 * NT] = n.z;
+		col[(3 * MAXV + 3 * MAXF + i) * NT] = d;
+	}
+	__device__ __forceinline__ void face(int i, int* x, int* y, int* z) const {
+		const int f = icol[i * NT];
+		*x = f & 255; *y = (f >> 8) & 255; *z = f >> 16;
+	}
+	__device__ __forceinline__ void set_face(int i, int x, int y, int z) { icol[i * NT] = x | (y << 8) | (z << 16); }
+	__device__ __forceinline__ void move_face(int dst, int src) {
+		icol[dst * NT] = icol[src * NT];
+		set_plane(dst, normal(src), dist(src));
+	}
+	__device__ __forceinline__ void edge(int i, int* x, int* y) const {
+		const int e = icol[(MAXF + i) * NT];
+		*x = e & 255; *y = e >> 8;
+	}
+	__device__ __forceinline__ void set_edge(int i, int x, int y) { icol[(MAXF + i) * NT] = x | (y << 8); }
+};
+
+// second tier of k_epa: the full-capacity polytope in local memory, for the rare pair that outgrows the shared store.
+// Out of line so that its 11.8 kB frame and its registers stay out of the common path.
+__device__ __noinline__ int epa_full(const DevView& d, uint4 cd, const Simplex& s, V3* normal, double* depth, int* status) {
+	EpaScratch e;
+	const PoseShape A = dev_pose_shape(d, d.cols[cd.z], (int)cd.x);
+	const PoseShape B = dev_pose_shape(d, d.cols[cd.w], (int)cd.x);
+	return epa_run(A, B, s, e, normal, depth, status, 0);
+}
+
+// EPA (epa.cpp:118) for every hit, one thread per hit, the polytope in shared memory (EpaShared). RP_EPA_STAGE_HULLS = 1
+// also stages the two hulls' vertices in shared memory as k_gjk does (EPA only ever asks for support points); with the
+// polytope there as well that halves the resident warps, and EPA scans each hull once or twice where GJK scans it four
+// times, so by default the vertices are read in place (world-minor arrays: coalesced across the lanes of a warp). Kept
+// apart from k_manifold: lanes leave EPA after different numbers of iterations, and the kernel boundary is what brings a
+// warp back together before the clipping code.
+#ifndef RP_EPA_STAGE_HULLS
+#define RP_EPA_STAGE_HULLS 0
+#endif
+#define RP_EPA_SMEM_BYTES ((RP_EPA_POLY_DOUBLES * 8 + RP_EPA_POLY_INTS * 4 + (RP_EPA_STAGE_HULLS ? RP_GJK_STAGE * 8 : 0)) * RP_EPA_THREADS)
 __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) {
 	const unsigned int nh = *d.hit_count;
-	__shared__ double s_stage[RP_GJK_STAGE * RP_EPA_THREADS];
-	EpaScratch e;
+	extern __shared__ __align__(16) unsigned char s_epa_raw[];
+	double* s_poly = reinterpret_cast<double*>(s_epa_raw);
+	double* s_stage = s_poly + RP_EPA_POLY_DOUBLES * RP_EPA_THREADS;
+	int* s_idx = reinterpret_cast<int*>(s_stage + (RP_EPA_STAGE_HULLS ? RP_GJK_STAGE * RP_EPA_THREADS : 0));
+	EpaShared<RP_EPA_THREADS> e;
+	e.col = s_poly + threadIdx.x;
+	e.icol = s_idx + threadIdx.x;
 	for (unsigned int hi = blockIdx.x * blockDim.x + threadIdx.x; hi < nh; hi += gridDim.x * blockDim.x) {
 		const uint4 cd = d.hits[hi];
 		const int w = (int)cd.x;
 		if (d.split_big && (d.cols[cd.z].nv + d.cols[cd.w].nv) * 3 > RP_GJK_STAGE) continue;  // k_epa_warp's
-		Shape A = dev_shape(d, d.cols[cd.z], w);
-		Shape B = dev_shape(d, d.cols[cd.w], w);
+		PoseShape A = dev_pose_shape(d, d.cols[cd.z], w);
+		PoseShape B = dev_pose_shape(d, d.cols[cd.w], w);
 		EpaOut out;
 		out.ok = 0; out.pad = 0; out.depth = 0.0; out.normal = v3(0.0, 0.0, 0.0);
 		int st = 0;
 		if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
 			out.ok = sphere_sphere(A, B, &out.normal, &out.depth) ? 1 : 0;
 		} else {
-			const V3* sp = d.simplex + (size_t)hi * 4;
-			Simplex s;
-			s.a = sp[0]; s.b = sp[1]; s.c = sp[2]; s.d = sp[3];
-			s.num = 4;
+			const Simplex s = ld_simplex(d, hi);
+			int r;
+#if RP_EPA_STAGE_HULLS
 			if ((A.nv + B.nv) * 3 <= RP_GJK_STAGE) {
+				PoseShape SA = A, SB = B;
 				double* col = s_stage + threadIdx.x;
-				const int used = stage_shape(A, col, RP_EPA_THREADS, false);
-				stage_shape(B, col + (size_t)used * RP_EPA_THREADS, RP_EPA_THREADS, false);
-				out.ok = epa(StagedShape<RP_EPA_THREADS>(A), StagedShape<RP_EPA_THREADS>(B), s, e, &out.normal, &out.depth, &st, 0) ? 1 : 0;
-			} else {
-				out.ok = epa(A, B, s, e, &out.normal, &out.depth, &st, 0) ? 1 : 0;
-			}
+				const int used = stage_shape(SA, col, RP_EPA_THREADS);
+				stage_shape(SB, col + (size_t)used * RP_EPA_THREADS, RP_EPA_THREADS);
+				r = epa_run(StagedShape<RP_EPA_THREADS>(SA), StagedShape<RP_EPA_THREADS>(SB), s, e, &out.normal, &out.depth, &st, 0);
+			} else
+#endif
+			r = epa_run(A, B, s, e, &out.normal, &out.depth, &st, 0);
+			if (r == EPA_OVERFLOW) r = epa_full(d, cd, s, &out.normal, &out.depth, &st);
+			out.ok = r == EPA_DONE ? 1 : 0;
 		}
 		d.epa_out[hi] = out;
 		if (st) atomicOr(&d.status[w], st);
@@ -967,16 +1082,13 @@ __global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_epa_warp(DevView d) {
 		const uint4 cd = d.hits[hi];
 		if (!((d.cols[cd.z].nv + d.cols[cd.w].nv) * 3 > RP_GJK_STAGE)) continue;  // k_epa's
 		const int w = (int)cd.x;
-		Shape A = dev_shape(d, d.cols[cd.z], w);
-		Shape B = dev_shape(d, d.cols[cd.w], w);
+		PoseShape A = dev_pose_shape(d, d.cols[cd.z], w);
+		PoseShape B = dev_pose_shape(d, d.cols[cd.w], w);
 		__syncwarp();
 		warp_stage(A, s_hull[wib][0]);
 		warp_stage(B, s_hull[wib][1]);
 		__syncwarp();
-		const V3* sp = d.simplex + (size_t)hi * 4;
-		Simplex s;
-		s.a = sp[0]; s.b = sp[1]; s.c = sp[2]; s.d = sp[3];
-		s.num = 4;
+		const Simplex s = ld_simplex(d, hi);
 		EpaOut out;
 		out.ok = 0; out.pad = 0; out.depth = 0.0; out.normal = v3(0.0, 0.0, 0.0);
 		int st = 0;
@@ -994,30 +1106,84 @@ __global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_epa_warp(DevView d) {
 	}
 }
 
-struct StageSink {
-	V3* stage;
-	int n, cap;
+// The two Sutherland-Hodgman polygon buffers of one thread in a thread-interleaved block of shared memory (store concept of
+// rp_narrow.h): RP_CLIP_SMALL_POINTS points each -- a box face clipped against the four side planes of another box face has
+// at most 8 vertices. A polygon that outgrows it (a cylinder's 64-gon cap) is rerun on the full store in local memory
+// (manifold_full). Round 1 kept 2 x 160 points plus a 320-point staging array (15 kB) in every thread's local memory.
+template <int NT>
+struct ClipShared {
+	enum { CAP = RP_CLIP_SMALL_POINTS, SOFT = 1 };
+	double* col;  // point i of buffer b: components at col[((b * CAP + i) * 3 + c) * NT]
+	__device__ __forceinline__ V3 get(int b, int i) const { const double* p = col + ((b * CAP + i) * 3) * NT; return v3(p[0], p[NT], p[2 * NT]); }
+	__device__ __forceinline__ void set(int b, int i, V3 v) { double* p = col + ((b * CAP + i) * 3) * NT; p[0] = v.x; p[NT] = v.y; p[2 * NT] = v.z; }
+};
+#define RP_MANIFOLD_SMEM_BYTES (2 * RP_CLIP_SMALL_POINTS * 3 * 8 * RP_MANIFOLD_THREADS)
+
+struct CountSink {
+	int n;
+	__device__ __forceinline__ void operator()(V3, V3) { ++n; }
+};
+// writes the contact records (pbd.cpp:408-424) of one manifold straight into the world's contact buffer
+struct ContactSink {
+	const DevView* d;
+	Body b1, b2;   // poses only
+	int w, off, n, cap;
 	__device__ __forceinline__ void operator()(V3 p1, V3 p2) {
 		if (n < cap) {
-			stage[2 * n] = p1;
-			stage[2 * n + 1] = p2;
+			st_contact(contact_ptr(*d, w, off + n), d->WS, make_contact(b1, b2, p1, p2));
+			if (w == d->dbg_world) {
+				d->dbg_points[2 * (off + n)] = p1;
+				d->dbg_points[2 * (off + n) + 1] = p2;
+			}
 		}
 		++n;
 	}
 };
-
-struct ManifoldScratch {
-	ClipScratch clip;
-	V3 stage[2 * RP_CLIP_MAX_POINTS];
-};
+// Second half of a manifold, shared by both tiers: count the contacts of the clipped polygon (manifold_emit with a counting
+// sink), take a contiguous run of the world's contact buffer (allocation order between pairs is irrelevant: the solver walks
+// pairs, not the buffer), emit again into it. Returns the number of contacts stored; *off_out = first slot.
+template <class C>
+__device__ __forceinline__ int emit_contacts(const DevView& d, const C& cs, const ClipResult& r, V3 normal, int w, const PairRec& pr, int* off_out,
+	int* status) {
+	CountSink cnt;
+	cnt.n = 0;
+	manifold_emit(cs, r, normal, cnt);
+	if (cnt.n == 0) return 0;
+	ContactSink sink;
+	sink.d = &d; sink.w = w; sink.n = 0;
+	sink.off = atomicAdd(&d.n_contacts[w], cnt.n);
+	sink.cap = cnt.n;
+	if (sink.off + cnt.n > d.max_contacts) {
+		*status |= ST_CONTACT_CAPACITY;
+		sink.cap = d.max_contacts - sink.off;
+		if (sink.cap < 0) sink.cap = 0;
+	}
+	const DynRef ra = dyn_ref(d, w, pr.a);
+	const DynRef rb = dyn_ref(d, w, pr.b);
+	sink.b1.x = ld3(ra, DF_X); sink.b1.q = ld4(ra, DF_Q);
+	sink.b2.x = ld3(rb, DF_X); sink.b2.q = ld4(rb, DF_Q);
+	manifold_emit(cs, r, normal, sink);
+	*off_out = sink.off;
+	return sink.cap;
+}
+// second tier of k_manifold: full-capacity polygon buffers in local memory. Out of line (7.7 kB frame).
+__device__ __noinline__ int manifold_full(const DevView& d, uint4 cd, V3 normal, PairRec pr, int sup1, int sup2, int* off_out, int* status) {
+	ClipScratch cs;
+	ClipResult r;
+	const int w = (int)cd.x;
+	const PoseShape A = dev_pose_shape(d, d.cols[cd.z], w);
+	const PoseShape B = dev_pose_shape(d, d.cols[cd.w], w);
+	manifold_clip(A, B, normal, cs, status, &r, sup1, sup2);
+	return emit_contacts(d, cs, r, normal, w, pr, off_out, status);
+}
 
 // One thread per colliding collider pair whose EPA converged: manifold (clipping.cpp:343), contact -> constraint
-// (pbd.cpp:408-424). The pair's contacts get a contiguous run in the world's contact buffer (allocation order between
-// pairs is irrelevant: the solver walks pairs, not the buffer), and the pair is appended to the work list of its
-// dependency level.
+// (pbd.cpp:408-424), and the pair is appended to the work list of its dependency level.
 __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manifold(DevView d) {
 	const unsigned int nh = *d.hit_count;
-	ManifoldScratch sc;
+	extern __shared__ __align__(16) unsigned char s_clip_raw[];
+	ClipShared<RP_MANIFOLD_THREADS> cs;
+	cs.col = reinterpret_cast<double*>(s_clip_raw) + threadIdx.x;
 	int made = 0;
 	const int lane = threadIdx.x & 31;
 	for (unsigned int h0 = blockIdx.x * blockDim.x; h0 < nh; h0 += gridDim.x * blockDim.x) {
@@ -1033,50 +1199,51 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 			const size_t pg = pidx(d, pair, w);
 			int st = 0;
 			if (eo.ok) {
-				Shape A = dev_shape(d, d.cols[cd.z], w);
-				Shape B = dev_shape(d, d.cols[cd.w], w);
-				StageSink sink;
-				sink.stage = sc.stage;
-				sink.n = 0;
-				sink.cap = RP_CLIP_MAX_POINTS;
-				int sup1 = -1, sup2 = -1;
-				if (d.split_big && (d.cols[cd.z].nv + d.cols[cd.w].nv) * 3 > RP_GJK_STAGE) {
-					const int2 sup = d.big_sup[hi];
-					sup1 = sup.x; sup2 = sup.y;
-				}
-				manifold(A, B, eo.normal, eo.depth, sc.clip, &st, sink, sup1, sup2);
-				n = sink.n;
-				if (n > sink.cap) {
-					st |= ST_CLIP_CAPACITY;
-					n = sink.cap;
-				}
-			}
-			if (n > 0) {
-				int off = atomicAdd(&d.n_contacts[w], n);
-				if (off + n > d.max_contacts) {
-					st |= ST_CONTACT_CAPACITY;
-					n = d.max_contacts - off;
-					if (n < 0) n = 0;
-				}
 				const PairRec pr = d.pairs[pg];
-				const DynRef ra = dyn_ref(d, w, pr.a);
-				const DynRef rb = dyn_ref(d, w, pr.b);
-				Body b1, b2;
-				b1.x = ld3(ra, DF_X); b1.q = ld4(ra, DF_Q);
-				b2.x = ld3(rb, DF_X); b2.q = ld4(rb, DF_Q);
-				for (int k = 0; k < n; ++k) {
-					st_contact(contact_ptr(d, w, off + k), d.WS, make_contact(b1, b2, sc.stage[2 * k], sc.stage[2 * k + 1]));
-					if (w == d.dbg_world) {
-						d.dbg_points[2 * (off + k)] = sc.stage[2 * k];
-						d.dbg_points[2 * (off + k) + 1] = sc.stage[2 * k + 1];
+				const int ta = d.cols[cd.z].type, tb = d.cols[cd.w].type;
+				int off = 0;
+				if (ta == SHAPE_SPHERE || tb == SHAPE_SPHERE) {
+					const PoseShape A = dev_pose_shape(d, d.cols[cd.z], w);
+					const PoseShape B = dev_pose_shape(d, d.cols[cd.w], w);
+					// clipping_get_contact_manifold's sphere cases (clipping.cpp:348-364): one contact
+					ClipResult r;
+					r.kind = 1; r.n = 0; r.cur = 0; r.ref1 = false;
+					r.rp_normal = r.rp_point = v3(0.0, 0.0, 0.0);
+					if (A.type == SHAPE_SPHERE) {
+						r.l1 = support(A, eo.normal);
+						r.l2 = sub(r.l1, scale(eo.depth, eo.normal));
+					} else {
+						r.l2 = support(B, zero_minus(eo.normal));
+						r.l1 = add(r.l2, scale(eo.depth, eo.normal));
+					}
+					n = emit_contacts(d, cs, r, eo.normal, w, pr, &off, &st);
+				} else {
+					int sup1 = -1, sup2 = -1;
+					if (d.split_big && (d.cols[cd.z].nv + d.cols[cd.w].nv) * 3 > RP_GJK_STAGE) {
+						const int2 sup = d.big_sup[hi];
+						sup1 = sup.x; sup2 = sup.y;
+					}
+					ClipResult r;
+					int ov;
+					{
+						const PoseShape A = dev_pose_shape(d, d.cols[cd.z], w);
+						const PoseShape B = dev_pose_shape(d, d.cols[cd.w], w);
+						ov = manifold_clip(A, B, eo.normal, cs, &st, &r, sup1, sup2);
+					}
+					if (ov == CLIP_OVERFLOW) {
+						n = manifold_full(d, cd, eo.normal, pr, sup1, sup2, &off, &st);
+					} else {
+						n = emit_contacts(d, cs, r, eo.normal, w, pr, &off, &st);
 					}
 				}
-				d.pair_normal[pg] = eo.normal;
-				d.pair_coff[pg] = off;
-				d.pair_ccnt[pg] = n;
-				made += n;
-				if (n > 0) lvl = d.pair_level[pg];
-				item.w = w; item.a = pr.a; item.b = pr.b; item.coff = off; item.cnt = n; item.normal = eo.normal;
+				if (n > 0) {
+					d.pair_normal[pg] = eo.normal;
+					d.pair_coff[pg] = off;
+					d.pair_ccnt[pg] = n;
+					made += n;
+					lvl = d.pair_level[pg];
+					item.w = w; item.a = pr.a; item.b = pr.b; item.coff = off; item.cnt = n; item.normal = eo.normal;
+				}
 			}
 			if (st) atomicOr(&d.status[w], st);
 		}
@@ -1087,7 +1254,14 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 		// and no CTA-wide barrier (four __syncthreads per trip made every warp wait for the CTA's slowest clipping case).
 		// A level's list can be filled from both ends -- small manifolds (<= RP_SMALL_MANIFOLD contacts) from the front,
 		// large ones from the back -- which groups manifolds of similar length (order within a level is free).
-		{
+		// World-block sweeps (k_solve_block) only need to know which of a world's units are live: (pair, level) appended to
+		// the world's own list; the block's CTA sorts them by level itself.
+		if (d.block_mode) {
+			if (lvl > 0) {
+				const int slot = atomicAdd(&d.n_live[w], 1);
+				d.live[(size_t)slot * d.WS + w] = make_uint2((unsigned int)pair, (unsigned int)lvl);
+			}
+		} else {
 			const int big = n > RP_SMALL_MANIFOLD ? 1 : 0;
 			const int key = lvl > 0 ? 2 * lvl + big : -1;
 			const unsigned int peers = __match_any_sync(0xffffffffu, key);
@@ -1166,6 +1340,11 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 	V3 normal = v3(0.0, 0.0, 0.0);
 	Body b1, b2;
 	b1.fixed = b2.fixed = 1;
+#ifdef RP_POS_PREFETCH
+	Contact next_ct;
+	next_ct.r1_lc = next_ct.r2_lc = v3(0.0, 0.0, 0.0);
+	next_ct.lambda_n = next_ct.lambda_t = 0.0;
+#endif
 	for (;;) {
 		const unsigned int got = q.take(!have);
 		if (got != 0xffffffffu) {
@@ -1183,6 +1362,9 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 			b2.x = ld3(r2, DF_X); b2.q = ld4(r2, DF_Q);
 			c = 0;
 			have = cnt > 0;
+#ifdef RP_POS_PREFETCH
+			if (have) next_ct = ld_contact(cs, d.WS);
+#endif
 		}
 		if (!__any_sync(0xffffffffu, have)) {
 			if (q.empty()) break;
@@ -1190,7 +1372,12 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 		}
 		if (have) {
 			double* cp = cs + (size_t)c * 8 * d.WS;
+#ifdef RP_POS_PREFETCH
+			Contact ct = next_ct;
+			if (c + 1 < cnt) next_ct = ld_contact(cp + (size_t)8 * d.WS, d.WS);  // in flight while this contact is solved
+#else
 			Contact ct = ld_contact(cp, d.WS);
+#endif
 			solve_contact(ct, normal, b1, b2, h, &st, PrevFromDyn{r1, r2});
 			cp[6 * (size_t)d.WS] = ct.lambda_n;
 			cp[7 * (size_t)d.WS] = ct.lambda_t;
@@ -1260,7 +1447,7 @@ __device__ __forceinline__ int list_live_levels(const DevView& d, LiveLevels& s,
 }
 
 template <bool JOINTS>
-__global__ void __launch_bounds__(128, RP_MINB_POS) k_solve_pos(DevView d, double h, int iters, int collisions, int live_lists) {
+__global__ void RP_POS_BOUNDS k_solve_pos(DevView d, double h, int iters, int collisions, int live_lists) {
 	cg::grid_group grid = cg::this_grid();
 	extern __shared__ __align__(16) unsigned char s_live_raw[];
 	LiveLevels& s_live = *reinterpret_cast<LiveLevels*>(s_live_raw);
@@ -1383,7 +1570,7 @@ __device__ __forceinline__ void vel_level(const DevView& d, double h, int level)
 	}
 }
 
-__global__ void __launch_bounds__(128, RP_MINB_VEL) k_solve_vel(DevView d, double h, int live_lists) {
+__global__ void __launch_bounds__(RP_VEL_THREADS, RP_MINB_VEL) k_solve_vel(DevView d, double h, int live_lists) {
 	cg::grid_group grid = cg::this_grid();
 	extern __shared__ __align__(16) unsigned char s_live_raw[];
 	LiveLevels& s_live = *reinterpret_cast<LiveLevels*>(s_live_raw);
@@ -1397,6 +1584,201 @@ __global__ void __launch_bounds__(128, RP_MINB_VEL) k_solve_vel(DevView d, doubl
 		if (dirty) grid.sync();
 		vel_level(d, h, level);
 		dirty = true;
+	}
+}
+
+// --------------------------------------------------------------------------------------------------- world-block sweeps
+// Dependencies between constraints never cross worlds, so a barrier between two levels only has to hold back the threads
+// that work on the SAME worlds. k_solve_block gives every CTA a block of `wpb` consecutive worlds and walks that block's
+// levels -- every positional iteration, then the velocity pass -- with __syncthreads() between them: no grid-wide barrier
+// (ncu, round 2 start: 45 % of k_solve_pos's and 30 % of k_solve_vel's stall samples sat in grid.sync()), no cooperative
+// launch holding whole SMs while most of the grid waits, one launch per substep for both sweeps, and blocks that finish
+// early make room for the next ones. The CTA first sorts its worlds' live units (k_manifold's per-world lists) by level
+// into its region of blk_items: histogram and cursors in shared memory; lanes of a warp that hold the same level take
+// consecutive slots, so the `wpb` worlds of one pair stay adjacent and their loads of the world-minor arrays share sectors.
+// Results are bit-identical to the level-major sweeps: the same units run in the same per-world level order.
+#define RP_SB_THREADS 128
+#ifndef RP_MINB_SB
+#define RP_MINB_SB 3
+#endif
+#define RP_SB_MAX_WPB 64
+
+__device__ __forceinline__ void pos_unit(const DevView& d, double h, int w, int pair, int* st) {
+	const size_t pg = pidx(d, pair, w);
+	const int2 ab = *reinterpret_cast<const int2*>(&d.pairs[pg]);
+	const int cnt = d.pair_ccnt[pg];
+	const V3 normal = d.pair_normal[pg];
+	double* cs = contact_ptr(d, w, d.pair_coff[pg]);
+	Body b1, b2;
+	load_static(b1, d, ab.x);
+	load_static(b2, d, ab.y);
+	const DynRef r1 = dyn_ref(d, w, ab.x);
+	const DynRef r2 = dyn_ref(d, w, ab.y);
+	b1.x = ld3(r1, DF_X); b1.q = ld4(r1, DF_Q);
+	b2.x = ld3(r2, DF_X); b2.q = ld4(r2, DF_Q);
+	for (int c = 0; c < cnt; ++c) {
+		double* cp = cs + (size_t)c * 8 * d.WS;
+		Contact ct = ld_contact(cp, d.WS);
+		solve_contact(ct, normal, b1, b2, h, st, PrevFromDyn{r1, r2});
+		cp[6 * (size_t)d.WS] = ct.lambda_n;
+		cp[7 * (size_t)d.WS] = ct.lambda_t;
+	}
+	if (!b1.fixed) { st3(r1, DF_X, b1.x); st4(r1, DF_Q, b1.q); }
+	if (!b2.fixed) { st3(r2, DF_X, b2.x); st4(r2, DF_Q, b2.q); }
+}
+
+__device__ __forceinline__ void vel_unit(const DevView& d, double h, int w, int pair, int epoch) {
+	const size_t pg = pidx(d, pair, w);
+	const int2 ab = *reinterpret_cast<const int2*>(&d.pairs[pg]);
+	const int cnt = d.pair_ccnt[pg];
+	const V3 normal = d.pair_normal[pg];
+	const double* cs = contact_ptr(d, w, d.pair_coff[pg]);
+	Body b1, b2;
+	load_static(b1, d, ab.x);
+	load_static(b2, d, ab.y);
+	const DynRef r1 = dyn_ref(d, w, ab.x);
+	const DynRef r2 = dyn_ref(d, w, ab.y);
+	const bool need_prev = b1.rest * b2.rest != 0.0;  // restitution 0 on either side: the previous velocities are never read
+	load_for_velocity(b1, r1, d.active[bidx(d, ab.x, w)], d.vstamp + bidx(d, ab.x, w), epoch, h, need_prev);
+	load_for_velocity(b2, r2, d.active[bidx(d, ab.y, w)], d.vstamp + bidx(d, ab.y, w), epoch, h, need_prev);
+	const AngPre tens = vel_tensors(b1, b2);
+	for (int c = 0; c < cnt; ++c) {
+		const Contact ct = ld_contact(cs + (size_t)c * 8 * d.WS, d.WS);
+		solve_contact_velocity(ct, normal, b1, b2, h, tens);
+	}
+	if (!b1.fixed) { st3(r1, DF_V, b1.v); st3(r1, DF_W, b1.w); }
+	if (!b2.fixed) { st3(r2, DF_V, b2.v); st3(r2, DF_W, b2.w); }
+}
+
+template <bool JOINTS>
+__global__ void __launch_bounds__(RP_SB_THREADS, RP_MINB_SB) k_solve_block(DevView d, double h, int iters, int collisions, int wpb) {
+	extern __shared__ __align__(16) int s_lv[];  // [max_levels + 2]: counts -> starts -> ends of the block's levels
+	__shared__ int s_nl[RP_SB_MAX_WPB];
+	__shared__ int s_max, s_nlmax;
+	const int tid = threadIdx.x, lane = tid & 31;
+	const int w0 = blockIdx.x * wpb;
+	const int nw = d.W - w0 < wpb ? d.W - w0 : wpb;
+	unsigned int* items = d.blk_items + (size_t)w0 * d.max_pairs;
+	int lmax = 0;
+	if (collisions) {
+		for (int l = tid; l < d.max_levels + 2; l += RP_SB_THREADS) s_lv[l] = 0;
+		if (tid == 0) { s_max = 0; s_nlmax = 0; }
+		__syncthreads();
+		if (tid < nw) {
+			const int n = d.n_live[w0 + tid];
+			s_nl[tid] = n;
+			atomicMax(&s_nlmax, n);
+		}
+		__syncthreads();
+		const int total = s_nlmax * nw;  // entry e = (slot e / nw of world e % nw): a pair's worlds are neighbours
+		for (int e = tid; e < total; e += RP_SB_THREADS) {
+			const int slot = e / nw, wl = e - slot * nw;
+			if (slot < s_nl[wl]) {
+				const int lvl = (int)d.live[(size_t)slot * d.WS + w0 + wl].y;
+				atomicAdd(&s_lv[lvl], 1);
+				atomicMax(&s_max, lvl);
+			}
+		}
+		__syncthreads();
+		lmax = s_max;
+		if (tid < 32) {  // exclusive scan of the counts of levels 1..lmax
+			int run = 0;
+			for (int base = 1; base <= lmax; base += 32) {
+				const int l = base + lane;
+				const int v = l <= lmax ? s_lv[l] : 0;
+				int inc = v;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const int t = __shfl_up_sync(0xffffffffu, inc, o);
+					if (lane >= o) inc += t;
+				}
+				if (l <= lmax) s_lv[l] = run + inc - v;
+				run += __shfl_sync(0xffffffffu, inc, 31);
+			}
+		}
+		__syncthreads();
+		const int rounds = (total + RP_SB_THREADS - 1) / RP_SB_THREADS;
+		for (int r = 0; r < rounds; ++r) {
+			const int e = r * RP_SB_THREADS + tid;
+			int lvl = -1;
+			unsigned int enc = 0u;
+			if (e < total) {
+				const int slot = e / nw, wl = e - slot * nw;
+				if (slot < s_nl[wl]) {
+					const uint2 rec = d.live[(size_t)slot * d.WS + w0 + wl];
+					lvl = (int)rec.y;
+					enc = (rec.x << 6) | (unsigned int)wl;
+				}
+			}
+			const unsigned int peers = __match_any_sync(0xffffffffu, lvl);
+			if (lvl > 0) {
+				const int leader = __ffs(peers) - 1;
+				int base = 0;
+				if (lane == leader) base = atomicAdd(&s_lv[lvl], __popc(peers));
+				base = __shfl_sync(peers, base, leader);
+				items[base + __popc(peers & ((1u << lane) - 1u))] = enc;
+			}
+		}
+		__syncthreads();  // s_lv[l] is now the END of level l (the start of level l + 1); s_lv[0] = 0
+	}
+	const int jl = JOINTS ? d.joint_levels : 0;
+	const int levels = lmax > jl ? lmax : jl;
+	int st = 0;
+	for (int it = 0; it < iters; ++it) {
+		for (int level = 1; level <= levels; ++level) {
+			bool any = false;
+			if (JOINTS && level <= jl) {
+				const int j0 = d.joint_lptr[level - 1], nj = d.joint_lptr[level] - j0;
+				any = nj > 0;
+				for (int i = tid; i < nj * nw; i += RP_SB_THREADS) {
+					const int ju = i / nw, w = w0 + (i - ju * nw);
+					const int u = d.joint_sched[j0 + ju];
+					const Joint j = d.joints[u];
+					Body b1, b2;
+					load_static(b1, d, j.e1);
+					load_static(b2, d, j.e2);
+					const DynRef r1 = dyn_ref(d, w, j.e1);
+					const DynRef r2 = dyn_ref(d, w, j.e2);
+					b1.x = ld3(r1, DF_X); b1.q = ld4(r1, DF_Q);
+					b2.x = ld3(r2, DF_X); b2.q = ld4(r2, DF_Q);
+					JointLambda lam = d.lambdas[(size_t)u * d.WS + w];
+					solve_joint(j, lam, b1, b2, h, &st);
+					d.lambdas[(size_t)u * d.WS + w] = lam;
+					if (!b1.fixed) { st3(r1, DF_X, b1.x); st4(r1, DF_Q, b1.q); }
+					if (!b2.fixed) { st3(r2, DF_X, b2.x); st4(r2, DF_Q, b2.q); }
+					if (st) {
+						atomicOr(&d.status[w], st);
+						st = 0;
+					}
+				}
+			}
+			if (collisions && level <= lmax) {
+				const int beg = s_lv[level - 1], end = s_lv[level];
+				any = any || end > beg;
+				for (int i = beg + tid; i < end; i += RP_SB_THREADS) {
+					const unsigned int enc = items[i];
+					const int w = w0 + (int)(enc & 63u);
+					pos_unit(d, h, w, (int)(enc >> 6), &st);
+					if (st) {
+						atomicOr(&d.status[w], st);
+						st = 0;
+					}
+				}
+			}
+			if (any) __syncthreads();
+		}
+	}
+	if (!collisions) return;
+	// velocity pass over the contacts (pbd.cpp:646-711), levels in the same order; joints take no part (pbd.cpp:712-739)
+	const int epoch = *d.epoch;
+	for (int level = 1; level <= lmax; ++level) {
+		const int beg = s_lv[level - 1], end = s_lv[level];
+		if (end == beg) continue;
+		for (int i = beg + tid; i < end; i += RP_SB_THREADS) {
+			const unsigned int enc = items[i];
+			vel_unit(d, h, w0 + (int)(enc & 63u), (int)(enc >> 6), epoch);
+		}
+		__syncthreads();
 	}
 }
 

@@ -201,22 +201,52 @@ RP_HD bool gjk(const SA& A, const SB& B, Simplex* out, int* status, int* iters) 
 }
 
 // ---------------------------------------------------------------------------------------------------------------- EPA
-
-struct EpaScratch {
-	V3 verts[RP_EPA_MAX_VERTS];
-	V3 normals[RP_EPA_MAX_FACES];
-	double dists[RP_EPA_MAX_FACES];
-	uint8_t faces[RP_EPA_MAX_FACES][3];
-	uint8_t edges[RP_EPA_MAX_EDGES][2];
+//
+// The polytope lives in a STORE: vertices, face index triples with their planes, and the edge list of the current
+// expansion, behind accessors, so the same routine runs on plain arrays (host checker; the device's full-capacity fallback in
+// local memory) and on a small thread-interleaved block of shared memory (k_epa: round 1's ncu showed the 11.8 kB
+// per-thread arrays missing L1 at every step). A store with SOFT = true reports exhaustion as EPA_OVERFLOW WITHOUT touching
+// the status word: the caller reruns the pair on a larger store, and since the routine is deterministic the rerun is the run
+// the reference would have made. A store with SOFT = false raises ST_EPA_CAPACITY (the reference's arrays are unbounded).
+template <int MAXV_, int MAXF_, int MAXE_, bool SOFT_>
+struct EpaArrays {
+	enum { MAXV = MAXV_, MAXF = MAXF_, MAXE = MAXE_, SOFT = SOFT_ ? 1 : 0 };
+	V3 verts[MAXV];
+	V3 normals[MAXF];
+	double dists[MAXF];
+	uint8_t faces[MAXF][3];
+	uint8_t edges[MAXE][2];
 	int nverts, nfaces, nedges;
 	V3 min_normal;   // closest face so far (first strictly smaller distance wins, epa.cpp:141-144,:222-228)
 	double min_dist;
+	RP_HD V3 vert(int i) const { return verts[i]; }
+	RP_HD void set_vert(int i, V3 v) { verts[i] = v; }
+	RP_HD V3 normal(int i) const { return normals[i]; }
+	RP_HD double dist(int i) const { return dists[i]; }
+	RP_HD void set_plane(int i, V3 n, double d) { normals[i] = n; dists[i] = d; }
+	RP_HD void face(int i, int* x, int* y, int* z) const { *x = faces[i][0]; *y = faces[i][1]; *z = faces[i][2]; }
+	RP_HD void set_face(int i, int x, int y, int z) { faces[i][0] = (uint8_t)x; faces[i][1] = (uint8_t)y; faces[i][2] = (uint8_t)z; }
+	RP_HD void move_face(int dst, int src) {
+		faces[dst][0] = faces[src][0]; faces[dst][1] = faces[src][1]; faces[dst][2] = faces[src][2];
+		dists[dst] = dists[src];
+		normals[dst] = normals[src];
+	}
+	RP_HD void edge(int i, int* x, int* y) const { *x = edges[i][0]; *y = edges[i][1]; }
+	RP_HD void set_edge(int i, int x, int y) { edges[i][0] = (uint8_t)x; edges[i][1] = (uint8_t)y; }
 };
+typedef EpaArrays<RP_EPA_MAX_VERTS, RP_EPA_MAX_FACES, RP_EPA_MAX_EDGES, false> EpaScratch;
+// capacities of the small store (the polytope of a box pair: EPA converges within 3 iterations for 97 % of the W256 pairs,
+// SURVEY.md 6; 4 expansions = 8 vertices, 4 + 2 * 4 = 12 faces, horizons of up to 12 edges in flight)
+#define RP_EPA_SMALL_VERTS 8
+#define RP_EPA_SMALL_FACES 12
+#define RP_EPA_SMALL_EDGES 12
+typedef EpaArrays<RP_EPA_SMALL_VERTS, RP_EPA_SMALL_FACES, RP_EPA_SMALL_EDGES, true> EpaSmallArrays;
 
 // get_face_normal_and_distance_to_origin (epa.cpp:32-77)
-RP_HD bool epa_face_plane(const EpaScratch& e, int ia, int ib, int ic, V3* normal_out, double* dist_out) {
-	V3 a = e.verts[ia];
-	V3 n = normalize(cross(sub(e.verts[ib], a), sub(e.verts[ic], a)));
+template <class E>
+RP_HD bool epa_face_plane(const E& e, int ia, int ib, int ic, V3* normal_out, double* dist_out) {
+	V3 a = e.vert(ia);
+	V3 n = normalize(cross(sub(e.vert(ib), a), sub(e.vert(ic), a)));
 	if (!(n.x != 0.0 || n.y != 0.0 || n.z != 0.0)) return false;  // epa.cpp:41
 	double dist = dot(n, a);
 	if (dist < -0.0) {
@@ -225,7 +255,7 @@ RP_HD bool epa_face_plane(const EpaScratch& e, int ia, int ib, int ic, V3* norma
 	} else if (dist >= -0.0 && dist <= 0.0) {
 		bool found = false;
 		for (int i = 0; i < e.nverts; ++i) {
-			double t = dot(n, e.verts[i]);
+			double t = dot(n, e.vert(i));
 			if (t < -0.0 || t > 0.0) {
 				n = t < -0.0 ? n : zero_minus(n);
 				found = true;
@@ -241,50 +271,60 @@ RP_HD bool epa_face_plane(const EpaScratch& e, int ia, int ib, int ic, V3* norma
 
 // add_edge (epa.cpp:79-110): an edge seen twice cancels -- by index in either direction or by coordinate-equal
 // endpoints (quirk q8); removal is swap-with-last (light_array.h:146)
-RP_HD bool epa_toggle_edge(EpaScratch& e, int x, int y) {
+template <class E>
+RP_HD bool epa_toggle_edge(E& e, int x, int y) {
 	for (int i = 0; i < e.nedges; ++i) {
-		int cx = e.edges[i][0], cy = e.edges[i][1];
+		int cx, cy;
+		e.edge(i, &cx, &cy);
 		bool hit = (x == cx && y == cy) || (x == cy && y == cx);
 		if (!hit) {
-			V3 c1 = e.verts[cx], c2 = e.verts[cy], e1 = e.verts[x], e2 = e.verts[y];
+			V3 c1 = e.vert(cx), c2 = e.vert(cy), e1 = e.vert(x), e2 = e.vert(y);
 			hit = (equal(c1, e1) && equal(c2, e2)) || (equal(c1, e2) && equal(c2, e1));
 		}
 		if (hit) {
 			--e.nedges;
-			e.edges[i][0] = e.edges[e.nedges][0];
-			e.edges[i][1] = e.edges[e.nedges][1];
+			int lx, ly;
+			e.edge(e.nedges, &lx, &ly);
+			e.set_edge(i, lx, ly);
 			return true;
 		}
 	}
-	if (e.nedges >= RP_EPA_MAX_EDGES) return false;
-	e.edges[e.nedges][0] = (uint8_t)x;
-	e.edges[e.nedges][1] = (uint8_t)y;
+	if (e.nedges >= E::MAXE) return false;
+	e.set_edge(e.nedges, x, y);
 	++e.nedges;
 	return true;
 }
 
 // epa (epa.cpp:118-238), cut into its loop-carried pieces like gjk above: epa_begin is the code before the loop
 // (polytope from the GJK tetrahedron, epa.cpp:8-30,:122-146), epa_step one trip of it. The running minimum lives in
-// the scratch record.
-enum { EPA_CONTINUE = 0, EPA_DONE = 1, EPA_FAIL = 2 };
+// the store.
+enum { EPA_CONTINUE = 0, EPA_DONE = 1, EPA_FAIL = 2, EPA_OVERFLOW = 3 };
 
-RP_HD int epa_begin(const Simplex& s, EpaScratch& e, int* status) {
-	e.verts[0] = s.a; e.verts[1] = s.b; e.verts[2] = s.c; e.verts[3] = s.d;
+template <class E>
+RP_HD int epa_out_of_room(int* status) {
+	if (E::SOFT) return EPA_OVERFLOW;
+	*status |= ST_EPA_CAPACITY;
+	return EPA_FAIL;
+}
+
+template <class E>
+RP_HD int epa_begin(const Simplex& s, E& e, int* status) {
+	e.set_vert(0, s.a); e.set_vert(1, s.b); e.set_vert(2, s.c); e.set_vert(3, s.d);
 	e.nverts = 4;
-	const uint8_t init_faces[4][3] = {{0, 1, 2}, {0, 2, 3}, {0, 3, 1}, {1, 2, 3}};
 	e.nfaces = 0;
 	e.nedges = 0;
 	e.min_normal = v3(0.0, 0.0, 0.0);
 	e.min_dist = 1.7976931348623157e308;
 	for (int i = 0; i < 4; ++i) {
+		// initial faces (0,1,2) (0,2,3) (0,3,1) (1,2,3) (epa.cpp:8-30)
+		const int fa = i == 3 ? 1 : 0, fb = i == 0 ? 1 : (i == 3 ? 2 : i + 1), fc = i == 0 ? 2 : (i == 2 ? 1 : 3);
 		V3 n; double d;
-		if (!epa_face_plane(e, init_faces[i][0], init_faces[i][1], init_faces[i][2], &n, &d)) {
+		if (!epa_face_plane(e, fa, fb, fc, &n, &d)) {
 			*status |= ST_EPA_DEGENERATE;
 			return EPA_FAIL;
 		}
-		e.faces[i][0] = init_faces[i][0]; e.faces[i][1] = init_faces[i][1]; e.faces[i][2] = init_faces[i][2];
-		e.normals[i] = n;
-		e.dists[i] = d;
+		e.set_face(i, fa, fb, fc);
+		e.set_plane(i, n, d);
 		e.nfaces = i + 1;
 		if (d < e.min_dist) {
 			e.min_dist = d;
@@ -294,76 +334,78 @@ RP_HD int epa_begin(const Simplex& s, EpaScratch& e, int* status) {
 	return EPA_CONTINUE;
 }
 
-template <class SA, class SB>
-RP_HD int epa_step(const SA& A, const SB& B, EpaScratch& e, int* status) {
+template <class SA, class SB, class E>
+RP_HD int epa_step(const SA& A, const SB& B, E& e, int* status) {
 	const V3 min_normal = e.min_normal;
 	V3 sp = support_minkowski(A, B, min_normal);
 	double d = dot(min_normal, sp);
 	if (fabs(d - e.min_dist) < 0.0001) return EPA_DONE;  // result: e.min_normal, e.min_dist
+	if (e.nverts >= E::MAXV) return epa_out_of_room<E>(status);  // (the full store holds 4 + RP_EPA_MAX_ITERS: never reached there)
 	int new_index = e.nverts;
-	e.verts[e.nverts++] = sp;  // capacity: 4 + RP_EPA_MAX_ITERS
+	e.set_vert(e.nverts++, sp);
 
 	// faces that see the new point are removed (swap-with-last while scanning, quirk q7), their edges toggled
 	int i = 0;
 	while (i < e.nfaces) {
-		int fx = e.faces[i][0], fy = e.faces[i][1], fz = e.faces[i][2];
-		V3 centroid = scale(1.0 / 3.0, add(add(e.verts[fy], e.verts[fz]), e.verts[fx]));  // triangle_centroid (epa.cpp:112)
-		if (dot(e.normals[i], sub(sp, centroid)) > 0.0) {
-			if (!epa_toggle_edge(e, fx, fy) || !epa_toggle_edge(e, fy, fz) || !epa_toggle_edge(e, fz, fx)) {
-				*status |= ST_EPA_CAPACITY;
-				return EPA_FAIL;
-			}
+		int fx, fy, fz;
+		e.face(i, &fx, &fy, &fz);
+		V3 centroid = scale(1.0 / 3.0, add(add(e.vert(fy), e.vert(fz)), e.vert(fx)));  // triangle_centroid (epa.cpp:112)
+		if (dot(e.normal(i), sub(sp, centroid)) > 0.0) {
+			if (!epa_toggle_edge(e, fx, fy) || !epa_toggle_edge(e, fy, fz) || !epa_toggle_edge(e, fz, fx)) return epa_out_of_room<E>(status);
 			int last = --e.nfaces;
-			e.faces[i][0] = e.faces[last][0]; e.faces[i][1] = e.faces[last][1]; e.faces[i][2] = e.faces[last][2];
-			e.dists[i] = e.dists[last];
-			e.normals[i] = e.normals[last];
+			e.move_face(i, last);
 		} else {
 			++i;
 		}
 	}
 	for (int k = 0; k < e.nedges; ++k) {
-		if (e.nfaces >= RP_EPA_MAX_FACES) {
-			*status |= ST_EPA_CAPACITY;
-			return EPA_FAIL;
-		}
+		if (e.nfaces >= E::MAXF) return epa_out_of_room<E>(status);
+		int ex, ey;
+		e.edge(k, &ex, &ey);
 		V3 n; double dd;
-		if (!epa_face_plane(e, e.edges[k][0], e.edges[k][1], new_index, &n, &dd)) {
+		if (!epa_face_plane(e, ex, ey, new_index, &n, &dd)) {
 			*status |= ST_EPA_DEGENERATE;
 			return EPA_FAIL;
 		}
 		int f = e.nfaces++;
-		e.faces[f][0] = e.edges[k][0]; e.faces[f][1] = e.edges[k][1]; e.faces[f][2] = (uint8_t)new_index;
-		e.normals[f] = n;
-		e.dists[f] = dd;
+		e.set_face(f, ex, ey, new_index);
+		e.set_plane(f, n, dd);
 	}
 	e.min_dist = 1.7976931348623157e308;
 	for (int k = 0; k < e.nfaces; ++k) {
-		if (e.dists[k] < e.min_dist) {
-			e.min_dist = e.dists[k];
-			e.min_normal = e.normals[k];
+		const double dk = e.dist(k);
+		if (dk < e.min_dist) {
+			e.min_dist = dk;
+			e.min_normal = e.normal(k);
 		}
 	}
 	e.nedges = 0;
 	return EPA_CONTINUE;
 }
 
-template <class SA, class SB>
-RP_HD bool epa(const SA& A, const SB& B, const Simplex& s, EpaScratch& e, V3* normal_out, double* depth_out, int* status,
-	int* iters) {
-	if (epa_begin(s, e, status) == EPA_FAIL) return false;
+// returns EPA_DONE (normal, depth written), EPA_FAIL (status says why) or, for a SOFT store, EPA_OVERFLOW (nothing written)
+template <class SA, class SB, class E>
+RP_HD int epa_run(const SA& A, const SB& B, const Simplex& s, E& e, V3* normal_out, double* depth_out, int* status, int* iters) {
+	if (epa_begin(s, e, status) == EPA_FAIL) return EPA_FAIL;
 	for (int it = 0; it < RP_EPA_MAX_ITERS; ++it) {
 		const int r = epa_step(A, B, e, status);
 		if (r == EPA_DONE) {
 			*normal_out = e.min_normal;
 			*depth_out = e.min_dist;
 			if (iters) *iters = it + 1;
-			return true;
+			return EPA_DONE;
 		}
-		if (r == EPA_FAIL) return false;
+		if (r != EPA_CONTINUE) return r;
 	}
 	*status |= ST_EPA_NO_CONVERGENCE;
 	if (iters) *iters = RP_EPA_MAX_ITERS;
-	return false;
+	return EPA_FAIL;
+}
+
+template <class SA, class SB>
+RP_HD bool epa(const SA& A, const SB& B, const Simplex& s, EpaScratch& e, V3* normal_out, double* depth_out, int* status,
+	int* iters) {
+	return epa_run(A, B, s, e, normal_out, depth_out, status, iters) == EPA_DONE;
 }
 
 // ----------------------------------------------------------------------------------------------------------- clipping
@@ -394,35 +436,57 @@ RP_HD bool clip_edge(const ClipPlane& pl, float offset, V3 start, V3 end, V3* ou
 	return false;
 }
 
-struct ClipScratch {
-	V3 buf[2][RP_CLIP_MAX_POINTS];
+// The two polygon buffers of Sutherland-Hodgman behind accessors, like the EPA store above: plain arrays of full capacity
+// (host checker; the device's fallback in local memory) or a small thread-interleaved block of shared memory (k_manifold: a
+// box face clipped against four planes never exceeds 8 points, while round 1's 160-point arrays were 7.7 kB of local memory
+// per thread). SOFT = true: running out of room is reported to the caller (who reruns on the full store) and leaves the
+// status word alone.
+template <int CAP_, bool SOFT_>
+struct ClipArrays {
+	enum { CAP = CAP_, SOFT = SOFT_ ? 1 : 0 };
+	V3 buf[2][CAP];
+	RP_HD V3 get(int b, int i) const { return buf[b][i]; }
+	RP_HD void set(int b, int i, V3 v) { buf[b][i] = v; }
 };
+typedef ClipArrays<RP_CLIP_MAX_POINTS, false> ClipScratch;
+#define RP_CLIP_SMALL_POINTS 8
+typedef ClipArrays<RP_CLIP_SMALL_POINTS, true> ClipSmallArrays;
 
-// One Sutherland-Hodgman pass of `in` against one plane (body of the loop at clipping.cpp:63-108). The reference tests
-// every vertex twice (as the end of one edge and the start of the next); the verdict is a pure function of the vertex,
-// so it is carried over instead.
-RP_HD int clip_pass(const ClipPlane& pl, const V3* in, int n_in, V3* out, bool remove_only, int* status) {
+// One Sutherland-Hodgman pass of buffer `src` against one plane into the other buffer (body of the loop at
+// clipping.cpp:63-108). The reference tests every vertex twice (as the end of one edge and the start of the next); the
+// verdict is a pure function of the vertex, so it is carried over instead. Returns the number of points written, or -1
+// when the store is full (a point that does not fit is never dropped silently).
+template <class C>
+RP_HD int clip_pass(const ClipPlane& pl, C& cs, int src, int n_in, bool remove_only) {
+	const int dst = src ^ 1;
 	int n_out = 0;
 	const float offset = clip_offset(pl);
-	V3 start = in[n_in - 1];
+	V3 start = cs.get(src, n_in - 1);
 	bool s_in = clip_inside(pl, offset, start);
 	for (int j = 0; j < n_in; ++j) {
-		V3 end = in[j];
+		V3 end = cs.get(src, j);
 		bool e_in = clip_inside(pl, offset, end);
 		V3 tmp;
-		if (n_out + 2 > RP_CLIP_MAX_POINTS) {
-			*status |= ST_CLIP_CAPACITY;
-			return n_out;
-		}
 		if (remove_only) {
-			if (e_in) out[n_out++] = end;
+			if (e_in) {
+				if (n_out >= C::CAP) return -1;
+				cs.set(dst, n_out++, end);
+			}
 		} else if (s_in && e_in) {
-			out[n_out++] = end;
+			if (n_out >= C::CAP) return -1;
+			cs.set(dst, n_out++, end);
 		} else if (s_in && !e_in) {
-			if (clip_edge(pl, offset, start, end, &tmp)) out[n_out++] = tmp;
+			if (clip_edge(pl, offset, start, end, &tmp)) {
+				if (n_out >= C::CAP) return -1;
+				cs.set(dst, n_out++, tmp);
+			}
 		} else if (!s_in && e_in) {
-			if (clip_edge(pl, offset, start, end, &tmp)) out[n_out++] = tmp;
-			out[n_out++] = end;
+			if (clip_edge(pl, offset, start, end, &tmp)) {
+				if (n_out >= C::CAP) return -1;
+				cs.set(dst, n_out++, tmp);
+			}
+			if (n_out >= C::CAP) return -1;
+			cs.set(dst, n_out++, end);
 		}
 		start = end;
 		s_in = e_in;
@@ -431,7 +495,8 @@ RP_HD int clip_pass(const ClipPlane& pl, const V3* in, int n_in, V3* out, bool r
 }
 
 // get_face_with_most_fitting_normal (clipping.cpp:136-152)
-RP_HD int clip_best_face(const Shape& s, int support_idx, V3 normal) {
+template <class S>
+RP_HD int clip_best_face(const S& s, int support_idx, V3 normal) {
 	double best = -1.7976931348623157e308;
 	int sel = 0;
 	for (int k = s.v2f_ptr[support_idx]; k < s.v2f_ptr[support_idx + 1]; ++k) {
@@ -461,12 +526,28 @@ RP_HD bool clip_skew_lines(V3 p1, V3 d1, V3 p2, V3 d2, V3* l1, V3* l2) {
 	return true;
 }
 
-// convex_convex_contact_manifold (clipping.cpp:249-341). Sink: void operator()(V3 p1, V3 p2).
+// convex_convex_contact_manifold (clipping.cpp:249-341), in two halves so that a caller can learn how many contacts there
+// are before it decides where they go (k_manifold counts, takes a run of the world's contact buffer, then writes the
+// records straight from the clip buffer -- no staging copy of the manifold):
+//   manifold_clip  everything up to and including the clipping: either the single edge-edge contact, or the candidate
+//                  points (incident face clipped against the reference face's side planes, then culled against the
+//                  reference plane) left in buffer `cur` of the store;
+//   manifold_emit  the final loop (clipping.cpp:322-338): penetration of each candidate along the normal, contact if < 0.
 // `sup1_known` / `sup2_known` (>= 0): the support vertices along +-normal when a caller has already found them (the GPU
 // finds them with a whole warp for large hulls, k_epa_warp); the scan here would return the same indices.
-template <class Sink>
-RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipScratch& cs, int* status, Sink& sink, int sup1_known = -1,
+enum { CLIP_OK = 0, CLIP_OVERFLOW = 1 };
+struct ClipResult {
+	int kind;          // 0: nothing (failed / empty), 1: one edge-edge contact (l1, l2), 2: `n` candidate points in buffer `cur`
+	int n, cur;
+	bool ref1;         // the reference face is on hull 1
+	V3 l1, l2;         // kind 1
+	V3 rp_normal, rp_point;  // reference plane (inverted face normal, first face vertex), kind 2
+};
+
+template <class S, class C>
+RP_HD int manifold_clip(const S& h1, const S& h2, V3 normal, C& cs, int* status, ClipResult* out, int sup1_known = -1,
 	int sup2_known = -1) {
+	out->kind = 0; out->n = 0; out->cur = 0; out->ref1 = false;
 	V3 inv_normal = zero_minus(normal);
 	int sup1 = sup1_known >= 0 ? sup1_known : support_index(h1, normal);
 	int sup2 = sup2_known >= 0 ? sup2_known : support_index(h2, inv_normal);
@@ -536,18 +617,17 @@ RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipS
 		V3 d1 = sub(vert(h1, e1n), p1);
 		V3 p2 = vert(h2, sup2);
 		V3 d2 = sub(vert(h2, e2n), p2);
-		V3 l1, l2;
-		if (!clip_skew_lines(p1, d1, p2, d2, &l1, &l2)) {
+		if (!clip_skew_lines(p1, d1, p2, d2, &out->l1, &out->l2)) {
 			*status |= ST_EDGE_PARALLEL;  // the reference aborts (clipping.cpp:279)
-			return;
+			return CLIP_OK;
 		}
-		sink(l1, l2);
-		return;
+		out->kind = 1;
+		return CLIP_OK;
 	}
 
 	bool ref1 = dot1 > dot2;
-	const Shape& R = ref1 ? h1 : h2;   // reference hull
-	const Shape& I = ref1 ? h2 : h1;   // incident hull
+	const S& R = ref1 ? h1 : h2;   // reference hull
+	const S& I = ref1 ? h2 : h1;   // incident hull
 	int rface = ref1 ? face1 : face2;
 	int iface = ref1 ? face2 : face1;
 
@@ -555,11 +635,12 @@ RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipS
 	int cur = 0;
 	int n = 0;
 	for (int k = I.face_ptr[iface]; k < I.face_ptr[iface + 1]; ++k) {
-		if (n >= RP_CLIP_MAX_POINTS) {
+		if (n >= C::CAP) {
+			if (C::SOFT) return CLIP_OVERFLOW;
 			*status |= ST_CLIP_CAPACITY;
-			return;
+			return CLIP_OK;
 		}
-		cs.buf[0][n++] = vert(I, I.face_idx[k]);
+		cs.set(0, n++, vert(I, I.face_idx[k]));
 	}
 	// boundary planes of the reference face (build_boundary_planes, clipping.cpp:121-134), clipped one at a time
 	// (sutherland_hodgman, clipping.cpp:52-113)
@@ -569,23 +650,42 @@ RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipS
 		ClipPlane pl;
 		pl.point = vert(R, R.face_idx[R.face_ptr[nf]]);
 		pl.normal = zero_minus(fnormal(R, nf));
-		n = clip_pass(pl, cs.buf[cur], n, cs.buf[cur ^ 1], false, status);
+		n = clip_pass(pl, cs, cur, n, false);
+		if (n < 0) {
+			if (C::SOFT) return CLIP_OVERFLOW;
+			*status |= ST_CLIP_CAPACITY;
+			return CLIP_OK;
+		}
 		cur ^= 1;
 	}
-	ClipPlane rp;
-	rp.normal = zero_minus(ref1 ? f1n : f2n);
-	rp.point = vert(R, R.face_idx[R.face_ptr[rface]]);
+	out->rp_normal = zero_minus(ref1 ? f1n : f2n);
+	out->rp_point = vert(R, R.face_idx[R.face_ptr[rface]]);
 	if (n != 0) {
-		n = clip_pass(rp, cs.buf[cur], n, cs.buf[cur ^ 1], true, status);
+		ClipPlane rp;
+		rp.normal = out->rp_normal;
+		rp.point = out->rp_point;
+		n = clip_pass(rp, cs, cur, n, true);  // (never grows: cannot overflow)
 		cur ^= 1;
 	}
-	for (int k = 0; k < n; ++k) {
-		V3 p = cs.buf[cur][k];
+	out->kind = 2; out->n = n; out->cur = cur; out->ref1 = ref1;
+	return CLIP_OK;
+}
+
+// Sink: void operator()(V3 p1, V3 p2), called once per contact in the reference's order
+template <class C, class Sink>
+RP_HD void manifold_emit(const C& cs, const ClipResult& r, V3 normal, Sink& sink) {
+	if (r.kind == 1) {
+		sink(r.l1, r.l2);
+		return;
+	}
+	if (r.kind != 2) return;
+	for (int k = 0; k < r.n; ++k) {
+		V3 p = cs.get(r.cur, k);
 		// get_closest_point_polygon (clipping.cpp:115-119)
-		double dd = dot(scale(-1.0, rp.normal), rp.point);
-		V3 closest = sub(p, scale(dot(rp.normal, p) + dd, rp.normal));
+		double dd = dot(scale(-1.0, r.rp_normal), r.rp_point);
+		V3 closest = sub(p, scale(dot(r.rp_normal, p) + dd, r.rp_normal));
 		V3 diff = sub(p, closest);
-		if (ref1) {
+		if (r.ref1) {
 			double pen = dot(diff, normal);
 			if (pen < 0.0) sink(sub(p, scale(pen, normal)), p);
 		} else {
@@ -593,6 +693,14 @@ RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipS
 			if (pen < 0.0) sink(p, add(p, scale(pen, normal)));
 		}
 	}
+}
+
+template <class Sink>
+RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipScratch& cs, int* status, Sink& sink, int sup1_known = -1,
+	int sup2_known = -1) {
+	ClipResult r;
+	manifold_clip(h1, h2, normal, cs, status, &r, sup1_known, sup2_known);
+	manifold_emit(cs, r, normal, sink);
 }
 
 // collider_get_contacts (collider.cpp:523-558) + clipping_get_contact_manifold (clipping.cpp:343-371) for one collider
@@ -608,6 +716,36 @@ RP_HD void manifold(const Shape& A, const Shape& B, V3 normal, double depth, Cli
 		sink(add(p, scale(depth, normal)), p);
 	} else {
 		manifold_hull_hull(A, B, normal, cs, status, sink, sup1_known, sup2_known);
+	}
+}
+
+// Two-tier drivers: the small store first, the full store when it runs out (what the CUDA kernels do with their
+// shared-memory stores; the CPU restatement calls these, so the rerun logic is checked against the compiled reference too).
+// `reruns` (optional) counts the pairs that needed the second tier.
+template <class SA, class SB, class Small, class Full>
+RP_HD bool epa_tiered(const SA& A, const SB& B, const Simplex& s, Small& small, Full& full, V3* normal_out, double* depth_out, int* status,
+	int* reruns) {
+	int r = epa_run(A, B, s, small, normal_out, depth_out, status, 0);
+	if (r == EPA_OVERFLOW) {
+		if (reruns) ++*reruns;
+		r = epa_run(A, B, s, full, normal_out, depth_out, status, 0);
+	}
+	return r == EPA_DONE;
+}
+template <class Small, class Full, class Sink>
+RP_HD void manifold_tiered(const Shape& A, const Shape& B, V3 normal, double depth, Small& small, Full& full, int* status, Sink& sink,
+	int* reruns) {
+	if (A.type == SHAPE_SPHERE || B.type == SHAPE_SPHERE) {
+		manifold(A, B, normal, depth, full, status, sink);
+		return;
+	}
+	ClipResult r;
+	if (manifold_clip(A, B, normal, small, status, &r) == CLIP_OVERFLOW) {
+		if (reruns) ++*reruns;
+		manifold_clip(A, B, normal, full, status, &r);
+		manifold_emit(full, r, normal, sink);
+	} else {
+		manifold_emit(small, r, normal, sink);
 	}
 }
 

@@ -100,6 +100,10 @@ RP_HD V3 vert(const StagedShape<NT>& s, int i) {
 	const double* p = s.vp + i * (3 * NT);
 	return v3(p[0], p[NT], p[2 * NT]);
 }
+RP_HD V3 fnormal_stored(const Shape& s, int i) {
+	const double* p = s.np + (size_t)i * s.ns;
+	return v3(p[0], p[s.ncs], p[2 * s.ncs]);
+}
 RP_HD V3 fnormal(const Shape& s, int i) {
 	const double* p = s.np + (size_t)i * s.ns;
 	return v3(p[0], p[s.ncs], p[2 * s.ncs]);
@@ -138,6 +142,32 @@ RP_HD V3 transform_normal(const Pose34& M, V3 n) {
 	          M.m[1][0] * n.x + M.m[1][1] * n.y + M.m[1][2] * n.z,
 	          M.m[2][0] * n.x + M.m[2][1] * n.y + M.m[2][2] * n.z);
 	return normalize(r);
+}
+
+// A collider whose transformed geometry is NOT stored: every vertex (and face normal) is evaluated from the body's model
+// matrix and the hull's local data at the moment it is asked for -- the same expressions collider_update evaluates
+// (collider.cpp:414-429), so the same bits. The CUDA narrowphase uses it for everything: a world's poses (56 B per body)
+// stay in L2 where the transformed hulls (336 B per cube, re-read by GJK, EPA and clipping: round 1's kernels stalled on
+// exactly those loads, ncu: a third of all stall samples of k_epa and k_manifold) did not, and the FP64 pipe has the room.
+struct PoseShape : Shape {
+	Pose34 M;
+	const V3* lv;   // local vertices of the hull (template, shared by all worlds)
+	const V3* ln;   // local face normals
+};
+RP_HD V3 ld_v3(const V3* p) {
+#ifdef __CUDA_ARCH__
+	return v3(__ldg(&p->x), __ldg(&p->y), __ldg(&p->z));
+#else
+	return *p;
+#endif
+}
+RP_HD V3 vert(const PoseShape& s, int i) { return transform_point(s.M, ld_v3(s.lv + i)); }
+RP_HD V3 fnormal(const PoseShape& s, int i) {
+#if defined(RP_STORED_NORMALS)
+	return fnormal_stored(s, i);
+#else
+	return transform_normal(s.M, ld_v3(s.ln + i));
+#endif
 }
 
 // support_point_get_index (support.cpp:5-17): first maximum wins (strict >), starting from -DBL_MAX

@@ -440,3 +440,50 @@ def test_spot_storm_compound_large_hulls(pkg, oracle_flavour):
     calls, contacts = b.step_logged(world=1, substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
     assert np.array_equal(calls, want_calls) and np.array_equal(contacts, want_contacts)
     assert want_contacts.shape[0] > 0
+
+
+@pytest.mark.parametrize("name,wpb", [("stack", 1), ("tumble", 3), ("coin", 4), ("mirror_cube", 2), ("hinge_joints", 4), ("mutual_orientation", 5),
+                                      ("cube_storm", 4), ("spheres", 64)])
+def test_world_block_sweeps_bit_exact(pkg, oracle_flavour, name, wpb):
+    """k_solve_block (one CTA per block of `wpb` worlds, both sweeps, CTA-scoped barriers between levels) is what large batches
+    run; small test batches would get the level-major cooperative sweeps, so it is forced here: same per-world level order,
+    hence the same bits as the sequential reference (contact scenes) / the joint tolerance (libm scenes), with world counts
+    that do not divide into blocks and worlds started from different states."""
+    sc = scenes.BUILDERS[name]()
+    W = 7
+    b = make(pkg, sc, n_worlds=W, sweep_block_worlds=wpb)
+    base = b.state()[0].copy()
+    states = np.repeat(base[None], W, axis=0)
+    rng = np.random.RandomState(5)
+    moving = [i for i, body in enumerate(sc.bodies) if not body.fixed]
+    for w in range(1, W, 2):  # odd worlds start perturbed: their level lists differ from their neighbours'
+        states[w, moving, 0] += 0.02 * rng.randn(len(moving))
+        states[w, moving, 7:10] += 0.2 * rng.randn(len(moving), 3)
+    b.upload(states)
+    frames = 60
+    for _ in range(frames):
+        step(b, sc)
+    got = b.state()
+    for w in (0, 1, 4, 5):
+        o = refdrv.RefWorld(oracle_flavour).load(sc)
+        o.set_state(states[w, :, :15])
+        for _ in range(frames):
+            o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+        if sc.constraints and name != "mutual_orientation":
+            assert np.abs(got[w, :, :7] - o.state()[:, :7]).max() <= 1e-9, (name, w)
+        else:
+            assert np.array_equal(got[w, :, :15], o.state()), (name, w, np.abs(got[w, :, :15] - o.state()).max())
+    assert not b.status().any()
+
+
+def test_world_block_sweeps_deep_levels(pkg, oracle_flavour):
+    """compound bodies chain 121 units per body pair: 1300+ mostly empty levels per block"""
+    sc = scenes.spot_storm(n=2)
+    b = make(pkg, sc, n_worlds=3, max_pairs=8192, max_contacts=8192, sweep_block_worlds=2)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    for f in range(30):
+        step(b, sc)
+        o.step(substeps=sc.substeps, iters=sc.iters, collisions=sc.collisions)
+    got = b.state()
+    assert np.array_equal(got[0, :, :15], o.state()) and np.array_equal(got[0], got[2])
+    assert not b.status().any()
