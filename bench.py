@@ -1,21 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- body-substeps/sec of the XPBD frame step on the north-star workload (BASELINE.json):
-4096 independent worlds x (256 cubes + floor) per GPU, dt = 1/60, 20 substeps, 1 positional iteration, collisions on.
+"""bench.py -- body-substeps/sec of the XPBD frame step (BASELINE.json's metric) on the workloads BASELINE.json names.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--worlds 4096]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload w256|c2|c3|c5] [--worlds W]
+                    [--scaling weak|strong]
 
-One "step" = one 60 Hz frame (= 20 substeps) of every world. The workload's window is frames 0..59 from the initial
-poses (nothing can fall asleep before 1.0 s of simulated quiet time, pbd.cpp:490-498, so it is not deflated
-by sleeping). Work per frame GROWS through the window (the cubes land on each other one after the other), so for K < 60
-the timed steps are the LAST K frames of the window (frames 60-K..59, the heavier end; the frames before them are
-stepped untimed after the W warm-up steps and a reset) -- a short run never reports a lighter workload than the default
-K = 60, which times the whole window; K > 60 runs on past it. `value` is timed on the device with CUDA events on the
-stream the kernels are launched on, with state resident in HBM; `e2e` is the same metric through the host-buffer call
-rp_batch_step_host (pinned host state in, pinned host state out, both copies inside the timed region).
-`--impl reference` times the UNMODIFIED reference (oracle/_ref, else the CPU restatement) on all host cores.
-Prints ONE JSON line on rank 0.
+Workloads (scenes come from the library's own example builders, rp_example_create; dt = 1/60 and the example's own
+substeps / iterations / collisions):
+  w256  the north star (default): W worlds x (256 cubes + floor), frames 0..59 from the initial poses
+  c2    BASELINE config 2: W copies of the reference's stack scene (8 cubes + floor), frames 0..59
+  c3    BASELINE config 3: brick wall 32 x 32 as ONE scene, graph-coloured sweeps (and the reference order beside it), frames 0..29
+  c5    BASELINE config 5: W = 16384 joint worlds (hinge_joints.cpp's levers, spun), sharded over the GPUs, frames 0..59
+One "step" = one 60 Hz frame of every world. Work per frame GROWS through a window (bodies land on each other one after the
+other), so for K smaller than the window the timed steps are the LAST K frames of it (the frames before them are stepped
+untimed after the W warm-up steps and a reset) -- a short run never reports a lighter workload than the whole window; and the
+line always carries a `window` block timed over the whole window as well. K larger than the window runs on past it.
+
+`value` is timed on the device with CUDA events on the stream the kernels are launched on, state resident in HBM; `e2e` is
+the same metric through the host-buffer call rp_batch_step_host (pinned host state in, pinned host state out, both copies
+inside the timed region). After the window the result is CHECKED: world 0 against the compiled reference's committed state
+for that frame (tests/golden), every other world against world 0, a digest of every world's state gathered over the process
+group -- `parity`. `--scaling weak` (default for w256, c2): W worlds per GPU; `strong` (default for c5): W worlds in total,
+split over the ranks by multi.partition. `--impl reference` times the UNMODIFIED reference (oracle/_ref, else the CPU
+restatement) on all host cores. Prints ONE JSON line on rank 0.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -27,48 +36,69 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 DT = 1.0 / 60.0
-SUBSTEPS = 20
-ITERS = 1
-WINDOW = 60  # frames of the workload's window
 
-
-def lead_in(steps):
-    """untimed frames stepped from the initial poses before the timed ones, so that K < WINDOW times frames WINDOW-K..WINDOW-1"""
-    return max(0, WINDOW - steps)
-
-
-def window_text(steps):
-    return "frames %d..%d from the initial poses" % (lead_in(steps), lead_in(steps) + steps - 1)
+# name -> example, params, perturb, default worlds, window (frames), default scaling, golden (file, key pattern, tolerance)
+WORKLOADS = {
+    "w256": dict(example="w256", params=(), perturb=False, worlds=4096, window=60, scaling="weak", coloured=False,
+                 golden=("windows.npz", "w256/state/%d", 0.0), text="w256x%d per GPU (256 cubes + floor per world)"),
+    "c2": dict(example="stack", params=(), perturb=False, worlds=4096, window=60, scaling="weak", coloured=False,
+               golden=("trajectories.npz", "stack/state/%d", 0.0), text="c2: stack.cpp x%d per GPU (8 cubes + floor per world)"),
+    "c3": dict(example="brick_wall", params=(32, 32), perturb=False, worlds=1, window=30, scaling="weak", coloured=True,
+               golden=("windows.npz", "brick_wall_32x32/state/%d", 0.0), text="c3: brick wall 32x32 as one scene x%d per GPU"),
+    "c5": dict(example="hinge_joints", params=(), perturb=True, worlds=16384, window=60, scaling="strong", coloured=False,
+               golden=("trajectories.npz", "hinge_joints/state/%d", 1e-9), text="c5: hinge_joints.cpp levers (spun) x%d"),
+}
 
 # Algorithmic work per item, derived in DESIGN.md ("Kernels and rooflines"): bytes that must move and FP64 operations
-# (mul/add/div/sqrt = 1 each, no FMA credit) for one body-substep / pair test / EPA+manifold run / solved contact.
-BYTES = dict(integrate=288.0, gjk=400.0, epa=16.0 + 96.0 + 384.0 + 40.0, manifold=40.0 + 16.0 + 672.0 + 2 * 56.0, manifold_contact=64.0, solve_pos_pair=2 * (112.0 + 56.0), solve_contact=80.0,
-             solve_vel_pair=2 * (128.0 + 48.0), solve_contact_vel=64.0)
-FLOPS = dict(integrate=590.0, gjk=620.0, epa=800.0, manifold=1200.0, solve_pos_contact=1100.0, solve_vel_contact=650.0)
+# (mul/add/div/sqrt = 1 each, no FMA credit) for one body-substep / pair test / EPA run / manifold / solved contact / joint.
+# Since round 2 the narrowphase reads poses, not stored hulls: 2 x 56 B of pose per pair + the records it passes on.
+BYTES = dict(integrate=288.0, gjk=16.0 + 2 * 56.0, epa=16.0 + 96.0 + 2 * 56.0 + 40.0, manifold=40.0 + 16.0 + 2 * 56.0 + 16.0 + 48.0,
+             manifold_contact=64.0, solve_pos_pair=2 * (112.0 + 56.0), solve_contact=80.0, solve_vel_pair=2 * (128.0 + 48.0),
+             solve_contact_vel=64.0, joint=2 * 2 * 56.0 + 48.0)
+FLOPS = dict(integrate=590.0, gjk=620.0 + 470.0, epa=800.0 + 560.0, manifold=1200.0 + 900.0, solve_pos_contact=1100.0, solve_vel_contact=650.0,
+             joint=1500.0)
 FLOP_PER_BODY_SUBSTEP = 4.0e3  # SURVEY.md 8(d): algorithmic FP64 flop per body-substep on the W256 world
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=0, help="timed frames (default: the workload's whole window)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU")
+    ap.add_argument("--workload", default="w256", choices=sorted(WORKLOADS))
+    ap.add_argument("--worlds", type=int, default=0, help="worlds per GPU (weak) / in total (strong); default: the workload's")
+    ap.add_argument("--scaling", default="", choices=["", "weak", "strong"])
     ap.add_argument("--no-cull", action="store_true", help="run GJK on every broadphase pair (disables the exact-safe bounds cull)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / profile / cpu baseline (kernel timing only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (tuning runs)")
     ap.add_argument("--hetero", action="store_true",
-                    help="also time the same window with every world started from a DIFFERENT pose set (random yaw and lateral "
-                         "offset per cube): reported next to the headline as `heterogeneous`")
+                    help="w256 only: also time the same window with every world started from a DIFFERENT pose set (random yaw and "
+                         "lateral offset per cube): reported next to the headline as `heterogeneous`")
     ap.add_argument("--e2e-parts", type=int, default=2, help="sub-batches (host threads) of the pipelined end-to-end leg")
     ap.add_argument("--ncu-frame", type=int, default=-1,
                     help="profiling aid: run this many frames, then bracket ONE more frame with cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints nothing")
-    return ap.parse_args()
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.steps <= 0:
+        args.steps = wl["window"]
+    if args.worlds <= 0:
+        args.worlds = wl["worlds"]
+    if not args.scaling:
+        args.scaling = wl["scaling"]
+    return args
+
+
+def lead_in(wl, steps):
+    """untimed frames stepped from the initial poses before the timed ones, so that K < window times the window's last K frames"""
+    return max(0, wl["window"] - steps)
+
+
+def window_text(wl, steps):
+    return "frames %d..%d from the initial poses" % (lead_in(wl, steps), lead_in(wl, steps) + steps - 1)
 
 
 def ncu_traffic(kernel):
@@ -76,11 +106,12 @@ def ncu_traffic(kernel):
     (profiles/ncu_traffic.json, written by profiles/summarise_ncu.py from the capture named inside it), or None."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
-        return None
-    for name, d in json.load(open(p)).get("kernels", {}).items():
+        return None, None
+    j = json.load(open(p))
+    for name, d in j.get("kernels", {}).items():
         if name.split("<")[0] == kernel:  # template instances are listed as k_solve_pos<0>
-            return d["dram_read"] + d["dram_write"]
-    return None
+            return d["dram_read"] + d["dram_write"], j.get("capture")
+    return None, None
 
 
 def measured_peaks():
@@ -138,35 +169,50 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_single_thread_baseline(flavour, budget_s=12.0):
-    """The reference's own single-threaded step on ONE host core: fresh W256 worlds, first 60 frames each."""
+# ------------------------------------------------------------------------------------------------------ reference arm
+def _refdrv():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import refdrv
-    import scenes
-    desc = scenes.w256()
-    frames, worlds, spent = 60, 0, 0.0
-    while spent < budget_s and worlds < 16:
+    return refdrv
+
+
+def _example_desc(wl):
+    """the workload's scene description from the library's example builder (host code; no GPU needed)"""
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    return pkg.example(wl["example"], wl["params"], perturb=wl["perturb"])
+
+
+def cpu_single_thread_baseline(wl, flavour, budget_s=12.0):
+    """The reference's own single-threaded step on ONE host core: fresh worlds of the workload, its whole window each."""
+    refdrv = _refdrv()
+    _, desc = _example_desc(wl)
+    frames, worlds, spent = wl["window"], 0, 0.0
+    while spent < budget_s and worlds < 64:
         w = refdrv.RefWorld(flavour).load(desc)
-        spent += w.run_timed(frames, DT, SUBSTEPS, ITERS, True)
+        spent += w.run_timed(frames, DT, desc.substeps, desc.iters, desc.collisions)
         worlds += 1
     nb = len(desc.bodies)
-    return {"value": nb * SUBSTEPS * frames * worlds / spent, "unit": "body-substeps/s", "cores": 1,
+    return {"value": nb * desc.substeps * frames * worlds / spent, "unit": "body-substeps/s", "cores": 1,
             "kind": "reference" if flavour == "strict" else "port",
-            "sample": "%d fresh W256 worlds x first %d frames, one thread, %.1f s (%.2f ms/frame/world)" % (worlds, frames, spent, 1e3 * spent / (frames * worlds))}
+            "sample": "%d fresh %s worlds x first %d frames, one thread, %.1f s (%.3f ms/frame/world)" % (
+                worlds, wl["example"], frames, spent, 1e3 * spent / (frames * worlds))}
 
 
-def _ref_worker(flavour, frames_warm, frames, barrier, q):
-    import refdrv
-    import scenes
-    w = refdrv.RefWorld(flavour).load(scenes.w256())
+def _ref_worker(wl, flavour, frames_warm, frames, barrier, q):
+    refdrv = _refdrv()
+    _, desc = _example_desc(wl)
+    step = (DT, desc.substeps, desc.iters, desc.collisions)
+    w = refdrv.RefWorld(flavour).load(desc)
     barrier.wait()
     if frames_warm:
-        w.run_timed(frames_warm, DT, SUBSTEPS, ITERS, True)
-        w = refdrv.RefWorld(flavour).load(scenes.w256())  # same timed frames as the GPU arm
-    if lead_in(frames):
-        w.run_timed(lead_in(frames), DT, SUBSTEPS, ITERS, True)
+        w.run_timed(frames_warm, *step)
+        w = refdrv.RefWorld(flavour).load(desc)  # same timed frames as the GPU arm
+    if lead_in(wl, frames):
+        w.run_timed(lead_in(wl, frames), *step)
     barrier.wait()
     t0 = time.perf_counter()
-    w.run_timed(frames, DT, SUBSTEPS, ITERS, True)
+    w.run_timed(frames, *step)
     q.put(time.perf_counter() - t0)
 
 
@@ -174,36 +220,39 @@ def run_reference(args):
     """Reference arm: the unmodified reference (one world per process, it is single-threaded with global state) on every
     host core at once; a step = one frame of `cores` worlds."""
     import multiprocessing as mp
-    import refdrv
+    refdrv = _refdrv()
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = WORKLOADS[args.workload]
     flavour = "strict" if refdrv.available("strict") else "port"
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    _, desc = _example_desc(wl)  # (also builds / loads the library before forking)
     ctx = mp.get_context("fork")
     barrier = ctx.Barrier(cores)
     q = ctx.Queue()
-    procs = [ctx.Process(target=_ref_worker, args=(flavour, args.warmup, args.steps, barrier, q)) for _ in range(cores)]
+    procs = [ctx.Process(target=_ref_worker, args=(wl, flavour, args.warmup, args.steps, barrier, q)) for _ in range(cores)]
     for p in procs:
         p.start()
     times = [q.get() for _ in procs]
     for p in procs:
         p.join()
     elapsed = max(times)
-    nb = 257
-    value = nb * cores * SUBSTEPS * args.steps / elapsed
+    nb = len(desc.bodies)
+    value = nb * cores * desc.substeps * args.steps / elapsed
     line = {"impl": "reference", "metric": "body-substeps/sec", "value": value, "unit": "body-substeps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "w256 (256 cubes + floor), %d worlds (one per host core), %s" % (cores, window_text(args.steps)),
-                       "bodies_per_world": nb, "substeps": SUBSTEPS, "pos_iters": ITERS, "dt": DT},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s scene, %d worlds (one per host core), %s" % (args.workload, wl["example"], cores, window_text(wl, args.steps)),
+                       "bodies_per_world": nb, "substeps": desc.substeps, "pos_iters": desc.iters, "dt": DT},
             "cpu_baseline": {"value": value, "unit": "body-substeps/s", "cores": cores, "kind": "reference" if flavour == "strict" else "port",
-                             "sample": "%d processes x 1 W256 world x %d frames" % (cores, args.steps)},
+                             "sample": "%d processes x 1 world x %d frames" % (cores, args.steps)},
             "e2e": {"value": value, "unit": "body-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------ our arm
 def hetero_state(init, W, NB, stride, rank):
     """Every cube of every world gets its own yaw in +-0.3 rad and a lateral offset in +-0.2: contacts form at different
     times and with different manifolds in every world (no cross-world coherence for the lane = world work order)."""
@@ -219,11 +268,45 @@ def hetero_state(init, W, NB, stride, rank):
     return st
 
 
+def check_parity(wl, batch, frame, job, total_worlds, coloured):
+    """The state after `frame` frames from the initial poses: world 0 against the compiled reference's committed output for that
+    frame, every world of this rank against world 0, and one digest per world gathered over the process group (all equal:
+    a G-GPU run is the 1-GPU run, world for world). Returns the `parity` block."""
+    fname, key, tol = wl["golden"]
+    st = batch.state()
+    same = bool((st == st[0][None]).all())
+    out = {"checked": False, "frame": frame, "worlds_identical_on_rank": same}
+    gold_path = os.path.join(ROOT, "tests", "golden", fname)
+    if os.path.exists(gold_path) and not coloured:
+        z = np.load(gold_path)
+        if key % frame in z.files:
+            want = z[key % frame]
+            diff = float(np.abs(st[0, :, :7] - want[:, :7]).max())
+            out["golden"] = "tests/golden/%s:%s" % (fname, key % frame)
+            out["max_abs_pose_diff_vs_reference"] = diff
+            out["tolerance"] = tol
+            ok = np.array_equal(st[0, :, :15], want) if tol == 0.0 else diff <= tol
+            out["checked"] = True
+            out["world0_matches_reference"] = bool(ok)
+    elif coloured:
+        out["note"] = "graph-coloured order: not bit-comparable by construction (accepted on physical criteria, tests/test_gpu_coloured.py)"
+        out["finite"] = bool(np.isfinite(st).all())
+    dig = np.array([int.from_bytes(hashlib.blake2b(st[w].tobytes(), digest_size=8).digest(), "little") for w in range(st.shape[0])], dtype=np.uint64)
+    allw = job.gather_worlds(dig.view(np.int64), total_worlds)
+    if allw is not None:
+        out["worlds"] = int(allw.shape[0])
+        out["all_worlds_one_digest"] = bool((allw == allw[0]).all())
+        out["digest"] = "%016x" % int(np.uint64(allw[0]))
+    ok_all = job.sum_over_ranks([0.0 if (same and out.get("world0_matches_reference", True)) else 1.0])[0] == 0.0
+    out["ok"] = bool(ok_all and out.get("all_worlds_one_digest", True))
+    return out
+
+
 def run_ours(args):
     import torch
     import __graft_entry__ as ge
-    import scenes
     pkg = ge.load_package()
+    wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -237,13 +320,22 @@ def run_ours(args):
     from rawphys_b200 import multi
     job = multi.Job(dist, "cuda")  # worlds are sharded over ranks with no data-path collective; NCCL only aggregates
 
-    desc = scenes.w256()
-    scene = pkg.Scene(desc)
-    W = args.worlds
-    batch = pkg.Batch(scene, n_worlds=W, device=local_rank, disable_cull=args.no_cull)
+    scene, desc = pkg.example(wl["example"], wl["params"], perturb=wl["perturb"])
+    SUB, ITERS, COLL = desc.substeps, desc.iters, desc.collisions
+    if args.scaling == "strong":
+        total_worlds = args.worlds
+        first_world, W = job.my_worlds(total_worlds)
+    else:
+        W = args.worlds
+        total_worlds = W * world_size
+        first_world = rank * W
+    coloured = wl["coloured"]
+    kw = dict(device=local_rank, disable_cull=args.no_cull, coloured=coloured)
+    batch = pkg.Batch(scene, n_worlds=W, **kw)
     batch.set_scene_forces(desc)
     NB = batch.NB
-    init = batch.state(0, 1)[0].copy()
+    init = scene.initial_state()
+    step = (DT, SUB, ITERS, COLL)
 
     def barrier():
         torch.cuda.synchronize()
@@ -257,10 +349,10 @@ def run_ours(args):
     if args.ncu_frame >= 0:
         if args.hetero:
             batch.upload(hetero_state(init, W, NB, pkg.STATE_STRIDE, rank))
-        batch.run(max(args.ncu_frame, 1), DT, SUBSTEPS, ITERS, True)
+        batch.run(max(args.ncu_frame, 1), *step)
         barrier()
         torch.cuda.profiler.start()
-        batch.run(1, DT, SUBSTEPS, ITERS, True)
+        batch.run(1, *step)
         barrier()
         torch.cuda.profiler.stop()
         batch.close()
@@ -268,38 +360,65 @@ def run_ours(args):
 
     # ---- device-resident throughput
     for _ in range(args.warmup):
-        batch.step(DT, SUBSTEPS, ITERS, True)
+        batch.step(*step)
 
-    def rewind():
+    def rewind(b=batch, frames=None):
         """every world back to the initial poses, then the untimed lead-in frames"""
-        batch.broadcast(init)
-        for _ in range(lead_in(args.steps)):
-            batch.step(DT, SUBSTEPS, ITERS, True)
+        b.broadcast(init)
+        for _ in range(lead_in(wl, args.steps) if frames is None else frames):
+            b.step(*step)
 
     rewind()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    ms = batch.run(args.steps, DT, SUBSTEPS, ITERS, True)
+    ms = batch.run(args.steps, *step)
     barrier()
     clocks = sampler.stop()
     ms = max_over_ranks(ms)
-    units = NB * W * SUBSTEPS * args.steps * world_size
+    units = NB * total_worlds * SUB * args.steps
     value = units / (ms * 1e-3)
     status = batch.status()
-    # kernels launched in the timed region: per frame 7 prologue kernels + per substep reset, integrate, cull, transform,
-    # gjk, epa, manifold, ONE positional and ONE velocity sweep (cooperative grids that walk the dependency levels with grid
-    # barriers), + the end-of-frame derive and frame counter
-    launches_total = args.steps * (7 + SUBSTEPS * (7 + 2) + 2)
-
     line = {"metric": "body-substeps/sec", "value": value, "unit": "body-substeps/s", "n_gpus": world_size, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "w256x%d per GPU (256 cubes + floor per world), %s" % (W, window_text(args.steps)),
-                       "worlds_per_gpu": W, "bodies_per_world": NB, "substeps": SUBSTEPS, "pos_iters": ITERS, "dt": DT, "mode": "batched-worlds, reference Gauss-Seidel order (level schedule)",
-                       "l2": "per-GPU state %.0f MB + transformed hulls %.0f MB > 126 MB L2: inputs larger than L2, no flush" % (
-                           W * NB * 208 / 1e6, W * NB * 336 / 1e6)},
-            "clocks": clocks, "gpu_launches": launches_total, "status_bits": int(np.bitwise_or.reduce(status))}
+            "config": {"workload": (wl["text"] % (W if args.scaling == "weak" else total_worlds)) + (" in total, split over the GPUs" if args.scaling == "strong" else "") + ", " + window_text(wl, args.steps),
+                       "worlds_per_gpu": W, "worlds_total": total_worlds, "bodies_per_world": NB, "substeps": SUB, "pos_iters": ITERS, "dt": DT,
+                       "mode": "one large scene, graph-coloured Gauss-Seidel" if coloured else "batched-worlds, reference Gauss-Seidel order (level schedule)",
+                       "l2": "per-GPU state %.0f MB (read and written by every kernel of a substep) %s 126 MB L2%s" % (
+                           W * NB * 208 / 1e6, ">" if W * NB * 208 / 1e6 > 126 else "<",
+                           ": inputs larger than L2, no flush" if W * NB * 208 / 1e6 > 126 else "; every step rewrites it, no flush")},
+            "clocks": clocks, "gpu_launches": args.steps * batch.graph_kernels(), "status_bits": int(np.bitwise_or.reduce(status))}
+    parity_done = False
+    if lead_in(wl, args.steps) + args.steps == wl["window"]:
+        line["parity"] = check_parity(wl, batch, wl["window"], job, total_worlds, coloured)
+        parity_done = True
+
+    # ---- the whole window (frames 0..window-1), always: what a K < window run times is its heavy end
+    if args.steps == wl["window"]:
+        line["window"] = {"frames": wl["window"], "value": value, "ms_per_step": ms / args.steps, "note": "same run as `value`"}
+    else:
+        rewind(frames=0)
+        barrier()
+        wms = max_over_ranks(batch.run(wl["window"], *step))
+        barrier()
+        line["window"] = {"frames": wl["window"], "value": NB * total_worlds * SUB * wl["window"] / (wms * 1e-3), "ms_per_step": wms / wl["window"],
+                          "note": "frames 0..%d from the initial poses, device-timed like `value`" % (wl["window"] - 1)}
+        if not parity_done:
+            line["parity"] = check_parity(wl, batch, wl["window"], job, total_worlds, coloured)
+    line["parity_checked"] = bool(line["parity"].get("checked")) and bool(line["parity"].get("ok"))
+
+    if args.workload == "c3":
+        # the same scene in the reference's own constraint order (bit-exact, deep dependency chains), for the record
+        rb = pkg.Batch(scene, n_worlds=W, device=local_rank)
+        rb.set_scene_forces(desc)
+        rb.step(*step)
+        rb.broadcast(init)
+        rms = max_over_ranks(rb.run(wl["window"], *step))
+        line["reference_order"] = {"ms_per_step": rms / wl["window"], "value": NB * total_worlds * SUB * wl["window"] / (rms * 1e-3),
+                                   "parity": check_parity(wl, rb, wl["window"], job, total_worlds, False)}
+        line["parity_checked"] = bool(line["reference_order"]["parity"].get("ok")) and bool(line["reference_order"]["parity"].get("checked"))
+        rb.close()
 
     if not args.no_extras:
         # ---- end to end through the host-buffer call (pinned host state in and out every step)
@@ -308,18 +427,19 @@ def run_ours(args):
         h_out = torch.empty(nrec, dtype=torch.float64).pin_memory()
         h_in.copy_(torch.from_numpy(np.ascontiguousarray(np.broadcast_to(init[None], (W, NB, pkg.STATE_STRIDE))).reshape(-1)))
         for _ in range(min(args.warmup, 2)):
-            batch.step_host(h_in.data_ptr(), h_out.data_ptr(), DT, SUBSTEPS, ITERS, True)
+            batch.step_host(h_in.data_ptr(), h_out.data_ptr(), *step)
         rewind()
         h_in.copy_(torch.from_numpy(batch.state().reshape(-1)))  # the state the timed frames start from, in host memory
         barrier()
         t0 = time.perf_counter()
         a, b = h_in, h_out
         for _ in range(args.steps):
-            batch.step_host(a.data_ptr(), b.data_ptr(), DT, SUBSTEPS, ITERS, True)
+            batch.step_host(a.data_ptr(), b.data_ptr(), *step)
             a, b = b, a
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
-        line["e2e"] = {"value": units / e2e_s, "unit": "body-substeps/s", "h2d_bytes_per_step": nrec * 8, "d2h_bytes_per_step": nrec * 8,
+        bytes_step = int(job.sum_over_ranks([nrec * 8])[0])
+        line["e2e"] = {"value": units / e2e_s, "unit": "body-substeps/s", "h2d_bytes_per_step": bytes_step, "d2h_bytes_per_step": bytes_step,
                        "ms_per_step": 1e3 * e2e_s / args.steps, "api": "rp_batch_step_host (upload state, step, download state, sync)"}
 
         # ---- the same end-to-end loop with the worlds split over P sub-batches, each driven by its own host thread on its
@@ -329,21 +449,21 @@ def run_ours(args):
         if P > 1 and W % P == 0 and W // P >= 32:
             rewind()
             start_state = torch.from_numpy(batch.state().reshape(-1))
-            halves = [pkg.Batch(scene, n_worlds=W // P, device=local_rank, disable_cull=args.no_cull) for _ in range(P)]
+            halves = [pkg.Batch(scene, n_worlds=W // P, **kw) for _ in range(P)]
             for hb in halves:
                 hb.set_scene_forces(desc)
             part = nrec // P
             h_in.copy_(start_state)
             bufs = [(h_in[i * part:(i + 1) * part], h_out[i * part:(i + 1) * part]) for i in range(P)]
             for hb, (a, b) in zip(halves, bufs):
-                hb.step_host(a.data_ptr(), b.data_ptr(), DT, SUBSTEPS, ITERS, True)  # warm-up (graph capture)
+                hb.step_host(a.data_ptr(), b.data_ptr(), *step)  # warm-up (graph capture)
             h_in.copy_(start_state)
             gate = threading.Barrier(P + 1)
 
             def drive(hb, a, b):
                 gate.wait()
                 for _ in range(args.steps):
-                    hb.step_host(a.data_ptr(), b.data_ptr(), DT, SUBSTEPS, ITERS, True)
+                    hb.step_host(a.data_ptr(), b.data_ptr(), *step)
                     a, b = b, a
 
             threads = [threading.Thread(target=drive, args=(hb, a, b)) for hb, (a, b) in zip(halves, bufs)]
@@ -360,78 +480,81 @@ def run_ours(args):
             for hb in halves:
                 hb.close()
             single = dict(line["e2e"])
-            piped = {"value": units / piped_s, "unit": "body-substeps/s", "h2d_bytes_per_step": nrec * 8, "d2h_bytes_per_step": nrec * 8,
+            piped = {"value": units / piped_s, "unit": "body-substeps/s", "h2d_bytes_per_step": bytes_step, "d2h_bytes_per_step": bytes_step,
                      "ms_per_step": 1e3 * piped_s / args.steps, "status_bits": bits,
                      "api": "rp_batch_step_host on %d sub-batches of %d worlds from %d host threads (the copies of one overlap the kernels of the others)" % (P, W // P, P)}
+            # the faster form is the headline, the other is kept beside it under a fixed name (whichever N this is)
             if piped["value"] > single["value"] and bits == 0:
                 line["e2e"] = piped
-                line["e2e_single_batch"] = single
+                line["e2e_other_form"] = single
             else:
-                line["e2e_two_half_batches"] = piped
+                line["e2e_other_form"] = piped
 
         # ---- per-kernel device time over the same window + roofline of the dominant kernel
         rewind()
         barrier()
         c0 = batch.counters()
-        fam = batch.profile(args.steps, DT, SUBSTEPS, ITERS, True)
+        fam = batch.profile(args.steps, *step)
         c1 = batch.counters()
         tests = c1["pair_tests"] - c0["pair_tests"]
+        runs = c1["gjk_runs"] - c0["gjk_runs"]
         hits = c1["gjk_hits"] - c0["gjk_hits"]
         contacts = c1["contacts"] - c0["contacts"]
-        bs = NB * W * SUBSTEPS * args.steps
-        alg_bytes = {"integrate": BYTES["integrate"] * bs, "gjk": BYTES["gjk"] * tests,
+        bs = NB * W * SUB * args.steps
+        nj = len(desc.constraints) * W * SUB * args.steps * ITERS
+        alg_bytes = {"integrate": BYTES["integrate"] * bs, "gjk": BYTES["gjk"] * runs,
                      "epa": BYTES["epa"] * hits,
                      "manifold": BYTES["manifold"] * hits + BYTES["manifold_contact"] * contacts,
-                     "solve_pos": BYTES["solve_pos_pair"] * hits + BYTES["solve_contact"] * contacts,
+                     "solve_pos": BYTES["solve_pos_pair"] * hits + BYTES["solve_contact"] * contacts + BYTES["joint"] * nj,
                      "solve_vel": BYTES["solve_vel_pair"] * hits + BYTES["solve_contact_vel"] * contacts}
-        alg_flops = {"integrate": FLOPS["integrate"] * bs, "gjk": FLOPS["gjk"] * tests, "epa": FLOPS["epa"] * hits, "manifold": FLOPS["manifold"] * hits,
-                     "solve_pos": FLOPS["solve_pos_contact"] * contacts, "solve_vel": FLOPS["solve_vel_contact"] * contacts}
+        alg_flops = {"integrate": FLOPS["integrate"] * bs, "gjk": FLOPS["gjk"] * runs, "epa": FLOPS["epa"] * hits, "manifold": FLOPS["manifold"] * hits,
+                     "solve_pos": FLOPS["solve_pos_contact"] * contacts + FLOPS["joint"] * nj, "solve_vel": FLOPS["solve_vel_contact"] * contacts}
         total_ms = sum(fam.values())
-        top = max(fam, key=fam.get)
+        timed = {k: v for k, v in fam.items() if k in alg_bytes}
+        top = max(timed, key=timed.get)
         hbm_peak, hbm_src = measured_peaks()
         fp64_nofma, fp64_fma = pkg.measure_fp64_peak(local_rank)
-        launches = SUBSTEPS * args.steps if top in alg_bytes else args.steps
+        launches = SUB * args.steps
         line["kernels"] = {k: {"ms": round(v, 3), "share": round(v / total_ms, 4)} for k, v in fam.items()}
-        if top in alg_bytes:
-            gbs = alg_bytes[top] / (fam[top] * 1e-3) / 1e9
-            line["roofline"] = {"kernel": "k_" + top, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                                "traffic": ncu_traffic("k_" + top), "peak_source": hbm_src, "avg_launch_ms": fam[top] / launches,
-                                "note": "schema bound; the binding resource of this path is the FP64 CUDA-core pipe, see fp64"}
-            tf = alg_flops[top] / (fam[top] * 1e-3) / 1e12
-            line["fp64"] = {"kernel": "k_" + top, "achieved_tflops": tf, "peak_tflops_no_fma": fp64_nofma, "peak_tflops_fma": fp64_fma,
-                            "frac_of_no_fma_peak": tf / fp64_nofma,
-                            "whole_step_tflops": FLOP_PER_BODY_SUBSTEP * (NB * W * SUBSTEPS * args.steps) / (ms * 1e-3) / 1e12,
-                            "whole_step_frac": FLOP_PER_BODY_SUBSTEP * (NB * W * SUBSTEPS * args.steps) / (ms * 1e-3) / 1e12 / fp64_nofma,
-                            "peak_source": "rp_measure_fp64_peak (DMUL+DADD chains, this run)"}
-        line["work_per_world_substep"] = {"pair_tests": tests / (W * SUBSTEPS * args.steps), "epa_runs": hits / (W * SUBSTEPS * args.steps),
-                                          "contacts": contacts / (W * SUBSTEPS * args.steps)}
+        gbs = alg_bytes[top] / (fam[top] * 1e-3) / 1e9
+        traffic, capture = ncu_traffic("k_" + top)
+        line["roofline"] = {"kernel": "k_" + top, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                            "traffic": traffic, "traffic_capture": capture, "peak_source": hbm_src, "avg_launch_ms": fam[top] / launches,
+                            "note": "schema bound; this kernel is latency-bound on dependent FP64 chains, the binding pipe is FP64: see fp64"}
+        tf = alg_flops[top] / (fam[top] * 1e-3) / 1e12
+        whole = FLOP_PER_BODY_SUBSTEP * (NB * W * SUB * args.steps) / (ms * 1e-3) / 1e12
+        line["fp64"] = {"kernel": "k_" + top, "achieved_tflops": tf, "peak_tflops_no_fma": fp64_nofma, "peak_tflops_fma": fp64_fma,
+                        "frac_of_no_fma_peak": tf / fp64_nofma, "whole_step_tflops": whole, "whole_step_frac": whole / fp64_nofma,
+                        "peak_source": "rp_measure_fp64_peak (DMUL+DADD chains, this run)"}
+        per = W * SUB * args.steps
+        line["work_per_world_substep"] = {"pair_tests": tests / per, "gjk_runs": runs / per, "epa_runs": hits / per, "contacts": contacts / per}
         if dist is not None:  # NCCL only gathers aggregate statistics
             t = job.sum_over_ranks([tests, hits, contacts])
             line["aggregate_work"] = {"pair_tests": float(t[0]), "epa_runs": float(t[1]), "contacts": float(t[2])}
-        if args.hetero:
-            # The headline workload is BASELINE.json's: 4096 COPIES of one scene, so the lanes of a warp (same pair index,
+        if args.hetero and args.workload == "w256":
+            # The headline workload is BASELINE.json's: W COPIES of one scene, so the lanes of a warp (same pair index,
             # neighbouring worlds) follow the same control flow. This leg breaks that (hetero_state). Same kernels, same window.
             st = hetero_state(init, W, NB, pkg.STATE_STRIDE, rank)
             batch.upload(st)
-            for _ in range(lead_in(args.steps)):
-                batch.step(DT, SUBSTEPS, ITERS, True)
+            for _ in range(lead_in(wl, args.steps)):
+                batch.step(*step)
             barrier()
             c0 = batch.counters()
-            hms = max_over_ranks(batch.run(args.steps, DT, SUBSTEPS, ITERS, True))
+            hms = max_over_ranks(batch.run(args.steps, *step))
             barrier()
             c1 = batch.counters()
             batch.upload(st)
-            for _ in range(lead_in(args.steps)):
-                batch.step(DT, SUBSTEPS, ITERS, True)
-            hfam = batch.profile(args.steps, DT, SUBSTEPS, ITERS, True)
+            for _ in range(lead_in(wl, args.steps)):
+                batch.step(*step)
+            hfam = batch.profile(args.steps, *step)
             line["heterogeneous"] = {"value": units / (hms * 1e-3), "unit": "body-substeps/s", "ms_per_step": hms / args.steps,
                                      "status_bits": int(np.bitwise_or.reduce(batch.status())),
                                      "kernels_ms": {k: round(v, 1) for k, v in hfam.items()},
-                                     "contacts_per_world_substep": (c1["contacts"] - c0["contacts"]) / (W * SUBSTEPS * args.steps),
+                                     "contacts_per_world_substep": (c1["contacts"] - c0["contacts"]) / (W * SUB * args.steps),
                                      "note": "every world started from its own poses (per-cube yaw +-0.3 rad, offset +-0.2): no cross-world coherence"}
         if rank == 0 and world_size == 1 and not args.no_cpu:
-            import refdrv
-            line["cpu_baseline"] = cpu_single_thread_baseline("strict" if refdrv.available("strict") else "port")
+            refdrv = _refdrv()
+            line["cpu_baseline"] = cpu_single_thread_baseline(wl, "strict" if refdrv.available("strict") else "port")
 
     if rank == 0:
         print(json.dumps(line), flush=True)

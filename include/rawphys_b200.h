@@ -103,6 +103,38 @@ int rp_scene_hull_sizes(const rp_scene* s, int body, int collider, int32_t out6[
 int rp_scene_hull_dump(const rp_scene* s, int body, int collider, double* verts, double* normals, uint32_t* face_ptr, uint32_t* face_idx,
 	uint32_t* v2f_ptr, uint32_t* v2f_idx, uint32_t* v2n_ptr, uint32_t* v2n_idx, uint32_t* f2n_ptr, uint32_t* f2n_idx);
 
+/* The scene as it was described -- what a caller needs to build the same scene somewhere else (the parity tests feed the
+ * oracle with it). body_desc: position[3], rotation xyzw[4], mass, fixed, static friction, dynamic friction, restitution,
+ * number of colliders, 3 reserved. A sphere collider reports nverts = nidx = 0 and its radius; a hull its input soup.
+ * joint_desc: ints = type (Constraint_Type, pbd.h:14-20), e1, e2, limited, the four axis selectors; vals = r1_lc[3], r2_lc[3],
+ * distance[3], compliance, lower, upper, lower2, upper2. initial_state: RP_STATE_STRIDE doubles per body. */
+int rp_scene_initial_state(const rp_scene* s, double* out);
+int rp_scene_body_desc(const rp_scene* s, int body, double out16[16]);
+int rp_scene_collider_soup_size(const rp_scene* s, int body, int collider, uint32_t* nverts, uint32_t* nidx, float* radius);
+int rp_scene_collider_soup(const rp_scene* s, int body, int collider, double* verts_xyz, uint32_t* indices);
+int rp_scene_num_joints(const rp_scene* s);
+int rp_scene_joint_desc(const rp_scene* s, int joint, int32_t ints8[8], double vals14[14]);
+
+/* ---------------------------------------------------------------------------------------------------- built-in scenes */
+/* The init() halves of the reference's 14 examples (src/examples/<name>.cpp) and the benchmark worlds built from the same
+ * pieces ("w256", "pile", "tumble", "spheres"), as scene templates; `info` receives what the example's update() passes to
+ * pbd_simulate (substeps, positional iterations, collisions) and its gravity. `params` (optional, 0 = default) per scene:
+ * stack {cubes}; w256 {stacks_x, stacks_z, height}; brick_wall {rows, cols}; cube_storm {n}; spot_storm {n, seed};
+ * pile {n_side, seed, spacing}; tumble {n, seed}; spheres {n}. `perturb` != 0 gives the joint scenes (hinge_joints, arm,
+ * triple_pendula, rott_pendulum), which are at rest until a user interacts, initial angular velocities. `mesh_dir` = directory of
+ * the <mesh>.f32 triangle soups (NULL: assets/meshes next to the library). Returns NULL on failure (rp_example_error()). */
+typedef struct {
+	uint32_t substeps, pos_iters;
+	int32_t collisions;
+	int32_t reserved0;
+	double gravity;
+} rp_example_info;
+int rp_example_count(void);
+const char* rp_example_name(int index);
+const char* rp_example_error(void);
+rp_scene* rp_example_create(const char* name, const double* params, uint32_t n_params, int perturb, const char* mesh_dir_or_null,
+	rp_example_info* info_or_null);
+
 /* ------------------------------------------------------------------------------------------------------- batches */
 /* Order of the Gauss-Seidel sweeps over a world's constraints (rp_batch_cfg.solve_order).
  * RP_ORDER_REFERENCE: the reference's array order (external constraints, then contacts in broadphase-pair order,
@@ -143,7 +175,14 @@ int rp_batch_add_gravity(rp_batch* b, double g);
  * substeps -- is enqueued on the batch's CUDA stream as ONE graph launch (captured once per (dt, substeps, iters,
  * collisions)) and the call returns without waiting for it; nothing about the frame is read back by the host. */
 int rp_batch_step(rp_batch* b, double dt, uint32_t num_substeps, uint32_t num_pos_iters, int enable_collisions);
+/* Waits for the batch's stream. Returns RP_ERR_CAPACITY if a fixed-capacity device buffer (broadphase pairs, contacts per
+ * substep: rp_batch_cfg, defaults max(128, 2 * pairs of the initial poses + 64) pairs and max(256, 8 * bodies) contacts per
+ * world) ran out in some world since creation or the last rp_batch_clear_status: pairs / contacts were dropped there and the
+ * world no longer follows the reference (rp_batch_get_status says which). rp_batch_step_host and rp_batch_download_state
+ * report the same way, after doing their work. */
 int rp_batch_sync(rp_batch* b);
+/* kernel nodes of the CUDA graph one rp_batch_step launches (0 before the first step) */
+int rp_batch_graph_kernels(const rp_batch* b);
 /* `frames` consecutive steps timed on the device with CUDA events on the batch's stream (milliseconds). */
 int rp_batch_run(rp_batch* b, uint32_t frames, double dt, uint32_t num_substeps, uint32_t num_pos_iters, int enable_collisions,
 	float* gpu_ms_out);

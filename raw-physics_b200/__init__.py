@@ -31,7 +31,8 @@ EXPORTS = [
     "rp_batch_num_bodies", "rp_batch_clear_forces", "rp_batch_add_force", "rp_batch_add_gravity", "rp_batch_step", "rp_batch_sync",
     "rp_batch_run", "rp_batch_upload_state", "rp_batch_download_state", "rp_batch_broadcast_state", "rp_batch_step_host",
     "rp_batch_get_status", "rp_batch_clear_status", "rp_batch_get_counters", "rp_batch_step_logged", "rp_batch_broad_pairs", "rp_batch_profile",
-    "rp_measure_fp64_peak",
+    "rp_measure_fp64_peak", "rp_scene_initial_state", "rp_scene_body_desc", "rp_scene_collider_soup_size", "rp_scene_collider_soup",
+    "rp_scene_num_joints", "rp_scene_joint_desc", "rp_batch_graph_kernels", "rp_example_count", "rp_example_name", "rp_example_error", "rp_example_create",
 ]
 KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "cull", "gjk", "manifold", "solve_pos", "derive", "solve_vel", "epa"]
 
@@ -42,8 +43,16 @@ class BatchCfg(C.Structure):
                 ("linear_sleeping_threshold", C.c_double), ("angular_sleeping_threshold", C.c_double), ("deactivation_time", C.c_double)]
 
 
+class ExampleInfo(C.Structure):
+    _fields_ = [("substeps", C.c_uint32), ("pos_iters", C.c_uint32), ("collisions", C.c_int32), ("reserved0", C.c_int32), ("gravity", C.c_double)]
+
+
 class RawPhysError(RuntimeError):
     pass
+
+
+class RawPhysCapacityError(RawPhysError):
+    """RP_ERR_CAPACITY: a fixed-capacity device buffer ran out in some world (pairs / contacts were dropped there)"""
 
 
 _lib = None
@@ -86,6 +95,7 @@ def lib():
     L.rp_batch_add_gravity.argtypes = [C.c_void_p, C.c_double]
     L.rp_batch_step.argtypes = [C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_int]
     L.rp_batch_sync.argtypes = [C.c_void_p]
+    L.rp_batch_graph_kernels.argtypes = [C.c_void_p]
     L.rp_batch_run.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_float)]
     L.rp_batch_upload_state.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     L.rp_batch_download_state.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
@@ -99,13 +109,25 @@ def lib():
     L.rp_batch_broad_pairs.argtypes = [C.c_void_p, C.c_uint32, _u32p, C.c_uint32, _u32p]
     L.rp_batch_profile.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_float)]
     L.rp_measure_fp64_peak.argtypes = [C.c_int, _dp]
+    L.rp_scene_initial_state.argtypes = [C.c_void_p, _dp]
+    L.rp_scene_body_desc.argtypes = [C.c_void_p, C.c_int, _dp]
+    L.rp_scene_collider_soup_size.argtypes = [C.c_void_p, C.c_int, C.c_int, _u32p, _u32p, C.POINTER(C.c_float)]
+    L.rp_scene_collider_soup.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _u32p]
+    L.rp_scene_num_joints.argtypes = [C.c_void_p]
+    L.rp_scene_joint_desc.argtypes = [C.c_void_p, C.c_int, _i32p, _dp]
+    L.rp_example_name.restype = C.c_char_p
+    L.rp_example_name.argtypes = [C.c_int]
+    L.rp_example_error.restype = C.c_char_p
+    L.rp_example_create.restype = C.c_void_p
+    L.rp_example_create.argtypes = [C.c_char_p, _dp, C.c_uint32, C.c_int, C.c_char_p, C.POINTER(ExampleInfo)]
     _lib = L
     return L
 
 
 def _check(rc, what):
     if rc != 0:
-        raise RawPhysError("%s failed (code %d): %s" % (what, rc, lib().rp_last_error().decode()))
+        cls = RawPhysCapacityError if rc == 3 else RawPhysError
+        raise cls("%s failed (code %d): %s" % (what, rc, lib().rp_last_error().decode()))
 
 
 def _d(a):
@@ -120,13 +142,50 @@ def _vec(x):
     return np.ascontiguousarray(x, dtype=np.float64)
 
 
+class ColliderDescPy:
+    def __init__(self, kind, vertices, indices, radius):
+        self.kind, self.vertices, self.indices, self.radius = kind, vertices, indices, radius
+
+
+class BodyDescPy:
+    def __init__(self, position, rotation, mass, fixed, colliders, mu_s, mu_d, restitution):
+        self.position, self.rotation, self.mass, self.fixed, self.colliders = position, rotation, mass, fixed, colliders
+        self.mu_s, self.mu_d, self.restitution = mu_s, mu_d, restitution
+
+
+class SceneDesc:
+    """A scene description with the attribute names of tests/scenes.py's Scene (see Scene.describe)."""
+
+    def __init__(self, name, substeps=20, iters=1, collisions=True, gravity=10.0):
+        self.name, self.substeps, self.iters, self.collisions, self.gravity = name, substeps, iters, collisions, gravity
+        self.bodies, self.constraints, self.forces, self.initial_state = [], [], [], None
+
+
+def example_names():
+    L = lib()
+    return [L.rp_example_name(i).decode() for i in range(L.rp_example_count())]
+
+
+def example(name, params=(), perturb=False, mesh_dir=None):
+    """A built-in scene (rp_example_create): -> (Scene, SceneDesc). The description carries the example's own step settings
+    (what its update() passes to pbd_simulate) and can be loaded into the oracle."""
+    L = lib()
+    p = np.ascontiguousarray(params, dtype=np.float64)
+    info = ExampleInfo()
+    h = L.rp_example_create(name.encode(), _d(p) if p.size else None, int(p.size), int(perturb), mesh_dir.encode() if mesh_dir else None, C.byref(info))
+    if not h:
+        raise RawPhysError("rp_example_create(%r): %s" % (name, L.rp_example_error().decode()))
+    sc = Scene(handle=h)
+    return sc, sc.describe(name, int(info.substeps), int(info.pos_iters), bool(info.collisions), float(info.gravity))
+
+
 class Scene:
     """Scene template (rp_scene). `desc` is a description object with .bodies (position, rotation xyzw, mass, fixed,
     colliders[kind, vertices, indices, radius], mu_s, mu_d, restitution) and .constraints (dicts), as tests/scenes.py builds."""
 
-    def __init__(self, desc=None):
+    def __init__(self, desc=None, handle=None):
         self.L = lib()
-        self.h = C.c_void_p(self.L.rp_scene_create())
+        self.h = C.c_void_p(handle if handle is not None else self.L.rp_scene_create())
         if desc is not None:
             self.load(desc)
 
@@ -174,6 +233,55 @@ class Scene:
     @property
     def n(self):
         return int(self.L.rp_scene_num_bodies(self.h))
+
+    def initial_state(self):
+        """[n, STATE_STRIDE] records the worlds of a batch start from"""
+        out = np.zeros((self.n, STATE_STRIDE))
+        _check(self.L.rp_scene_initial_state(self.h, _d(out)), "rp_scene_initial_state")
+        return out
+
+    def describe(self, name="scene", substeps=20, iters=1, collisions=True, gravity=10.0):
+        """The scene as a description object with the attributes of tests/scenes.py's Scene (bodies with their collider soups,
+        constraint dicts, step settings, initial state): what refdrv.RefWorld.load() and Scene.load() take."""
+        L = self.L
+        d = SceneDesc(name=name, substeps=substeps, iters=iters, collisions=collisions, gravity=gravity)
+        for b in range(self.n):
+            o = np.zeros(16)
+            _check(L.rp_scene_body_desc(self.h, b, _d(o)), "rp_scene_body_desc")
+            cols = []
+            for c in range(int(o[12])):
+                nv, ni, rad = C.c_uint32(), C.c_uint32(), C.c_float()
+                _check(L.rp_scene_collider_soup_size(self.h, b, c, C.byref(nv), C.byref(ni), C.byref(rad)), "rp_scene_collider_soup_size")
+                if nv.value == 0:
+                    cols.append(ColliderDescPy("sphere", None, None, float(rad.value)))
+                else:
+                    v = np.zeros((nv.value, 3))
+                    idx = np.zeros(ni.value, dtype=np.uint32)
+                    _check(L.rp_scene_collider_soup(self.h, b, c, _d(v), _u(idx)), "rp_scene_collider_soup")
+                    cols.append(ColliderDescPy("hull", v, idx, 0.0))
+            d.bodies.append(BodyDescPy(tuple(o[0:3]), tuple(o[3:7]), float(o[7]), bool(o[8]), cols, float(o[9]), float(o[10]), float(o[11])))
+        names = ["e1_aligned", "e2_aligned", "e1_limit", "e2_limit"]
+        for j in range(int(L.rp_scene_num_joints(self.h))):
+            iv = np.zeros(8, dtype=np.int32)
+            dv = np.zeros(14)
+            _check(L.rp_scene_joint_desc(self.h, j, iv.ctypes.data_as(_i32p), _d(dv)), "rp_scene_joint_desc")
+            t, e1, e2 = int(iv[0]), int(iv[1]), int(iv[2])
+            r1, r2 = tuple(dv[0:3]), tuple(dv[3:6])
+            if t == 0:
+                c = dict(type="positional", e1=e1, e2=e2, r1=r1, r2=r2, compliance=float(dv[9]), distance=tuple(dv[6:9]))
+            elif t == 2:
+                c = dict(type="mutual_orientation", e1=e1, e2=e2, compliance=float(dv[9]))
+            elif t == 3:
+                c = dict(type="hinge", e1=e1, e2=e2, r1=r1, r2=r2, compliance=float(dv[9]), limited=bool(iv[3]), lower=float(dv[10]), upper=float(dv[11]))
+                c.update({k: int(iv[4 + i]) for i, k in enumerate(names)})
+            else:
+                c = dict(type="spherical", e1=e1, e2=e2, r1=r1, r2=r2, e1_swing=int(iv[4]), e2_swing=int(iv[5]), e1_twist=int(iv[6]), e2_twist=int(iv[7]),
+                         swing_lower=float(dv[10]), swing_upper=float(dv[11]), twist_lower=float(dv[12]), twist_upper=float(dv[13]))
+            d.constraints.append(c)
+        st = self.initial_state()
+        if np.any(st[:, 7:13] != 0.0):
+            d.initial_state = st[:, :15].copy()
+        return d
 
     def params(self):
         out = np.zeros((self.n, PARAM_STRIDE))
@@ -253,11 +361,22 @@ class Batch:
         _check(self.L.rp_batch_run(self.h, frames, dt, substeps, iters, int(collisions), C.byref(ms)), "rp_batch_run")
         return float(ms.value)
 
-    def state(self, first=0, n=None):
+    def state(self, first=0, n=None, ignore_capacity=False):
+        """[n, NB, STATE_STRIDE] records. Raises RawPhysCapacityError if some world ran out of pair / contact capacity since the
+        last clear_status() (its trajectory no longer follows the reference) unless `ignore_capacity`."""
         n = self.W - first if n is None else n
         out = np.zeros((n, self.NB, STATE_STRIDE))
-        _check(self.L.rp_batch_download_state(self.h, first, n, out.ctypes.data), "rp_batch_download_state")
+        rc = self.L.rp_batch_download_state(self.h, first, n, out.ctypes.data)
+        if not (rc == 3 and ignore_capacity):
+            _check(rc, "rp_batch_download_state")
         return out
+
+    def graph_kernels(self):
+        """kernel launches inside the CUDA graph of one step()"""
+        return int(self.L.rp_batch_graph_kernels(self.h))
+
+    def clear_status(self):
+        _check(self.L.rp_batch_clear_status(self.h), "rp_batch_clear_status")
 
     def upload(self, state, first=0):
         st = np.ascontiguousarray(state, dtype=np.float64).reshape(-1, self.NB, STATE_STRIDE)

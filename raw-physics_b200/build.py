@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librawphys_b200.so")
-SOURCES = [os.path.join(CSRC, "rp_batch.cu"), os.path.join(CSRC, "rp_scene.cpp")]
+SOURCES = [os.path.join(CSRC, "rp_batch.cu"), os.path.join(CSRC, "rp_scene.cpp"), os.path.join(CSRC, "rp_examples.cpp")]
 HEADERS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cuh"))] + [
     os.path.join(os.path.dirname(HERE), "include", "rawphys_b200.h")]
 

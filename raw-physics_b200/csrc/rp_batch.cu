@@ -35,10 +35,6 @@ static int fail(int code, const std::string& msg) {
 #endif
 #define RP_SCHED_SMEM_MAX (160 * 1024)  // dynamic shared memory k_schedule<true> may ask for (opted in at batch creation)
 
-struct rp_scene {
-	Scene s;
-};
-
 struct GraphKey {
 	double dt;
 	uint32_t substeps, iters;
@@ -72,6 +68,9 @@ struct rp_batch {
 	int sweep_wpb = 0;            // worlds per CTA of the world-block sweeps (k_solve_block); 0 = level-major cooperative sweeps
 	size_t sweep_smem = 0;        // dynamic shared memory of k_solve_block (its per-level cursors)
 	std::vector<int> joint_level;  // template-constant levels of the external constraints
+	int* overflow_dev = 0;        // [1] OR of the capacity bits of every world's status word (k_status_overflow)
+	int* overflow_pin = 0;        // pinned host copy
+	int graph_kernels = 0;        // kernel nodes of the captured frame graph
 	bool have_graph = false;
 	GraphKey graph_key;
 	cudaGraph_t graph = 0;
@@ -116,6 +115,20 @@ static cudaError_t launch_cooperative(void (*kernel)(Args...), unsigned int grid
 	return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+static std::vector<double> initial_records(const Scene& s) {
+	std::vector<double> rec(s.bodies.size() * RP_STATE_STRIDE, 0.0);
+	for (size_t i = 0; i < s.bodies.size(); ++i) {
+		double* r = &rec[i * RP_STATE_STRIDE];
+		const BodyInit& b = s.bodies[i];
+		r[0] = b.x.x; r[1] = b.x.y; r[2] = b.x.z;
+		r[3] = b.q.x; r[4] = b.q.y; r[5] = b.q.z; r[6] = b.q.w;
+		r[7] = b.v0.x; r[8] = b.v0.y; r[9] = b.v0.z;
+		r[10] = b.w0.x; r[11] = b.w0.y; r[12] = b.w0.z;
+		r[13] = 1.0;  // entity->active = true (entity.cpp:50)
+	}
+	return rec;
+}
+
 extern "C" {
 
 const char* rp_last_error(void) { return g_err.c_str(); }
@@ -146,6 +159,8 @@ int rp_scene_collider_sphere(rp_scene* s, float radius) {
 }
 int rp_scene_add_body(rp_scene* s, const double pos[3], const double quat[4], double mass, int fixed, double mu_s, double mu_d, double rest) {
 	if (!s || !pos || !quat) return -1;
+	// the reference would divide by a zero mass / invert a singular tensor silently (entity.cpp:40-47): refused here
+	if (!fixed && !(mass > 0.0)) return -1;
 	return s->s.add_body(pos, quat, mass, fixed, mu_s, mu_d, rest);
 }
 
@@ -188,8 +203,9 @@ int rp_scene_add_body_params(rp_scene* s, const double pos[3], const double quat
 }
 
 static bool valid_pair(const rp_scene* s, int e1, int e2) {
+	if (!s) return false;
 	int n = (int)s->s.bodies.size();
-	return s && e1 >= 0 && e2 >= 0 && e1 < n && e2 < n && e1 != e2;
+	return e1 >= 0 && e2 >= 0 && e1 < n && e2 < n && e1 != e2;
 }
 static V3 vec(const double* p) { return v3(p[0], p[1], p[2]); }
 static Joint blank_joint(int type, int e1, int e2) {
@@ -200,7 +216,7 @@ static Joint blank_joint(int type, int e1, int e2) {
 }
 
 int rp_scene_add_positional_constraint(rp_scene* s, int e1, int e2, const double r1[3], const double r2[3], double compliance, const double dist[3]) {
-	if (!s || !valid_pair(s, e1, e2)) return -1;
+	if (!s || !valid_pair(s, e1, e2) || !r1 || !r2 || !dist) return -1;
 	Joint j = blank_joint(JOINT_POSITIONAL, e1, e2);
 	j.r1_lc = vec(r1); j.r2_lc = vec(r2); j.compliance = compliance; j.distance = vec(dist);
 	s->s.joints.push_back(j);
@@ -215,7 +231,7 @@ int rp_scene_add_mutual_orientation_constraint(rp_scene* s, int e1, int e2, doub
 }
 int rp_scene_add_hinge_joint_constraint(rp_scene* s, int e1, int e2, const double r1[3], const double r2[3], double compliance, int a1, int a2,
 	int limited, int l1, int l2, double lower, double upper) {
-	if (!s || !valid_pair(s, e1, e2)) return -1;
+	if (!s || !valid_pair(s, e1, e2) || !r1 || !r2 || a1 < 0 || a1 > 5 || a2 < 0 || a2 > 5 || l1 < 0 || l1 > 5 || l2 < 0 || l2 > 5) return -1;
 	Joint j = blank_joint(JOINT_HINGE, e1, e2);
 	j.r1_lc = vec(r1); j.r2_lc = vec(r2); j.compliance = compliance;
 	j.axis[0] = a1; j.axis[1] = a2; j.axis[2] = l1; j.axis[3] = l2;
@@ -225,7 +241,7 @@ int rp_scene_add_hinge_joint_constraint(rp_scene* s, int e1, int e2, const doubl
 }
 int rp_scene_add_spherical_joint_constraint(rp_scene* s, int e1, int e2, const double r1[3], const double r2[3], int sw1, int sw2, int tw1,
 	int tw2, double swing_lower, double swing_upper, double twist_lower, double twist_upper) {
-	if (!s || !valid_pair(s, e1, e2)) return -1;
+	if (!s || !valid_pair(s, e1, e2) || !r1 || !r2 || sw1 < 0 || sw1 > 5 || sw2 < 0 || sw2 > 5 || tw1 < 0 || tw1 > 5 || tw2 < 0 || tw2 > 5) return -1;
 	Joint j = blank_joint(JOINT_SPHERICAL, e1, e2);
 	j.r1_lc = vec(r1); j.r2_lc = vec(r2);
 	j.axis[0] = sw1; j.axis[1] = sw2; j.axis[2] = tw1; j.axis[3] = tw2;
@@ -267,6 +283,7 @@ static const HullHost* find_hull(const rp_scene* s, int body, int collider, bool
 }
 
 int rp_scene_hull_sizes(const rp_scene* s, int body, int collider, int32_t out6[6]) {
+	if (!out6) return RP_ERR_ARG;
 	bool sphere;
 	const HullHost* h = find_hull(s, body, collider, &sphere);
 	if (sphere) {
@@ -287,13 +304,67 @@ int rp_scene_hull_dump(const rp_scene* s, int body, int collider, double* verts,
 	uint32_t* v2f_ptr, uint32_t* v2f_idx, uint32_t* v2n_ptr, uint32_t* v2n_idx, uint32_t* f2n_ptr, uint32_t* f2n_idx) {
 	bool sphere;
 	const HullHost* h = find_hull(s, body, collider, &sphere);
-	if (!h) return RP_ERR_ARG;
+	if (!h || !verts || !normals || !face_ptr || !face_idx || !v2f_ptr || !v2f_idx || !v2n_ptr || !v2n_idx || !f2n_ptr || !f2n_idx) return RP_ERR_ARG;
 	memcpy(verts, h->verts.data(), sizeof(V3) * h->verts.size());
 	memcpy(normals, h->normals.data(), sizeof(V3) * h->normals.size());
 	copy_u32(h->face_ptr, face_ptr); copy_u32(h->face_idx, face_idx);
 	copy_u32(h->v2f_ptr, v2f_ptr); copy_u32(h->v2f_idx, v2f_idx);
 	copy_u32(h->v2n_ptr, v2n_ptr); copy_u32(h->v2n_idx, v2n_idx);
 	copy_u32(h->f2n_ptr, f2n_ptr); copy_u32(h->f2n_idx, f2n_idx);
+	return RP_OK;
+}
+
+// the scene as it was described: what a caller needs to build the same scene elsewhere (the tests feed the oracle with it)
+int rp_scene_initial_state(const rp_scene* s, double* out) {
+	if (!s || !out) return RP_ERR_ARG;
+	const std::vector<double> rec = initial_records(s->s);
+	memcpy(out, rec.data(), rec.size() * sizeof(double));
+	return RP_OK;
+}
+int rp_scene_body_desc(const rp_scene* s, int body, double out[16]) {
+	if (!s || !out || body < 0 || body >= (int)s->s.bodies.size()) return RP_ERR_ARG;
+	const BodyInit& b = s->s.bodies[body];
+	const double v[16] = {b.x.x, b.x.y, b.x.z, b.q.x, b.q.y, b.q.z, b.q.w, b.mass, b.fixed ? 1.0 : 0.0, b.mu_s, b.mu_d, b.rest, (double)b.ncol, 0, 0, 0};
+	memcpy(out, v, sizeof(v));
+	return RP_OK;
+}
+int rp_scene_collider_soup_size(const rp_scene* s, int body, int collider, uint32_t* nverts, uint32_t* nidx, float* radius) {
+	if (!s || !nverts || !nidx || !radius || body < 0 || body >= (int)s->s.bodies.size()) return RP_ERR_ARG;
+	const BodyInit& b = s->s.bodies[body];
+	if (collider < 0 || collider >= b.ncol) return RP_ERR_ARG;
+	const ColliderDesc& c = s->s.colliders[b.col0 + collider];
+	*radius = c.radius;
+	if (c.type != SHAPE_HULL) {
+		*nverts = *nidx = 0;
+		return RP_OK;
+	}
+	const HullHost& h = s->s.hulls[c.hull];
+	*nverts = (uint32_t)(h.key.size() / 3);
+	*nidx = (uint32_t)h.key_idx.size();
+	return RP_OK;
+}
+int rp_scene_collider_soup(const rp_scene* s, int body, int collider, double* verts, uint32_t* idx) {
+	bool sphere;
+	const HullHost* h = 0;
+	if (s && body >= 0 && body < (int)s->s.bodies.size()) {
+		const BodyInit& b = s->s.bodies[body];
+		if (collider >= 0 && collider < b.ncol && s->s.colliders[b.col0 + collider].type == SHAPE_HULL) h = &s->s.hulls[s->s.colliders[b.col0 + collider].hull];
+	}
+	(void)sphere;
+	if (!h || !verts || !idx) return RP_ERR_ARG;
+	memcpy(verts, h->key.data(), h->key.size() * sizeof(double));
+	memcpy(idx, h->key_idx.data(), h->key_idx.size() * sizeof(uint32_t));
+	return RP_OK;
+}
+int rp_scene_num_joints(const rp_scene* s) { return s ? (int)s->s.joints.size() : -1; }
+int rp_scene_joint_desc(const rp_scene* s, int joint, int32_t ints[8], double vals[14]) {
+	if (!s || !ints || !vals || joint < 0 || joint >= (int)s->s.joints.size()) return RP_ERR_ARG;
+	const Joint& j = s->s.joints[joint];
+	const int32_t iv[8] = {j.type, j.e1, j.e2, j.limited, j.axis[0], j.axis[1], j.axis[2], j.axis[3]};
+	const double dv[14] = {j.r1_lc.x, j.r1_lc.y, j.r1_lc.z, j.r2_lc.x, j.r2_lc.y, j.r2_lc.z, j.distance.x, j.distance.y, j.distance.z, j.compliance,
+		j.lower, j.upper, j.lower2, j.upper2};
+	memcpy(ints, iv, sizeof(iv));
+	memcpy(vals, dv, sizeof(dv));
 	return RP_OK;
 }
 
@@ -315,21 +386,10 @@ void rp_batch_destroy(rp_batch* b) {
 	for (size_t i = 0; i < b->allocs.size(); ++i) cudaFree(b->allocs[i]);
 	if (b->ev0) cudaEventDestroy(b->ev0);
 	if (b->ev1) cudaEventDestroy(b->ev1);
+	if (b->overflow_pin) cudaFreeHost(b->overflow_pin);
 	if (b->stream) cudaStreamDestroy(b->stream);
 	cudaGetLastError();
 	delete b;
-}
-
-static std::vector<double> initial_records(const Scene& s) {
-	std::vector<double> rec(s.bodies.size() * RP_STATE_STRIDE, 0.0);
-	for (size_t i = 0; i < s.bodies.size(); ++i) {
-		double* r = &rec[i * RP_STATE_STRIDE];
-		const BodyInit& b = s.bodies[i];
-		r[0] = b.x.x; r[1] = b.x.y; r[2] = b.x.z;
-		r[3] = b.q.x; r[4] = b.q.y; r[5] = b.q.z; r[6] = b.q.w;
-		r[13] = 1.0;  // entity->active = true (entity.cpp:50)
-	}
-	return rec;
 }
 
 static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, const rp_batch_cfg* cfg_in, rp_batch* b) {
@@ -615,6 +675,9 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.counters, 8))) return rc;
 	if ((rc = dev_alloc(b, &d.dbg_points, 2 * (size_t)d.max_contacts, false))) return rc;
 	if ((rc = dev_alloc(b, &b->rec_dev, WB * RP_STATE_STRIDE, false))) return rc;
+	if ((rc = dev_alloc(b, &b->overflow_dev, 1))) return rc;
+	RP_CUDA(cudaMallocHost((void**)&b->overflow_pin, sizeof(int)));
+	*b->overflow_pin = 0;
 
 	std::vector<double> rec = initial_records(s);
 	RP_CUDA(cudaMemcpyAsync(b->rec_dev, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
@@ -799,6 +862,9 @@ int rp_batch_step(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int
 		cudaError_t e = cudaStreamEndCapture(b->stream, &b->graph);
 		if (e != cudaSuccess) return fail(RP_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
 		RP_CUDA(cudaGraphInstantiate(&b->graph_exec, b->graph, 0));
+		size_t nodes = 0;
+		RP_CUDA(cudaGraphGetNodes(b->graph, 0, &nodes));
+		b->graph_kernels = (int)nodes;
 		b->graph_key = key;
 		b->have_graph = true;
 	}
@@ -806,13 +872,35 @@ int rp_batch_step(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int
 	return RP_OK;
 }
 
+// A fixed-capacity device buffer that ran out (broadphase pairs, contacts, the full-size polytope / clip stores) drops work:
+// the worlds concerned carry the bit in their status word, and every call that synchronises with the device reports it --
+// rp_batch_sync, rp_batch_step_host, rp_batch_download_state return RP_ERR_CAPACITY (after doing their work: the state is
+// downloaded, the stream is idle) until rp_batch_clear_status. Costs one tiny kernel and a 4-byte copy per synchronising call.
+static int enqueue_overflow_check(rp_batch* b) {
+	RP_CUDA(cudaMemsetAsync(b->overflow_dev, 0, sizeof(int), b->stream));
+	k_status_overflow<<<(unsigned int)((b->d.W + 255) / 256), 256, 0, b->stream>>>(b->d, b->overflow_dev);
+	RP_CUDA(cudaGetLastError());
+	RP_CUDA(cudaMemcpyAsync(b->overflow_pin, b->overflow_dev, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+	return RP_OK;
+}
+static int overflow_result(rp_batch* b) {
+	const int bits = *b->overflow_pin;
+	if (!bits) return RP_OK;
+	char msg[160];
+	snprintf(msg, sizeof(msg), "capacity exhausted in some world (status bits 0x%x): raise rp_batch_cfg.max_pairs_per_world / max_contacts_per_world", bits);
+	return fail(RP_ERR_CAPACITY, msg);
+}
+
 int rp_batch_sync(rp_batch* b) {
 	if (!b) return RP_ERR_ARG;
 	RP_CUDA(cudaSetDevice(b->device));
+	int rc = enqueue_overflow_check(b);
+	if (rc) return rc;
 	RP_CUDA(cudaStreamSynchronize(b->stream));
 	RP_CUDA(cudaGetLastError());
-	return RP_OK;
+	return overflow_result(b);
 }
+int rp_batch_graph_kernels(const rp_batch* b) { return b ? b->graph_kernels : -1; }
 
 int rp_batch_run(rp_batch* b, uint32_t frames, double dt, uint32_t substeps, uint32_t iters, int collisions, float* ms_out) {
 	if (!b) return RP_ERR_ARG;
@@ -832,7 +920,7 @@ int rp_batch_run(rp_batch* b, uint32_t frames, double dt, uint32_t substeps, uin
 
 // ----------------------------------------------------------------------------------------------------------- state
 static int upload_impl(rp_batch* b, uint32_t first, uint32_t n, const double* host, int broadcast) {
-	if (!b || !host || first + n > (uint32_t)b->d.W || n == 0) return fail(RP_ERR_ARG, "state transfer: bad range");
+	if (!b || !host || n == 0 || first >= (uint32_t)b->d.W || n > (uint32_t)b->d.W - first) return fail(RP_ERR_ARG, "state transfer: bad range");
 	RP_CUDA(cudaSetDevice(b->device));
 	const size_t nrec = (size_t)(broadcast ? 1 : n) * b->d.NB;
 	RP_CUDA(cudaMemcpyAsync(b->rec_dev, host, nrec * RP_STATE_STRIDE * sizeof(double), cudaMemcpyHostToDevice, b->stream));
@@ -855,7 +943,7 @@ int rp_batch_broadcast_state(rp_batch* b, const double* host_one_world) {
 	return RP_OK;
 }
 static int download_async(rp_batch* b, uint32_t first, uint32_t n, double* host) {
-	if (!b || !host || first + n > (uint32_t)b->d.W || n == 0) return fail(RP_ERR_ARG, "state transfer: bad range");
+	if (!b || !host || n == 0 || first >= (uint32_t)b->d.W || n > (uint32_t)b->d.W - first) return fail(RP_ERR_ARG, "state transfer: bad range");
 	RP_CUDA(cudaSetDevice(b->device));
 	const size_t total = (size_t)n * b->d.NB;
 	k_pack_state<<<dim3(b->d.NB, (n + 127) / 128), 128, 0, b->stream>>>(b->d, b->rec_dev, (int)first, (int)n);
@@ -866,8 +954,9 @@ static int download_async(rp_batch* b, uint32_t first, uint32_t n, double* host)
 int rp_batch_download_state(rp_batch* b, uint32_t first, uint32_t n, double* host) {
 	int rc = download_async(b, first, n, host);
 	if (rc) return rc;
+	if ((rc = enqueue_overflow_check(b))) return rc;
 	RP_CUDA(cudaStreamSynchronize(b->stream));
-	return RP_OK;
+	return overflow_result(b);
 }
 
 int rp_batch_step_host(rp_batch* b, const double* in, double* out, double dt, uint32_t substeps, uint32_t iters, int collisions) {
@@ -876,8 +965,9 @@ int rp_batch_step_host(rp_batch* b, const double* in, double* out, double dt, ui
 	if (in && (rc = upload_impl(b, 0, (uint32_t)b->d.W, in, 0))) return rc;
 	if ((rc = rp_batch_step(b, dt, substeps, iters, collisions))) return rc;
 	if (out && (rc = download_async(b, 0, (uint32_t)b->d.W, out))) return rc;
+	if ((rc = enqueue_overflow_check(b))) return rc;
 	RP_CUDA(cudaStreamSynchronize(b->stream));
-	return RP_OK;
+	return overflow_result(b);
 }
 
 int rp_batch_get_status(rp_batch* b, int32_t* out) {
@@ -891,6 +981,7 @@ int rp_batch_clear_status(rp_batch* b) {
 	if (!b) return RP_ERR_ARG;
 	RP_CUDA(cudaSetDevice(b->device));
 	RP_CUDA(cudaMemsetAsync(b->d.status, 0, sizeof(int) * b->d.W, b->stream));
+	*b->overflow_pin = 0;
 	return RP_OK;
 }
 int rp_batch_get_counters(rp_batch* b, uint64_t out8[8]) {
@@ -960,6 +1051,10 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t substeps, uint32_t ite
 	int rc = flush_forces(b);
 	if (rc) return rc;
 	DevView& d = b->d;
+	struct DbgGuard {  // whatever way this function is left, the batch's view goes back to "no world is logged"
+		DevView& d;
+		~DbgGuard() { d.dbg_world = -1; }
+	} guard{d};
 	d.dbg_world = (int)world;
 	const double h = dt / substeps;
 	enqueue_prologue(b, dt, collisions ? 1 : 0);
@@ -1030,6 +1125,12 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 	const double h = dt / substeps;
 	std::vector<cudaEvent_t> ev;
 	std::vector<int> fam;
+	struct EventGuard {
+		std::vector<cudaEvent_t>& ev;
+		~EventGuard() {
+			for (size_t i = 0; i < ev.size(); ++i) cudaEventDestroy(ev[i]);
+		}
+	} guard{ev};
 	auto mark = [&](int family) -> int {
 		cudaEvent_t e;
 		RP_CUDA(cudaEventCreate(&e));
@@ -1087,7 +1188,6 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 		RP_CUDA(cudaEventElapsedTime(&ms, ev[i - 1], ev[i]));
 		ms_out[fam[i]] += ms;
 	}
-	for (size_t i = 0; i < ev.size(); ++i) cudaEventDestroy(ev[i]);
 	return RP_OK;
 }
 
@@ -1100,8 +1200,17 @@ int rp_measure_fp64_peak(int device, double out2[2]) {
 	RP_CUDA(cudaGetDeviceProperties(&prop, device));
 	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
 	double* buf = 0;
+	cudaEvent_t e0 = 0, e1 = 0;
+	struct ProbeGuard {
+		double*& buf;
+		cudaEvent_t &e0, &e1;
+		~ProbeGuard() {
+			if (e0) cudaEventDestroy(e0);
+			if (e1) cudaEventDestroy(e1);
+			if (buf) cudaFree(buf);
+		}
+	} guard{buf, e0, e1};
 	RP_CUDA(cudaMalloc(&buf, sizeof(double) * blocks * threads));
-	cudaEvent_t e0, e1;
 	RP_CUDA(cudaEventCreate(&e0));
 	RP_CUDA(cudaEventCreate(&e1));
 	for (int mode = 0; mode < 2; ++mode) {
@@ -1119,9 +1228,6 @@ int rp_measure_fp64_peak(int device, double out2[2]) {
 		const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
 		out2[mode] = flops / (best * 1e-3) / 1e12;
 	}
-	cudaEventDestroy(e0);
-	cudaEventDestroy(e1);
-	cudaFree(buf);
 	return RP_OK;
 }
 

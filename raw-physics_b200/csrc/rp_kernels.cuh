@@ -753,7 +753,9 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 	const int w0 = wlive ? w : 0;
 	const int* active = d.active + w0;
 	const size_t S = d.WS;
+#if defined(RP_STORED_NORMALS)
 	const int epoch = *d.epoch;
+#endif
 	int tested = 0;
 	const int warps_per_cta = blockDim.x >> 5;
 	const int stride = gridDim.x * warps_per_cta;
@@ -1802,6 +1804,14 @@ __global__ void __launch_bounds__(256) k_fp64_probe(double* out, int iters, doub
 }
 
 __global__ void k_count_frame(DevView d) { atomicAdd(&d.counters[CNT_FRAMES], 1ull); }
+
+// OR of the capacity bits of every world's status word (rp_batch_sync and the other synchronising calls report it)
+__global__ void __launch_bounds__(256) k_status_overflow(DevView d, int* out) {
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	int bits = w < d.W ? d.status[w] & (ST_EPA_CAPACITY | ST_CLIP_CAPACITY | ST_CONTACT_CAPACITY | ST_PAIR_CAPACITY) : 0;
+	for (int o = 16; o > 0; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
+	if ((threadIdx.x & 31) == 0 && bits) atomicOr(out, bits);
+}
 
 // -------------------------------------------------------------------------------------------------- state pack/unpack
 // host record (rawphys_b200.h RP_STATE_STRIDE = 21 doubles, [world][body]) <-> world-minor dynamic state + active +

@@ -181,8 +181,16 @@ int Scene::add_hull_collider(const double* vx, uint32_t nverts, const uint32_t* 
 		}
 	}
 	if (id < 0) {
+		HullHost h = build_hull(vx, nverts, indices, nidx);
+		// A zero-area triangle has no normal (NaN after normalisation in the reference, collider.cpp:180-192) and leaves a face
+		// that clipping would index out of its row; an empty face likewise. Refused instead of built.
+		if (h.face_ptr.size() < 2) return -1;
+		for (size_t f = 0; f + 1 < h.face_ptr.size(); ++f) {
+			const V3 n = h.normals[f];
+			if (h.face_ptr[f + 1] - h.face_ptr[f] < 3 || !(n.x == n.x && n.y == n.y && n.z == n.z) || (n.x == 0.0 && n.y == 0.0 && n.z == 0.0)) return -1;
+		}
 		id = (int)hulls.size();
-		hulls.push_back(build_hull(vx, nverts, indices, nidx));
+		hulls.push_back(h);
 	}
 	ColliderDesc c;
 	c.type = SHAPE_HULL;
@@ -246,6 +254,8 @@ int Scene::add_body(const double* pos, const double* quat, double mass, int fixe
 	b.ncol = (int)pending.size();
 	b.fixed = fixed ? 1 : 0;
 	b.mu_s = mu_s; b.mu_d = mu_d; b.rest = rest;
+	b.mass = mass;
+	b.v0 = b.w0 = v3(0.0, 0.0, 0.0);
 
 	// colliders_get_bounding_sphere_radius (collider.cpp:510-521)
 	double rmax = -1.7976931348623157e308;
@@ -299,7 +309,12 @@ int Scene::add_body(const double* pos, const double* quat, double mass, int fixe
 				}
 			}
 		}
-		inverse(b.inertia, &b.inv_inertia);
+		// a tensor that cannot be inverted (no hull vertices, all of them on one line ...) is refused; the reference would go on
+		// with whatever gm_mat3_inverse left (entity.cpp:45-47 asserts on it)
+		if (!inverse(b.inertia, &b.inv_inertia)) {
+			pending.clear();
+			return -1;
+		}
 	}
 	return commit_body(*this, b);
 }
@@ -315,6 +330,8 @@ int Scene::add_body_params(const double* pos, const double* quat, double inv_mas
 	b.mu_s = mu_s; b.mu_d = mu_d; b.rest = rest;
 	b.radius = radius;
 	b.inv_mass = inv_mass;
+	b.mass = 0.0;
+	b.v0 = b.w0 = v3(0.0, 0.0, 0.0);
 	for (int r = 0; r < 3; ++r) {
 		for (int c = 0; c < 3; ++c) {
 			b.inertia.m[r][c] = inertia9[3 * r + c];

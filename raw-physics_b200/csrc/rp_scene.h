@@ -30,6 +30,8 @@ struct BodyInit {
 	double mu_s, mu_d, rest;
 	int fixed;
 	int col0, ncol;         // collider range
+	double mass;            // as given to add_body (0 when the body was adopted through add_body_params)
+	V3 v0, w0;              // initial velocities (zero unless an example's `perturb` variant sets them)
 };
 
 struct Scene {
@@ -66,4 +68,8 @@ HullPoolHost pool_hulls(const Scene& s);
 HullHost build_hull(const double* verts_xyz, uint32_t nverts, const uint32_t* indices, uint32_t nidx);
 
 }  // namespace rp
+
+struct rp_scene {  // the opaque handle of include/rawphys_b200.h
+	rp::Scene s;
+};
 #endif

@@ -12,6 +12,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _device_count():
+    try:
+        import __graft_entry__ as ge
+        ge.build()
+        return int(ge.load_package().lib().rp_device_count())
+    except Exception:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a box without a CUDA device skips the GPU tests instead of failing in them (`-m gpu` on such a
+    box still selects them: they are then reported as skipped, not passed)."""
+    if not any("gpu" in it.keywords for it in items) or _device_count() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (the product has no CPU path)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def pkg():
     import __graft_entry__ as ge
@@ -21,7 +41,15 @@ def pkg():
 
 def _oracle_flavour():
     import refdrv
-    return "strict" if refdrv.available("strict") else "port"
+    if refdrv.available("strict"):
+        return "strict"
+    # LOUD: the CPU restatement shares its arithmetic headers with the product, so agreement with it alone proves little; the
+    # independent checks on such a box are the committed fixtures (tests/golden/*.npz, outputs of the compiled reference)
+    import warnings
+    warnings.warn("oracle/_ref/libref_oracle.so (the compiled reference) is ABSENT: live comparisons fall back to the CPU restatement "
+                  "oracle/port; only the golden-fixture tests pin parity on this machine", stacklevel=1)
+    sys.stderr.write("\n*** oracle fallback: compiled reference absent, using oracle/port ***\n")
+    return "port"
 
 
 @pytest.fixture(scope="session")

@@ -79,3 +79,26 @@ def test_headless_levers_within_tolerance(pkg, oracle_flavour, tmp_path):
         worst = max(worst, float(np.abs(dump[f][:, :7] - o.state()[:, :7]).max()))
     print("levers: worst |pose diff| = %g" % worst)
     assert worst <= 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,extra,frames,exact", [
+    ("cube_storm", [], 60, True), ("coin", [], 60, True), ("seesaw", [], 60, True), ("mirror_cube", [], 60, True), ("spring", [], 60, True),
+    ("cube_and_ramp", [], 60, True), ("spot_storm", ["--params", "2,99"], 12, True), ("debug", [], 5, True),
+    ("arm", ["--perturb"], 40, False), ("rott_pendulum", ["--perturb"], 20, False), ("triple_pendula", ["--perturb"], 20, False),
+])
+def test_headless_runs_every_example(pkg, oracle_flavour, tmp_path, scene, extra, frames, exact):
+    """the init()/update() halves of the remaining examples in host C++ (rp_example_create + the frame loop of
+    rp_headless), each with the step settings its own update() uses, against the oracle stepping the same description."""
+    info, dump = run(tmp_path, "--scene", scene, "--frames", frames, "--worlds", 3, "--dump-every", frames, *extra)
+    assert info["status_bits"] == 0 and info["diverged_worlds"] == 0
+    params = [float(x) for x in extra[extra.index("--params") + 1].split(",")] if "--params" in extra else ()
+    _, desc = pkg.example(scene, params, perturb="--perturb" in extra)
+    o = refdrv.RefWorld(oracle_flavour).load(desc)
+    for _ in range(frames):
+        o.step(substeps=desc.substeps, iters=desc.iters, collisions=desc.collisions)
+    got, want = dump[frames][:, :15], o.state()
+    if exact:
+        assert np.array_equal(got, want), (scene, np.abs(got - want).max())
+    else:
+        assert np.abs(got[:, :7] - want[:, :7]).max() <= 1e-9

@@ -247,13 +247,41 @@ def test_work_counters_match_oracle(pkg, oracle_flavour):
 
 
 def test_capacity_overflow_is_reported_not_fatal(pkg):
+    """A world that runs out of contact (or pair) capacity drops work: the status word says so, and every synchronising call
+    returns RP_ERR_CAPACITY -- after doing its work -- until the status is cleared."""
     sc = scenes.cube_storm()
-    b = make(pkg, sc, max_contacts=8)
+    b = make(pkg, sc, n_worlds=2, max_contacts=8)
     for _ in range(90):
         step(b, sc)
+    with pytest.raises(pkg.RawPhysCapacityError):
+        b.sync()
+    with pytest.raises(pkg.RawPhysCapacityError):
+        b.state()
+    buf = np.zeros((2, b.NB, 21))
+    with pytest.raises(pkg.RawPhysCapacityError):
+        b.step_host(None, buf.ctypes.data)
     st = b.status()
-    assert st[0] & 64  # RP_ST_CONTACT_CAPACITY
-    assert np.isfinite(b.state()).all()
+    assert st[0] & 64 and st[1] & 64  # RP_ST_CONTACT_CAPACITY
+    assert np.isfinite(buf).all() and np.isfinite(b.state(ignore_capacity=True)).all()
+    b.clear_status()
+    b.sync()
+    # too few pairs
+    b = make(pkg, sc, max_pairs=4)
+    step(b, sc)
+    with pytest.raises(pkg.RawPhysCapacityError):
+        b.sync()
+    assert b.status()[0] & 128  # RP_ST_PAIR_CAPACITY
+
+
+def test_state_transfer_ranges_are_checked(pkg):
+    sc = scenes.stack()
+    b = make(pkg, sc, n_worlds=3)
+    buf = np.zeros((4, b.NB, 21))
+    L = pkg.lib()
+    for first, n in [(0xFFFFFFFF, 2), (3, 1), (2, 2), (0, 0), (0, 4)]:
+        assert L.rp_batch_download_state(b.h, first, n, buf.ctypes.data) == 1
+        assert L.rp_batch_upload_state(b.h, first, n, buf.ctypes.data) == 1
+    assert L.rp_batch_download_state(b.h, 2, 1, buf.ctypes.data) == 0
 
 
 def test_large_batch_invariants(pkg):

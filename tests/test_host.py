@@ -144,3 +144,41 @@ def test_shim_build_links_against_the_library(pkg):
     for needle in ("rp_scene_collider_hull_topology", "rp_scene_add_body_params", "rp_batch_step_host", "_Z12pbd_simulatedPP6Entityjji",
                    "_Z29pbd_simulate_with_constraintsdPP6EntityP10Constraintjji"):
         assert needle in src
+
+
+def test_scene_builder_validates_its_inputs(pkg):
+    """The header's contract: a status code instead of the reference's assert / silent garbage."""
+    L = pkg.lib()
+    s = L.rp_scene_create()
+    cube = scenes.hull("cube", (1.0, 1.0, 1.0))
+    v = np.ascontiguousarray(cube.vertices)
+    idx = np.ascontiguousarray(cube.indices)
+    dp, up = C.POINTER(C.c_double), C.POINTER(C.c_uint32)
+    pos, quat = np.zeros(3), np.array([0.0, 0.0, 0.0, 1.0])
+    d = lambda a: a.ctypes.data_as(dp)
+    # a non-fixed body needs a positive mass ...
+    assert L.rp_scene_collider_hull(s, d(v), v.shape[0], idx.ctypes.data_as(up), idx.shape[0]) >= 0
+    assert L.rp_scene_add_body(s, d(pos), d(quat), 0.0, 0, 0.5, 0.5, 0.0) == -1
+    assert L.rp_scene_add_body(s, d(pos), d(quat), -1.0, 0, 0.5, 0.5, 0.0) == -1
+    assert L.rp_scene_add_body(s, d(pos), d(quat), 1.0, 0, 0.5, 0.5, 0.0) == 0
+    # ... and an invertible inertia tensor: a body without any collider has none
+    assert L.rp_scene_add_body(s, d(pos), d(quat), 1.0, 0, 0.5, 0.5, 0.0) == -1
+    assert L.rp_scene_add_body(s, d(pos), d(quat), 0.0, 1, 0.5, 0.5, 0.0) == 1  # (fixed: fine)
+    # zero-area triangles have no normal
+    flat = np.array([[0.0, 0, 0], [1.0, 0, 0], [2.0, 0, 0]])
+    tri = np.arange(3, dtype=np.uint32)
+    assert L.rp_scene_collider_hull(s, d(flat), 3, tri.ctypes.data_as(up), 3) == -1
+    # constraints: NULL vectors, axis selectors out of range
+    r = np.zeros(3)
+    assert L.rp_scene_add_positional_constraint(s, 0, 1, None, d(r), 0.0, d(r)) == -1
+    assert L.rp_scene_add_positional_constraint(s, 0, 1, d(r), d(r), 0.0, None) == -1
+    assert L.rp_scene_add_hinge_joint_constraint(s, 0, 1, d(r), None, 0.0, 0, 0, 0, 0, 0, 0.0, 0.0) == -1
+    assert L.rp_scene_add_hinge_joint_constraint(s, 0, 1, d(r), d(r), 0.0, 6, 0, 0, 0, 0, 0.0, 0.0) == -1
+    assert L.rp_scene_add_spherical_joint_constraint(s, 0, 1, d(r), d(r), 0, 0, -1, 0, 0.0, 0.0, 0.0, 0.0) == -1
+    assert L.rp_scene_add_positional_constraint(s, 0, 1, d(r), d(r), 0.0, d(r)) == 0
+    # output pointers
+    assert L.rp_scene_hull_sizes(s, 0, 0, None) != 0
+    sizes = np.zeros(6, dtype=np.int32)
+    assert L.rp_scene_hull_sizes(s, 0, 0, sizes.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+    assert L.rp_scene_hull_dump(s, 0, 0, None, None, None, None, None, None, None, None, None, None) != 0
+    L.rp_scene_destroy(s)
