@@ -120,7 +120,7 @@ int rp_scene_joint_desc(const rp_scene* s, int joint, int32_t ints8[8], double v
  * pieces ("w256", "pile", "tumble", "spheres"), as scene templates; `info` receives what the example's update() passes to
  * pbd_simulate (substeps, positional iterations, collisions) and its gravity. `params` (optional, 0 = default) per scene:
  * stack {cubes}; w256 {stacks_x, stacks_z, height}; brick_wall {rows, cols}; cube_storm {n}; spot_storm {n, seed};
- * pile {n_side, seed, spacing}; tumble {n, seed}; spheres {n}. `perturb` != 0 gives the joint scenes (hinge_joints, arm,
+ * pile {n_side, seed, spacing, layers}; tumble {n, seed}; spheres {n}. `perturb` != 0 gives the joint scenes (hinge_joints, arm,
  * triple_pendula, rott_pendulum), which are at rest until a user interacts, initial angular velocities. `mesh_dir` = directory of
  * the <mesh>.f32 triangle soups (NULL: assets/meshes next to the library). Returns NULL on failure (rp_example_error()). */
 typedef struct {
@@ -150,7 +150,8 @@ typedef struct {
 	uint32_t disable_cull;            /* 1 = run GJK on every broadphase pair (the exact-safe bounds cull is on by default) */
 	uint32_t solve_order;             /* RP_ORDER_REFERENCE (default) or RP_ORDER_COLOURED */
 	uint32_t sweep_block_worlds;      /* worlds per CTA of the world-block Gauss-Seidel sweeps; 0 = choose (level-major sweeps for small batches) */
-	uint32_t reserved0;
+	uint32_t large_scene;             /* per-frame prologue for ONE LARGE SCENE (uniform-grid broadphase, union-find islands, parallel graph
+	                                     colouring): 0 = when a world has >= 4096 bodies, 1 = never, 2 = always */
 	double linear_sleeping_threshold;   /* pbd.cpp:13, default 0.10 */
 	double angular_sleeping_threshold;  /* pbd.cpp:14, default 0.10 */
 	double deactivation_time;           /* pbd.cpp:15, default 1.0 */
@@ -216,6 +217,10 @@ int rp_batch_step_logged(rp_batch* b, double dt, uint32_t num_substeps, uint32_t
 	uint32_t* calls_out, uint32_t max_calls, double* contacts_out, uint32_t max_contacts, uint32_t* n_calls, uint32_t* n_contacts);
 /* broadphase pairs of one world for its current poses (broad_get_collision_pairs, broad.cpp:6): (e1, e2) body ids */
 int rp_batch_broad_pairs(rp_batch* b, uint32_t world, uint32_t* pairs_out, uint32_t max_pairs, uint32_t* n_pairs);
+
+/* the schedule of one world for its current poses: every broadphase collider pair (bodies a < b) with the dependency level
+ * (RP_ORDER_REFERENCE) or colour (RP_ORDER_COLOURED) the sweeps run it at; 0 = skipped (both sides fixed or asleep, pbd.cpp:594) */
+int rp_batch_pair_levels(rp_batch* b, uint32_t world, uint32_t* pairs_out, int32_t* levels_out, uint32_t max_pairs, uint32_t* n_pairs);
 
 /* Profiling aids (bench.py). Kernel families of one frame, in launch order. */
 enum {

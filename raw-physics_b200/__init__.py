@@ -32,14 +32,14 @@ EXPORTS = [
     "rp_batch_run", "rp_batch_upload_state", "rp_batch_download_state", "rp_batch_broadcast_state", "rp_batch_step_host",
     "rp_batch_get_status", "rp_batch_clear_status", "rp_batch_get_counters", "rp_batch_step_logged", "rp_batch_broad_pairs", "rp_batch_profile",
     "rp_measure_fp64_peak", "rp_scene_initial_state", "rp_scene_body_desc", "rp_scene_collider_soup_size", "rp_scene_collider_soup",
-    "rp_scene_num_joints", "rp_scene_joint_desc", "rp_batch_graph_kernels", "rp_example_count", "rp_example_name", "rp_example_error", "rp_example_create",
+    "rp_scene_num_joints", "rp_scene_joint_desc", "rp_batch_graph_kernels", "rp_batch_pair_levels", "rp_example_count", "rp_example_name", "rp_example_error", "rp_example_create",
 ]
 KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "cull", "gjk", "manifold", "solve_pos", "derive", "solve_vel", "epa"]
 
 
 class BatchCfg(C.Structure):
     _fields_ = [("max_pairs_per_world", C.c_uint32), ("max_contacts_per_world", C.c_uint32), ("disable_cull", C.c_uint32),
-                ("solve_order", C.c_uint32), ("sweep_block_worlds", C.c_uint32), ("reserved0", C.c_uint32),
+                ("solve_order", C.c_uint32), ("sweep_block_worlds", C.c_uint32), ("large_scene", C.c_uint32),
                 ("linear_sleeping_threshold", C.c_double), ("angular_sleeping_threshold", C.c_double), ("deactivation_time", C.c_double)]
 
 
@@ -107,6 +107,7 @@ def lib():
     L.rp_batch_step_logged.argtypes = [C.c_void_p, C.c_double, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, _u32p, C.c_uint32, _dp,
                                        C.c_uint32, _u32p, _u32p]
     L.rp_batch_broad_pairs.argtypes = [C.c_void_p, C.c_uint32, _u32p, C.c_uint32, _u32p]
+    L.rp_batch_pair_levels.argtypes = [C.c_void_p, C.c_uint32, _u32p, _i32p, C.c_uint32, _u32p]
     L.rp_batch_profile.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_float)]
     L.rp_measure_fp64_peak.argtypes = [C.c_int, _dp]
     L.rp_scene_initial_state.argtypes = [C.c_void_p, _dp]
@@ -308,7 +309,7 @@ class Scene:
 class Batch:
     """n_worlds instances of a scene on one GPU (rp_batch)."""
 
-    def __init__(self, scene, n_worlds=1, device=0, max_pairs=0, max_contacts=0, disable_cull=False, coloured=False, sweep_block_worlds=0):
+    def __init__(self, scene, n_worlds=1, device=0, max_pairs=0, max_contacts=0, disable_cull=False, coloured=False, sweep_block_worlds=0, large_scene=0):
         self.L = lib()
         self.scene = scene
         cfg = BatchCfg()
@@ -317,7 +318,8 @@ class Batch:
         cfg.max_contacts_per_world = max_contacts
         cfg.disable_cull = int(disable_cull)
         cfg.solve_order = 1 if coloured else 0  # RP_ORDER_COLOURED / RP_ORDER_REFERENCE
-        cfg.sweep_block_worlds = sweep_block_worlds  # 0: the library chooses (world-block sweeps for large batches)
+        cfg.sweep_block_worlds = sweep_block_worlds  # 0: level-major sweeps
+        cfg.large_scene = large_scene  # 0: grid broadphase / union-find islands / parallel colouring from 4096 bodies per world; 1 never; 2 always
         h = C.c_void_p()
         _check(self.L.rp_batch_create(scene.h, n_worlds, device, C.byref(cfg), C.byref(h)), "rp_batch_create")
         self.h = h
@@ -422,6 +424,18 @@ class Batch:
         n = C.c_uint32()
         _check(self.L.rp_batch_broad_pairs(self.h, world, _u(buf), max_pairs, C.byref(n)), "rp_batch_broad_pairs")
         return buf[:n.value].astype(np.int64)
+
+
+def _pair_levels(self, world=0, max_pairs=1 << 21):
+    """(pairs [n, 2], levels [n]) of one world's schedule for its current poses"""
+    pairs = np.zeros((max_pairs, 2), dtype=np.uint32)
+    levels = np.zeros(max_pairs, dtype=np.int32)
+    n = C.c_uint32()
+    _check(self.L.rp_batch_pair_levels(self.h, world, _u(pairs), levels.ctypes.data_as(_i32p), max_pairs, C.byref(n)), "rp_batch_pair_levels")
+    return pairs[:n.value].astype(np.int64), levels[:n.value].copy()
+
+
+Batch.pair_levels = _pair_levels
 
 
 def measure_fp64_peak(device=0):

@@ -10,6 +10,7 @@
 
 #include "../../include/rawphys_b200.h"
 #include "rp_kernels.cuh"
+#include "rp_large.cuh"
 #include "rp_scene.h"
 
 using namespace rp;
@@ -33,6 +34,7 @@ static int fail(int code, const std::string& msg) {
 #ifndef RP_CULL_CTAS_PER_SM
 #define RP_CULL_CTAS_PER_SM 16  // k_cull grid: CTAs of 8 warps per SM's worth of pair indices (a warp walks the rest in trips)
 #endif
+#define RP_COLOUR_ROUNDS 40  // independent-set rounds of the parallel colouring enqueued per frame (a round that has nothing left to do returns at once)
 #define RP_SCHED_SMEM_MAX (160 * 1024)  // dynamic shared memory k_schedule<true> may ask for (opted in at batch creation)
 
 struct GraphKey {
@@ -65,6 +67,11 @@ struct rp_batch {
 	unsigned int transform_slices = 1;  // gridDim.z of k_transform: threads that share one collider's vertices and normals
 	bool has_big_pairs = false;   // some collider pair is too large for k_gjk's per-thread staging: k_gjk_warp is launched too
 	bool no_restitution = false;  // every body's restitution coefficient is zero (k_integrate's store_velocities)
+	// one large scene (rp_large.cuh): uniform-grid broadphase, union-find islands, parallel colouring
+	bool large = false;
+	GridView grid;
+	ColourView col;
+	int grid_tiles_table = 0, grid_tiles_rows = 0;
 	int sweep_wpb = 0;            // worlds per CTA of the world-block sweeps (k_solve_block); 0 = level-major cooperative sweeps
 	size_t sweep_smem = 0;        // dynamic shared memory of k_solve_block (its per-level cursors)
 	std::vector<int> joint_level;  // template-constant levels of the external constraints
@@ -95,6 +102,11 @@ static int dev_upload(rp_batch* b, const T** out, const std::vector<T>& v) {
 	if (!v.empty()) RP_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, b->stream));
 	*out = p;
 	return RP_OK;
+}
+
+// CTAs for one thread per (item, world) (flat_item_world)
+static unsigned int flat_grid(const rp_batch* b, size_t n_items, unsigned int threads) {
+	return (unsigned int)((n_items * (size_t)b->d.W + threads - 1) / threads);
 }
 
 // launches `kernel` as a cooperative grid (cg::this_grid().sync() inside); capturable into the frame graph
@@ -430,15 +442,75 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	d.sleep_time = cfg.deactivation_time;
 	d.dbg_world = -1;
 
-	// capacities: derived from the broadphase of the initial poses unless given
-	size_t init_pairs = 0;
-	for (int i = 0; i < d.NB; ++i) {
-		for (int j = i + 1; j < d.NB; ++j) {
-			double dist = length(sub(s.bodies[i].x, s.bodies[j].x));
-			if (dist <= s.bodies[i].radius + s.bodies[j].radius + 0.1) init_pairs += (size_t)s.bodies[i].ncol * s.bodies[j].ncol;
+	// One large scene (rp_large.cuh) or many small worlds? Bodies far larger than the typical one (the floor) stay out of the
+	// uniform grid: its cell edge is set by the largest of the others.
+	if (cfg.large_scene > 2) return fail(RP_ERR_ARG, "rp_batch_create: unknown large_scene");
+	b->large = cfg.large_scene == 2 || (cfg.large_scene == 0 && d.NB >= 4096);
+	std::vector<unsigned char> is_large(d.NB, 0);
+	std::vector<int> large_ids;
+	double r_small = 0.0;
+	if (b->large) {
+		std::vector<double> radii(d.NB);
+		for (int i = 0; i < d.NB; ++i) radii[i] = s.bodies[i].radius;
+		std::nth_element(radii.begin(), radii.begin() + d.NB / 2, radii.end());
+		const double cut = 4.0 * radii[d.NB / 2];
+		for (int i = 0; i < d.NB; ++i) {
+			if (s.bodies[i].radius > cut) {
+				is_large[i] = 1;
+				large_ids.push_back(i);
+			} else {
+				r_small = std::max(r_small, s.bodies[i].radius);
+			}
 		}
 	}
-	size_t mp = cfg.max_pairs_per_world ? cfg.max_pairs_per_world : std::max<size_t>(128, 2 * init_pairs + 64);
+	const double cell_edge = (2.0 * r_small + 0.1) * (1.0 + 1e-6);
+
+	// capacities: derived from the broadphase of the initial poses unless given
+	size_t init_pairs = 0;
+	if (!b->large) {
+		for (int i = 0; i < d.NB; ++i) {
+			for (int j = i + 1; j < d.NB; ++j) {
+				double dist = length(sub(s.bodies[i].x, s.bodies[j].x));
+				if (dist <= s.bodies[i].radius + s.bodies[j].radius + 0.1) init_pairs += (size_t)s.bodies[i].ncol * s.bodies[j].ncol;
+			}
+		}
+	} else if (!cfg.max_pairs_per_world) {
+		// the same count through a host-side grid of the same cells (the quadratic loop above takes minutes for 65 k bodies)
+		std::vector<std::pair<long long, int>> keyed;
+		auto key_of = [&](long long cx, long long cy, long long cz) { return ((cx + (1ll << 20)) << 42) ^ ((cy + (1ll << 20)) << 21) ^ (cz + (1ll << 20)); };
+		for (int i = 0; i < d.NB; ++i) {
+			if (is_large[i]) continue;
+			const V3 x = s.bodies[i].x;
+			keyed.push_back(std::make_pair(key_of((long long)floor(x.x / cell_edge), (long long)floor(x.y / cell_edge), (long long)floor(x.z / cell_edge)), i));
+		}
+		std::sort(keyed.begin(), keyed.end());
+		for (size_t k = 0; k < keyed.size(); ++k) {
+			const int i = keyed[k].second;
+			const V3 x = s.bodies[i].x;
+			const long long cx = (long long)floor(x.x / cell_edge), cy = (long long)floor(x.y / cell_edge), cz = (long long)floor(x.z / cell_edge);
+			for (long long dz = -1; dz <= 1; ++dz) {
+				for (long long dy = -1; dy <= 1; ++dy) {
+					for (long long dx = -1; dx <= 1; ++dx) {
+						const long long key = key_of(cx + dx, cy + dy, cz + dz);
+						auto it = std::lower_bound(keyed.begin(), keyed.end(), std::make_pair(key, -1));
+						for (; it != keyed.end() && it->first == key; ++it) {
+							const int j = it->second;
+							if (j > i && length(sub(x, s.bodies[j].x)) <= s.bodies[i].radius + s.bodies[j].radius + 0.1) init_pairs += (size_t)s.bodies[i].ncol * s.bodies[j].ncol;
+						}
+					}
+				}
+			}
+		}
+		for (size_t l = 0; l < large_ids.size(); ++l) {
+			const int i = large_ids[l];
+			for (int j = 0; j < d.NB; ++j) {
+				if (j == i || (is_large[j] && j < i)) continue;
+				if (length(sub(s.bodies[i].x, s.bodies[j].x)) <= s.bodies[i].radius + s.bodies[j].radius + 0.1) init_pairs += (size_t)s.bodies[i].ncol * s.bodies[j].ncol;
+			}
+		}
+	}
+	// (a large scene's bodies are expected to pile up: room for 8 pairs per body on top of what the initial poses need)
+	size_t mp = cfg.max_pairs_per_world ? cfg.max_pairs_per_world : std::max<size_t>(128, 2 * init_pairs + 64 + (b->large ? 8 * (size_t)d.NB : 0));
 	mp = (mp + 127) / 128 * 128;
 	d.max_pairs = (int)mp;
 	d.max_contacts = (int)(cfg.max_contacts_per_world ? cfg.max_contacts_per_world : std::max<size_t>(256, 8 * (size_t)d.NB));
@@ -589,7 +661,41 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 #endif
 	if ((rc = dev_alloc(b, &d.pairs, SP))) return rc;
 	if ((rc = dev_alloc(b, &d.n_pairs, W))) return rc;
-	{
+	if (b->large) {
+		GridView& g = b->grid;
+		memset(&g, 0, sizeof(g));
+		g.table = 1024;
+		while (g.table < 2 * d.NB) g.table *= 2;
+		g.inv_cell = 1.0 / cell_edge;
+		g.n_large = (int)large_ids.size();
+		const int most = std::max(std::max(g.table + 1, d.NB + 1), 1);
+		const size_t tiles = ((size_t)most + RP_SCAN_TILE - 1) / RP_SCAN_TILE;
+		if ((rc = dev_upload(b, &g.large, large_ids))) return rc;
+		if ((rc = dev_upload(b, &g.is_large, is_large))) return rc;
+		if ((rc = dev_alloc(b, &g.bucket, WB))) return rc;
+		if ((rc = dev_alloc(b, &g.start, W * ((size_t)g.table + 1)))) return rc;
+		if ((rc = dev_alloc(b, &g.cursor, W * (size_t)g.table))) return rc;
+		if ((rc = dev_alloc(b, &g.sorted, WB))) return rc;
+		if ((rc = dev_alloc(b, &g.row, W * ((size_t)d.NB + 1)))) return rc;
+		if ((rc = dev_alloc(b, &g.sums, W * tiles))) return rc;
+		if ((rc = dev_alloc(b, &g.totals, W))) return rc;
+		if (b->coloured) {
+			ColourView& c = b->col;
+			memset(&c, 0, sizeof(c));
+			if ((rc = dev_alloc(b, &c.deg, W * ((size_t)d.NB + 1)))) return rc;
+			if ((rc = dev_alloc(b, &c.fill, WB))) return rc;
+			if ((rc = dev_alloc(b, &c.adj, 2 * WP))) return rc;
+			if ((rc = dev_alloc(b, &c.colour, WP))) return rc;
+			if ((rc = dev_alloc(b, &c.pending, WP))) return rc;
+			if ((rc = dev_alloc(b, &c.remaining, RP_COLOUR_ROUNDS + 1))) return rc;
+			c.sums = g.sums;
+			c.totals = g.totals;
+		}
+		d.n_cells = 0;
+		if ((rc = dev_alloc(b, &d.cells, 1))) return rc;
+		if ((rc = dev_alloc(b, &d.cell_mask, 1))) return rc;
+		if ((rc = dev_alloc(b, &d.cell_off, 1))) return rc;
+	} else {
 		std::vector<int2> cells;
 		for (int i = 0; i + 1 < d.NB; ++i) {
 			for (int j0 = i + 1; j0 < d.NB; j0 += 32) cells.push_back(make_int2(i, j0));
@@ -733,8 +839,52 @@ static int flush_forces(rp_batch* b) {
 	return RP_OK;
 }
 
+// exclusive scan of data[world][0..n) in place (k_scan_*), grand totals to totals[world] (or nowhere)
+static void launch_scan(rp_batch* b, int* data, int n, size_t world_stride, int* sums, int* totals) {
+	const int tiles = (n + RP_SCAN_TILE - 1) / RP_SCAN_TILE;
+	k_scan_tiles<<<dim3(tiles, b->d.W), RP_SCAN_THREADS, 0, b->stream>>>(data, n, world_stride, sums, tiles);
+	k_scan_sums<<<b->d.W, RP_SCAN_THREADS, 0, b->stream>>>(sums, tiles, totals);
+	k_scan_add<<<dim3(tiles, b->d.W), RP_SCAN_THREADS, 0, b->stream>>>(data, n, world_stride, sums, tiles);
+}
+// coloured order of a large scene: per-body adjacency of the units, then rounds of independent sets (rp_large.cuh)
+static void launch_colouring(rp_batch* b, int collisions) {
+	const DevView& d = b->d;
+	const ColourView& c = b->col;
+	const size_t W = (size_t)d.W;
+	cudaMemsetAsync(c.deg, 0, W * (d.NB + 1) * sizeof(int), b->stream);
+	cudaMemsetAsync(c.fill, 0, W * d.NB * sizeof(int), b->stream);
+	cudaMemsetAsync(c.pending, 0, W * d.max_pairs * sizeof(int), b->stream);
+	cudaMemsetAsync(c.remaining, 0, (RP_COLOUR_ROUNDS + 1) * sizeof(int), b->stream);
+	const unsigned int per_pair = flat_grid(b, (size_t)d.max_pairs, 256);
+	k_col_degree<<<per_pair, 256, 0, b->stream>>>(d, c, collisions);
+	launch_scan(b, c.deg, d.NB + 1, (size_t)d.NB + 1, c.sums, 0);
+	k_col_fill<<<per_pair, 256, 0, b->stream>>>(d, c);
+	for (int r = 0; r < RP_COLOUR_ROUNDS; ++r) {
+		k_col_round<<<per_pair, 256, 0, b->stream>>>(d, c, r);
+		k_col_commit<<<per_pair, 256, 0, b->stream>>>(d, c, r);
+	}
+	k_col_leftover<<<per_pair, 256, 0, b->stream>>>(d, c, RP_COLOUR_ROUNDS);
+	k_col_levels<<<1, 32, 0, b->stream>>>(d);
+}
+static void launch_islands(rp_batch* b, double dt) {
+	const DevView& d = b->d;
+	if (!b->large) {
+		k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
+		return;
+	}
+	const unsigned int per_body = flat_grid(b, (size_t)d.NB, 256);
+	k_uf_init<<<per_body, 256, 0, b->stream>>>(d);
+	k_uf_hook<<<flat_grid(b, (size_t)d.max_pairs + d.NJ, 256), 256, 0, b->stream>>>(d);
+	k_uf_sleep<<<per_body, 256, 0, b->stream>>>(d, dt);
+	k_uf_apply<<<per_body, 256, 0, b->stream>>>(d);
+}
+
 static void launch_schedule(rp_batch* b, int collisions) {
 	const DevView& d = b->d;
+	if (b->large && b->coloured) {
+		launch_colouring(b, collisions);
+		return;
+	}
 	const size_t entry = b->coloured ? sizeof(unsigned long long) : sizeof(int);
 	const size_t lanes = d.W < 32 ? d.W : 32;  // columns of the shared tables (k_schedule's SL)
 	const size_t smem = ((size_t)d.NB * lanes * entry + RP_SCHED_HIST * lanes * sizeof(int) + (size_t)d.NB * lanes + 15) / 16 * 16;
@@ -747,13 +897,35 @@ static void launch_schedule(rp_batch* b, int collisions) {
 		else k_schedule<false, false><<<grid, 32, 0, b->stream>>>(d, collisions);
 	}
 }
+static void launch_broad_grid(rp_batch* b) {
+	const DevView& d = b->d;
+	const GridView& g = b->grid;
+	const size_t W = (size_t)d.W;
+	cudaMemsetAsync(g.start, 0, W * (g.table + 1) * sizeof(int), b->stream);
+	cudaMemsetAsync(g.cursor, 0, W * g.table * sizeof(int), b->stream);
+	cudaMemsetAsync(g.row, 0, W * (d.NB + 1) * sizeof(int), b->stream);
+	const unsigned int per_body = flat_grid(b, (size_t)d.NB, 256);
+	k_grid_count<<<per_body, 256, 0, b->stream>>>(d, g);
+	launch_scan(b, g.start, g.table + 1, (size_t)g.table + 1, g.sums, 0);
+	k_grid_fill<<<per_body, 256, 0, b->stream>>>(d, g);
+	k_grid_rowcount<<<flat_grid(b, (size_t)d.NB, 128), 128, 0, b->stream>>>(d, g);
+	if (g.n_large) k_grid_large_count<<<dim3(g.n_large, d.W), RP_SCAN_THREADS, 0, b->stream>>>(d, g);
+	launch_scan(b, g.row, d.NB + 1, (size_t)d.NB + 1, g.sums, g.totals);
+	k_grid_finish<<<(d.W + 63) / 64, 64, 0, b->stream>>>(d, g);
+	k_grid_rowwrite<<<flat_grid(b, (size_t)d.NB, 128), 128, 0, b->stream>>>(d, g);
+	if (g.n_large) k_grid_large_write<<<dim3(g.n_large, d.W), RP_SCAN_THREADS, 0, b->stream>>>(d, g);
+}
 static void launch_broad(rp_batch* b) {
 	const DevView& d = b->d;
+	if (b->large) {
+		launch_broad_grid(b);
+		return;
+	}
 	if (d.n_cells > 0) {
-		const dim3 grid((d.n_cells + 7) / 8, (d.W + 31) / 32), blk(32, 8);
-		k_broad_cells<<<grid, blk, 0, b->stream>>>(d);
+		const unsigned int grid = flat_grid(b, (size_t)d.n_cells, 256);
+		k_broad_cells<<<grid, 256, 0, b->stream>>>(d);
 		k_broad_scan<<<(d.W + 31) / 32, dim3(32, RP_BROAD_SEGS), 0, b->stream>>>(d);
-		k_broad_write<<<grid, blk, 0, b->stream>>>(d);
+		k_broad_write<<<grid, 256, 0, b->stream>>>(d);
 	}
 }
 
@@ -761,7 +933,7 @@ static void launch_broad(rp_batch* b) {
 static void enqueue_prologue(rp_batch* b, double dt, int collisions) {
 	const DevView& d = b->d;
 	launch_broad(b);
-	k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
+	launch_islands(b, dt);
 	k_level_reset<<<1, 256, 0, b->stream>>>(d);
 	launch_schedule(b, collisions);
 	k_level_offsets<<<1, 1, 0, b->stream>>>(d);
@@ -782,19 +954,20 @@ static void enqueue_integrate(rp_batch* b, double h, bool last_substep) {
 	const DevView& d = b->d;
 	k_substep_reset<<<(unsigned int)((std::max(d.W, d.max_levels + 2) + 255) / 256), 256, 0, b->stream>>>(d);
 	const int store_velocities = last_substep || !b->no_restitution ? 1 : 0;
-	k_integrate<<<dim3(d.NB, (d.W + RP_INT_THREADS - 1) / RP_INT_THREADS), RP_INT_THREADS, 0, b->stream>>>(d, h, store_velocities);
+	k_integrate<<<flat_grid(b, (size_t)d.NB, RP_INT_THREADS), RP_INT_THREADS, 0, b->stream>>>(d, h, store_velocities);
 }
 // grid of the per-hit kernel: the hit count lives on the device, so the launch covers the candidate capacity in
 // grid-stride trips of at most this many CTAs
 static unsigned int manifold_grid(const rp_batch* b) { return (unsigned int)b->sm_count * 16u; }
 static void launch_cull(rp_batch* b) {
 	const DevView& d = b->d;
-	const unsigned int wblocks = (unsigned int)((d.W + RP_INT_THREADS - 1) / RP_INT_THREADS);
 	if (d.NC == 0) return;  // bodies without colliders (joint-only scenes): no pairs, no candidates, nothing to transform
-	if (d.split_bounds) k_bounds<<<dim3(d.NC, wblocks), RP_INT_THREADS, 0, b->stream>>>(d);
-	k_cull<<<dim3(b->cull_chunks, (d.W + 31) / 32), 256, 0, b->stream>>>(d, b->cull);
+	if (d.split_bounds) k_bounds<<<flat_grid(b, (size_t)d.NC, RP_INT_THREADS), RP_INT_THREADS, 0, b->stream>>>(d);
+	// lane = world (warp = one pair index of 32 worlds) for batches of at least a warp of worlds, thread = (pair, world) below
+	if (d.W >= 32) k_cull<<<dim3(b->cull_chunks, (d.W + 31) / 32), 256, 0, b->stream>>>(d, b->cull);
+	else k_cull_flat<<<flat_grid(b, (size_t)d.max_pairs, 256), 256, 0, b->stream>>>(d, b->cull);
 #if defined(RP_STORED_NORMALS)
-	k_transform<<<dim3(d.NC, wblocks, b->transform_slices), RP_INT_THREADS, 0, b->stream>>>(d);
+	k_transform<<<dim3(d.NC, (unsigned int)((d.W + RP_INT_THREADS - 1) / RP_INT_THREADS), b->transform_slices), RP_INT_THREADS, 0, b->stream>>>(d);
 #endif
 }
 static void launch_gjk(rp_batch* b) {
@@ -826,7 +999,7 @@ static void enqueue_solve(rp_batch* b, double h, uint32_t iters, int collisions)
 }
 static void enqueue_frame_end(rp_batch* b, double h) {
 	const DevView& d = b->d;
-	k_derive<<<dim3(d.NB, (d.W + 127) / 128), 128, 0, b->stream>>>(d, h);
+	k_derive<<<flat_grid(b, (size_t)d.NB, 128), 128, 0, b->stream>>>(d, h);
 	k_count_frame<<<1, 1, 0, b->stream>>>(d);
 }
 
@@ -1041,6 +1214,34 @@ int rp_batch_broad_pairs(rp_batch* b, uint32_t world, uint32_t* pairs_out, uint3
 	return RP_OK;
 }
 
+// the schedule of one world for its current poses: every broadphase collider pair with the level (reference order) or colour
+// (coloured order) the sweeps would run it at (0 = skipped: both sides fixed or asleep)
+int rp_batch_pair_levels(rp_batch* b, uint32_t world, uint32_t* pairs_out, int32_t* levels_out, uint32_t max_pairs, uint32_t* n_out) {
+	if (!b || world >= (uint32_t)b->d.W || !n_out) return RP_ERR_ARG;
+	RP_CUDA(cudaSetDevice(b->device));
+	const DevView& d = b->d;
+	launch_broad(b);
+	launch_islands(b, 0.0);  // (dt = 0: the deactivation timers do not advance)
+	k_level_reset<<<1, 256, 0, b->stream>>>(d);
+	launch_schedule(b, 1);
+	RP_CUDA(cudaGetLastError());
+	std::vector<int> np, lv;
+	std::vector<PairRec> pr;
+	int rc = fetch(b, np, d.n_pairs + world, 1);
+	if (rc) return rc;
+	if ((rc = fetch_world(b, pr, d.pairs, (size_t)np[0], (int)world))) return rc;
+	if ((rc = fetch_world(b, lv, d.pair_level, (size_t)np[0], (int)world))) return rc;
+	for (int i = 0; i < np[0] && (uint32_t)i < max_pairs; ++i) {
+		if (pairs_out) {
+			pairs_out[2 * i] = (uint32_t)pr[i].a;
+			pairs_out[2 * i + 1] = (uint32_t)pr[i].b;
+		}
+		if (levels_out) levels_out[i] = lv[i];
+	}
+	*n_out = (uint32_t)np[0];
+	return RP_OK;
+}
+
 int rp_batch_step_logged(rp_batch* b, double dt, uint32_t substeps, uint32_t iters, int collisions, uint32_t world, uint32_t* calls_out,
 	uint32_t max_calls, double* contacts_out, uint32_t max_contacts, uint32_t* n_calls, uint32_t* n_contacts) {
 	if (!b || substeps == 0 || world >= (uint32_t)b->d.W || !n_calls || !n_contacts) return fail(RP_ERR_ARG, "rp_batch_step_logged: bad argument");
@@ -1143,7 +1344,7 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 		if ((rc = mark(-1))) return rc;
 		launch_broad(b);
 		if ((rc = mark(RP_K_BROAD))) return rc;
-		k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
+		launch_islands(b, dt);
 		if ((rc = mark(RP_K_ISLANDS))) return rc;
 		k_level_reset<<<1, 256, 0, b->stream>>>(d);
 		launch_schedule(b, collisions ? 1 : 0);

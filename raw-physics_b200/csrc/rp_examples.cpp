@@ -424,16 +424,17 @@ bool ex_debug(Build& b, const double*, uint32_t) {
 }
 
 // BASELINE config 4: a lattice of n_side^3 bodies alternating ico hull / cylinder hull scaled (1, 0.5, 1) / analytic sphere r = 1
-// above the floor, seeded random orientations; params: n_side, seed, spacing
+// above the floor, seeded random orientations; params: n_side, seed, spacing, layers (default n_side)
 bool ex_pile(Build& b, const double* p, uint32_t np) {
 	if (!add_floor(b)) return false;
 	const int n = (int)param(p, np, 0, 4);
 	NumpyRng rng((uint32_t)param(p, np, 1, 12345));
 	const double spacing = param(p, np, 2, 3.0);
+	const int layers = (int)param(p, np, 3, n);
 	std::vector<double> ico, cyl;
 	if (!load_soup(b, "ico", 1.0, 1.0, 1.0, ico) || !load_soup(b, "cylinder", 1.0, 0.5, 1.0, cyl)) return false;
 	int kind = 0;
-	for (int i = 0; i < n; ++i) {
+	for (int i = 0; i < layers; ++i) {
 		for (int j = 0; j < n; ++j) {
 			for (int l = 0; l < n; ++l) {
 				const V3 pos = v3((j - n / 2.0) * spacing, 1.5 + i * spacing, (l - n / 2.0) * spacing);

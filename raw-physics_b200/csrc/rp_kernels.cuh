@@ -100,6 +100,19 @@ __device__ __forceinline__ void st_contact(double* p, size_t S, const Contact& c
 __device__ __forceinline__ size_t bidx(const DevView& d, int b, int w) { return (size_t)b * d.WS + w; }  // per-body arrays
 __device__ __forceinline__ size_t pidx(const DevView& d, int p, int w) { return (size_t)p * d.WS + w; }  // per-pair arrays
 
+// Thread -> (item, world) for the kernels that do one thing per item per world, world fastest: consecutive threads are
+// consecutive worlds of one item, so world-minor accesses coalesce; a batch of fewer worlds than a warp (one large scene: WS = W
+// then, see rp_batch_create) gets consecutive ITEMS in a warp instead of 31 idle lanes per item, and the accesses still
+// coalesce because its world stride is W. Launch ceil(n_items * W / blockDim.x) CTAs (flat_grid).
+__device__ __forceinline__ bool flat_item_world(const DevView& d, int n_items, int* item, int* w) {
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long long)n_items * d.W) return false;
+	const int it = (int)(t / d.W);
+	*item = it;
+	*w = (int)(t - (long long)it * d.W);
+	return true;
+}
+
 __device__ __forceinline__ void load_static(Body& b, const DevView& d, int body) {
 	const BodyStatic& s = d.bstat[body];
 	const BodyClass& c = d.bclass[s.cls];
@@ -180,9 +193,8 @@ __device__ __forceinline__ PoseShape dev_pose_shape(const DevView& d, const Coll
 // steps each. Pass 1 leaves a bit mask of the near j of every cell and the number of collider pairs they expand to;
 // k_broad_scan turns the counts into offsets (cell order = pair order); pass 2 expands the masks. Nothing is tested twice.
 __global__ void __launch_bounds__(256) k_broad_cells(DevView d) {
-	const int w = blockIdx.y * 32 + threadIdx.x;
-	const int c = blockIdx.x * blockDim.y + threadIdx.y;
-	if (w >= d.W || c >= d.n_cells) return;
+	int w, c;
+	if (!flat_item_world(d, d.n_cells, &c, &w)) return;
 	const int2 cell = d.cells[c];
 	const int i = cell.x, j0 = cell.y;
 	const int j1 = j0 + 32 < d.NB ? j0 + 32 : d.NB;
@@ -292,9 +304,8 @@ __global__ void __launch_bounds__(32 * RP_BROAD_SEGS) k_broad_scan(DevView d) {
 // pass 2: every cell writes the pairs of its mask at its offset (collider pairs of one body pair stay adjacent, sub-collider
 // i outer, j inner: collider.cpp:563-571)
 __global__ void __launch_bounds__(256) k_broad_write(DevView d) {
-	const int w = blockIdx.y * 32 + threadIdx.x;
-	const int c = blockIdx.x * blockDim.y + threadIdx.y;
-	if (w >= d.W || c >= d.n_cells) return;
+	int w, c;
+	if (!flat_item_world(d, d.n_cells, &c, &w)) return;
 	unsigned int mask = d.cell_mask[(size_t)c * d.WS + w];
 	if (!mask) return;
 	int out = d.cell_off[(size_t)c * d.WS + w];
@@ -592,9 +603,8 @@ __device__ __forceinline__ void collider_bounds(const DevView& d, const Collider
 // for k_cull. Grid = (bodies, world blocks): a CTA is ONE body in 128 consecutive worlds, so the statics and the hull
 // are the same for every lane and every load/store of the world-minor arrays is coalesced.
 __global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate(DevView d, double h, int store_velocities) {
-	const int w = blockIdx.y * RP_INT_THREADS + threadIdx.x;
-	const int b = blockIdx.x;
-	if (w >= d.W) return;
+	int w, b;
+	if (!flat_item_world(d, d.NB, &b, &w)) return;
 	const int epoch = *d.epoch;
 	const size_t S = d.WS;
 	if (b < d.NJ) {  // copy_constraints resets every lambda each substep (pbd.cpp:426-462)
@@ -648,9 +658,8 @@ __global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate
 // the bounds of every collider, one thread per (collider, world): for scenes whose bodies carry so many vertices (compound
 // bodies of large hulls) that k_integrate's one thread per body would walk thousands of them
 __global__ void __launch_bounds__(RP_INT_THREADS) k_bounds(DevView d) {
-	const int w = blockIdx.y * RP_INT_THREADS + threadIdx.x;
-	const int c = blockIdx.x;
-	if (w >= d.W) return;
+	int w, c;
+	if (!flat_item_world(d, d.NC, &c, &w)) return;
 	const ColliderDesc cd = d.cols[c];
 	const DynRef r = dyn_ref(d, w, cd.body);
 	const V3 x = ld3(r, DF_X);
@@ -1475,9 +1484,8 @@ __global__ void RP_POS_BOUNDS k_solve_pos(DevView d, double h, int iters, int co
 // body's own (x, q, prev x, prev q, v, w), none of which the velocity pass writes before deriving, so WHEN it happens
 // between the positional sweep and the first read of v/w does not change a bit.
 __global__ void __launch_bounds__(128) k_derive(DevView d, double h) {
-	const int w = blockIdx.y * blockDim.x + threadIdx.x;
-	const int b = blockIdx.x;
-	if (w >= d.W) return;
+	int w, b;
+	if (!flat_item_world(d, d.NB, &b, &w)) return;
 	const int epoch = *d.epoch;
 	// every body leaves the frame stamped "current" (a body that wakes up next frame must not look pending)
 	if (d.vstamp[bidx(d, b, w)] == epoch) return;
