@@ -66,6 +66,7 @@ struct rp_batch {
 	size_t live_smem = 0;      // dynamic shared memory of the sweep kernels for that list
 	unsigned int transform_slices = 1;  // gridDim.z of k_transform: threads that share one collider's vertices and normals
 	bool has_big_pairs = false;   // some collider pair is too large for k_gjk's per-thread staging: k_gjk_warp is launched too
+	bool no_islands = false;      // rp_batch_cfg.disable_islands: nothing ever falls asleep (the reference without ENABLE_SIMULATION_ISLANDS)
 	bool no_restitution = false;  // every body's restitution coefficient is zero (k_integrate's store_velocities)
 	// one large scene (rp_large.cuh): uniform-grid broadphase, union-find islands, parallel colouring
 	bool large = false;
@@ -516,6 +517,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	d.max_contacts = (int)(cfg.max_contacts_per_world ? cfg.max_contacts_per_world : std::max<size_t>(256, 8 * (size_t)d.NB));
 	d.max_units = d.NJ + d.max_pairs;
 	b->cull = cfg.disable_cull ? 0 : 1;
+	b->no_islands = cfg.disable_islands != 0;
 	{
 		// k_cull: grid.y = groups of 32 worlds (lane = world), a CTA's 8 warps take 8 pair indices per trip
 		const int groups = (d.W + 31) / 32;
@@ -724,7 +726,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 			const int nv = s.colliders[c].nv;
 			if (nv > n1) { n2 = n1; n1 = nv; } else if (nv > n2) n2 = nv;
 		}
-		b->has_big_pairs = (n1 + n2) * 3 > RP_GJK_STAGE;
+		b->has_big_pairs = warp_pair_verts(n1 + n2);
 		// heavy geometry: bounds per collider instead of per body, and several threads per collider in k_transform
 		int body_most = 0, collider_most = 0;
 		for (size_t i = 0; i < s.bodies.size(); ++i) {
@@ -868,6 +870,7 @@ static void launch_colouring(rp_batch* b, int collisions) {
 }
 static void launch_islands(rp_batch* b, double dt) {
 	const DevView& d = b->d;
+	if (b->no_islands) return;  // pbd.cpp:476-533 compiled out: every body stays active, no deactivation timers
 	if (!b->large) {
 		k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
 		return;
@@ -978,6 +981,7 @@ static void launch_manifold(rp_batch* b) {
 	k_epa<<<b->sm_count * 16, RP_EPA_THREADS, RP_EPA_SMEM_BYTES, b->stream>>>(b->d);
 	if (b->has_big_pairs) k_epa_warp<<<b->sm_count * 8, RP_GJK_WARP_THREADS, 0, b->stream>>>(b->d);
 	k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, RP_MANIFOLD_SMEM_BYTES, b->stream>>>(b->d);
+	if (b->has_big_pairs) k_manifold_warp<<<b->sm_count * 8, RP_CLIPW_THREADS, 0, b->stream>>>(b->d);
 }
 static void enqueue_narrow(rp_batch* b) {
 	launch_cull(b);
@@ -1364,6 +1368,7 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 				if (b->has_big_pairs) k_epa_warp<<<b->sm_count * 8, RP_GJK_WARP_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_EPA))) return rc;
 				k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, RP_MANIFOLD_SMEM_BYTES, b->stream>>>(d);
+				if (b->has_big_pairs) k_manifold_warp<<<b->sm_count * 8, RP_CLIPW_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_MANIFOLD))) return rc;
 			}
 			if (b->sweep_wpb > 0) {

@@ -45,6 +45,14 @@
 
 #define RP_GJK_THREADS 64
 #define RP_GJK_STAGE 48          // doubles of shared memory per thread: two hulls of up to 16 vertices in total
+// Three sizes of collider pair. Up to RP_GJK_STAGE / 3 vertices in total: one thread per pair, both hulls staged in shared memory
+// (k_gjk). Up to RP_WARP_PAIR_VERTS: still one thread per pair, vertices evaluated from the pose at every use (icosahedra, the
+// 58-vertex spot hulls against a box: a warp per pair would idle most of its lanes in every scan). Above: one WARP per pair
+// (k_gjk_warp, k_epa_warp, k_manifold_warp: cylinders with 128 vertices, 64-gon faces).
+#ifndef RP_WARP_PAIR_VERTS
+#define RP_WARP_PAIR_VERTS 72
+#endif
+__host__ __device__ __forceinline__ bool warp_pair_verts(int total_vertices) { return total_vertices > RP_WARP_PAIR_VERTS; }
 #define RP_MANIFOLD_THREADS 128
 #define RP_EPA_THREADS 64
 
@@ -817,7 +825,7 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 			const int p = p0 + u * stride;
 			if (in[u]) d.pair_ccnt[pidx(d, p, w)] = 0;
 			// pairs whose hulls do not fit k_gjk's per-thread staging block go to the back of the list, for k_gjk_warp
-			const bool big = keep[u] && (d.cols[pr[u].ca].nv + d.cols[pr[u].cb].nv) * 3 > RP_GJK_STAGE;
+			const bool big = keep[u] && warp_pair_verts(d.cols[pr[u].ca].nv + d.cols[pr[u].cb].nv);
 			const unsigned int front = warp_append(d.cand_count, keep[u] && !big);
 			const unsigned int back = warp_append(d.big_count, big);
 			const unsigned int slot = big ? d.cand_cap - 1u - back : front;
@@ -1050,7 +1058,7 @@ __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) 
 	for (unsigned int hi = blockIdx.x * blockDim.x + threadIdx.x; hi < nh; hi += gridDim.x * blockDim.x) {
 		const uint4 cd = d.hits[hi];
 		const int w = (int)cd.x;
-		if (d.split_big && (d.cols[cd.z].nv + d.cols[cd.w].nv) * 3 > RP_GJK_STAGE) continue;  // k_epa_warp's
+		if (d.split_big && warp_pair_verts(d.cols[cd.z].nv + d.cols[cd.w].nv)) continue;  // k_epa_warp's
 		PoseShape A = dev_pose_shape(d, d.cols[cd.z], w);
 		PoseShape B = dev_pose_shape(d, d.cols[cd.w], w);
 		EpaOut out;
@@ -1091,7 +1099,7 @@ __global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_epa_warp(DevView d) {
 	const unsigned int warps = gridDim.x * (RP_GJK_WARP_THREADS / 32);
 	for (unsigned int hi = blockIdx.x * (RP_GJK_WARP_THREADS / 32) + wib; hi < nh; hi += warps) {
 		const uint4 cd = d.hits[hi];
-		if (!((d.cols[cd.z].nv + d.cols[cd.w].nv) * 3 > RP_GJK_STAGE)) continue;  // k_epa's
+		if (!(warp_pair_verts(d.cols[cd.z].nv + d.cols[cd.w].nv))) continue;  // k_epa's
 		const int w = (int)cd.x;
 		PoseShape A = dev_pose_shape(d, d.cols[cd.z], w);
 		PoseShape B = dev_pose_shape(d, d.cols[cd.w], w);
@@ -1209,7 +1217,9 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 			w = (int)cd.x; pair = (int)cd.y;
 			const size_t pg = pidx(d, pair, w);
 			int st = 0;
-			if (eo.ok) {
+			// pairs of large hulls are k_manifold_warp's (the whole warp clips one polygon)
+			const bool warp_pair = d.split_big && warp_pair_verts(d.cols[cd.z].nv + d.cols[cd.w].nv);
+			if (eo.ok && !warp_pair) {
 				const PairRec pr = d.pairs[pg];
 				const int ta = d.cols[cd.z].type, tb = d.cols[cd.w].type;
 				int off = 0;
@@ -1229,11 +1239,7 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 					}
 					n = emit_contacts(d, cs, r, eo.normal, w, pr, &off, &st);
 				} else {
-					int sup1 = -1, sup2 = -1;
-					if (d.split_big && (d.cols[cd.z].nv + d.cols[cd.w].nv) * 3 > RP_GJK_STAGE) {
-						const int2 sup = d.big_sup[hi];
-						sup1 = sup.x; sup2 = sup.y;
-					}
+					const int sup1 = -1, sup2 = -1;
 					ClipResult r;
 					int ov;
 					{
@@ -1287,6 +1293,215 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 		}
 	}
 	for (int o = 16; o > 0; o >>= 1) made += __shfl_down_sync(0xffffffffu, made, o);
+	if (lane == 0 && made) atomicAdd(&d.counters[CNT_CONTACTS], (unsigned long long)made);
+}
+
+// ---- one WARP per colliding pair of LARGE hulls (the pairs k_gjk_warp / k_epa_warp took): Sutherland-Hodgman with the lanes
+// sharing out the polygon. A cylinder cap is a 64-gon clipped against the 64 side planes of the other cap (clipping.cpp:52-113);
+// one thread walking that is 4096 dependent inside tests per pair. Here, per plane, lane l takes vertices l, l + 32, ...: the
+// inside test of the vertex and of its predecessor, the edge intersection if they differ (the same expressions, float round
+// trips included), and a warp prefix sum of the 0 / 1 / 2 points each lane emits puts them where the sequential loop would
+// (intersection before end point, edges in order). Face selection and the edge-edge test run redundantly on all lanes (the
+// same instance, as in k_epa_warp). The final cull against the reference plane and the contact emission are compactions of
+// the same kind.
+#define RP_CLIPW_THREADS 128
+__device__ __forceinline__ int warp_exclusive_scan(int v, int* total) {
+	const int lane = threadIdx.x & 31;
+	int inc = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const int t = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= o) inc += t;
+	}
+	*total = __shfl_sync(0xffffffffu, inc, 31);
+	return inc - v;
+}
+// one pass of `in` (n_in points) against a plane into `out`; returns the number of points written, -1 if they do not fit
+__device__ __forceinline__ int warp_clip_pass(const ClipPlane& pl, const V3* in, int n_in, V3* out, bool remove_only) {
+	const int lane = threadIdx.x & 31;
+	const float offset = clip_offset(pl);
+	int base = 0;
+	bool overflow = false;
+	for (int j0 = 0; j0 < n_in; j0 += 32) {
+		const int j = j0 + lane;
+		int cnt = 0;
+		bool has_x = false;
+		V3 x = v3(0.0, 0.0, 0.0), end = v3(0.0, 0.0, 0.0);
+		bool e_in = false;
+		if (j < n_in) {
+			end = in[j];
+			const V3 start = in[j == 0 ? n_in - 1 : j - 1];
+			e_in = clip_inside(pl, offset, end);
+			if (remove_only) {
+				cnt = e_in ? 1 : 0;
+			} else {
+				const bool s_in = clip_inside(pl, offset, start);
+				if (s_in != e_in) has_x = clip_edge(pl, offset, start, end, &x);
+				cnt = (has_x ? 1 : 0) + (e_in ? 1 : 0);
+			}
+		}
+		int total;
+		int at = base + warp_exclusive_scan(cnt, &total);
+		if (base + total > RP_CLIP_MAX_POINTS) {
+			overflow = true;
+			break;
+		}
+		if (has_x) out[at++] = x;
+		if (e_in && j < n_in) out[at] = end;
+		base += total;
+	}
+	__syncwarp();
+	return overflow ? -1 : base;
+}
+
+__global__ void __launch_bounds__(RP_CLIPW_THREADS) k_manifold_warp(DevView d) {
+	const unsigned int nh = *d.hit_count;
+	__shared__ V3 s_poly[RP_CLIPW_THREADS / 32][2][RP_CLIP_MAX_POINTS];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const unsigned int warps = gridDim.x * (RP_CLIPW_THREADS / 32);
+	int made = 0;
+	for (unsigned int hi = blockIdx.x * (RP_CLIPW_THREADS / 32) + wib; hi < nh; hi += warps) {
+		const uint4 cd = d.hits[hi];
+		if (!(warp_pair_verts(d.cols[cd.z].nv + d.cols[cd.w].nv))) continue;  // k_manifold's
+		const EpaOut eo = d.epa_out[hi];
+		if (!eo.ok) continue;
+		const int w = (int)cd.x, pair = (int)cd.y;
+		const size_t pg = pidx(d, pair, w);
+		const PairRec pr = d.pairs[pg];
+		const PoseShape A = dev_pose_shape(d, d.cols[cd.z], w);
+		const PoseShape B = dev_pose_shape(d, d.cols[cd.w], w);
+		const V3 normal = eo.normal;
+		int st = 0;
+		V3* buf0 = s_poly[wib][0];
+		V3* buf1 = s_poly[wib][1];
+		__syncwarp();
+		// the n contacts end up as (pts1[k], pts2[k])
+		int n = 0;
+		V3* pts1 = buf0;
+		V3* pts2 = buf1;
+		if (A.type == SHAPE_SPHERE || B.type == SHAPE_SPHERE) {  // clipping.cpp:348-364
+			if (lane == 0) {
+				if (A.type == SHAPE_SPHERE) {
+					buf0[0] = support(A, normal);
+					buf1[0] = sub(buf0[0], scale(eo.depth, normal));
+				} else {
+					buf1[0] = support(B, zero_minus(normal));
+					buf0[0] = add(buf1[0], scale(eo.depth, normal));
+				}
+			}
+			n = 1;
+		} else {
+			const int2 sup = d.big_sup[hi];
+			FaceChoice fc;
+			manifold_select(A, B, normal, &st, &fc, sup.x, sup.y);
+			if (fc.kind == 1) {
+				if (lane == 0) {
+					buf0[0] = fc.l1;
+					buf1[0] = fc.l2;
+				}
+				n = 1;
+			} else if (fc.kind == 2) {
+				const PoseShape& R = fc.ref1 ? A : B;
+				const PoseShape& I = fc.ref1 ? B : A;
+				// incident polygon (clipping.cpp:241-247)
+				int m = I.face_ptr[fc.iface + 1] - I.face_ptr[fc.iface];
+				if (m > RP_CLIP_MAX_POINTS) {
+					st |= ST_CLIP_CAPACITY;
+					m = 0;
+				}
+				for (int k = lane; k < m; k += 32) buf0[k] = vert(I, I.face_idx[I.face_ptr[fc.iface] + k]);
+				__syncwarp();
+				V3* cur = buf0;
+				V3* oth = buf1;
+				for (int k = R.f2n_ptr[fc.rface]; k < R.f2n_ptr[fc.rface + 1] && m > 0; ++k) {
+					const int nf = R.f2n_idx[k];
+					ClipPlane pl;
+					pl.point = vert(R, R.face_idx[R.face_ptr[nf]]);
+					pl.normal = zero_minus(fnormal(R, nf));
+					m = warp_clip_pass(pl, cur, m, oth, false);
+					if (m < 0) {
+						st |= ST_CLIP_CAPACITY;
+						m = 0;
+					}
+					V3* t = cur; cur = oth; oth = t;
+				}
+				ClipPlane rp;
+				rp.normal = zero_minus(fc.ref_normal);
+				rp.point = vert(R, R.face_idx[R.face_ptr[fc.rface]]);
+				if (m > 0) {
+					m = warp_clip_pass(rp, cur, m, oth, true);
+					V3* t = cur; cur = oth; oth = t;
+				}
+				// penetration of every candidate (clipping.cpp:322-338) and ordered compaction of the contacts: p1 into `oth`, p2 in
+				// place over `cur` (slot at <= j, and every candidate of the trip has been read before any slot is written)
+				int base = 0;
+				for (int j0 = 0; j0 < m; j0 += 32) {
+					const int j = j0 + lane;
+					V3 p1 = v3(0.0, 0.0, 0.0), p2 = p1;
+					const bool hit = j < m && manifold_point(cur[j], rp.normal, rp.point, fc.ref1, normal, &p1, &p2);
+					int total;
+					const int at = base + warp_exclusive_scan(hit ? 1 : 0, &total);
+					__syncwarp();
+					if (hit) {
+						oth[at] = p1;
+						cur[at] = p2;
+					}
+					base += total;
+				}
+				n = base;
+				pts1 = oth;
+				pts2 = cur;
+			}
+		}
+		__syncwarp();
+		int off = 0;
+		if (n > 0) {
+			if (lane == 0) {
+				off = atomicAdd(&d.n_contacts[w], n);
+				if (off + n > d.max_contacts) {
+					st |= ST_CONTACT_CAPACITY;
+					n = d.max_contacts - off;
+					if (n < 0) n = 0;
+				}
+			}
+			off = __shfl_sync(0xffffffffu, off, 0);
+			n = __shfl_sync(0xffffffffu, n, 0);
+			Body b1, b2;
+			const DynRef ra = dyn_ref(d, w, pr.a);
+			const DynRef rb = dyn_ref(d, w, pr.b);
+			b1.x = ld3(ra, DF_X); b1.q = ld4(ra, DF_Q);
+			b2.x = ld3(rb, DF_X); b2.q = ld4(rb, DF_Q);
+			for (int k = lane; k < n; k += 32) {
+				st_contact(contact_ptr(d, w, off + k), d.WS, make_contact(b1, b2, pts1[k], pts2[k]));
+				if (w == d.dbg_world) {
+					d.dbg_points[2 * (off + k)] = pts1[k];
+					d.dbg_points[2 * (off + k) + 1] = pts2[k];
+				}
+			}
+		}
+		if (lane == 0) {
+			if (n > 0) {
+				d.pair_normal[pg] = normal;
+				d.pair_coff[pg] = off;
+				d.pair_ccnt[pg] = n;
+				made += n;
+				const int lvl = d.pair_level[pg];
+				if (lvl > 0) {
+					if (d.block_mode) {
+						const int slot = atomicAdd(&d.n_live[w], 1);
+						d.live[(size_t)slot * d.WS + w] = make_uint2((unsigned int)pair, (unsigned int)lvl);
+					} else {
+						SolveItem item;
+						item.w = w; item.a = pr.a; item.b = pr.b; item.coff = off; item.cnt = n; item.pad = 0; item.normal = normal;
+						const int big = n > RP_SMALL_MANIFOLD ? 1 : 0;
+						const int slot = atomicAdd(&d.lvl_fill[(size_t)lvl * RP_LVL_STRIDE + big], 1);
+						d.lvl_items[big ? d.lvl_off[lvl + 1] - 1 - slot : d.lvl_off[lvl] + slot] = item;
+					}
+				}
+			}
+			if (st) atomicOr(&d.status[w], st);
+		}
+	}
 	if (lane == 0 && made) atomicAdd(&d.counters[CNT_CONTACTS], (unsigned long long)made);
 }
 

@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(256) k_cull_flat(DevView d, int cull) {
 			if (lo_a - hi_b > RP_CULL_MARGIN || lo_b - hi_a > RP_CULL_MARGIN) keep = false;
 		}
 	}
-	if (keep) big = (d.cols[pr.ca].nv + d.cols[pr.cb].nv) * 3 > RP_GJK_STAGE;
+	if (keep) big = warp_pair_verts(d.cols[pr.ca].nv + d.cols[pr.cb].nv);
 	const unsigned int front = warp_append(d.cand_count, keep && !big);
 	const unsigned int back = warp_append(d.big_count, big);
 	if (keep) {

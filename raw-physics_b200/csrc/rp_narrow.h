@@ -544,10 +544,18 @@ struct ClipResult {
 	V3 rp_normal, rp_point;  // reference plane (inverted face normal, first face vertex), kind 2
 };
 
-template <class S, class C>
-RP_HD int manifold_clip(const S& h1, const S& h2, V3 normal, C& cs, int* status, ClipResult* out, int sup1_known = -1,
-	int sup2_known = -1) {
-	out->kind = 0; out->n = 0; out->cur = 0; out->ref1 = false;
+// front half of convex_convex_contact_manifold (clipping.cpp:249-300): support vertices, best-aligned faces, the edge-edge
+// test; the result is either the single edge contact or which face is clipped against which
+struct FaceChoice {
+	int kind;          // 0: nothing (the reference would have aborted), 1: edge-edge contact (l1, l2), 2: clip iface against rface's neighbours
+	bool ref1;         // the reference face is on hull 1
+	int rface, iface;
+	V3 l1, l2;
+	V3 ref_normal;     // normal of the reference face
+};
+template <class S>
+RP_HD void manifold_select(const S& h1, const S& h2, V3 normal, int* status, FaceChoice* out, int sup1_known = -1, int sup2_known = -1) {
+	out->kind = 0; out->ref1 = false; out->rface = out->iface = 0;
 	V3 inv_normal = zero_minus(normal);
 	int sup1 = sup1_known >= 0 ? sup1_known : support_index(h1, normal);
 	int sup2 = sup2_known >= 0 ? sup2_known : support_index(h2, inv_normal);
@@ -619,17 +627,33 @@ RP_HD int manifold_clip(const S& h1, const S& h2, V3 normal, C& cs, int* status,
 		V3 d2 = sub(vert(h2, e2n), p2);
 		if (!clip_skew_lines(p1, d1, p2, d2, &out->l1, &out->l2)) {
 			*status |= ST_EDGE_PARALLEL;  // the reference aborts (clipping.cpp:279)
-			return CLIP_OK;
+			return;
 		}
 		out->kind = 1;
+		return;
+	}
+	out->kind = 2;
+	out->ref1 = dot1 > dot2;
+	out->rface = out->ref1 ? face1 : face2;
+	out->iface = out->ref1 ? face2 : face1;
+	out->ref_normal = out->ref1 ? f1n : f2n;
+}
+
+template <class S, class C>
+RP_HD int manifold_clip(const S& h1, const S& h2, V3 normal, C& cs, int* status, ClipResult* out, int sup1_known = -1,
+	int sup2_known = -1) {
+	out->kind = 0; out->n = 0; out->cur = 0; out->ref1 = false;
+	FaceChoice fc;
+	manifold_select(h1, h2, normal, status, &fc, sup1_known, sup2_known);
+	if (fc.kind == 0) return CLIP_OK;
+	if (fc.kind == 1) {
+		out->kind = 1; out->l1 = fc.l1; out->l2 = fc.l2;
 		return CLIP_OK;
 	}
-
-	bool ref1 = dot1 > dot2;
+	const bool ref1 = fc.ref1;
 	const S& R = ref1 ? h1 : h2;   // reference hull
 	const S& I = ref1 ? h2 : h1;   // incident hull
-	int rface = ref1 ? face1 : face2;
-	int iface = ref1 ? face2 : face1;
+	const int rface = fc.rface, iface = fc.iface;
 
 	// incident polygon (get_vertices_of_faces, clipping.cpp:241-247)
 	int cur = 0;
@@ -658,7 +682,7 @@ RP_HD int manifold_clip(const S& h1, const S& h2, V3 normal, C& cs, int* status,
 		}
 		cur ^= 1;
 	}
-	out->rp_normal = zero_minus(ref1 ? f1n : f2n);
+	out->rp_normal = zero_minus(fc.ref_normal);
 	out->rp_point = vert(R, R.face_idx[R.face_ptr[rface]]);
 	if (n != 0) {
 		ClipPlane rp;
@@ -671,6 +695,26 @@ RP_HD int manifold_clip(const S& h1, const S& h2, V3 normal, C& cs, int* status,
 	return CLIP_OK;
 }
 
+// one candidate point of the clipped polygon (clipping.cpp:322-338): its penetration along the normal; a contact if negative
+RP_HD bool manifold_point(V3 p, V3 rp_normal, V3 rp_point, bool ref1, V3 normal, V3* p1, V3* p2) {
+	// get_closest_point_polygon (clipping.cpp:115-119)
+	double dd = dot(scale(-1.0, rp_normal), rp_point);
+	V3 closest = sub(p, scale(dot(rp_normal, p) + dd, rp_normal));
+	V3 diff = sub(p, closest);
+	if (ref1) {
+		double pen = dot(diff, normal);
+		if (!(pen < 0.0)) return false;
+		*p1 = sub(p, scale(pen, normal));
+		*p2 = p;
+	} else {
+		double pen = -dot(diff, normal);
+		if (!(pen < 0.0)) return false;
+		*p1 = p;
+		*p2 = add(p, scale(pen, normal));
+	}
+	return true;
+}
+
 // Sink: void operator()(V3 p1, V3 p2), called once per contact in the reference's order
 template <class C, class Sink>
 RP_HD void manifold_emit(const C& cs, const ClipResult& r, V3 normal, Sink& sink) {
@@ -680,18 +724,8 @@ RP_HD void manifold_emit(const C& cs, const ClipResult& r, V3 normal, Sink& sink
 	}
 	if (r.kind != 2) return;
 	for (int k = 0; k < r.n; ++k) {
-		V3 p = cs.get(r.cur, k);
-		// get_closest_point_polygon (clipping.cpp:115-119)
-		double dd = dot(scale(-1.0, r.rp_normal), r.rp_point);
-		V3 closest = sub(p, scale(dot(r.rp_normal, p) + dd, r.rp_normal));
-		V3 diff = sub(p, closest);
-		if (r.ref1) {
-			double pen = dot(diff, normal);
-			if (pen < 0.0) sink(sub(p, scale(pen, normal)), p);
-		} else {
-			double pen = -dot(diff, normal);
-			if (pen < 0.0) sink(p, add(p, scale(pen, normal)));
-		}
+		V3 p1, p2;
+		if (manifold_point(cs.get(r.cur, k), r.rp_normal, r.rp_point, r.ref1, normal, &p1, &p2)) sink(p1, p2);
 	}
 }
 

@@ -1,7 +1,7 @@
 # the other BASELINE configurations through bench.py: `gpurun --timeout 900 -- 'bash scripts/gpu_workloads.sh TAG'`
 T=${1:-wl}
 mkdir -p gpurun_out
-for WL in c2 c3 c5; do
+for WL in ${2:-c2 c3 c5 pile}; do
   timeout 400 python bench.py --workload $WL --warmup 3 > gpurun_out/${T}_$WL.json 2> gpurun_out/${T}_$WL.err || tail -5 gpurun_out/${T}_$WL.err
   python -c "
 import json

@@ -515,3 +515,24 @@ def test_world_block_sweeps_deep_levels(pkg, oracle_flavour):
     got = b.state()
     assert np.array_equal(got[0, :, :15], o.state()) and np.array_equal(got[0], got[2])
     assert not b.status().any()
+
+
+def test_islands_disabled_nothing_sleeps(pkg, oracle_flavour):
+    """rp_batch_cfg.disable_islands = the reference compiled without ENABLE_SIMULATION_ISLANDS (pbd.cpp:12, :476-533): no
+    deactivation timers, every body stays active. Until the first island of the reference falls asleep the two are the same
+    computation (bit for bit); afterwards the reference's cubes rest while these keep being solved."""
+    sc = scenes.stack()
+    b = make(pkg, sc, n_worlds=2, disable_islands=True)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    diverged_at = None
+    for f in range(600):
+        step(b, sc)
+        o.step()
+        if diverged_at is None and not o.state()[1:, 13].all():
+            diverged_at = f
+        if diverged_at is None and f % 20 == 19:
+            assert np.array_equal(b.state()[0, :, :13], o.state()[:, :13]), f
+    st = b.state()[0]
+    assert diverged_at is not None and diverged_at > 100
+    assert st[:, 13].all() and not st[:, 14].any()  # all active, timers untouched
+    assert not b.status().any()
