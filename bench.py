@@ -547,6 +547,7 @@ def run_ours(args):
                         "peak_source": "rp_measure_fp64_peak (DMUL+DADD chains, this run)"}
         per = W * SUB * args.steps
         line["work_per_world_substep"] = {"pair_tests": tests / per, "gjk_runs": runs / per, "epa_runs": hits / per, "contacts": contacts / per}
+        line["sweep_depth"] = (c1["levels"] - c0["levels"]) / (W * args.steps)  # levels (reference order) / colours walked per sweep
         if dist is not None:  # NCCL only gathers aggregate statistics
             t = job.sum_over_ranks([tests, hits, contacts])
             line["aggregate_work"] = {"pair_tests": float(t[0]), "epa_runs": float(t[1]), "contacts": float(t[2])}

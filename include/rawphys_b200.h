@@ -163,6 +163,11 @@ void rp_batch_cfg_default(rp_batch_cfg* cfg);
 /* 1 <= n_worlds <= 65535 per batch (several batches may live on one device, each with its own stream); RP_ERR_ARG otherwise.
  * Device memory is allocated here and nowhere else: about 1.1 MB per world of 257 bodies. */
 int rp_batch_create(const rp_scene* scene, uint32_t n_worlds, int cuda_device, const rp_batch_cfg* cfg_or_null, rp_batch** out);
+/* Entity counts that change mid-run (examples_util_throw_object, examples_util.cpp:52-95, creates bodies between frames;
+ * entity_destroy, entity.cpp:67-77, removes them): a new batch for `scene` -- same world count, same device as `src` -- whose
+ * body i takes its state in every world from body new_from_old[i] of `src` (device to device), or starts from the scene's initial
+ * state where new_from_old[i] = -1. `src` stays valid and is destroyed separately. Between frames only. */
+int rp_batch_create_from(const rp_scene* scene, rp_batch* src, const int32_t* new_from_old, const rp_batch_cfg* cfg_or_null, rp_batch** out);
 void rp_batch_destroy(rp_batch* b);
 uint32_t rp_batch_num_worlds(const rp_batch* b);
 uint32_t rp_batch_num_bodies(const rp_batch* b);

@@ -32,7 +32,7 @@ EXPORTS = [
     "rp_batch_run", "rp_batch_upload_state", "rp_batch_download_state", "rp_batch_broadcast_state", "rp_batch_step_host",
     "rp_batch_get_status", "rp_batch_clear_status", "rp_batch_get_counters", "rp_batch_step_logged", "rp_batch_broad_pairs", "rp_batch_profile",
     "rp_measure_fp64_peak", "rp_scene_initial_state", "rp_scene_body_desc", "rp_scene_collider_soup_size", "rp_scene_collider_soup",
-    "rp_scene_num_joints", "rp_scene_joint_desc", "rp_batch_graph_kernels", "rp_batch_pair_levels", "rp_example_count", "rp_example_name", "rp_example_error", "rp_example_create",
+    "rp_scene_num_joints", "rp_scene_joint_desc", "rp_batch_graph_kernels", "rp_batch_pair_levels", "rp_batch_create_from", "rp_example_count", "rp_example_name", "rp_example_error", "rp_example_create",
 ]
 KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "cull", "gjk", "manifold", "solve_pos", "derive", "solve_vel", "epa"]
 
@@ -86,6 +86,7 @@ def lib():
     L.rp_batch_cfg_default.argtypes = [C.POINTER(BatchCfg)]
     L.rp_batch_create.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(BatchCfg), C.POINTER(C.c_void_p)]
     L.rp_batch_destroy.argtypes = [C.c_void_p]
+    L.rp_batch_create_from.argtypes = [C.c_void_p, C.c_void_p, _i32p, C.POINTER(BatchCfg), C.POINTER(C.c_void_p)]
     L.rp_batch_num_worlds.argtypes = [C.c_void_p]
     L.rp_batch_num_worlds.restype = C.c_uint32
     L.rp_batch_num_bodies.argtypes = [C.c_void_p]
@@ -326,6 +327,23 @@ class Batch:
         self.h = h
         self.W = int(self.L.rp_batch_num_worlds(h))
         self.NB = int(self.L.rp_batch_num_bodies(h))
+
+    @classmethod
+    def create_from(cls, scene, src, new_from_old):
+        """A batch for `scene` whose body i continues body new_from_old[i] of `src` in every world (-1: a new body, from the
+        scene's initial state): entity counts that change mid-run (rp_batch_create_from)."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        self.scene = scene
+        m = np.ascontiguousarray(new_from_old, dtype=np.int32)
+        if m.shape != (scene.n,):
+            raise ValueError("one entry per body of the new scene")
+        h = C.c_void_p()
+        _check(self.L.rp_batch_create_from(scene.h, src.h, m.ctypes.data_as(_i32p), None, C.byref(h)), "rp_batch_create_from")
+        self.h = h
+        self.W = int(self.L.rp_batch_num_worlds(h))
+        self.NB = int(self.L.rp_batch_num_bodies(h))
+        return self
 
     def close(self):
         if getattr(self, "h", None):

@@ -810,6 +810,36 @@ int rp_batch_create(const rp_scene* scene, uint32_t n_worlds, int device, const 
 	return RP_OK;
 }
 
+int rp_batch_create_from(const rp_scene* scene, rp_batch* src, const int32_t* new_from_old, const rp_batch_cfg* cfg, rp_batch** out) {
+	if (!scene || !src || !new_from_old || !out || scene->s.bodies.empty()) return fail(RP_ERR_ARG, "rp_batch_create_from: bad argument");
+	if (!scene->s.pending.empty()) return fail(RP_ERR_ARG, "rp_batch_create_from: colliders queued without a body");
+	const int nb = (int)scene->s.bodies.size();
+	std::vector<int> map(new_from_old, new_from_old + nb);
+	for (int i = 0; i < nb; ++i) {
+		if (map[i] >= src->d.NB) return fail(RP_ERR_ARG, "rp_batch_create_from: mapping points past the source's bodies");
+	}
+	rp_batch* b = new rp_batch();
+	int rc = create_impl(scene, (uint32_t)src->d.W, src->device, cfg, b);
+	if (!rc) {
+		// state moves device to device: the source's stream first finishes what it was given
+		const int* map_dev = 0;
+		if (cudaStreamSynchronize(src->stream) != cudaSuccess) rc = fail(RP_ERR_CUDA, "rp_batch_create_from: source stream");
+		if (!rc) rc = dev_upload(b, &map_dev, map);
+		if (!rc) {
+			k_adopt_bodies<<<flat_grid(b, (size_t)nb, 128), 128, 0, b->stream>>>(b->d, src->d, map_dev);
+			if (cudaStreamSynchronize(b->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = fail(RP_ERR_CUDA, "rp_batch_create_from: copy");
+		}
+	}
+	if (rc) {
+		std::string keep = g_err;
+		rp_batch_destroy(b);
+		g_err = keep;
+		return rc;
+	}
+	*out = b;
+	return RP_OK;
+}
+
 uint32_t rp_batch_num_worlds(const rp_batch* b) { return b ? (uint32_t)b->d.W : 0; }
 uint32_t rp_batch_num_bodies(const rp_batch* b) { return b ? (uint32_t)b->d.NB : 0; }
 

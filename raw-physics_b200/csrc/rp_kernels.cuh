@@ -2028,6 +2028,20 @@ __global__ void __launch_bounds__(256) k_fp64_probe(double* out, int iters, doub
 
 __global__ void k_count_frame(DevView d) { atomicAdd(&d.counters[CNT_FRAMES], 1ull); }
 
+// rp_batch_create_from: the per-world state of body `map[i]` of another batch becomes the state of body i of this one
+__global__ void __launch_bounds__(128) k_adopt_bodies(DevView dst, DevView src, const int* map) {
+	int w, b;
+	if (!flat_item_world(dst, dst.NB, &b, &w)) return;
+	const int o = map[b];
+	if (o < 0) return;
+	const DynRef to = dyn_ref(dst, w, b), from = dyn_ref(src, w, o);
+#pragma unroll
+	for (int f = 0; f < RP_DYN_DOUBLES; ++f) to.p[f * to.s] = from.p[f * from.s];
+	dst.active[bidx(dst, b, w)] = src.active[bidx(src, o, w)];
+	dst.deact[bidx(dst, b, w)] = src.deact[bidx(src, o, w)];
+	dst.vstamp[bidx(dst, b, w)] = *dst.epoch;  // between frames every body's velocities are current (k_derive)
+}
+
 // OR of the capacity bits of every world's status word (rp_batch_sync and the other synchronising calls report it)
 __global__ void __launch_bounds__(256) k_status_overflow(DevView d, int* out) {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;

@@ -125,6 +125,22 @@ class RefWorld:
         self.n = int(L.ref_num_entities())
         return self
 
+    def add_body(self, b):
+        """entity_create[_fixed] for one more body of a scenes.BodyDesc kind, at any time (bodies thrown in mid-run)"""
+        L = self.lib
+        L.ref_collider_begin()
+        for col in b.colliders:
+            if col.kind == "sphere":
+                L.ref_collider_add_sphere(C.c_float(col.radius))
+            else:
+                v = np.ascontiguousarray(col.vertices, dtype=np.float64)
+                idx = np.ascontiguousarray(col.indices, dtype=np.uint32)
+                L.ref_collider_add_hull(_d(v), v.shape[0], _u(idx), idx.shape[0])
+        pos = np.asarray(b.position, dtype=np.float64)
+        quat = np.asarray(b.rotation, dtype=np.float64)
+        L.ref_entity_create(_d(pos), _d(quat), b.mass, int(b.fixed), b.mu_s, b.mu_d, b.restitution)
+        self.n = int(L.ref_num_entities())
+
     def quaternion_new(self, axis, angle_degrees):
         a = np.asarray(axis, dtype=np.float64)
         out = np.zeros(4)

@@ -536,3 +536,41 @@ def test_islands_disabled_nothing_sleeps(pkg, oracle_flavour):
     assert diverged_at is not None and diverged_at > 100
     assert st[:, 13].all() and not st[:, 14].any()  # all active, timers untouched
     assert not b.status().any()
+
+
+def test_bodies_thrown_in_mid_run(pkg, oracle_flavour):
+    """examples_util_throw_object (examples_util.cpp:52-95): an icosahedron, then a sphere, created between frames and thrown at
+    the stack at 15 m/s. rp_batch_create_from carries every world's state over device to
+    device; the reference creates the entities in its global table at the same frames. Bit for bit throughout."""
+    sc = scenes.stack()
+    b = make(pkg, sc, n_worlds=3)
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+
+    def both(frames):
+        for _ in range(frames):
+            b.step()
+            o.step()
+        assert np.array_equal(b.state()[0, :, :15], o.state())
+        assert np.array_equal(b.state()[0], b.state()[2])
+
+    both(25)
+    thrown = [scenes.BodyDesc((6.0, 4.0, 0.5), scenes.quaternion_new((0.35, 0.44, 0.12), 0.0), 1.0, False, [scenes.hull("ico", (1.0, 1.0, 1.0))], 0.8, 0.8, 0.0),
+              scenes.BodyDesc((-5.0, 9.0, 0.2), scenes.quaternion_new((0.35, 0.44, 0.12), 0.0), 1.0, False, [scenes.sphere(1.0)], 0.8, 0.8, 0.0)]
+    vel = [(-15.0, 0.0, 0.0), (12.0, -3.0, 0.0)]
+    for k in range(2):
+        sc.bodies.append(thrown[k])
+        nb = len(sc.bodies)
+        nbatch = pkg.Batch.create_from(pkg.Scene(sc), b, list(range(nb - 1)) + [-1])
+        nbatch.set_scene_forces(sc)
+        st = nbatch.state()
+        st[:, nb - 1, 7:10] = vel[k]  # e->linear_velocity = ... (examples_util.cpp:94)
+        nbatch.upload(st)
+        b.close()
+        b = nbatch
+        o.add_body(thrown[k])
+        ost = o.state()
+        ost[nb - 1, 7:10] = vel[k]
+        o.set_state(ost)
+        both(20)
+    assert np.abs(b.state()[0, 1:9, 7:13]).max() > 0.5  # the stack was hit
+    assert not b.status().any()
