@@ -116,7 +116,7 @@ def ncu_traffic(kernel):
     j = json.load(open(p))
     for name, d in j.get("kernels", {}).items():
         if name.split("<")[0] == kernel:  # template instances are listed as k_solve_pos<0>
-            return d["dram_read"] + d["dram_write"], j.get("capture")
+            return d["dram_read"] + d["dram_write"], j.get("source")
     return None, None
 
 

@@ -265,7 +265,9 @@ void step(r64 dt, Entity** es, Constraint* cs, u32 substeps, u32 iters, boolean 
 				if (rp_batch_add_force(g_batch, (int)i, fp, fv) != RP_OK) die("rp_batch_add_force");
 			}
 		}
-		if (rp_batch_step_host(g_batch, in.data(), out.data(), dt, substeps, iters, collisions ? 1 : 0) != RP_OK) die("rp_batch_step_host");
+		// (RP_ERR_CAPACITY: the step ran, but a fixed device buffer overflowed -- handled through the status word just below)
+		const int step_rc = rp_batch_step_host(g_batch, in.data(), out.data(), dt, substeps, iters, collisions ? 1 : 0);
+		if (step_rc != RP_OK && step_rc != RP_ERR_CAPACITY) die("rp_batch_step_host");
 		int32_t status = 0;
 		if (rp_batch_get_status(g_batch, &status) != RP_OK) die("rp_batch_get_status");
 		if (status && rp_batch_clear_status(g_batch) != RP_OK) die("rp_batch_clear_status");
