@@ -174,7 +174,8 @@ def example(name, params=(), perturb=False, mesh_dir=None):
     L = lib()
     p = np.ascontiguousarray(params, dtype=np.float64)
     info = ExampleInfo()
-    h = L.rp_example_create(name.encode(), _d(p) if p.size else None, int(p.size), int(perturb), mesh_dir.encode() if mesh_dir else None, C.byref(info))
+    mesh_dir = mesh_dir or os.path.join(HERE, "assets", "meshes")  # (explicit: a tuning variant of the library lives elsewhere)
+    h = L.rp_example_create(name.encode(), _d(p) if p.size else None, int(p.size), int(perturb), mesh_dir.encode(), C.byref(info))
     if not h:
         raise RawPhysError("rp_example_create(%r): %s" % (name, L.rp_example_error().decode()))
     sc = Scene(handle=h)

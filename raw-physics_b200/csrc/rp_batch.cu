@@ -106,8 +106,10 @@ static int dev_upload(rp_batch* b, const T** out, const std::vector<T>& v) {
 }
 
 // CTAs for one thread per (item, world) (flat_item_world)
-static unsigned int flat_grid(const rp_batch* b, size_t n_items, unsigned int threads) {
-	return (unsigned int)((n_items * (size_t)b->d.W + threads - 1) / threads);
+static dim3 flat_grid(const rp_batch* b, size_t n_items, unsigned int threads) {
+	const size_t W = (size_t)b->d.W;
+	if (W >= 2 * (size_t)threads && n_items > 0 && n_items < 65536) return dim3((unsigned int)n_items, (unsigned int)((W + threads - 1) / threads));
+	return dim3((unsigned int)((n_items * W + threads - 1) / threads));
 }
 
 // launches `kernel` as a cooperative grid (cg::this_grid().sync() inside); capturable into the frame graph
@@ -887,7 +889,7 @@ static void launch_colouring(rp_batch* b, int collisions) {
 	cudaMemsetAsync(c.fill, 0, W * d.NB * sizeof(int), b->stream);
 	cudaMemsetAsync(c.pending, 0, W * d.max_pairs * sizeof(int), b->stream);
 	cudaMemsetAsync(c.remaining, 0, (RP_COLOUR_ROUNDS + 1) * sizeof(int), b->stream);
-	const unsigned int per_pair = flat_grid(b, (size_t)d.max_pairs, 256);
+	const dim3 per_pair = flat_grid(b, (size_t)d.max_pairs, 256);
 	k_col_degree<<<per_pair, 256, 0, b->stream>>>(d, c, collisions);
 	launch_scan(b, c.deg, d.NB + 1, (size_t)d.NB + 1, c.sums, 0);
 	k_col_fill<<<per_pair, 256, 0, b->stream>>>(d, c);
@@ -905,7 +907,7 @@ static void launch_islands(rp_batch* b, double dt) {
 		k_islands<<<d.W, 256, 0, b->stream>>>(d, dt);
 		return;
 	}
-	const unsigned int per_body = flat_grid(b, (size_t)d.NB, 256);
+	const dim3 per_body = flat_grid(b, (size_t)d.NB, 256);
 	k_uf_init<<<per_body, 256, 0, b->stream>>>(d);
 	k_uf_hook<<<flat_grid(b, (size_t)d.max_pairs + d.NJ, 256), 256, 0, b->stream>>>(d);
 	k_uf_sleep<<<per_body, 256, 0, b->stream>>>(d, dt);
@@ -937,7 +939,7 @@ static void launch_broad_grid(rp_batch* b) {
 	cudaMemsetAsync(g.start, 0, W * (g.table + 1) * sizeof(int), b->stream);
 	cudaMemsetAsync(g.cursor, 0, W * g.table * sizeof(int), b->stream);
 	cudaMemsetAsync(g.row, 0, W * (d.NB + 1) * sizeof(int), b->stream);
-	const unsigned int per_body = flat_grid(b, (size_t)d.NB, 256);
+	const dim3 per_body = flat_grid(b, (size_t)d.NB, 256);
 	k_grid_count<<<per_body, 256, 0, b->stream>>>(d, g);
 	launch_scan(b, g.start, g.table + 1, (size_t)g.table + 1, g.sums, 0);
 	k_grid_fill<<<per_body, 256, 0, b->stream>>>(d, g);
@@ -955,7 +957,7 @@ static void launch_broad(rp_batch* b) {
 		return;
 	}
 	if (d.n_cells > 0) {
-		const unsigned int grid = flat_grid(b, (size_t)d.n_cells, 256);
+		const dim3 grid = flat_grid(b, (size_t)d.n_cells, 256);
 		k_broad_cells<<<grid, 256, 0, b->stream>>>(d);
 		k_broad_scan<<<(d.W + 31) / 32, dim3(32, RP_BROAD_SEGS), 0, b->stream>>>(d);
 		k_broad_write<<<grid, 256, 0, b->stream>>>(d);

@@ -111,13 +111,26 @@ __device__ __forceinline__ size_t pidx(const DevView& d, int p, int w) { return 
 // Thread -> (item, world) for the kernels that do one thing per item per world, world fastest: consecutive threads are
 // consecutive worlds of one item, so world-minor accesses coalesce; a batch of fewer worlds than a warp (one large scene: WS = W
 // then, see rp_batch_create) gets consecutive ITEMS in a warp instead of 31 idle lanes per item, and the accesses still
-// coalesce because its world stride is W. Launch ceil(n_items * W / blockDim.x) CTAs (flat_grid).
+// coalesce because its world stride is W. Launch flat_grid() CTAs: ceil(n_items * W / blockDim.x), or (items, world blocks) for
+// batches of at least two CTAs' worth of worlds (consecutive CTAs then walk the items of one world block, as round 1 did).
 __device__ __forceinline__ bool flat_item_world(const DevView& d, int n_items, int* item, int* w) {
-	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= (long long)n_items * d.W) return false;
-	const int it = (int)(t / d.W);
-	*item = it;
-	*w = (int)(t - (long long)it * d.W);
+	if (gridDim.y > 1) {  // batches of whole CTAs of worlds: grid = (items, world blocks), a CTA = one item in blockDim.x worlds
+		*item = (int)blockIdx.x;
+		*w = (int)(blockIdx.y * blockDim.x + threadIdx.x);
+		return *w < d.W;
+	}
+	const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned long long total = (unsigned long long)n_items * (unsigned long long)d.W;
+	if (t >= total) return false;
+	if (total <= 0xffffffffull) {  // (a 64-bit division is a ~100-instruction subroutine; every batch but the very largest fits 32 bits)
+		const unsigned int it = (unsigned int)t / (unsigned int)d.W;
+		*item = (int)it;
+		*w = (int)((unsigned int)t - it * (unsigned int)d.W);
+	} else {
+		const unsigned long long it = t / (unsigned long long)d.W;
+		*item = (int)it;
+		*w = (int)(t - it * (unsigned long long)d.W);
+	}
 	return true;
 }
 

@@ -237,9 +237,11 @@ struct EpaArrays {
 typedef EpaArrays<RP_EPA_MAX_VERTS, RP_EPA_MAX_FACES, RP_EPA_MAX_EDGES, false> EpaScratch;
 // capacities of the small store (the polytope of a box pair: EPA converges within 3 iterations for 97 % of the W256 pairs,
 // SURVEY.md 6; 4 expansions = 8 vertices, 4 + 2 * 4 = 12 faces, horizons of up to 12 edges in flight)
+#ifndef RP_EPA_SMALL_VERTS
 #define RP_EPA_SMALL_VERTS 8
 #define RP_EPA_SMALL_FACES 12
 #define RP_EPA_SMALL_EDGES 12
+#endif
 typedef EpaArrays<RP_EPA_SMALL_VERTS, RP_EPA_SMALL_FACES, RP_EPA_SMALL_EDGES, true> EpaSmallArrays;
 
 // get_face_normal_and_distance_to_origin (epa.cpp:32-77)
