@@ -73,6 +73,10 @@ struct rp_batch {
 	GridView grid;
 	ColourView col;
 	int grid_tiles_table = 0, grid_tiles_rows = 0;
+	// CTAs per SM the per-pair narrowphase kernels are launched with (grid-stride loops over the work lists, whose lengths only
+	// the device knows): a multiple of what is resident at once, so that an empty or short list costs one wave of CTAs
+	unsigned int grid_gjk = 8, grid_epa = 5, grid_manifold = 4;  // = resident CTAs per SM: measured on config 5 (1.82 -> 1.35 ms/frame vs 16 each) and W256 (no change)
+	size_t expected_pairs = 0;    // worlds x collider pairs of the initial poses: what sizes the narrowphase grids
 	int sweep_wpb = 0;            // worlds per CTA of the world-block sweeps (k_solve_block); 0 = level-major cooperative sweeps
 	size_t sweep_smem = 0;        // dynamic shared memory of k_solve_block (its per-level cursors)
 	std::vector<int> joint_level;  // template-constant levels of the external constraints
@@ -516,6 +520,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	size_t mp = cfg.max_pairs_per_world ? cfg.max_pairs_per_world : std::max<size_t>(128, 2 * init_pairs + 64 + (b->large ? 8 * (size_t)d.NB : 0));
 	mp = (mp + 127) / 128 * 128;
 	d.max_pairs = (int)mp;
+	b->expected_pairs = (size_t)d.W * std::max<size_t>(init_pairs, b->large ? mp / 2 : 1);
 	d.max_contacts = (int)(cfg.max_contacts_per_world ? cfg.max_contacts_per_world : std::max<size_t>(256, 8 * (size_t)d.NB));
 	d.max_units = d.NJ + d.max_pairs;
 	b->cull = cfg.disable_cull ? 0 : 1;
@@ -543,6 +548,25 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_vel, RP_VEL_THREADS, b->live_smem));
 		if (per_sm < 1) return fail(RP_ERR_CUDA, "k_solve_vel does not fit an SM");
 		b->vel_grid = (unsigned int)(b->sm_count * per_sm);
+	}
+	if (const char* e = getenv("RP_NARROW_GRID")) {  // tuning aid: "gjk,epa,manifold" CTAs per SM
+		unsigned int a = 0, c = 0, m = 0;
+		if (sscanf(e, "%u,%u,%u", &a, &c, &m) == 3 && a && c && m) {
+			b->grid_gjk = a; b->grid_epa = c; b->grid_manifold = m;
+		}
+	}
+	if (const char* e = getenv("RP_CARVEOUT")) {  // tuning aid: one shared-memory carve-out (percent) for every kernel of the substep
+		const int pct = atoi(e);
+		cudaFuncSetAttribute(k_integrate, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute(k_cull, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute(k_gjk, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute(k_epa, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute(k_manifold, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute(k_solve_pos<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute(k_solve_pos<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute(k_solve_vel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute(k_substep_reset, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaGetLastError();
 	}
 	// the polytope / clip-polygon stores of the narrowphase live in (dynamic) shared memory
 	RP_CUDA(cudaFuncSetAttribute(k_epa, cudaFuncAttributeMaxDynamicSharedMemorySize, RP_EPA_SMEM_BYTES));
@@ -993,7 +1017,18 @@ static void enqueue_integrate(rp_batch* b, double h, bool last_substep) {
 }
 // grid of the per-hit kernel: the hit count lives on the device, so the launch covers the candidate capacity in
 // grid-stride trips of at most this many CTAs
-static unsigned int manifold_grid(const rp_batch* b) { return (unsigned int)b->sm_count * 16u; }
+// at most the resident CTAs (one wave), at least one CTA per SM, in between what the pairs of the initial poses would fill:
+// worlds of a few bodies (config 5) pay for every CTA of a mostly empty launch (592 CTAs of k_manifold finding no hit: 9 us)
+static unsigned int narrow_grid(const rp_batch* b, unsigned int per_sm, unsigned int threads) {
+	const size_t want = (b->expected_pairs + threads - 1) / threads;
+	const size_t most = (size_t)b->sm_count * per_sm, least = (size_t)b->sm_count;
+	return (unsigned int)std::min(most, std::max(least, want));
+}
+// the warp-per-pair kernels: 4 pairs per CTA at a time, 186 registers -> 2 CTAs resident per SM; two waves
+static unsigned int warp_grid(const rp_batch* b) { return narrow_grid(b, 4, 4); }
+static unsigned int manifold_grid(const rp_batch* b) { return narrow_grid(b, b->grid_manifold, RP_MANIFOLD_THREADS); }
+static unsigned int epa_grid(const rp_batch* b) { return narrow_grid(b, b->grid_epa, RP_EPA_THREADS); }
+static unsigned int gjk_grid(const rp_batch* b) { return narrow_grid(b, b->grid_gjk, RP_GJK_THREADS); }
 static void launch_cull(rp_batch* b) {
 	const DevView& d = b->d;
 	if (d.NC == 0) return;  // bodies without colliders (joint-only scenes): no pairs, no candidates, nothing to transform
@@ -1006,14 +1041,14 @@ static void launch_cull(rp_batch* b) {
 #endif
 }
 static void launch_gjk(rp_batch* b) {
-	k_gjk<<<b->sm_count * 16, RP_GJK_THREADS, 0, b->stream>>>(b->d);
-	if (b->has_big_pairs) k_gjk_warp<<<b->sm_count * 8, RP_GJK_WARP_THREADS, 0, b->stream>>>(b->d);
+	k_gjk<<<gjk_grid(b), RP_GJK_THREADS, 0, b->stream>>>(b->d);
+	if (b->has_big_pairs) k_gjk_warp<<<warp_grid(b), RP_GJK_WARP_THREADS, 0, b->stream>>>(b->d);
 }
 static void launch_manifold(rp_batch* b) {
-	k_epa<<<b->sm_count * 16, RP_EPA_THREADS, RP_EPA_SMEM_BYTES, b->stream>>>(b->d);
-	if (b->has_big_pairs) k_epa_warp<<<b->sm_count * 8, RP_GJK_WARP_THREADS, 0, b->stream>>>(b->d);
+	k_epa<<<epa_grid(b), RP_EPA_THREADS, RP_EPA_SMEM_BYTES, b->stream>>>(b->d);
+	if (b->has_big_pairs) k_epa_warp<<<warp_grid(b), RP_GJK_WARP_THREADS, 0, b->stream>>>(b->d);
 	k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, RP_MANIFOLD_SMEM_BYTES, b->stream>>>(b->d);
-	if (b->has_big_pairs) k_manifold_warp<<<b->sm_count * 8, RP_CLIPW_THREADS, 0, b->stream>>>(b->d);
+	if (b->has_big_pairs) k_manifold_warp<<<warp_grid(b), RP_CLIPW_THREADS, 0, b->stream>>>(b->d);
 }
 static void enqueue_narrow(rp_batch* b) {
 	launch_cull(b);
@@ -1396,11 +1431,11 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 				if ((rc = mark(RP_K_CULL))) return rc;
 				launch_gjk(b);
 				if ((rc = mark(RP_K_GJK))) return rc;
-				k_epa<<<b->sm_count * 16, RP_EPA_THREADS, RP_EPA_SMEM_BYTES, b->stream>>>(d);
-				if (b->has_big_pairs) k_epa_warp<<<b->sm_count * 8, RP_GJK_WARP_THREADS, 0, b->stream>>>(d);
+				k_epa<<<epa_grid(b), RP_EPA_THREADS, RP_EPA_SMEM_BYTES, b->stream>>>(d);
+				if (b->has_big_pairs) k_epa_warp<<<warp_grid(b), RP_GJK_WARP_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_EPA))) return rc;
 				k_manifold<<<manifold_grid(b), RP_MANIFOLD_THREADS, RP_MANIFOLD_SMEM_BYTES, b->stream>>>(d);
-				if (b->has_big_pairs) k_manifold_warp<<<b->sm_count * 8, RP_CLIPW_THREADS, 0, b->stream>>>(d);
+				if (b->has_big_pairs) k_manifold_warp<<<warp_grid(b), RP_CLIPW_THREADS, 0, b->stream>>>(d);
 				if ((rc = mark(RP_K_MANIFOLD))) return rc;
 			}
 			if (b->sweep_wpb > 0) {

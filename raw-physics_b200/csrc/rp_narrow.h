@@ -653,8 +653,10 @@ RP_HD int manifold_clip(const S& h1, const S& h2, V3 normal, C& cs, int* status,
 		return CLIP_OK;
 	}
 	const bool ref1 = fc.ref1;
-	const S& R = ref1 ? h1 : h2;   // reference hull
-	const S& I = ref1 ? h2 : h1;   // incident hull
+	// (copies, not references: a reference chosen at run time keeps BOTH shapes -- two model matrices on the device -- alive
+	// through the whole clipping loop; as copies the incident hull is dead once its polygon has been read)
+	const S R = ref1 ? h1 : h2;   // reference hull
+	const S I = ref1 ? h2 : h1;   // incident hull
 	const int rface = fc.rface, iface = fc.iface;
 
 	// incident polygon (get_vertices_of_faces, clipping.cpp:241-247)
