@@ -129,17 +129,19 @@ void narrow_pair(World& w, int ca, int cb, std::vector<LoggedContact>& out) {
 	// the small stores the CUDA kernels keep in shared memory, with the full ones as second tier (rp_narrow.h)
 	static EpaSmallArrays es_small;
 	static ClipSmallArrays cs_small;
+	int sup_a = -1, sup_b = -1;
 	if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
 		if (!sphere_sphere(A, B, &normal, &depth)) return;
 	} else {
 		Simplex s;
 		if (!gjk(A, B, &s, &w.status, 0)) return;
-		if (!epa_tiered(A, B, s, es_small, es, &normal, &depth, &w.status, &g_epa_reruns)) return;
+		if (!epa_tiered(A, B, s, es_small, es, &normal, &depth, &w.status, &g_epa_reruns, &sup_a, &sup_b)) return;
 	}
 	VecSink sink;
 	sink.out = &out;
 	sink.n = normal;
-	manifold_tiered(A, B, normal, depth, cs_small, cs, &w.status, sink, &g_clip_reruns);
+	// (EPA's last support vertices stand in for the manifold's own support scans, as on the device)
+	manifold_tiered(A, B, normal, depth, cs_small, cs, &w.status, sink, &g_clip_reruns, sup_a, sup_b);
 }
 
 int uf_find(std::vector<int>& p, int x) {

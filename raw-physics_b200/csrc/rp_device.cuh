@@ -46,6 +46,7 @@ struct EpaOut {  // result of EPA (or the analytic sphere-sphere test) for one h
 	V3 normal;
 	double depth;
 	int ok, pad;
+	int sup_a, sup_b;  // support vertices of the two hulls along +normal / -normal (EPA's last support call), -1 when unknown
 };
 
 enum { CNT_PAIR_TESTS = 0, CNT_HITS = 1, CNT_CONTACTS = 2, CNT_BROAD_PAIRS = 3, CNT_LEVELS = 4, CNT_FRAMES = 5, CNT_CANDS = 6 };

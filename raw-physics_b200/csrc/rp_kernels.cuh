@@ -1042,11 +1042,11 @@ struct EpaShared {
 
 // second tier of k_epa: the full-capacity polytope in local memory, for the rare pair that outgrows the shared store.
 // Out of line so that its 11.8 kB frame and its registers stay out of the common path.
-__device__ __noinline__ int epa_full(const DevView& d, uint4 cd, const Simplex& s, V3* normal, double* depth, int* status) {
+__device__ __noinline__ int epa_full(const DevView& d, uint4 cd, const Simplex& s, V3* normal, double* depth, int* status, int* sup_a, int* sup_b) {
 	EpaScratch e;
 	const PoseShape A = dev_pose_shape(d, d.cols[cd.z], (int)cd.x);
 	const PoseShape B = dev_pose_shape(d, d.cols[cd.w], (int)cd.x);
-	return epa_run(A, B, s, e, normal, depth, status, 0);
+	return epa_run(A, B, s, e, normal, depth, status, 0, sup_a, sup_b);
 }
 
 // EPA (epa.cpp:118) for every hit, one thread per hit, the polytope in shared memory (EpaShared). RP_EPA_STAGE_HULLS = 1
@@ -1076,6 +1076,7 @@ __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) 
 		PoseShape B = dev_pose_shape(d, d.cols[cd.w], w);
 		EpaOut out;
 		out.ok = 0; out.pad = 0; out.depth = 0.0; out.normal = v3(0.0, 0.0, 0.0);
+		out.sup_a = out.sup_b = -1;
 		int st = 0;
 		if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
 			out.ok = sphere_sphere(A, B, &out.normal, &out.depth) ? 1 : 0;
@@ -1088,11 +1089,11 @@ __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) 
 				double* col = s_stage + threadIdx.x;
 				const int used = stage_shape(SA, col, RP_EPA_THREADS);
 				stage_shape(SB, col + (size_t)used * RP_EPA_THREADS, RP_EPA_THREADS);
-				r = epa_run(StagedShape<RP_EPA_THREADS>(SA), StagedShape<RP_EPA_THREADS>(SB), s, e, &out.normal, &out.depth, &st, 0);
+				r = epa_run(StagedShape<RP_EPA_THREADS>(SA), StagedShape<RP_EPA_THREADS>(SB), s, e, &out.normal, &out.depth, &st, 0, &out.sup_a, &out.sup_b);
 			} else
 #endif
-			r = epa_run(A, B, s, e, &out.normal, &out.depth, &st, 0);
-			if (r == EPA_OVERFLOW) r = epa_full(d, cd, s, &out.normal, &out.depth, &st);
+			r = epa_run(A, B, s, e, &out.normal, &out.depth, &st, 0, &out.sup_a, &out.sup_b);
+			if (r == EPA_OVERFLOW) r = epa_full(d, cd, s, &out.normal, &out.depth, &st, &out.sup_a, &out.sup_b);
 			out.ok = r == EPA_DONE ? 1 : 0;
 		}
 		d.epa_out[hi] = out;
@@ -1123,6 +1124,7 @@ __global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_epa_warp(DevView d) {
 		const Simplex s = ld_simplex(d, hi);
 		EpaOut out;
 		out.ok = 0; out.pad = 0; out.depth = 0.0; out.normal = v3(0.0, 0.0, 0.0);
+		out.sup_a = out.sup_b = -1;
 		int st = 0;
 		out.ok = epa(WarpShape(A), WarpShape(B), s, e, &out.normal, &out.depth, &st, 0) ? 1 : 0;  // the same instance on all lanes
 		int2 sup = make_int2(-1, -1);
@@ -1252,7 +1254,7 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 					}
 					n = emit_contacts(d, cs, r, eo.normal, w, pr, &off, &st);
 				} else {
-					const int sup1 = -1, sup2 = -1;
+					const int sup1 = eo.sup_a, sup2 = eo.sup_b;  // EPA's last support vertices = the ones clipping starts from
 					ClipResult r;
 					int ov;
 					{

@@ -337,9 +337,14 @@ RP_HD int epa_begin(const Simplex& s, E& e, int* status) {
 }
 
 template <class SA, class SB, class E>
-RP_HD int epa_step(const SA& A, const SB& B, E& e, int* status) {
+RP_HD int epa_step(const SA& A, const SB& B, E& e, int* status, int* sup_a = 0, int* sup_b = 0) {
 	const V3 min_normal = e.min_normal;
-	V3 sp = support_minkowski(A, B, min_normal);
+	int ia = -1, ib = -1;
+	V3 sp = support_minkowski_idx(A, B, min_normal, &ia, &ib);
+	if (sup_a) {  // (on EPA_DONE these are the support vertices along the returned normal)
+		*sup_a = ia;
+		*sup_b = ib;
+	}
 	double d = dot(min_normal, sp);
 	if (fabs(d - e.min_dist) < 0.0001) return EPA_DONE;  // result: e.min_normal, e.min_dist
 	if (e.nverts >= E::MAXV) return epa_out_of_room<E>(status);  // (the full store holds 4 + RP_EPA_MAX_ITERS: never reached there)
@@ -387,10 +392,11 @@ RP_HD int epa_step(const SA& A, const SB& B, E& e, int* status) {
 
 // returns EPA_DONE (normal, depth written), EPA_FAIL (status says why) or, for a SOFT store, EPA_OVERFLOW (nothing written)
 template <class SA, class SB, class E>
-RP_HD int epa_run(const SA& A, const SB& B, const Simplex& s, E& e, V3* normal_out, double* depth_out, int* status, int* iters) {
+RP_HD int epa_run(const SA& A, const SB& B, const Simplex& s, E& e, V3* normal_out, double* depth_out, int* status, int* iters,
+	int* sup_a = 0, int* sup_b = 0) {
 	if (epa_begin(s, e, status) == EPA_FAIL) return EPA_FAIL;
 	for (int it = 0; it < RP_EPA_MAX_ITERS; ++it) {
-		const int r = epa_step(A, B, e, status);
+		const int r = epa_step(A, B, e, status, sup_a, sup_b);
 		if (r == EPA_DONE) {
 			*normal_out = e.min_normal;
 			*depth_out = e.min_dist;
@@ -496,19 +502,30 @@ RP_HD int clip_pass(const ClipPlane& pl, C& cs, int src, int n_in, bool remove_o
 	return n_out;
 }
 
-// get_face_with_most_fitting_normal (clipping.cpp:136-152)
+// get_face_with_most_fitting_normal (clipping.cpp:136-152). vertex_to_faces lists a face once per triangle of it that touches
+// the vertex (cube corner: [0, 0, 2, 5, 5]); a repeated entry projects exactly as its first occurrence and can never win
+// the strict comparison, so consecutive repeats are skipped (on the device a face normal costs a matrix product and a
+// normalisation). `normal_out` receives the chosen face's normal.
 template <class S>
-RP_HD int clip_best_face(const S& s, int support_idx, V3 normal) {
+RP_HD int clip_best_face(const S& s, int support_idx, V3 normal, V3* normal_out) {
 	double best = -1.7976931348623157e308;
-	int sel = 0;
+	int sel = 0, prev = -1;
+	V3 sel_n = v3(0.0, 0.0, 0.0);
+	bool any = false;
 	for (int k = s.v2f_ptr[support_idx]; k < s.v2f_ptr[support_idx + 1]; ++k) {
 		int f = s.v2f_idx[k];
-		double proj = dot(fnormal(s, f), normal);
+		if (f == prev) continue;
+		prev = f;
+		V3 fn = fnormal(s, f);
+		double proj = dot(fn, normal);
 		if (proj > best) {
 			best = proj;
 			sel = f;
+			sel_n = fn;
+			any = true;
 		}
 	}
+	*normal_out = any ? sel_n : fnormal(s, sel);  // (no face beat -DBL_MAX: an empty list or NaNs; the reference returns face 0)
 	return sel;
 }
 
@@ -561,10 +578,10 @@ RP_HD void manifold_select(const S& h1, const S& h2, V3 normal, int* status, Fac
 	V3 inv_normal = zero_minus(normal);
 	int sup1 = sup1_known >= 0 ? sup1_known : support_index(h1, normal);
 	int sup2 = sup2_known >= 0 ? sup2_known : support_index(h2, inv_normal);
-	int face1 = clip_best_face(h1, sup1, normal);
-	int face2 = clip_best_face(h2, sup2, inv_normal);
+	V3 f1n, f2n;
+	int face1 = clip_best_face(h1, sup1, normal, &f1n);
+	int face2 = clip_best_face(h2, sup2, inv_normal, &f2n);
 
-	V3 f1n = fnormal(h1, face1), f2n = fnormal(h2, face2);
 	double dot1 = dot(f1n, normal);
 	double dot2 = dot(f2n, inv_normal);
 	const double EPS = 0.0001;
@@ -762,25 +779,25 @@ RP_HD void manifold(const Shape& A, const Shape& B, V3 normal, double depth, Cli
 // `reruns` (optional) counts the pairs that needed the second tier.
 template <class SA, class SB, class Small, class Full>
 RP_HD bool epa_tiered(const SA& A, const SB& B, const Simplex& s, Small& small, Full& full, V3* normal_out, double* depth_out, int* status,
-	int* reruns) {
-	int r = epa_run(A, B, s, small, normal_out, depth_out, status, 0);
+	int* reruns, int* sup_a = 0, int* sup_b = 0) {
+	int r = epa_run(A, B, s, small, normal_out, depth_out, status, 0, sup_a, sup_b);
 	if (r == EPA_OVERFLOW) {
 		if (reruns) ++*reruns;
-		r = epa_run(A, B, s, full, normal_out, depth_out, status, 0);
+		r = epa_run(A, B, s, full, normal_out, depth_out, status, 0, sup_a, sup_b);
 	}
 	return r == EPA_DONE;
 }
 template <class Small, class Full, class Sink>
 RP_HD void manifold_tiered(const Shape& A, const Shape& B, V3 normal, double depth, Small& small, Full& full, int* status, Sink& sink,
-	int* reruns) {
+	int* reruns, int sup1_known = -1, int sup2_known = -1) {
 	if (A.type == SHAPE_SPHERE || B.type == SHAPE_SPHERE) {
 		manifold(A, B, normal, depth, full, status, sink);
 		return;
 	}
 	ClipResult r;
-	if (manifold_clip(A, B, normal, small, status, &r) == CLIP_OVERFLOW) {
+	if (manifold_clip(A, B, normal, small, status, &r, sup1_known, sup2_known) == CLIP_OVERFLOW) {
 		if (reruns) ++*reruns;
-		manifold_clip(A, B, normal, full, status, &r);
+		manifold_clip(A, B, normal, full, status, &r, sup1_known, sup2_known);
 		manifold_emit(full, r, normal, sink);
 	} else {
 		manifold_emit(small, r, normal, sink);

@@ -198,6 +198,30 @@ RP_HD V3 support_minkowski(const SA& a, const SB& b, V3 d) {
 	V3 s2 = support(b, scale(-1.0, d));
 	return sub(s1, s2);
 }
+// the same, also telling which hull vertices were chosen (-1 for a sphere): EPA's last support call is made along the normal it
+// returns, and convex_convex_contact_manifold starts from the support vertices along +-normal (clipping.cpp:255-256). Its
+// second direction is (0,0,0) - n where this one is -1.0 * n: the two differ at most in the sign of a zero component, which
+// changes no comparison of the scan (+0 == -0), so the indices are the ones the manifold's own scans would find.
+template <class SA, class SB>
+RP_HD V3 support_minkowski_idx(const SA& a, const SB& b, V3 d, int* ia, int* ib) {
+	V3 s1, s2;
+	if (a.type == SHAPE_HULL) {
+		*ia = support_index(a, d);
+		s1 = vert(a, *ia);
+	} else {
+		*ia = -1;
+		s1 = support(a, d);
+	}
+	const V3 nd = scale(-1.0, d);
+	if (b.type == SHAPE_HULL) {
+		*ib = support_index(b, nd);
+		s2 = vert(b, *ib);
+	} else {
+		*ib = -1;
+		s2 = support(b, nd);
+	}
+	return sub(s1, s2);
+}
 
 }  // namespace rp
 #endif
