@@ -63,7 +63,7 @@ WORKLOADS = {
 BYTES = dict(integrate=288.0, gjk=16.0 + 2 * 56.0, epa=16.0 + 96.0 + 2 * 56.0 + 40.0, manifold=40.0 + 16.0 + 2 * 56.0 + 16.0 + 48.0,
              manifold_contact=64.0, solve_pos_pair=2 * (112.0 + 56.0), solve_contact=80.0, solve_vel_pair=2 * (128.0 + 48.0),
              solve_contact_vel=64.0, joint=2 * 2 * 56.0 + 48.0)
-FLOPS = dict(integrate=590.0, gjk=620.0 + 470.0, epa=800.0 + 560.0, manifold=1200.0 + 900.0, solve_pos_contact=1100.0, solve_vel_contact=650.0,
+FLOPS = dict(integrate=590.0, gjk=620.0 + 470.0, epa=800.0 + 560.0, manifold=1200.0 + 500.0, solve_pos_contact=1100.0, solve_vel_contact=650.0,
              joint=1500.0)
 FLOP_PER_BODY_SUBSTEP = 4.0e3  # algorithmic FP64 flop per body-substep on the W256 world
 
