@@ -7,6 +7,8 @@
 //   rp_headless --scene NAME [--params a,b,c] [--perturb] [--rows R] [--cols C] [--worlds W] [--frames F] [--dt DT]
 //               [--substeps S] [--iters I] [--device D] [--meshes DIR] [--dump FILE] [--dump-every K] [--no-collisions]
 //               [--coloured]   (RP_ORDER_COLOURED: graph-coloured sweeps for one large scene, not bit-comparable)
+//               [--gpus G]     (the worlds in G contiguous shards, one batch per CUDA device d, d + 1, ...: worlds never interact,
+//                               so there is no exchange between them; every frame is enqueued on all devices before any is waited for)
 //
 // NAME is any built-in scene of the library (rp_example_create: the init() halves of all 14 examples under src/examples plus
 // the benchmark worlds; `levers` = hinge_joints --perturb); substeps, iterations and collisions default to what that
@@ -35,7 +37,7 @@ namespace {
 struct Options {
 	std::string scene = "stack", meshes, dump;
 	std::vector<double> params;
-	int rows = 0, cols = 0, worlds = 1, frames = 60, substeps = 0, iters = -1, device = 0, dump_every = 1;
+	int rows = 0, cols = 0, worlds = 1, frames = 60, substeps = 0, iters = -1, device = 0, dump_every = 1, gpus = 1;
 	double dt = 1.0 / 60.0;
 	bool collisions = true, coloured = false, perturb = false, list = false;
 };
@@ -75,6 +77,7 @@ void parse(int argc, char** argv, Options& o) {
 		else if (a == "--substeps") o.substeps = atoi(next());
 		else if (a == "--iters") o.iters = atoi(next());
 		else if (a == "--device") o.device = atoi(next());
+		else if (a == "--gpus") o.gpus = atoi(next());
 		else if (a == "--dt") o.dt = atof(next());
 		else if (a == "--meshes") o.meshes = next();
 		else if (a == "--dump") o.dump = next();
@@ -83,7 +86,7 @@ void parse(int argc, char** argv, Options& o) {
 		else if (a == "--coloured") o.coloured = true;
 		else die("unknown argument " + a);
 	}
-	if (o.worlds < 1 || o.frames < 0 || o.substeps < 0 || o.dump_every < 1 || o.rows < 0 || o.cols < 0) die("bad argument value");
+	if (o.worlds < 1 || o.frames < 0 || o.substeps < 0 || o.dump_every < 1 || o.rows < 0 || o.cols < 0 || o.gpus < 1 || o.gpus > o.worlds) die("bad argument value");
 }
 
 }  // namespace
@@ -113,11 +116,18 @@ int main(int argc, char** argv) {
 	if (o.iters < 0) o.iters = (int)info.pos_iters;
 	if (!info.collisions) o.collisions = false;
 
-	rp_batch* batch = 0;
+	if (o.device + o.gpus > rp_device_count()) die("not that many CUDA devices");
 	rp_batch_cfg cfg;
 	rp_batch_cfg_default(&cfg);
 	cfg.solve_order = o.coloured ? RP_ORDER_COLOURED : RP_ORDER_REFERENCE;
-	if (rp_batch_create(scene, (uint32_t)o.worlds, o.device, &cfg, &batch) != RP_OK) die("rp_batch_create");
+	// shards: contiguous blocks of worlds, sizes differing by at most one (the partition of raw-physics_b200/multi.py)
+	std::vector<rp_batch*> shards((size_t)o.gpus, (rp_batch*)0);
+	std::vector<int> shard_worlds((size_t)o.gpus);
+	for (int g = 0; g < o.gpus; ++g) {
+		shard_worlds[g] = o.worlds / o.gpus + (g < o.worlds % o.gpus ? 1 : 0);
+		if (rp_batch_create(scene, (uint32_t)shard_worlds[g], o.device + g, &cfg, &shards[g]) != RP_OK) die("rp_batch_create");
+	}
+	rp_batch* batch = shards[0];
 	const uint32_t nb = rp_batch_num_bodies(batch);
 	std::vector<double> state((size_t)nb * RP_STATE_STRIDE);
 
@@ -134,18 +144,25 @@ int main(int argc, char** argv) {
 
 	const auto t0 = std::chrono::steady_clock::now();
 	for (int f = 1; f <= o.frames; ++f) {
-		// an example's update(): gravity on every entity, simulate, clear forces (stack.cpp:93-102)
-		if (rp_batch_clear_forces(batch) != RP_OK || rp_batch_add_gravity(batch, info.gravity) != RP_OK) die("forces");
-		if (rp_batch_step(batch, o.dt, (uint32_t)o.substeps, (uint32_t)o.iters, o.collisions ? 1 : 0) != RP_OK) die("rp_batch_step");
+		// an example's update(): gravity on every entity, simulate, clear forces (stack.cpp:93-102) -- on every shard; the step
+		// only enqueues the frame's graph on the shard's stream, so the devices run side by side
+		for (rp_batch* b : shards) {
+			if (rp_batch_clear_forces(b) != RP_OK || rp_batch_add_gravity(b, info.gravity) != RP_OK) die("forces");
+			if (rp_batch_step(b, o.dt, (uint32_t)o.substeps, (uint32_t)o.iters, o.collisions ? 1 : 0) != RP_OK) die("rp_batch_step");
+		}
 		if (dump && (f % o.dump_every == 0 || f == o.frames)) {
-			if (rp_batch_download_state(batch, 0, 1, state.data()) != RP_OK) die("rp_batch_download_state");
+			const int rc = rp_batch_download_state(batch, 0, 1, state.data());
+			if (rc != RP_OK && rc != RP_ERR_CAPACITY) die("rp_batch_download_state");
 			const uint32_t tag[2] = {(uint32_t)f, 0u};
 			fwrite(tag, sizeof(tag), 1, dump);
 			fwrite(state.data(), sizeof(double), state.size(), dump);
 			++records;
 		}
 	}
-	if (rp_batch_sync(batch) != RP_OK) die("rp_batch_sync");
+	for (rp_batch* b : shards) {
+		const int rc = rp_batch_sync(b);
+		if (rc != RP_OK && rc != RP_ERR_CAPACITY) die("rp_batch_sync");  // (capacity: reported through the status bits below)
+	}
 	const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 	if (dump) {
 		fseek(dump, 12, SEEK_SET);
@@ -153,32 +170,35 @@ int main(int argc, char** argv) {
 		fclose(dump);
 	}
 
-	// every world started from the same poses: they must still agree bit for bit, and no world may have raised a flag
-	std::vector<int32_t> status((size_t)o.worlds);
-	if (rp_batch_get_status(batch, status.data()) != RP_OK) die("rp_batch_get_status");
+	// every world started from the same poses: they must still agree bit for bit -- within a shard and across the devices --
+	// and no world may have raised a flag
 	int32_t bits = 0;
-	for (int32_t s : status) bits |= s;
 	int diverged = 0;
-	if (o.worlds > 1) {
-		std::vector<double> first((size_t)nb * RP_STATE_STRIDE), other(first.size());
-		if (rp_batch_download_state(batch, 0, 1, first.data()) != RP_OK) die("rp_batch_download_state");
-		const int probes[3] = {1, o.worlds / 2, o.worlds - 1};
+	uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	std::vector<double> first((size_t)nb * RP_STATE_STRIDE), other(first.size());
+	for (int g = 0; g < o.gpus; ++g) {
+		std::vector<int32_t> status((size_t)shard_worlds[g]);
+		if (rp_batch_get_status(shards[g], status.data()) != RP_OK) die("rp_batch_get_status");
+		for (int32_t s : status) bits |= s;
+		if (bits) rp_batch_clear_status(shards[g]);
+		const int probes[3] = {0, shard_worlds[g] / 2, shard_worlds[g] - 1};
 		for (int w : probes) {
-			if (rp_batch_download_state(batch, (uint32_t)w, 1, other.data()) != RP_OK) die("rp_batch_download_state");
-			if (memcmp(first.data(), other.data(), first.size() * sizeof(double)) != 0) ++diverged;
+			if (rp_batch_download_state(shards[g], (uint32_t)w, 1, g == 0 && w == 0 ? first.data() : other.data()) != RP_OK) die("rp_batch_download_state");
+			if (!(g == 0 && w == 0) && memcmp(first.data(), other.data(), first.size() * sizeof(double)) != 0) ++diverged;
 		}
+		uint64_t c[8];
+		if (rp_batch_get_counters(shards[g], c) != RP_OK) die("rp_batch_get_counters");
+		for (int k = 0; k < 8; ++k) counters[k] += (k == 5 && g > 0) ? 0 : c[k];  // (frames: counted once)
 	}
-	uint64_t counters[8];
-	if (rp_batch_get_counters(batch, counters) != RP_OK) die("rp_batch_get_counters");
 	const double units = (double)nb * o.worlds * o.substeps * o.frames;
-	printf("{\"scene\": \"%s\", \"order\": \"%s\", \"sweep_depth\": %.1f, \"worlds\": %d, \"bodies\": %u, \"frames\": %d, \"substeps\": %d, \"seconds\": %.6f, \"ms_per_frame\": %.4f, "
-	       "\"body_substeps_per_s\": %.6g, \"status_bits\": %d, \"diverged_worlds\": %d, \"pair_tests\": %llu, \"epa_runs\": %llu, "
+	printf("{\"scene\": \"%s\", \"order\": \"%s\", \"sweep_depth\": %.1f, \"worlds\": %d, \"gpus\": %d, \"bodies\": %u, \"frames\": %d, \"substeps\": %d, \"seconds\": %.6f, "
+	       "\"ms_per_frame\": %.4f, \"body_substeps_per_s\": %.6g, \"status_bits\": %d, \"diverged_worlds\": %d, \"pair_tests\": %llu, \"epa_runs\": %llu, "
 	       "\"contacts\": %llu}\n",
-		o.scene.c_str(), o.coloured ? "coloured" : "reference", counters[5] ? (double)counters[4] / (double)counters[5] / o.worlds : 0.0, o.worlds, nb,
+		o.scene.c_str(), o.coloured ? "coloured" : "reference", counters[5] ? (double)counters[4] / (double)counters[5] / o.worlds : 0.0, o.worlds, o.gpus, nb,
 		o.frames, o.substeps, seconds, o.frames ? 1e3 * seconds / o.frames : 0.0,
 		seconds > 0.0 ? units / seconds : 0.0, (int)bits, diverged, (unsigned long long)counters[0], (unsigned long long)counters[1],
 		(unsigned long long)counters[2]);
-	rp_batch_destroy(batch);
+	for (rp_batch* b : shards) rp_batch_destroy(b);
 	rp_scene_destroy(scene);
 	return bits || diverged ? 2 : 0;
 }

@@ -102,3 +102,18 @@ def test_headless_runs_every_example(pkg, oracle_flavour, tmp_path, scene, extra
         assert np.array_equal(got, want), (scene, np.abs(got - want).max())
     else:
         assert np.abs(got[:, :7] - want[:, :7]).max() <= 1e-9
+
+
+@pytest.mark.gpu
+def test_headless_shards_over_two_gpus(pkg, oracle_flavour, tmp_path):
+    """--gpus 2: the worlds in two contiguous shards, one batch per device, every frame enqueued on both before either is
+    waited for; the shards agree with each other bit for bit and with the oracle. Needs two devices."""
+    if pkg.lib().rp_device_count() < 2:
+        pytest.skip("one CUDA device")
+    info, dump = run(tmp_path, "--scene", "stack", "--frames", 45, "--worlds", 65, "--gpus", 2, "--dump-every", 45)
+    assert info["status_bits"] == 0 and info["diverged_worlds"] == 0 and info["gpus"] == 2 and info["worlds"] == 65
+    sc = scenes.stack()
+    o = refdrv.RefWorld(oracle_flavour).load(sc)
+    for _ in range(45):
+        o.step()
+    assert np.array_equal(dump[45][:, :15], o.state())
