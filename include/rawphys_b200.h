@@ -151,7 +151,7 @@ typedef struct {
 	uint32_t solve_order;             /* RP_ORDER_REFERENCE (default) or RP_ORDER_COLOURED */
 	uint32_t sweep_block_worlds;      /* worlds per CTA of the world-block Gauss-Seidel sweeps; 0 = choose (level-major sweeps for small batches) */
 	uint32_t large_scene;             /* per-frame prologue for ONE LARGE SCENE (uniform-grid broadphase, union-find islands, parallel graph
-	                                     colouring): 0 = when a world has >= 4096 bodies, 1 = never, 2 = always */
+	                                     colouring): 0 = when a world has >= 4096 bodies (>= 1024 in the coloured order), 1 = never, 2 = always */
 	uint32_t disable_islands;         /* 1 = the reference built without ENABLE_SIMULATION_ISLANDS (pbd.cpp:12): no islands, nothing sleeps */
 	uint32_t reserved0;
 	double linear_sleeping_threshold;   /* pbd.cpp:13, default 0.10 */

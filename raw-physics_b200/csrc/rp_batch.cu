@@ -451,8 +451,10 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 
 	// One large scene (rp_large.cuh) or many small worlds? Bodies far larger than the typical one (the floor) stay out of the
 	// uniform grid: its cell edge is set by the largest of the others.
+	if (const char* e = getenv("RP_LARGE_SCENE")) cfg.large_scene = (uint32_t)atoi(e);  // tuning aid
 	if (cfg.large_scene > 2) return fail(RP_ERR_ARG, "rp_batch_create: unknown large_scene");
-	b->large = cfg.large_scene == 2 || (cfg.large_scene == 0 && d.NB >= 4096);
+	// (the coloured order's schedule is one sequential thread per world otherwise: worth replacing from ~1000 bodies)
+	b->large = cfg.large_scene == 2 || (cfg.large_scene == 0 && d.NB >= (b->coloured ? 1024 : 4096));
 	std::vector<unsigned char> is_large(d.NB, 0);
 	std::vector<int> large_ids;
 	double r_small = 0.0;
