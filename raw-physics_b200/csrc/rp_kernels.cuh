@@ -146,31 +146,7 @@ __device__ __forceinline__ void load_static(Body& b, const DevView& d, int body)
 	b.fixed = s.fixed;
 }
 
-// A collider of world w at its current pose: transformed vertices / normals addressed in the world-minor arrays
-// (vertex stride 3 * WS, component stride WS).
-__device__ __forceinline__ Shape dev_shape(const DevView& d, const ColliderDesc& c, int w) {
-	Shape s;
-	s.type = c.type;
-	s.radius = c.radius;
-	s.vp = d.tv + (size_t)c.tv0 * 3 * d.WS + w; s.vs = 3 * d.WS; s.vcs = d.WS;
-	s.np = d.tn + (size_t)c.tn0 * 3 * d.WS + w; s.ns = 3 * d.WS; s.ncs = d.WS;
-	if (c.type == SHAPE_SPHERE) {
-		s.center = v3(s.vp[0], s.vp[d.WS], s.vp[2 * (size_t)d.WS]);
-		s.nv = 0; s.nf = 0;
-		s.face_ptr = s.face_idx = s.v2f_ptr = s.v2f_idx = s.v2n_ptr = s.v2n_idx = s.f2n_ptr = s.f2n_idx = 0;
-	} else {
-		const HullTopo h = d.pool.hulls[c.hull];
-		s.center = v3(0.0, 0.0, 0.0);
-		s.nv = h.nv; s.nf = h.nf;
-		s.face_ptr = d.pool.face_ptr + h.fptr0; s.face_idx = d.pool.face_idx;
-		s.v2f_ptr = d.pool.v2f_ptr + h.v2f0; s.v2f_idx = d.pool.v2f_idx;
-		s.v2n_ptr = d.pool.v2n_ptr + h.v2n0; s.v2n_idx = d.pool.v2n_idx;
-		s.f2n_ptr = d.pool.f2n_ptr + h.f2n0; s.f2n_idx = d.pool.f2n_idx;
-	}
-	return s;
-}
-
-// The same collider as a PoseShape (rp_shape.h): nothing of its transformed geometry is read from memory -- the body's pose
+// A collider of world w at its current pose, as a PoseShape (rp_shape.h): nothing of its transformed geometry is read from memory -- the body's pose
 // (7 doubles, world-minor, coalesced) gives the model matrix, and vertices / face normals are evaluated from the hull's local
 // data (template arrays: the same addresses for every lane that works on the same hull, L1-resident) when they are needed.
 __device__ __forceinline__ PoseShape dev_pose_shape(const DevView& d, const ColliderDesc& c, int w) {
@@ -1581,11 +1557,6 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 	V3 normal = v3(0.0, 0.0, 0.0);
 	Body b1, b2;
 	b1.fixed = b2.fixed = 1;
-#ifdef RP_POS_PREFETCH
-	Contact next_ct;
-	next_ct.r1_lc = next_ct.r2_lc = v3(0.0, 0.0, 0.0);
-	next_ct.lambda_n = next_ct.lambda_t = 0.0;
-#endif
 	for (;;) {
 		const unsigned int got = q.take(!have);
 		if (got != 0xffffffffu) {
@@ -1603,9 +1574,6 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 			b2.x = ld3(r2, DF_X); b2.q = ld4(r2, DF_Q);
 			c = 0;
 			have = cnt > 0;
-#ifdef RP_POS_PREFETCH
-			if (have) next_ct = ld_contact(cs, d.WS);
-#endif
 		}
 		if (!__any_sync(0xffffffffu, have)) {
 			if (q.empty()) break;
@@ -1613,12 +1581,7 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 		}
 		if (have) {
 			double* cp = cs + (size_t)c * 8 * d.WS;
-#ifdef RP_POS_PREFETCH
-			Contact ct = next_ct;
-			if (c + 1 < cnt) next_ct = ld_contact(cp + (size_t)8 * d.WS, d.WS);  // in flight while this contact is solved
-#else
 			Contact ct = ld_contact(cp, d.WS);
-#endif
 			solve_contact(ct, normal, b1, b2, h, &st, PrevFromDyn{r1, r2});
 			cp[6 * (size_t)d.WS] = ct.lambda_n;
 			cp[7 * (size_t)d.WS] = ct.lambda_t;
