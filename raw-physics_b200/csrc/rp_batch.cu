@@ -804,6 +804,19 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		if ((rc = dev_alloc(b, &d.n_live, W))) return rc;
 		if ((rc = dev_alloc(b, &d.blk_items, d.block_mode ? WP : 1, false))) return rc;
 	}
+	{
+		// Dataflow sweeps (pos_flow / vel_flow): contact-only batches of at least two warps of worlds in the reference's order.
+		// One large scene keeps the barrier form (a single world's counter would take every unit's update), and so do scenes
+		// with external constraints (their joint levels are not in the item sequence).
+		int flow = d.NJ == 0 && d.W >= 64 && !b->large && !b->coloured && !d.block_mode ? 1 : 0;
+		if (const char* e = getenv("RP_FLOW")) flow = flow && atoi(e) != 0;  // tuning aid: RP_FLOW=0 -> grid barriers between levels
+		d.flow_mode = flow;
+		const size_t rows = flow ? (size_t)RP_FLOW_LEVELS + 2 : 0;
+		if ((rc = dev_alloc(b, &d.wl_cnt, std::max<size_t>(1, rows * WS)))) return rc;
+		if ((rc = dev_alloc(b, &d.wl_pre, std::max<size_t>(1, rows * WS)))) return rc;
+		if ((rc = dev_alloc(b, &d.flow_done, 2 * WS + 32))) return rc;
+		if ((rc = dev_alloc(b, &d.flow_cursor, 2))) return rc;
+	}
 	if ((rc = dev_alloc(b, &d.contacts, WS * d.max_contacts * 8, false))) return rc;
 	if ((rc = dev_alloc(b, &d.n_contacts, W))) return rc;
 	if ((rc = dev_alloc(b, &d.lambdas, WS * std::max(d.NJ, 1)))) return rc;
@@ -1007,8 +1020,8 @@ static void launch_solve_pos(rp_batch* b, double h, uint32_t iters, int collisio
 	if (b->d.NJ > 0) launch_cooperative(k_solve_pos<true>, b->pos_grid, (unsigned int)RP_POS_THREADS, b->live_smem, b->stream, b->d, h, (int)iters, collisions, b->live_lists);
 	else launch_cooperative(k_solve_pos<false>, b->pos_grid, (unsigned int)RP_POS_THREADS, b->live_smem, b->stream, b->d, h, (int)iters, collisions, b->live_lists);
 }
-static void launch_solve_vel(rp_batch* b, double h) {
-	launch_cooperative(k_solve_vel, b->vel_grid, (unsigned int)RP_VEL_THREADS, b->live_smem, b->stream, b->d, h, b->live_lists);
+static void launch_solve_vel(rp_batch* b, double h, uint32_t iters) {
+	launch_cooperative(k_solve_vel, b->vel_grid, (unsigned int)RP_VEL_THREADS, b->live_smem, b->stream, b->d, h, b->live_lists, (int)iters);
 }
 
 static void enqueue_integrate(rp_batch* b, double h, bool last_substep) {
@@ -1068,7 +1081,7 @@ static void enqueue_solve(rp_batch* b, double h, uint32_t iters, int collisions)
 	launch_solve_pos(b, h, iters, collisions);
 	// velocity derivation (pbd.cpp:623-643) is lazy: a body's velocities are derived by the first velocity-level unit
 	// that touches it, else by the next substep's k_integrate, else by k_derive at the end of the frame
-	if (collisions) launch_solve_vel(b, h);
+	if (collisions) launch_solve_vel(b, h, iters);
 }
 static void enqueue_frame_end(rp_batch* b, double h) {
 	const DevView& d = b->d;
@@ -1447,7 +1460,7 @@ int rp_batch_profile(rp_batch* b, uint32_t frames, double dt, uint32_t substeps,
 				launch_solve_pos(b, h, iters, collisions ? 1 : 0);
 				if ((rc = mark(RP_K_SOLVE_POS))) return rc;
 				if (collisions) {
-					launch_solve_vel(b, h);
+					launch_solve_vel(b, h, iters);
 					if ((rc = mark(RP_K_SOLVE_VEL))) return rc;
 				}
 			}

@@ -57,6 +57,7 @@ __host__ __device__ __forceinline__ bool warp_pair_verts(int total_vertices) { r
 #define RP_EPA_THREADS 64
 
 #define RP_LVL_STRIDE 32   // ints between consecutive level fill counters (one 128-byte line each: [0] front, [1] back)
+#define RP_FLOW_LEVELS 62  // deepest schedule the dataflow sweeps take (their per-level tables sit in static shared memory)
 #ifndef RP_SMALL_MANIFOLD
 #define RP_SMALL_MANIFOLD 1000000  // (off: the refill loops of the solver kernels make manifold length irrelevant)
 // manifolds of up to this many contacts fill a level list from the front, larger ones from the back
@@ -572,7 +573,14 @@ __global__ void __launch_bounds__(256) k_substep_reset(DevView d) {
 	if (i < d.W) {
 		d.n_contacts[i] = 0;
 		d.n_live[i] = 0;
+		if (d.flow_mode) {
+			const int nl = min(*d.lvl_max, RP_FLOW_LEVELS);
+			for (int l = 1; l <= nl; ++l) d.wl_cnt[(size_t)l * d.WS + i] = 0;
+			d.flow_done[i] = 0u;
+			d.flow_done[d.WS + i] = 0u;
+		}
 	}
+	if (i < 2 && d.flow_mode) d.flow_cursor[i] = 0u;
 }
 
 #define RP_INT_THREADS 128
@@ -1280,6 +1288,7 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 				slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1u));
 				const int at = big ? d.lvl_off[lvl + 1] - 1 - slot : d.lvl_off[lvl] + slot;
 				d.lvl_items[at] = item;
+				if (d.flow_mode && lvl <= RP_FLOW_LEVELS) atomicAdd(&d.wl_cnt[(size_t)lvl * d.WS + w], 1);
 			}
 		}
 	}
@@ -1487,6 +1496,7 @@ __global__ void __launch_bounds__(RP_CLIPW_THREADS) k_manifold_warp(DevView d) {
 						const int big = n > RP_SMALL_MANIFOLD ? 1 : 0;
 						const int slot = atomicAdd(&d.lvl_fill[(size_t)lvl * RP_LVL_STRIDE + big], 1);
 						d.lvl_items[big ? d.lvl_off[lvl + 1] - 1 - slot : d.lvl_off[lvl] + slot] = item;
+						if (d.flow_mode && lvl <= RP_FLOW_LEVELS) atomicAdd(&d.wl_cnt[(size_t)lvl * d.WS + w], 1);
 					}
 				}
 			}
@@ -1650,12 +1660,221 @@ __device__ __forceinline__ int list_live_levels(const DevView& d, LiveLevels& s,
 	return s.n;
 }
 
+
+// ------------------------------------------------------------------------------------------------------ dataflow sweeps
+// The dependency between two levels never crosses worlds: a unit of level l in world w only has to wait for the units of
+// world w at lower levels. The level-major sweeps above hold the WHOLE grid at a barrier between two levels anyway (ncu,
+// frame 40: 4.2 barrier-stall cycles per issued instruction, and 22.6 of 32 lanes active because every warp's share of a
+// level ends in a partly filled trip). The dataflow form keeps the level-major item lists but replaces the barriers by
+// per-world counters:
+//  * k_manifold counts the units it lists per (level, world) (wl_cnt); the positional kernel turns the counts into a
+//    prefix over levels (wl_pre: units of the world at lower levels), one grid barrier per substep instead of one per level;
+//  * all levels (and positional iterations) form ONE item sequence in level-major order; a warp claims the next 32 items with
+//    one atomic on a global cursor and hands them to its lanes as they fall free (lanes stay full across level boundaries);
+//  * a lane that holds a unit polls flow_done[w] (ld.acquire.gpu) until it equals the number of units that precede the unit in
+//    its world; a finished unit stores its bodies and bumps the counter (red.release.gpu).
+// No deadlock: items are claimed in sequence order and a warp hands its claimed items to lanes in order, so the lowest
+// unfinished item of the sequence is always held by a lane, everything it waits for has finished, and it runs (the grid is
+// the cooperative launch's resident CTAs, so every claiming warp is running). The per-world order of units is the level
+// order either way: results are bit-identical to the barrier form. A lane that polls 2^16 times without success gives up,
+// flags the world (RP_ST_SOLVER_SINGULAR), tells every other lane to stop waiting and proceeds: a logic error cannot hang the device.
+struct FlowTables {
+	int cum[RP_FLOW_LEVELS + 2];   // items of levels < l (cum[levels + 1] = all)
+	int npf[RP_FLOW_LEVELS + 2], off0[RP_FLOW_LEVELS + 2], off1[RP_FLOW_LEVELS + 2];
+};
+// every CTA builds the same tables from the level fill counters; returns the number of items of one pass over the levels
+__device__ __forceinline__ unsigned int flow_tables(const DevView& d, FlowTables& t, int levels) {
+	if (threadIdx.x == 0) {
+		int run = 0;
+		for (int l = 1; l <= levels; ++l) {
+			const int f = d.lvl_fill[(size_t)l * RP_LVL_STRIDE], bk = d.lvl_fill[(size_t)l * RP_LVL_STRIDE + 1];
+			t.cum[l] = run;
+			t.npf[l] = f;
+			t.off0[l] = d.lvl_off[l];
+			t.off1[l] = d.lvl_off[l + 1];
+			run += f + bk;
+		}
+		t.cum[levels + 1] = run;
+	}
+	__syncthreads();
+	return (unsigned int)t.cum[levels + 1];
+}
+// wl_pre[l][w] = units of world w at levels < l, for l = 1 .. levels + 1
+__device__ __forceinline__ void flow_prefix(const DevView& d, int levels) {
+	const unsigned int n = (unsigned int)(levels + 1) * (unsigned int)d.W;
+	for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const unsigned int l1 = i / (unsigned int)d.W;
+		const int w = (int)(i - l1 * (unsigned int)d.W);
+		int run = 0;
+		for (int l = 1; l <= (int)l1; ++l) run += d.wl_cnt[(size_t)l * d.WS + w];
+		d.wl_pre[(size_t)(l1 + 1) * d.WS + w] = run;
+	}
+}
+__device__ __forceinline__ unsigned int flow_poll(const unsigned int* p) {
+	unsigned int v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void flow_signal(unsigned int* p) {
+	asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+#define RP_FLOW_SPIN_LIMIT (1 << 16)
+// one failed poll: counts it; true when the lane should stop waiting -- it ran out of patience (and then raises the batch-wide
+// "broken" word behind the done counters, which every other waiting lane looks at now and then), or someone else did
+__device__ __forceinline__ bool flow_give_up(const DevView& d, int* spins) {
+	unsigned int* broken = d.flow_done + 2 * (size_t)d.WS;
+	if (++*spins > RP_FLOW_SPIN_LIMIT) {
+		atomicExch(broken, 1u);
+		return true;
+	}
+	return (*spins & 255) == 0 && *reinterpret_cast<volatile unsigned int*>(broken) != 0u;
+}
+// a warp's claim on the item sequence: [next, end) is claimed and not yet handed to a lane
+struct FlowQueue {
+	unsigned int next, end, total;
+	bool more;  // the global cursor may still have items
+	__device__ __forceinline__ void init(unsigned int total_items) {
+		next = end = 0u;
+		total = total_items;
+		more = total_items > 0u;
+	}
+	// every lane calls this; lanes with want == true get the next items in sequence order (0xffffffff: none left)
+	__device__ __forceinline__ unsigned int take(bool want, unsigned int* cursor) {
+		const unsigned int mask = __ballot_sync(0xffffffffu, want);
+		if (mask == 0u) return 0xffffffffu;
+		const unsigned int n = __popc(mask), rank = __popc(mask & ((1u << (threadIdx.x & 31)) - 1u));
+		const unsigned int avail = end - next;
+		unsigned int got = 0xffffffffu;
+		if (avail >= n || !more) {
+			if (want && rank < avail) got = next + rank;
+			next += n < avail ? n : avail;
+			return got;
+		}
+		unsigned int base = 0u;
+		if ((threadIdx.x & 31) == 0) base = atomicAdd(cursor, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		unsigned int end2 = base + 32u;
+		if (base >= total) {
+			more = false;
+			base = end2 = total;
+		} else if (end2 > total) {
+			end2 = total;
+		}
+		if (want) {
+			if (rank < avail) got = next + rank;
+			else if (base + (rank - avail) < end2) got = base + (rank - avail);
+		}
+		const unsigned int used = n - avail;
+		next = base + used < end2 ? base + used : end2;
+		end = end2;
+		return got;
+	}
+	__device__ __forceinline__ bool drained() const { return next >= end && !more; }
+};
+// item g of the sequence -> iteration, level, slot of the level-major list
+__device__ __forceinline__ int flow_locate(const FlowTables& t, int levels, unsigned int per_pass, unsigned int g, int* it, int* level) {
+	const unsigned int pass = g / per_pass;
+	const int k = (int)(g - pass * per_pass);
+	int l = 1;
+	while (l < levels && k >= t.cum[l + 1]) ++l;
+	*it = (int)pass;
+	*level = l;
+	const int j = k - t.cum[l];
+	return j < t.npf[l] ? t.off0[l] + j : t.off1[l] - 1 - (j - t.npf[l]);
+}
+
+// positional sweep, dataflow form: every level of every iteration in one pass (see above); contact-only scenes
+__device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, double h, int levels, unsigned int per_pass, int iters) {
+	FlowQueue q;
+	q.init(per_pass * (unsigned int)iters);
+	const size_t total_row = (size_t)(levels + 1) * d.WS;
+	int st = 0;
+	bool have = false, ready = false;
+	int w = 0, cnt = 0, c = 0, ia = 0, ib = 0, spins = 0;
+	unsigned int need = 0u;
+	double* cs = 0;
+	DynRef r1, r2;
+	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
+	V3 normal = v3(0.0, 0.0, 0.0);
+	Body b1, b2;
+	b1.fixed = b2.fixed = 1;
+	for (;;) {
+		const unsigned int got = q.take(!have, d.flow_cursor);
+		if (got != 0xffffffffu) {
+			int it, level;
+			const SolveItem item = d.lvl_items[flow_locate(t, levels, per_pass, got, &it, &level)];
+			w = item.w;
+			cnt = item.cnt;
+			normal = item.normal;
+			ia = item.a; ib = item.b;
+			cs = contact_ptr(d, w, item.coff);
+			need = (unsigned int)d.wl_pre[(size_t)level * d.WS + w];
+			if (it > 0) need += (unsigned int)it * (unsigned int)d.wl_pre[total_row + w];
+			have = cnt > 0;
+			ready = false;
+			spins = 0;
+		}
+		if (!__any_sync(0xffffffffu, have)) {
+			if (q.drained()) break;
+			continue;
+		}
+		if (have && !ready) {
+			bool go = need == 0u;
+			if (!go) {
+				go = flow_poll(d.flow_done + w) >= need;
+				if (!go && flow_give_up(d, &spins)) {
+					st |= ST_SOLVER_SINGULAR;
+					go = true;
+				}
+			}
+			if (go) {
+				load_static(b1, d, ia);
+				load_static(b2, d, ib);
+				r1 = dyn_ref(d, w, ia);
+				r2 = dyn_ref(d, w, ib);
+				b1.x = ld3(r1, DF_X); b1.q = ld4(r1, DF_Q);
+				b2.x = ld3(r2, DF_X); b2.q = ld4(r2, DF_Q);
+				c = 0;
+				ready = true;
+			}
+		}
+		if (have && ready) {
+			double* cp = cs + (size_t)c * 8 * d.WS;
+			Contact ct = ld_contact(cp, d.WS);
+			solve_contact(ct, normal, b1, b2, h, &st, PrevFromDyn{r1, r2});
+			cp[6 * (size_t)d.WS] = ct.lambda_n;
+			cp[7 * (size_t)d.WS] = ct.lambda_t;
+			if (++c == cnt) {
+				if (!b1.fixed) { st3(r1, DF_X, b1.x); st4(r1, DF_Q, b1.q); }
+				if (!b2.fixed) { st3(r2, DF_X, b2.x); st4(r2, DF_Q, b2.q); }
+				if (st) {
+					atomicOr(&d.status[w], st);
+					st = 0;
+				}
+				flow_signal(d.flow_done + w);
+				have = false;
+			}
+		}
+	}
+}
+
 template <bool JOINTS>
 __global__ void RP_POS_BOUNDS k_solve_pos(DevView d, double h, int iters, int collisions, int live_lists) {
 	cg::grid_group grid = cg::this_grid();
 	extern __shared__ __align__(16) unsigned char s_live_raw[];
 	LiveLevels& s_live = *reinterpret_cast<LiveLevels*>(s_live_raw);
 	const int levels = *d.lvl_max;  // this frame's sweep depth over all worlds (k_schedule): read here, the host never needs it
+	if (!JOINTS && d.flow_mode && collisions && levels <= RP_FLOW_LEVELS) {
+		__shared__ FlowTables s_flow;
+		const unsigned int per_pass = flow_tables(d, s_flow, levels);
+		if (per_pass == 0u) return;
+		if ((unsigned long long)per_pass * (unsigned long long)iters < 0x7fffff00ull) {  // (same decision in every CTA)
+			flow_prefix(d, levels);
+			grid.sync();
+			pos_flow(d, s_flow, h, levels, per_pass, iters);
+			return;
+		}
+	}
 	const int n_live = list_live_levels<JOINTS>(d, s_live, levels, collisions, live_lists);
 	const int trips = n_live >= 0 ? n_live : levels;
 	bool dirty = false;
@@ -1773,11 +1992,93 @@ __device__ __forceinline__ void vel_level(const DevView& d, double h, int level)
 	}
 }
 
-__global__ void __launch_bounds__(RP_VEL_THREADS, RP_MINB_VEL) k_solve_vel(DevView d, double h, int live_lists) {
+
+// velocity pass, dataflow form (the prefix table is the one the positional kernel of this substep left)
+__device__ __forceinline__ void vel_flow(const DevView& d, const FlowTables& t, double h, int levels, unsigned int per_pass) {
+	FlowQueue q;
+	q.init(per_pass);
+	unsigned int* done = d.flow_done + d.WS;
+	bool have = false, ready = false;
+	int w = 0, cnt = 0, c = 0, ia = 0, ib = 0, spins = 0;
+	unsigned int need = 0u;
+	const double* cs = 0;
+	DynRef r1, r2;
+	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
+	AngPre tens;
+	tens.ii1 = tens.ii2 = zero_m3();
+	const int epoch = *d.epoch;
+	V3 normal = v3(0.0, 0.0, 0.0);
+	Body b1, b2;
+	b1.fixed = b2.fixed = 1;
+	for (;;) {
+		const unsigned int got = q.take(!have, d.flow_cursor + 1);
+		if (got != 0xffffffffu) {
+			int it, level;
+			const SolveItem item = d.lvl_items[flow_locate(t, levels, per_pass, got, &it, &level)];
+			w = item.w;
+			cnt = item.cnt;
+			normal = item.normal;
+			ia = item.a; ib = item.b;
+			cs = contact_ptr(d, w, item.coff);
+			need = (unsigned int)d.wl_pre[(size_t)level * d.WS + w];
+			have = cnt > 0;
+			ready = false;
+			spins = 0;
+		}
+		if (!__any_sync(0xffffffffu, have)) {
+			if (q.drained()) break;
+			continue;
+		}
+		if (have && !ready) {
+			bool go = need == 0u;
+			if (!go) {
+				go = flow_poll(done + w) >= need;
+				if (!go && flow_give_up(d, &spins)) {
+					atomicOr(&d.status[w], (int)ST_SOLVER_SINGULAR);
+					go = true;
+				}
+			}
+			if (go) {
+				load_static(b1, d, ia);
+				load_static(b2, d, ib);
+				r1 = dyn_ref(d, w, ia);
+				r2 = dyn_ref(d, w, ib);
+				const bool need_prev = b1.rest * b2.rest != 0.0;
+				load_for_velocity(b1, r1, d.active[bidx(d, ia, w)], d.vstamp + bidx(d, ia, w), epoch, h, need_prev);
+				load_for_velocity(b2, r2, d.active[bidx(d, ib, w)], d.vstamp + bidx(d, ib, w), epoch, h, need_prev);
+				tens = vel_tensors(b1, b2);
+				c = 0;
+				ready = true;
+			}
+		}
+		if (have && ready) {
+			const Contact ct = ld_contact(cs + (size_t)c * 8 * d.WS, d.WS);
+			solve_contact_velocity(ct, normal, b1, b2, h, tens);
+			if (++c == cnt) {
+				if (!b1.fixed) { st3(r1, DF_V, b1.v); st3(r1, DF_W, b1.w); }
+				if (!b2.fixed) { st3(r2, DF_V, b2.v); st3(r2, DF_W, b2.w); }
+				flow_signal(done + w);
+				have = false;
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(RP_VEL_THREADS, RP_MINB_VEL) k_solve_vel(DevView d, double h, int live_lists, int flow_iters) {
 	cg::grid_group grid = cg::this_grid();
 	extern __shared__ __align__(16) unsigned char s_live_raw[];
 	LiveLevels& s_live = *reinterpret_cast<LiveLevels*>(s_live_raw);
 	const int levels = *d.lvl_max;
+	// (flow_iters = the positional iterations of this substep's k_solve_pos: the same decision as there, or 0 for the barrier form)
+	if (flow_iters > 0 && d.flow_mode && levels <= RP_FLOW_LEVELS) {
+		__shared__ FlowTables s_flow;
+		const unsigned int per_pass = flow_tables(d, s_flow, levels);
+		if (per_pass == 0u) return;
+		if ((unsigned long long)per_pass * (unsigned long long)flow_iters < 0x7fffff00ull) {
+			vel_flow(d, s_flow, h, levels, per_pass);
+			return;
+		}
+	}
 	const int n_live = list_live_levels<false>(d, s_live, levels, 1, live_lists);
 	const int trips = n_live >= 0 ? n_live : levels;
 	bool dirty = false;
