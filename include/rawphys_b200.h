@@ -64,6 +64,12 @@ void rp_scene_destroy(rp_scene* s);
 /* collider_convex_hull_create (collider.cpp:194): triangle soup, vertices already scaled (3 doubles each), indices in
  * triples. The collider is queued for the NEXT rp_scene_add_body call. Returns its index within that body, or -1. */
 int rp_scene_collider_hull(rp_scene* s, const double* vertices_xyz, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices);
+/* Where rp_scene_collider_hull builds the hull topology from now on: cuda_device >= 0 = on that GPU (csrc/rp_hull.cuh: the
+ * quadratic passes of collider_convex_hull_create as one thread per output row, the order-defining flood fill as one thread;
+ * the arrays are identical to the host build's), -1 = on the host (the default). rp_scene_hull_build_stats: hulls built so far
+ * (identical soups share one) and the time that took, milliseconds. */
+int rp_scene_set_hull_device(rp_scene* s, int cuda_device);
+int rp_scene_hull_build_stats(const rp_scene* s, int* hulls_built, double* milliseconds);
 /* collider_sphere_create (collider.cpp:12) */
 int rp_scene_collider_sphere(rp_scene* s, float radius);
 /* entity_create / entity_create_fixed (entity.cpp:67-77): consumes the queued colliders. Returns the body id or -1. */
@@ -134,6 +140,9 @@ const char* rp_example_name(int index);
 const char* rp_example_error(void);
 rp_scene* rp_example_create(const char* name, const double* params, uint32_t n_params, int perturb, const char* mesh_dir_or_null,
 	rp_example_info* info_or_null);
+/* the same with the hulls built on a GPU (rp_scene_set_hull_device; -1 = host) */
+rp_scene* rp_example_create_on(const char* name, const double* params, uint32_t n_params, int perturb, const char* mesh_dir_or_null,
+	rp_example_info* info_or_null, int hull_cuda_device);
 
 /* ------------------------------------------------------------------------------------------------------- batches */
 /* Order of the Gauss-Seidel sweeps over a world's constraints (rp_batch_cfg.solve_order).

@@ -33,6 +33,7 @@ EXPORTS = [
     "rp_batch_get_status", "rp_batch_clear_status", "rp_batch_get_counters", "rp_batch_step_logged", "rp_batch_broad_pairs", "rp_batch_profile",
     "rp_measure_fp64_peak", "rp_scene_initial_state", "rp_scene_body_desc", "rp_scene_collider_soup_size", "rp_scene_collider_soup",
     "rp_scene_num_joints", "rp_scene_joint_desc", "rp_batch_graph_kernels", "rp_batch_pair_levels", "rp_batch_create_from", "rp_example_count", "rp_example_name", "rp_example_error", "rp_example_create",
+    "rp_example_create_on", "rp_scene_set_hull_device", "rp_scene_hull_build_stats",
 ]
 KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "cull", "gjk", "manifold", "solve_pos", "derive", "solve_vel", "epa"]
 
@@ -122,6 +123,10 @@ def lib():
     L.rp_example_error.restype = C.c_char_p
     L.rp_example_create.restype = C.c_void_p
     L.rp_example_create.argtypes = [C.c_char_p, _dp, C.c_uint32, C.c_int, C.c_char_p, C.POINTER(ExampleInfo)]
+    L.rp_example_create_on.restype = C.c_void_p
+    L.rp_example_create_on.argtypes = [C.c_char_p, _dp, C.c_uint32, C.c_int, C.c_char_p, C.POINTER(ExampleInfo), C.c_int]
+    L.rp_scene_set_hull_device.argtypes = [C.c_void_p, C.c_int]
+    L.rp_scene_hull_build_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -168,14 +173,16 @@ def example_names():
     return [L.rp_example_name(i).decode() for i in range(L.rp_example_count())]
 
 
-def example(name, params=(), perturb=False, mesh_dir=None):
+def example(name, params=(), perturb=False, mesh_dir=None, hull_device=-1):
     """A built-in scene (rp_example_create): -> (Scene, SceneDesc). The description carries the example's own step settings
-    (what its update() passes to pbd_simulate) and can be loaded into the oracle."""
+    (what its update() passes to pbd_simulate) and can be loaded into the oracle. hull_device >= 0: hull topology is built on
+    that GPU (rp_scene_set_hull_device) instead of the host."""
     L = lib()
     p = np.ascontiguousarray(params, dtype=np.float64)
     info = ExampleInfo()
     mesh_dir = mesh_dir or os.path.join(HERE, "assets", "meshes")  # (explicit: a tuning variant of the library lives elsewhere)
-    h = L.rp_example_create(name.encode(), _d(p) if p.size else None, int(p.size), int(perturb), mesh_dir.encode(), C.byref(info))
+    h = L.rp_example_create_on(name.encode(), _d(p) if p.size else None, int(p.size), int(perturb), mesh_dir.encode(), C.byref(info),
+                               int(hull_device))
     if not h:
         raise RawPhysError("rp_example_create(%r): %s" % (name, L.rp_example_error().decode()))
     sc = Scene(handle=h)
@@ -186,11 +193,19 @@ class Scene:
     """Scene template (rp_scene). `desc` is a description object with .bodies (position, rotation xyzw, mass, fixed,
     colliders[kind, vertices, indices, radius], mu_s, mu_d, restitution) and .constraints (dicts), as tests/scenes.py builds."""
 
-    def __init__(self, desc=None, handle=None):
+    def __init__(self, desc=None, handle=None, hull_device=-1):
         self.L = lib()
         self.h = C.c_void_p(handle if handle is not None else self.L.rp_scene_create())
+        if hull_device >= 0 and self.L.rp_scene_set_hull_device(self.h, int(hull_device)) != 0:
+            raise RawPhysError("rp_scene_set_hull_device: %s" % self.L.rp_last_error().decode())
         if desc is not None:
             self.load(desc)
+
+    def hull_build_stats(self):
+        """(hulls built, milliseconds spent building them)"""
+        n, ms = C.c_int(0), C.c_double(0.0)
+        self.L.rp_scene_hull_build_stats(self.h, C.byref(n), C.byref(ms))
+        return n.value, ms.value
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -12,6 +12,7 @@
 #include "rp_kernels.cuh"
 #include "rp_large.cuh"
 #include "rp_scene.h"
+#include "rp_hull.cuh"
 
 using namespace rp;
 
@@ -171,6 +172,28 @@ int rp_scene_collider_hull(rp_scene* s, const double* v, uint32_t nv, const uint
 		if (idx[i] >= nv) return -1;
 	}
 	return s->s.add_hull_collider(v, nv, idx, nidx);
+}
+int rp_scene_set_hull_device(rp_scene* s, int cuda_device) {
+	if (!s) return RP_ERR_ARG;
+	if (cuda_device < 0) {
+		s->s.hull_builder = nullptr;
+		s->s.hull_device = -1;
+		return RP_OK;
+	}
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || cuda_device >= n) {
+		cudaGetLastError();
+		return fail(RP_ERR_CUDA, "rp_scene_set_hull_device: no such CUDA device");
+	}
+	s->s.hull_builder = rp::build_hull_device;
+	s->s.hull_device = cuda_device;
+	return RP_OK;
+}
+int rp_scene_hull_build_stats(const rp_scene* s, int* hulls_built, double* milliseconds) {
+	if (!s) return RP_ERR_ARG;
+	if (hulls_built) *hulls_built = s->s.hulls_built;
+	if (milliseconds) *milliseconds = s->s.hull_build_ms;
+	return RP_OK;
 }
 int rp_scene_collider_sphere(rp_scene* s, float radius) {
 	if (!s) return -1;
@@ -778,7 +801,7 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 	if ((rc = dev_alloc(b, &d.lvl_cap, (size_t)d.max_levels + 2))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_off, (size_t)d.max_levels + 2))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_fill, ((size_t)d.max_levels + 2) * RP_LVL_STRIDE))) return rc;
-	if ((rc = dev_alloc(b, &d.lvl_max, 1))) return rc;
+	if ((rc = dev_alloc(b, &d.lvl_max, 2))) return rc;
 	if ((rc = dev_alloc(b, &d.lvl_items, WP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.pair_normal, SP, false))) return rc;
 	if ((rc = dev_alloc(b, &d.pair_coff, SP))) return rc;
@@ -805,11 +828,17 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		if ((rc = dev_alloc(b, &d.blk_items, d.block_mode ? WP : 1, false))) return rc;
 	}
 	{
-		// Dataflow sweeps (pos_flow / vel_flow): contact-only batches of at least two warps of worlds in the reference's order.
-		// One large scene keeps the barrier form (a single world's counter would take every unit's update), and so do scenes
-		// with external constraints (their joint levels are not in the item sequence).
+		// Dataflow sweeps (pos_flow / vel_flow): contact-only batches of at least two warps of worlds. Measured (B200, ms per
+		// frame): w256 x 4096 frames 40..59 24.1 -> 20.2, stack x 4096 2.56 -> 2.30. Scenes with external constraints can run it
+		// (their joints head each level's items) but keep the barrier form by default: the levers x 16384 have two or three
+		// levels per sweep and pay more for the prefix pass than they save (1.26 -> 1.36); one large scene is bound by the
+		// latency of its units, not by the barriers (brick wall 32 x 32 coloured: 5.37 vs 5.43), and keeps it too.
 		int flow = d.NJ == 0 && d.W >= 64 && !b->large && !b->coloured && !d.block_mode ? 1 : 0;
-		if (const char* e = getenv("RP_FLOW")) flow = flow && atoi(e) != 0;  // tuning aid: RP_FLOW=0 -> grid barriers between levels
+		if (const char* e = getenv("RP_FLOW")) {  // tuning aid: 0 = grid barriers between levels, 2 = dataflow for any batch
+			const int v = atoi(e);
+			if (v == 0) flow = 0;
+			if (v == 2 && !d.block_mode) flow = 1;
+		}
 		d.flow_mode = flow;
 		const size_t rows = flow ? (size_t)RP_FLOW_LEVELS + 2 : 0;
 		if ((rc = dev_alloc(b, &d.wl_cnt, std::max<size_t>(1, rows * WS)))) return rc;

@@ -520,6 +520,11 @@ const char* rp_example_name(int index) { return index >= 0 && index < N_EXAMPLES
 const char* rp_example_error(void) { return g_example_err.c_str(); }
 
 rp_scene* rp_example_create(const char* name, const double* params, uint32_t n_params, int perturb, const char* mesh_dir, rp_example_info* info) {
+	return rp_example_create_on(name, params, n_params, perturb, mesh_dir, info, -1);
+}
+
+rp_scene* rp_example_create_on(const char* name, const double* params, uint32_t n_params, int perturb, const char* mesh_dir, rp_example_info* info,
+	int hull_cuda_device) {
 	g_example_err.clear();
 	if (!name) {
 		g_example_err = "rp_example_create: no name";
@@ -529,6 +534,11 @@ rp_scene* rp_example_create(const char* name, const double* params, uint32_t n_p
 		if (strcmp(EXAMPLES[i].name, name) != 0) continue;
 		Build b;
 		b.sc = rp_scene_create();
+		if (hull_cuda_device >= 0 && rp_scene_set_hull_device(b.sc, hull_cuda_device) != RP_OK) {
+			g_example_err = std::string("rp_example_create_on: ") + rp_last_error();
+			rp_scene_destroy(b.sc);
+			return 0;
+		}
 		b.meshes = mesh_dir && *mesh_dir ? mesh_dir : default_mesh_dir();
 		b.perturb = perturb != 0;
 		if (!EXAMPLES[i].build(b, params, n_params)) {

@@ -545,7 +545,10 @@ __global__ void __launch_bounds__(32) k_schedule(DevView d, int collisions) {
 // zeroes the per-frame level capacities (before k_schedule) / turns them into list offsets (after it)
 __global__ void __launch_bounds__(256) k_level_reset(DevView d) {
 	for (int l = threadIdx.x; l < d.max_levels + 2; l += blockDim.x) d.lvl_cap[l] = 0;
-	if (threadIdx.x == 0) *d.lvl_max = 0;
+	if (threadIdx.x == 0) {
+		d.lvl_max[1] = d.lvl_max[0];  // the previous frame's depth: its last substep left per-world counts up to there (k_substep_reset)
+		d.lvl_max[0] = 0;
+	}
 }
 __global__ void k_level_offsets(DevView d) {
 	int run = 0;
@@ -574,7 +577,7 @@ __global__ void __launch_bounds__(256) k_substep_reset(DevView d) {
 		d.n_contacts[i] = 0;
 		d.n_live[i] = 0;
 		if (d.flow_mode) {
-			const int nl = min(*d.lvl_max, RP_FLOW_LEVELS);
+			const int nl = min(max(d.lvl_max[0], d.lvl_max[1]), RP_FLOW_LEVELS);
 			for (int l = 1; l <= nl; ++l) d.wl_cnt[(size_t)l * d.WS + i] = 0;
 			d.flow_done[i] = 0u;
 			d.flow_done[d.WS + i] = 0u;
@@ -1680,21 +1683,27 @@ __device__ __forceinline__ int list_live_levels(const DevView& d, LiveLevels& s,
 // flags the world (RP_ST_SOLVER_SINGULAR), tells every other lane to stop waiting and proceeds: a logic error cannot hang the device.
 struct FlowTables {
 	int cum[RP_FLOW_LEVELS + 2];   // items of levels < l (cum[levels + 1] = all)
+	int jn[RP_FLOW_LEVELS + 2];    // (joint, world) items that head level l: its joints x W
 	int npf[RP_FLOW_LEVELS + 2], off0[RP_FLOW_LEVELS + 2], off1[RP_FLOW_LEVELS + 2];
 };
-// every CTA builds the same tables from the level fill counters; returns the number of items of one pass over the levels
-__device__ __forceinline__ unsigned int flow_tables(const DevView& d, FlowTables& t, int levels) {
+// every CTA builds the same tables from the level fill counters; returns the number of items of one pass over the levels.
+// A level's items are its joints in every world (world fastest: lane = world), then its contact units.
+template <bool JOINTS>
+__device__ __forceinline__ unsigned int flow_tables(const DevView& d, FlowTables& t, int levels, int collisions) {
 	if (threadIdx.x == 0) {
-		int run = 0;
+		long long run = 0;
 		for (int l = 1; l <= levels; ++l) {
-			const int f = d.lvl_fill[(size_t)l * RP_LVL_STRIDE], bk = d.lvl_fill[(size_t)l * RP_LVL_STRIDE + 1];
-			t.cum[l] = run;
+			const int f = collisions ? d.lvl_fill[(size_t)l * RP_LVL_STRIDE] : 0, bk = collisions ? d.lvl_fill[(size_t)l * RP_LVL_STRIDE + 1] : 0;
+			const int nj = JOINTS && l <= d.joint_levels ? d.joint_lptr[l] - d.joint_lptr[l - 1] : 0;
+			t.cum[l] = (int)run;
+			t.jn[l] = nj * d.W;
 			t.npf[l] = f;
 			t.off0[l] = d.lvl_off[l];
 			t.off1[l] = d.lvl_off[l + 1];
-			run += f + bk;
+			run += (long long)nj * d.W + f + bk;
+			if (run > 0x7fffff00ll) run = 0x7fffff00ll;  // (the caller falls back to the barrier form)
 		}
-		t.cum[levels + 1] = run;
+		t.cum[levels + 1] = (int)run;
 	}
 	__syncthreads();
 	return (unsigned int)t.cum[levels + 1];
@@ -1771,19 +1780,27 @@ struct FlowQueue {
 	}
 	__device__ __forceinline__ bool drained() const { return next >= end && !more; }
 };
-// item g of the sequence -> iteration, level, slot of the level-major list
-__device__ __forceinline__ int flow_locate(const FlowTables& t, int levels, unsigned int per_pass, unsigned int g, int* it, int* level) {
+// item g of the sequence -> iteration, level, and either the slot of the level-major contact list (return value >= 0) or,
+// for one of the level's joint items, -1 and its index among them (*joint_item: joint-in-level * W + world)
+__device__ __forceinline__ int flow_locate(const FlowTables& t, int levels, unsigned int per_pass, unsigned int g, int* it, int* level, int* joint_item) {
 	const unsigned int pass = g / per_pass;
 	const int k = (int)(g - pass * per_pass);
 	int l = 1;
 	while (l < levels && k >= t.cum[l + 1]) ++l;
 	*it = (int)pass;
 	*level = l;
-	const int j = k - t.cum[l];
+	int j = k - t.cum[l];
+	if (j < t.jn[l]) {
+		*joint_item = j;
+		return -1;
+	}
+	j -= t.jn[l];
 	return j < t.npf[l] ? t.off0[l] + j : t.off1[l] - 1 - (j - t.npf[l]);
 }
 
-// positional sweep, dataflow form: every level of every iteration in one pass (see above); contact-only scenes
+// positional sweep, dataflow form: every level of every iteration in one pass (see above). A joint item is solved in one trip
+// of the loop, a contact unit in one trip per contact.
+template <bool JOINTS>
 __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, double h, int levels, unsigned int per_pass, int iters) {
 	FlowQueue q;
 	q.init(per_pass * (unsigned int)iters);
@@ -1791,6 +1808,7 @@ __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, 
 	int st = 0;
 	bool have = false, ready = false;
 	int w = 0, cnt = 0, c = 0, ia = 0, ib = 0, spins = 0;
+	int ju = -1;  // the joint a lane holds (JOINTS), -1: a contact unit
 	unsigned int need = 0u;
 	double* cs = 0;
 	DynRef r1, r2;
@@ -1801,15 +1819,28 @@ __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, 
 	for (;;) {
 		const unsigned int got = q.take(!have, d.flow_cursor);
 		if (got != 0xffffffffu) {
-			int it, level;
-			const SolveItem item = d.lvl_items[flow_locate(t, levels, per_pass, got, &it, &level)];
-			w = item.w;
-			cnt = item.cnt;
-			normal = item.normal;
-			ia = item.a; ib = item.b;
-			cs = contact_ptr(d, w, item.coff);
+			int it, level, jitem = 0;
+			const int slot = flow_locate(t, levels, per_pass, got, &it, &level, &jitem);
+			if (JOINTS && slot < 0) {
+				const unsigned int jl = (unsigned int)jitem / (unsigned int)d.W;
+				w = (int)((unsigned int)jitem - jl * (unsigned int)d.W);
+				ju = d.joint_sched[d.joint_lptr[level - 1] + (int)jl];
+				const Joint j = d.joints[ju];
+				ia = j.e1; ib = j.e2;
+				cnt = 1;
+			} else {
+				const SolveItem item = d.lvl_items[slot];
+				w = item.w;
+				cnt = item.cnt;
+				normal = item.normal;
+				ia = item.a; ib = item.b;
+				cs = contact_ptr(d, w, item.coff);
+				ju = -1;
+			}
+			// units of this world that precede the item: everything of earlier passes, the joints and the contact units of lower levels
 			need = (unsigned int)d.wl_pre[(size_t)level * d.WS + w];
-			if (it > 0) need += (unsigned int)it * (unsigned int)d.wl_pre[total_row + w];
+			if (JOINTS) need += (unsigned int)d.joint_lptr[min(level - 1, d.joint_levels)];
+			if (it > 0) need += (unsigned int)it * ((unsigned int)d.wl_pre[total_row + w] + (JOINTS ? (unsigned int)d.NJ : 0u));
 			have = cnt > 0;
 			ready = false;
 			spins = 0;
@@ -1839,12 +1870,21 @@ __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, 
 			}
 		}
 		if (have && ready) {
-			double* cp = cs + (size_t)c * 8 * d.WS;
-			Contact ct = ld_contact(cp, d.WS);
-			solve_contact(ct, normal, b1, b2, h, &st, PrevFromDyn{r1, r2});
-			cp[6 * (size_t)d.WS] = ct.lambda_n;
-			cp[7 * (size_t)d.WS] = ct.lambda_t;
-			if (++c == cnt) {
+			if (JOINTS && ju >= 0) {
+				const Joint j = d.joints[ju];
+				JointLambda lam = d.lambdas[(size_t)ju * d.WS + w];
+				solve_joint(j, lam, b1, b2, h, &st);
+				d.lambdas[(size_t)ju * d.WS + w] = lam;
+				c = cnt;
+			} else {
+				double* cp = cs + (size_t)c * 8 * d.WS;
+				Contact ct = ld_contact(cp, d.WS);
+				solve_contact(ct, normal, b1, b2, h, &st, PrevFromDyn{r1, r2});
+				cp[6 * (size_t)d.WS] = ct.lambda_n;
+				cp[7 * (size_t)d.WS] = ct.lambda_t;
+				++c;
+			}
+			if (c == cnt) {
 				if (!b1.fixed) { st3(r1, DF_X, b1.x); st4(r1, DF_Q, b1.q); }
 				if (!b2.fixed) { st3(r2, DF_X, b2.x); st4(r2, DF_Q, b2.q); }
 				if (st) {
@@ -1864,14 +1904,14 @@ __global__ void RP_POS_BOUNDS k_solve_pos(DevView d, double h, int iters, int co
 	extern __shared__ __align__(16) unsigned char s_live_raw[];
 	LiveLevels& s_live = *reinterpret_cast<LiveLevels*>(s_live_raw);
 	const int levels = *d.lvl_max;  // this frame's sweep depth over all worlds (k_schedule): read here, the host never needs it
-	if (!JOINTS && d.flow_mode && collisions && levels <= RP_FLOW_LEVELS) {
+	if (d.flow_mode && levels <= RP_FLOW_LEVELS) {
 		__shared__ FlowTables s_flow;
-		const unsigned int per_pass = flow_tables(d, s_flow, levels);
+		const unsigned int per_pass = flow_tables<JOINTS>(d, s_flow, levels, collisions);
 		if (per_pass == 0u) return;
 		if ((unsigned long long)per_pass * (unsigned long long)iters < 0x7fffff00ull) {  // (same decision in every CTA)
 			flow_prefix(d, levels);
 			grid.sync();
-			pos_flow(d, s_flow, h, levels, per_pass, iters);
+			pos_flow<JOINTS>(d, s_flow, h, levels, per_pass, iters);
 			return;
 		}
 	}
@@ -2013,8 +2053,8 @@ __device__ __forceinline__ void vel_flow(const DevView& d, const FlowTables& t, 
 	for (;;) {
 		const unsigned int got = q.take(!have, d.flow_cursor + 1);
 		if (got != 0xffffffffu) {
-			int it, level;
-			const SolveItem item = d.lvl_items[flow_locate(t, levels, per_pass, got, &it, &level)];
+			int it, level, jitem;
+			const SolveItem item = d.lvl_items[flow_locate(t, levels, per_pass, got, &it, &level, &jitem)];
 			w = item.w;
 			cnt = item.cnt;
 			normal = item.normal;
@@ -2072,9 +2112,11 @@ __global__ void __launch_bounds__(RP_VEL_THREADS, RP_MINB_VEL) k_solve_vel(DevVi
 	// (flow_iters = the positional iterations of this substep's k_solve_pos: the same decision as there, or 0 for the barrier form)
 	if (flow_iters > 0 && d.flow_mode && levels <= RP_FLOW_LEVELS) {
 		__shared__ FlowTables s_flow;
-		const unsigned int per_pass = flow_tables(d, s_flow, levels);
+		// the positional kernel of this substep took the dataflow form (and left the prefix table) iff ITS item count fitted: the
+		// velocity pass has the contact units only, so its own count is checked against the same bound with the joints added
+		const unsigned int per_pass = flow_tables<false>(d, s_flow, levels, 1);
 		if (per_pass == 0u) return;
-		if ((unsigned long long)per_pass * (unsigned long long)flow_iters < 0x7fffff00ull) {
+		if (((unsigned long long)per_pass + (unsigned long long)d.NJ * d.W) * (unsigned long long)flow_iters < 0x7fffff00ull) {
 			vel_flow(d, s_flow, h, levels, per_pass);
 			return;
 		}

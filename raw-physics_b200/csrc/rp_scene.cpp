@@ -2,6 +2,7 @@
 #include "rp_scene.h"
 
 #include <algorithm>
+#include <chrono>
 #include <string.h>
 
 namespace rp {
@@ -181,7 +182,18 @@ int Scene::add_hull_collider(const double* vx, uint32_t nverts, const uint32_t* 
 		}
 	}
 	if (id < 0) {
-		HullHost h = build_hull(vx, nverts, indices, nidx);
+		HullHost h;
+		if (hull_builder) {
+			float ms = 0.f;
+			std::string err;
+			if (!hull_builder(hull_device, vx, nverts, indices, nidx, &h, &ms, &err)) return -1;
+			hull_build_ms += ms;
+		} else {
+			const auto t0 = std::chrono::steady_clock::now();
+			h = build_hull(vx, nverts, indices, nidx);
+			hull_build_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		}
+		++hulls_built;
 		// A zero-area triangle has no normal (NaN after normalisation in the reference, collider.cpp:180-192) and leaves a face
 		// that clipping would index out of its row; an empty face likewise. Refused instead of built.
 		if (h.face_ptr.size() < 2) return -1;

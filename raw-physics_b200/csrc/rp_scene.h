@@ -10,6 +10,7 @@
 #ifndef RP_SCENE_H
 #define RP_SCENE_H
 
+#include <string>
 #include <vector>
 #include "rp_solve.h"
 
@@ -42,6 +43,13 @@ struct Scene {
 	std::vector<ColliderDesc> pending;        // colliders of the body being assembled
 	int total_tv = 0, total_tn = 0;           // transformed vertices / normals per world
 	std::vector<V3> force, torque;            // per-body external force / torque sums for the coming frame(s)
+	// hull topology builder: build_hull() on the host, or (set through rp_scene_set_hull_device) the device build of rp_hull.cuh,
+	// reached through a pointer because this file is also compiled into the CPU checker, which has no CUDA
+	bool (*hull_builder)(int device, const double* verts_xyz, uint32_t nverts, const uint32_t* indices, uint32_t nidx, HullHost* out,
+		float* ms_out, std::string* err) = nullptr;
+	int hull_device = -1;
+	double hull_build_ms = 0.0;               // time spent building hull topology (host: wall clock; device: CUDA events)
+	int hulls_built = 0;
 
 	int add_hull_collider(const double* verts_xyz, uint32_t nverts, const uint32_t* indices, uint32_t nidx);
 	int add_sphere_collider(float radius);

@@ -5,7 +5,8 @@
 //
 //   rp_headless --list
 //   rp_headless --scene NAME [--params a,b,c] [--perturb] [--rows R] [--cols C] [--worlds W] [--frames F] [--dt DT]
-//               [--substeps S] [--iters I] [--device D] [--meshes DIR] [--dump FILE] [--dump-every K] [--no-collisions]
+//               [--substeps S] [--iters I] [--device D] [--meshes DIR] [--dump FILE] [--dump-every K] [--dump-worlds N] [--no-collisions]
+//               [--device-hulls]   (hull topology built on the GPU: rp_example_create_on, csrc/rp_hull.cuh)
 //               [--coloured]   (RP_ORDER_COLOURED: graph-coloured sweeps for one large scene, not bit-comparable)
 //               [--gpus G]     (the worlds in G contiguous shards, one batch per CUDA device d, d + 1, ...: worlds never interact,
 //                               so there is no exchange between them; every frame is enqueued on all devices before any is waited for)
@@ -17,9 +18,12 @@
 // reference's OBJ files as triangle soups of float positions (what obj_parse returns, obj.cpp:73-81), one `<name>.f32`
 // file each (raw little-endian float triples), by default in assets/meshes next to the library.
 //
-// --dump writes the state of world 0 every K frames (default: every frame): a 32-byte header {"RPHD", u32 version = 1,
-// u32 bodies, u32 records, u32 stride = RP_STATE_STRIDE, u32 every, u64 reserved} followed by `records` blocks of
-// {u32 frame, u32 0, double state[bodies][stride]}. Frame numbers count completed steps (1 = after the first step).
+// --dump writes the state of the first N worlds (--dump-worlds, default 1) every K frames (default: every frame): a 32-byte
+// header {"RPHD", u32 version (1: one world, 2: several), u32 bodies, u32 records, u32 stride = RP_STATE_STRIDE, u32 every,
+// u32 worlds (version 2), u32 reserved} followed by `records` blocks of {u32 frame, u32 0, double state[worlds][bodies][stride]}.
+// Frame numbers count completed steps (1 = after the first step). raw-physics_b200/viewer.py turns a dump into an animated GIF
+// or an .obj (the counterpart of looking at the reference's window).
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -37,9 +41,9 @@ namespace {
 struct Options {
 	std::string scene = "stack", meshes, dump;
 	std::vector<double> params;
-	int rows = 0, cols = 0, worlds = 1, frames = 60, substeps = 0, iters = -1, device = 0, dump_every = 1, gpus = 1;
+	int rows = 0, cols = 0, worlds = 1, frames = 60, substeps = 0, iters = -1, device = 0, dump_every = 1, dump_worlds = 1, gpus = 1;
 	double dt = 1.0 / 60.0;
-	bool collisions = true, coloured = false, perturb = false, list = false;
+	bool collisions = true, coloured = false, perturb = false, list = false, device_hulls = false;
 };
 
 [[noreturn]] void die(const std::string& what) {
@@ -82,11 +86,13 @@ void parse(int argc, char** argv, Options& o) {
 		else if (a == "--meshes") o.meshes = next();
 		else if (a == "--dump") o.dump = next();
 		else if (a == "--dump-every") o.dump_every = atoi(next());
+		else if (a == "--dump-worlds") o.dump_worlds = atoi(next());
+		else if (a == "--device-hulls") o.device_hulls = true;
 		else if (a == "--no-collisions") o.collisions = false;
 		else if (a == "--coloured") o.coloured = true;
 		else die("unknown argument " + a);
 	}
-	if (o.worlds < 1 || o.frames < 0 || o.substeps < 0 || o.dump_every < 1 || o.rows < 0 || o.cols < 0 || o.gpus < 1 || o.gpus > o.worlds) die("bad argument value");
+	if (o.worlds < 1 || o.frames < 0 || o.substeps < 0 || o.dump_every < 1 || o.rows < 0 || o.cols < 0 || o.gpus < 1 || o.gpus > o.worlds || o.dump_worlds < 1) die("bad argument value");
 }
 
 }  // namespace
@@ -109,9 +115,12 @@ int main(int argc, char** argv) {
 		o.params.push_back(o.cols ? o.cols : 32);
 	}
 	rp_example_info info;
-	rp_scene* scene = rp_example_create(o.scene.c_str(), o.params.empty() ? 0 : o.params.data(), (uint32_t)o.params.size(), o.perturb ? 1 : 0,
-		o.meshes.empty() ? 0 : o.meshes.c_str(), &info);
+	rp_scene* scene = rp_example_create_on(o.scene.c_str(), o.params.empty() ? 0 : o.params.data(), (uint32_t)o.params.size(), o.perturb ? 1 : 0,
+		o.meshes.empty() ? 0 : o.meshes.c_str(), &info, o.device_hulls ? o.device : -1);
 	if (!scene) die(std::string("rp_example_create: ") + rp_example_error());
+	int hulls_built = 0;
+	double hull_ms = 0.0;
+	rp_scene_hull_build_stats(scene, &hulls_built, &hull_ms);
 	if (o.substeps == 0) o.substeps = (int)info.substeps;
 	if (o.iters < 0) o.iters = (int)info.pos_iters;
 	if (!info.collisions) o.collisions = false;
@@ -129,17 +138,17 @@ int main(int argc, char** argv) {
 	}
 	rp_batch* batch = shards[0];
 	const uint32_t nb = rp_batch_num_bodies(batch);
-	std::vector<double> state((size_t)nb * RP_STATE_STRIDE);
+	const uint32_t dump_worlds = (uint32_t)std::min(o.dump_worlds, shard_worlds[0]);
+	std::vector<double> state((size_t)dump_worlds * nb * RP_STATE_STRIDE);
 
 	FILE* dump = 0;
 	uint32_t records = 0;
 	if (!o.dump.empty()) {
 		dump = fopen(o.dump.c_str(), "wb");
 		if (!dump) die("cannot write " + o.dump);
-		const uint32_t head[6] = {0x44485052u /* "RPHD" */, 1u, nb, 0u, (uint32_t)RP_STATE_STRIDE, (uint32_t)o.dump_every};
-		const uint64_t reserved = 0;
+		const uint32_t head[8] = {0x44485052u /* "RPHD" */, dump_worlds > 1 ? 2u : 1u, nb, 0u, (uint32_t)RP_STATE_STRIDE, (uint32_t)o.dump_every,
+			dump_worlds > 1 ? dump_worlds : 0u, 0u};
 		fwrite(head, sizeof(head), 1, dump);
-		fwrite(&reserved, sizeof(reserved), 1, dump);
 	}
 
 	const auto t0 = std::chrono::steady_clock::now();
@@ -151,7 +160,7 @@ int main(int argc, char** argv) {
 			if (rp_batch_step(b, o.dt, (uint32_t)o.substeps, (uint32_t)o.iters, o.collisions ? 1 : 0) != RP_OK) die("rp_batch_step");
 		}
 		if (dump && (f % o.dump_every == 0 || f == o.frames)) {
-			const int rc = rp_batch_download_state(batch, 0, 1, state.data());
+			const int rc = rp_batch_download_state(batch, 0, dump_worlds, state.data());
 			if (rc != RP_OK && rc != RP_ERR_CAPACITY) die("rp_batch_download_state");
 			const uint32_t tag[2] = {(uint32_t)f, 0u};
 			fwrite(tag, sizeof(tag), 1, dump);
@@ -193,11 +202,11 @@ int main(int argc, char** argv) {
 	const double units = (double)nb * o.worlds * o.substeps * o.frames;
 	printf("{\"scene\": \"%s\", \"order\": \"%s\", \"sweep_depth\": %.1f, \"worlds\": %d, \"gpus\": %d, \"bodies\": %u, \"frames\": %d, \"substeps\": %d, \"seconds\": %.6f, "
 	       "\"ms_per_frame\": %.4f, \"body_substeps_per_s\": %.6g, \"status_bits\": %d, \"diverged_worlds\": %d, \"pair_tests\": %llu, \"epa_runs\": %llu, "
-	       "\"contacts\": %llu}\n",
+	       "\"contacts\": %llu, \"hulls_built\": %d, \"hull_build_ms\": %.3f, \"hull_builder\": \"%s\"}\n",
 		o.scene.c_str(), o.coloured ? "coloured" : "reference", counters[5] ? (double)counters[4] / (double)counters[5] / o.worlds : 0.0, o.worlds, o.gpus, nb,
 		o.frames, o.substeps, seconds, o.frames ? 1e3 * seconds / o.frames : 0.0,
 		seconds > 0.0 ? units / seconds : 0.0, (int)bits, diverged, (unsigned long long)counters[0], (unsigned long long)counters[1],
-		(unsigned long long)counters[2]);
+		(unsigned long long)counters[2], hulls_built, hull_ms, o.device_hulls ? "device" : "host");
 	for (rp_batch* b : shards) rp_batch_destroy(b);
 	rp_scene_destroy(scene);
 	return bits || diverged ? 2 : 0;

@@ -117,3 +117,29 @@ def test_headless_shards_over_two_gpus(pkg, oracle_flavour, tmp_path):
     for _ in range(45):
         o.step()
     assert np.array_equal(dump[45][:, :15], o.state())
+
+
+@pytest.mark.gpu
+def test_headless_device_hulls_and_multi_world_dump(pkg, oracle_flavour, tmp_path):
+    """--device-hulls (hull topology built by csrc/rp_hull.cuh) and --dump-worlds (8 f4: a version-2 dump of
+    several worlds, read back and drawn by raw-physics_b200/viewer.py): coin.cpp's 64-gon cylinder caps, bit-exact against
+    the oracle, every dumped world identical."""
+    import importlib
+    viewer = importlib.import_module("rawphys_b200.viewer")
+    dump = str(tmp_path / "coin.rphd")
+    r = subprocess.run([EXE, "--scene", "coin", "--frames", "40", "--worlds", "4", "--dump", dump, "--dump-every", "10", "--dump-worlds", "3",
+                        "--device-hulls"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["hull_builder"] == "device" and info["hulls_built"] >= 2 and info["status_bits"] == 0
+    frames, states = viewer.load_dump(dump)
+    assert list(frames) == [10, 20, 30, 40] and states.shape[1] == 3
+    assert np.array_equal(states[:, 0], states[:, 1]) and np.array_equal(states[:, 0], states[:, 2])
+    scene, desc = pkg.example("coin")
+    o = refdrv.RefWorld(oracle_flavour).load(desc)
+    for _ in range(40):
+        o.step(substeps=desc.substeps, iters=desc.iters, collisions=desc.collisions)
+    assert np.array_equal(states[-1, 0][:, :15], o.state())
+    gif = str(tmp_path / "coin.gif")
+    assert viewer.render_gif(viewer.scene_geometry(scene), frames, states, gif, size=128) == 4
+    assert os.path.getsize(gif) > 1000

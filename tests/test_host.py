@@ -182,3 +182,12 @@ def test_scene_builder_validates_its_inputs(pkg):
     assert L.rp_scene_hull_sizes(s, 0, 0, sizes.ctypes.data_as(C.POINTER(C.c_int32))) == 0
     assert L.rp_scene_hull_dump(s, 0, 0, None, None, None, None, None, None, None, None, None, None) != 0
     L.rp_scene_destroy(s)
+
+
+def test_device_hull_builder_needs_a_device(pkg):
+    """rp_scene_set_hull_device: -1 (host) always works; a CUDA device that does not exist is an error, not a silent host build"""
+    L = pkg.lib()
+    s = pkg.Scene()
+    assert L.rp_scene_set_hull_device(s.h, -1) == 0
+    assert L.rp_scene_set_hull_device(s.h, 4096) != 0
+    assert s.hull_build_stats() == (0, 0.0)
