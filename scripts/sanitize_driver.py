@@ -27,7 +27,15 @@ def run(name, params=(), perturb=False, worlds=3, frames=3, **kw):
     print("ok", name, kw, flush=True)
 
 
-run("stack", worlds=5, frames=40)               # contacts form around frame 30
+run("stack", worlds=5, frames=40)               # contacts form around frame 30 (fewer than 64 worlds: barrier sweeps)
+run("stack", worlds=70, frames=36)              # 64 worlds and more: dataflow sweeps (pos_flow / vel_flow)
+os.environ["RP_FLOW"] = "2"                     # ... forced on for a joint scene with contacts and for one large scene
+run("seesaw", worlds=40, frames=30)
+run("brick_wall", (6, 6), worlds=1, frames=30, coloured=True)
+del os.environ["RP_FLOW"]
+scene, desc = pkg.example("spot_storm", (1, 7), hull_device=0)   # device-side hull construction (rp_hull.cuh), 529-vertex hull included
+assert scene.hull_build_stats()[0] >= 11
+print("ok device hulls", scene.hull_build_stats(), flush=True)
 run("w256", worlds=64, frames=2)
 run("w256", (2, 2, 4), worlds=33, frames=45, sweep_block_worlds=4)
 run("hinge_joints", perturb=True, worlds=40, frames=5)
