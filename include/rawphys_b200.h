@@ -15,6 +15,11 @@
  * batch call fails with RP_ERR_CUDA.
  *
  * Body ids are the order of rp_scene_add_body calls and equal the reference's eids when its eid_counter starts at 0.
+ *
+ * The reference's compile-time switches (pbd.cpp:12-16, pbd_base_constraints.cpp:4): ENABLE_SIMULATION_ISLANDS and the three
+ * sleeping constants are run-time fields of rp_batch_cfg; USE_QUATERNIONS_LINEARIZED_FORMULAS stays a compile-time switch -- the
+ * same sources built with -DRP_EXACT_QUATERNIONS give librawphys_b200_exactq.so (same ABI), the reference WITHOUT that define:
+ * orientation updates by axis-angle quaternions through sin / cos (raw-physics_b200/build.py build_exactq).
  */
 #ifndef RAWPHYS_B200_H
 #define RAWPHYS_B200_H

@@ -52,6 +52,18 @@ def build(force=False, verbose=False, out=None, defines=()):
     return out or OUT
 
 
+# The reference's compile-time switch USE_QUATERNIONS_LINEARIZED_FORMULAS (pbd.cpp:16, pbd_base_constraints.cpp:4) is a compile-time
+# switch here too: -DRP_EXACT_QUATERNIONS builds the non-linearised orientation updates (axis-angle through libm sin / cos) into a
+# second library with the same C ABI. Load it with RAWPHYS_B200_LIB=.../librawphys_b200_exactq.so or link against it.
+EXACTQ_OUT = os.path.join(HERE, "librawphys_b200_exactq.so")
+
+
+def build_exactq(force=False):
+    if not force and os.path.exists(EXACTQ_OUT) and all(os.path.getmtime(f) <= os.path.getmtime(EXACTQ_OUT) for f in SOURCES + HEADERS + [os.path.abspath(__file__)]):
+        return EXACTQ_OUT
+    return build(out=EXACTQ_OUT, defines=("RP_EXACT_QUATERNIONS",))
+
+
 HOST_SRC = os.path.join(HERE, "host", "rp_headless.cpp")
 HOST_OUT = os.path.join(HERE, "rp_headless")
 
@@ -71,5 +83,6 @@ def build_host(force=False):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    build_exactq(force="--force" in sys.argv)
     build_host(force="--force" in sys.argv)

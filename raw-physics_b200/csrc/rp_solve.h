@@ -67,6 +67,12 @@ RP_HD void integrate(Body& b, double h, V3 force, V3 torque) {
 	M3 iinv = world_tensor(b.q, b.inv_inertia);
 	M3 iw = world_tensor(b.q, b.inertia);
 	b.w = add(b.w, scale(h, mul(iinv, sub(torque, cross(b.w, mul(iw, b.w))))));
+#if defined(RP_EXACT_QUATERNIONS)
+	// the reference built without USE_QUATERNIONS_LINEARIZED_FORMULAS (pbd.cpp:16, :570-575): rotation by |w| h about w
+	const double angle = length(b.w) * h;
+	const Q4 change = quat_axis_angle(normalize(b.w), angle);
+	b.q = normalize(mul(change, b.q));
+#else
 	Q4 aux = q4(b.w.x, b.w.y, b.w.z, 0.0);
 	Q4 dq = mul(aux, b.q);
 	b.q.x = b.q.x + h * 0.5 * dq.x;
@@ -74,6 +80,7 @@ RP_HD void integrate(Body& b, double h, V3 force, V3 torque) {
 	b.q.z = b.q.z + h * 0.5 * dq.z;
 	b.q.w = b.q.w + h * 0.5 * dq.w;
 	b.q = normalize(b.q);
+#endif
 }
 
 // pbd.cpp:623-643 for one body
@@ -137,6 +144,13 @@ RP_HD double pos_delta_lambda(const PosPre& p, const Body& b1, const Body& b2, d
 
 // quaternion update shared by both apply routines (pbd_base_constraints.cpp:87-103, :189-207): q +/- 0.5 * ((aux,0) (x) q)
 RP_HD void apply_rotation(Body& b, V3 aux, double sign_half) {
+#if defined(RP_EXACT_QUATERNIONS)
+	// the non-linearised branch (pbd_base_constraints.cpp:105-121, :209-225): rotation by +-|aux| about aux
+	const double angle = sign_half > 0.0 ? length(aux) : -length(aux);
+	const Q4 change = quat_axis_angle(normalize(aux), angle);
+	b.q = normalize(mul(change, b.q));
+	return;
+#endif
 	Q4 d = mul(q4(aux.x, aux.y, aux.z, 0.0), b.q);
 	if (sign_half > 0.0) {
 		b.q.x = b.q.x + 0.5 * d.x; b.q.y = b.q.y + 0.5 * d.y; b.q.z = b.q.z + 0.5 * d.z; b.q.w = b.q.w + 0.5 * d.w;

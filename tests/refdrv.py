@@ -26,6 +26,11 @@ def _u(a):
 def lib_path(flavour="strict"):
     if flavour == "port":
         return os.path.join(ROOT, "oracle", "libport_oracle.so")
+    # the reference / the restatement built WITHOUT USE_QUATERNIONS_LINEARIZED_FORMULAS (oracle/Makefile ref_exactq, port_exactq)
+    if flavour == "port_exactq":
+        return os.path.join(ROOT, "oracle", "libport_oracle_exactq.so")
+    if flavour == "strict_exactq":
+        return os.path.join(ROOT, "oracle", "_ref", "libref_oracle_exactq.so")
     # "shim": the reference's own object code for everything except the frame step, whose two entry points are
     # redirected to raw-physics_b200/shim/pbd_b200.cpp -> librawphys_b200.so (oracle/Makefile `shim`); needs a GPU to step
     name = {"strict": "libref_oracle.so", "shim": "libref_shim.so"}.get(flavour, "libref_oracle_fastmath.so")
@@ -54,7 +59,7 @@ class RefWorld:
 
     def __init__(self, flavour="strict"):
         self.flavour = flavour
-        self.lib = _Prefixed(C.CDLL(lib_path(flavour)), "port" if flavour == "port" else "ref")
+        self.lib = _Prefixed(C.CDLL(lib_path(flavour)), "port" if flavour.startswith("port") else "ref")
         L = self.lib
         L.ref_entity_create.restype = C.c_uint64
         L.ref_entity_create.argtypes = [_dp, _dp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double]
