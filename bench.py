@@ -77,6 +77,9 @@ def parse():
     ap.add_argument("--workload", default="w256", choices=sorted(WORKLOADS))
     ap.add_argument("--worlds", type=int, default=0, help="worlds per GPU (weak) / in total (strong); default: the workload's")
     ap.add_argument("--scaling", default="", choices=["", "weak", "strong"])
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
+                    help="f64: the product (the reference's arithmetic, bit for bit). f32: the single-precision fast-mode build of the same "
+                         "sources (librawphys_b200_f32.so): a separate, clearly labelled line, never the headline -- accepted on physical criteria")
     ap.add_argument("--no-cull", action="store_true", help="run GJK on every broadphase pair (disables the exact-safe bounds cull)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / profile / cpu baseline (kernel timing only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (tuning runs)")
@@ -291,7 +294,7 @@ def hetero_state(init, W, NB, stride, rank):
     return st
 
 
-def check_parity(wl, batch, frame, job, total_worlds, coloured):
+def check_parity(wl, batch, frame, job, total_worlds, coloured, precision="f64"):
     """The state after `frame` frames from the initial poses: world 0 against the compiled reference's committed output for that
     frame, every world of this rank against world 0, and one digest per world gathered over the process group (all equal:
     a G-GPU run is the 1-GPU run, world for world). Returns the `parity` block."""
@@ -300,7 +303,21 @@ def check_parity(wl, batch, frame, job, total_worlds, coloured):
     same = bool((st == st[0][None]).all())
     out = {"checked": False, "frame": frame, "worlds_identical_on_rank": same}
     gold_path = os.path.join(ROOT, "tests", "golden", fname) if fname else ""
-    if fname and os.path.exists(gold_path) and not coloured:
+    if precision == "f32" and not coloured:
+        # single precision: the reference's trajectory is out of reach by construction (its contacts are knife-edge sensitive to
+        # rounding, SURVEY.md TL;DR 3). Accepted on physical criteria; the distance to the reference's state is reported, not judged.
+        out["note"] = "single-precision fast mode: accepted on physical criteria, distance to the FP64 reference reported only"
+        out["finite"] = bool(np.isfinite(st).all())
+        out["max_speed"] = float(np.sqrt((st[0, :, 7:10] ** 2).sum(axis=1)).max())
+        out["lowest_body_centre_y"] = float(st[0, 1:, 1].min()) if st.shape[1] > 1 else None
+        if fname and os.path.exists(gold_path):
+            z = np.load(gold_path)
+            if key % frame in z.files:
+                out["max_abs_pose_diff_vs_reference"] = float(np.abs(st[0, :, :7] - z[key % frame][:, :7]).max())
+                out["golden"] = "tests/golden/%s:%s" % (fname, key % frame)
+        out["checked"] = True
+        out["world0_matches_reference"] = bool(out["finite"] and out["max_speed"] < 60.0)
+    elif fname and os.path.exists(gold_path) and not coloured:
         z = np.load(gold_path)
         if key % frame in z.files:
             want = z[key % frame]
@@ -420,7 +437,7 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": args.steps * batch.graph_kernels(), "status_bits": int(np.bitwise_or.reduce(status))}
     parity_done = False
     if lead_in(wl, args.steps) + args.steps == wl["window"]:
-        line["parity"] = check_parity(wl, batch, wl["window"], job, total_worlds, coloured)
+        line["parity"] = check_parity(wl, batch, wl["window"], job, total_worlds, coloured, args.precision)
         parity_done = True
 
     # ---- the whole window (frames 0..window-1), always: what a K < window run times is its heavy end
@@ -434,8 +451,11 @@ def run_ours(args):
         line["window"] = {"frames": wl["window"], "value": NB * total_worlds * SUB * wl["window"] / (wms * 1e-3), "ms_per_step": wms / wl["window"],
                           "note": "frames 0..%d from the initial poses, device-timed like `value`" % (wl["window"] - 1)}
         if not parity_done:
-            line["parity"] = check_parity(wl, batch, wl["window"], job, total_worlds, coloured)
+            line["parity"] = check_parity(wl, batch, wl["window"], job, total_worlds, coloured, args.precision)
     line["parity_checked"] = bool(line["parity"].get("checked")) and bool(line["parity"].get("ok"))
+    if args.precision == "f32":
+        line["dtype"] = "f32"
+        line["precision_note"] = "fast mode: same kernels compiled with real = float; NOT the headline (BASELINE's metric is quoted in the reference's FP64 arithmetic)"
 
     if args.workload == "c3":
         # the same scene in the reference's own constraint order (bit-exact, deep dependency chains), for the record
@@ -553,6 +573,11 @@ def run_ours(args):
                             "note": "schema bound; this kernel is latency-bound on dependent FP64 chains, the binding pipe is FP64: see fp64"}
         tf = alg_flops[top] / (fam[top] * 1e-3) / 1e12
         whole = FLOP_PER_BODY_SUBSTEP * (NB * W * SUB * args.steps) / (ms * 1e-3) / 1e12
+        if args.precision == "f32":
+            # nominal FP32 CUDA-core rate without FMA credit: 148 SMs x 128 lanes x the sampled SM clock (no measured figure in MEASURED_PEAKS.json)
+            fp32_nofma = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12
+            line["fp32"] = {"kernel": "k_" + top, "achieved_tflops": tf, "peak_tflops_no_fma": fp32_nofma, "frac_of_no_fma_peak": tf / fp32_nofma,
+                            "whole_step_tflops": whole, "whole_step_frac": whole / fp32_nofma, "peak_source": "nominal: 148 SMs x 128 FP32 lanes x SM clock, FMA not counted"}
         line["fp64"] = {"kernel": "k_" + top, "achieved_tflops": tf, "peak_tflops_no_fma": fp64_nofma, "peak_tflops_fma": fp64_fma,
                         "frac_of_no_fma_peak": tf / fp64_nofma, "whole_step_tflops": whole, "whole_step_frac": whole / fp64_nofma,
                         "peak_source": "rp_measure_fp64_peak (DMUL+DADD chains, this run)"}
@@ -606,6 +631,8 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
+        if args.precision == "f32":  # the package binds one library per process: chosen before it is loaded
+            os.environ["RAWPHYS_B200_LIB"] = os.environ.get("RP_F32_LIB") or os.path.join(ROOT, "raw-physics_b200", "librawphys_b200_f32.so")  # (RP_F32_LIB: tuning variants)
         run_ours(args)
 
 

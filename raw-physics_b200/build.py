@@ -64,6 +64,17 @@ def build_exactq(force=False):
     return build(out=EXACTQ_OUT, defines=("RP_EXACT_QUATERNIONS",))
 
 
+# Single-precision "fast mode" (SURVEY.md 7 hard part 1, 8d): the same sources with `real` = float (rp_math.h). Same C ABI (host
+# records stay double, converted at upload / download); results are NOT comparable with the reference beyond float accuracy.
+F32_OUT = os.path.join(HERE, "librawphys_b200_f32.so")
+
+
+def build_f32(force=False):
+    if not force and os.path.exists(F32_OUT) and all(os.path.getmtime(f) <= os.path.getmtime(F32_OUT) for f in SOURCES + HEADERS + [os.path.abspath(__file__)]):
+        return F32_OUT
+    return build(out=F32_OUT, defines=("RP_REAL_F32",))
+
+
 HOST_SRC = os.path.join(HERE, "host", "rp_headless.cpp")
 HOST_OUT = os.path.join(HERE, "rp_headless")
 
@@ -85,4 +96,5 @@ def build_host(force=False):
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     build_exactq(force="--force" in sys.argv)
+    build_f32(force="--force" in sys.argv)
     build_host(force="--force" in sys.argv)

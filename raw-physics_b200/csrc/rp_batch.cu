@@ -230,8 +230,8 @@ int rp_scene_collider_hull_topology(rp_scene* s, const double* verts, uint32_t n
 	HullHost h;
 	h.verts.resize(nv);
 	h.normals.resize(nf);
-	memcpy(h.verts.data(), verts, sizeof(V3) * nv);
-	memcpy(h.normals.data(), normals, sizeof(V3) * nf);
+	for (uint32_t i = 0; i < nv; ++i) h.verts[i] = v3((real)verts[3 * i], (real)verts[3 * i + 1], (real)verts[3 * i + 2]);
+	for (uint32_t i = 0; i < nf; ++i) h.normals[i] = v3((real)normals[3 * i], (real)normals[3 * i + 1], (real)normals[3 * i + 2]);
 	csr_copy(face_ptr, face_idx, nf, h.face_ptr, h.face_idx);
 	csr_copy(v2f_ptr, v2f_idx, nv, h.v2f_ptr, h.v2f_idx);
 	csr_copy(v2n_ptr, v2n_idx, nv, h.v2n_ptr, h.v2n_idx);
@@ -347,8 +347,12 @@ int rp_scene_hull_dump(const rp_scene* s, int body, int collider, double* verts,
 	bool sphere;
 	const HullHost* h = find_hull(s, body, collider, &sphere);
 	if (!h || !verts || !normals || !face_ptr || !face_idx || !v2f_ptr || !v2f_idx || !v2n_ptr || !v2n_idx || !f2n_ptr || !f2n_idx) return RP_ERR_ARG;
-	memcpy(verts, h->verts.data(), sizeof(V3) * h->verts.size());
-	memcpy(normals, h->normals.data(), sizeof(V3) * h->normals.size());
+	for (size_t i = 0; i < h->verts.size(); ++i) {
+		verts[3 * i] = h->verts[i].x; verts[3 * i + 1] = h->verts[i].y; verts[3 * i + 2] = h->verts[i].z;
+	}
+	for (size_t i = 0; i < h->normals.size(); ++i) {
+		normals[3 * i] = h->normals[i].x; normals[3 * i + 1] = h->normals[i].y; normals[3 * i + 2] = h->normals[i].z;
+	}
 	copy_u32(h->face_ptr, face_ptr); copy_u32(h->face_idx, face_idx);
 	copy_u32(h->v2f_ptr, v2f_ptr); copy_u32(h->v2f_idx, v2f_idx);
 	copy_u32(h->v2n_ptr, v2n_ptr); copy_u32(h->v2n_idx, v2n_idx);
@@ -1046,11 +1050,11 @@ static void enqueue_prologue(rp_batch* b, double dt, int collisions) {
 // (WarpQueue): launch exactly the CTAs that are resident at once (occupancy measured at batch creation).
 static void launch_solve_pos(rp_batch* b, double h, uint32_t iters, int collisions) {
 	if (iters == 0) return;
-	if (b->d.NJ > 0) launch_cooperative(k_solve_pos<true>, b->pos_grid, (unsigned int)RP_POS_THREADS, b->live_smem, b->stream, b->d, h, (int)iters, collisions, b->live_lists);
-	else launch_cooperative(k_solve_pos<false>, b->pos_grid, (unsigned int)RP_POS_THREADS, b->live_smem, b->stream, b->d, h, (int)iters, collisions, b->live_lists);
+	if (b->d.NJ > 0) launch_cooperative(k_solve_pos<true>, b->pos_grid, (unsigned int)RP_POS_THREADS, b->live_smem, b->stream, b->d, (real)h, (int)iters, collisions, b->live_lists);
+	else launch_cooperative(k_solve_pos<false>, b->pos_grid, (unsigned int)RP_POS_THREADS, b->live_smem, b->stream, b->d, (real)h, (int)iters, collisions, b->live_lists);
 }
 static void launch_solve_vel(rp_batch* b, double h, uint32_t iters) {
-	launch_cooperative(k_solve_vel, b->vel_grid, (unsigned int)RP_VEL_THREADS, b->live_smem, b->stream, b->d, h, b->live_lists, (int)iters);
+	launch_cooperative(k_solve_vel, b->vel_grid, (unsigned int)RP_VEL_THREADS, b->live_smem, b->stream, b->d, (real)h, b->live_lists, (int)iters);
 }
 
 static void enqueue_integrate(rp_batch* b, double h, bool last_substep) {

@@ -20,15 +20,15 @@ namespace rp {
 // tensors and coefficients share one record (W256: 2 classes for 257 bodies), so the lanes of a warp that work on
 // different bodies of the same class read the SAME addresses (one broadcast wavefront instead of 32 scattered ones).
 struct BodyClass {
-	double inv_mass;
+	real inv_mass;
 	M3 inertia, inv_inertia;
-	double mu_s, mu_d, rest;
-	double ii_bound;   // tensor_bound(inv_inertia), see solve_contact
+	real mu_s, mu_d, rest;
+	real ii_bound;   // tensor_bound(inv_inertia), see solve_contact
 };
 // per-body static parameters, shared by all worlds (template)
 struct BodyStatic {
-	double radius;
-	double rfar;              // (radius + 0.1) * (1 + 1e-9): this body's share of the broadphase's axis-reject threshold
+	real radius;
+	real rfar;              // (radius + 0.1) * (1 + 1e-9): this body's share of the broadphase's axis-reject threshold
 	int cls;                  // index into DevView::bclass
 	int fixed, col0, ncol;
 	int tv0, tvn, tn0, tnn;   // extent of the body's colliders in a world's transformed vertex / normal arrays
@@ -44,7 +44,7 @@ struct __align__(16) SolveItem {  // one unit of a sweep: a collider pair's mani
 };
 struct EpaOut {  // result of EPA (or the analytic sphere-sphere test) for one hit: work item of k_manifold
 	V3 normal;
-	double depth;
+	real depth;
 	int ok, pad;
 	int sup_a, sup_b;  // support vertices of the two hulls along +normal / -normal (EPA's last support call), -1 when unknown
 };
@@ -55,7 +55,7 @@ struct DevView {
 	int W, NB, NC, NJ, TV, TN;
 	int WS;              // world stride of every world-minor array: W rounded up to a multiple of 32 (W itself when W < 32)
 	int max_pairs, max_contacts, max_units;
-	double lin_sleep, ang_sleep, sleep_time;
+	real lin_sleep, ang_sleep, sleep_time;
 	// template
 	const BodyStatic* bstat;
 	const BodyClass* bclass;
@@ -65,13 +65,13 @@ struct DevView {
 	const V3* force;
 	const V3* torque;
 	// per world, world-minor ([...][WS]) unless noted
-	double* dyn;         // [NB][RP_DYN_DOUBLES][WS]
+	real* dyn;         // [NB][RP_DYN_DOUBLES][WS]
 	int* active;         // [NB][WS]
 	int* vstamp;         // [NB][WS] substep counter value at which the body's velocities were last derived (lazy k_derive)
 	int* epoch;          // [1] substep counter, +1 per substep (k_substep_reset)
-	double* deact;       // [NB][WS]
-	double* tv;          // [TV][3][WS] transformed vertices (sphere: centre)
-	double* tn;          // [TN][3][WS] transformed face normals
+	real* deact;       // [NB][WS]
+	real* tv;          // [TV][3][WS] transformed vertices (sphere: centre)
+	real* tn;          // [TN][3][WS] transformed face normals
 	PairRec* pairs;      // [max_pairs][WS]
 	int* n_pairs;        // [W]
 	int n_cells;         // broadphase cells: (row i, 32 consecutive j) pieces of the i < j triangle, in (i, j) order
@@ -94,7 +94,7 @@ struct DevView {
 	int split_big;             // the scene has such pairs: k_epa leaves them to k_epa_warp, k_manifold takes their supports from big_sup
 	int2* big_sup;             // [W * max_pairs] per hit of a large pair: support vertices of the two hulls along +-normal (k_epa_warp)
 	uint4* hits;         // [W * max_pairs] the colliding candidates' records, dense (one load tells EPA / clipping where their inputs are)
-	double* simplex;     // [12][W * max_pairs] final GJK tetrahedron of each hit, as component planes (st_simplex)
+	real* simplex;     // [12][W * max_pairs] final GJK tetrahedron of each hit, as component planes (st_simplex)
 	unsigned int* hit_count;
 	EpaOut* epa_out;     // [W * max_pairs] per hit
 	// level-major work lists shared by all worlds: the pairs of dependency level l that have contacts this substep
@@ -126,7 +126,7 @@ struct DevView {
 	V3* pair_normal;     // [max_pairs][WS]
 	int* pair_coff;      // [max_pairs][WS]
 	int* pair_ccnt;      // [max_pairs][WS]
-	double* contacts;    // [max_contacts][8][WS] contact records (r1_lc, r2_lc, lambda_n, lambda_t), see contact_ptr
+	real* contacts;    // [max_contacts][8][WS] contact records (r1_lc, r2_lc, lambda_n, lambda_t), see contact_ptr
 	int* n_contacts;     // [W]
 	JointLambda* lambdas;  // [NJ][WS]
 	int* status;         // [W]

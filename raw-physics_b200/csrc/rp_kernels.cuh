@@ -76,7 +76,7 @@ namespace rp {
 enum { DF_X = 0, DF_Q = 3, DF_V = 7, DF_W = 10, DF_PX = 13, DF_PQ = 16, DF_PV = 20, DF_PW = 23 };  // fields of a body's dynamic record
 
 struct DynRef {  // one body's dynamic record: field component f at p[f * s]
-	double* p;
+	real* p;
 	size_t s;
 };
 __device__ __forceinline__ DynRef dyn_ref(const DevView& d, int w, int b) {
@@ -92,8 +92,8 @@ __device__ __forceinline__ void st4(const DynRef& r, int f, Q4 q) {
 	r.p[f * r.s] = q.x; r.p[(f + 1) * r.s] = q.y; r.p[(f + 2) * r.s] = q.z; r.p[(f + 3) * r.s] = q.w;
 }
 // contact record (r1_lc, r2_lc, lambda_n, lambda_t) of slot k of a world: component f at p[(k * 8 + f) * WS]
-__device__ __forceinline__ double* contact_ptr(const DevView& d, int w, int slot) { return d.contacts + (size_t)slot * 8 * d.WS + w; }
-__device__ __forceinline__ Contact ld_contact(const double* p, size_t S) {
+__device__ __forceinline__ real* contact_ptr(const DevView& d, int w, int slot) { return d.contacts + (size_t)slot * 8 * d.WS + w; }
+__device__ __forceinline__ Contact ld_contact(const real* p, size_t S) {
 	Contact c;
 	c.r1_lc = v3(p[0], p[S], p[2 * S]);
 	c.r2_lc = v3(p[3 * S], p[4 * S], p[5 * S]);
@@ -101,7 +101,7 @@ __device__ __forceinline__ Contact ld_contact(const double* p, size_t S) {
 	c.lambda_t = p[7 * S];
 	return c;
 }
-__device__ __forceinline__ void st_contact(double* p, size_t S, const Contact& c) {
+__device__ __forceinline__ void st_contact(real* p, size_t S, const Contact& c) {
 	p[0] = c.r1_lc.x; p[S] = c.r1_lc.y; p[2 * S] = c.r1_lc.z;
 	p[3 * S] = c.r2_lc.x; p[4 * S] = c.r2_lc.y; p[5 * S] = c.r2_lc.z;
 	p[6 * S] = c.lambda_n; p[7 * S] = c.lambda_t;
@@ -163,11 +163,11 @@ __device__ __forceinline__ PoseShape dev_pose_shape(const DevView& d, const Coll
 		s.nv = 0; s.nf = 0;
 		s.face_ptr = s.face_idx = s.v2f_ptr = s.v2f_idx = s.v2n_ptr = s.v2n_idx = s.f2n_ptr = s.f2n_idx = 0;
 		s.lv = s.ln = 0;
-		s.M = model_matrix(q4(0.0, 0.0, 0.0, 1.0), x);
+		s.M = model_matrix(q4(RL(0.0), RL(0.0), RL(0.0), RL(1.0)), x);
 	} else {
 		const HullTopo h = d.pool.hulls[c.hull];
 		s.M = model_matrix(ld4(r, DF_Q), x);
-		s.center = v3(0.0, 0.0, 0.0);
+		s.center = v3(RL(0.0), RL(0.0), RL(0.0));
 		s.nv = h.nv; s.nf = h.nf;
 		s.lv = d.pool.verts + h.vert0;
 		s.ln = d.pool.normals + h.face0;
@@ -196,23 +196,23 @@ __global__ void __launch_bounds__(256) k_broad_cells(DevView d) {
 	const int2 cell = d.cells[c];
 	const int i = cell.x, j0 = cell.y;
 	const int j1 = j0 + 32 < d.NB ? j0 + 32 : d.NB;
-	const double* X = d.dyn + w;  // x of body j: X[(j * RP_DYN_DOUBLES + c) * WS]
+	const real* X = d.dyn + w;  // x of body j: X[(j * RP_DYN_DOUBLES + c) * WS]
 	const size_t S = d.WS;
 	const size_t body_stride = (size_t)RP_DYN_DOUBLES * S;
 	const V3 xi = v3(X[(size_t)i * body_stride], X[(size_t)i * body_stride + S], X[(size_t)i * body_stride + 2 * S]);
-	const double ri = d.bstat[i].radius;
+	const real ri = d.bstat[i].radius;
 	const int nci = d.bstat[i].ncol;
 	// Axis rejects first: |x_i - x_j| along one axis already above (r_i + r_j + 0.1)(1 + 1e-9) puts the distance the
 	// reference computes (sqrt of a sum of rounded squares, each term within 3 ulp) above r_i + r_j + 0.1 as well, so the
 	// pair is not emitted -- decided after one load and three FP64 instructions instead of fifteen. The threshold is the
 	// sum of two per-body terms prepared once (BodyStatic::rfar), both rounded up by 1e-9 >> the 1e-16 roundings involved.
 	// Survivors get the reference's own expression below.
-	const double ri_far = ri * (1.0 + 1e-9);
+	const real ri_far = ri * (RL(1.0) + RL(1e-9));
 	unsigned int mask = 0u;
 	int count = 0;
 	// the x coordinates of RP_BROAD_BATCH bodies are fetched together (independent loads in flight), then looked at in order
 	for (int jb = j0; jb < j1; jb += RP_BROAD_BATCH) {
-		double xs[RP_BROAD_BATCH], thrs[RP_BROAD_BATCH];
+		real xs[RP_BROAD_BATCH], thrs[RP_BROAD_BATCH];
 #pragma unroll
 		for (int k = 0; k < RP_BROAD_BATCH; ++k) {
 			const int jj = jb + k < j1 ? jb + k : j1 - 1;
@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(256) k_broad_cells(DevView d) {
 		for (int k = 0; k < RP_BROAD_BATCH; ++k) {
 			const int j = jb + k;
 			if (j >= j1) break;
-			const double thr = thrs[k];
-			const double* xj = X + (size_t)j * body_stride;
+			const real thr = thrs[k];
+			const real* xj = X + (size_t)j * body_stride;
 			V3 dv;
 			dv.x = xi.x - xs[k];
 			if (fabs(dv.x) > thr) continue;
@@ -235,11 +235,11 @@ __global__ void __launch_bounds__(256) k_broad_cells(DevView d) {
 			// broad.cpp:19-20 compares sqrt(|xi - xj|^2) with ri + rj + 0.1. Squared distances outside a 4e-12 relative
 			// band around maxd^2 decide the comparison without the square root (sqrt is monotonic and both roundings are
 			// 1e-16 effects); inside the band the reference's expression is evaluated as written.
-			const double d2 = dv.x * dv.x + dv.y * dv.y + dv.z * dv.z;
-			const double maxd = ri + d.bstat[j].radius + 0.1;
-			const double m2 = maxd * maxd;
-			bool near = d2 < m2 * (1.0 - 4e-12);
-			if (!near && !(d2 > m2 * (1.0 + 4e-12))) near = sqrt(d2) <= maxd;
+			const real d2 = dv.x * dv.x + dv.y * dv.y + dv.z * dv.z;
+			const real maxd = ri + d.bstat[j].radius + RL(0.1);
+			const real m2 = maxd * maxd;
+			bool near = d2 < m2 * (RL(1.0) - RL(4e-12));
+			if (!near && !(d2 > m2 * (RL(1.0) + RL(4e-12)))) near = sqrt(d2) <= maxd;
 			if (near) {
 				mask |= 1u << (j - j0);
 				count += nci * d.bstat[j].ncol;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) k_broad_write(DevView d) {
 // connected components of {pairs, external constraints} restricted to non-fixed bodies; the result does not depend on
 // the order in which unions happen, so min-label propagation replaces the reference's union-find. One CTA per world
 // (labels and flags are [W][NB] scratch; the strided reads of the world-minor arrays are once per frame).
-__global__ void __launch_bounds__(256) k_islands(DevView d, double dt) {
+__global__ void __launch_bounds__(256) k_islands(DevView d, real dt) {
 	const int w = blockIdx.x;
 	int* label = d.label + (size_t)w * d.NB;
 	int* flag = d.isl_flag + (size_t)w * d.NB;
@@ -371,11 +371,11 @@ __global__ void __launch_bounds__(256) k_islands(DevView d, double dt) {
 	for (int b = threadIdx.x; b < d.NB; b += blockDim.x) {
 		if (d.bstat[b].fixed) continue;
 		const DynRef r = dyn_ref(d, w, b);
-		double lv = length(ld3(r, DF_V));
-		double av = length(ld3(r, DF_W));
-		double t = d.deact[bidx(d, b, w)];
+		real lv = length(ld3(r, DF_V));
+		real av = length(ld3(r, DF_W));
+		real t = d.deact[bidx(d, b, w)];
 		if (lv < d.lin_sleep && av < d.ang_sleep) t += dt;
-		else t = 0.0;
+		else t = RL(0.0);
 		d.deact[bidx(d, b, w)] = t;
 		if (t < d.sleep_time) flag[label[b]] = 0;
 	}
@@ -587,22 +587,30 @@ __global__ void __launch_bounds__(256) k_substep_reset(DevView d) {
 }
 
 #define RP_INT_THREADS 128
+// float bounds rounded outwards from the arithmetic type (in single precision the value is a float already)
+#if defined(RP_REAL_F32)
+__device__ __forceinline__ float bound_down(real x) { return x; }
+__device__ __forceinline__ float bound_up(real x) { return x; }
+#else
+__device__ __forceinline__ float bound_down(real x) { return __double2float_rd(x); }
+__device__ __forceinline__ float bound_up(real x) { return __double2float_ru(x); }
+#endif
 // world-space bounds of one collider from its body's pose (collider_update's bounds, see k_integrate / k_bounds)
 __device__ __forceinline__ void collider_bounds(const DevView& d, const ColliderDesc& cd, const Pose34& M, V3 x, float* bb, size_t S) {
 	if (cd.type == SHAPE_SPHERE) {
-		const double rad = (double)cd.radius;
-		bb[0] = __double2float_rd(x.x - rad); bb[S] = __double2float_rd(x.y - rad); bb[2 * S] = __double2float_rd(x.z - rad);
-		bb[3 * S] = __double2float_ru(x.x + rad); bb[4 * S] = __double2float_ru(x.y + rad); bb[5 * S] = __double2float_ru(x.z + rad);
+		const real rad = (real)cd.radius;
+		bb[0] = bound_down(x.x - rad); bb[S] = bound_down(x.y - rad); bb[2 * S] = bound_down(x.z - rad);
+		bb[3 * S] = bound_up(x.x + rad); bb[4 * S] = bound_up(x.y + rad); bb[5 * S] = bound_up(x.z + rad);
 	} else {
 		const HullTopo t = d.pool.hulls[cd.hull];
-		double lo0 = 1.7976931348623157e308, lo1 = lo0, lo2 = lo0, hi0 = -lo0, hi1 = -lo0, hi2 = -lo0;
+		real lo0 = RL(RP_REAL_MAX), lo1 = lo0, lo2 = lo0, hi0 = -lo0, hi1 = -lo0, hi2 = -lo0;
 		for (int k = 0; k < t.nv; ++k) {
 			const V3 p = transform_point(M, d.pool.verts[t.vert0 + k]);
 			lo0 = fmin(lo0, p.x); lo1 = fmin(lo1, p.y); lo2 = fmin(lo2, p.z);
 			hi0 = fmax(hi0, p.x); hi1 = fmax(hi1, p.y); hi2 = fmax(hi2, p.z);
 		}
-		bb[0] = __double2float_rd(lo0); bb[S] = __double2float_rd(lo1); bb[2 * S] = __double2float_rd(lo2);
-		bb[3 * S] = __double2float_ru(hi0); bb[4 * S] = __double2float_ru(hi1); bb[5 * S] = __double2float_ru(hi2);
+		bb[0] = bound_down(lo0); bb[S] = bound_down(lo1); bb[2 * S] = bound_down(lo2);
+		bb[3 * S] = bound_up(hi0); bb[4 * S] = bound_up(hi1); bb[5 * S] = bound_up(hi2);
 	}
 }
 // pbd.cpp:537-577 (integration) and collider.cpp:409-445 (collider_update) for one body per thread. The reference
@@ -610,7 +618,7 @@ __device__ __forceinline__ void collider_bounds(const DevView& d, const Collider
 // so once per body per substep is exactly equivalent. Also leaves each collider's world-space bounds
 // for k_cull. Grid = (bodies, world blocks): a CTA is ONE body in 128 consecutive worlds, so the statics and the hull
 // are the same for every lane and every load/store of the world-minor arrays is coalesced.
-__global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate(DevView d, double h, int store_velocities) {
+__global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate(DevView d, real h, int store_velocities) {
 	int w, b;
 	if (!flat_item_world(d, d.NB, &b, &w)) return;
 	const int epoch = *d.epoch;
@@ -618,7 +626,7 @@ __global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate
 	if (b < d.NJ) {  // copy_constraints resets every lambda each substep (pbd.cpp:426-462)
 		for (int j = b; j < d.NJ; j += d.NB) {
 			JointLambda z;
-			z.a = z.b = z.c = 0.0;
+			z.a = z.b = z.c = RL(0.0);
 			d.lambdas[(size_t)j * S + w] = z;
 		}
 	}
@@ -635,7 +643,7 @@ __global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate
 	// derivation would have left as previous velocities is not stored either: nothing reads it before this substep's
 	// derivation rewrites it.)
 	if (moving && d.vstamp[bidx(d, b, w)] != epoch - 1) {
-		body.v = body.w = v3(0.0, 0.0, 0.0);
+		body.v = body.w = v3(RL(0.0), RL(0.0), RL(0.0));
 		body.px = ld3(r, DF_PX); body.pq = ld4(r, DF_PQ);
 		derive_velocity(body, h);
 	} else {
@@ -691,7 +699,7 @@ __global__ void __launch_bounds__(RP_INT_THREADS) k_transform(DevView d) {
 	const Pose34 M = model_matrix(ld4(r, DF_Q), ld3(r, DF_X));
 	const int first = blockIdx.z, step = gridDim.z;
 	const HullTopo t = d.pool.hulls[cd.hull];
-	double* tn = d.tn + (size_t)cd.tn0 * 3 * S + w;
+	real* tn = d.tn + (size_t)cd.tn0 * 3 * S + w;
 	for (int k = first; k < t.nf; k += step) {
 		const V3 n = transform_normal(M, d.pool.normals[t.face0 + k]);
 		tn[(size_t)(3 * k) * S] = n.x; tn[(size_t)(3 * k + 1) * S] = n.y; tn[(size_t)(3 * k + 2) * S] = n.z;
@@ -703,7 +711,7 @@ __global__ void __launch_bounds__(RP_INT_THREADS) k_transform(DevView d) {
 // base[e * nthreads], so the 32 lanes of a warp touch 32 consecutive doubles per access whatever (world, body) each lane
 // holds. The narrowphase scans the same vertices many times (support mapping), and 16 vertices x 3 x 32 lanes of a warp
 // are 12 kB -- more than a warp's share of L1. Returns the number of doubles used.
-__device__ __forceinline__ int stage_shape(PoseShape& s, double* col, int nthreads) {
+__device__ __forceinline__ int stage_shape(PoseShape& s, real* col, int nthreads) {
 	// the vertices are evaluated from the pose (collider_update's expression, collider.cpp:414-422), not loaded
 	for (int k = 0; k < s.nv; ++k) {
 		const V3 p = vert(s, k);
@@ -717,13 +725,13 @@ __device__ __forceinline__ int stage_shape(PoseShape& s, double* col, int nthrea
 // consecutive hits, so every access is one coalesced request (as 4 x V3 records per hit the twelve loads of k_epa each touched
 // 32 different sectors: 9 % of its stall samples, ncu round 2)
 __device__ __forceinline__ void st_simplex(const DevView& d, unsigned int slot, const Simplex& s) {
-	double* o = d.simplex + slot;
+	real* o = d.simplex + slot;
 	const size_t S = d.cand_cap;
 	o[0] = s.a.x; o[S] = s.a.y; o[2 * S] = s.a.z; o[3 * S] = s.b.x; o[4 * S] = s.b.y; o[5 * S] = s.b.z;
 	o[6 * S] = s.c.x; o[7 * S] = s.c.y; o[8 * S] = s.c.z; o[9 * S] = s.d.x; o[10 * S] = s.d.y; o[11 * S] = s.d.z;
 }
 __device__ __forceinline__ Simplex ld_simplex(const DevView& d, unsigned int slot) {
-	const double* o = d.simplex + slot;
+	const real* o = d.simplex + slot;
 	const size_t S = d.cand_cap;
 	Simplex s;
 	s.a = v3(o[0], o[S], o[2 * S]); s.b = v3(o[3 * S], o[4 * S], o[5 * S]);
@@ -750,7 +758,11 @@ __device__ __forceinline__ unsigned int warp_append(unsigned int* counter, bool 
 // are separated by more than RP_CULL_MARGIN along an axis, every Minkowski-difference support point has that coordinate
 // strictly positive (or strictly negative), the origin is outside the difference, and gjk_collides returns false: the
 // pair yields no contacts, exactly as if GJK had run. Survivors go to the dense candidate list of k_gjk.
+#if defined(RP_REAL_F32)
+#define RP_CULL_MARGIN 1e-5f  // (single precision: the bounds and the vertices GJK sees carry float rounding)
+#else
 #define RP_CULL_MARGIN 1e-7
+#endif
 #ifndef RP_CULL_ILP
 #define RP_CULL_ILP 1
 #endif
@@ -791,7 +803,7 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 			pr[u] = d.pairs[pidx(d, in[u] ? p : 0, w0)];
 		}
 		int fa[RP_CULL_ILP], fb[RP_CULL_ILP], aa[RP_CULL_ILP], ab[RP_CULL_ILP], ta[RP_CULL_ILP], tb[RP_CULL_ILP];
-		double lo_a[RP_CULL_ILP], hi_a[RP_CULL_ILP], lo_b[RP_CULL_ILP], hi_b[RP_CULL_ILP];
+		real lo_a[RP_CULL_ILP], hi_a[RP_CULL_ILP], lo_b[RP_CULL_ILP], hi_b[RP_CULL_ILP];
 #pragma unroll
 		for (int u = 0; u < RP_CULL_ILP; ++u) {
 			fa[u] = d.bstat[pr[u].a].fixed; fb[u] = d.bstat[pr[u].b].fixed;
@@ -814,8 +826,8 @@ __global__ void __launch_bounds__(256) k_cull(DevView d, int cull) {
 			if (__any_sync(0xffffffffu, bounds[u])) {
 				const float* pa = d.aabb + (size_t)pr[u].ca * 6 * S + w0;
 				const float* pb = d.aabb + (size_t)pr[u].cb * 6 * S + w0;
-				const double ax0 = pa[0], ax1 = pa[3 * S], az0 = pa[2 * S], az1 = pa[5 * S];
-				const double bx0 = pb[0], bx1 = pb[3 * S], bz0 = pb[2 * S], bz1 = pb[5 * S];
+				const real ax0 = pa[0], ax1 = pa[3 * S], az0 = pa[2 * S], az1 = pa[5 * S];
+				const real bx0 = pb[0], bx1 = pb[3 * S], bz0 = pb[2 * S], bz1 = pb[5 * S];
 				if (bounds[u] && (ax0 - bx1 > RP_CULL_MARGIN || bx0 - ax1 > RP_CULL_MARGIN || az0 - bz1 > RP_CULL_MARGIN ||
 					bz0 - az1 > RP_CULL_MARGIN)) keep[u] = false;
 			}
@@ -874,12 +886,12 @@ struct WarpQueue {
 __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) {
 	const unsigned int nc = *d.cand_count;
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&d.counters[CNT_CANDS], (unsigned long long)nc + *d.big_count);
-	__shared__ double s_stage[RP_GJK_STAGE * RP_GJK_THREADS];
+	__shared__ real s_stage[RP_GJK_STAGE * RP_GJK_THREADS];
 	for (unsigned int c0 = blockIdx.x * blockDim.x; c0 < nc; c0 += gridDim.x * blockDim.x) {
 		const unsigned int ci = c0 + threadIdx.x;
 		bool hit = false;
 		Simplex s;
-		s.a = s.b = s.c = s.d = v3(0.0, 0.0, 0.0);
+		s.a = s.b = s.c = s.d = v3(RL(0.0), RL(0.0), RL(0.0));
 		uint4 cd = make_uint4(0u, 0u, 0u, 0u);
 		if (ci < nc) {
 			cd = d.cands[ci];  // (world, pair, collider a, collider b): everything the narrowphase needs to find its inputs
@@ -889,11 +901,11 @@ __global__ void __launch_bounds__(RP_GJK_THREADS, RP_MINB_GJK) k_gjk(DevView d) 
 			int st = 0;
 			if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
 				V3 n;
-				double depth;
+				real depth;
 				hit = sphere_sphere(A, B, &n, &depth);
 			} else {
 				if ((A.nv + B.nv) * 3 <= RP_GJK_STAGE) {
-					double* col = s_stage + threadIdx.x;
+					real* col = s_stage + threadIdx.x;
 					const int used = stage_shape(A, col, RP_GJK_THREADS);
 					stage_shape(B, col + (size_t)used * RP_GJK_THREADS, RP_GJK_THREADS);
 					hit = gjk(StagedShape<RP_GJK_THREADS>(A), StagedShape<RP_GJK_THREADS>(B), &s, &st, 0);
@@ -930,9 +942,9 @@ __device__ __forceinline__ V3 vert(const WarpShape& s, int i) {
 __device__ __forceinline__ int support_index(const WarpShape& s, V3 d) {
 	const int lane = threadIdx.x & 31;
 	int best = 0x7fffffff;
-	double best_dot = -1.7976931348623157e308;
+	real best_dot = -RL(RP_REAL_MAX);
 	for (int i = lane; i < s.nv; i += 32) {
-		const double t = dot(vert(s, i), d);
+		const real t = dot(vert(s, i), d);
 		if (t > best_dot) {
 			best = i;
 			best_dot = t;
@@ -940,7 +952,7 @@ __device__ __forceinline__ int support_index(const WarpShape& s, V3 d) {
 	}
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) {
-		const double od = __shfl_xor_sync(0xffffffffu, best_dot, o);
+		const real od = __shfl_xor_sync(0xffffffffu, best_dot, o);
 		const int oi = __shfl_xor_sync(0xffffffffu, best, o);
 		if (od > best_dot || (od == best_dot && oi < best)) {
 			best_dot = od;
@@ -950,7 +962,7 @@ __device__ __forceinline__ int support_index(const WarpShape& s, V3 d) {
 	return best == 0x7fffffff ? 0 : best;
 }
 // evaluates a hull's transformed vertices into the warp's block of shared memory as component planes
-__device__ __forceinline__ void warp_stage(PoseShape& s, double* block) {
+__device__ __forceinline__ void warp_stage(PoseShape& s, real* block) {
 	if (s.type != SHAPE_HULL || s.nv > RP_WARP_HULL_MAX) return;  // spheres have no vertices; larger hulls are evaluated in place
 	const int lane = threadIdx.x & 31;
 	for (int k = lane; k < s.nv; k += 32) {
@@ -961,7 +973,7 @@ __device__ __forceinline__ void warp_stage(PoseShape& s, double* block) {
 }
 __global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_gjk_warp(DevView d) {
 	const unsigned int nb = *d.big_count;
-	__shared__ double s_hull[RP_GJK_WARP_THREADS / 32][2][3 * RP_WARP_HULL_MAX];
+	__shared__ real s_hull[RP_GJK_WARP_THREADS / 32][2][3 * RP_WARP_HULL_MAX];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const unsigned int warps = gridDim.x * (RP_GJK_WARP_THREADS / 32);
 	for (unsigned int k = blockIdx.x * (RP_GJK_WARP_THREADS / 32) + wib; k < nb; k += warps) {
@@ -997,17 +1009,17 @@ __global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_gjk_warp(DevView d) {
 template <int NT>
 struct EpaShared {
 	enum { MAXV = RP_EPA_SMALL_VERTS, MAXF = RP_EPA_SMALL_FACES, MAXE = RP_EPA_SMALL_EDGES, SOFT = 1 };
-	double* col;  // this thread's column of doubles: vertices [0, 3V), normals [3V, 3V + 3F), distances [3V + 3F, 3V + 4F)
+	real* col;  // this thread's column of doubles: vertices [0, 3V), normals [3V, 3V + 3F), distances [3V + 3F, 3V + 4F)
 	int* icol;    // this thread's column of ints: faces [0, F), edges [F, F + E)
 	int nverts, nfaces, nedges;
 	V3 min_normal;
-	double min_dist;
-	__device__ __forceinline__ V3 vert(int i) const { const double* p = col + (3 * i) * NT; return v3(p[0], p[NT], p[2 * NT]); }
-	__device__ __forceinline__ void set_vert(int i, V3 v) { double* p = col + (3 * i) * NT; p[0] = v.x; p[NT] = v.y; p[2 * NT] = v.z; }
-	__device__ __forceinline__ V3 normal(int i) const { const double* p = col + (3 * MAXV + 3 * i) * NT; return v3(p[0], p[NT], p[2 * NT]); }
-	__device__ __forceinline__ double dist(int i) const { return col[(3 * MAXV + 3 * MAXF + i) * NT]; }
-	__device__ __forceinline__ void set_plane(int i, V3 n, double d) {
-		double* p = col + (3 * MAXV + 3 * i) * NT;
+	real min_dist;
+	__device__ __forceinline__ V3 vert(int i) const { const real* p = col + (3 * i) * NT; return v3(p[0], p[NT], p[2 * NT]); }
+	__device__ __forceinline__ void set_vert(int i, V3 v) { real* p = col + (3 * i) * NT; p[0] = v.x; p[NT] = v.y; p[2 * NT] = v.z; }
+	__device__ __forceinline__ V3 normal(int i) const { const real* p = col + (3 * MAXV + 3 * i) * NT; return v3(p[0], p[NT], p[2 * NT]); }
+	__device__ __forceinline__ real dist(int i) const { return col[(3 * MAXV + 3 * MAXF + i) * NT]; }
+	__device__ __forceinline__ void set_plane(int i, V3 n, real d) {
+		real* p = col + (3 * MAXV + 3 * i) * NT;
 		p[0] = n.x; p[NT] = n.y; p[2 * NT] = n.z;
 		col[(3 * MAXV + 3 * MAXF + i) * NT] = d;
 	}
@@ -1029,7 +1041,7 @@ struct EpaShared {
 
 // second tier of k_epa: the full-capacity polytope in local memory, for the rare pair that outgrows the shared store.
 // Out of line so that its 11.8 kB frame and its registers stay out of the common path.
-__device__ __noinline__ int epa_full(const DevView& d, uint4 cd, const Simplex& s, V3* normal, double* depth, int* status, int* sup_a, int* sup_b) {
+__device__ __noinline__ int epa_full(const DevView& d, uint4 cd, const Simplex& s, V3* normal, real* depth, int* status, int* sup_a, int* sup_b) {
 	EpaScratch e;
 	const PoseShape A = dev_pose_shape(d, d.cols[cd.z], (int)cd.x);
 	const PoseShape B = dev_pose_shape(d, d.cols[cd.w], (int)cd.x);
@@ -1045,12 +1057,12 @@ __device__ __noinline__ int epa_full(const DevView& d, uint4 cd, const Simplex& 
 #ifndef RP_EPA_STAGE_HULLS
 #define RP_EPA_STAGE_HULLS 0
 #endif
-#define RP_EPA_SMEM_BYTES ((RP_EPA_POLY_DOUBLES * 8 + RP_EPA_POLY_INTS * 4 + (RP_EPA_STAGE_HULLS ? RP_GJK_STAGE * 8 : 0)) * RP_EPA_THREADS)
+#define RP_EPA_SMEM_BYTES ((RP_EPA_POLY_DOUBLES * (int)sizeof(real) + RP_EPA_POLY_INTS * 4 + (RP_EPA_STAGE_HULLS ? RP_GJK_STAGE * (int)sizeof(real) : 0)) * RP_EPA_THREADS)
 __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) {
 	const unsigned int nh = *d.hit_count;
 	extern __shared__ __align__(16) unsigned char s_epa_raw[];
-	double* s_poly = reinterpret_cast<double*>(s_epa_raw);
-	double* s_stage = s_poly + RP_EPA_POLY_DOUBLES * RP_EPA_THREADS;
+	real* s_poly = reinterpret_cast<real*>(s_epa_raw);
+	real* s_stage = s_poly + RP_EPA_POLY_DOUBLES * RP_EPA_THREADS;
 	int* s_idx = reinterpret_cast<int*>(s_stage + (RP_EPA_STAGE_HULLS ? RP_GJK_STAGE * RP_EPA_THREADS : 0));
 	EpaShared<RP_EPA_THREADS> e;
 	e.col = s_poly + threadIdx.x;
@@ -1062,7 +1074,7 @@ __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) 
 		PoseShape A = dev_pose_shape(d, d.cols[cd.z], w);
 		PoseShape B = dev_pose_shape(d, d.cols[cd.w], w);
 		EpaOut out;
-		out.ok = 0; out.pad = 0; out.depth = 0.0; out.normal = v3(0.0, 0.0, 0.0);
+		out.ok = 0; out.pad = 0; out.depth = RL(0.0); out.normal = v3(RL(0.0), RL(0.0), RL(0.0));
 		out.sup_a = out.sup_b = -1;
 		int st = 0;
 		if (A.type == SHAPE_SPHERE && B.type == SHAPE_SPHERE) {
@@ -1073,7 +1085,7 @@ __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) 
 #if RP_EPA_STAGE_HULLS
 			if ((A.nv + B.nv) * 3 <= RP_GJK_STAGE) {
 				PoseShape SA = A, SB = B;
-				double* col = s_stage + threadIdx.x;
+				real* col = s_stage + threadIdx.x;
 				const int used = stage_shape(SA, col, RP_EPA_THREADS);
 				stage_shape(SB, col + (size_t)used * RP_EPA_THREADS, RP_EPA_THREADS);
 				r = epa_run(StagedShape<RP_EPA_THREADS>(SA), StagedShape<RP_EPA_THREADS>(SB), s, e, &out.normal, &out.depth, &st, 0, &out.sup_a, &out.sup_b);
@@ -1094,7 +1106,7 @@ __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) 
 // +-normal that clipping starts from (convex_convex_contact_manifold, clipping.cpp:255-256) and leaves them for k_manifold.
 __global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_epa_warp(DevView d) {
 	const unsigned int nh = *d.hit_count;
-	__shared__ double s_hull[RP_GJK_WARP_THREADS / 32][2][3 * RP_WARP_HULL_MAX];
+	__shared__ real s_hull[RP_GJK_WARP_THREADS / 32][2][3 * RP_WARP_HULL_MAX];
 	EpaScratch e;
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const unsigned int warps = gridDim.x * (RP_GJK_WARP_THREADS / 32);
@@ -1110,7 +1122,7 @@ __global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_epa_warp(DevView d) {
 		__syncwarp();
 		const Simplex s = ld_simplex(d, hi);
 		EpaOut out;
-		out.ok = 0; out.pad = 0; out.depth = 0.0; out.normal = v3(0.0, 0.0, 0.0);
+		out.ok = 0; out.pad = 0; out.depth = RL(0.0); out.normal = v3(RL(0.0), RL(0.0), RL(0.0));
 		out.sup_a = out.sup_b = -1;
 		int st = 0;
 		out.ok = epa(WarpShape(A), WarpShape(B), s, e, &out.normal, &out.depth, &st, 0) ? 1 : 0;  // the same instance on all lanes
@@ -1134,11 +1146,11 @@ __global__ void __launch_bounds__(RP_GJK_WARP_THREADS) k_epa_warp(DevView d) {
 template <int NT>
 struct ClipShared {
 	enum { CAP = RP_CLIP_SMALL_POINTS, SOFT = 1 };
-	double* col;  // point i of buffer b: components at col[((b * CAP + i) * 3 + c) * NT]
-	__device__ __forceinline__ V3 get(int b, int i) const { const double* p = col + ((b * CAP + i) * 3) * NT; return v3(p[0], p[NT], p[2 * NT]); }
-	__device__ __forceinline__ void set(int b, int i, V3 v) { double* p = col + ((b * CAP + i) * 3) * NT; p[0] = v.x; p[NT] = v.y; p[2 * NT] = v.z; }
+	real* col;  // point i of buffer b: components at col[((b * CAP + i) * 3 + c) * NT]
+	__device__ __forceinline__ V3 get(int b, int i) const { const real* p = col + ((b * CAP + i) * 3) * NT; return v3(p[0], p[NT], p[2 * NT]); }
+	__device__ __forceinline__ void set(int b, int i, V3 v) { real* p = col + ((b * CAP + i) * 3) * NT; p[0] = v.x; p[NT] = v.y; p[2 * NT] = v.z; }
 };
-#define RP_MANIFOLD_SMEM_BYTES (2 * RP_CLIP_SMALL_POINTS * 3 * 8 * RP_MANIFOLD_THREADS)
+#define RP_MANIFOLD_SMEM_BYTES (2 * RP_CLIP_SMALL_POINTS * 3 * (int)sizeof(real) * RP_MANIFOLD_THREADS)
 
 struct CountSink {
 	int n;
@@ -1204,7 +1216,7 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 	const unsigned int nh = *d.hit_count;
 	extern __shared__ __align__(16) unsigned char s_clip_raw[];
 	ClipShared<RP_MANIFOLD_THREADS> cs;
-	cs.col = reinterpret_cast<double*>(s_clip_raw) + threadIdx.x;
+	cs.col = reinterpret_cast<real*>(s_clip_raw) + threadIdx.x;
 	int made = 0;
 	const int lane = threadIdx.x & 31;
 	for (unsigned int h0 = blockIdx.x * blockDim.x; h0 < nh; h0 += gridDim.x * blockDim.x) {
@@ -1212,7 +1224,7 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 		int n = 0, lvl = -1, w = 0, pair = 0;
 		SolveItem item;
 		item.w = item.a = item.b = item.coff = item.cnt = item.pad = 0;
-		item.normal = v3(0.0, 0.0, 0.0);
+		item.normal = v3(RL(0.0), RL(0.0), RL(0.0));
 		if (hi < nh) {
 			const EpaOut eo = d.epa_out[hi];
 			const uint4 cd = d.hits[hi];
@@ -1231,7 +1243,7 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 					// clipping_get_contact_manifold's sphere cases (clipping.cpp:348-364): one contact
 					ClipResult r;
 					r.kind = 1; r.n = 0; r.cur = 0; r.ref1 = false;
-					r.rp_normal = r.rp_point = v3(0.0, 0.0, 0.0);
+					r.rp_normal = r.rp_point = v3(RL(0.0), RL(0.0), RL(0.0));
 					if (A.type == SHAPE_SPHERE) {
 						r.l1 = support(A, eo.normal);
 						r.l2 = sub(r.l1, scale(eo.depth, eo.normal));
@@ -1329,7 +1341,7 @@ __device__ __forceinline__ int warp_clip_pass(const ClipPlane& pl, const V3* in,
 		const int j = j0 + lane;
 		int cnt = 0;
 		bool has_x = false;
-		V3 x = v3(0.0, 0.0, 0.0), end = v3(0.0, 0.0, 0.0);
+		V3 x = v3(RL(0.0), RL(0.0), RL(0.0)), end = v3(RL(0.0), RL(0.0), RL(0.0));
 		bool e_in = false;
 		if (j < n_in) {
 			end = in[j];
@@ -1440,7 +1452,7 @@ __global__ void __launch_bounds__(RP_CLIPW_THREADS) k_manifold_warp(DevView d) {
 				int base = 0;
 				for (int j0 = 0; j0 < m; j0 += 32) {
 					const int j = j0 + lane;
-					V3 p1 = v3(0.0, 0.0, 0.0), p2 = p1;
+					V3 p1 = v3(RL(0.0), RL(0.0), RL(0.0)), p2 = p1;
 					const bool hit = j < m && manifold_point(cur[j], rp.normal, rp.point, fc.ref1, normal, &p1, &p2);
 					int total;
 					const int at = base + warp_exclusive_scan(hit ? 1 : 0, &total);
@@ -1532,7 +1544,7 @@ struct PrevFromDyn {
 	}
 };
 template <bool JOINTS>
-__device__ __forceinline__ void pos_level(const DevView& d, double h, int level, int nj, int collisions) {
+__device__ __forceinline__ void pos_level(const DevView& d, real h, int level, int nj, int collisions) {
 	const int njw = JOINTS ? nj * d.W : 0;
 	int st = 0;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < njw; i += gridDim.x * blockDim.x) {
@@ -1564,10 +1576,10 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 	q.init((unsigned int)np);
 	bool have = false;
 	int w = 0, cnt = 0, c = 0;
-	double* cs = 0;
+	real* cs = 0;
 	DynRef r1, r2;
 	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
-	V3 normal = v3(0.0, 0.0, 0.0);
+	V3 normal = v3(RL(0.0), RL(0.0), RL(0.0));
 	Body b1, b2;
 	b1.fixed = b2.fixed = 1;
 	for (;;) {
@@ -1593,7 +1605,7 @@ __device__ __forceinline__ void pos_level(const DevView& d, double h, int level,
 			continue;
 		}
 		if (have) {
-			double* cp = cs + (size_t)c * 8 * d.WS;
+			real* cp = cs + (size_t)c * 8 * d.WS;
 			Contact ct = ld_contact(cp, d.WS);
 			solve_contact(ct, normal, b1, b2, h, &st, PrevFromDyn{r1, r2});
 			cp[6 * (size_t)d.WS] = ct.lambda_n;
@@ -1801,7 +1813,7 @@ __device__ __forceinline__ int flow_locate(const FlowTables& t, int levels, unsi
 // positional sweep, dataflow form: every level of every iteration in one pass (see above). A joint item is solved in one trip
 // of the loop, a contact unit in one trip per contact.
 template <bool JOINTS>
-__device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, double h, int levels, unsigned int per_pass, int iters) {
+__device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, real h, int levels, unsigned int per_pass, int iters) {
 	FlowQueue q;
 	q.init(per_pass * (unsigned int)iters);
 	const size_t total_row = (size_t)(levels + 1) * d.WS;
@@ -1810,10 +1822,10 @@ __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, 
 	int w = 0, cnt = 0, c = 0, ia = 0, ib = 0, spins = 0;
 	int ju = -1;  // the joint a lane holds (JOINTS), -1: a contact unit
 	unsigned int need = 0u;
-	double* cs = 0;
+	real* cs = 0;
 	DynRef r1, r2;
 	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
-	V3 normal = v3(0.0, 0.0, 0.0);
+	V3 normal = v3(RL(0.0), RL(0.0), RL(0.0));
 	Body b1, b2;
 	b1.fixed = b2.fixed = 1;
 	for (;;) {
@@ -1877,7 +1889,7 @@ __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, 
 				d.lambdas[(size_t)ju * d.WS + w] = lam;
 				c = cnt;
 			} else {
-				double* cp = cs + (size_t)c * 8 * d.WS;
+				real* cp = cs + (size_t)c * 8 * d.WS;
 				Contact ct = ld_contact(cp, d.WS);
 				solve_contact(ct, normal, b1, b2, h, &st, PrevFromDyn{r1, r2});
 				cp[6 * (size_t)d.WS] = ct.lambda_n;
@@ -1899,7 +1911,7 @@ __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, 
 }
 
 template <bool JOINTS>
-__global__ void RP_POS_BOUNDS k_solve_pos(DevView d, double h, int iters, int collisions, int live_lists) {
+__global__ void RP_POS_BOUNDS k_solve_pos(DevView d, real h, int iters, int collisions, int live_lists) {
 	cg::grid_group grid = cg::this_grid();
 	extern __shared__ __align__(16) unsigned char s_live_raw[];
 	LiveLevels& s_live = *reinterpret_cast<LiveLevels*>(s_live_raw);
@@ -1935,7 +1947,7 @@ __global__ void RP_POS_BOUNDS k_solve_pos(DevView d, double h, int iters, int co
 // end of the frame (not touched by a velocity-level unit of the last substep). Derivation is a pure function of the
 // body's own (x, q, prev x, prev q, v, w), none of which the velocity pass writes before deriving, so WHEN it happens
 // between the positional sweep and the first read of v/w does not change a bit.
-__global__ void __launch_bounds__(128) k_derive(DevView d, double h) {
+__global__ void __launch_bounds__(128) k_derive(DevView d, real h) {
 	int w, b;
 	if (!flat_item_world(d, d.NB, &b, &w)) return;
 	const int epoch = *d.epoch;
@@ -1957,7 +1969,7 @@ __global__ void __launch_bounds__(128) k_derive(DevView d, double h) {
 // (first velocity-level unit that touches it), derives them here (pbd.cpp:623-643), stores the previous velocities the
 // derivation leaves (they are part of the body's state) and stamps the body; returns true if it did. The previous
 // velocities are kept in registers only if the restitution term will read them (`need_prev`).
-__device__ __forceinline__ bool load_for_velocity(Body& b, const DynRef& r, int active, int* stamp, int epoch, double h, bool need_prev) {
+__device__ __forceinline__ bool load_for_velocity(Body& b, const DynRef& r, int active, int* stamp, int epoch, real h, bool need_prev) {
 	b.q = ld4(r, DF_Q); b.v = ld3(r, DF_V); b.w = ld3(r, DF_W);
 	b.active = active;
 	if (!(b.fixed || !b.active) && *stamp != epoch) {
@@ -1975,7 +1987,7 @@ __device__ __forceinline__ bool load_for_velocity(Body& b, const DynRef& r, int 
 
 // velocity pass over the contacts of one level (pbd.cpp:646-711); the hinge branch of the reference's velocity pass is
 // an empty TODO (pbd.cpp:712-739), so joints take no part
-__device__ __forceinline__ void vel_level(const DevView& d, double h, int level) {
+__device__ __forceinline__ void vel_level(const DevView& d, real h, int level) {
 	const int npf = d.lvl_fill[(size_t)level * RP_LVL_STRIDE];
 	const int np = npf + d.lvl_fill[(size_t)level * RP_LVL_STRIDE + 1];
 	const int off0 = d.lvl_off[level], off1 = d.lvl_off[level + 1];
@@ -1983,13 +1995,13 @@ __device__ __forceinline__ void vel_level(const DevView& d, double h, int level)
 	q.init((unsigned int)np);
 	bool have = false;
 	int cnt = 0, c = 0;
-	const double* cs = 0;
+	const real* cs = 0;
 	DynRef r1, r2;
 	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
 	AngPre tens;
 	tens.ii1 = tens.ii2 = zero_m3();
 	const int epoch = *d.epoch;
-	V3 normal = v3(0.0, 0.0, 0.0);
+	V3 normal = v3(RL(0.0), RL(0.0), RL(0.0));
 	Body b1, b2;
 	b1.fixed = b2.fixed = 1;
 	for (;;) {
@@ -2008,7 +2020,7 @@ __device__ __forceinline__ void vel_level(const DevView& d, double h, int level)
 				r1 = dyn_ref(d, w, pr.a);
 				r2 = dyn_ref(d, w, pr.b);
 				// restitution 0 on either side: the velocity solve never reads the previous velocities (solve_contact_velocity)
-				const bool need_prev = b1.rest * b2.rest != 0.0;
+				const bool need_prev = b1.rest * b2.rest != RL(0.0);
 				load_for_velocity(b1, r1, d.active[bidx(d, pr.a, w)], d.vstamp + bidx(d, pr.a, w), epoch, h, need_prev);
 				load_for_velocity(b2, r2, d.active[bidx(d, pr.b, w)], d.vstamp + bidx(d, pr.b, w), epoch, h, need_prev);
 				tens = vel_tensors(b1, b2);
@@ -2034,20 +2046,20 @@ __device__ __forceinline__ void vel_level(const DevView& d, double h, int level)
 
 
 // velocity pass, dataflow form (the prefix table is the one the positional kernel of this substep left)
-__device__ __forceinline__ void vel_flow(const DevView& d, const FlowTables& t, double h, int levels, unsigned int per_pass) {
+__device__ __forceinline__ void vel_flow(const DevView& d, const FlowTables& t, real h, int levels, unsigned int per_pass) {
 	FlowQueue q;
 	q.init(per_pass);
 	unsigned int* done = d.flow_done + d.WS;
 	bool have = false, ready = false;
 	int w = 0, cnt = 0, c = 0, ia = 0, ib = 0, spins = 0;
 	unsigned int need = 0u;
-	const double* cs = 0;
+	const real* cs = 0;
 	DynRef r1, r2;
 	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
 	AngPre tens;
 	tens.ii1 = tens.ii2 = zero_m3();
 	const int epoch = *d.epoch;
-	V3 normal = v3(0.0, 0.0, 0.0);
+	V3 normal = v3(RL(0.0), RL(0.0), RL(0.0));
 	Body b1, b2;
 	b1.fixed = b2.fixed = 1;
 	for (;;) {
@@ -2083,7 +2095,7 @@ __device__ __forceinline__ void vel_flow(const DevView& d, const FlowTables& t, 
 				load_static(b2, d, ib);
 				r1 = dyn_ref(d, w, ia);
 				r2 = dyn_ref(d, w, ib);
-				const bool need_prev = b1.rest * b2.rest != 0.0;
+				const bool need_prev = b1.rest * b2.rest != RL(0.0);
 				load_for_velocity(b1, r1, d.active[bidx(d, ia, w)], d.vstamp + bidx(d, ia, w), epoch, h, need_prev);
 				load_for_velocity(b2, r2, d.active[bidx(d, ib, w)], d.vstamp + bidx(d, ib, w), epoch, h, need_prev);
 				tens = vel_tensors(b1, b2);
@@ -2104,7 +2116,7 @@ __device__ __forceinline__ void vel_flow(const DevView& d, const FlowTables& t, 
 	}
 }
 
-__global__ void __launch_bounds__(RP_VEL_THREADS, RP_MINB_VEL) k_solve_vel(DevView d, double h, int live_lists, int flow_iters) {
+__global__ void __launch_bounds__(RP_VEL_THREADS, RP_MINB_VEL) k_solve_vel(DevView d, real h, int live_lists, int flow_iters) {
 	cg::grid_group grid = cg::this_grid();
 	extern __shared__ __align__(16) unsigned char s_live_raw[];
 	LiveLevels& s_live = *reinterpret_cast<LiveLevels*>(s_live_raw);
@@ -2149,12 +2161,12 @@ __global__ void __launch_bounds__(RP_VEL_THREADS, RP_MINB_VEL) k_solve_vel(DevVi
 #endif
 #define RP_SB_MAX_WPB 64
 
-__device__ __forceinline__ void pos_unit(const DevView& d, double h, int w, int pair, int* st) {
+__device__ __forceinline__ void pos_unit(const DevView& d, real h, int w, int pair, int* st) {
 	const size_t pg = pidx(d, pair, w);
 	const int2 ab = *reinterpret_cast<const int2*>(&d.pairs[pg]);
 	const int cnt = d.pair_ccnt[pg];
 	const V3 normal = d.pair_normal[pg];
-	double* cs = contact_ptr(d, w, d.pair_coff[pg]);
+	real* cs = contact_ptr(d, w, d.pair_coff[pg]);
 	Body b1, b2;
 	load_static(b1, d, ab.x);
 	load_static(b2, d, ab.y);
@@ -2163,7 +2175,7 @@ __device__ __forceinline__ void pos_unit(const DevView& d, double h, int w, int 
 	b1.x = ld3(r1, DF_X); b1.q = ld4(r1, DF_Q);
 	b2.x = ld3(r2, DF_X); b2.q = ld4(r2, DF_Q);
 	for (int c = 0; c < cnt; ++c) {
-		double* cp = cs + (size_t)c * 8 * d.WS;
+		real* cp = cs + (size_t)c * 8 * d.WS;
 		Contact ct = ld_contact(cp, d.WS);
 		solve_contact(ct, normal, b1, b2, h, st, PrevFromDyn{r1, r2});
 		cp[6 * (size_t)d.WS] = ct.lambda_n;
@@ -2173,18 +2185,18 @@ __device__ __forceinline__ void pos_unit(const DevView& d, double h, int w, int 
 	if (!b2.fixed) { st3(r2, DF_X, b2.x); st4(r2, DF_Q, b2.q); }
 }
 
-__device__ __forceinline__ void vel_unit(const DevView& d, double h, int w, int pair, int epoch) {
+__device__ __forceinline__ void vel_unit(const DevView& d, real h, int w, int pair, int epoch) {
 	const size_t pg = pidx(d, pair, w);
 	const int2 ab = *reinterpret_cast<const int2*>(&d.pairs[pg]);
 	const int cnt = d.pair_ccnt[pg];
 	const V3 normal = d.pair_normal[pg];
-	const double* cs = contact_ptr(d, w, d.pair_coff[pg]);
+	const real* cs = contact_ptr(d, w, d.pair_coff[pg]);
 	Body b1, b2;
 	load_static(b1, d, ab.x);
 	load_static(b2, d, ab.y);
 	const DynRef r1 = dyn_ref(d, w, ab.x);
 	const DynRef r2 = dyn_ref(d, w, ab.y);
-	const bool need_prev = b1.rest * b2.rest != 0.0;  // restitution 0 on either side: the previous velocities are never read
+	const bool need_prev = b1.rest * b2.rest != RL(0.0);  // restitution 0 on either side: the previous velocities are never read
 	load_for_velocity(b1, r1, d.active[bidx(d, ab.x, w)], d.vstamp + bidx(d, ab.x, w), epoch, h, need_prev);
 	load_for_velocity(b2, r2, d.active[bidx(d, ab.y, w)], d.vstamp + bidx(d, ab.y, w), epoch, h, need_prev);
 	const AngPre tens = vel_tensors(b1, b2);
@@ -2197,7 +2209,7 @@ __device__ __forceinline__ void vel_unit(const DevView& d, double h, int w, int 
 }
 
 template <bool JOINTS>
-__global__ void __launch_bounds__(RP_SB_THREADS, RP_MINB_SB) k_solve_block(DevView d, double h, int iters, int collisions, int wpb) {
+__global__ void __launch_bounds__(RP_SB_THREADS, RP_MINB_SB) k_solve_block(DevView d, real h, int iters, int collisions, int wpb) {
 	extern __shared__ __align__(16) int s_lv[];  // [max_levels + 2]: counts -> starts -> ends of the block's levels
 	__shared__ int s_nl[RP_SB_MAX_WPB];
 	__shared__ int s_max, s_nlmax;
@@ -2378,15 +2390,15 @@ __global__ void __launch_bounds__(128) k_unpack_state(DevView d, const double* r
 	const int wl = blockIdx.y * blockDim.x + threadIdx.x;
 	const int b = blockIdx.x;
 	if (wl >= n_worlds) return;
-	const double* r = rec + (broadcast ? (size_t)b : (size_t)wl * d.NB + b) * 21;
+	const double* r = rec + (broadcast ? (size_t)b : (size_t)wl * d.NB + b) * 21;  // (the host record is double whatever `real` is)
 	const int w = first_world + wl;
 	const DynRef o = dyn_ref(d, w, b);
-	st3(o, DF_X, v3(r[0], r[1], r[2])); st4(o, DF_Q, q4(r[3], r[4], r[5], r[6]));
-	st3(o, DF_V, v3(r[7], r[8], r[9])); st3(o, DF_W, v3(r[10], r[11], r[12]));
-	st3(o, DF_PX, v3(r[0], r[1], r[2])); st4(o, DF_PQ, q4(r[3], r[4], r[5], r[6]));
-	st3(o, DF_PV, v3(r[15], r[16], r[17])); st3(o, DF_PW, v3(r[18], r[19], r[20]));
+	st3(o, DF_X, v3((real)r[0], (real)r[1], (real)r[2])); st4(o, DF_Q, q4((real)r[3], (real)r[4], (real)r[5], (real)r[6]));
+	st3(o, DF_V, v3((real)r[7], (real)r[8], (real)r[9])); st3(o, DF_W, v3((real)r[10], (real)r[11], (real)r[12]));
+	st3(o, DF_PX, v3((real)r[0], (real)r[1], (real)r[2])); st4(o, DF_PQ, q4((real)r[3], (real)r[4], (real)r[5], (real)r[6]));
+	st3(o, DF_PV, v3((real)r[15], (real)r[16], (real)r[17])); st3(o, DF_PW, v3((real)r[18], (real)r[19], (real)r[20]));
 	d.active[bidx(d, b, w)] = r[13] != 0.0 ? 1 : 0;
-	d.deact[bidx(d, b, w)] = r[14];
+	d.deact[bidx(d, b, w)] = (real)r[14];
 	d.vstamp[bidx(d, b, w)] = *d.epoch;  // uploaded velocities are current
 }
 __global__ void __launch_bounds__(128) k_pack_state(DevView d, double* rec, int first_world, int n_worlds) {

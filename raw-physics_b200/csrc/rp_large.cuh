@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(RP_SCAN_THREADS) k_scan_add(int* data, int n, 
 // ------------------------------------------------------------------------------------------------ grid broadphase
 struct GridView {
 	int table;            // buckets (power of two)
-	double inv_cell;      // 1 / cell edge; cell edge = (2 * r_small_max + 0.1) * (1 + 1e-6)
+	real inv_cell;      // 1 / cell edge; cell edge = (2 * r_small_max + 0.1) * (1 + 1e-6)
 	int n_large;          // bodies kept out of the grid
 	const int* large;     // [n_large] their indices, ascending
 	const unsigned char* is_large;  // [NB]
@@ -127,9 +127,9 @@ __device__ __forceinline__ int grid_bucket(const GridView& g, int cx, int cy, in
 }
 __device__ __forceinline__ V3 body_x(const DevView& d, int w, int b) { return ld3(dyn_ref(d, w, b), DF_X); }
 // broad.cpp:19-20 as written
-__device__ __forceinline__ bool broad_near(V3 xi, double ri, V3 xj, double rj) {
+__device__ __forceinline__ bool broad_near(V3 xi, real ri, V3 xj, real rj) {
 	const V3 dv = sub(xi, xj);
-	return sqrt(dv.x * dv.x + dv.y * dv.y + dv.z * dv.z) <= ri + rj + 0.1;
+	return sqrt(dv.x * dv.x + dv.y * dv.y + dv.z * dv.z) <= ri + rj + RL(0.1);
 }
 
 __global__ void __launch_bounds__(256) k_grid_count(DevView d, GridView g) {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) k_grid_fill(DevView d, GridView g) {
 template <class F>
 __device__ __forceinline__ void grid_row_visit(const DevView& d, const GridView& g, int w, int i, F f) {
 	const V3 xi = body_x(d, w, i);
-	const double ri = d.bstat[i].radius;
+	const real ri = d.bstat[i].radius;
 	const int3 c = grid_cell(g, xi);
 	int seen[27];
 	int ns = 0;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(128) k_grid_rowcount(DevView d, GridView g) {
 __global__ void __launch_bounds__(RP_SCAN_THREADS) k_grid_large_count(DevView d, GridView g) {
 	const int i = g.large[blockIdx.x], w = blockIdx.y;
 	const V3 xi = body_x(d, w, i);
-	const double ri = d.bstat[i].radius;
+	const real ri = d.bstat[i].radius;
 	const int nci = d.bstat[i].ncol;
 	int count = 0;
 	for (int j = i + 1 + threadIdx.x; j < d.NB; j += RP_SCAN_THREADS) {
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(128) k_grid_rowwrite(DevView d, GridView g) {
 __global__ void __launch_bounds__(RP_SCAN_THREADS) k_grid_large_write(DevView d, GridView g) {
 	const int i = g.large[blockIdx.x], w = blockIdx.y;
 	const V3 xi = body_x(d, w, i);
-	const double ri = d.bstat[i].radius;
+	const real ri = d.bstat[i].radius;
 	const int nci = d.bstat[i].ncol;
 	int base = g.row[(size_t)w * (d.NB + 1) + i];
 	for (int j0 = i + 1; j0 < d.NB; j0 += RP_SCAN_THREADS) {
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256) k_uf_hook(DevView d) {
 		if (atomicCAS(&parent[hi], hi, lo) == hi) break;
 	}
 }
-__global__ void __launch_bounds__(256) k_uf_sleep(DevView d, double dt) {
+__global__ void __launch_bounds__(256) k_uf_sleep(DevView d, real dt) {
 	int w, b;
 	if (!flat_item_world(d, d.NB, &b, &w)) return;
 	if (d.bstat[b].fixed) return;
@@ -343,10 +343,10 @@ __global__ void __launch_bounds__(256) k_uf_sleep(DevView d, double dt) {
 	const int root = uf_root(parent, b);
 	parent[b] = root;
 	const DynRef r = dyn_ref(d, w, b);
-	const double lv = length(ld3(r, DF_V)), av = length(ld3(r, DF_W));
-	double t = d.deact[bidx(d, b, w)];
+	const real lv = length(ld3(r, DF_V)), av = length(ld3(r, DF_W));
+	real t = d.deact[bidx(d, b, w)];
 	if (lv < d.lin_sleep && av < d.ang_sleep) t += dt;
-	else t = 0.0;
+	else t = RL(0.0);
 	d.deact[bidx(d, b, w)] = t;
 	if (t < d.sleep_time) d.isl_flag[(size_t)w * d.NB + root] = 0;
 }
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256) k_cull_flat(DevView d, int cull) {
 		const float* pb = d.aabb + (size_t)pr.cb * 6 * S + w;
 #pragma unroll
 		for (int ax = 0; ax < 3; ++ax) {
-			const double lo_a = pa[ax * S], hi_a = pa[(3 + ax) * S], lo_b = pb[ax * S], hi_b = pb[(3 + ax) * S];
+			const real lo_a = pa[ax * S], hi_a = pa[(3 + ax) * S], lo_b = pb[ax * S], hi_b = pb[(3 + ax) * S];
 			if (lo_a - hi_b > RP_CULL_MARGIN || lo_b - hi_a > RP_CULL_MARGIN) keep = false;
 		}
 	}

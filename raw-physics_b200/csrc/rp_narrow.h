@@ -49,11 +49,11 @@ RP_HD V3 cross3(V3 a, V3 b, V3 c) { return cross(cross(a, b), c); }
 // Returns true when the origin projects inside the triangle (caller finishes that region); on the "A region" branches
 // only `a` is (re)written and num is left as it was (quirk q3).
 RP_HD bool gjk_triangle_edges(Simplex* s, V3* dir, V3 a, V3 P, V3 Q, V3 ap, V3 aq, V3 n, V3 ao, V3 ap_alt) {
-	if (dot(cross(n, aq), ao) >= 0.0) {
-		if (dot(aq, ao) >= 0.0) {
+	if (dot(cross(n, aq), ao) >= RL(0.0)) {
+		if (dot(aq, ao) >= RL(0.0)) {
 			s->a = a; s->b = Q; s->num = 2;
 			*dir = cross3(aq, ao, aq);
-		} else if (dot(ap, ao) >= 0.0) {
+		} else if (dot(ap, ao) >= RL(0.0)) {
 			s->a = a; s->b = P; s->num = 2;
 			*dir = cross3(ap_alt, ao, ap_alt);
 		} else {
@@ -62,8 +62,8 @@ RP_HD bool gjk_triangle_edges(Simplex* s, V3* dir, V3 a, V3 P, V3 Q, V3 ap, V3 a
 		}
 		return false;
 	}
-	if (dot(cross(ap, n), ao) >= 0.0) {
-		if (dot(ap, ao) >= 0.0) {
+	if (dot(cross(ap, n), ao) >= RL(0.0)) {
+		if (dot(ap, ao) >= RL(0.0)) {
 			s->a = a; s->b = P; s->num = 2;
 			*dir = cross3(ap, ao, ap);
 		} else {
@@ -76,7 +76,7 @@ RP_HD bool gjk_triangle_edges(Simplex* s, V3* dir, V3 a, V3 P, V3 Q, V3 ap, V3 a
 }
 
 RP_HD void gjk_line(Simplex* s, V3* dir, V3 a, V3 P, V3 ap, V3 ao) {
-	if (dot(ap, ao) >= 0.0) {
+	if (dot(ap, ao) >= RL(0.0)) {
 		s->a = a; s->b = P; s->num = 2;
 		*dir = cross3(ap, ao, ap);
 	} else {
@@ -99,7 +99,7 @@ RP_HD bool gjk_do_simplex(Simplex* s, V3* dir) {
 	V3 abc = cross(ab, ac);
 	if (s->num == 3) {  // gjk.cpp:57-120
 		if (gjk_triangle_edges(s, dir, a, b, c, ab, ac, abc, ao, ab)) {
-			if (dot(abc, ao) >= 0.0) {
+			if (dot(abc, ao) >= RL(0.0)) {
 				s->a = a; s->b = b; s->c = c; s->num = 3;
 				*dir = abc;
 			} else {
@@ -115,9 +115,9 @@ RP_HD bool gjk_do_simplex(Simplex* s, V3* dir) {
 	V3 acd = cross(ac, ad);
 	V3 adb = cross(ad, ab);
 	int planes = 0;
-	if (dot(abc, ao) >= 0.0) planes |= 1;
-	if (dot(acd, ao) >= 0.0) planes |= 2;
-	if (dot(adb, ao) >= 0.0) planes |= 4;
+	if (dot(abc, ao) >= RL(0.0)) planes |= 1;
+	if (dot(acd, ao) >= RL(0.0)) planes |= 2;
+	if (dot(adb, ao) >= RL(0.0)) planes |= 4;
 	switch (planes) {
 		case 0: return true;
 		case 1:
@@ -156,16 +156,16 @@ enum { GJK_CONTINUE = 0, GJK_HIT = 1, GJK_MISS = 2 };
 
 template <class SA, class SB>
 RP_HD void gjk_begin(const SA& A, const SB& B, Simplex* s, V3* dir) {
-	s->a = support_minkowski(A, B, v3(0.0, 0.0, 1.0));
-	s->b = s->c = s->d = v3(0.0, 0.0, 0.0);
+	s->a = support_minkowski(A, B, v3(RL(0.0), RL(0.0), RL(1.0)));
+	s->b = s->c = s->d = v3(RL(0.0), RL(0.0), RL(0.0));
 	s->num = 1;
-	*dir = scale(-1.0, s->a);
+	*dir = scale(-RL(1.0), s->a);
 }
 
 template <class SA, class SB>
 RP_HD int gjk_step(const SA& A, const SB& B, Simplex* s, V3* dir, int* status) {
 	V3 p = support_minkowski(A, B, *dir);
-	if (dot(p, *dir) < 0.0) return GJK_MISS;
+	if (dot(p, *dir) < RL(0.0)) return GJK_MISS;
 	// add_to_simplex (gjk.cpp:7-30)
 	if (s->num == 1) {
 		s->b = s->a;
@@ -213,17 +213,17 @@ struct EpaArrays {
 	enum { MAXV = MAXV_, MAXF = MAXF_, MAXE = MAXE_, SOFT = SOFT_ ? 1 : 0 };
 	V3 verts[MAXV];
 	V3 normals[MAXF];
-	double dists[MAXF];
+	real dists[MAXF];
 	uint8_t faces[MAXF][3];
 	uint8_t edges[MAXE][2];
 	int nverts, nfaces, nedges;
 	V3 min_normal;   // closest face so far (first strictly smaller distance wins, epa.cpp:141-144,:222-228)
-	double min_dist;
+	real min_dist;
 	RP_HD V3 vert(int i) const { return verts[i]; }
 	RP_HD void set_vert(int i, V3 v) { verts[i] = v; }
 	RP_HD V3 normal(int i) const { return normals[i]; }
-	RP_HD double dist(int i) const { return dists[i]; }
-	RP_HD void set_plane(int i, V3 n, double d) { normals[i] = n; dists[i] = d; }
+	RP_HD real dist(int i) const { return dists[i]; }
+	RP_HD void set_plane(int i, V3 n, real d) { normals[i] = n; dists[i] = d; }
 	RP_HD void face(int i, int* x, int* y, int* z) const { *x = faces[i][0]; *y = faces[i][1]; *z = faces[i][2]; }
 	RP_HD void set_face(int i, int x, int y, int z) { faces[i][0] = (uint8_t)x; faces[i][1] = (uint8_t)y; faces[i][2] = (uint8_t)z; }
 	RP_HD void move_face(int dst, int src) {
@@ -246,20 +246,20 @@ typedef EpaArrays<RP_EPA_SMALL_VERTS, RP_EPA_SMALL_FACES, RP_EPA_SMALL_EDGES, tr
 
 // get_face_normal_and_distance_to_origin (epa.cpp:32-77)
 template <class E>
-RP_HD bool epa_face_plane(const E& e, int ia, int ib, int ic, V3* normal_out, double* dist_out) {
+RP_HD bool epa_face_plane(const E& e, int ia, int ib, int ic, V3* normal_out, real* dist_out) {
 	V3 a = e.vert(ia);
 	V3 n = normalize(cross(sub(e.vert(ib), a), sub(e.vert(ic), a)));
-	if (!(n.x != 0.0 || n.y != 0.0 || n.z != 0.0)) return false;  // epa.cpp:41
-	double dist = dot(n, a);
-	if (dist < -0.0) {
+	if (!(n.x != RL(0.0) || n.y != RL(0.0) || n.z != RL(0.0))) return false;  // epa.cpp:41
+	real dist = dot(n, a);
+	if (dist < -RL(0.0)) {
 		n = zero_minus(n);
 		dist = -dist;
-	} else if (dist >= -0.0 && dist <= 0.0) {
+	} else if (dist >= -RL(0.0) && dist <= RL(0.0)) {
 		bool found = false;
 		for (int i = 0; i < e.nverts; ++i) {
-			double t = dot(n, e.vert(i));
-			if (t < -0.0 || t > 0.0) {
-				n = t < -0.0 ? n : zero_minus(n);
+			real t = dot(n, e.vert(i));
+			if (t < -RL(0.0) || t > RL(0.0)) {
+				n = t < -RL(0.0) ? n : zero_minus(n);
 				found = true;
 				break;
 			}
@@ -315,12 +315,12 @@ RP_HD int epa_begin(const Simplex& s, E& e, int* status) {
 	e.nverts = 4;
 	e.nfaces = 0;
 	e.nedges = 0;
-	e.min_normal = v3(0.0, 0.0, 0.0);
-	e.min_dist = 1.7976931348623157e308;
+	e.min_normal = v3(RL(0.0), RL(0.0), RL(0.0));
+	e.min_dist = RL(RP_REAL_MAX);
 	for (int i = 0; i < 4; ++i) {
 		// initial faces (0,1,2) (0,2,3) (0,3,1) (1,2,3) (epa.cpp:8-30)
 		const int fa = i == 3 ? 1 : 0, fb = i == 0 ? 1 : (i == 3 ? 2 : i + 1), fc = i == 0 ? 2 : (i == 2 ? 1 : 3);
-		V3 n; double d;
+		V3 n; real d;
 		if (!epa_face_plane(e, fa, fb, fc, &n, &d)) {
 			*status |= ST_EPA_DEGENERATE;
 			return EPA_FAIL;
@@ -345,8 +345,8 @@ RP_HD int epa_step(const SA& A, const SB& B, E& e, int* status, int* sup_a = 0, 
 		*sup_a = ia;
 		*sup_b = ib;
 	}
-	double d = dot(min_normal, sp);
-	if (fabs(d - e.min_dist) < 0.0001) return EPA_DONE;  // result: e.min_normal, e.min_dist
+	real d = dot(min_normal, sp);
+	if (fabs(d - e.min_dist) < RL(0.0001)) return EPA_DONE;  // result: e.min_normal, e.min_dist
 	if (e.nverts >= E::MAXV) return epa_out_of_room<E>(status);  // (the full store holds 4 + RP_EPA_MAX_ITERS: never reached there)
 	int new_index = e.nverts;
 	e.set_vert(e.nverts++, sp);
@@ -356,8 +356,8 @@ RP_HD int epa_step(const SA& A, const SB& B, E& e, int* status, int* sup_a = 0, 
 	while (i < e.nfaces) {
 		int fx, fy, fz;
 		e.face(i, &fx, &fy, &fz);
-		V3 centroid = scale(1.0 / 3.0, add(add(e.vert(fy), e.vert(fz)), e.vert(fx)));  // triangle_centroid (epa.cpp:112)
-		if (dot(e.normal(i), sub(sp, centroid)) > 0.0) {
+		V3 centroid = scale(RL(1.0) / RL(3.0), add(add(e.vert(fy), e.vert(fz)), e.vert(fx)));  // triangle_centroid (epa.cpp:112)
+		if (dot(e.normal(i), sub(sp, centroid)) > RL(0.0)) {
 			if (!epa_toggle_edge(e, fx, fy) || !epa_toggle_edge(e, fy, fz) || !epa_toggle_edge(e, fz, fx)) return epa_out_of_room<E>(status);
 			int last = --e.nfaces;
 			e.move_face(i, last);
@@ -369,7 +369,7 @@ RP_HD int epa_step(const SA& A, const SB& B, E& e, int* status, int* sup_a = 0, 
 		if (e.nfaces >= E::MAXF) return epa_out_of_room<E>(status);
 		int ex, ey;
 		e.edge(k, &ex, &ey);
-		V3 n; double dd;
+		V3 n; real dd;
 		if (!epa_face_plane(e, ex, ey, new_index, &n, &dd)) {
 			*status |= ST_EPA_DEGENERATE;
 			return EPA_FAIL;
@@ -378,9 +378,9 @@ RP_HD int epa_step(const SA& A, const SB& B, E& e, int* status, int* sup_a = 0, 
 		e.set_face(f, ex, ey, new_index);
 		e.set_plane(f, n, dd);
 	}
-	e.min_dist = 1.7976931348623157e308;
+	e.min_dist = RL(RP_REAL_MAX);
 	for (int k = 0; k < e.nfaces; ++k) {
-		const double dk = e.dist(k);
+		const real dk = e.dist(k);
 		if (dk < e.min_dist) {
 			e.min_dist = dk;
 			e.min_normal = e.normal(k);
@@ -392,7 +392,7 @@ RP_HD int epa_step(const SA& A, const SB& B, E& e, int* status, int* sup_a = 0, 
 
 // returns EPA_DONE (normal, depth written), EPA_FAIL (status says why) or, for a SOFT store, EPA_OVERFLOW (nothing written)
 template <class SA, class SB, class E>
-RP_HD int epa_run(const SA& A, const SB& B, const Simplex& s, E& e, V3* normal_out, double* depth_out, int* status, int* iters,
+RP_HD int epa_run(const SA& A, const SB& B, const Simplex& s, E& e, V3* normal_out, real* depth_out, int* status, int* iters,
 	int* sup_a = 0, int* sup_b = 0) {
 	if (epa_begin(s, e, status) == EPA_FAIL) return EPA_FAIL;
 	for (int it = 0; it < RP_EPA_MAX_ITERS; ++it) {
@@ -411,7 +411,7 @@ RP_HD int epa_run(const SA& A, const SB& B, const Simplex& s, E& e, V3* normal_o
 }
 
 template <class SA, class SB>
-RP_HD bool epa(const SA& A, const SB& B, const Simplex& s, EpaScratch& e, V3* normal_out, double* depth_out, int* status,
+RP_HD bool epa(const SA& A, const SB& B, const Simplex& s, EpaScratch& e, V3* normal_out, real* depth_out, int* status,
 	int* iters) {
 	return epa_run(A, B, s, e, normal_out, depth_out, status, iters) == EPA_DONE;
 }
@@ -428,17 +428,17 @@ struct ClipPlane {
 // is_point_in_plane (clipping.cpp:12-19): the plane offset is rounded to float (quirk q6). `offset` is
 // (float)(-dot(normal, point)), hoisted out of the per-vertex calls (same inputs, same value).
 RP_HD float clip_offset(const ClipPlane& pl) { return (float)(-dot(pl.normal, pl.point)); }
-RP_HD bool clip_inside(const ClipPlane& pl, float offset, V3 p) { return !(dot(p, pl.normal) + (double)offset < 0.0); }
+RP_HD bool clip_inside(const ClipPlane& pl, float offset, V3 p) { return !(dot(p, pl.normal) + (real)offset < RL(0.0)); }
 
 // plane_edge_intersection (clipping.cpp:21-46): ab_p, the plane offset and the edge factor pass through float
 RP_HD bool clip_edge(const ClipPlane& pl, float offset, V3 start, V3 end, V3* out) {
 	V3 ab = sub(end, start);
 	float ab_p = (float)dot(pl.normal, ab);
-	if (fabs((double)ab_p) > 0.000001) {
-		V3 p_co = scale((double)(-offset), pl.normal);
-		float fac = (float)fdiv(-dot(pl.normal, sub(start, p_co)), (double)ab_p);
-		fac = (float)RP_MINF(RP_MAXF((double)fac, 0.0), 1.0);
-		*out = add(start, scale((double)fac, ab));
+	if (fabs((real)ab_p) > RL(0.000001)) {
+		V3 p_co = scale((real)(-offset), pl.normal);
+		float fac = (float)fdiv(-dot(pl.normal, sub(start, p_co)), (real)ab_p);
+		fac = (float)RP_MINF(RP_MAXF((real)fac, RL(0.0)), RL(1.0));
+		*out = add(start, scale((real)fac, ab));
 		return true;
 	}
 	return false;
@@ -508,16 +508,16 @@ RP_HD int clip_pass(const ClipPlane& pl, C& cs, int src, int n_in, bool remove_o
 // normalisation). `normal_out` receives the chosen face's normal.
 template <class S>
 RP_HD int clip_best_face(const S& s, int support_idx, V3 normal, V3* normal_out) {
-	double best = -1.7976931348623157e308;
+	real best = -RL(RP_REAL_MAX);
 	int sel = 0, prev = -1;
-	V3 sel_n = v3(0.0, 0.0, 0.0);
+	V3 sel_n = v3(RL(0.0), RL(0.0), RL(0.0));
 	bool any = false;
 	for (int k = s.v2f_ptr[support_idx]; k < s.v2f_ptr[support_idx + 1]; ++k) {
 		int f = s.v2f_idx[k];
 		if (f == prev) continue;
 		prev = f;
 		V3 fn = fnormal(s, f);
-		double proj = dot(fn, normal);
+		real proj = dot(fn, normal);
 		if (proj > best) {
 			best = proj;
 			sel = f;
@@ -531,15 +531,15 @@ RP_HD int clip_best_face(const S& s, int support_idx, V3 normal, V3* normal_out)
 
 // collision_distance_between_skew_lines (clipping.cpp:210-247), quirk q5: the names are swapped but self-consistent
 RP_HD bool clip_skew_lines(V3 p1, V3 d1, V3 p2, V3 d2, V3* l1, V3* l2) {
-	double n1 = d1.x * d2.x + d1.y * d2.y + d1.z * d2.z;
-	double n2 = d2.x * d2.x + d2.y * d2.y + d2.z * d2.z;
-	double m1 = -d1.x * d1.x - d1.y * d1.y - d1.z * d1.z;
-	double m2 = -d2.x * d1.x - d2.y * d1.y - d2.z * d1.z;
-	double r1 = -d1.x * p2.x + d1.x * p1.x - d1.y * p2.y + d1.y * p1.y - d1.z * p2.z + d1.z * p1.z;
-	double r2 = -d2.x * p2.x + d2.x * p1.x - d2.y * p2.y + d2.y * p1.y - d2.z * p2.z + d2.z * p1.z;
+	real n1 = d1.x * d2.x + d1.y * d2.y + d1.z * d2.z;
+	real n2 = d2.x * d2.x + d2.y * d2.y + d2.z * d2.z;
+	real m1 = -d1.x * d1.x - d1.y * d1.y - d1.z * d1.z;
+	real m2 = -d2.x * d1.x - d2.y * d1.y - d2.z * d1.z;
+	real r1 = -d1.x * p2.x + d1.x * p1.x - d1.y * p2.y + d1.y * p1.y - d1.z * p2.z + d1.z * p1.z;
+	real r2 = -d2.x * p2.x + d2.x * p1.x - d2.y * p2.y + d2.y * p1.y - d2.z * p2.z + d2.z * p1.z;
 	if ((n1 * m2) - (n2 * m1) == 0) return false;
-	double n = fdiv((r1 * m2) - (r2 * m1), (n1 * m2) - (n2 * m1));
-	double m = fdiv((n1 * r2) - (n2 * r1), (n1 * m2) - (n2 * m1));
+	real n = fdiv((r1 * m2) - (r2 * m1), (n1 * m2) - (n2 * m1));
+	real m = fdiv((n1 * r2) - (n2 * r1), (n1 * m2) - (n2 * m1));
 	*l1 = add(p1, scale(m, d1));
 	*l2 = add(p2, scale(n, d2));
 	return true;
@@ -582,9 +582,9 @@ RP_HD void manifold_select(const S& h1, const S& h2, V3 normal, int* status, Fac
 	int face1 = clip_best_face(h1, sup1, normal, &f1n);
 	int face2 = clip_best_face(h2, sup2, inv_normal, &f2n);
 
-	double dot1 = dot(f1n, normal);
-	double dot2 = dot(f2n, inv_normal);
-	const double EPS = 0.0001;
+	real dot1 = dot(f1n, normal);
+	real dot2 = dot(f2n, inv_normal);
+	const real EPS = RL(0.0001);
 
 	// get_edge_with_most_fitting_normal (clipping.cpp:154-201) picks, over all pairs of edges leaving the two support
 	// vertices, the unit cross product best aligned with the collision normal (first maximum wins, both signs tried).
@@ -595,10 +595,10 @@ RP_HD void manifold_select(const S& h1, const S& h2, V3 normal, int* status, Fac
 	//      order with the original strict comparison, runs only on candidates within 1e-3 of the best score -- the
 	//      first exact maximum is always among them, and everything before it is exactly smaller, so the selected
 	//      edge pair, the edge normal and the maximum are the ones the full loop would return.
-	double best = -1.7976931348623157e308;
+	real best = -RL(RP_REAL_MAX);
 	int e1n = 0, e2n = 0;
-	V3 edge_normal = v3(0.0, 0.0, 0.0);
-	const bool edge_possible = !(dot1 + EPS > 1.000000000001 || dot2 + EPS > 1.000000000001);
+	V3 edge_normal = v3(RL(0.0), RL(0.0), RL(0.0));
+	const bool edge_possible = !(dot1 + EPS > RL(1.000000000001) || dot2 + EPS > RL(1.000000000001));
 	if (edge_possible) {
 		V3 s1 = vert(h1, sup1), s2 = vert(h2, sup2);
 		const float nx = (float)normal.x, ny = (float)normal.y, nz = (float)normal.z;
@@ -626,7 +626,7 @@ RP_HD void manifold_select(const S& h1, const S& h2, V3 normal, int* status, Fac
 					if (!degenerate && score < best_score - 1e-3f) continue;
 					V3 cn = normalize(cross(edge1, edge2));
 					V3 cni = zero_minus(cn);
-					double t = dot(cn, normal);
+					real t = dot(cn, normal);
 					if (t > best) {
 						best = t; e1n = h1.v2n_idx[i]; e2n = h2.v2n_idx[j]; edge_normal = cn;
 					}
@@ -638,7 +638,7 @@ RP_HD void manifold_select(const S& h1, const S& h2, V3 normal, int* status, Fac
 			}
 		}
 	}
-	double dote = dot(edge_normal, normal);
+	real dote = dot(edge_normal, normal);
 	if (edge_possible && dote > dot1 + EPS && dote > dot2 + EPS) {
 		V3 p1 = vert(h1, sup1);
 		V3 d1 = sub(vert(h1, e1n), p1);
@@ -719,17 +719,17 @@ RP_HD int manifold_clip(const S& h1, const S& h2, V3 normal, C& cs, int* status,
 // one candidate point of the clipped polygon (clipping.cpp:322-338): its penetration along the normal; a contact if negative
 RP_HD bool manifold_point(V3 p, V3 rp_normal, V3 rp_point, bool ref1, V3 normal, V3* p1, V3* p2) {
 	// get_closest_point_polygon (clipping.cpp:115-119)
-	double dd = dot(scale(-1.0, rp_normal), rp_point);
+	real dd = dot(scale(-RL(1.0), rp_normal), rp_point);
 	V3 closest = sub(p, scale(dot(rp_normal, p) + dd, rp_normal));
 	V3 diff = sub(p, closest);
 	if (ref1) {
-		double pen = dot(diff, normal);
-		if (!(pen < 0.0)) return false;
+		real pen = dot(diff, normal);
+		if (!(pen < RL(0.0))) return false;
 		*p1 = sub(p, scale(pen, normal));
 		*p2 = p;
 	} else {
-		double pen = -dot(diff, normal);
-		if (!(pen < 0.0)) return false;
+		real pen = -dot(diff, normal);
+		if (!(pen < RL(0.0))) return false;
 		*p1 = p;
 		*p2 = add(p, scale(pen, normal));
 	}
@@ -761,7 +761,7 @@ RP_HD void manifold_hull_hull(const Shape& h1, const Shape& h2, V3 normal, ClipS
 // collider_get_contacts (collider.cpp:523-558) + clipping_get_contact_manifold (clipping.cpp:343-371) for one collider
 // pair whose GJK verdict is already known to be "colliding" (hull involved) -- see narrow_pair below for the front half.
 template <class Sink>
-RP_HD void manifold(const Shape& A, const Shape& B, V3 normal, double depth, ClipScratch& cs, int* status, Sink& sink, int sup1_known = -1,
+RP_HD void manifold(const Shape& A, const Shape& B, V3 normal, real depth, ClipScratch& cs, int* status, Sink& sink, int sup1_known = -1,
 	int sup2_known = -1) {
 	if (A.type == SHAPE_SPHERE) {
 		V3 p = support(A, normal);
@@ -778,7 +778,7 @@ RP_HD void manifold(const Shape& A, const Shape& B, V3 normal, double depth, Cli
 // shared-memory stores; the CPU restatement calls these, so the rerun logic is checked against the compiled reference too).
 // `reruns` (optional) counts the pairs that needed the second tier.
 template <class SA, class SB, class Small, class Full>
-RP_HD bool epa_tiered(const SA& A, const SB& B, const Simplex& s, Small& small, Full& full, V3* normal_out, double* depth_out, int* status,
+RP_HD bool epa_tiered(const SA& A, const SB& B, const Simplex& s, Small& small, Full& full, V3* normal_out, real* depth_out, int* status,
 	int* reruns, int* sup_a = 0, int* sup_b = 0) {
 	int r = epa_run(A, B, s, small, normal_out, depth_out, status, 0, sup_a, sup_b);
 	if (r == EPA_OVERFLOW) {
@@ -788,7 +788,7 @@ RP_HD bool epa_tiered(const SA& A, const SB& B, const Simplex& s, Small& small, 
 	return r == EPA_DONE;
 }
 template <class Small, class Full, class Sink>
-RP_HD void manifold_tiered(const Shape& A, const Shape& B, V3 normal, double depth, Small& small, Full& full, int* status, Sink& sink,
+RP_HD void manifold_tiered(const Shape& A, const Shape& B, V3 normal, real depth, Small& small, Full& full, int* status, Sink& sink,
 	int* reruns, int sup1_known = -1, int sup2_known = -1) {
 	if (A.type == SHAPE_SPHERE || B.type == SHAPE_SPHERE) {
 		manifold(A, B, normal, depth, full, status, sink);
@@ -805,13 +805,13 @@ RP_HD void manifold_tiered(const Shape& A, const Shape& B, V3 normal, double dep
 }
 
 // sphere-sphere analytic test (collider.cpp:530-542): squared distance and radius sum are float (quirk q6)
-RP_HD bool sphere_sphere(const Shape& A, const Shape& B, V3* normal, double* depth) {
+RP_HD bool sphere_sphere(const Shape& A, const Shape& B, V3* normal, real* depth) {
 	V3 dv = sub(A.center, B.center);
 	float dist2 = (float)dot(dv, dv);
 	float min_dist = A.radius + B.radius;
 	if (dist2 < (min_dist * min_dist)) {
 		*normal = normalize(sub(B.center, A.center));
-		*depth = (double)(min_dist - sqrtf(dist2));
+		*depth = (real)(min_dist - sqrtf(dist2));
 		return true;
 	}
 	return false;

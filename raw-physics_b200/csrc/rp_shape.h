@@ -51,8 +51,8 @@ struct Shape {
 	V3 center;                // sphere centre (collider.cpp:433)
 	// transformed vertices / (re-normalised) face normals, addressed as base[i * stride + c * cstride] so the same code
 	// reads the AoS arrays in global memory (stride 3, cstride 1) and thread-interleaved copies staged in shared memory
-	const double* vp; int vs, vcs;
-	const double* np; int ns, ncs;
+	const real* vp; int vs, vcs;
+	const real* np; int ns, ncs;
 	int nv, nf;
 	const int* face_ptr; const int* face_idx;
 	const int* v2f_ptr; const int* v2f_idx;
@@ -64,15 +64,15 @@ RP_HD Shape make_shape(const HullPool& pool, const ColliderDesc& c, const V3* wo
 	Shape s;
 	s.type = c.type;
 	s.radius = c.radius;
-	s.vp = (const double*)(world_tv + c.tv0); s.vs = 3; s.vcs = 1;
-	s.np = (const double*)(world_tn + c.tn0); s.ns = 3; s.ncs = 1;
+	s.vp = (const real*)(world_tv + c.tv0); s.vs = 3; s.vcs = 1;
+	s.np = (const real*)(world_tn + c.tn0); s.ns = 3; s.ncs = 1;
 	if (c.type == SHAPE_SPHERE) {
 		s.center = world_tv[c.tv0];
 		s.nv = 0; s.nf = 0;
 		s.face_ptr = s.face_idx = s.v2f_ptr = s.v2f_idx = s.v2n_ptr = s.v2n_idx = s.f2n_ptr = s.f2n_idx = 0;
 	} else {
 		const HullTopo h = pool.hulls[c.hull];
-		s.center = v3(0.0, 0.0, 0.0);
+		s.center = v3(RL(0.0), RL(0.0), RL(0.0));
 		s.nv = h.nv; s.nf = h.nf;
 		s.face_ptr = pool.face_ptr + h.fptr0; s.face_idx = pool.face_idx;
 		s.v2f_ptr = pool.v2f_ptr + h.v2f0; s.v2f_idx = pool.v2f_idx;
@@ -83,7 +83,7 @@ RP_HD Shape make_shape(const HullPool& pool, const ColliderDesc& c, const V3* wo
 }
 
 RP_HD V3 vert(const Shape& s, int i) {
-	const double* p = s.vp + (size_t)i * s.vs;
+	const real* p = s.vp + (size_t)i * s.vs;
 	return v3(p[0], p[s.vcs], p[2 * s.vcs]);
 }
 // A shape whose vertices were staged into a thread-interleaved block of NT columns (k_gjk / k_epa): the strides are
@@ -97,15 +97,15 @@ struct StagedShape : Shape {
 };
 template <int NT>
 RP_HD V3 vert(const StagedShape<NT>& s, int i) {
-	const double* p = s.vp + i * (3 * NT);
+	const real* p = s.vp + i * (3 * NT);
 	return v3(p[0], p[NT], p[2 * NT]);
 }
 RP_HD V3 fnormal_stored(const Shape& s, int i) {
-	const double* p = s.np + (size_t)i * s.ns;
+	const real* p = s.np + (size_t)i * s.ns;
 	return v3(p[0], p[s.ncs], p[2 * s.ncs]);
 }
 RP_HD V3 fnormal(const Shape& s, int i) {
-	const double* p = s.np + (size_t)i * s.ns;
+	const real* p = s.np + (size_t)i * s.ns;
 	return v3(p[0], p[s.ncs], p[2 * s.ncs]);
 }
 
@@ -113,18 +113,18 @@ RP_HD V3 fnormal(const Shape& s, int i) {
 // (util.cpp:60-74 with quaternion_get_matrix, quaternion.cpp:107): every entry keeps its four-term sum, including the
 // products with the matrices' structural zeros, so signed zeros come out as in the reference.
 struct Pose34 {
-	double m[3][4];
+	real m[3][4];
 };
 
 RP_HD Pose34 model_matrix(Q4 q, V3 t) {
 	M3 R = to_mat3(q);
-	double T[3][4] = {{1.0, 0.0, 0.0, t.x}, {0.0, 1.0, 0.0, t.y}, {0.0, 0.0, 1.0, t.z}};
+	real T[3][4] = {{RL(1.0), RL(0.0), RL(0.0), t.x}, {RL(0.0), RL(1.0), RL(0.0), t.y}, {RL(0.0), RL(0.0), RL(1.0), t.z}};
 	Pose34 M;
 #pragma unroll
 	for (int i = 0; i < 3; ++i) {
 #pragma unroll
-		for (int j = 0; j < 3; ++j) M.m[i][j] = T[i][0] * R.m[0][j] + T[i][1] * R.m[1][j] + T[i][2] * R.m[2][j] + T[i][3] * 0.0;
-		M.m[i][3] = T[i][0] * 0.0 + T[i][1] * 0.0 + T[i][2] * 0.0 + T[i][3] * 1.0;
+		for (int j = 0; j < 3; ++j) M.m[i][j] = T[i][0] * R.m[0][j] + T[i][1] * R.m[1][j] + T[i][2] * R.m[2][j] + T[i][3] * RL(0.0);
+		M.m[i][3] = T[i][0] * RL(0.0) + T[i][1] * RL(0.0) + T[i][2] * RL(0.0) + T[i][3] * RL(1.0);
 	}
 	return M;
 }
@@ -132,9 +132,9 @@ RP_HD Pose34 model_matrix(Q4 q, V3 t) {
 // collider_update, vertex half (collider.cpp:414-422): gm_mat4_multiply_vec4(M, (v,1)); the following scale by
 // 1/w is the identity because row 3 of M is (+0,+0,+0,1) and so w == 1 exactly.
 RP_HD V3 transform_point(const Pose34& M, V3 v) {
-	return v3(v.x * M.m[0][0] + v.y * M.m[0][1] + v.z * M.m[0][2] + 1.0 * M.m[0][3],
-	          v.x * M.m[1][0] + v.y * M.m[1][1] + v.z * M.m[1][2] + 1.0 * M.m[1][3],
-	          v.x * M.m[2][0] + v.y * M.m[2][1] + v.z * M.m[2][2] + 1.0 * M.m[2][3]);
+	return v3(v.x * M.m[0][0] + v.y * M.m[0][1] + v.z * M.m[0][2] + RL(1.0) * M.m[0][3],
+	          v.x * M.m[1][0] + v.y * M.m[1][1] + v.z * M.m[1][2] + RL(1.0) * M.m[1][3],
+	          v.x * M.m[2][0] + v.y * M.m[2][1] + v.z * M.m[2][2] + RL(1.0) * M.m[2][3]);
 }
 // collider_update, normal half (collider.cpp:425-429): rotate then RE-NORMALISE (not a bitwise no-op)
 RP_HD V3 transform_normal(const Pose34& M, V3 n) {
@@ -174,10 +174,10 @@ RP_HD V3 fnormal(const PoseShape& s, int i) {
 template <class S>
 RP_HD int support_index(const S& s, V3 d) {
 	int best = 0;
-	double best_dot = -1.7976931348623157e308;
+	real best_dot = -RL(RP_REAL_MAX);
 #pragma unroll 4
 	for (int i = 0; i < s.nv; ++i) {
-		double t = dot(vert(s, i), d);
+		real t = dot(vert(s, i), d);
 		if (t > best_dot) {
 			best = i;
 			best_dot = t;
@@ -189,13 +189,13 @@ RP_HD int support_index(const S& s, V3 d) {
 template <class S>
 RP_HD V3 support(const S& s, V3 d) {
 	if (s.type == SHAPE_HULL) return vert(s, support_index(s, d));
-	return add(s.center, scale((double)s.radius, normalize(d)));
+	return add(s.center, scale((real)s.radius, normalize(d)));
 }
 // support_point_of_minkowski_difference (support.cpp:34-39)
 template <class SA, class SB>
 RP_HD V3 support_minkowski(const SA& a, const SB& b, V3 d) {
 	V3 s1 = support(a, d);
-	V3 s2 = support(b, scale(-1.0, d));
+	V3 s2 = support(b, scale(-RL(1.0), d));
 	return sub(s1, s2);
 }
 // the same, also telling which hull vertices were chosen (-1 for a sphere): EPA's last support call is made along the normal it
@@ -212,7 +212,7 @@ RP_HD V3 support_minkowski_idx(const SA& a, const SB& b, V3 d, int* ia, int* ib)
 		*ia = -1;
 		s1 = support(a, d);
 	}
-	const V3 nd = scale(-1.0, d);
+	const V3 nd = scale(-RL(1.0), d);
 	if (b.type == SHAPE_HULL) {
 		*ib = support_index(b, nd);
 		s2 = vert(b, *ib);

@@ -12,18 +12,18 @@
 
 namespace rp {
 
-#define RP_PI_F 3.14159265358979  // include/gm.h:8
+#define RP_PI_F RL(3.14159265358979)  // include/gm.h:8
 
 struct Body {
 	V3 x; Q4 q;          // world_position, world_rotation
 	V3 v; V3 w;          // linear_velocity, angular_velocity
 	V3 px; Q4 pq;        // previous_world_position / rotation
 	V3 pv; V3 pw;        // previous_linear_velocity / angular_velocity
-	double inv_mass;
+	real inv_mass;
 	M3 inertia, inv_inertia;  // body-frame tensors (entity.h:32-33)
 	const M3* inv_inertia_p;  // device code: where inv_inertia lives in the template (read when needed, see inv_inertia_of)
-	double mu_s, mu_d, rest;
-	double ii_bound;     // an upper bound of the largest eigenvalue of inv_inertia (its infinity norm; tensor_bound)
+	real mu_s, mu_d, rest;
+	real ii_bound;     // an upper bound of the largest eigenvalue of inv_inertia (its infinity norm; tensor_bound)
 	int fixed, active;
 };
 
@@ -47,10 +47,10 @@ RP_HD const M3& inv_inertia_of(const Body& b) { return b.inv_inertia; }
 #endif
 
 // infinity norm of a symmetric (or any) 3x3 tensor: >= its spectral radius
-RP_HD double tensor_bound(const M3& a) {
-	double best = 0.0;
+RP_HD real tensor_bound(const M3& a) {
+	real best = RL(0.0);
 	for (int i = 0; i < 3; ++i) {
-		double row = fabs(a.m[i][0]) + fabs(a.m[i][1]) + fabs(a.m[i][2]);
+		real row = fabs(a.m[i][0]) + fabs(a.m[i][1]) + fabs(a.m[i][2]);
 		if (row > best) best = row;
 	}
 	return best;
@@ -58,7 +58,7 @@ RP_HD double tensor_bound(const M3& a) {
 
 // ------------------------------------------------------------------------------------------------------- integration
 // pbd.cpp:537-577 for one body. `force`/`torque` are the sums of calculate_external_force/torque (physics_util.cpp:5-23).
-RP_HD void integrate(Body& b, double h, V3 force, V3 torque) {
+RP_HD void integrate(Body& b, real h, V3 force, V3 torque) {
 	b.px = b.x;
 	b.pq = b.q;
 	if (b.fixed || !b.active) return;
@@ -69,29 +69,29 @@ RP_HD void integrate(Body& b, double h, V3 force, V3 torque) {
 	b.w = add(b.w, scale(h, mul(iinv, sub(torque, cross(b.w, mul(iw, b.w))))));
 #if defined(RP_EXACT_QUATERNIONS)
 	// the reference built without USE_QUATERNIONS_LINEARIZED_FORMULAS (pbd.cpp:16, :570-575): rotation by |w| h about w
-	const double angle = length(b.w) * h;
+	const real angle = length(b.w) * h;
 	const Q4 change = quat_axis_angle(normalize(b.w), angle);
 	b.q = normalize(mul(change, b.q));
 #else
-	Q4 aux = q4(b.w.x, b.w.y, b.w.z, 0.0);
+	Q4 aux = q4(b.w.x, b.w.y, b.w.z, RL(0.0));
 	Q4 dq = mul(aux, b.q);
-	b.q.x = b.q.x + h * 0.5 * dq.x;
-	b.q.y = b.q.y + h * 0.5 * dq.y;
-	b.q.z = b.q.z + h * 0.5 * dq.z;
-	b.q.w = b.q.w + h * 0.5 * dq.w;
+	b.q.x = b.q.x + h * RL(0.5) * dq.x;
+	b.q.y = b.q.y + h * RL(0.5) * dq.y;
+	b.q.z = b.q.z + h * RL(0.5) * dq.z;
+	b.q.w = b.q.w + h * RL(0.5) * dq.w;
 	b.q = normalize(b.q);
 #endif
 }
 
 // pbd.cpp:623-643 for one body
-RP_HD void derive_velocity(Body& b, double h) {
+RP_HD void derive_velocity(Body& b, real h) {
 	if (b.fixed || !b.active) return;
 	b.pv = b.v;
 	b.pw = b.w;
-	b.v = scale(1.0 / h, sub(b.x, b.px));
+	b.v = scale(RL(1.0) / h, sub(b.x, b.px));
 	Q4 dq = mul(b.q, conj(b.pq));
-	if (dq.w >= 0.0) b.w = scale(2.0 / h, v3(dq.x, dq.y, dq.z));
-	else b.w = scale(-2.0 / h, v3(dq.x, dq.y, dq.z));
+	if (dq.w >= RL(0.0)) b.w = scale(RL(2.0) / h, v3(dq.x, dq.y, dq.z));
+	else b.w = scale(-RL(2.0) / h, v3(dq.x, dq.y, dq.z));
 }
 
 // ---------------------------------------------------------------------------------------------- positional primitive
@@ -110,7 +110,7 @@ RP_HD M3 zero_m3() {
 #pragma unroll
 	for (int i = 0; i < 3; ++i) {
 #pragma unroll
-		for (int j = 0; j < 3; ++j) z.m[i][j] = 0.0;
+		for (int j = 0; j < 3; ++j) z.m[i][j] = RL(0.0);
 	}
 	return z;
 }
@@ -124,52 +124,52 @@ RP_HD PosPre pos_pre(const Body& b1, const Body& b2, V3 r1_lc, V3 r2_lc) {
 	return p;
 }
 // generalised inverse mass of one body along n at arm r (pbd_base_constraints.cpp:38-39, pbd.cpp:697-698)
-RP_HD double inv_mass_along(const Body& b, V3 r, const M3& ii, V3 n) {
-	if (b.fixed) return 0.0;
+RP_HD real inv_mass_along(const Body& b, V3 r, const M3& ii, V3 n) {
+	if (b.fixed) return RL(0.0);
 	return b.inv_mass + dot(cross(r, n), mul(ii, cross(r, n)));
 }
 
 // positional_constraint_get_delta_lambda (pbd_base_constraints.cpp:17-47)
-RP_HD double pos_delta_lambda(const PosPre& p, const Body& b1, const Body& b2, double h, double compliance, double lambda, V3 dx,
+RP_HD real pos_delta_lambda(const PosPre& p, const Body& b1, const Body& b2, real h, real compliance, real lambda, V3 dx,
 	int* status) {
-	double c = length(dx);
-	if (c <= 1e-50) return 0.0;
+	real c = length(dx);
+	if (c <= RL(1e-50)) return RL(0.0);
 	V3 n = divide(dx, c);
-	double w1 = inv_mass_along(b1, p.r1, p.ii1, n);
-	double w2 = inv_mass_along(b2, p.r2, p.ii2, n);
-	if (!(w1 + w2 != 0.0)) *status |= ST_SOLVER_SINGULAR;  // the reference asserts
-	double til = fdiv(compliance, h * h);
+	real w1 = inv_mass_along(b1, p.r1, p.ii1, n);
+	real w2 = inv_mass_along(b2, p.r2, p.ii2, n);
+	if (!(w1 + w2 != RL(0.0))) *status |= ST_SOLVER_SINGULAR;  // the reference asserts
+	real til = fdiv(compliance, h * h);
 	return (-c - til * lambda) / (w1 + w2 + til);
 }
 
 // quaternion update shared by both apply routines (pbd_base_constraints.cpp:87-103, :189-207): q +/- 0.5 * ((aux,0) (x) q)
-RP_HD void apply_rotation(Body& b, V3 aux, double sign_half) {
+RP_HD void apply_rotation(Body& b, V3 aux, real sign_half) {
 #if defined(RP_EXACT_QUATERNIONS)
 	// the non-linearised branch (pbd_base_constraints.cpp:105-121, :209-225): rotation by +-|aux| about aux
-	const double angle = sign_half > 0.0 ? length(aux) : -length(aux);
+	const real angle = sign_half > RL(0.0) ? length(aux) : -length(aux);
 	const Q4 change = quat_axis_angle(normalize(aux), angle);
 	b.q = normalize(mul(change, b.q));
 	return;
 #endif
-	Q4 d = mul(q4(aux.x, aux.y, aux.z, 0.0), b.q);
-	if (sign_half > 0.0) {
-		b.q.x = b.q.x + 0.5 * d.x; b.q.y = b.q.y + 0.5 * d.y; b.q.z = b.q.z + 0.5 * d.z; b.q.w = b.q.w + 0.5 * d.w;
+	Q4 d = mul(q4(aux.x, aux.y, aux.z, RL(0.0)), b.q);
+	if (sign_half > RL(0.0)) {
+		b.q.x = b.q.x + RL(0.5) * d.x; b.q.y = b.q.y + RL(0.5) * d.y; b.q.z = b.q.z + RL(0.5) * d.z; b.q.w = b.q.w + RL(0.5) * d.w;
 	} else {
-		b.q.x = b.q.x - 0.5 * d.x; b.q.y = b.q.y - 0.5 * d.y; b.q.z = b.q.z - 0.5 * d.z; b.q.w = b.q.w - 0.5 * d.w;
+		b.q.x = b.q.x - RL(0.5) * d.x; b.q.y = b.q.y - RL(0.5) * d.y; b.q.z = b.q.z - RL(0.5) * d.z; b.q.w = b.q.w - RL(0.5) * d.w;
 	}
 	b.q = normalize(b.q);
 }
 
 // positional_constraint_apply (pbd_base_constraints.cpp:50-123)
-RP_HD void pos_apply(const PosPre& p, Body& b1, Body& b2, double dl, V3 dx) {
-	double c = length(dx);
-	if (c <= 1e-50) return;
+RP_HD void pos_apply(const PosPre& p, Body& b1, Body& b2, real dl, V3 dx) {
+	real c = length(dx);
+	if (c <= RL(1e-50)) return;
 	V3 n = divide(dx, c);
 	V3 imp = scale(dl, n);
 	if (!b1.fixed) b1.x = add(b1.x, scale(b1.inv_mass, imp));
 	if (!b2.fixed) b2.x = add(b2.x, scale(-b2.inv_mass, imp));
-	if (!b1.fixed) apply_rotation(b1, mul(p.ii1, cross(p.r1, imp)), 1.0);
-	if (!b2.fixed) apply_rotation(b2, mul(p.ii2, cross(p.r2, imp)), -1.0);
+	if (!b1.fixed) apply_rotation(b1, mul(p.ii1, cross(p.r1, imp)), RL(1.0));
+	if (!b2.fixed) apply_rotation(b2, mul(p.ii2, cross(p.r2, imp)), -RL(1.0));
 }
 
 // ------------------------------------------------------------------------------------------------- angular primitive
@@ -184,31 +184,31 @@ RP_HD AngPre ang_pre(const Body& b1, const Body& b2) {
 	return a;
 }
 // angular_constraint_get_delta_lambda (pbd_base_constraints.cpp:133-161)
-RP_HD double ang_delta_lambda(const AngPre& a, double h, double compliance, double lambda, V3 dq, int* status) {
-	double theta = length(dq);
-	if (theta <= 1e-50) return 0.0;
+RP_HD real ang_delta_lambda(const AngPre& a, real h, real compliance, real lambda, V3 dq, int* status) {
+	real theta = length(dq);
+	if (theta <= RL(1e-50)) return RL(0.0);
 	V3 n = divide(dq, theta);
 	// a fixed body's term n . (0 n) is a signed zero; w1 + w2 is then the other body's term (or +-0, flagged below)
-	double w1 = dot(n, mul(a.ii1, n));
-	double w2 = dot(n, mul(a.ii2, n));
-	if (!(w1 + w2 != 0.0)) *status |= ST_SOLVER_SINGULAR;
-	double til = fdiv(compliance, h * h);
+	real w1 = dot(n, mul(a.ii1, n));
+	real w2 = dot(n, mul(a.ii2, n));
+	if (!(w1 + w2 != RL(0.0))) *status |= ST_SOLVER_SINGULAR;
+	real til = fdiv(compliance, h * h);
 	return (-theta - til * lambda) / (w1 + w2 + til);
 }
 // angular_constraint_apply (pbd_base_constraints.cpp:164-227)
-RP_HD void ang_apply(const AngPre& a, Body& b1, Body& b2, double dl, V3 dq) {
-	double theta = length(dq);
-	if (theta <= 1e-50) return;
+RP_HD void ang_apply(const AngPre& a, Body& b1, Body& b2, real dl, V3 dq) {
+	real theta = length(dq);
+	if (theta <= RL(1e-50)) return;
 	V3 n = divide(dq, theta);
 	V3 imp = scale(-dl, n);
-	if (!b1.fixed) apply_rotation(b1, mul(a.ii1, imp), 1.0);
-	if (!b2.fixed) apply_rotation(b2, mul(a.ii2, imp), -1.0);
+	if (!b1.fixed) apply_rotation(b1, mul(a.ii1, imp), RL(1.0));
+	if (!b2.fixed) apply_rotation(b2, mul(a.ii2, imp), -RL(1.0));
 }
 
 // ------------------------------------------------------------------------------------------------------ contact solve
 struct Contact {  // Collision_Constraint minus the normal, which is shared by a collider pair's whole manifold
 	V3 r1_lc, r2_lc;
-	double lambda_n, lambda_t;
+	real lambda_n, lambda_t;
 };
 
 // clipping_contact_to_collision_constraint (pbd.cpp:408-424)
@@ -216,8 +216,8 @@ RP_HD Contact make_contact(const Body& b1, const Body& b2, V3 p1, V3 p2) {
 	Contact c;
 	c.r1_lc = rotate(conj(b1.q), sub(p1, b1.x));
 	c.r2_lc = rotate(conj(b2.q), sub(p2, b2.x));
-	c.lambda_n = 0.0;
-	c.lambda_t = 0.0;
+	c.lambda_n = RL(0.0);
+	c.lambda_t = RL(0.0);
 	return c;
 }
 
@@ -231,14 +231,14 @@ struct PrevInBody {
 	RP_HD void operator()(Body&, Body&) const {}
 };
 template <class PrevPose>
-RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, int* status, const PrevPose& prev) {
+RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, real h, int* status, const PrevPose& prev) {
 	PosPre p = pos_pre(b1, b2, c.r1_lc, c.r2_lc);
 	V3 p1 = add(b1.x, p.r1);
 	V3 p2 = add(b2.x, p.r2);
-	double d = dot(sub(p1, p2), normal);
-	if (d > 0.0) {
+	real d = dot(sub(p1, p2), normal);
+	if (d > RL(0.0)) {
 		V3 dx = scale(d, normal);
-		double dl = pos_delta_lambda(p, b1, b2, h, 0.0, c.lambda_n, dx, status);
+		real dl = pos_delta_lambda(p, b1, b2, h, RL(0.0), c.lambda_n, dx, status);
 		pos_apply(p, b1, b2, dl, dx);
 		c.lambda_n += dl;
 
@@ -252,12 +252,12 @@ RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, in
 		// error of either side -- the floating-point test cannot come out true, and nothing else in the skipped code
 		// has an effect (lambda_t and the bodies are only written inside the branch).
 		{
-			const double wub = (b1.fixed ? 0.0 : b1.inv_mass + dot(c.r1_lc, c.r1_lc) * b1.ii_bound) +
-			                   (b2.fixed ? 0.0 : b2.inv_mass + dot(c.r2_lc, c.r2_lc) * b2.ii_bound);
-			const double mu_ln = ((b1.mu_s + b2.mu_s) / 2.0) * c.lambda_n;
-			if (wub > 0.0) {
-				const double step = length(dx) / wub;
-				const double margin = 1e-6 * (fabs(c.lambda_t) + step + fabs(mu_ln));
+			const real wub = (b1.fixed ? RL(0.0) : b1.inv_mass + dot(c.r1_lc, c.r1_lc) * b1.ii_bound) +
+			                   (b2.fixed ? RL(0.0) : b2.inv_mass + dot(c.r2_lc, c.r2_lc) * b2.ii_bound);
+			const real mu_ln = ((b1.mu_s + b2.mu_s) / RL(2.0)) * c.lambda_n;
+			if (wub > RL(0.0)) {
+				const real step = length(dx) / wub;
+				const real margin = RL(1e-6) * (fabs(c.lambda_t) + step + fabs(mu_ln));
 				if (c.lambda_t - step + margin < mu_ln) {
 #if defined(RP_COUNT_FRICTION) && !defined(__CUDA_ARCH__)
 					++g_friction_skipped;
@@ -273,10 +273,10 @@ RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, in
 		p = pos_pre(b1, b2, c.r1_lc, c.r2_lc);
 		p1 = add(b1.x, p.r1);
 		p2 = add(b2.x, p.r2);
-		dl = pos_delta_lambda(p, b1, b2, h, 0.0, c.lambda_t, dx, status);
-		double mu = (b1.mu_s + b2.mu_s) / 2.0;
-		double lambda_n = c.lambda_n;
-		double lambda_t = c.lambda_t + dl;
+		dl = pos_delta_lambda(p, b1, b2, h, RL(0.0), c.lambda_t, dx, status);
+		real mu = (b1.mu_s + b2.mu_s) / RL(2.0);
+		real lambda_n = c.lambda_n;
+		real lambda_t = c.lambda_t + dl;
 		if (lambda_t > mu * lambda_n) {
 			prev(b1, b2);
 			V3 p1t = add(b1.px, rotate(b1.pq, c.r1_lc));
@@ -292,7 +292,7 @@ RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, in
 	}
 }
 
-RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, int* status) {
+RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, real h, int* status) {
 	solve_contact(c, normal, b1, b2, h, status, PrevInBody());
 }
 
@@ -302,34 +302,34 @@ RP_HD void solve_contact(Contact& c, V3 normal, Body& b1, Body& b2, double h, in
 // values per contact (pbd.cpp:651).
 RP_HD AngPre vel_tensors(const Body& b1, const Body& b2) { return ang_pre(b1, b2); }
 
-RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, double h, const AngPre& t) {
+RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, real h, const AngPre& t) {
 	PosPre p;
 	p.r1 = rotate(b1.q, c.r1_lc);
 	p.r2 = rotate(b2.q, c.r2_lc);
 	p.ii1 = t.ii1;
 	p.ii2 = t.ii2;
 	V3 v = sub(add(b1.v, cross(b1.w, p.r1)), add(b2.v, cross(b2.w, p.r2)));
-	double vn = dot(n, v);
+	real vn = dot(n, v);
 	V3 vt = sub(v, scale(vn, n));
-	V3 dv = v3(0.0, 0.0, 0.0);
-	double mu = (b1.mu_d + b2.mu_d) / 2.0;
-	double fn = fdiv(c.lambda_n, h);
-	double fact = RP_MINF(mu * fabs(fn), length(vt));
+	V3 dv = v3(RL(0.0), RL(0.0), RL(0.0));
+	real mu = (b1.mu_d + b2.mu_d) / RL(2.0);
+	real fn = fdiv(c.lambda_n, h);
+	real fact = RP_MINF(mu * fabs(fn), length(vt));
 	dv = add(dv, scale(-fact, normalize(vt)));
-	double e = b1.rest * b2.rest;
-	if (e == 0.0) {
+	real e = b1.rest * b2.rest;
+	if (e == RL(0.0)) {
 		// -e * vn_til is a signed zero (or NaN), which the reference's MIN(x, 0) turns into +0.0 either way: the previous
 		// velocities are not needed at all (callers may leave pv / pw unloaded when either restitution is zero)
-		fact = -vn + 0.0;
+		fact = -vn + RL(0.0);
 	} else {
 		V3 vtil = sub(add(b1.pv, cross(b1.pw, p.r1)), add(b2.pv, cross(b2.pw, p.r2)));
-		double vn_til = dot(n, vtil);
-		fact = -vn + RP_MINF(-e * vn_til, 0.0);
+		real vn_til = dot(n, vtil);
+		fact = -vn + RP_MINF(-e * vn_til, RL(0.0));
 	}
 	dv = add(dv, scale(fact, n));
-	double w1 = inv_mass_along(b1, p.r1, p.ii1, n);
-	double w2 = inv_mass_along(b2, p.r2, p.ii2, n);
-	V3 imp = scale(1.0 / (w1 + w2), dv);
+	real w1 = inv_mass_along(b1, p.r1, p.ii1, n);
+	real w2 = inv_mass_along(b2, p.r2, p.ii2, n);
+	V3 imp = scale(RL(1.0) / (w1 + w2), dv);
 	if (!b1.fixed) {
 		b1.v = add(b1.v, scale(b1.inv_mass, imp));
 		b1.w = add(b1.w, mul(p.ii1, cross(p.r1, imp)));
@@ -339,7 +339,7 @@ RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, do
 		b2.w = add(b2.w, zero_minus(mul(p.ii2, cross(p.r2, imp))));
 	}
 }
-RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, double h) {
+RP_HD void solve_contact_velocity(const Contact& c, V3 n, Body& b1, Body& b2, real h) {
 	solve_contact_velocity(c, n, b1, b2, h, vel_tensors(b1, b2));
 }
 
@@ -353,21 +353,21 @@ struct Joint {  // the external Constraint union (pbd.h:22-91), flattened
 	int axis[4];            // hinge: e1_aligned, e2_aligned, e1_limit, e2_limit; spherical: e1_swing, e2_swing, e1_twist, e2_twist
 	V3 r1_lc, r2_lc;
 	V3 distance;            // positional
-	double compliance;
-	double lower, upper;    // hinge limits / spherical swing limits
-	double lower2, upper2;  // spherical twist limits
+	real compliance;
+	real lower, upper;    // hinge limits / spherical swing limits
+	real lower2, upper2;  // spherical twist limits
 };
 
 struct JointLambda {  // reset to zero every substep (copy_constraints, pbd.cpp:426-462)
-	double a, b, c;
+	real a, b, c;
 };
 
 // limit_angle (pbd.cpp:175-217)
-RP_HD bool limit_angle(V3 n, V3 n1, V3 n2, double alpha, double beta, V3* dq) {
-	double phi = asin(dot(cross(n1, n2), n));
-	if (dot(n1, n2) < 0.0) phi = RP_PI_F - phi;
-	if (phi > RP_PI_F) phi = phi - 2.0 * RP_PI_F;
-	if (phi < -RP_PI_F) phi = phi + 2.0 * RP_PI_F;
+RP_HD bool limit_angle(V3 n, V3 n1, V3 n2, real alpha, real beta, V3* dq) {
+	real phi = asin(dot(cross(n1, n2), n));
+	if (dot(n1, n2) < RL(0.0)) phi = RP_PI_F - phi;
+	if (phi > RP_PI_F) phi = phi - RL(2.0) * RP_PI_F;
+	if (phi < -RP_PI_F) phi = phi + RL(2.0) * RP_PI_F;
 	if (phi < alpha || phi > beta) {
 		phi = ((phi) > (beta)) ? (beta) : (((phi) < (alpha)) ? (alpha) : (phi));  // CLAMP (common.h:22)
 		Q4 rot = quat_axis_angle(n, phi);
@@ -379,18 +379,18 @@ RP_HD bool limit_angle(V3 n, V3 n1, V3 n2, double alpha, double beta, V3* dq) {
 }
 
 // solve_constraint for the four external types (pbd.cpp:81-97, :156-173, :245-299, :301-379)
-RP_HD void solve_joint(const Joint& j, JointLambda& l, Body& b1, Body& b2, double h, int* status) {
+RP_HD void solve_joint(const Joint& j, JointLambda& l, Body& b1, Body& b2, real h, int* status) {
 	if (j.type == JOINT_POSITIONAL) {
 		V3 dx = sub(sub(b1.x, b2.x), j.distance);
 		PosPre p = pos_pre(b1, b2, j.r1_lc, j.r2_lc);
-		double dl = pos_delta_lambda(p, b1, b2, h, j.compliance, l.a, dx, status);
+		real dl = pos_delta_lambda(p, b1, b2, h, j.compliance, l.a, dx, status);
 		pos_apply(p, b1, b2, dl, dx);
 		l.a += dl;
 	} else if (j.type == JOINT_MUTUAL_ORIENTATION) {
 		AngPre a = ang_pre(b1, b2);
 		Q4 aux = mul(b1.q, conj(b2.q));
-		V3 dq = v3(2.0 * aux.x, 2.0 * aux.y, 2.0 * aux.z);
-		double dl = ang_delta_lambda(a, h, j.compliance, l.a, dq, status);
+		V3 dq = v3(RL(2.0) * aux.x, RL(2.0) * aux.y, RL(2.0) * aux.z);
+		real dl = ang_delta_lambda(a, h, j.compliance, l.a, dq, status);
 		ang_apply(a, b1, b2, dl, dq);
 		l.a += dl;
 	} else if (j.type == JOINT_HINGE) {
@@ -399,13 +399,13 @@ RP_HD void solve_joint(const Joint& j, JointLambda& l, Body& b1, Body& b2, doubl
 		V3 a1 = axis_world(b1.q, j.axis[0]);
 		V3 a2 = axis_world(b2.q, j.axis[1]);
 		V3 dq = cross(a1, a2);
-		double dl = ang_delta_lambda(a, h, j.compliance, l.a, dq, status);
+		real dl = ang_delta_lambda(a, h, j.compliance, l.a, dq, status);
 		ang_apply(a, b1, b2, dl, dq);
 		l.a += dl;
 
 		PosPre p = pos_pre(b1, b2, j.r1_lc, j.r2_lc);
 		V3 dx = sub(add(b1.x, p.r1), add(b2.x, p.r2));
-		dl = pos_delta_lambda(p, b1, b2, h, 0.0, l.b, dx, status);
+		dl = pos_delta_lambda(p, b1, b2, h, RL(0.0), l.b, dx, status);
 		pos_apply(p, b1, b2, dl, dx);
 		l.b += dl;
 
@@ -415,30 +415,30 @@ RP_HD void solve_joint(const Joint& j, JointLambda& l, Body& b1, Body& b2, doubl
 			V3 n = axis_world(b1.q, j.axis[0]);
 			if (limit_angle(n, n1, n2, j.lower, j.upper, &dq)) {
 				AngPre a2p = ang_pre(b1, b2);
-				double dl2 = ang_delta_lambda(a2p, h, 0.0, l.c, dq, status);
+				real dl2 = ang_delta_lambda(a2p, h, RL(0.0), l.c, dq, status);
 				ang_apply(a2p, b1, b2, dl2, dq);
 				l.c += dl2;
 			}
 		}
 	} else {
 		// spherical: l.a = lambda_pos, l.b = lambda_swing, l.c = lambda_twist
-		const double EPS = 1e-50;
+		const real EPS = RL(1e-50);
 		PosPre p = pos_pre(b1, b2, j.r1_lc, j.r2_lc);
 		V3 dx = sub(add(b1.x, p.r1), add(b2.x, p.r2));
-		double dl = pos_delta_lambda(p, b1, b2, h, 0.0, l.a, dx, status);
+		real dl = pos_delta_lambda(p, b1, b2, h, RL(0.0), l.a, dx, status);
 		pos_apply(p, b1, b2, dl, dx);
 		l.a += dl;
 
 		V3 n1 = axis_world(b1.q, j.axis[0]);
 		V3 n2 = axis_world(b2.q, j.axis[1]);
 		V3 n = cross(n1, n2);
-		double nl = length(n);
+		real nl = length(n);
 		if (nl > EPS) {
 			n = divide(n, nl);
 			V3 dq;
 			if (limit_angle(n, n1, n2, j.lower, j.upper, &dq)) {
 				AngPre a = ang_pre(b1, b2);
-				double d2 = ang_delta_lambda(a, h, 0.0, l.b, dq, status);
+				real d2 = ang_delta_lambda(a, h, RL(0.0), l.b, dq, status);
 				ang_apply(a, b1, b2, d2, dq);
 				l.b += d2;
 			}
@@ -453,14 +453,14 @@ RP_HD void solve_joint(const Joint& j, JointLambda& l, Body& b1, Body& b2, doubl
 			n = divide(n, nl);
 			n1 = sub(t1, scale(dot(n, t1), n));
 			n2 = sub(t2, scale(dot(n, t2), n));
-			double l1 = length(n1), l2 = length(n2);
+			real l1 = length(n1), l2 = length(n2);
 			if (l1 > EPS && l2 > EPS) {
 				n1 = divide(n1, l1);
 				n2 = divide(n2, l2);
 				V3 dq;
 				if (limit_angle(n, n1, n2, j.lower2, j.upper2, &dq)) {
 					AngPre a = ang_pre(b1, b2);
-					double d3 = ang_delta_lambda(a, h, 0.0, l.c, dq, status);
+					real d3 = ang_delta_lambda(a, h, RL(0.0), l.c, dq, status);
 					ang_apply(a, b1, b2, d3, dq);
 					l.c += d3;
 				}
