@@ -87,6 +87,12 @@ __device__ __forceinline__ DynRef dyn_ref(const DevView& d, int w, int b) {
 }
 __device__ __forceinline__ V3 ld3(const DynRef& r, int f) { return v3(r.p[f * r.s], r.p[(f + 1) * r.s], r.p[(f + 2) * r.s]); }
 __device__ __forceinline__ Q4 ld4(const DynRef& r, int f) { return q4(r.p[f * r.s], r.p[(f + 1) * r.s], r.p[(f + 2) * r.s], r.p[(f + 3) * r.s]); }
+// the same through L2 only (ld.global.cg): for state that units running on OTHER SMs write during the same launch (dataflow sweeps),
+// where a line cached in this SM's L1 by an earlier unit would be stale
+__device__ __forceinline__ V3 ld3cg(const DynRef& r, int f) { return v3(__ldcg(r.p + f * r.s), __ldcg(r.p + (f + 1) * r.s), __ldcg(r.p + (f + 2) * r.s)); }
+__device__ __forceinline__ Q4 ld4cg(const DynRef& r, int f) {
+	return q4(__ldcg(r.p + f * r.s), __ldcg(r.p + (f + 1) * r.s), __ldcg(r.p + (f + 2) * r.s), __ldcg(r.p + (f + 3) * r.s));
+}
 __device__ __forceinline__ void st3(const DynRef& r, int f, V3 v) { r.p[f * r.s] = v.x; r.p[(f + 1) * r.s] = v.y; r.p[(f + 2) * r.s] = v.z; }
 __device__ __forceinline__ void st4(const DynRef& r, int f, Q4 q) {
 	r.p[f * r.s] = q.x; r.p[(f + 1) * r.s] = q.y; r.p[(f + 2) * r.s] = q.z; r.p[(f + 3) * r.s] = q.w;
@@ -1731,9 +1737,15 @@ __device__ __forceinline__ void flow_prefix(const DevView& d, int levels) {
 		d.wl_pre[(size_t)(l1 + 1) * d.WS + w] = run;
 	}
 }
+// The counter is read with a RELAXED load and the state a unit then loads goes through L2 (ld3cg / ld4cg / __ldcg): an acquire
+// load (or fence) is LD + CCTL.IVALL on sm_100a -- it drops the SM's whole L1 on every poll, for every warp on the SM, although
+// the only lines that can be stale are the ones read through L2 anyway (first version of this kernel: L1 hit 67 -> 41 %, and
+// worlds that differ from each other, whose sweeps are memory-bound, lost what the full lanes had won). Ordering: the
+// producer's stores are performed at L2 (release fence) before its counter update; the consumer issues its loads only after the
+// poll's value has come back and been tested, and they read L2.
 __device__ __forceinline__ unsigned int flow_poll(const unsigned int* p) {
 	unsigned int v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
 __device__ __forceinline__ void flow_signal(unsigned int* p) {
@@ -1875,8 +1887,8 @@ __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, 
 				load_static(b2, d, ib);
 				r1 = dyn_ref(d, w, ia);
 				r2 = dyn_ref(d, w, ib);
-				b1.x = ld3(r1, DF_X); b1.q = ld4(r1, DF_Q);
-				b2.x = ld3(r2, DF_X); b2.q = ld4(r2, DF_Q);
+				b1.x = ld3cg(r1, DF_X); b1.q = ld4cg(r1, DF_Q);
+				b2.x = ld3cg(r2, DF_X); b2.q = ld4cg(r2, DF_Q);
 				c = 0;
 				ready = true;
 			}
@@ -1884,13 +1896,17 @@ __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, 
 		if (have && ready) {
 			if (JOINTS && ju >= 0) {
 				const Joint j = d.joints[ju];
-				JointLambda lam = d.lambdas[(size_t)ju * d.WS + w];
+				const real* lp = &d.lambdas[(size_t)ju * d.WS + w].a;  // (an earlier iteration's value may come from another SM)
+				JointLambda lam;
+				lam.a = __ldcg(lp); lam.b = __ldcg(lp + 1); lam.c = __ldcg(lp + 2);
 				solve_joint(j, lam, b1, b2, h, &st);
 				d.lambdas[(size_t)ju * d.WS + w] = lam;
 				c = cnt;
 			} else {
 				real* cp = cs + (size_t)c * 8 * d.WS;
 				Contact ct = ld_contact(cp, d.WS);
+				ct.lambda_n = __ldcg(cp + 6 * (size_t)d.WS);  // (written by the previous iteration's unit, possibly on another SM)
+				ct.lambda_t = __ldcg(cp + 7 * (size_t)d.WS);
 				solve_contact(ct, normal, b1, b2, h, &st, PrevFromDyn{r1, r2});
 				cp[6 * (size_t)d.WS] = ct.lambda_n;
 				cp[7 * (size_t)d.WS] = ct.lambda_t;
@@ -1969,10 +1985,13 @@ __global__ void __launch_bounds__(128) k_derive(DevView d, real h) {
 // (first velocity-level unit that touches it), derives them here (pbd.cpp:623-643), stores the previous velocities the
 // derivation leaves (they are part of the body's state) and stamps the body; returns true if it did. The previous
 // velocities are kept in registers only if the restitution term will read them (`need_prev`).
+// CG: velocities, previous velocities and the stamp are read through L2 (dataflow form: other SMs write them during the launch).
+template <bool CG = false>
 __device__ __forceinline__ bool load_for_velocity(Body& b, const DynRef& r, int active, int* stamp, int epoch, real h, bool need_prev) {
-	b.q = ld4(r, DF_Q); b.v = ld3(r, DF_V); b.w = ld3(r, DF_W);
+	b.q = ld4(r, DF_Q);
+	if (CG) { b.v = ld3cg(r, DF_V); b.w = ld3cg(r, DF_W); } else { b.v = ld3(r, DF_V); b.w = ld3(r, DF_W); }
 	b.active = active;
-	if (!(b.fixed || !b.active) && *stamp != epoch) {
+	if (!(b.fixed || !b.active) && (CG ? __ldcg(stamp) : *stamp) != epoch) {
 		b.x = ld3(r, DF_X); b.px = ld3(r, DF_PX); b.pq = ld4(r, DF_PQ);
 		derive_velocity(b, h);
 		st3(r, DF_PV, b.pv); st3(r, DF_PW, b.pw);
@@ -1980,7 +1999,7 @@ __device__ __forceinline__ bool load_for_velocity(Body& b, const DynRef& r, int 
 		return true;
 	}
 	if (need_prev) {
-		b.pv = ld3(r, DF_PV); b.pw = ld3(r, DF_PW);
+		if (CG) { b.pv = ld3cg(r, DF_PV); b.pw = ld3cg(r, DF_PW); } else { b.pv = ld3(r, DF_PV); b.pw = ld3(r, DF_PW); }
 	}
 	return false;
 }
@@ -2096,8 +2115,8 @@ __device__ __forceinline__ void vel_flow(const DevView& d, const FlowTables& t, 
 				r1 = dyn_ref(d, w, ia);
 				r2 = dyn_ref(d, w, ib);
 				const bool need_prev = b1.rest * b2.rest != RL(0.0);
-				load_for_velocity(b1, r1, d.active[bidx(d, ia, w)], d.vstamp + bidx(d, ia, w), epoch, h, need_prev);
-				load_for_velocity(b2, r2, d.active[bidx(d, ib, w)], d.vstamp + bidx(d, ib, w), epoch, h, need_prev);
+				load_for_velocity<true>(b1, r1, d.active[bidx(d, ia, w)], d.vstamp + bidx(d, ia, w), epoch, h, need_prev);
+				load_for_velocity<true>(b2, r2, d.active[bidx(d, ib, w)], d.vstamp + bidx(d, ib, w), epoch, h, need_prev);
 				tens = vel_tensors(b1, b2);
 				c = 0;
 				ready = true;
