@@ -78,8 +78,8 @@ def parse():
     ap.add_argument("--worlds", type=int, default=0, help="worlds per GPU (weak) / in total (strong); default: the workload's")
     ap.add_argument("--scaling", default="", choices=["", "weak", "strong"])
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
-                    help="f64: the product (the reference's arithmetic, bit for bit). f32: the single-precision fast-mode build of the same "
-                         "sources (librawphys_b200_f32.so): a separate, clearly labelled line, never the headline -- accepted on physical criteria")
+                    help="f64: the product (the reference's arithmetic, bit for bit). f32: the single-precision EXPERIMENT built from the same "
+                         "sources (librawphys_b200_f32.so): a separate, clearly labelled line, never the headline (DESIGN.md 7)")
     ap.add_argument("--no-cull", action="store_true", help="run GJK on every broadphase pair (disables the exact-safe bounds cull)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / profile / cpu baseline (kernel timing only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (tuning runs)")
@@ -455,7 +455,7 @@ def run_ours(args):
     line["parity_checked"] = bool(line["parity"].get("checked")) and bool(line["parity"].get("ok"))
     if args.precision == "f32":
         line["dtype"] = "f32"
-        line["precision_note"] = "fast mode: same kernels compiled with real = float; NOT the headline (BASELINE's metric is quoted in the reference's FP64 arithmetic)"
+        line["precision_note"] = "single-precision experiment: same kernels compiled with real = float; NOT the headline (BASELINE's metric is quoted in the reference's FP64 arithmetic) and not stable for loaded stacks beyond the first seconds (DESIGN.md 7)"
 
     if args.workload == "c3":
         # the same scene in the reference's own constraint order (bit-exact, deep dependency chains), for the record

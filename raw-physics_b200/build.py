@@ -64,8 +64,8 @@ def build_exactq(force=False):
     return build(out=EXACTQ_OUT, defines=("RP_EXACT_QUATERNIONS",))
 
 
-# Single-precision "fast mode" (SURVEY.md 7 hard part 1, 8d): the same sources with `real` = float (rp_math.h). Same C ABI (host
-# records stay double, converted at upload / download); results are NOT comparable with the reference beyond float accuracy.
+# Single precision (SURVEY.md 7 hard part 1, 8d "fast mode"): the same sources with `real` = float (rp_math.h). Same C ABI (host
+# records stay double, converted at upload / download). An experiment, not a product mode: see DESIGN.md 7 for what holds and what does not.
 F32_OUT = os.path.join(HERE, "librawphys_b200_f32.so")
 
 

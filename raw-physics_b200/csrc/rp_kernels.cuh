@@ -1099,6 +1099,12 @@ __global__ void __launch_bounds__(RP_EPA_THREADS, RP_MINB_EPA) k_epa(DevView d) 
 #endif
 			r = epa_run(A, B, s, e, &out.normal, &out.depth, &st, 0, &out.sup_a, &out.sup_b);
 			if (r == EPA_OVERFLOW) r = epa_full(d, cd, s, &out.normal, &out.depth, &st, &out.sup_a, &out.sup_b);
+#if defined(RP_REAL_F32)
+			if (r == EPA_FAIL && sat_face_fallback(A, B, &out.normal, &out.depth, &out.sup_a, &out.sup_b)) {  // (rp_narrow.h: single precision only)
+				r = EPA_DONE;
+				st &= ~(ST_EPA_DEGENERATE | ST_EPA_NO_CONVERGENCE);
+			}
+#endif
 			out.ok = r == EPA_DONE ? 1 : 0;
 		}
 		d.epa_out[hi] = out;

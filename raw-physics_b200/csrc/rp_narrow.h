@@ -410,6 +410,38 @@ RP_HD int epa_run(const SA& A, const SB& B, const Simplex& s, E& e, V3* normal_o
 	return EPA_FAIL;
 }
 
+#if defined(RP_REAL_F32)
+// Single precision only. In float, boxes at rest are EXACTLY axis-aligned (rotation noise below 6e-8 rounds away), their
+// Minkowski difference is an exact grid, and EPA keeps meeting exactly collinear / coplanar points where the reference asserts
+// (epa.cpp:41, :72): the same failure every substep, the pair stays contact-free, the body sinks, and the deep overlap that is
+// finally detected throws the stack apart. When EPA gives up, the penetration is taken from the FACE normals instead: the support
+// function of A - B, h(n) = n . (support_A(n) - support_B(-n)), is minimised over the faces of A and the reversed faces of B
+// (its minimum over ALL directions, which is what EPA looks for, lies on a face of A - B; the edge-edge faces are left out, a
+// resting contact is a face contact). Not part of the FP64 product: there such pairs are flagged, as the reference aborts.
+template <class SA, class SB>
+RP_HD bool sat_face_fallback(const SA& A, const SB& B, V3* normal_out, real* depth_out, int* sup_a, int* sup_b) {
+	if (A.type != SHAPE_HULL || B.type != SHAPE_HULL) return false;
+	real best = RL(RP_REAL_MAX);
+	for (int pass = 0; pass < 2; ++pass) {
+		const int nf = pass == 0 ? A.nf : B.nf;
+		for (int i = 0; i < nf; ++i) {
+			const V3 n = pass == 0 ? fnormal(A, i) : zero_minus(fnormal(B, i));
+			int ia, ib;
+			const V3 sp = support_minkowski_idx(A, B, n, &ia, &ib);
+			const real hgt = dot(n, sp);
+			if (hgt < best) {
+				best = hgt;
+				*normal_out = n;
+				if (sup_a) { *sup_a = ia; *sup_b = ib; }
+			}
+		}
+	}
+	if (!(best > RL(0.0)) || !(best < RL(RP_REAL_MAX))) return false;  // separated along some face normal (or no faces): no contact
+	*depth_out = best;
+	return true;
+}
+#endif
+
 template <class SA, class SB>
 RP_HD bool epa(const SA& A, const SB& B, const Simplex& s, EpaScratch& e, V3* normal_out, real* depth_out, int* status,
 	int* iters) {

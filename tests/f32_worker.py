@@ -26,11 +26,12 @@ def run(tag, name, params=(), perturb=False, worlds=3, frames=(60,), **kw):
             out["%s/state/%d" % (tag, f)] = st[worlds - 1]
             out["%s/same/%d" % (tag, f)] = np.array([np.array_equal(st[0], st[worlds - 1])])
     out["%s/status" % tag] = b.status()
+    out["%s/fixed" % tag] = np.array([bool(bd.fixed) for bd in desc.bodies])
     b.close()
 
 
-run("stack", "stack", frames=(10, 60, 240, 360))
-run("stack70", "stack", worlds=70, frames=(120,))          # dataflow sweeps
+run("stack", "stack", frames=(10, 60, 240))
+run("stack70", "stack", worlds=70, frames=(60,))           # dataflow sweeps
 run("w256", "w256", (2, 2, 4), worlds=33, frames=(60, 120))
 run("wall", "brick_wall", (8, 8), worlds=1, frames=(90,), coloured=True)
 run("levers", "hinge_joints", perturb=True, worlds=4, frames=(60,))
