@@ -40,7 +40,7 @@ KERNEL_FAMILIES = ["broadphase", "islands", "schedule", "integrate", "cull", "gj
 
 class BatchCfg(C.Structure):
     _fields_ = [("max_pairs_per_world", C.c_uint32), ("max_contacts_per_world", C.c_uint32), ("disable_cull", C.c_uint32),
-                ("solve_order", C.c_uint32), ("sweep_block_worlds", C.c_uint32), ("large_scene", C.c_uint32), ("disable_islands", C.c_uint32), ("reserved0", C.c_uint32),
+                ("solve_order", C.c_uint32), ("sweep_block_worlds", C.c_uint32), ("large_scene", C.c_uint32), ("disable_islands", C.c_uint32), ("sweep_form", C.c_uint32),
                 ("linear_sleeping_threshold", C.c_double), ("angular_sleeping_threshold", C.c_double), ("deactivation_time", C.c_double)]
 
 
@@ -326,7 +326,8 @@ class Scene:
 class Batch:
     """n_worlds instances of a scene on one GPU (rp_batch)."""
 
-    def __init__(self, scene, n_worlds=1, device=0, max_pairs=0, max_contacts=0, disable_cull=False, coloured=False, sweep_block_worlds=0, large_scene=0, disable_islands=False):
+    def __init__(self, scene, n_worlds=1, device=0, max_pairs=0, max_contacts=0, disable_cull=False, coloured=False, sweep_block_worlds=0, large_scene=0, disable_islands=False,
+                 sweep_form=0):
         self.L = lib()
         self.scene = scene
         cfg = BatchCfg()
@@ -337,6 +338,7 @@ class Batch:
         cfg.solve_order = 1 if coloured else 0  # RP_ORDER_COLOURED / RP_ORDER_REFERENCE
         cfg.sweep_block_worlds = sweep_block_worlds  # 0: level-major sweeps
         cfg.disable_islands = int(disable_islands)
+        cfg.sweep_form = int(sweep_form)  # 0 choose, 1 grid barriers between levels, 2 dataflow (rawphys_b200.h)
         cfg.large_scene = large_scene  # 0: grid broadphase / union-find islands / parallel colouring from 4096 bodies per world; 1 never; 2 always
         h = C.c_void_p()
         _check(self.L.rp_batch_create(scene.h, n_worlds, device, C.byref(cfg), C.byref(h)), "rp_batch_create")

@@ -838,7 +838,9 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		// levels per sweep and pay more for the prefix pass than they save (1.26 -> 1.36); one large scene is bound by the
 		// latency of its units, not by the barriers (brick wall 32 x 32 coloured: 5.37 vs 5.43), and keeps it too.
 		int flow = d.NJ == 0 && d.W >= 64 && !b->large && !b->coloured && !d.block_mode ? 1 : 0;
-		if (const char* e = getenv("RP_FLOW")) {  // tuning aid: 0 = grid barriers between levels, 2 = dataflow for any batch
+		if (cfg.sweep_form == 1) flow = 0;
+		if (cfg.sweep_form == 2 && !d.block_mode) flow = 1;
+		if (const char* e = getenv("RP_FLOW")) {  // tuning aid, overrides rp_batch_cfg.sweep_form: 0 = grid barriers between levels, 2 = dataflow for any batch
 			const int v = atoi(e);
 			if (v == 0) flow = 0;
 			if (v == 2 && !d.block_mode) flow = 1;

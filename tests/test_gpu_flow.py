@@ -49,6 +49,21 @@ def test_dataflow_sweeps_equal_barrier_sweeps(pkg, name, params, perturb, frames
     assert np.array_equal(flow[0], flow[-1])
 
 
+def test_sweep_form_is_a_batch_setting(pkg):
+    """rp_batch_cfg.sweep_form (1 = barriers, 2 = dataflow) without the environment: same bits"""
+    scene, desc = pkg.example("stack")
+    out = []
+    for form in (1, 2):
+        b = pkg.Batch(scene, n_worlds=66, device=0, sweep_form=form)
+        b.set_scene_forces(desc)
+        for _ in range(40):
+            b.step()
+        out.append(b.state())
+        assert not b.status().any()
+        b.close()
+    assert np.array_equal(out[0].view(np.uint64), out[1].view(np.uint64))
+
+
 def test_dataflow_default_matches_the_oracle(pkg, oracle_flavour):
     """70 worlds of the stack scene take the dataflow form by default; 60 frames against the oracle stepped alongside"""
     st, bits, desc = run(pkg, "stack", worlds=70, frames=60)
