@@ -832,12 +832,13 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 		if ((rc = dev_alloc(b, &d.blk_items, d.block_mode ? WP : 1, false))) return rc;
 	}
 	{
-		// Dataflow sweeps (pos_flow / vel_flow): contact-only batches of at least two warps of worlds. Measured (B200, ms per
-		// frame): w256 x 4096 frames 40..59 24.1 -> 20.2, stack x 4096 2.56 -> 2.30. Scenes with external constraints can run it
-		// (their joints head each level's items) but keep the barrier form by default: the levers x 16384 have two or three
-		// levels per sweep and pay more for the prefix pass than they save (1.26 -> 1.36); one large scene is bound by the
-		// latency of its units, not by the barriers (brick wall 32 x 32 coloured: 5.37 vs 5.43), and keeps it too.
-		int flow = d.NJ == 0 && d.W >= 64 && !b->large && !b->coloured && !d.block_mode ? 1 : 0;
+		// Dataflow sweeps (pos_flow / vel_flow: a unit waits for the previous live unit of each of its two bodies, no grid barriers)
+		// for contact-only scenes: batches of at least two warps of worlds, and one large / coloured scene. Measured (B200, ms per
+		// frame, barrier form -> dataflow): w256 x 4096 frames 40..59 24.1 -> 20.5, stack x 4096 2.56 -> 2.24, brick wall 32 x 32
+		// coloured 5.39 -> 4.23, the 65,600-body pile 54.3 -> 39.2 (its sweeps 4.2x: a 64-contact manifold no longer holds a whole
+		// level up). Scenes with external constraints can run it (their joints are links of the chains) but keep the barrier
+		// form by default: the levers x 16384 have two or three levels per sweep and nothing to gain (1.25 -> 1.31).
+		int flow = d.NJ == 0 && (d.W >= 64 || b->large || b->coloured) && !d.block_mode ? 1 : 0;
 		if (cfg.sweep_form == 1) flow = 0;
 		if (cfg.sweep_form == 2 && !d.block_mode) flow = 1;
 		if (const char* e = getenv("RP_FLOW")) {  // tuning aid, overrides rp_batch_cfg.sweep_form: 0 = grid barriers between levels, 2 = dataflow for any batch
@@ -846,11 +847,17 @@ static int create_impl(const rp_scene* scene, uint32_t n_worlds, int device, con
 			if (v == 2 && !d.block_mode) flow = 1;
 		}
 		d.flow_mode = flow;
-		const size_t rows = flow ? (size_t)RP_FLOW_LEVELS + 2 : 0;
-		if ((rc = dev_alloc(b, &d.wl_cnt, std::max<size_t>(1, rows * WS)))) return rc;
-		if ((rc = dev_alloc(b, &d.wl_pre, std::max<size_t>(1, rows * WS)))) return rc;
-		if ((rc = dev_alloc(b, &d.flow_done, 2 * WS + 32))) return rc;
-		if ((rc = dev_alloc(b, &d.flow_cursor, 2))) return rc;
+		if ((rc = dev_alloc(b, &d.body_live, flow ? SB : 1))) return rc;
+		if ((rc = dev_alloc(b, &d.body_done, flow ? 2 * SB : 1))) return rc;
+		if ((rc = dev_alloc(b, &d.flow_cursor, 4))) return rc;
+		// levels of the joints on each body (template constant): they are links of the body's chain in every substep
+		std::vector<unsigned long long> jmask((size_t)d.NB, 0ull);
+		for (int u = 0; u < d.NJ; ++u) {
+			if (b->joint_level[u] < 1 || b->joint_level[u] > RP_FLOW_LEVELS) continue;  // (deeper schedules keep the barrier form)
+			jmask[s.joints[u].e1] |= 1ull << b->joint_level[u];
+			jmask[s.joints[u].e2] |= 1ull << b->joint_level[u];
+		}
+		if ((rc = dev_upload(b, &d.joint_body_mask, jmask))) return rc;
 	}
 	if ((rc = dev_alloc(b, &d.contacts, WS * d.max_contacts * 8, false))) return rc;
 	if ((rc = dev_alloc(b, &d.n_contacts, W))) return rc;

@@ -104,13 +104,13 @@ struct DevView {
 	int* lvl_fill;       // [max_levels + 2] pairs of level l with contacts (per substep)
 	int* lvl_max;        // [1] deepest level of the frame over all worlds
 	SolveItem* lvl_items;  // [W * max_pairs] level l occupies [lvl_off[l], lvl_off[l] + lvl_fill[l])
-	// dataflow sweeps (pos_flow / vel_flow in rp_kernels.cuh): per-world counts of this substep's units by level, their
-	// prefix over levels, and per-world counters of finished units that stand in for the grid-wide barrier between levels
-	int flow_mode;             // 1: the sweeps of contact-only batches run without grid barriers
-	int* wl_cnt;               // [RP_FLOW_LEVELS + 2][WS] units of world w at level l with contacts this substep (k_manifold)
-	int* wl_pre;               // [RP_FLOW_LEVELS + 2][WS] units of world w at levels < l; row (levels + 1) = the world's total
-	unsigned int* flow_done;   // [2][WS] units of world w finished in this substep's positional / velocity sweep
-	unsigned int* flow_cursor; // [2] next unclaimed item of the positional / velocity sweep
+	// dataflow sweeps (pos_flow / vel_flow in rp_kernels.cuh): which levels of a body's chain of units are live this substep, and
+	// how far each body's chain has got in the current sweep -- these stand in for the grid-wide barrier between levels
+	int flow_mode;                   // 1: the sweeps run without grid barriers
+	unsigned long long* body_live;   // [NB][WS] bit l: a unit of level l with contacts this substep touches this body (k_manifold; cleared by k_integrate)
+	unsigned long long* body_done;   // [2][NB][WS] (pass << 6 | level) of the last unit finished on this body in the positional / velocity sweep
+	const unsigned long long* joint_body_mask;  // [NB] bit l: a joint of level l touches this body (template constant)
+	unsigned int* flow_cursor;       // [2] next unclaimed item of the positional / velocity sweep; [2] set when a lane gave up waiting
 	// world-block sweeps (k_solve_block): the units of each WORLD that have contacts this substep, and each world block's
 	// units sorted by level
 	int block_mode;      // 1: the sweeps run per block of `worlds per block` consecutive worlds, CTA-scoped barriers between levels

@@ -115,6 +115,12 @@ __device__ __forceinline__ void st_contact(real* p, size_t S, const Contact& c) 
 __device__ __forceinline__ size_t bidx(const DevView& d, int b, int w) { return (size_t)b * d.WS + w; }  // per-body arrays
 __device__ __forceinline__ size_t pidx(const DevView& d, int p, int w) { return (size_t)p * d.WS + w; }  // per-pair arrays
 
+// dataflow sweeps: a unit of level `lvl` with contacts this substep touches bodies a and b (fixed bodies are never written and carry no chain)
+__device__ __forceinline__ void flow_mark_live(const DevView& d, int a, int b, int w, int lvl) {
+	if (!d.bstat[a].fixed) atomicOr(&d.body_live[bidx(d, a, w)], 1ull << lvl);
+	if (!d.bstat[b].fixed) atomicOr(&d.body_live[bidx(d, b, w)], 1ull << lvl);
+}
+
 // Thread -> (item, world) for the kernels that do one thing per item per world, world fastest: consecutive threads are
 // consecutive worlds of one item, so world-minor accesses coalesce; a batch of fewer worlds than a warp (one large scene: WS = W
 // then, see rp_batch_create) gets consecutive ITEMS in a warp instead of 31 idle lanes per item, and the accesses still
@@ -551,10 +557,7 @@ __global__ void __launch_bounds__(32) k_schedule(DevView d, int collisions) {
 // zeroes the per-frame level capacities (before k_schedule) / turns them into list offsets (after it)
 __global__ void __launch_bounds__(256) k_level_reset(DevView d) {
 	for (int l = threadIdx.x; l < d.max_levels + 2; l += blockDim.x) d.lvl_cap[l] = 0;
-	if (threadIdx.x == 0) {
-		d.lvl_max[1] = d.lvl_max[0];  // the previous frame's depth: its last substep left per-world counts up to there (k_substep_reset)
-		d.lvl_max[0] = 0;
-	}
+	if (threadIdx.x == 0) *d.lvl_max = 0;
 }
 __global__ void k_level_offsets(DevView d) {
 	int run = 0;
@@ -582,12 +585,6 @@ __global__ void __launch_bounds__(256) k_substep_reset(DevView d) {
 	if (i < d.W) {
 		d.n_contacts[i] = 0;
 		d.n_live[i] = 0;
-		if (d.flow_mode) {
-			const int nl = min(max(d.lvl_max[0], d.lvl_max[1]), RP_FLOW_LEVELS);
-			for (int l = 1; l <= nl; ++l) d.wl_cnt[(size_t)l * d.WS + i] = 0;
-			d.flow_done[i] = 0u;
-			d.flow_done[d.WS + i] = 0u;
-		}
 	}
 	if (i < 2 && d.flow_mode) d.flow_cursor[i] = 0u;
 }
@@ -637,6 +634,7 @@ __global__ void __launch_bounds__(RP_INT_THREADS, RP_MINB_INTEGRATE) k_integrate
 		}
 	}
 	const BodyStatic s = d.bstat[b];
+	if (d.flow_mode) d.body_live[bidx(d, b, w)] = 0ull;  // this substep's k_manifold marks the levels at which the body has live units
 	Body body;
 	load_static(body, d, b);
 	const DynRef r = dyn_ref(d, w, b);
@@ -1315,7 +1313,7 @@ __global__ void __launch_bounds__(RP_MANIFOLD_THREADS, RP_MINB_MANIFOLD) k_manif
 				slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1u));
 				const int at = big ? d.lvl_off[lvl + 1] - 1 - slot : d.lvl_off[lvl] + slot;
 				d.lvl_items[at] = item;
-				if (d.flow_mode && lvl <= RP_FLOW_LEVELS) atomicAdd(&d.wl_cnt[(size_t)lvl * d.WS + w], 1);
+				if (d.flow_mode && lvl <= RP_FLOW_LEVELS) flow_mark_live(d, item.a, item.b, w, lvl);
 			}
 		}
 	}
@@ -1523,7 +1521,7 @@ __global__ void __launch_bounds__(RP_CLIPW_THREADS) k_manifold_warp(DevView d) {
 						const int big = n > RP_SMALL_MANIFOLD ? 1 : 0;
 						const int slot = atomicAdd(&d.lvl_fill[(size_t)lvl * RP_LVL_STRIDE + big], 1);
 						d.lvl_items[big ? d.lvl_off[lvl + 1] - 1 - slot : d.lvl_off[lvl] + slot] = item;
-						if (d.flow_mode && lvl <= RP_FLOW_LEVELS) atomicAdd(&d.wl_cnt[(size_t)lvl * d.WS + w], 1);
+						if (d.flow_mode && lvl <= RP_FLOW_LEVELS) flow_mark_live(d, item.a, item.b, w, lvl);
 					}
 				}
 			}
@@ -1689,22 +1687,28 @@ __device__ __forceinline__ int list_live_levels(const DevView& d, LiveLevels& s,
 
 
 // ------------------------------------------------------------------------------------------------------ dataflow sweeps
-// The dependency between two levels never crosses worlds: a unit of level l in world w only has to wait for the units of
-// world w at lower levels. The level-major sweeps above hold the WHOLE grid at a barrier between two levels anyway (ncu,
-// frame 40: 4.2 barrier-stall cycles per issued instruction, and 22.6 of 32 lanes active because every warp's share of a
-// level ends in a partly filled trip). The dataflow form keeps the level-major item lists but replaces the barriers by
-// per-world counters:
-//  * k_manifold counts the units it lists per (level, world) (wl_cnt); the positional kernel turns the counts into a
-//    prefix over levels (wl_pre: units of the world at lower levels), one grid barrier per substep instead of one per level;
+// A unit only has to wait for the units that touch one of its two bodies and come before it in the reference's order -- on each
+// body those form a chain of strictly increasing levels. The level-major sweeps above hold the WHOLE grid at a barrier between two
+// levels anyway (ncu, frame 40: 4.2 barrier-stall cycles per issued instruction, and 22.6 of 32 lanes active because every warp's
+// share of a level ends in a partly filled trip). The dataflow form keeps the level-major item lists but replaces the barriers
+// by the chains themselves:
+//  * k_manifold marks, per body, the levels at which the body has a unit with contacts this substep (body_live: one 64-bit mask
+//    per body and world, cleared by k_integrate); joints add the template-constant mask of their levels;
 //  * all levels (and positional iterations) form ONE item sequence in level-major order; a warp claims the next 32 items with
 //    one atomic on a global cursor and hands them to its lanes as they fall free (lanes stay full across level boundaries);
-//  * a lane that holds a unit polls flow_done[w] (ld.acquire.gpu) until it equals the number of units that precede the unit in
-//    its world; a finished unit stores its bodies and bumps the counter (red.release.gpu).
+//  * a unit of level l waits, for each of its non-fixed bodies, until body_done says that the body's previous live unit (the
+//    highest marked level below l; in a later positional iteration and with none below, the body's LAST unit of the iteration
+//    before) has finished; a finished unit stores its bodies and then, with release semantics, (pass << 6 | level) into body_done
+//    of both. Pass numbers grow from substep to substep (substep counter * 256 + iteration), so nothing is ever reset.
+// A first version kept one counter per WORLD (units finished / units at lower levels): right, and as fast on copies of one scene,
+// but a world's units of one level are spread over the whole level list, so its level was only complete when the list's tail
+// was, and worlds with uneven work had 10 - 13 of 32 lanes running.
 // No deadlock: items are claimed in sequence order and a warp hands its claimed items to lanes in order, so the lowest
-// unfinished item of the sequence is always held by a lane, everything it waits for has finished, and it runs (the grid is
-// the cooperative launch's resident CTAs, so every claiming warp is running). The per-world order of units is the level
-// order either way: results are bit-identical to the barrier form. A lane that polls 2^16 times without success gives up,
-// flags the world (RP_ST_SOLVER_SINGULAR), tells every other lane to stop waiting and proceeds: a logic error cannot hang the device.
+// unfinished item of the sequence is always held by a lane, everything it waits for has a lower level or an earlier pass and has
+// finished, and it runs (the grid is the cooperative launch's resident CTAs, so every claiming warp is running). Every body's
+// units still run in level order, which is the reference's order: results are bit-identical to the barrier form. A lane that
+// polls 2^16 times without success gives up, flags the world (RP_ST_SOLVER_SINGULAR), tells every other lane to stop waiting and
+// proceeds: a logic error cannot hang the device.
 struct FlowTables {
 	int cum[RP_FLOW_LEVELS + 2];   // items of levels < l (cum[levels + 1] = all)
 	int jn[RP_FLOW_LEVELS + 2];    // (joint, world) items that head level l: its joints x W
@@ -1732,36 +1736,36 @@ __device__ __forceinline__ unsigned int flow_tables(const DevView& d, FlowTables
 	__syncthreads();
 	return (unsigned int)t.cum[levels + 1];
 }
-// wl_pre[l][w] = units of world w at levels < l, for l = 1 .. levels + 1
-__device__ __forceinline__ void flow_prefix(const DevView& d, int levels) {
-	const unsigned int n = (unsigned int)(levels + 1) * (unsigned int)d.W;
-	for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		const unsigned int l1 = i / (unsigned int)d.W;
-		const int w = (int)(i - l1 * (unsigned int)d.W);
-		int run = 0;
-		for (int l = 1; l <= (int)l1; ++l) run += d.wl_cnt[(size_t)l * d.WS + w];
-		d.wl_pre[(size_t)(l1 + 1) * d.WS + w] = run;
-	}
-}
-// The counter is read with a RELAXED load and the state a unit then loads goes through L2 (ld3cg / ld4cg / __ldcg): an acquire
+// The chain state is read with RELAXED loads and the state a unit then loads goes through L2 (ld3cg / ld4cg / __ldcg): an acquire
 // load (or fence) is LD + CCTL.IVALL on sm_100a -- it drops the SM's whole L1 on every poll, for every warp on the SM, although
-// the only lines that can be stale are the ones read through L2 anyway (first version of this kernel: L1 hit 67 -> 41 %, and
-// worlds that differ from each other, whose sweeps are memory-bound, lost what the full lanes had won). Ordering: the
-// producer's stores are performed at L2 (release fence) before its counter update; the consumer issues its loads only after the
-// poll's value has come back and been tested, and they read L2.
-__device__ __forceinline__ unsigned int flow_poll(const unsigned int* p) {
-	unsigned int v;
-	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// the only lines that can be stale are the ones read through L2 anyway. Ordering: the producer's stores are performed at L2
+// (release) before its body_done update; the consumer issues its loads only after the poll's value has come back and been
+// tested, and they read L2.
+__device__ __forceinline__ unsigned long long flow_poll(const unsigned long long* p) {
+	unsigned long long v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
 }
-__device__ __forceinline__ void flow_signal(unsigned int* p) {
-	asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+__device__ __forceinline__ void flow_signal(unsigned long long* p, unsigned long long v) {
+	asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// what body_done of `body` must have reached before a unit of `level` in pass `pass` (iteration `it` of its sweep) may run; 0 = nothing
+template <bool JOINTS>
+__device__ __forceinline__ unsigned long long flow_need(const DevView& d, int body, int w, int level, unsigned long long pass, int it) {
+	if (d.bstat[body].fixed) return 0ull;
+	unsigned long long m = d.body_live[bidx(d, body, w)];
+	if (JOINTS) m |= d.joint_body_mask[body];
+	const unsigned long long below = m & ((1ull << level) - 1ull);
+	if (below) return (pass << 6) | (unsigned long long)(63 - __clzll((long long)below));
+	if (it > 0 && m) return ((pass - 1ull) << 6) | (unsigned long long)(63 - __clzll((long long)m));
+	return 0ull;
 }
 #define RP_FLOW_SPIN_LIMIT (1 << 16)
+#define RP_FLOW_MAX_ITERS 250  // positional iterations per pass number block (pass = substep counter * 256 + iteration + 1)
 // one failed poll: counts it; true when the lane should stop waiting -- it ran out of patience (and then raises the batch-wide
-// "broken" word behind the done counters, which every other waiting lane looks at now and then), or someone else did
+// "broken" word behind the cursors, which every other waiting lane looks at now and then), or someone else did
 __device__ __forceinline__ bool flow_give_up(const DevView& d, int* spins) {
-	unsigned int* broken = d.flow_done + 2 * (size_t)d.WS;
+	unsigned int* broken = d.flow_cursor + 2;
 	if (++*spins > RP_FLOW_SPIN_LIMIT) {
 		atomicExch(broken, 1u);
 		return true;
@@ -1834,12 +1838,13 @@ template <bool JOINTS>
 __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, real h, int levels, unsigned int per_pass, int iters) {
 	FlowQueue q;
 	q.init(per_pass * (unsigned int)iters);
-	const size_t total_row = (size_t)(levels + 1) * d.WS;
+	const unsigned long long pass0 = (unsigned long long)(unsigned int)*d.epoch * 256ull + 1ull;  // pass number of iteration 0
+	unsigned long long* const done = d.body_done;
 	int st = 0;
 	bool have = false, ready = false;
 	int w = 0, cnt = 0, c = 0, ia = 0, ib = 0, spins = 0;
 	int ju = -1;  // the joint a lane holds (JOINTS), -1: a contact unit
-	unsigned int need = 0u;
+	unsigned long long need1 = 0ull, need2 = 0ull, mine = 0ull;
 	real* cs = 0;
 	DynRef r1, r2;
 	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
@@ -1867,10 +1872,10 @@ __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, 
 				cs = contact_ptr(d, w, item.coff);
 				ju = -1;
 			}
-			// units of this world that precede the item: everything of earlier passes, the joints and the contact units of lower levels
-			need = (unsigned int)d.wl_pre[(size_t)level * d.WS + w];
-			if (JOINTS) need += (unsigned int)d.joint_lptr[min(level - 1, d.joint_levels)];
-			if (it > 0) need += (unsigned int)it * ((unsigned int)d.wl_pre[total_row + w] + (JOINTS ? (unsigned int)d.NJ : 0u));
+			// how far the chains of its two bodies must have got, and what it will write there itself
+			need1 = flow_need<JOINTS>(d, ia, w, level, pass0 + (unsigned long long)it, it);
+			need2 = flow_need<JOINTS>(d, ib, w, level, pass0 + (unsigned long long)it, it);
+			mine = ((pass0 + (unsigned long long)it) << 6) | (unsigned long long)level;
 			have = cnt > 0;
 			ready = false;
 			spins = 0;
@@ -1880,13 +1885,10 @@ __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, 
 			continue;
 		}
 		if (have && !ready) {
-			bool go = need == 0u;
-			if (!go) {
-				go = flow_poll(d.flow_done + w) >= need;
-				if (!go && flow_give_up(d, &spins)) {
-					st |= ST_SOLVER_SINGULAR;
-					go = true;
-				}
+			bool go = (need1 == 0ull || flow_poll(done + bidx(d, ia, w)) >= need1) && (need2 == 0ull || flow_poll(done + bidx(d, ib, w)) >= need2);
+			if (!go && flow_give_up(d, &spins)) {
+				st |= ST_SOLVER_SINGULAR;
+				go = true;
 			}
 			if (go) {
 				load_static(b1, d, ia);
@@ -1925,7 +1927,8 @@ __device__ __forceinline__ void pos_flow(const DevView& d, const FlowTables& t, 
 					atomicOr(&d.status[w], st);
 					st = 0;
 				}
-				flow_signal(d.flow_done + w);
+				if (!b1.fixed) flow_signal(done + bidx(d, ia, w), mine);
+				if (!b2.fixed) flow_signal(done + bidx(d, ib, w), mine);
 				have = false;
 			}
 		}
@@ -1942,9 +1945,7 @@ __global__ void RP_POS_BOUNDS k_solve_pos(DevView d, real h, int iters, int coll
 		__shared__ FlowTables s_flow;
 		const unsigned int per_pass = flow_tables<JOINTS>(d, s_flow, levels, collisions);
 		if (per_pass == 0u) return;
-		if ((unsigned long long)per_pass * (unsigned long long)iters < 0x7fffff00ull) {  // (same decision in every CTA)
-			flow_prefix(d, levels);
-			grid.sync();
+		if ((unsigned long long)per_pass * (unsigned long long)iters < 0x7fffff00ull && iters <= RP_FLOW_MAX_ITERS) {  // (same decision in every CTA)
 			pos_flow<JOINTS>(d, s_flow, h, levels, per_pass, iters);
 			return;
 		}
@@ -2074,10 +2075,11 @@ __device__ __forceinline__ void vel_level(const DevView& d, real h, int level) {
 __device__ __forceinline__ void vel_flow(const DevView& d, const FlowTables& t, real h, int levels, unsigned int per_pass) {
 	FlowQueue q;
 	q.init(per_pass);
-	unsigned int* done = d.flow_done + d.WS;
+	unsigned long long* const done = d.body_done + (size_t)d.NB * d.WS;
+	const unsigned long long pass = (unsigned long long)(unsigned int)*d.epoch * 256ull + 1ull;
 	bool have = false, ready = false;
 	int w = 0, cnt = 0, c = 0, ia = 0, ib = 0, spins = 0;
-	unsigned int need = 0u;
+	unsigned long long need1 = 0ull, need2 = 0ull, mine = 0ull;
 	const real* cs = 0;
 	DynRef r1, r2;
 	r1.p = r2.p = 0; r1.s = r2.s = d.WS;
@@ -2097,7 +2099,9 @@ __device__ __forceinline__ void vel_flow(const DevView& d, const FlowTables& t, 
 			normal = item.normal;
 			ia = item.a; ib = item.b;
 			cs = contact_ptr(d, w, item.coff);
-			need = (unsigned int)d.wl_pre[(size_t)level * d.WS + w];
+			need1 = flow_need<false>(d, ia, w, level, pass, 0);  // (joints take no part in the velocity pass)
+			need2 = flow_need<false>(d, ib, w, level, pass, 0);
+			mine = (pass << 6) | (unsigned long long)level;
 			have = cnt > 0;
 			ready = false;
 			spins = 0;
@@ -2107,13 +2111,10 @@ __device__ __forceinline__ void vel_flow(const DevView& d, const FlowTables& t, 
 			continue;
 		}
 		if (have && !ready) {
-			bool go = need == 0u;
-			if (!go) {
-				go = flow_poll(done + w) >= need;
-				if (!go && flow_give_up(d, &spins)) {
-					atomicOr(&d.status[w], (int)ST_SOLVER_SINGULAR);
-					go = true;
-				}
+			bool go = (need1 == 0ull || flow_poll(done + bidx(d, ia, w)) >= need1) && (need2 == 0ull || flow_poll(done + bidx(d, ib, w)) >= need2);
+			if (!go && flow_give_up(d, &spins)) {
+				atomicOr(&d.status[w], (int)ST_SOLVER_SINGULAR);
+				go = true;
 			}
 			if (go) {
 				load_static(b1, d, ia);
@@ -2134,7 +2135,8 @@ __device__ __forceinline__ void vel_flow(const DevView& d, const FlowTables& t, 
 			if (++c == cnt) {
 				if (!b1.fixed) { st3(r1, DF_V, b1.v); st3(r1, DF_W, b1.w); }
 				if (!b2.fixed) { st3(r2, DF_V, b2.v); st3(r2, DF_W, b2.w); }
-				flow_signal(done + w);
+				if (!b1.fixed) flow_signal(done + bidx(d, ia, w), mine);
+				if (!b2.fixed) flow_signal(done + bidx(d, ib, w), mine);
 				have = false;
 			}
 		}
@@ -2149,11 +2151,10 @@ __global__ void __launch_bounds__(RP_VEL_THREADS, RP_MINB_VEL) k_solve_vel(DevVi
 	// (flow_iters = the positional iterations of this substep's k_solve_pos: the same decision as there, or 0 for the barrier form)
 	if (flow_iters > 0 && d.flow_mode && levels <= RP_FLOW_LEVELS) {
 		__shared__ FlowTables s_flow;
-		// the positional kernel of this substep took the dataflow form (and left the prefix table) iff ITS item count fitted: the
-		// velocity pass has the contact units only, so its own count is checked against the same bound with the joints added
+		// (the same bound as the positional kernel's, whose item count includes the joints)
 		const unsigned int per_pass = flow_tables<false>(d, s_flow, levels, 1);
 		if (per_pass == 0u) return;
-		if (((unsigned long long)per_pass + (unsigned long long)d.NJ * d.W) * (unsigned long long)flow_iters < 0x7fffff00ull) {
+		if (((unsigned long long)per_pass + (unsigned long long)d.NJ * d.W) * (unsigned long long)flow_iters < 0x7fffff00ull && flow_iters <= RP_FLOW_MAX_ITERS) {
 			vel_flow(d, s_flow, h, levels, per_pass);
 			return;
 		}
