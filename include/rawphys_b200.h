@@ -167,10 +167,11 @@ typedef struct {
 	uint32_t large_scene;             /* per-frame prologue for ONE LARGE SCENE (uniform-grid broadphase, union-find islands, parallel graph
 	                                     colouring): 0 = when a world has >= 4096 bodies (>= 1024 in the coloured order), 1 = never, 2 = always */
 	uint32_t disable_islands;         /* 1 = the reference built without ENABLE_SIMULATION_ISLANDS (pbd.cpp:12): no islands, nothing sleeps */
-	uint32_t sweep_form;              /* how the Gauss-Seidel sweeps keep a world's levels in order (same results either way): 0 = choose
-	                                     (dataflow -- per-world counters of finished units, no grid barriers -- for contact-only batches of at least
-	                                     64 worlds, grid barriers between levels otherwise), 1 = grid barriers (a batch of worlds that differ from
-	                                     each other measured 3 % faster with them), 2 = dataflow wherever it applies */
+	uint32_t sweep_form;              /* how the Gauss-Seidel sweeps keep the reference's order (same results either way): 0 = choose (dataflow --
+	                                     a unit waits for the previous live unit of each of its two bodies, no grid barriers -- for contact-only scenes:
+	                                     batches of at least 64 worlds and one large / coloured scene; grid barriers between levels otherwise), 1 = grid
+	                                     barriers (a batch of worlds that differ from each other measured 3 % faster with them), 2 = dataflow wherever
+	                                     it applies (scenes with joints included) */
 	double linear_sleeping_threshold;   /* pbd.cpp:13, default 0.10 */
 	double angular_sleeping_threshold;  /* pbd.cpp:14, default 0.10 */
 	double deactivation_time;           /* pbd.cpp:15, default 1.0 */

@@ -53,9 +53,9 @@ lines = ["# ncu summary, round 2, second session (commit %s)\n" % d["commit"],
          "## One substep (frame 40)\n"] + table(d) + ["\n## Per-frame prologue (frame 40)\n"] + table(pr) + ["""
 ## Reading
 
-* **Sweeps, dataflow form.** `k_solve_pos` %.0f -> %.0f us, `k_solve_vel` %.0f -> %.0f us against the capture of the first session (`profiles/r2/`), same frame, same work:
-  active lanes %.1f -> %.1f of 32 (`k_solve_pos`), barrier stalls 4.2 -> %.2f per issued instruction. The one grid barrier left per substep (after the prefix
-  pass) and the release fence before each counter update show up as %.2f barrier and ~0.6 membar-stall cycles per issue; the substep as a whole %.0f -> %.0f us under ncu.
+* **Sweeps, dataflow form (per-body chains).** `k_solve_pos` %.0f -> %.0f us, `k_solve_vel` %.0f -> %.0f us against the capture of the first session (`profiles/r2/`), same frame, same work:
+  active lanes %.1f -> %.1f of 32 (`k_solve_pos`), barrier stalls 4.2 -> %.2f per issued instruction (%.2f: no grid barrier is left); the release fences before the
+  chain updates show up as membar stalls instead (~1 cycle per issue); the substep as a whole %.0f -> %.0f us under ncu. `k_manifold` pays two atomics per unit for the live-level masks.
 * What is left is the narrowphase: `k_gjk` + `k_epa` + `k_manifold` = %.0f of %.0f us. By source line (`sass_lines.py` on this capture), `k_gjk` spends its samples
   in the support scans (the dot products and staged-vertex loads of `support_index`, 45 %%), `k_epa` in re-deriving geometry from the poses (`to_mat3`,
   `model_matrix`, `transform_point`: 20 %%) and in the dependent loads that start a hit (hit record -> collider -> pose -> simplex: 16 %%) with 8 warps per SM to
