@@ -42,11 +42,12 @@ def build(force=False, verbose=False, out=None, defines=()):
     cmd = [nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out or OUT] + SOURCES
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as f:
+    log_name = "build.log" if out is None else "build_%s.log" % os.path.splitext(os.path.basename(out))[0]  # (variants build side by side)
+    with open(os.path.join(HERE, log_name), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if r.returncode != 0:
         sys.stderr.write(log)
-        raise RuntimeError("nvcc failed (see raw-physics_b200/build.log)")
+        raise RuntimeError("nvcc failed (see raw-physics_b200/%s)" % log_name)
     if verbose:
         print(log)
     return out or OUT
@@ -75,6 +76,14 @@ def build_f32(force=False):
     return build(out=F32_OUT, defines=("RP_REAL_F32",))
 
 
+def build_all(force=False):
+    """the product library and its two build variants, compiled side by side (three nvcc processes)"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(3) as ex:
+        jobs = [ex.submit(build, force), ex.submit(build_exactq, force), ex.submit(build_f32, force)]
+        return [j.result() for j in jobs]
+
+
 HOST_SRC = os.path.join(HERE, "host", "rp_headless.cpp")
 HOST_OUT = os.path.join(HERE, "rp_headless")
 
@@ -94,7 +103,5 @@ def build_host(force=False):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    build_exactq(force="--force" in sys.argv)
-    build_f32(force="--force" in sys.argv)
+    build_all(force="--force" in sys.argv)
     build_host(force="--force" in sys.argv)
